@@ -1,0 +1,183 @@
+/* ov2b200.h - C ABI of the B200-native OV2SLAM hot paths (libov2b200.so).
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its
+ * callers (visual_front_end.cpp, map_manager.cpp, estimator.cpp) call three C++ classes
+ * directly.  The C++ shim classes in ov2slam_b200/host/ keep those class declarations
+ * unchanged and forward to the entry points below; every entry point names the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - Plain C types only.  All functions return an ov2_status (0 = OK); none throws or exits.
+ *   - There is no CPU fallback: without a CUDA device ov2_create() fails with
+ *     OV2_ERR_NO_DEVICE and every other call needs a context.
+ *   - Array arguments may point to HOST memory (pageable or pinned) or to DEVICE memory of the
+ *     context's device; the library detects which (cudaPointerGetAttributes).  Host inputs are
+ *     copied H2D on the context's stream, host outputs are copied D2H and the call returns after
+ *     they have landed.  With device pointers only, a call just enqueues work on the stream
+ *     (use ov2_sync()).
+ *   - A context is not re-entrant; use one per host thread (the reference calls
+ *     fbKltTracking concurrently from the front-end and mapper threads, map_manager.cpp:510).
+ *   - Batches are either "fixed stride" (frame_idx == NULL: element i belongs to frame slot
+ *     first_frame + i / per_frame) or "ragged" (frame_idx[i] gives the frame slot).
+ */
+#ifndef OV2B200_H
+#define OV2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define OV2_API __attribute__((visibility("default")))
+#else
+#define OV2_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    OV2_OK = 0,
+    OV2_ERR_NO_DEVICE = 1,   /* no CUDA device / driver: there is no CPU path */
+    OV2_ERR_CUDA = 2,        /* a CUDA call failed; see ov2_last_error() */
+    OV2_ERR_INVALID = 3,     /* bad argument */
+    OV2_ERR_CAPACITY = 4,    /* a fixed-capacity device buffer overflowed (reported, never silent) */
+    OV2_ERR_NOMEM = 5,
+    OV2_ERR_NUMERIC = 6      /* BA: non-finite cost / failed factorisation */
+} ov2_status;
+
+typedef struct ov2_ctx ov2_ctx;   /* device + stream + scratch arenas */
+typedef struct ov2_pyr ov2_pyr;   /* device-resident image pyramids for a batch of frames */
+
+/* ------------------------------------------------------------------ context */
+OV2_API ov2_status ov2_create(int device, ov2_ctx** out);
+OV2_API void       ov2_destroy(ov2_ctx* ctx);
+OV2_API const char* ov2_last_error(const ov2_ctx* ctx);      /* valid until the next call on ctx */
+OV2_API const char* ov2_version(void);
+/* Run the context's work on an existing stream (e.g. torch's current stream). NULL = own stream. */
+OV2_API ov2_status ov2_set_stream(ov2_ctx* ctx, void* cuda_stream);
+OV2_API ov2_status ov2_sync(ov2_ctx* ctx);
+/* Pinned host memory helpers (for callers that want true async H2D/D2H). */
+OV2_API ov2_status ov2_host_alloc(ov2_ctx* ctx, size_t bytes, void** out);
+OV2_API ov2_status ov2_host_free(ov2_ctx* ctx, void* p);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+OV2_API uint64_t   ov2_launch_count(const ov2_ctx* ctx);
+
+/* ------------------------------------------------------------------ P: pyramid
+ * Replaces cv::buildOpticalFlowPyramid(img, pyr, Size(9,9), 3) as called by
+ * VisualFrontEnd::preprocessImage (/root/reference/src/visual_front_end.cpp:1172, also :53 and
+ * src/mapper.cpp:81).  The Scharr derivative planes are not materialised; the tracker
+ * recomputes them on the fly from the 8-bit levels (identical values). */
+OV2_API ov2_status ov2_pyr_create(ov2_ctx* ctx, int batch, int width, int height, int nlevels_extra, ov2_pyr** out);
+OV2_API void       ov2_pyr_destroy(ov2_pyr* pyr);
+/* Load `count` 8-bit images into frame slots [first, first+count) and build their levels.
+ * `images` = host or device pointer; row r of image k starts at images + k*frame_stride + r*row_stride.
+ * Device images are used in place as level 0 (they must stay alive and unchanged while the
+ * pyramid is used); host images are copied into the pyramid's own level-0 storage. */
+OV2_API ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* pyr, const uint8_t* images, size_t row_stride,
+                         size_t frame_stride, int first, int count);
+/* Copy one level of one frame slot back to host (tests). `out` holds level_w*level_h bytes, packed. */
+OV2_API ov2_status ov2_pyr_download(ov2_ctx* ctx, const ov2_pyr* pyr, int frame, int level, uint8_t* out,
+                            int* level_w, int* level_h);
+
+/* ------------------------------------------------------------------ K: forward/backward KLT
+ * Replaces FeatureTracker::fbKltTracking(vprevpyr, vcurpyr, nwinsize, nbpyrlvl, ferr,
+ * fmax_fbklt_dist, vkps, vpriorkps, vkpstatus) (/root/reference/src/feature_tracker.cpp:35-137;
+ * declaration include/feature_tracker.hpp:44-47), i.e. forward cv::calcOpticalFlowPyrLK with
+ * USE_INITIAL_FLOW|LK_GET_MIN_EIGENVALS, the status/err/inBorder filter, the level-0 backward
+ * pass and the forward-backward distance test, fused per keypoint. */
+typedef struct {
+    int   win;        /* nwinsize (9) */
+    int   max_iter;   /* klt_convg_crit_.maxCount (30) */
+    float eps;        /* klt_convg_crit_.epsilon (0.01f) */
+    float ferr;       /* nklt_err (30) */
+    float fb_dist;    /* fmax_fbklt_dist (0.5) */
+} ov2_klt_params;
+
+/* n keypoints.  nbpyrlvl: per-keypoint pyramid depth (the reference's two calls, nbpyrlvl 1 for
+ * keypoints with a 3D prior and 3 for the rest, visual_front_end.cpp:196,242, become one launch),
+ * or NULL to use nbpyrlvl_all for every keypoint.  kps = vkps (n x 2 float), priors_inout =
+ * vpriorkps (in: initial guess, out: forward result), status_out = vkpstatus (n bytes, 0/1). */
+OV2_API ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_pyr* cur, const ov2_klt_params* prm,
+                      int n, const int32_t* frame_idx, int first_frame, int per_frame,
+                      const uint8_t* nbpyrlvl, int nbpyrlvl_all,
+                      const float* kps, float* priors_inout, uint8_t* status_out);
+
+/* ------------------------------------------------------------------ F + S: grid FAST + cornerSubPix
+ * Replaces FeatureExtractor::detectGridFAST(im, ncellsize, vcurkps, roi)
+ * (/root/reference/src/feature_extractor.cpp:443-570; include/feature_extractor.hpp:41-42) with
+ * the sequential ascending cell order as the defined semantics, including the CV_32F-mask byte
+ * aliasing, libstdc++ std::sort tie resolution, the response >= 20 rule, disc painting, the
+ * adaptive nfast_th_ update (:546-552) and cv::cornerSubPix((3,3),(-1,-1),{30,0.01}) (:556-565).
+ *
+ * Frames [first, first+count) of `pyr` (level 0).  Existing keypoints of frame k are
+ * curkps[2*curkp_offsets[k] .. 2*curkp_offsets[k+1]) (curkp_offsets has count+1 entries; NULL =
+ * no existing keypoints).  fast_th_inout[k] is the per-stream nfast_th_ state (in: threshold to
+ * use, out: adapted threshold).  out_pts holds count * max_per_frame points (x, y float; unused
+ * slots are set to (-1, -1)), in the reference's cell order; out_counts[k] = number found;
+ * max_per_frame >= (H/cellsize)*(W/cellsize).  out_pts_int (optional, may be NULL) receives the
+ * integer pixel positions before sub-pixel refinement (int32 x, y). */
+OV2_API ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int cellsize,
+                         const int32_t* curkp_offsets, const float* curkps,
+                         int32_t* fast_th_inout, int max_per_frame,
+                         float* out_pts, int32_t* out_counts, int32_t* out_pts_int, int do_subpix);
+
+/* Test hook: stage F1 alone (per-cell FAST-9/16 + NMS candidates of one frame, pre-filtered by the
+ * mask byte rule), for cell-by-cell parity against cv::FastFeatureDetector. */
+OV2_API ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int frame, int cellsize, int fast_th,
+                                uint32_t* cand_out, int32_t* cand_n_out, int cap_in, int* cap_out);
+
+/* ------------------------------------------------------------------ B: descriptors
+ * Replaces FeatureExtractor::describeBRIEF(im, vpts)
+ * (/root/reference/src/feature_extractor.cpp:224-285), non-contrib branch
+ * cv::ORB::create(500, 1., 0) (:245): 256 tests of the ORB pattern on the float32-Gaussian
+ * smoothed image, centre = cvRound(pt), points whose rounded centre is closer than 31 px to the
+ * border (and points with x < 0, used as "empty slot" markers) get valid = 0 and a zero
+ * descriptor, mirroring the empty cv::Mat the reference returns for them. */
+OV2_API ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, const int32_t* frame_idx, int first_frame, int per_frame,
+                        const float* pts, uint8_t* desc32_out, uint8_t* valid_out);
+
+/* ------------------------------------------------------------------ L: local bundle adjustment
+ * Replaces the solve sections of Optimizer::localBA(Frame&, bool)
+ * (/root/reference/src/optimizer.cpp:436-479 robust solve, :492-594 outlier scan,
+ *  :603-627 refinement, :637-735 second scan), i.e. Ceres 2.0 TrustRegionMinimizer +
+ * LevenbergMarquardtStrategy + SCHUR linear solver on ReprojectionErrorKSE3AnchInvDepth
+ * residuals (src/ceres_parametrization.cpp:361-473) with SE3LeftParameterization.
+ * The flat problem description is what localBA's setup (:43-430) builds from the map. */
+typedef struct {
+    int32_t  ncam, npts, nobs;
+    const double*  K;              /* [4] fx, fy, cx, cy (constant block) */
+    double*        pose;           /* [ncam][7] Twc = tx,ty,tz,qx,qy,qz,qw ; in/out */
+    const uint8_t* pose_const;     /* [ncam] 1 = SetParameterBlockConstant */
+    const int32_t* lm_anchor_cam;  /* [npts] */
+    const double*  lm_anchor_px;   /* [npts][2] undistorted anchor pixel */
+    double*        lm_invdepth;    /* [npts] in/out */
+    const int32_t* obs_cam;        /* [nobs] observing camera (non-anchor observations) */
+    const int32_t* obs_lm;         /* [nobs] landmark index, sorted ascending (CSR by landmark) */
+    const double*  obs_px;         /* [nobs][2] */
+} ov2_ba_problem;
+
+typedef struct {
+    int    max_iters_robust;   /* 5  (optimizer.cpp:462) */
+    int    max_iters_refine;   /* 10 (optimizer.cpp:610) */
+    double huber_th;           /* robust_mono_th = 5.9915 (loss = HuberLoss(sqrt(th)), :49) */
+    double function_tolerance; /* 1e-3 (:463) */
+    int    use_robust;         /* buse_robust_cost */
+    int    apply_l2_after_robust; /* (:603) */
+} ov2_ba_opts;
+
+typedef struct {
+    int    iters_robust, iters_refine;  /* LM iterations executed (successful + unsuccessful) */
+    double initial_cost, final_cost;    /* of the last solve that ran */
+    int    n_outliers_first, n_outliers_second;
+    int    termination;                 /* 0 convergence, 1 max iterations, 2 failure */
+} ov2_ba_result;
+
+/* outlier_out (optional): [nobs] bytes, bit0 = flagged after solve #1, bit1 = after solve #2. */
+OV2_API ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                             ov2_ba_result* res, uint8_t* outlier_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OV2B200_H */

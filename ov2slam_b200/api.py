@@ -1,0 +1,318 @@
+"""ctypes binding of libov2b200.so (include/ov2b200.h) + thin numpy/torch-friendly wrappers.
+
+This is the Python-side mirror of the reference's operator interface for the hot paths:
+
+    FeatureTracker.fb_klt_tracking   <- FeatureTracker::fbKltTracking   (feature_tracker.cpp:35-137)
+    FeatureExtractor.detect_grid_fast<- FeatureExtractor::detectGridFAST(feature_extractor.cpp:443-570)
+    FeatureExtractor.describe_brief  <- FeatureExtractor::describeBRIEF (feature_extractor.cpp:224-285)
+    Optimizer.local_ba               <- Optimizer::localBA solve part   (optimizer.cpp:436-735)
+
+Everything computes on the GPU through the C ABI.  There is NO CPU fallback: if the shared
+library is missing it is an ImportError-like failure (Ov2Error), if no CUDA device is present
+ov2_create() returns OV2_ERR_NO_DEVICE.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from pathlib import Path
+
+import numpy as np
+
+_LIBPATH = Path(__file__).resolve().parent / "lib" / "libov2b200.so"
+_lib = None
+
+OV2_OK = 0
+STATUS_NAMES = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "CAPACITY", 5: "NOMEM", 6: "NUMERIC"}
+
+ABI_SYMBOLS = [
+    "ov2_create", "ov2_destroy", "ov2_last_error", "ov2_version", "ov2_set_stream", "ov2_sync",
+    "ov2_host_alloc", "ov2_host_free", "ov2_launch_count",
+    "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_localba_solve",
+]
+
+
+class Ov2Error(RuntimeError):
+    pass
+
+
+class KltParams(C.Structure):
+    _fields_ = [("win", C.c_int), ("max_iter", C.c_int), ("eps", C.c_float), ("ferr", C.c_float),
+                ("fb_dist", C.c_float)]
+
+
+class BaProblem(C.Structure):
+    _fields_ = [("ncam", C.c_int32), ("npts", C.c_int32), ("nobs", C.c_int32),
+                ("K", C.c_void_p), ("pose", C.c_void_p), ("pose_const", C.c_void_p),
+                ("lm_anchor_cam", C.c_void_p), ("lm_anchor_px", C.c_void_p), ("lm_invdepth", C.c_void_p),
+                ("obs_cam", C.c_void_p), ("obs_lm", C.c_void_p), ("obs_px", C.c_void_p)]
+
+
+class BaOpts(C.Structure):
+    _fields_ = [("max_iters_robust", C.c_int), ("max_iters_refine", C.c_int), ("huber_th", C.c_double),
+                ("function_tolerance", C.c_double), ("use_robust", C.c_int), ("apply_l2_after_robust", C.c_int)]
+
+
+class BaResult(C.Structure):
+    _fields_ = [("iters_robust", C.c_int), ("iters_refine", C.c_int), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("n_outliers_first", C.c_int), ("n_outliers_second", C.c_int),
+                ("termination", C.c_int)]
+
+
+def lib_path() -> Path:
+    return _LIBPATH
+
+
+def load():
+    """Load the shared library (build it first with ov2slam_b200.build.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIBPATH.exists():
+        raise Ov2Error(f"{_LIBPATH} is missing: run `python -m ov2slam_b200.build` "
+                       "(there is no CPU fallback for the hot paths)")
+    lib = C.CDLL(str(_LIBPATH))
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.ov2_create.argtypes = [i32, C.POINTER(vp)]
+    lib.ov2_destroy.argtypes = [vp]
+    lib.ov2_destroy.restype = None
+    lib.ov2_last_error.argtypes = [vp]
+    lib.ov2_last_error.restype = C.c_char_p
+    lib.ov2_version.restype = C.c_char_p
+    lib.ov2_set_stream.argtypes = [vp, vp]
+    lib.ov2_sync.argtypes = [vp]
+    lib.ov2_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.ov2_host_free.argtypes = [vp, vp]
+    lib.ov2_launch_count.argtypes = [vp]
+    lib.ov2_launch_count.restype = C.c_uint64
+    lib.ov2_pyr_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
+    lib.ov2_pyr_destroy.argtypes = [vp]
+    lib.ov2_pyr_destroy.restype = None
+    lib.ov2_pyr_build.argtypes = [vp, vp, vp, sz, sz, i32, i32]
+    lib.ov2_pyr_download.argtypes = [vp, vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.ov2_fb_klt.argtypes = [vp, vp, vp, C.POINTER(KltParams), i32, vp, i32, i32, vp, i32, vp, vp, vp]
+    lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
+    lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
+    lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host), a torch tensor (host or CUDA), an int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise Ov2Error("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise Ov2Error("tensor must be contiguous")
+        return a.data_ptr()
+    raise Ov2Error(f"unsupported array type {type(a)}")
+
+
+class Context:
+    """ov2_ctx: one CUDA device + stream + scratch arena.  Not re-entrant."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.ov2_create(int(device), C.byref(h))
+        if st != OV2_OK:
+            raise Ov2Error(f"ov2_create(device={device}) failed: {STATUS_NAMES.get(st, st)} "
+                           "(the hot paths run on a CUDA device only; there is no CPU fallback)")
+        self.h = h
+        self.device = device
+        self._pyramids = []   # weak refs: pyramids must be destroyed before the context
+        if stream is not None:
+            self.check(self.lib.ov2_set_stream(self.h, C.c_void_p(stream)))
+
+    def check(self, st: int):
+        if st != OV2_OK:
+            msg = self.lib.ov2_last_error(self.h)
+            raise Ov2Error(f"{STATUS_NAMES.get(st, st)}: {msg.decode() if msg else ''}")
+
+    def sync(self):
+        self.check(self.lib.ov2_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.ov2_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            for r in self._pyramids:
+                p = r()
+                if p is not None:
+                    p.close()
+            self._pyramids = []
+            self.lib.ov2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pyramid:
+    """ov2_pyr: device-resident pyramids of a batch of frames (P)."""
+
+    def __init__(self, ctx: Context, batch: int, width: int, height: int, nlevels_extra: int = 3):
+        self.ctx = ctx
+        self.batch, self.w, self.h, self.nlev = batch, width, height, nlevels_extra + 1
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ov2_pyr_create(ctx.h, batch, width, height, nlevels_extra, C.byref(h)))
+        self.h_ = h
+        self._keepalive = None
+        ctx._pyramids.append(weakref.ref(self))
+
+    def build(self, images, first: int = 0, count: int | None = None, row_stride=None, frame_stride=None):
+        """images: (count, H, W) uint8 numpy array (host) or CUDA torch tensor (used in place)."""
+        if count is None:
+            count = images.shape[0] if images.ndim == 3 else 1
+        rs = int(row_stride if row_stride is not None else self.w)
+        fs = int(frame_stride if frame_stride is not None else rs * self.h)
+        self.ctx.check(self.ctx.lib.ov2_pyr_build(self.ctx.h, self.h_, _ptr(images), rs, fs, first, count))
+        if hasattr(images, "data_ptr"):
+            self._keepalive = images
+
+    def download(self, frame: int, level: int) -> np.ndarray:
+        lw, lh = self.w, self.h
+        for _ in range(level):
+            lw, lh = (lw + 1) // 2, (lh + 1) // 2
+        out = np.empty((lh, lw), np.uint8)
+        a, b = C.c_int(), C.c_int()
+        self.ctx.check(self.ctx.lib.ov2_pyr_download(self.ctx.h, self.h_, frame, level, out.ctypes.data,
+                                                     C.byref(a), C.byref(b)))
+        assert (a.value, b.value) == (lw, lh)
+        return out
+
+    def close(self):
+        if self.h_ and self.ctx.h:
+            self.ctx.lib.ov2_pyr_destroy(self.h_)
+        self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FeatureTracker:
+    """Mirror of the reference's FeatureTracker (include/feature_tracker.hpp:33-56)."""
+
+    def __init__(self, ctx: Context, nmax_iter: int = 30, fmax_px_precision: float = 0.01):
+        self.ctx = ctx
+        self.nmax_iter = nmax_iter
+        self.fmax_px_precision = float(np.float32(fmax_px_precision))
+
+    def fb_klt_tracking(self, prev: Pyramid, cur: Pyramid, nwinsize, nbpyrlvl, ferr, fmax_fbklt_dist,
+                        kps, priors_inout, status_out, n=None, frame_idx=None, first_frame=0, per_frame=None):
+        """fbKltTracking over a (ragged or fixed-stride) batch.  nbpyrlvl: int or per-keypoint uint8
+        array.  kps / priors_inout: (n, 2) float32; status_out: (n,) uint8.  Arrays may be numpy
+        (host) or CUDA tensors (device)."""
+        if n is None:
+            n = int(kps.shape[0])
+        prm = KltParams(int(nwinsize), int(self.nmax_iter), self.fmax_px_precision, float(ferr), float(fmax_fbklt_dist))
+        if isinstance(nbpyrlvl, (int, np.integer)):
+            lv_ptr, lv_all = None, int(nbpyrlvl)
+        else:
+            lv_ptr, lv_all = _ptr(nbpyrlvl), 0
+        if frame_idx is None and per_frame is None:
+            per_frame = max(n, 1)
+        self.ctx.check(self.ctx.lib.ov2_fb_klt(self.ctx.h, prev.h_, cur.h_, C.byref(prm), n, _ptr(frame_idx),
+                                               int(first_frame), int(per_frame or 0), lv_ptr, lv_all,
+                                               _ptr(kps), _ptr(priors_inout), _ptr(status_out)))
+
+
+class FeatureExtractor:
+    """Mirror of the reference's FeatureExtractor (include/feature_extractor.hpp:31-55) for the
+    hot-path methods detectGridFAST and describeBRIEF."""
+
+    def __init__(self, ctx: Context, nmaxpts: int = 0, nmaxdist: int = 50, dmaxquality: float = 0.0, nfast_th: int = 10):
+        self.ctx = ctx
+        self.nmaxpts_, self.nmaxdist_, self.dmaxquality_, self.nfast_th_ = nmaxpts, nmaxdist, dmaxquality, nfast_th
+
+    def detect_grid_fast(self, pyr: Pyramid, ncellsize: int, first: int, count: int, fast_th_inout,
+                         out_pts, out_counts, curkp_offsets=None, curkps=None, out_pts_int=None,
+                         max_per_frame=None, do_subpix=True):
+        if max_per_frame is None:
+            max_per_frame = (pyr.h // ncellsize) * (pyr.w // ncellsize)
+        self.ctx.check(self.ctx.lib.ov2_grid_fast(self.ctx.h, pyr.h_, first, count, ncellsize,
+                                                  _ptr(curkp_offsets), _ptr(curkps), _ptr(fast_th_inout),
+                                                  int(max_per_frame), _ptr(out_pts), _ptr(out_counts),
+                                                  _ptr(out_pts_int), 1 if do_subpix else 0))
+
+    def detect_grid_fast_frame(self, pyr: Pyramid, frame: int, ncellsize: int, vcurkps):
+        """Single-frame convenience with the reference's signature shape:
+        detectGridFAST(im, ncellsize, vcurkps, roi) -> points; carries nfast_th_ like the class does."""
+        ncell = (pyr.h // ncellsize) * (pyr.w // ncellsize)
+        cur = np.ascontiguousarray(vcurkps, np.float32).reshape(-1, 2)
+        off = np.array([0, len(cur)], np.int32)
+        th = np.array([self.nfast_th_], np.int32)
+        pts = np.empty((ncell, 2), np.float32)
+        ipts = np.empty((ncell, 2), np.int32)
+        cnt = np.zeros(1, np.int32)
+        self.detect_grid_fast(pyr, ncellsize, frame, 1, th, pts, cnt, off, cur if len(cur) else None, ipts)
+        self.nfast_th_ = int(th[0])
+        return pts[:cnt[0]].copy(), ipts[:cnt[0]].copy()
+
+    def debug_fast_cells(self, pyr: Pyramid, frame: int, ncellsize: int, fast_th: int):
+        """Stage F1 only: list per cell of (x, y, response) candidates (cell-local, scan order)."""
+        ncell = (pyr.h // ncellsize) * (pyr.w // ncellsize)
+        cand = np.zeros((ncell, 128), np.uint32)
+        cn = np.zeros(ncell, np.int32)
+        cap = C.c_int()
+        self.ctx.check(self.ctx.lib.ov2_debug_fast_cells(self.ctx.h, pyr.h_, frame, ncellsize, int(fast_th),
+                                                         cand.ctypes.data, cn.ctypes.data, 128, C.byref(cap)))
+        flat = cand.reshape(-1)[:ncell * cap.value].reshape(ncell, cap.value)
+        return [[(int(v & 255), int((v >> 8) & 255), float(v >> 16)) for v in flat[c, :cn[c]]] for c in range(ncell)]
+
+    def describe_brief(self, pyr: Pyramid, pts, desc_out, valid_out, n=None, frame_idx=None, first_frame=0,
+                       per_frame=None):
+        if n is None:
+            n = int(pts.shape[0])
+        if frame_idx is None and per_frame is None:
+            per_frame = max(n, 1)
+        self.ctx.check(self.ctx.lib.ov2_describe(self.ctx.h, pyr.h_, n, _ptr(frame_idx), int(first_frame),
+                                                 int(per_frame or 0), _ptr(pts), _ptr(desc_out), _ptr(valid_out)))
+
+
+DEFAULT_BA_OPTS = dict(max_iters_robust=5, max_iters_refine=10, huber_th=5.9915, function_tolerance=1e-3,
+                       use_robust=1, apply_l2_after_robust=1)
+
+
+class Optimizer:
+    """Mirror of the solve part of the reference's Optimizer::localBA (optimizer.cpp:436-735)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def local_ba(self, pb: dict, **opts):
+        """pb: dict of flat arrays as produced by synth.make_ba_problem (poses / inverse depths are
+        updated in place).  Returns (result dict, outlier flags uint8[nobs])."""
+        o = dict(DEFAULT_BA_OPTS)
+        o.update(opts)
+        bo = BaOpts(**o)
+        ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
+        keep = {k: np.ascontiguousarray(pb[k]) for k in
+                ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px")}
+        assert keep["pose"].dtype == np.float64 and keep["obs_px"].dtype == np.float64
+        assert keep["obs_cam"].dtype == np.int32 and keep["pose_const"].dtype == np.uint8
+        p = BaProblem(ncam, npts, nobs, *[keep[k].ctypes.data for k in
+                                          ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
+                                           "obs_cam", "obs_lm", "obs_px")])
+        res = BaResult()
+        flags = np.zeros(nobs, np.uint8)
+        self.ctx.check(self.ctx.lib.ov2_localba_solve(self.ctx.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data))
+        pb["pose"][...] = keep["pose"]
+        pb["lm_invdepth"][...] = keep["lm_invdepth"]
+        return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags

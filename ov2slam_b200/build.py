@@ -1,0 +1,74 @@
+"""Build libov2b200.so (hand-written sm_100a CUDA + the extern "C" ABI of include/ov2b200.h).
+
+Plain nvcc, in-tree output (ov2slam_b200/lib/), so the library travels to the GPU box with the
+repo snapshot.  nvcc cross-compiles without a GPU.  No torch in the link: the ABI is plain C.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIB = ROOT / "lib"
+SO = LIB / "libov2b200.so"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+# Per-file flags.  The image kernels reproduce OpenCV's float32 operation order, so FMA
+# contraction is off there (-fmad=false); the FMAs OpenCV itself issues are explicit __fmaf_rn.
+SOURCES = {
+    "ctx.cu": [],
+    "frontend_pyr.cu": ["-fmad=false"],
+    "frontend_klt.cu": ["-fmad=false"],
+    "frontend_fast.cu": ["-fmad=false"],
+    "frontend_desc.cu": ["-fmad=false"],
+    "ba_solver.cu": [],
+}
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _newer(a: Path, b: Path) -> bool:
+    return (not b.exists()) or a.stat().st_mtime > b.stat().st_mtime
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    LIB.mkdir(exist_ok=True)
+    objdir = LIB / "obj"
+    objdir.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((ROOT.parent / "include").glob("*.h"))
+    newest_hdr = max(h.stat().st_mtime for h in headers)
+    objs = []
+    relink = force
+    for name, extra in SOURCES.items():
+        src = CSRC / name
+        if not src.exists():
+            continue
+        obj = objdir / (name + ".o")
+        if force or _newer(src, obj) or obj.stat().st_mtime < newest_hdr:
+            cmd = [_nvcc(), *ARCH, *COMMON, *extra, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+            relink = True
+        objs.append(str(obj))
+    if relink or not SO.exists():
+        cmd = [_nvcc(), *ARCH, "-shared", "-o", str(SO), *objs, "-Xcompiler", "-fPIC", "-cudart", "shared"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,219 @@
+// Context, scratch arena, host<->device argument staging, pyramid storage.
+#include "ov2_common.cuh"
+
+#include <string.h>
+
+ov2_status ov2_fail(ov2_ctx* ctx, ov2_status st, const char* what, cudaError_t ce) {
+    if (ctx) {
+        ctx->err = what ? what : "";
+        if (ce != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(ce);
+        }
+    }
+    return st;
+}
+
+extern "C" const char* ov2_version(void) { return "ov2b200 0.1 (sm_100a)"; }
+
+extern "C" ov2_status ov2_create(int device, ov2_ctx** out) {
+    if (!out) return OV2_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return OV2_ERR_NO_DEVICE;  // no CPU path exists
+    if (device < 0 || device >= ndev) return OV2_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return OV2_ERR_CUDA;
+    ov2_ctx* c = new ov2_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return OV2_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return OV2_OK;
+}
+
+extern "C" void ov2_destroy(ov2_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ch : ctx->chunks) cudaFree(ch.p);
+    if (ctx->ba_ws) cudaFree(ctx->ba_ws);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* ov2_last_error(const ov2_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+extern "C" ov2_status ov2_set_stream(ov2_ctx* ctx, void* s) {
+    if (!ctx) return OV2_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    } else {
+        OV2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_sync(ov2_ctx* ctx) {
+    if (!ctx) return OV2_ERR_INVALID;
+    OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_host_alloc(ov2_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return OV2_ERR_INVALID;
+    OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    OV2_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_host_free(ov2_ctx* ctx, void* p) {
+    if (!ctx) return OV2_ERR_INVALID;
+    OV2_CUDA(ctx, cudaFreeHost(p));
+    return OV2_OK;
+}
+
+extern "C" uint64_t ov2_launch_count(const ov2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------ call scope
+ov2_status ov2_begin(ov2_ctx* ctx) {
+    if (!ctx) return OV2_ERR_INVALID;
+    OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->pending.clear();
+    if (ctx->chunks.size() > 1) {
+        // consolidate: previous call outgrew the arena
+        OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        size_t total = 0;
+        for (auto& ch : ctx->chunks) { total += ch.cap; cudaFree(ch.p); }
+        ctx->chunks.clear();
+        char* p = nullptr;
+        OV2_CUDA(ctx, cudaMalloc(&p, total));
+        ctx->chunks.push_back({p, total});
+    }
+    ctx->chunk_off = 0;
+    return OV2_OK;
+}
+
+ov2_status ov2_scratch(ov2_ctx* ctx, size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (ctx->chunks.empty() || ctx->chunk_off + bytes > ctx->chunks.back().cap) {
+        size_t cap = ctx->chunks.empty() ? (size_t)(4 << 20) : ctx->chunks.back().cap * 2;
+        if (cap < bytes) cap = bytes;
+        char* p = nullptr;
+        OV2_CUDA(ctx, cudaMalloc(&p, cap));
+        ctx->chunks.push_back({p, cap});
+        ctx->chunk_off = 0;
+    }
+    *out = ctx->chunks.back().p + ctx->chunk_off;
+    ctx->chunk_off += bytes;
+    return OV2_OK;
+}
+
+bool ov2_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+ov2_status ov2_stage_in(ov2_ctx* ctx, const void* p, size_t bytes, const void** dev) {
+    if (!p || bytes == 0) { *dev = nullptr; return OV2_OK; }
+    if (ov2_is_device_ptr(p)) { *dev = p; return OV2_OK; }
+    void* d = nullptr;
+    ov2_status st = ov2_scratch(ctx, bytes, &d);
+    if (st != OV2_OK) return st;
+    OV2_CUDA(ctx, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    return OV2_OK;
+}
+
+ov2_status ov2_stage_out(ov2_ctx* ctx, void* p, size_t bytes, void** dev, bool copy_in) {
+    if (!p || bytes == 0) { *dev = nullptr; return OV2_OK; }
+    if (ov2_is_device_ptr(p)) { *dev = p; return OV2_OK; }
+    void* d = nullptr;
+    ov2_status st = ov2_scratch(ctx, bytes, &d);
+    if (st != OV2_OK) return st;
+    if (copy_in) OV2_CUDA(ctx, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->pending.push_back({p, d, bytes});
+    *dev = d;
+    return OV2_OK;
+}
+
+ov2_status ov2_end(ov2_ctx* ctx) {
+    if (ctx->pending.empty()) return OV2_OK;
+    for (auto& pd : ctx->pending)
+        OV2_CUDA(ctx, cudaMemcpyAsync(pd.host, pd.dev, pd.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending.clear();
+    OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OV2_OK;
+}
+
+// ------------------------------------------------------------------------ pyramid storage
+extern "C" ov2_status ov2_pyr_create(ov2_ctx* ctx, int batch, int width, int height, int nlevels_extra,
+                                     ov2_pyr** out) {
+    if (!ctx || !out || batch <= 0 || width < 16 || height < 16 || nlevels_extra < 0 ||
+        nlevels_extra + 1 > OV2_MAX_LEVELS)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_create: bad arguments");
+    OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    ov2_pyr* p = new ov2_pyr();
+    p->ctx = ctx;
+    p->batch = batch;
+    p->nlev = nlevels_extra + 1;
+    int w = width, h = height;
+    for (int l = 0; l < p->nlev; ++l) {
+        p->w[l] = w;
+        p->h[l] = h;
+        p->pitch[l] = ((size_t)w + 127) & ~(size_t)127;
+        p->fstride[l] = p->pitch[l] * (size_t)h;
+        if (l > 0) {
+            cudaError_t e = cudaMalloc(&p->own[l], p->fstride[l] * (size_t)batch);
+            if (e != cudaSuccess) {
+                for (int k = 1; k < l; ++k) cudaFree(p->own[k]);
+                delete p;
+                return ov2_fail(ctx, OV2_ERR_NOMEM, "ov2_pyr_create: cudaMalloc", e);
+            }
+        }
+        w = (w + 1) / 2;
+        h = (h + 1) / 2;
+    }
+    *out = p;
+    return OV2_OK;
+}
+
+extern "C" void ov2_pyr_destroy(ov2_pyr* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (int l = 0; l < p->nlev; ++l)
+        if (p->own[l]) cudaFree(p->own[l]);
+    delete p;
+}
+
+extern "C" ov2_status ov2_pyr_download(ov2_ctx* ctx, const ov2_pyr* p, int frame, int level, uint8_t* out,
+                                       int* level_w, int* level_h) {
+    if (!ctx || !p || frame < 0 || frame >= p->batch || level < 0 || level >= p->nlev || !out)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_download: bad arguments");
+    OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint8_t* base = level == 0 ? p->l0 : p->own[level];
+    if (!base) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_download: pyramid not built");
+    size_t pitch = level == 0 ? p->l0_pitch : p->pitch[level];
+    size_t fs = level == 0 ? p->l0_fstride : p->fstride[level];
+    OV2_CUDA(ctx, cudaMemcpy2DAsync(out, p->w[level], base + fs * (size_t)frame, pitch, p->w[level],
+                                    p->h[level], cudaMemcpyDeviceToHost, ctx->stream));
+    OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (level_w) *level_w = p->w[level];
+    if (level_h) *level_h = p->h[level];
+    return OV2_OK;
+}

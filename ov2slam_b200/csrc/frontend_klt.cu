@@ -1,0 +1,291 @@
+// K: forward/backward pyramidal Lucas-Kanade, one warp per keypoint, everything fused.
+//
+// Reference behaviour replaced: FeatureTracker::fbKltTracking
+// (/root/reference/src/feature_tracker.cpp:35-137): forward cv::calcOpticalFlowPyrLK
+// (USE_INITIAL_FLOW | LK_GET_MIN_EIGENVALS, maxLevel = nbpyrlvl) -> status / err / inBorder
+// filter -> backward LK at level 0 -> forward-backward distance test.
+//
+// OpenCV's LK semantics (pinned by oracle/image_ref.py::_lk_ref against cv2):
+// 14-bit fixed-point bilinear weights, template / derivative patches as int16 (5 fractional bits
+// on intensities), normal equations from *integer* window sums scaled by 2^-20 in float32.
+// The window sums are reduced as integers across the warp (redux.sync, exact and order
+// independent) and converted to float32 once; all float32 steps keep OpenCV's operation order
+// (this file is compiled with -fmad=false so nothing is contracted into FMAs).
+//
+// Scharr derivatives are computed on the fly from a 12x12 8-bit neighbourhood (reflect-101 at
+// the image edge, constant 0 outside the image - exactly the planes buildOpticalFlowPyramid
+// would have materialised), so the tracker reads only the 8-bit pyramid.
+#include "ov2_common.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct KltArgs {
+    PyrView prev, cur;
+    int n;
+    const int32_t* frame_idx;
+    int first_frame, per_frame;
+    const uint8_t* lvls;
+    int lvl_all;
+    const float2* kps;
+    float2* priors;
+    uint8_t* status;
+    int max_iter;
+    float eps, ferr, fb_dist;
+};
+
+__device__ __forceinline__ int reflect101_safe(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+// exact 64-bit warp sum of per-lane int32 partials via two 32-bit redux ops
+__device__ __forceinline__ long long warp_sum64(int s) {
+    int lo = s & 0xFFFF;
+    int hi = s >> 16;
+    int slo = __reduce_add_sync(FULL, lo);
+    int shi = __reduce_add_sync(FULL, hi);
+    return ((long long)shi << 16) + (long long)slo;
+}
+
+// One calcOpticalFlowPyrLK track for one point (whole warp cooperates).
+// Ipyr = template pyramid, Jpyr = search pyramid.  nxt: in = initial guess, out = result.
+template <int WIN>
+__device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, float2 pt, float2& nxt, int maxlevel,
+                         int max_iter, double eps2, float& err_out, uint8_t* sP, int* sD, int lane) {
+    constexpr int NPX = WIN * WIN;
+    constexpr int PER_LANE = (NPX + 31) / 32;
+    constexpr int PW = WIN + 3;  // u8 neighbourhood (WIN+1 bilinear footprint + 1-px Scharr halo each side)
+    constexpr int DW = WIN + 1;  // derivative / search patch width
+    const float half = (WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    bool status = true;
+    float err = 0.f;
+
+    for (int level = maxlevel; level >= 0; --level) {
+        const int lw = Ipyr.w[level], lh = Ipyr.h[level];
+        const uint8_t* Iimg = Ipyr.lvl[level] + Ipyr.fstride[level] * frame;
+        const uint8_t* Jimg = Jpyr.lvl[level] + Jpyr.fstride[level] * frame;
+        const int Ipitch = Ipyr.pitch[level], Jpitch = Jpyr.pitch[level];
+        const float sc = 1.f / (float)(1 << level);
+        float2 prevPt = make_float2(pt.x * sc, pt.y * sc);
+        float2 nextPt;
+        if (level == maxlevel) nextPt = make_float2(nxt.x * sc, nxt.y * sc);
+        else nextPt = make_float2(nxt.x * 2.f, nxt.y * 2.f);
+        nxt = nextPt;
+        prevPt.x -= half;
+        prevPt.y -= half;
+        const int ix = __float2int_rd(prevPt.x), iy = __float2int_rd(prevPt.y);
+        if (ix < -WIN || ix >= lw || iy < -WIN || iy >= lh) {
+            if (level == 0) { status = false; err = 0.f; }
+            continue;
+        }
+        float a = prevPt.x - (float)ix, b = prevPt.y - (float)iy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+        int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+        int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+
+        // ---- 8-bit neighbourhood rows iy-1.., cols ix-1.. (reflect-101 = the padded level)
+        __syncwarp();
+        for (int i = lane; i < PW * PW; i += 32) {
+            int r = i / PW, c = i - r * PW;
+            int y = reflect101_safe(iy - 1 + r, lh), x = reflect101_safe(ix - 1 + c, lw);
+            sP[i] = __ldg(Iimg + (size_t)y * Ipitch + x);
+        }
+        __syncwarp();
+        // ---- Scharr at the DWxDW bilinear footprint; 0 outside the image (BORDER_CONSTANT)
+        for (int i = lane; i < DW * DW; i += 32) {
+            int r = i / DW, c = i - r * DW;
+            int y = iy + r, x = ix + c;
+            int dx = 0, dy = 0;
+            if (x >= 0 && x < lw && y >= 0 && y < lh) {
+                const uint8_t* p0 = sP + r * PW + c;  // row y-1, col x-1
+                const uint8_t* p1 = p0 + PW;
+                const uint8_t* p2 = p1 + PW;
+                int t0l = ((int)p0[0] + (int)p2[0]) * 3 + (int)p1[0] * 10;
+                int t0r = ((int)p0[2] + (int)p2[2]) * 3 + (int)p1[2] * 10;
+                dx = t0r - t0l;
+                int t1l = (int)p2[0] - (int)p0[0], t1c = (int)p2[1] - (int)p0[1], t1r = (int)p2[2] - (int)p0[2];
+                dy = (t1l + t1r) * 3 + t1c * 10;
+            }
+            sD[i] = (int)(((unsigned)dx & 0xFFFFu) | ((unsigned)dy << 16));
+        }
+        __syncwarp();
+        // ---- template patch (int16 semantics) + exact integer normal-equation sums
+        short Iv[PER_LANE], Ixv[PER_LANE], Iyv[PER_LANE];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+        for (int k = 0; k < PER_LANE; ++k) {
+            int p = lane + 32 * k;
+            Iv[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
+            if (p < NPX) {
+                int y = p / WIN, x = p - y * WIN;
+                const uint8_t* q = sP + (y + 1) * PW + (x + 1);
+                int ival = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[PW] * iw10 + (int)q[PW + 1] * iw11 + (1 << 8)) >> 9;
+                const int* d = sD + y * DW + x;
+                int d00 = d[0], d01 = d[1], d10 = d[DW], d11 = d[DW + 1];
+                int ixval = ((int)(short)(d00 & 0xFFFF) * iw00 + (int)(short)(d01 & 0xFFFF) * iw01 +
+                             (int)(short)(d10 & 0xFFFF) * iw10 + (int)(short)(d11 & 0xFFFF) * iw11 + (1 << 13)) >> 14;
+                int iyval = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
+                Iv[k] = (short)ival; Ixv[k] = (short)ixval; Iyv[k] = (short)iyval;
+                sA11 += ixval * ixval;
+                sA12 += ixval * iyval;
+                sA22 += iyval * iyval;
+            }
+        }
+        // |sums| <= 81 * 4080^2 = 1.35e9 < 2^31 for WIN = 9; use the 64-bit path to be safe for any WIN
+        float A11 = __ll2float_rn(warp_sum64(sA11)) * FLT_SCALE;
+        float A12 = __ll2float_rn(warp_sum64(sA12)) * FLT_SCALE;
+        float A22 = __ll2float_rn(warp_sum64(sA22)) * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - __fsqrt_rn((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+        err = minEig;
+        if ((double)minEig < 1e-4 || D < 1.1920928955078125e-07f) {
+            if (level == 0) status = false;
+            continue;
+        }
+        D = 1.f / D;
+        nextPt.x -= half;
+        nextPt.y -= half;
+        float2 prevDelta = make_float2(0.f, 0.f);
+        for (int j = 0; j < max_iter; ++j) {
+            const int jx = __float2int_rd(nextPt.x), jy = __float2int_rd(nextPt.y);
+            if (jx < -WIN || jx >= lw || jy < -WIN || jy >= lh) {
+                if (level == 0) status = false;
+                break;
+            }
+            a = nextPt.x - (float)jx;
+            b = nextPt.y - (float)jy;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+            iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+            iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            __syncwarp();
+            for (int i = lane; i < DW * DW; i += 32) {
+                int r = i / DW, c = i - r * DW;
+                int y = reflect101_safe(jy + r, lh), x = reflect101_safe(jx + c, lw);
+                sP[i] = __ldg(Jimg + (size_t)y * Jpitch + x);
+            }
+            __syncwarp();
+            int sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int k = 0; k < PER_LANE; ++k) {
+                int p = lane + 32 * k;
+                if (p < NPX) {
+                    int y = p / WIN, x = p - y * WIN;
+                    const uint8_t* q = sP + y * DW + x;
+                    int jval = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[DW] * iw10 + (int)q[DW + 1] * iw11 + (1 << 8)) >> 9;
+                    int diff = jval - (int)Iv[k];
+                    sb1 += diff * (int)Ixv[k];
+                    sb2 += diff * (int)Iyv[k];
+                }
+            }
+            float b1 = __ll2float_rn(warp_sum64(sb1)) * FLT_SCALE;
+            float b2 = __ll2float_rn(warp_sum64(sb2)) * FLT_SCALE;
+            float2 delta = make_float2((A12 * b2 - A22 * b1) * D, (A12 * b1 - A11 * b2) * D);
+            nextPt.x += delta.x;
+            nextPt.y += delta.y;
+            nxt = make_float2(nextPt.x + half, nextPt.y + half);
+            if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= eps2) break;
+            if (j > 0 && (double)fabsf(delta.x + prevDelta.x) < 0.01 && (double)fabsf(delta.y + prevDelta.y) < 0.01) {
+                nxt.x -= delta.x * 0.5f;
+                nxt.y -= delta.y * 0.5f;
+                break;
+            }
+            prevDelta = delta;
+        }
+    }
+    err_out = err;
+    return status;
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) fb_klt_kernel(KltArgs A) {
+    __shared__ __align__(16) uint8_t sPall[WARPS_PER_CTA][((WIN + 3) * (WIN + 3) + 15) & ~15];
+    __shared__ int sDall[WARPS_PER_CTA][(WIN + 1) * (WIN + 1)];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WARPS_PER_CTA + warp;
+    if (i >= A.n) return;
+    const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
+    int maxlevel = A.lvls ? (int)A.lvls[i] : A.lvl_all;
+    if (maxlevel > A.prev.nlev - 1) maxlevel = A.prev.nlev - 1;  // feature_tracker.cpp:50-52
+    if (maxlevel < 0) maxlevel = 0;
+    const float2 kp = A.kps[i];
+    float2 fwd = A.priors[i];
+    const double eps2 = (double)A.eps * (double)A.eps;
+    float err = 0.f;
+    bool ok = lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, eps2, err, sPall[warp], sDall[warp], lane);
+    // feature_tracker.cpp:79-101
+    if (ok && err > A.ferr) ok = false;
+    if (ok) {
+        const float w0 = (float)A.cur.w[0], h0 = (float)A.cur.h[0];
+        if (!(1.f <= fwd.x && fwd.x < w0 - 1.f && 1.f <= fwd.y && fwd.y < h0 - 1.f)) ok = false;
+    }
+    if (ok) {
+        // backward: template from the current image at the forward result, search the previous image
+        float2 back = kp;
+        float err2 = 0.f;
+        bool ok2 = lk_track<WIN>(A.cur, A.prev, frame, fwd, back, 0, A.max_iter, eps2, err2, sPall[warp], sDall[warp], lane);
+        if (!ok2) ok = false;
+        else {
+            float dx = kp.x - back.x, dy = kp.y - back.y;
+            double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            if (nrm > (double)A.fb_dist) ok = false;
+        }
+    }
+    if (lane == 0) {
+        A.priors[i] = fwd;
+        A.status[i] = ok ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_pyr* cur, const ov2_klt_params* prm,
+                                 int n, const int32_t* frame_idx, int first_frame, int per_frame, const uint8_t* nbpyrlvl,
+                                 int nbpyrlvl_all, const float* kps, float* priors_inout, uint8_t* status_out) {
+    if (!ctx || !prev || !cur || !prm || n < 0) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_fb_klt: bad arguments");
+    if (n == 0) return OV2_OK;  // feature_tracker.cpp:43-46
+    if (!kps || !priors_inout || !status_out || (!frame_idx && per_frame <= 0))
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_fb_klt: null array");
+    if (prm->win != 9) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_fb_klt: only nwinsize = 9 is built (all reference configs)");
+    if (prev->nlev != cur->nlev || prev->w[0] != cur->w[0] || prev->h[0] != cur->h[0] || !prev->l0 || !cur->l0)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_fb_klt: pyramids not built / mismatched");
+    if (!frame_idx && (first_frame < 0 || first_frame + (n + per_frame - 1) / per_frame > prev->batch))
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_fb_klt: more frames than pyramid slots");
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    KltArgs A;
+    A.prev = make_view(prev);
+    A.cur = make_view(cur);
+    A.n = n;
+    A.first_frame = first_frame;
+    A.per_frame = per_frame;
+    A.lvl_all = nbpyrlvl_all;
+    A.max_iter = prm->max_iter;
+    A.eps = prm->eps;
+    A.ferr = prm->ferr;
+    A.fb_dist = prm->fb_dist;
+    const void* d = nullptr;
+    void* o = nullptr;
+    if ((st = ov2_stage_in(ctx, frame_idx, sizeof(int32_t) * (size_t)n, &d)) != OV2_OK) return st;
+    A.frame_idx = (const int32_t*)d;
+    if ((st = ov2_stage_in(ctx, nbpyrlvl, (size_t)n, &d)) != OV2_OK) return st;
+    A.lvls = (const uint8_t*)d;
+    if ((st = ov2_stage_in(ctx, kps, sizeof(float) * 2 * (size_t)n, &d)) != OV2_OK) return st;
+    A.kps = (const float2*)d;
+    if ((st = ov2_stage_out(ctx, priors_inout, sizeof(float) * 2 * (size_t)n, &o, true)) != OV2_OK) return st;
+    A.priors = (float2*)o;
+    if ((st = ov2_stage_out(ctx, status_out, (size_t)n, &o)) != OV2_OK) return st;
+    A.status = (uint8_t*)o;
+    fb_klt_kernel<9><<<div_up(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, ctx->stream>>>(A);
+    OV2_CHECK_LAUNCH(ctx, "fb_klt_kernel");
+    return ov2_end(ctx);
+}

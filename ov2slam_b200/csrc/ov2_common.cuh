@@ -1,0 +1,100 @@
+// Shared host/device plumbing for libov2b200 (context, scratch arenas, argument staging).
+// Product code: nothing here may include or call anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ov2b200.h"
+
+#define OV2_MAX_LEVELS 8
+
+struct ov2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // device scratch: bump allocator, reset at the start of every API call
+    struct Chunk { char* p; size_t cap; };
+    std::vector<Chunk> chunks;
+    size_t chunk_off = 0;
+    // pending device->host copies of the current call
+    struct Pending { void* host; const void* dev; size_t bytes; };
+    std::vector<Pending> pending;
+    // persistent small device blocks (tables)
+    void* ba_ws = nullptr; size_t ba_ws_cap = 0;
+};
+
+struct ov2_pyr {
+    ov2_ctx* ctx = nullptr;
+    int batch = 0, nlev = 0;
+    int w[OV2_MAX_LEVELS] = {0}, h[OV2_MAX_LEVELS] = {0};
+    size_t pitch[OV2_MAX_LEVELS] = {0}, fstride[OV2_MAX_LEVELS] = {0};
+    uint8_t* own[OV2_MAX_LEVELS] = {nullptr};   // own[0] allocated lazily (host-image path only)
+    const uint8_t* l0 = nullptr;                 // level-0 base (own[0] or caller's device images)
+    size_t l0_pitch = 0, l0_fstride = 0;
+    int l0_mode = 0;                             // 0 unset, 1 own, 2 external
+};
+
+// What kernels see of a pyramid.
+struct PyrView {
+    const uint8_t* lvl[4];
+    int w[4], h[4];
+    int pitch[4];
+    long long fstride[4];
+    int nlev;
+};
+
+static inline PyrView make_view(const ov2_pyr* p) {
+    PyrView v;
+    for (int l = 0; l < 4; ++l) {
+        int ll = l < p->nlev ? l : p->nlev - 1;
+        v.lvl[l] = ll == 0 ? p->l0 : p->own[ll];
+        v.w[l] = p->w[ll];
+        v.h[l] = p->h[ll];
+        v.pitch[l] = (int)(ll == 0 ? p->l0_pitch : p->pitch[ll]);
+        v.fstride[l] = (long long)(ll == 0 ? p->l0_fstride : p->fstride[ll]);
+    }
+    v.nlev = p->nlev < 4 ? p->nlev : 4;
+    return v;
+}
+
+ov2_status ov2_fail(ov2_ctx* ctx, ov2_status st, const char* what, cudaError_t ce = cudaSuccess);
+
+#define OV2_CUDA(ctx, call)                                                         \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) return ov2_fail((ctx), OV2_ERR_CUDA, #call, _e);     \
+    } while (0)
+
+#define OV2_CHECK_LAUNCH(ctx, name)                                                 \
+    do {                                                                            \
+        (ctx)->launches++;                                                          \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) return ov2_fail((ctx), OV2_ERR_CUDA, name, _e);      \
+    } while (0)
+
+// --- call scope: scratch + staging ------------------------------------------------------
+ov2_status ov2_begin(ov2_ctx* ctx);                               // reset scratch, bind device
+ov2_status ov2_scratch(ov2_ctx* ctx, size_t bytes, void** out);   // 256-byte aligned device scratch
+bool       ov2_is_device_ptr(const void* p);
+// input: returns a device pointer holding `bytes` of *p (p itself if already on the device)
+ov2_status ov2_stage_in(ov2_ctx* ctx, const void* p, size_t bytes, const void** dev);
+// output: returns a device pointer to write; host destinations are copied back by ov2_end()
+ov2_status ov2_stage_out(ov2_ctx* ctx, void* p, size_t bytes, void** dev, bool copy_in = false);
+ov2_status ov2_end(ov2_ctx* ctx);                                 // D2H of pending outputs + sync if any
+
+// --- device helpers ------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // BORDER_REFLECT_101: ... 2 1 | 0 1 2 ... n-2 n-1 | n-2 n-3 ...   (|overshoot| < n assumed)
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+__device__ __forceinline__ int clampi(int i, int lo, int hi) { return i < lo ? lo : (i > hi ? hi : i); }
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }

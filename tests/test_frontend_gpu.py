@@ -1,0 +1,250 @@
+"""GPU parity tests of the front-end image path: CUDA (through the C ABI) vs the oracle.
+
+Bars: bit-exact for pyramid levels, FAST keypoint positions / thresholds and descriptor
+bitstrings; stated float tolerances for cornerSubPix and KLT (see each test).
+The oracle here is oracle/image_ref.py (numpy restatement, itself pinned against cv2 4.13 by
+tests/test_oracle_image.py) and, when cv2 is importable on the box, cv2 itself.
+"""
+import numpy as np
+import pytest
+
+from ov2slam_b200 import api, synth
+from oracle import image_ref as R
+
+pytestmark = pytest.mark.gpu
+
+SUBPIX_TOL = 2e-4   # px; cv2-vs-restatement itself differs by up to 3e-5 (double summation order)
+KLT_TOL = 1e-3      # px; see test_klt_parity
+
+
+def _oracle_detect(im, cs, kps, th):
+    return R.detect_grid_fast_nosubpix(im, cs, kps, th, use_cv2=R.HAVE_CV2)
+
+
+def _subpix(im, pts):
+    return R.corner_subpix_cv2(im, pts) if R.HAVE_CV2 else R.corner_subpix_ref(im, pts)
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (752, 480), (333, 245)])
+def test_pyramid_bit_exact(ctx, w, h):
+    imgs = np.stack([synth.make_frame(10 + i, w, h) for i in range(3)])
+    pyr = api.Pyramid(ctx, 3, w, h, 3)
+    pyr.build(imgs)
+    for f in range(3):
+        ref = R.build_pyramid_ref(imgs[f], 3)
+        for lvl in range(4):
+            got = pyr.download(f, lvl)
+            assert got.shape == ref[lvl].shape
+            assert np.array_equal(got, ref[lvl]), (f, lvl)
+    pyr.close()
+
+
+def test_pyramid_device_images_in_place(ctx):
+    torch = pytest.importorskip("torch")
+    w, h = 640, 480
+    imgs = np.stack([synth.make_frame(20 + i, w, h) for i in range(2)])
+    d = torch.from_numpy(imgs).cuda()
+    pyr = api.Pyramid(ctx, 2, w, h, 3)
+    pyr.build(d)
+    ctx.sync()
+    for f in range(2):
+        ref = R.build_pyramid_ref(imgs[f], 3)
+        for lvl in range(4):
+            assert np.array_equal(pyr.download(f, lvl), ref[lvl])
+    pyr.close()
+
+
+@pytest.mark.parametrize("cs", [50, 35, 16])
+@pytest.mark.parametrize("with_kps", [False, True])
+def test_grid_fast_bit_exact(ctx, cs, with_kps):
+    w, h = 640, 480
+    nfr = 4
+    imgs = np.stack([synth.make_frame(30 + i, w, h) for i in range(nfr)])
+    pyr = api.Pyramid(ctx, nfr, w, h, 0)
+    pyr.build(imgs)
+    fe = api.FeatureExtractor(ctx)
+    ncell = (h // cs) * (w // cs)
+    rng = np.random.default_rng(cs)
+    kps_list = []
+    for f in range(nfr):
+        n = int(rng.integers(5, 60)) if with_kps else 0
+        k = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+        if n:
+            k[0] = [0.4, 0.4]          # disc clipped at the corner
+            k[1] = [w - 1.0, h - 1.0]
+            k[2] = [100.5, 200.5]      # round-half-even centre
+        kps_list.append(k)
+    off = np.concatenate([[0], np.cumsum([len(k) for k in kps_list])]).astype(np.int32)
+    allk = np.concatenate(kps_list).astype(np.float32) if off[-1] else None
+    ths = np.array([10, 10, 6, 20], np.int32)
+    th_in = ths.copy()
+    pts = np.empty((nfr, ncell, 2), np.float32)
+    ipts = np.empty((nfr, ncell, 2), np.int32)
+    cnt = np.zeros(nfr, np.int32)
+    fe.detect_grid_fast(pyr, cs, 0, nfr, ths, pts, cnt, off if with_kps else None, allk, ipts)
+    for f in range(nfr):
+        ref_i, ref_th, _ = _oracle_detect(imgs[f], cs, kps_list[f], int(th_in[f]))
+        assert cnt[f] == len(ref_i), (f, cnt[f], len(ref_i))
+        assert np.array_equal(ipts[f, :cnt[f]], ref_i), f
+        assert ths[f] == ref_th, (f, ths[f], ref_th)
+        assert (pts[f, cnt[f]:] == -1).all()
+        ref_s = _subpix(imgs[f], ref_i.astype(np.float32))
+        d = np.abs(pts[f, :cnt[f]] - ref_s)
+        assert d.max() <= SUBPIX_TOL, (f, d.max())
+    pyr.close()
+
+
+def test_grid_fast_threshold_state_sequence(ctx):
+    """nfast_th_ adapts across calls (feature_extractor.cpp:546-552): 10 -> 6 -> 3 -> 1 -> 0 on a
+    textureless image, and the class-like wrapper carries the state."""
+    w, h = 640, 480
+    flat = np.full((1, h, w), 128, np.uint8)
+    pyr = api.Pyramid(ctx, 1, w, h, 0)
+    pyr.build(flat)
+    fe = api.FeatureExtractor(ctx, nfast_th=10)
+    seen = []
+    for _ in range(5):
+        p, _ = fe.detect_grid_fast_frame(pyr, 0, 50, np.zeros((0, 2), np.float32))
+        assert len(p) == 0
+        seen.append(fe.nfast_th_)
+    assert seen == [6, 3, 1, 0, 0]
+    pyr.close()
+
+
+def test_subpix_border_points(ctx):
+    """cornerSubPix at the image border goes through getRectSubPix's replicated-border path."""
+    w, h = 640, 480
+    im = synth.make_frame(41, w, h)
+    # use detect with a tiny artificial cell grid?  No: call S through grid_fast on a frame whose
+    # detections are near the border is not controllable, so compare on synthetic detections by
+    # building an image whose strongest corners sit at the border cells.
+    pyr = api.Pyramid(ctx, 1, w, h, 0)
+    pyr.build(im[None])
+    fe = api.FeatureExtractor(ctx, nfast_th=10)
+    pts, ipts = fe.detect_grid_fast_frame(pyr, 0, 16, np.zeros((0, 2), np.float32))
+    near = (ipts[:, 0] <= 5) | (ipts[:, 1] <= 5)
+    assert near.sum() > 0
+    ref = _subpix(im, ipts.astype(np.float32))
+    assert np.abs(pts - ref).max() <= SUBPIX_TOL
+    pyr.close()
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (752, 480)])
+def test_describe_bit_exact(ctx, w, h):
+    nfr = 3
+    imgs = np.stack([synth.make_frame(50 + i, w, h) for i in range(nfr)])
+    imgs[2] = np.random.default_rng(5).integers(0, 256, (h, w)).astype(np.uint8)  # raw noise
+    pyr = api.Pyramid(ctx, nfr, w, h, 0)
+    pyr.build(imgs)
+    fe = api.FeatureExtractor(ctx)
+    rng = np.random.default_rng(1)
+    n_per = 400
+    pts = (rng.random((nfr, n_per, 2)) * [w, h]).astype(np.float32)
+    pts[:, :50] = np.rint(pts[:, :50])
+    pts[:, 50:80] = np.floor(pts[:, 50:80]) + 0.5          # round-half-even centres
+    pts[:, 80:100, 0] = rng.uniform(29.5, 32.5, (nfr, 20))  # border rule on the rounded point
+    pts[:, 100:120, 0] = rng.uniform(w - 32.5, w - 29.5, (nfr, 20))
+    pts[:, 120:140, 1] = rng.uniform(29.5, 32.5, (nfr, 20))
+    pts[:, 140:160, 1] = rng.uniform(h - 32.5, h - 29.5, (nfr, 20))
+    pts[:, 160] = [-1, -1]                                  # empty-slot marker
+    desc = np.empty((nfr, n_per, 32), np.uint8)
+    valid = np.empty((nfr, n_per), np.uint8)
+    fe.describe_brief(pyr, pts.reshape(-1, 2), desc.reshape(-1, 32), valid.reshape(-1), per_frame=n_per)
+    for f in range(nfr):
+        q = pts[f].copy()
+        q[160] = [0, 0]
+        rd, rv = (R.describe_cv2 if R.HAVE_CV2 else R.describe_ref)(imgs[f], q)
+        assert np.array_equal(valid[f], rv), f
+        assert np.array_equal(desc[f], rd), (f, int(np.unpackbits(desc[f] ^ rd).sum()))
+    # ragged addressing gives the same answer
+    fidx = np.repeat(np.arange(nfr, dtype=np.int32), n_per)
+    desc2 = np.empty_like(desc)
+    valid2 = np.empty_like(valid)
+    fe.describe_brief(pyr, pts.reshape(-1, 2), desc2.reshape(-1, 32), valid2.reshape(-1), frame_idx=fidx)
+    assert np.array_equal(desc, desc2) and np.array_equal(valid, valid2)
+    pyr.close()
+
+
+def _klt_inputs(seed, w, h, n_border=60):
+    prev, cur, flow = synth.make_pair(seed, w, h)
+    ipts, _, _ = R.detect_grid_fast_nosubpix(prev, 16, np.zeros((0, 2)), 10, use_cv2=False)
+    kps = ipts.astype(np.float32) + np.random.default_rng(seed).uniform(-0.5, 0.5, ipts.shape).astype(np.float32)
+    rng = np.random.default_rng(seed + 1)
+    b = (rng.random((n_border, 2)) * [w, h]).astype(np.float32)
+    q = n_border // 4
+    b[:q, 0] = rng.uniform(0, 7, q)
+    b[q:2 * q, 0] = rng.uniform(w - 8, w, q)
+    b[2 * q:3 * q, 1] = rng.uniform(0, 7, q)
+    b[3 * q:, 1] = rng.uniform(h - 8, h, n_border - 3 * q)
+    kps = np.concatenate([kps[:340], b]).astype(np.float32)
+    is3d, pri = synth.make_priors(seed, kps, flow)
+    return prev, cur, flow, kps, is3d, pri
+
+
+@pytest.mark.parametrize("nbpyrlvl", [0, 1, 3])
+def test_klt_parity(ctx, nbpyrlvl):
+    """fbKltTracking vs the oracle.  Tolerance: status flags identical and tracked positions within
+    1e-3 px, except keypoints the oracle itself marks borderline - none are expected: the integer
+    window sums make the arithmetic reproducible, so in practice positions are bit-equal."""
+    w, h = 640, 480
+    prev, cur, flow, kps, is3d, pri = _klt_inputs(7, w, h)
+    pp = api.Pyramid(ctx, 1, w, h, 3)
+    cp = api.Pyramid(ctx, 1, w, h, 3)
+    pp.build(prev[None])
+    cp.build(cur[None])
+    ft = api.FeatureTracker(ctx, 30, 0.01)
+    out = pri.copy()
+    st = np.zeros(len(kps), np.uint8)
+    ft.fb_klt_tracking(pp, cp, 9, nbpyrlvl, 30.0, 0.5, kps, out, st)
+    ref_fn = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
+    rp, rs = ref_fn(prev, cur, kps, pri, 9, nbpyrlvl)
+    assert np.array_equal(st, rs), np.nonzero(st != rs)[0]
+    d = np.abs(out - rp).max(axis=1)
+    assert d.max() <= KLT_TOL, (d.max(), np.argmax(d))
+    assert (d == 0).mean() > 0.98
+    assert st.mean() > 0.5
+    pp.close()
+    cp.close()
+
+
+def test_klt_mixed_levels_batched(ctx):
+    """The reference's two calls (nbpyrlvl 1 for 3D-prior keypoints, 3 for the rest,
+    visual_front_end.cpp:196,242) fused in one ragged launch over several frames."""
+    w, h = 640, 480
+    nfr = 3
+    data = [_klt_inputs(60 + f, w, h, 20) for f in range(nfr)]
+    prevs = np.stack([d[0] for d in data])
+    curs = np.stack([d[1] for d in data])
+    pp = api.Pyramid(ctx, nfr, w, h, 3)
+    cp = api.Pyramid(ctx, nfr, w, h, 3)
+    pp.build(prevs)
+    cp.build(curs)
+    kps = np.concatenate([d[3] for d in data])
+    pri = np.concatenate([d[5] for d in data])
+    lv = np.concatenate([np.where(d[4], 1, 3) for d in data]).astype(np.uint8)
+    fidx = np.concatenate([np.full(len(d[3]), f, np.int32) for f, d in enumerate(data)])
+    out = pri.copy()
+    st = np.zeros(len(kps), np.uint8)
+    api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, lv, 30.0, 0.5, kps, out, st, frame_idx=fidx)
+    ref_fn = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
+    o = 0
+    for f, d in enumerate(data):
+        n = len(d[3])
+        for lvl in (1, 3):
+            sel = np.nonzero(lv[o:o + n] == lvl)[0]
+            rp, rs = ref_fn(d[0], d[1], d[3][sel], d[5][sel], 9, lvl)
+            assert np.array_equal(st[o:o + n][sel], rs)
+            assert np.abs(out[o:o + n][sel] - rp).max() <= KLT_TOL
+        o += n
+    pp.close()
+    cp.close()
+
+
+def test_empty_inputs(ctx):
+    w, h = 640, 480
+    pyr = api.Pyramid(ctx, 1, w, h, 3)
+    pyr.build(synth.make_frame(1, w, h)[None])
+    z = np.zeros((0, 2), np.float32)
+    api.FeatureTracker(ctx).fb_klt_tracking(pyr, pyr, 9, 3, 30.0, 0.5, z, z.copy(), np.zeros(0, np.uint8), n=0, per_frame=1)
+    api.FeatureExtractor(ctx).describe_brief(pyr, z, np.zeros((0, 32), np.uint8), np.zeros(0, np.uint8), n=0, per_frame=1)
+    pyr.close()
