@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py - front-end frames/s (+ local-BA solves/s) on N B200s vs the CPU reference path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" is one pass of the front-end hot path over one batch of B synthetic
+(prev, cur) 640x480 frame pairs per GPU (BASELINE.json configs[1]):
+
+    P  pyramids of prev and cur            (visual_front_end.cpp:1172)
+    K  forward/backward KLT, 1024 kps/frame (feature_tracker.cpp:35-137; 60 % with a motion prior
+       at nbpyrlvl 1, the rest at nbpyrlvl 3, as visual_front_end.cpp:196,242)
+    F  detectGridFAST + cornerSubPix on cur (feature_extractor.cpp:443-570), parameters_files/fast:
+       cell 50, nfast_th 10, no existing keypoints (full-grid detection)
+    B  describeBRIEF of the tracked and of the new keypoints (feature_extractor.cpp:224-285)
+
+  value  = frames/s with all inputs already resident in HBM (device pointers through the C ABI)
+  e2e    = frames/s through the same C ABI calls with HOST (pinned) buffers: H2D of the images and
+           keypoints and D2H of every result inside the timed region
+  --impl reference : the reference's own CPU path (OpenCV call sequence, oracle/image_ref.py) on
+           the box's host cores.
+
+No part of the GPU arm touches oracle/; only the cpu_baseline leg and --impl reference do.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W_IMG, H_IMG = 640, 480
+NKP = 1024
+CELL = 50
+FAST_TH = 10
+FRAC3D = 0.6
+
+
+# ----------------------------------------------------------------------------- helpers
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+                out["sm_mhz"] = float(np.median(busy))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[5 + k].strip().lower().startswith("active") for r in rows if len(r) >= 9):
+                        out["reasons"].append(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One worker: run the reference's OpenCV call sequence on a share of the frame pairs."""
+    seeds, nkp = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import image_ref as R
+    from ov2slam_b200 import synth
+    data = []
+    for s in seeds:
+        prev, cur, flow = synth.make_pair(s, W_IMG, H_IMG)
+        rng = np.random.default_rng(s + 5)
+        kps = np.stack([rng.uniform(12, W_IMG - 12, nkp), rng.uniform(12, H_IMG - 12, nkp)], axis=1).astype(np.float32)
+        is3d, pri = synth.make_priors(s, kps, flow, FRAC3D)
+        data.append((prev, cur, kps, pri, is3d))
+    if data:  # untimed warm-up of this process (cv2 paging, detector creation)
+        _cpu_frame(R, cv2, *data[0])
+    t0 = time.perf_counter()
+    ntracked = 0
+    for prev, cur, kps, pri, is3d in data:
+        r = _cpu_frame(R, cv2, prev, cur, kps, pri, is3d)
+        ntracked += int(r)
+    return time.perf_counter() - t0, len(data), ntracked
+
+
+def _cpu_frame(R, cv2, prev, cur, kps, pri, is3d):
+    """Same work as one GPU-arm frame: P(prev), P(cur), K (two calls), F + S (empty vcurkps), B."""
+    cv2.buildOpticalFlowPyramid(prev, (9, 9), 3)
+    cv2.buildOpticalFlowPyramid(cur, (9, 9), 3)
+    tracked = pri.copy()
+    status = np.zeros(len(kps), np.uint8)
+    i3 = np.nonzero(is3d)[0]
+    i2 = np.nonzero(~is3d)[0]
+    if len(i3):
+        tracked[i3], status[i3] = R.fb_klt_cv2(prev, cur, kps[i3], tracked[i3], 9, 1)
+    if len(i2):
+        tracked[i2], status[i2] = R.fb_klt_cv2(prev, cur, kps[i2], tracked[i2], 9, 3)
+    newpts, _, _ = R.detect_grid_fast_cv2(cur, CELL, np.zeros((0, 2), np.float32), FAST_TH)
+    R.describe_cv2(cur, tracked)
+    R.describe_cv2(cur, newpts)
+    return status.sum()
+
+
+def run_cpu_reference(nframes: int, nproc: int, first_seed: int = 1000):
+    """frames/s of the OpenCV reference sequence over `nframes` pairs with `nproc` processes.
+    Input generation is outside the timed region (each worker times only its processing loop);
+    throughput = frames / max worker time (workers run concurrently)."""
+    import multiprocessing as mp
+    nproc = max(1, min(nproc, nframes))
+    seeds = [first_seed + i for i in range(nframes)]
+    shares = [seeds[i::nproc] for i in range(nproc)]
+    if nproc == 1:
+        res = [_cpu_worker((shares[0], NKP))]
+    else:
+        ctxmp = mp.get_context("fork")
+        with ctxmp.Pool(nproc) as pool:
+            res = pool.map(_cpu_worker, [(s, NKP) for s in shares])
+    tmax = max(r[0] for r in res)
+    n = sum(r[1] for r in res)
+    return n / tmax, tmax, n
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    nframes = int(min(max(6 * cores, 64), 1536))
+    # warm-up steps (page in cv2, fork pool once) then K timed steps, each a bounded sample
+    for _ in range(max(1, min(args.warmup, 1))):
+        run_cpu_reference(min(nframes, cores), cores)
+    vals = []
+    t_total = 0.0
+    for _ in range(args.steps):
+        fps, t, n = run_cpu_reference(nframes, cores)
+        vals.append(fps)
+        t_total += t
+    fps = float(np.mean(vals))
+    try:
+        import cv2
+        ver = cv2.__version__
+    except Exception:
+        ver = "?"
+    line = {
+        "impl": "reference", "metric": "front-end frames/sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+        "config": _config(nframes, "reference CPU arm: one step = %d frame pairs" % nframes),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{nframes} frame pairs/step, OpenCV {ver} call sequence of feature_tracker.cpp/"
+                                   f"feature_extractor.cpp via cv2 (oracle/image_ref.py), {cores} processes x 1 cv2 thread"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def _config(batch, note=""):
+    return {"workload": "C2: FAST+descriptor+fb-KLT front-end, batch of %d synthetic 640x480 frame pairs per GPU" % batch,
+            "width": W_IMG, "height": H_IMG, "keypoints_per_frame": NKP, "klt": "win 9, nbpyrlvl 1 (60% prior) / 3, 30 it, eps 0.01, fb 0.5",
+            "fast": "cell %d, th %d, full grid (no existing kps), cornerSubPix" % (CELL, FAST_TH),
+            "descriptor": "ORB-fallback 256-bit (reference's non-contrib branch), tracked + new keypoints",
+            "l2": "inputs (2 x batch x 307 KB = 157 MB at batch 256) exceed the 126 MB L2", "note": note}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class Workload:
+    def __init__(self, torch, api, ctx, rank: int, batch: int):
+        from ov2slam_b200 import synth
+        self.torch, self.api, self.ctx, self.B = torch, api, ctx, batch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        base = 1000 + rank * 100003
+        prevs = np.empty((batch, H_IMG, W_IMG), np.uint8)
+        curs = np.empty_like(prevs)
+        kps = np.empty((batch, NKP, 2), np.float32)
+        pri = np.empty_like(kps)
+        lv = np.empty((batch, NKP), np.uint8)
+        for i in range(batch):
+            prevs[i], curs[i], flow = synth.make_pair(base + i, W_IMG, H_IMG)
+            rng = np.random.default_rng(base + i + 5)
+            kps[i] = np.stack([rng.uniform(12, W_IMG - 12, NKP), rng.uniform(12, H_IMG - 12, NKP)], axis=1)
+            is3d, pri[i] = synth.make_priors(base + i, kps[i], flow, FRAC3D)
+            lv[i] = np.where(is3d, 1, 3)
+        self.ncell = (H_IMG // CELL) * (W_IMG // CELL)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        # host (pinned) copies: the e2e arm reads inputs from and writes results to these
+        self.h_prev, self.h_cur = pin(prevs), pin(curs)
+        self.h_kps, self.h_pri0, self.h_lv = pin(kps.reshape(-1, 2)), pin(pri.reshape(-1, 2)), pin(lv.reshape(-1))
+        n = batch * NKP
+        self.h_pri = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        self.h_status = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self.h_th = torch.empty(batch, dtype=torch.int32).pin_memory()
+        self.h_new = torch.empty((batch * self.ncell, 2), dtype=torch.float32).pin_memory()
+        self.h_cnt = torch.empty(batch, dtype=torch.int32).pin_memory()
+        self.h_desc_t = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+        self.h_val_t = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self.h_desc_n = torch.empty((batch * self.ncell, 32), dtype=torch.uint8).pin_memory()
+        self.h_val_n = torch.empty(batch * self.ncell, dtype=torch.uint8).pin_memory()
+        # device-resident copies for the `value` arm
+        self.d_prev, self.d_cur = self.h_prev.to(dev), self.h_cur.to(dev)
+        self.d_kps, self.d_pri0, self.d_lv = self.h_kps.to(dev), self.h_pri0.to(dev), self.h_lv.to(dev)
+        self.d_pri = torch.empty_like(self.d_pri0)
+        self.d_status = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.d_th = torch.empty(batch, dtype=torch.int32, device=dev)
+        self.d_new = torch.empty((batch * self.ncell, 2), dtype=torch.float32, device=dev)
+        self.d_cnt = torch.empty(batch, dtype=torch.int32, device=dev)
+        self.d_desc_t = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+        self.d_val_t = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.d_desc_n = torch.empty((batch * self.ncell, 32), dtype=torch.uint8, device=dev)
+        self.d_val_n = torch.empty(batch * self.ncell, dtype=torch.uint8, device=dev)
+        # two pyramid sets: one aliasing the device images, one owning level 0 (host uploads)
+        self.pyr_prev_d = api.Pyramid(ctx, batch, W_IMG, H_IMG, 3)
+        self.pyr_cur_d = api.Pyramid(ctx, batch, W_IMG, H_IMG, 3)
+        self.pyr_prev_h = api.Pyramid(ctx, batch, W_IMG, H_IMG, 3)
+        self.pyr_cur_h = api.Pyramid(ctx, batch, W_IMG, H_IMG, 3)
+        self.ft = api.FeatureTracker(ctx, 30, 0.01)
+        self.fe = api.FeatureExtractor(ctx, nmaxdist=CELL, nfast_th=FAST_TH)
+        self.h2d = (self.h_prev.numel() + self.h_cur.numel() + self.h_kps.numel() * 4 + self.h_pri0.numel() * 4 +
+                    self.h_lv.numel() + self.h_th.numel() * 4 + n * 8 + batch * self.ncell * 8)
+        self.d2h = (n * 8 + n + batch * 4 + batch * self.ncell * 8 + batch * 4 + n * 33 + batch * self.ncell * 33)
+
+    def step_resident(self):
+        B, n = self.B, self.B * NKP
+        self.pyr_prev_d.build(self.d_prev)
+        self.pyr_cur_d.build(self.d_cur)
+        self.d_pri.copy_(self.d_pri0)          # vpriorkps is in/out: fresh guess every step
+        self.d_th.fill_(FAST_TH)               # constant work per step
+        self.ft.fb_klt_tracking(self.pyr_prev_d, self.pyr_cur_d, 9, self.d_lv, 30.0, 0.5, self.d_kps, self.d_pri,
+                                self.d_status, n=n, per_frame=NKP)
+        self.fe.detect_grid_fast(self.pyr_cur_d, CELL, 0, B, self.d_th, self.d_new, self.d_cnt, max_per_frame=self.ncell)
+        self.fe.describe_brief(self.pyr_cur_d, self.d_pri, self.d_desc_t, self.d_val_t, n=n, per_frame=NKP)
+        self.fe.describe_brief(self.pyr_cur_d, self.d_new, self.d_desc_n, self.d_val_n, n=B * self.ncell, per_frame=self.ncell)
+
+    def step_e2e(self):
+        B, n = self.B, self.B * NKP
+        self.pyr_prev_h.build(self.h_prev.numpy())       # H2D inside
+        self.pyr_cur_h.build(self.h_cur.numpy())
+        self.h_pri.copy_(self.h_pri0)
+        self.h_th.fill_(FAST_TH)
+        self.ft.fb_klt_tracking(self.pyr_prev_h, self.pyr_cur_h, 9, self.h_lv.numpy(), 30.0, 0.5, self.h_kps.numpy(),
+                                self.h_pri.numpy(), self.h_status.numpy(), n=n, per_frame=NKP)
+        self.fe.detect_grid_fast(self.pyr_cur_h, CELL, 0, B, self.h_th.numpy(), self.h_new.numpy(), self.h_cnt.numpy(),
+                                 max_per_frame=self.ncell)
+        self.fe.describe_brief(self.pyr_cur_h, self.h_pri.numpy(), self.h_desc_t.numpy(), self.h_val_t.numpy(), n=n, per_frame=NKP)
+        self.fe.describe_brief(self.pyr_cur_h, self.h_new.numpy(), self.h_desc_n.numpy(), self.h_val_n.numpy(),
+                               n=B * self.ncell, per_frame=self.ncell)
+        return int(self.h_status.sum()), int(self.h_cnt.sum())
+
+
+# SURVEY.md 8(d) algorithmic bytes per unit (stated in DESIGN.md)
+def algorithmic_bytes(kernel: str, batch: int) -> float:
+    wh = W_IMG * H_IMG
+    ncell = (H_IMG // CELL) * (W_IMG // CELL)
+    if kernel == "fb_klt_kernel":       # per keypoint: fwd 0.9 KB + bwd 0.22 KB compulsory gathers
+        return batch * NKP * (900.0 + 220.0)
+    if kernel == "pyr_down_kernel":     # per frame and level pair: read level, write quarter (3 launches / pyramid)
+        return batch * wh * (1 + 0.25 + 0.25 + 0.0625 + 0.0625 + 0.015625) / 3.0
+    if kernel == "fast_cells_kernel":   # read the cells once + candidate lists
+        return batch * (ncell * CELL * CELL + ncell * 8.0)
+    if kernel == "fast_sweep_kernel":
+        return batch * ncell * 64.0
+    if kernel == "subpix_kernel":
+        return batch * ncell * (81.0 * 4 + 16)
+    if kernel == "describe_kernel":     # 32x32 raw window + 32 B descriptor per keypoint
+        return batch * NKP * (1024.0 + 40.0)
+    return 0.0
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from ov2slam_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a real (non-default) stream: the C ABI context launches on it and torch's helper ops
+    # (copy_/fill_) are ordered with the kernels because it is also torch's current stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = api.Context(local, stream=stream.cuda_stream)
+    wl = Workload(torch, api, ctx, rank, args.batch)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        t = torch.tensor([ms, wall * 1000.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, wall_res, launches = timed(wl.step_resident, args.steps, args.warmup)
+    ms_e2e_dev, wall_e2e, _ = timed(wl.step_e2e, args.steps, max(1, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    # device events miss host-side staging of the last D2H sync; use the larger of event/wall time for e2e
+    ms_e2e = max(ms_e2e_dev, wall_e2e)
+    frames = world * args.batch * args.steps
+    value = frames / (ms_res / 1000.0)
+    e2e = frames / (ms_e2e / 1000.0)
+
+    line = None
+    if rank == 0:
+        # roofline pass: per-kernel CUDA-event durations on the launching stream (separate, untimed run)
+        ctx.profile(True)
+        for _ in range(3):
+            wl.step_resident()
+        rep = ctx.profile_report()
+        ctx.profile(False)
+        peak, peak_src = _peaks()
+        tot = sum(v[0] for v in rep.values()) or 1.0
+        dom = max(rep.items(), key=lambda kv: kv[1][0])
+        dname, (dms, dn) = dom
+        avg_ms = dms / dn
+        alg = algorithmic_bytes(dname, args.batch)
+        if dname == "describe_kernel":   # two launches of different size per step: use the per-step total
+            alg = args.batch * (NKP + (H_IMG // CELL) * (W_IMG // CELL)) * 1064.0 / 2.0
+        achieved = alg / (avg_ms * 1e-3) / 1e9
+        shares = {k: round(v[0] / tot, 4) for k, v in rep.items()}
+        roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": _ncu_traffic(dname), "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares,
+                "note": "KLT is gather/iteration bound by construction (SURVEY.md 8d-ii): HBM fraction is low by design"}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            nfr = int(min(max(6 * cores, 64), 1536))
+            fps, t, n = run_cpu_reference(nfr, cores)
+            fps1, t1, n1 = run_cpu_reference(16, 1)
+            try:
+                import cv2
+                ver = cv2.__version__
+            except Exception:
+                ver = "?"
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"{n} frame pairs, OpenCV {ver} call sequence (oracle/image_ref.py) in {cores} processes x 1 cv2 thread; "
+                             f"single core: {fps1:.1f} frames/s on {n1} pairs"}
+        line = {
+            "metric": "front-end frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32",
+            "data": "synthetic", "config": _config(args.batch, "per-GPU batch fixed (weak scaling); no data-path collective"),
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        if world == 1 and not args.no_ba:
+            try:
+                line["localba"] = ba_bench(torch, api, ctx)
+            except Exception as e:  # the BA leg must never take the front-end line down
+                line["localba"] = {"error": str(e)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _ncu_traffic(kernel: str):
+    """dram bytes per launch from the committed ncu summary (profiles/), or None."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        return json.loads(p.read_text()).get(kernel)
+    except Exception:
+        return None
+
+
+def ba_bench(torch, api, ctx):
+    """local-BA solves/s on the C3 problem (10 KF x 2k pts x 8k obs), second half of the metric."""
+    from ov2slam_b200 import synth
+    opt = api.Optimizer(ctx)
+    pb0 = synth.make_ba_problem(3, 10, 2000, 8000)
+    reps = 20
+    its = 0
+    pb = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
+    opt.local_ba(pb)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pb = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
+        res, _ = opt.local_ba(pb)
+        its += res["iters_robust"] + res["iters_refine"]
+    dt = time.perf_counter() - t0
+    return {"metric": "local-BA solves/sec", "value": reps / dt, "unit": "solves/s", "config": "C3: 10 KF x 2000 pts x 8000 obs",
+            "lm_iterations_per_solve": its / reps, "e2e": True, "final_cost": res["final_cost"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ba", action="store_true", help="skip the local-BA leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

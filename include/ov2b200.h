@@ -63,6 +63,13 @@ OV2_API ov2_status ov2_host_free(ov2_ctx* ctx, void* p);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 OV2_API uint64_t   ov2_launch_count(const ov2_ctx* ctx);
 
+/* Per-kernel timing with CUDA events on the launching stream (serialises launches; for
+ * bench.py's roofline pass, never on during the timed benchmark region).
+ * ov2_profile_query: idx-th kernel class -> name, accumulated ms, launch count; returns 0 past the end. */
+OV2_API ov2_status ov2_profile_enable(ov2_ctx* ctx, int on);
+OV2_API int        ov2_profile_query(const ov2_ctx* ctx, int idx, char* name_out, int name_cap, double* total_ms,
+                             uint64_t* launches);
+
 /* ------------------------------------------------------------------ P: pyramid
  * Replaces cv::buildOpticalFlowPyramid(img, pyr, Size(9,9), 3) as called by
  * VisualFrontEnd::preprocessImage (/root/reference/src/visual_front_end.cpp:1172, also :53 and

@@ -27,7 +27,7 @@ STATUS_NAMES = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "CAPACITY",
 
 ABI_SYMBOLS = [
     "ov2_create", "ov2_destroy", "ov2_last_error", "ov2_version", "ov2_set_stream", "ov2_sync",
-    "ov2_host_alloc", "ov2_host_free", "ov2_launch_count",
+    "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download",
     "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_localba_solve",
 ]
@@ -86,6 +86,8 @@ def load():
     lib.ov2_host_free.argtypes = [vp, vp]
     lib.ov2_launch_count.argtypes = [vp]
     lib.ov2_launch_count.restype = C.c_uint64
+    lib.ov2_profile_enable.argtypes = [vp, i32]
+    lib.ov2_profile_query.argtypes = [vp, i32, C.c_char_p, i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.ov2_pyr_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
     lib.ov2_pyr_destroy.argtypes = [vp]
     lib.ov2_pyr_destroy.restype = None
@@ -143,6 +145,20 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ov2_launch_count(self.h))
+
+    def profile(self, on: bool):
+        self.check(self.lib.ov2_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (total ms, launches)} accumulated since profile(True)."""
+        out = {}
+        buf = C.create_string_buffer(64)
+        ms, n = C.c_double(), C.c_uint64()
+        i = 0
+        while self.lib.ov2_profile_query(self.h, i, buf, 64, C.byref(ms), C.byref(n)):
+            out[buf.value.decode()] = (ms.value, int(n.value))
+            i += 1
+        return out
 
     def close(self):
         if self.h:

@@ -42,6 +42,7 @@ extern "C" void ov2_destroy(ov2_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& ch : ctx->chunks) cudaFree(ch.p);
     if (ctx->ba_ws) cudaFree(ctx->ba_ws);
+    if (ctx->pe0) { cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -80,6 +81,42 @@ extern "C" ov2_status ov2_host_free(ov2_ctx* ctx, void* p) {
     if (!ctx) return OV2_ERR_INVALID;
     OV2_CUDA(ctx, cudaFreeHost(p));
     return OV2_OK;
+}
+
+void ov2_prof_begin(ov2_ctx* ctx) { cudaEventRecord(ctx->pe0, ctx->stream); }
+
+void ov2_prof_end(ov2_ctx* ctx, const char* name) {
+    cudaEventRecord(ctx->pe1, ctx->stream);
+    cudaEventSynchronize(ctx->pe1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->pe0, ctx->pe1);
+    for (auto& p : ctx->prof)
+        if (p.name == name) { p.ms += ms; p.n++; return; }
+    ctx->prof.push_back({name, (double)ms, 1});
+}
+
+extern "C" ov2_status ov2_profile_enable(ov2_ctx* ctx, int on) {
+    if (!ctx) return OV2_ERR_INVALID;
+    OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->pe0) {
+        OV2_CUDA(ctx, cudaEventCreate(&ctx->pe0));
+        OV2_CUDA(ctx, cudaEventCreate(&ctx->pe1));
+    }
+    ctx->profiling = on != 0;
+    if (on) ctx->prof.clear();
+    return OV2_OK;
+}
+
+extern "C" int ov2_profile_query(const ov2_ctx* ctx, int idx, char* name_out, int name_cap, double* total_ms,
+                                 uint64_t* launches) {
+    if (!ctx || idx < 0 || idx >= (int)ctx->prof.size()) return 0;
+    const auto& p = ctx->prof[idx];
+    if (name_out && name_cap > 0) {
+        snprintf(name_out, name_cap, "%s", p.name.c_str());
+    }
+    if (total_ms) *total_ms = p.ms;
+    if (launches) *launches = p.n;
+    return 1;
 }
 
 extern "C" uint64_t ov2_launch_count(const ov2_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -18,7 +18,7 @@ namespace {
 
 constexpr int WARPS = 4;
 
-__constant__ signed char c_pat[256][4];
+__device__ __align__(16) signed char g_pat[256][4];   // global (not __constant__): every lane reads its own 8 pairs
 __constant__ float c_gk[7];
 
 struct DescArgs {
@@ -30,8 +30,8 @@ struct DescArgs {
 };
 
 __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
-    __shared__ uint8_t sraw[WARPS][32 * 32];
-    __shared__ float srow[WARPS][32 * 27];   // 32 rows x 26 cols (+1 pad)
+    __shared__ float sraw[WARPS][32 * 33];   // 32x32 raw window as float (+1 pad: conflict-free rows)
+    __shared__ float srow[WARPS][32 * 27];   // row-filtered: 32 rows x 26 cols (+1 pad)
     __shared__ uint8_t ssm[WARPS][26 * 28];  // 26 x 26 smoothed (+2 pad)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * WARPS + warp;
@@ -47,47 +47,64 @@ __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
     }
     const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
     const uint8_t* img = A.img + A.fstride * frame + (size_t)(cy - 16) * A.pitch + (cx - 16);
-    uint8_t* raw = sraw[warp];
+    float* raw = sraw[warp];
     float* row = srow[warp];
     uint8_t* sm = ssm[warp];
-    // raw window rows cy-16..cy+15, cols cx-16..cx+15: lane = column
-    for (int r = 0; r < 32; ++r) raw[r * 32 + lane] = __ldg(img + (size_t)r * A.pitch + lane);
+    // raw window rows cy-16..cy+15, cols cx-16..cx+15 (lane = column): 32 coalesced 32-byte reads
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) raw[r * 33 + lane] = (float)__ldg(img + (size_t)r * A.pitch + lane);
     __syncwarp();
-    // row filter: output col c (0..25) <-> image col cx-13+c, taps raw cols c..c+6
     const float k0 = c_gk[0], k1 = c_gk[1], k2 = c_gk[2], k3 = c_gk[3];
-    for (int e = lane; e < 32 * 26; e += 32) {
-        int r = e / 26, c = e - r * 26;
-        const uint8_t* p = raw + r * 32 + c;
-        float acc = (float)p[0] * k0;
-        acc = __fmaf_rn((float)p[1], k1, acc);
-        acc = __fmaf_rn((float)p[2], k2, acc);
-        acc = __fmaf_rn((float)p[3], k3, acc);
-        acc = __fmaf_rn((float)p[4], k2, acc);
-        acc = __fmaf_rn((float)p[5], k1, acc);
-        acc = __fmaf_rn((float)p[6], k0, acc);
-        row[r * 27 + c] = acc;
+    // row filter, lane = row: output col c (0..25) <-> image col cx-13+c, taps raw cols c..c+6,
+    // sequential FMA chain exactly as OpenCV's float row filter evaluates it
+    {
+        const float* p = raw + lane * 33;
+        float x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3], x4 = p[4], x5 = p[5];
+#pragma unroll
+        for (int c = 0; c < 26; ++c) {
+            const float x6 = p[c + 6];
+            float acc = x0 * k0;
+            acc = __fmaf_rn(x1, k1, acc);
+            acc = __fmaf_rn(x2, k2, acc);
+            acc = __fmaf_rn(x3, k3, acc);
+            acc = __fmaf_rn(x4, k2, acc);
+            acc = __fmaf_rn(x5, k1, acc);
+            acc = __fmaf_rn(x6, k0, acc);
+            row[lane * 27 + c] = acc;
+            x0 = x1; x1 = x2; x2 = x3; x3 = x4; x4 = x5; x5 = x6;
+        }
     }
     __syncwarp();
-    // column filter: output row q (0..25) <-> image row cy-13+q, taps rows q..q+6 (centre q+3)
-    for (int e = lane; e < 26 * 26; e += 32) {
-        int q = e / 26, c = e - q * 26;
-        const float* p = row + q * 27 + c;
-        float acc = p[3 * 27] * k3;
-        acc = __fmaf_rn(p[2 * 27] + p[4 * 27], k2, acc);
-        acc = __fmaf_rn(p[1 * 27] + p[5 * 27], k1, acc);
-        acc = __fmaf_rn(p[0] + p[6 * 27], k0, acc);
-        int v = __float2int_rn(acc);
-        v = v < 0 ? 0 : (v > 255 ? 255 : v);
-        sm[q * 28 + c] = (uint8_t)v;
+    // column filter, lane = column: output row q (0..25) <-> image row cy-13+q, taps rows q..q+6
+    // (centre q+3), symmetric pairs + FMA as OpenCV's float column filter, rint -> u8
+    if (lane < 26) {
+        const float* p = row + lane;
+        float y0 = p[0], y1 = p[27], y2 = p[2 * 27], y3 = p[3 * 27], y4 = p[4 * 27], y5 = p[5 * 27];
+#pragma unroll
+        for (int q = 0; q < 26; ++q) {
+            const float y6 = p[(q + 6) * 27];
+            float acc = y3 * k3;
+            acc = __fmaf_rn(y2 + y4, k2, acc);
+            acc = __fmaf_rn(y1 + y5, k1, acc);
+            acc = __fmaf_rn(y0 + y6, k0, acc);
+            int v = __float2int_rn(acc);
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            sm[q * 28 + lane] = (uint8_t)v;
+            y0 = y1; y1 = y2; y2 = y3; y3 = y4; y4 = y5; y5 = y6;
+        }
     }
     __syncwarp();
     // 8 tests per lane -> one descriptor byte per lane
     unsigned byte = 0;
+    const int4 pa = __ldg(reinterpret_cast<const int4*>(&g_pat[lane * 8][0]));
+    const int4 pb = __ldg(reinterpret_cast<const int4*>(&g_pat[lane * 8 + 4][0]));
+    const int pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const signed char* t = c_pat[lane * 8 + k];
-        int a = sm[(t[1] + 13) * 28 + (t[0] + 13)];
-        int b = sm[(t[3] + 13) * 28 + (t[2] + 13)];
+        const int t0 = (int)(signed char)(pw[k] & 255), t1 = (int)(signed char)((pw[k] >> 8) & 255);
+        const int t2 = (int)(signed char)((pw[k] >> 16) & 255), t3 = (int)(signed char)((pw[k] >> 24) & 255);
+        int a = sm[(t1 + 13) * 28 + (t0 + 13)];
+        int b = sm[(t3 + 13) * 28 + (t2 + 13)];
         byte |= (unsigned)(a < b) << k;
     }
     dout[lane] = (uint8_t)byte;
@@ -114,7 +131,7 @@ extern "C" ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, cons
         const float kf[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f,
                              0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
         OV2_CUDA(ctx, cudaMemcpyToSymbol(c_gk, kf, sizeof(kf)));
-        OV2_CUDA(ctx, cudaMemcpyToSymbol(c_pat, OV2_ORB_PATTERN, sizeof(OV2_ORB_PATTERN)));
+        OV2_CUDA(ctx, cudaMemcpyToSymbol(g_pat, OV2_ORB_PATTERN, sizeof(OV2_ORB_PATTERN)));
         g_tables_loaded[ctx->device] = true;
     }
     DescArgs A;
@@ -130,7 +147,6 @@ extern "C" ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, cons
     A.desc = (uint8_t*)o;
     if ((st = ov2_stage_out(ctx, valid_out, (size_t)n, &o)) != OV2_OK) return st;
     A.valid = (uint8_t*)o;
-    describe_kernel<<<div_up(n, WARPS), WARPS * 32, 0, ctx->stream>>>(A);
-    OV2_CHECK_LAUNCH(ctx, "describe_kernel");
+    OV2_LAUNCH(ctx, "describe_kernel", describe_kernel<<<div_up(n, WARPS), WARPS * 32, 0, ctx->stream>>>(A));
     return ov2_end(ctx);
 }

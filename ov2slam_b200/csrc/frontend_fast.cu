@@ -47,6 +47,8 @@ __global__ void fast_cells_kernel(FastArgs A) {
     uint8_t* roi = smem;                       // cs*cs
     uint8_t* sc = smem + cs * cs;              // cs*cs: score s (0 = not a corner at th)
     uint8_t* keep = sc + cs * cs;              // cs*cs
+    uint16_t* clist = (uint16_t*)(keep + ((cs * cs + 1) & ~1));   // corner pixel indices (compacted)
+    __shared__ int s_ncorner;
     const int cell = blockIdx.x, fr = blockIdx.y;
     const int r = cell / A.nwc, c = cell - r * A.nwc;
     const int x0 = c * cs, y0 = r * cs;
@@ -64,63 +66,79 @@ __global__ void fast_cells_kernel(FastArgs A) {
         sc[i] = 0;
         keep[i] = 0;
     }
+    if (threadIdx.x == 0) s_ncorner = 0;
     __syncthreads();
     const int in_w = cs - 6;
+    // pass 1: corner test for every interior pixel.  Quick reject first: every 9-arc of the
+    // 16-ring contains at least two of the compass points {0,4,8,12}.
     for (int i = threadIdx.x; i < in_w * in_w; i += blockDim.x) {
         int yy = 3 + i / in_w, xx = 3 + i % in_w;
         const uint8_t* p = roi + yy * cs + xx;
         const int v = *p;
-        int d[16];
+        const int c0 = v - (int)p[-3 * cs], c4 = v - (int)p[3], c8 = v - (int)p[3 * cs], c12 = v - (int)p[-3];
+        const int nb = (c0 > th) + (c4 > th) + (c8 > th) + (c12 > th);
+        const int nd = (c0 < -th) + (c4 < -th) + (c8 < -th) + (c12 < -th);
+        if (nb < 2 && nd < 2) continue;
         unsigned bright = 0, dark = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            d[k] = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
-            bright |= (unsigned)(d[k] > th) << k;
-            dark |= (unsigned)(d[k] < -th) << k;
+            int dk_ = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
+            bright |= (unsigned)(dk_ > th) << k;
+            dark |= (unsigned)(dk_ < -th) << k;
         }
-        // 9 contiguous set bits on the 16-ring?
         unsigned b = bright | (bright << 16), dk = dark | (dark << 16);
         b &= b >> 1; b &= b >> 2; b &= b >> 4; b &= b >> 1;
         dk &= dk >> 1; dk &= dk >> 2; dk &= dk >> 4; dk &= dk >> 1;
         if ((b | dk) & 0xFFFFu) {
-            // exact score s = max over the 16 arcs of min(d) / min(-d) = the largest t for which a
-            // 9-run of (d >= t) or of (d <= -t) exists: bisection on t with the same bit test.
-            int lo = th + 1, hi = 256;   // P(lo) holds (corner at th), P(256) cannot
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                unsigned bm = 0, dm = 0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    bm |= (unsigned)(d[k] >= mid) << k;
-                    dm |= (unsigned)(d[k] <= -mid) << k;
-                }
-                bm |= bm << 16; dm |= dm << 16;
-                bm &= bm >> 1; bm &= bm >> 2; bm &= bm >> 4; bm &= bm >> 1;
-                dm &= dm >> 1; dm &= dm >> 2; dm &= dm >> 4; dm &= dm >> 1;
-                if ((bm | dm) & 0xFFFFu) lo = mid; else hi = mid;
-            }
-            sc[yy * cs + xx] = (uint8_t)lo;   // th < s <= 255
+            int pos = atomicAdd(&s_ncorner, 1);
+            clist[pos] = (uint16_t)(yy * cs + xx);
         }
     }
     __syncthreads();
+    // pass 2 (dense over the corners): exact score s = max over the 16 arcs of min(d) / min(-d)
+    // = the largest t for which a 9-run of (d >= t) or (d <= -t) exists: bisection on t.
+    const int ncorner = s_ncorner;
+    for (int i = threadIdx.x; i < ncorner; i += blockDim.x) {
+        const int pi = clist[i];
+        const uint8_t* p = roi + pi;
+        const int v = *p;
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
+        int lo = th + 1, hi = 256;   // P(lo) holds (corner at th), P(256) cannot
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            unsigned bm = 0, dm = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                bm |= (unsigned)(d[k] >= mid) << k;
+                dm |= (unsigned)(d[k] <= -mid) << k;
+            }
+            bm |= bm << 16; dm |= dm << 16;
+            bm &= bm >> 1; bm &= bm >> 2; bm &= bm >> 4; bm &= bm >> 1;
+            dm &= dm >> 1; dm &= dm >> 2; dm &= dm >> 4; dm &= dm >> 1;
+            if ((bm | dm) & 0xFFFFu) lo = mid; else hi = mid;
+        }
+        sc[pi] = (uint8_t)lo;   // th < s <= 255
+    }
+    __syncthreads();
     // 3x3 NMS on response = s - 1 (non-corners count 0): strictly greater than all 8 neighbours
-    for (int i = threadIdx.x; i < in_w * in_w; i += blockDim.x) {
-        int yy = 3 + i / in_w, xx = 3 + i % in_w;
-        int s = sc[yy * cs + xx];
-        if (s == 0) continue;
-        int resp = s - 1;
+    for (int i = threadIdx.x; i < ncorner; i += blockDim.x) {
+        const int pi = clist[i];
+        const int xx = pi % cs;
+        const int resp = (int)sc[pi] - 1;
         bool ok = true;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 if (dx == 0 && dy == 0) continue;
-                int sn = sc[(yy + dy) * cs + xx + dx];
+                int sn = sc[pi + dy * cs + dx];
                 int rn = sn ? sn - 1 : 0;
                 ok = ok && (resp > rn);
             }
         // CV_32F mask read as bytes: only cell-local x % 4 in {2,3} can see a non-zero byte of 1.0f
-        if (ok && (xx & 2)) keep[yy * cs + xx] = 1;
+        if (ok && (xx & 2)) keep[pi] = 1;
     }
     __syncthreads();
     // ordered emission (row-major scan order) by warp 0
@@ -481,11 +499,10 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     FA.th = d_th; FA.cand = d_cand; FA.cand_n = d_candn; FA.overflow = d_ovf;
     {
         int threads = cellsize > 24 ? 128 : 32;
-        size_t smem = (size_t)3 * cellsize * cellsize;
+        size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
         if (smem > 48 * 1024)
             OV2_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fast_cells_kernel<<<dim3(ncells, count), threads, smem, ctx->stream>>>(FA);
-        OV2_CHECK_LAUNCH(ctx, "fast_cells_kernel");
+        OV2_LAUNCH(ctx, "fast_cells_kernel", fast_cells_kernel<<<dim3(ncells, count), threads, smem, ctx->stream>>>(FA));
     }
     SweepArgs SA;
     SA.w = W; SA.h = H; SA.cs = cellsize; SA.nwc = nwc; SA.nhc = nhc; SA.cap = cap;
@@ -500,8 +517,7 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
         if (smem > 227 * 1024) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_grid_fast: image too large for the shared-memory mask bitmap");
         if (smem > 48 * 1024)
             OV2_CUDA(ctx, cudaFuncSetAttribute(fast_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fast_sweep_kernel<<<count, 32, smem, ctx->stream>>>(SA);
-        OV2_CHECK_LAUNCH(ctx, "fast_sweep_kernel");
+        OV2_LAUNCH(ctx, "fast_sweep_kernel", fast_sweep_kernel<<<count, 32, smem, ctx->stream>>>(SA));
     }
     SubpixArgs PA;
     PA.img = pyr->l0; PA.w = W; PA.h = H; PA.pitch = (int)pyr->l0_pitch; PA.fstride = (long long)pyr->l0_fstride;
@@ -515,8 +531,7 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
             PA.mask[i * 7 + j] = (float)(vy * expf(-x * x));
         }
     }
-    subpix_kernel<<<div_up(PA.n, 4), 128, 0, ctx->stream>>>(PA);
-    OV2_CHECK_LAUNCH(ctx, "subpix_kernel");
+    OV2_LAUNCH(ctx, "subpix_kernel", subpix_kernel<<<div_up(PA.n, 4), 128, 0, ctx->stream>>>(PA));
     // capacity overflow is an error, never a silent truncation
     int ovf = 0;
     bool host_out = !ctx->pending.empty();
@@ -563,8 +578,7 @@ extern "C" ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int
     FA.overflow = (int32_t*)o;
     OV2_CUDA(ctx, cudaMemsetAsync(FA.overflow, 0, sizeof(int32_t), ctx->stream));
     int threads = cellsize > 24 ? 128 : 32;
-    size_t smem = (size_t)3 * cellsize * cellsize;
-    fast_cells_kernel<<<dim3(ncells, 1), threads, smem, ctx->stream>>>(FA);
-    OV2_CHECK_LAUNCH(ctx, "fast_cells_kernel");
+    size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
+    OV2_LAUNCH(ctx, "fast_cells_kernel", fast_cells_kernel<<<dim3(ncells, 1), threads, smem, ctx->stream>>>(FA));
     return ov2_end(ctx);
 }

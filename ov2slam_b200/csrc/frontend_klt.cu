@@ -285,7 +285,6 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
     A.priors = (float2*)o;
     if ((st = ov2_stage_out(ctx, status_out, (size_t)n, &o)) != OV2_OK) return st;
     A.status = (uint8_t*)o;
-    fb_klt_kernel<9><<<div_up(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, ctx->stream>>>(A);
-    OV2_CHECK_LAUNCH(ctx, "fb_klt_kernel");
+    OV2_LAUNCH(ctx, "fb_klt_kernel", fb_klt_kernel<9><<<div_up(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, ctx->stream>>>(A));
     return ov2_end(ctx);
 }

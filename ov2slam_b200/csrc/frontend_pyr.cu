@@ -124,10 +124,9 @@ extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* ima
         int spitch = (int)(l == 1 ? p->l0_pitch : p->pitch[l - 1]);
         long long sfs = (long long)(l == 1 ? p->l0_fstride : p->fstride[l - 1]);
         dim3 grid(div_up(p->w[l], OUT_W), div_up(p->h[l], OUT_H), count);
-        pyr_down_kernel<<<grid, dim3(TX, TY), 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], spitch, sfs, p->own[l],
+        OV2_LAUNCH(ctx, "pyr_down_kernel", pyr_down_kernel<<<grid, dim3(TX, TY), 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], spitch, sfs, p->own[l],
                                                                p->w[l], p->h[l], (int)p->pitch[l],
-                                                               (long long)p->fstride[l], first);
-        OV2_CHECK_LAUNCH(ctx, "pyr_down_kernel");
+                                                               (long long)p->fstride[l], first));
     }
     return ov2_end(ctx);
 }

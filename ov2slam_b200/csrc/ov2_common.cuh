@@ -28,6 +28,11 @@ struct ov2_ctx {
     std::vector<Pending> pending;
     // persistent small device blocks (tables)
     void* ba_ws = nullptr; size_t ba_ws_cap = 0;
+    // optional per-kernel CUDA-event timing (ov2_profile_enable): serialises launches
+    bool profiling = false;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    struct Prof { std::string name; double ms; uint64_t n; };
+    std::vector<Prof> prof;
 };
 
 struct ov2_pyr {
@@ -77,6 +82,21 @@ ov2_status ov2_fail(ov2_ctx* ctx, ov2_status st, const char* what, cudaError_t c
         (ctx)->launches++;                                                          \
         cudaError_t _e = cudaGetLastError();                                        \
         if (_e != cudaSuccess) return ov2_fail((ctx), OV2_ERR_CUDA, name, _e);      \
+    } while (0)
+
+void ov2_prof_begin(ov2_ctx* ctx);
+void ov2_prof_end(ov2_ctx* ctx, const char* name);
+
+// Launch wrapper: counts the launch, checks the launch error and, when profiling is on, times
+// the kernel with CUDA events on the launching stream.
+#define OV2_LAUNCH(ctx, name, ...)                                                  \
+    do {                                                                            \
+        if ((ctx)->profiling) ov2_prof_begin(ctx);                                  \
+        __VA_ARGS__;                                                                \
+        (ctx)->launches++;                                                          \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) return ov2_fail((ctx), OV2_ERR_CUDA, name, _e);      \
+        if ((ctx)->profiling) ov2_prof_end(ctx, name);                              \
     } while (0)
 
 // --- call scope: scratch + staging ------------------------------------------------------

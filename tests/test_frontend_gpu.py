@@ -248,3 +248,39 @@ def test_empty_inputs(ctx):
     api.FeatureTracker(ctx).fb_klt_tracking(pyr, pyr, 9, 3, 30.0, 0.5, z, z.copy(), np.zeros(0, np.uint8), n=0, per_frame=1)
     api.FeatureExtractor(ctx).describe_brief(pyr, z, np.zeros((0, 32), np.uint8), np.zeros(0, np.uint8), n=0, per_frame=1)
     pyr.close()
+
+
+def test_against_committed_goldens(ctx):
+    """CUDA vs the golden vectors generated from the real OpenCV call sequence in the build
+    container (tests/golden/frontend_golden.npz, scripts/make_golden.py) - independent of whether
+    cv2 exists on the GPU box."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "frontend_golden.npz")
+    w, h = int(g["w"]), int(g["h"])
+    prev, cur, flow = synth.make_pair(int(g["seed"]), w, h)
+    pp = api.Pyramid(ctx, 1, w, h, 3)
+    cp = api.Pyramid(ctx, 1, w, h, 3)
+    pp.build(prev[None])
+    cp.build(cur[None])
+    for l in range(1, 4):
+        assert np.array_equal(cp.download(0, l), g[f"pyr{l}"])
+    for cs in (50, 35, 16):
+        for tag in ("empty", "kps"):
+            fe = api.FeatureExtractor(ctx, nfast_th=10)
+            pts, ipts = fe.detect_grid_fast_frame(pp, 0, cs, g[f"fast_{cs}_{tag}_in"])
+            assert np.array_equal(ipts, g[f"fast_{cs}_{tag}_int"]), (cs, tag)
+            assert fe.nfast_th_ == int(g[f"fast_{cs}_{tag}_th"])
+            assert np.abs(pts - g[f"fast_{cs}_{tag}_subpix"]).max() <= SUBPIX_TOL
+    pts = g["desc_pts"]
+    d = np.empty((len(pts), 32), np.uint8)
+    v = np.empty(len(pts), np.uint8)
+    api.FeatureExtractor(ctx).describe_brief(pp, pts, d, v)
+    assert np.array_equal(v, g["desc_valid"]) and np.array_equal(d, g["desc"])
+    for lvl in (0, 1, 3):
+        out = g["klt_pri"].copy()
+        st = np.zeros(len(out), np.uint8)
+        api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, lvl, 30.0, 0.5, g["klt_kps"], out, st)
+        assert np.array_equal(st, g[f"klt_{lvl}_status"]), lvl
+        assert np.abs(out - g[f"klt_{lvl}_tracked"]).max() <= KLT_TOL
+    pp.close()
+    cp.close()

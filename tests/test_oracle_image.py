@@ -1,0 +1,163 @@
+"""CPU tests: the oracle's numpy restatement (what documents the semantics the CUDA kernels
+implement) is pinned against the real OpenCV the reference calls (cv2 4.13) and against the
+committed golden vectors generated from cv2 (scripts/make_golden.py)."""
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import image_ref as R
+from ov2slam_b200 import synth
+
+GOLD = Path(__file__).parent / "golden" / "frontend_golden.npz"
+needs_cv2 = pytest.mark.skipif(not R.HAVE_CV2, reason="cv2 not importable")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(GOLD)
+    prev, cur, flow = synth.make_pair(int(g["seed"]), int(g["w"]), int(g["h"]))
+    assert hashlib.sha256(prev.tobytes() + cur.tobytes()).hexdigest() == str(g["img_sha"]), \
+        "synthetic generator drifted: golden inputs no longer reproducible"
+    return g, prev, cur, flow
+
+
+def test_golden_pyramid(gold):
+    g, prev, cur, _ = gold
+    pyr = R.build_pyramid_ref(cur, 3)
+    for l in range(1, 4):
+        assert np.array_equal(pyr[l], g[f"pyr{l}"])
+
+
+@pytest.mark.parametrize("cs", [50, 35, 16])
+@pytest.mark.parametrize("tag", ["empty", "kps"])
+def test_golden_grid_fast(gold, cs, tag):
+    g, prev, _, _ = gold
+    ipts, th, _ = R.detect_grid_fast_nosubpix(prev, cs, g[f"fast_{cs}_{tag}_in"], 10, use_cv2=False)
+    assert np.array_equal(ipts, g[f"fast_{cs}_{tag}_int"])
+    assert th == int(g[f"fast_{cs}_{tag}_th"])
+
+
+def test_golden_subpix(gold):
+    g, prev, _, _ = gold
+    ip = g["fast_50_empty_int"]
+    sp = R.corner_subpix_ref(prev, ip.astype(np.float32))
+    d = np.abs(sp - g["fast_50_empty_subpix"])
+    assert d.max() <= 1e-4 and (d == 0).mean() > 0.9
+
+
+def test_golden_descriptors(gold):
+    g, prev, _, _ = gold
+    d, v = R.describe_ref(prev, g["desc_pts"])
+    assert np.array_equal(v, g["desc_valid"]) and np.array_equal(d, g["desc"])
+
+
+def test_golden_klt(gold):
+    g, prev, cur, _ = gold
+    sel = np.r_[0:60, 300:360]   # the python restatement is slow: a subset incl. the random points
+    for lvl in (0, 3):
+        t, s = R.fb_klt_ref(prev, cur, g["klt_kps"][sel], g["klt_pri"][sel], 9, lvl)
+        assert np.array_equal(s, g[f"klt_{lvl}_status"][sel])
+        assert np.abs(t - g[f"klt_{lvl}_tracked"][sel]).max() <= 1e-3
+
+
+@needs_cv2
+def test_pyramid_and_scharr_vs_cv2():
+    import cv2
+    for w, h in ((640, 480), (333, 245)):
+        im = synth.make_frame(7, w, h)
+        for a, b in zip(R.build_pyramid_ref(im), R.build_pyramid_cv2(im)):
+            assert np.array_equal(a, b)
+        n, pyr = cv2.buildOpticalFlowPyramid(im, (9, 9), 3)
+        for l in range(4):
+            ix, iy = R.scharr_ref(R.build_pyramid_ref(im)[l])
+            assert np.array_equal(pyr[2 * l + 1][..., 0], ix) and np.array_equal(pyr[2 * l + 1][..., 1], iy)
+
+
+@needs_cv2
+def test_fast_and_circle_vs_cv2():
+    import cv2
+    im = synth.make_frame(8)
+    for th in (0, 1, 6, 10, 20):
+        for (x, y, cs) in ((0, 0, 50), (550, 400, 50), (35, 70, 35), (16, 32, 16)):
+            roi = np.ascontiguousarray(im[y:y + cs, x:x + cs])
+            assert R.fast_detect_ref(roi, th) == R.fast_detect_cv2(roi, th)
+    for r in range(1, 33):
+        m = np.ones((80, 80), np.float32)
+        cv2.circle(m, (40, 40), r, 0, -1)
+        m2 = np.ones((80, 80), np.float32)
+        R.paint_disc(m2, 40, 40, R.circle_halfwidths(r))
+        assert np.array_equal(m, m2), r
+
+
+@needs_cv2
+@pytest.mark.parametrize("cs", [50, 16])
+def test_grid_fast_vs_cv2(cs):
+    im = synth.make_frame(9)
+    rng = np.random.default_rng(cs)
+    k = (rng.random((40, 2)) * [640, 480]).astype(np.float32)
+    a = R.detect_grid_fast_nosubpix(im, cs, k, 10, True)
+    b = R.detect_grid_fast_nosubpix(im, cs, k, 10, False)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2]
+
+
+@needs_cv2
+def test_get_rect_subpix_and_subpix_vs_cv2():
+    import cv2
+    im = synth.make_frame(5)
+    h, w = im.shape
+    rng = np.random.default_rng(3)
+    for k in range(300):
+        cx = np.float32(rng.choice([rng.uniform(0, 7), rng.uniform(w - 8, w), rng.uniform(8, w - 8)]))
+        cy = np.float32(rng.choice([rng.uniform(0, 7), rng.uniform(h - 8, h), rng.uniform(8, h - 8)]))
+        ref = cv2.getRectSubPix(im, (9, 9), (float(cx), float(cy)), patchType=cv2.CV_32F)
+        assert np.array_equal(R._get_rect_subpix_9(im, cx, cy), ref), (cx, cy)
+    ipts, _, _ = R.detect_grid_fast_nosubpix(im, 16, np.zeros((0, 2)), 10, True)
+    extra = np.array([[3, 3], [636, 3], [3, 476], [636, 476], [1, 200], [638, 100], [320, 1], [300, 478]], np.int32)
+    p = np.concatenate([ipts[:150], extra]).astype(np.float32)
+    d = np.abs(R.corner_subpix_cv2(im, p) - R.corner_subpix_ref(im, p))
+    assert d.max() <= 1e-4, d.max()
+    assert (d == 0).mean() > 0.9
+
+
+@needs_cv2
+def test_descriptor_vs_cv2_and_kernel_constants():
+    import cv2
+    assert np.array_equal(cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel(), R.gauss7_kernel())
+    # the float32 constants hard-coded in ov2slam_b200/csrc/frontend_desc.cu
+    hexes = ["0x1.1f5f62p-4", "0x1.0c70fcp-3", "0x1.869472p-3", "0x1.ba95c0p-3"]
+    assert [float.fromhex(x) for x in hexes] == [float(v) for v in R.gauss7_kernel()[:4]]
+    bad = tot = 0
+    for seed, (w, h) in enumerate([(640, 480), (752, 480)]):
+        im = synth.make_frame(100 + seed, w, h)
+        rng = np.random.default_rng(seed)
+        pts = (rng.random((600, 2)) * [w, h]).astype(np.float32)
+        pts[:80] = np.floor(pts[:80]) + 0.5
+        pts[80:120, 0] = rng.uniform(29.5, 32.5, 40)
+        pts[120:160, 0] = rng.uniform(w - 32.5, w - 29.5, 40)
+        da, va = R.describe_cv2(im, pts)
+        db, vb = R.describe_ref(im, pts)
+        assert np.array_equal(va, vb)
+        bad += int(np.unpackbits(da ^ db).sum())
+        tot += int(va.sum()) * 256
+    assert bad == 0 and tot > 100000
+
+
+@needs_cv2
+def test_klt_vs_cv2():
+    prev, cur, flow = synth.make_pair(7)
+    rng = np.random.default_rng(0)
+    ipts, _, _ = R.detect_grid_fast_nosubpix(prev, 16, np.zeros((0, 2)), 10, True)
+    b = (rng.random((40, 2)) * [640, 480]).astype(np.float32)
+    b[:10, 0] = rng.uniform(0, 7, 10)
+    b[10:20, 0] = rng.uniform(632, 640, 10)
+    b[20:30, 1] = rng.uniform(0, 7, 10)
+    b[30:, 1] = rng.uniform(472, 480, 10)
+    kps = np.concatenate([R.corner_subpix_cv2(prev, ipts[:80].astype(np.float32)), b])
+    _, pri = synth.make_priors(7, kps, flow)
+    for lvl in (0, 1, 3):
+        ta, sa = R.fb_klt_cv2(prev, cur, kps, pri, 9, lvl)
+        tb, sb = R.fb_klt_ref(prev, cur, kps, pri, 9, lvl)
+        assert np.array_equal(sa, sb)
+        assert np.abs(ta - tb).max() <= 1e-3
