@@ -1,5 +1,753 @@
-// L: local bundle adjustment (placeholder until the solver lands; fails loudly, never falls back).
+// L: local bundle adjustment on the GPU (float64).
+//
+// Reference behaviour replaced: the solve sections of Optimizer::localBA
+// (/root/reference/src/optimizer.cpp:436-479, :492-594, :603-627, :637-735), i.e. Ceres 2.0's
+// TrustRegionMinimizer (trust_region_minimizer.cc:67-134) + LevenbergMarquardtStrategy
+// (levenberg_marquardt_strategy.cc:66-160) + Schur linear solver (schur_eliminator_impl.h:179-377)
+// on ReprojectionErrorKSE3AnchInvDepth residual blocks (src/ceres_parametrization.cpp:361-473)
+// with SE3LeftParameterization (se3left_parametrization.hpp:41-60) and HuberLoss(sqrt(5.9915)).
+//
+// Per LM iteration (device kernels, LM controller scalars on the host):
+//   ba_eval_kernel<true>   one thread per residual block: r, analytic Jacobians (anchor 2x6,
+//                          observer 2x6, inverse depth 2x1), robustified by sqrt(rho') (the
+//                          Corrector's alpha = 0 branch is the only one Huber reaches), cost
+//   ba_schur_kernel        one warp per landmark (observations are CSR by landmark): E'E (scalar),
+//                          E'r, F'F blocks, E'F rows, Schur complement and reduced rhs accumulated
+//                          into the (6 Ncv)^2 camera system with fp64 atomics (RED.ADD.F64)
+//   ba_reduced_solve_kernel one CTA: Jacobi scaling / LM damping of the camera diagonal, Cholesky
+//                          (U'U) in shared memory when it fits, two triangular solves, camera Plus
+//   ba_backsub_kernel      one warp per landmark: y_e, candidate inverse depth, model cost change
+//   ba_eval_kernel<false>  candidate cost (and the chi2 / depth flags the reference reads afterwards)
+// Jacobi scaling is applied algebraically (damping_i = clamp(s_i^2 c_i)/(radius s_i^2) on the
+// unscaled system), which is the same linear system Ceres solves after ScaleColumns.
 #include "ov2_common.cuh"
-extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem*, const ov2_ba_opts*, ov2_ba_result*, uint8_t*) {
-    return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: not built in this revision");
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_VAR_CAMS = 64;
+constexpr int MAX_N = 6 * MAX_VAR_CAMS;
+constexpr double SOPHUS_EPS = 1e-10;
+
+enum { SC_COST = 0, SC_CAND_COST, SC_MCC, SC_STEP2, SC_CANDX2, SC_GMAX_LM, SC_GMAX_CAM, SC_CHOL_FAIL, SC_NBAD, SC_COUNT = 16 };
+
+struct BaDev {
+    int ncam, npts, nobs, ncv, n;
+    double fx, fy, cx, cy;
+    double huber_a, huber_b;
+    int use_huber;
+    const uint8_t* pose_const;
+    const int32_t* lm_anchor_cam;
+    const double* lm_anchor_px;
+    const int32_t* obs_cam;
+    const int32_t* obs_lm;
+    const double* obs_px;
+    const int32_t* lm_ptr;
+    uint8_t* active;
+    int32_t* cam_slot;
+    uint8_t* cam_used;
+    double* Jr; double* Ja; double* Jo; double* Jl;
+    double* chi2; uint8_t* dpos;
+    double* cn_cam; double* sc_cam; double* sc_lm;
+    double* S; double* rhs; double* z; double* gcam;
+    double* ete; double* ge;
+    double* scal;
+    uint8_t* flags;
+};
+
+// ------------------------------------------------------------------ small SE3 helpers
+__device__ __forceinline__ void quat_to_rot(const double* q, double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+__device__ __forceinline__ void load_pose(const double* p, double t[3], double q[4]) {
+    t[0] = p[0]; t[1] = p[1]; t[2] = p[2];
+    const double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);  // SE3d(q, t) normalises
+    q[0] = p[3] / n; q[1] = p[4] / n; q[2] = p[5] / n; q[3] = p[6] / n;
+}
+
+// SE3LeftParameterization::Plus: out = Sophus::SE3d::exp(delta) * (q, t)
+__device__ void pose_plus(const double* pose, const double* d, double* out) {
+    double t[3], q[4];
+    load_pose(pose, t, q);
+    const double ox = d[3], oy = d[4], oz = d[5];
+    const double th2 = ox * ox + oy * oy + oz * oz;
+    double imag, real, theta;
+    if (th2 < SOPHUS_EPS * SOPHUS_EPS) {
+        theta = 0.0;
+        const double th4 = th2 * th2;
+        imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+        real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+    } else {
+        theta = sqrt(th2);
+        const double h = 0.5 * theta;
+        imag = sin(h) / theta;
+        real = cos(h);
+    }
+    const double e[4] = {imag * ox, imag * oy, imag * oz, real};
+    double Re[9];
+    quat_to_rot(e, Re);
+    double V[9];
+    if (theta < SOPHUS_EPS) {
+        for (int i = 0; i < 9; ++i) V[i] = Re[i];
+    } else {
+        const double a = (1.0 - cos(theta)) / th2;
+        const double b = (theta - sin(theta)) / (th2 * theta);
+        const double O[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+        double O2[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+        for (int i = 0; i < 9; ++i) V[i] = a * O[i] + b * O2[i];
+        V[0] += 1.0; V[4] += 1.0; V[8] += 1.0;
+    }
+    const double et[3] = {V[0] * d[0] + V[1] * d[1] + V[2] * d[2], V[3] * d[0] + V[4] * d[1] + V[5] * d[2],
+                          V[6] * d[0] + V[7] * d[1] + V[8] * d[2]};
+    // quaternion product (so3.hpp:338-342), then normalisation
+    double r[4];
+    r[3] = e[3] * q[3] - e[0] * q[0] - e[1] * q[1] - e[2] * q[2];
+    r[0] = e[3] * q[0] + e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
+    r[1] = e[3] * q[1] + e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
+    r[2] = e[3] * q[2] + e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
+    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    out[0] = et[0] + Re[0] * t[0] + Re[1] * t[1] + Re[2] * t[2];
+    out[1] = et[1] + Re[3] * t[0] + Re[4] * t[1] + Re[5] * t[2];
+    out[2] = et[2] + Re[6] * t[0] + Re[7] * t[1] + Re[8] * t[2];
+    out[3] = r[0] / n; out[4] = r[1] / n; out[5] = r[2] / n; out[6] = r[3] / n;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+    // for non-negative doubles the bit pattern orders like an unsigned integer
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------ residual blocks
+template <bool JAC>
+__global__ void __launch_bounds__(128) ba_eval_kernel(BaDev D, const double* __restrict__ pose,
+                                                      const double* __restrict__ invd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (i < D.nobs && D.active[i]) {
+        const int lm = D.obs_lm[i];
+        const int ca = D.lm_anchor_cam[lm], co = D.obs_cam[i];
+        double ta[3], qa[4], to[3], qo[4], Rwa[9], Rwc[9];
+        load_pose(pose + 7 * ca, ta, qa);
+        load_pose(pose + 7 * co, to, qo);
+        quat_to_rot(qa, Rwa);
+        quat_to_rot(qo, Rwc);
+        const double zanch = 1.0 / invd[lm];
+        const double bx = (D.lm_anchor_px[2 * lm] - D.cx) / D.fx, by = (D.lm_anchor_px[2 * lm + 1] - D.cy) / D.fy;
+        const double ap[3] = {zanch * bx, zanch * by, zanch};
+        const double rp[3] = {Rwa[0] * ap[0] + Rwa[1] * ap[1] + Rwa[2] * ap[2], Rwa[3] * ap[0] + Rwa[4] * ap[1] + Rwa[5] * ap[2],
+                              Rwa[6] * ap[0] + Rwa[7] * ap[1] + Rwa[8] * ap[2]};  // Rwanch * anchpt
+        const double wp[3] = {rp[0] + ta[0], rp[1] + ta[1], rp[2] + ta[2]};
+        const double dv[3] = {wp[0] - to[0], wp[1] - to[1], wp[2] - to[2]};
+        // Rcw = Rwc^T
+        const double lc[3] = {Rwc[0] * dv[0] + Rwc[3] * dv[1] + Rwc[6] * dv[2], Rwc[1] * dv[0] + Rwc[4] * dv[1] + Rwc[7] * dv[2],
+                              Rwc[2] * dv[0] + Rwc[5] * dv[1] + Rwc[8] * dv[2]};
+        const double linvz = 1.0 / lc[2];
+        double r0 = D.fx * lc[0] * linvz + D.cx - D.obs_px[2 * i];
+        double r1 = D.fy * lc[1] * linvz + D.cy - D.obs_px[2 * i + 1];
+        const double s = r0 * r0 + r1 * r1;
+        D.chi2[i] = s;
+        D.dpos[i] = lc[2] > 0.0 ? 1 : 0;
+        double w = 1.0;
+        if (D.use_huber && s > D.huber_b) {
+            const double rs = sqrt(s);
+            const double rho1 = fmax(DBL_MIN, D.huber_a / rs);
+            cost = 0.5 * (2.0 * D.huber_a * rs - D.huber_b);
+            w = sqrt(rho1);
+        } else {
+            cost = 0.5 * s;
+        }
+        if (JAC) {
+            const double linvz2 = linvz * linvz;
+            const double jc[6] = {linvz * D.fx, 0.0, -lc[0] * linvz2 * D.fx, 0.0, linvz * D.fy, -lc[1] * linvz2 * D.fy};
+            double JR[6];  // J_lcam * Rcw  (2x3)
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 3; ++b)
+                    JR[3 * a + b] = jc[3 * a] * Rwc[3 * b] + jc[3 * a + 1] * Rwc[3 * b + 1] + jc[3 * a + 2] * Rwc[3 * b + 2];  // Rcw = Rwc^T
+            // JR * hat(wpt)
+            double JS[6];
+            for (int a = 0; a < 2; ++a) {
+                const double j0 = JR[3 * a], j1 = JR[3 * a + 1], j2 = JR[3 * a + 2];
+                JS[3 * a] = j1 * wp[2] - j2 * wp[1];
+                JS[3 * a + 1] = j2 * wp[0] - j0 * wp[2];
+                JS[3 * a + 2] = j0 * wp[1] - j1 * wp[0];
+            }
+            double* Ja = D.Ja + 12 * (size_t)i;
+            double* Jo = D.Jo + 12 * (size_t)i;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 3; ++b) {
+                    Ja[6 * a + b] = w * JR[3 * a + b];
+                    Ja[6 * a + 3 + b] = -w * JS[3 * a + b];
+                    Jo[6 * a + b] = -w * JR[3 * a + b];
+                    Jo[6 * a + 3 + b] = w * JS[3 * a + b];
+                }
+            // J_lambda = -zanch * Rwanch * anchpt
+            const double jl[3] = {-zanch * rp[0], -zanch * rp[1], -zanch * rp[2]};
+            D.Jl[2 * (size_t)i] = w * (JR[0] * jl[0] + JR[1] * jl[1] + JR[2] * jl[2]);
+            D.Jl[2 * (size_t)i + 1] = w * (JR[3] * jl[0] + JR[4] * jl[1] + JR[5] * jl[2]);
+            D.Jr[2 * (size_t)i] = w * r0;
+            D.Jr[2 * (size_t)i + 1] = w * r1;
+        }
+    }
+    cost = warp_sum(cost);
+    if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(D.scal + (JAC ? SC_COST : SC_CAND_COST), cost);
+}
+
+// ------------------------------------------------------------------ Schur elimination (warp / landmark)
+constexpr int SCHUR_WARPS = 4;
+
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, double radius, int first_iter) {
+    __shared__ double s_etf[SCHUR_WARPS][MAX_VAR_CAMS + 1][6];
+    __shared__ int s_slot[SCHUR_WARPS][MAX_VAR_CAMS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.x * SCHUR_WARPS + warp;
+    if (l >= D.npts) return;
+    const int p0 = D.lm_ptr[l], p1 = D.lm_ptr[l + 1];
+    const int n = D.n;
+    // E'E, E'r
+    double cnl = 0.0, ge = 0.0;
+    int nact = 0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!D.active[p]) continue;
+        const double a = D.Jl[2 * (size_t)p], b = D.Jl[2 * (size_t)p + 1];
+        cnl += a * a + b * b;
+        ge += a * D.Jr[2 * (size_t)p] + b * D.Jr[2 * (size_t)p + 1];
+        nact++;
+    }
+    cnl = warp_sum(cnl);
+    ge = warp_sum(ge);
+    nact = __reduce_add_sync(FULL, nact);
+    if (nact == 0) {   // unused parameter block: dropped from the program (program.cc:305-387)
+        if (lane == 0) { D.ete[l] = 0.0; D.ge[l] = 0.0; }
+        return;
+    }
+    double sc = D.sc_lm[l];
+    if (first_iter) {
+        sc = 1.0 / (1.0 + sqrt(cnl));
+        if (lane == 0) D.sc_lm[l] = sc;
+    }
+    const double diag = fmin(fmax(cnl * sc * sc, 1e-6), 1e32);
+    const double ete = cnl + diag / (radius * sc * sc);
+    const double inv_ete = 1.0 / ete;
+    if (lane == 0) {
+        D.ete[l] = ete;
+        D.ge[l] = ge;
+        atomic_max_pos(D.scal + SC_GMAX_LM, fabs(ge));
+    }
+    // touching variable cameras: entry 0 = anchor, then one per active observation
+    const int sa = D.cam_slot[D.lm_anchor_cam[l]];
+    int m = 0;   // number of entries (uniform across the warp)
+    if (sa >= 0) {
+        if (lane < 6) s_etf[warp][0][lane] = 0.0;
+        if (lane == 0) s_slot[warp][0] = sa;
+        m = 1;
+    }
+    __syncwarp();
+    // per observation (serial over the landmark's observations, lanes over matrix entries)
+    for (int p = p0; p < p1; ++p) {
+        if (!D.active[p]) continue;
+        const int so = D.cam_slot[D.obs_cam[p]];
+        const double* Ja = D.Ja + 12 * (size_t)p;
+        const double* Jo = D.Jo + 12 * (size_t)p;
+        const double jl0 = D.Jl[2 * (size_t)p], jl1 = D.Jl[2 * (size_t)p + 1];
+        const double r0 = D.Jr[2 * (size_t)p], r1 = D.Jr[2 * (size_t)p + 1];
+        if (sa >= 0) {
+            // anchor block: F'F (upper triangle of the 6x6), F'r, column norms, E'F
+            for (int e = lane; e < 36; e += 32) {
+                const int a = e / 6, b = e - 6 * a;
+                if (a <= b) atomicAdd(D.S + (size_t)(6 * sa + a) * n + 6 * sa + b, Ja[a] * Ja[b] + Ja[6 + a] * Ja[6 + b]);
+            }
+            if (lane < 6) {
+                atomicAdd(D.gcam + 6 * sa + lane, Ja[lane] * r0 + Ja[6 + lane] * r1);
+                atomicAdd(D.cn_cam + 6 * sa + lane, Ja[lane] * Ja[lane] + Ja[6 + lane] * Ja[6 + lane]);
+                s_etf[warp][0][lane] += jl0 * Ja[lane] + jl1 * Ja[6 + lane];
+            }
+        }
+        if (so >= 0) {
+            for (int e = lane; e < 36; e += 32) {
+                const int a = e / 6, b = e - 6 * a;
+                if (a <= b) atomicAdd(D.S + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
+            }
+            if (lane < 6) {
+                atomicAdd(D.gcam + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
+                atomicAdd(D.cn_cam + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
+                s_etf[warp][m][lane] = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
+            }
+            if (lane == 0) s_slot[warp][m] = so;
+            if (sa >= 0) {
+                // cross block Ja' Jo into the upper block (min slot, max slot)
+                for (int e = lane; e < 36; e += 32) {
+                    const int a = e / 6, b = e - 6 * a;   // a: anchor column, b: observer column
+                    const double v = Ja[a] * Jo[b] + Ja[6 + a] * Jo[6 + b];
+                    if (sa < so) atomicAdd(D.S + (size_t)(6 * sa + a) * n + 6 * so + b, v);
+                    else atomicAdd(D.S + (size_t)(6 * so + b) * n + 6 * sa + a, v);
+                }
+            }
+            m++;
+        }
+        __syncwarp();
+    }
+    // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i = F'r - EtF_i ge / ete
+    const int npair = m * m;
+    for (int e = lane; e < npair * 36; e += 32) {
+        const int pr = e / 36, q = e - 36 * pr;
+        const int i = pr / m, j = pr - m * i;
+        const int si = s_slot[warp][i], sj = s_slot[warp][j];
+        if (si > sj || (si == sj && i > j)) continue;   // upper block triangle; (i,i) once
+        const int a = q / 6, b = q - 6 * a;
+        if (si == sj && a > b) continue;
+        double v = s_etf[warp][i][a] * s_etf[warp][j][b] * inv_ete;
+        if (si == sj && i != j) {
+            // cannot happen (a camera observes a landmark once, and the anchor is never an observer)
+            v *= 2.0;
+        }
+        atomicAdd(D.S + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
+    }
+    for (int e = lane; e < m * 6; e += 32) {
+        const int i = e / 6, a = e - 6 * i;
+        atomicAdd(D.rhs + 6 * s_slot[warp][i] + a, -s_etf[warp][i][a] * ge * inv_ete);
+    }
+}
+
+// ------------------------------------------------------------------ reduced camera system (one CTA)
+__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int use_smem,
+                                                                const double* __restrict__ pose, double* __restrict__ cand) {
+    extern __shared__ double sA[];
+    __shared__ double s_piv;
+    __shared__ int s_fail;
+    const int n = D.n, tid = threadIdx.x, nt = blockDim.x;
+    double* A = use_smem ? sA : D.S;
+    double* w = D.z;   // solution vector (global, n doubles)
+    if (tid == 0) s_fail = 0;
+    // Jacobi scaling (iteration 0), LM damping, rhs = F'r - (Schur part already accumulated)
+    for (int i = tid; i < n; i += nt) {
+        const double cn = D.cn_cam[i];
+        double sc = D.sc_cam[i];
+        if (first_iter) {
+            sc = 1.0 / (1.0 + sqrt(cn));
+            D.sc_cam[i] = sc;
+        }
+        const double diag = fmin(fmax(cn * sc * sc, 1e-6), 1e32);
+        D.S[(size_t)i * n + i] += diag / (radius * sc * sc);
+        w[i] = D.gcam[i] + D.rhs[i];
+    }
+    __syncthreads();
+    if (use_smem) {
+        for (int e = tid; e < n * n; e += nt) sA[e] = D.S[e];
+        __syncthreads();
+    }
+    // Cholesky A = U'U on the upper triangle, right-looking
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            const double d = A[(size_t)j * n + j];
+            if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; s_piv = 1.0; }
+            else s_piv = sqrt(d);
+        }
+        __syncthreads();
+        if (s_fail) break;
+        const double piv = s_piv;
+        for (int c = j + tid; c < n; c += nt) A[(size_t)j * n + c] = (c == j) ? piv : A[(size_t)j * n + c] / piv;
+        __syncthreads();
+        const int rem = n - j - 1;
+        // trailing update A[r][c] -= U[j][r] U[j][c] for j < r <= c
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int rr = e / rem, cc = e - rr * rem;
+            if (cc < rr) continue;
+            const int r = j + 1 + rr, c = j + 1 + cc;
+            A[(size_t)r * n + c] -= A[(size_t)j * n + r] * A[(size_t)j * n + c];
+        }
+        __syncthreads();
+    }
+    if (s_fail) {
+        if (tid == 0) D.scal[SC_CHOL_FAIL] = 1.0;
+        return;
+    }
+    // forward: U' y = b   (column-oriented: after fixing y_j subtract U[j][c] y_j from b_c)
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) w[j] = w[j] / A[(size_t)j * n + j];
+        __syncthreads();
+        const double yj = w[j];
+        for (int c = j + 1 + tid; c < n; c += nt) w[c] -= A[(size_t)j * n + c] * yj;
+        __syncthreads();
+    }
+    // backward: U z = y
+    for (int j = n - 1; j >= 0; --j) {
+        if (tid == 0) w[j] = w[j] / A[(size_t)j * n + j];
+        __syncthreads();
+        const double zj = w[j];
+        for (int r = tid; r < j; r += nt) w[r] -= A[(size_t)r * n + j] * zj;
+        __syncthreads();
+    }
+    // candidate camera poses: Plus(x, delta), delta = -z ; step / candidate norms ; gradient max norm
+    double st2 = 0.0, cx2 = 0.0, gm = 0.0;
+    for (int c = tid; c < D.ncam; c += nt) {
+        const int s = D.cam_slot[c];
+        if (s < 0) continue;
+        double d[6], g[6], out[7], pg[7];
+        for (int k = 0; k < 6; ++k) { d[k] = -w[6 * s + k]; g[k] = -D.gcam[6 * s + k]; }
+        pose_plus(pose + 7 * c, d, out);
+        pose_plus(pose + 7 * c, g, pg);
+        for (int k = 0; k < 7; ++k) {
+            cand[7 * c + k] = out[k];
+            const double df = pose[7 * c + k] - out[k];
+            st2 += df * df;
+            cx2 += out[k] * out[k];
+            gm = fmax(gm, fabs(pose[7 * c + k] - pg[k]));
+        }
+    }
+    st2 = warp_sum(st2);
+    cx2 = warp_sum(cx2);
+    for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(FULL, gm, o));
+    if ((tid & 31) == 0) {
+        if (st2 != 0.0) atomicAdd(D.scal + SC_STEP2, st2);
+        if (cx2 != 0.0) atomicAdd(D.scal + SC_CANDX2, cx2);
+        atomic_max_pos(D.scal + SC_GMAX_CAM, gm);
+    }
+}
+
+// ------------------------------------------------------------------ back-substitution (warp / landmark)
+__global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* __restrict__ invd, double* __restrict__ cand_invd) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.x * 4 + warp;
+    if (l >= D.npts) return;
+    const double ete = D.ete[l];
+    if (ete == 0.0) return;   // landmark not in the program: candidate stays equal
+    const int p0 = D.lm_ptr[l], p1 = D.lm_ptr[l + 1];
+    const int sa = D.cam_slot[D.lm_anchor_cam[l]];
+    double za[6] = {0, 0, 0, 0, 0, 0};
+    if (sa >= 0)
+        for (int k = 0; k < 6; ++k) za[k] = D.z[6 * sa + k];
+    // y_e = (E'r - sum_obs Jl' (Ja z_a + Jo z_o)) / ete
+    double acc = 0.0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!D.active[p]) continue;
+        const int so = D.cam_slot[D.obs_cam[p]];
+        const double* Ja = D.Ja + 12 * (size_t)p;
+        const double* Jo = D.Jo + 12 * (size_t)p;
+        double f0 = 0.0, f1 = 0.0;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 += Ja[k] * za[k]; f1 += Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = D.z[6 * so + k]; f0 += Jo[k] * zk; f1 += Jo[6 + k] * zk; }
+        acc += D.Jl[2 * (size_t)p] * f0 + D.Jl[2 * (size_t)p + 1] * f1;
+    }
+    acc = warp_sum(acc);
+    const double y = (D.ge[l] - acc) / ete;
+    const double dl = -y;
+    const double cl = invd[l] + dl;
+    // model cost change: -(J delta)'(r + J delta / 2), delta = -[z; y]
+    double mcc = 0.0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!D.active[p]) continue;
+        const int so = D.cam_slot[D.obs_cam[p]];
+        const double* Ja = D.Ja + 12 * (size_t)p;
+        const double* Jo = D.Jo + 12 * (size_t)p;
+        double f0 = D.Jl[2 * (size_t)p] * dl, f1 = D.Jl[2 * (size_t)p + 1] * dl;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 -= Ja[k] * za[k]; f1 -= Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = D.z[6 * so + k]; f0 -= Jo[k] * zk; f1 -= Jo[6 + k] * zk; }
+        mcc -= f0 * (D.Jr[2 * (size_t)p] + 0.5 * f0) + f1 * (D.Jr[2 * (size_t)p + 1] + 0.5 * f1);
+    }
+    mcc = warp_sum(mcc);
+    if (lane == 0) {
+        cand_invd[l] = cl;
+        atomicAdd(D.scal + SC_MCC, mcc);
+        atomicAdd(D.scal + SC_STEP2, dl * dl);
+        atomicAdd(D.scal + SC_CANDX2, cl * cl);
+    }
+}
+
+// ------------------------------------------------------------------ outlier scan (optimizer.cpp:500-530)
+__global__ void ba_flag_kernel(BaDev D, double th, int bit, int deactivate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (i < D.nobs && D.active[i]) {
+        bad = (D.chi2[i] > th) || !D.dpos[i];
+        if (bad) {
+            D.flags[i] |= (uint8_t)bit;
+            if (deactivate) D.active[i] = 0;   // problem.RemoveResidualBlock
+        }
+    }
+    const int nb = __reduce_add_sync(FULL, bad);
+    if ((threadIdx.x & 31) == 0 && nb) atomicAdd(D.scal + SC_NBAD, (double)nb);
+}
+
+__global__ void ba_cam_used_kernel(BaDev D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D.nobs && D.active[i]) {
+        D.cam_used[D.obs_cam[i]] = 1;
+        D.cam_used[D.lm_anchor_cam[D.obs_lm[i]]] = 1;
+    }
+}
+
+struct Summary { int iterations; double initial_cost, final_cost; int termination; };
+
+}  // namespace
+
+// One ceres::Solve on the currently active residual blocks.
+static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*& cand_pose, double*& invd,
+                                 double*& cand_invd, int max_iters, double function_tolerance, Summary* out) {
+    cudaStream_t st = ctx->stream;
+    const int nobs = D.nobs;
+    // Program::RemoveFixedBlocks: cameras that are constant or touch no active residual drop out
+    OV2_CUDA(ctx, cudaMemsetAsync(D.cam_used, 0, D.ncam, st));
+    OV2_LAUNCH(ctx, "ba_cam_used_kernel", ba_cam_used_kernel<<<div_up(nobs, 256), 256, 0, st>>>(D));
+    std::vector<uint8_t> used(D.ncam), cst(D.ncam);
+    OV2_CUDA(ctx, cudaMemcpyAsync(used.data(), D.cam_used, D.ncam, cudaMemcpyDeviceToHost, st));
+    OV2_CUDA(ctx, cudaMemcpyAsync(cst.data(), D.pose_const, D.ncam, cudaMemcpyDeviceToHost, st));
+    OV2_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<int32_t> slot(D.ncam, -1);
+    int ncv = 0;
+    bool any = false;
+    for (int c = 0; c < D.ncam; ++c) {
+        any = any || used[c];
+        if (used[c] && !cst[c]) slot[c] = ncv++;
+    }
+    out->iterations = 0;
+    out->initial_cost = out->final_cost = 0.0;
+    out->termination = 0;
+    if (!any) return OV2_OK;   // no residual blocks
+    if (ncv > MAX_VAR_CAMS) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: more than 64 optimised keyframes");
+    D.ncv = ncv;
+    D.n = 6 * ncv;
+    const int n = D.n;
+    OV2_CUDA(ctx, cudaMemcpyAsync(D.cam_slot, slot.data(), sizeof(int32_t) * D.ncam, cudaMemcpyHostToDevice, st));
+    const size_t smem_need = (size_t)n * n * sizeof(double);
+    const int use_smem = smem_need <= 200 * 1024 ? 1 : 0;
+    if (use_smem && smem_need > 48 * 1024)
+        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+
+    // candidate buffers start equal to x: parameter blocks that are not in this solve's program
+    // (constant / unused) must keep their current value through pointer swaps
+    OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
+    OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, invd, sizeof(double) * D.npts, cudaMemcpyDeviceToDevice, st));
+    double h[SC_COUNT];
+    auto eval_jac = [&]() -> ov2_status {
+        OV2_CUDA(ctx, cudaMemsetAsync(D.scal, 0, sizeof(double) * SC_COUNT, st));
+        OV2_LAUNCH(ctx, "ba_eval_kernel<jac>", ba_eval_kernel<true><<<div_up(nobs, 128), 128, 0, st>>>(D, pose, invd));
+        return OV2_OK;
+    };
+    ov2_status s = eval_jac();
+    if (s != OV2_OK) return s;
+    double x_cost = 0.0, minimum_cost = DBL_MAX, xnorm = -1.0, gmax = DBL_MAX;
+    double radius = 1e4, decrease_factor = 2.0;
+    bool step_successful = true, have_cost = false;
+    int iteration = 0, num_invalid = 0, first_iter = 1;
+    bool need_system = true;   // S / rhs must be (re)assembled for the current J
+    for (;;) {
+        if (need_system && !have_cost) {
+            // cost of the Jacobian evaluation is needed before the controller can continue
+            OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+            OV2_CUDA(ctx, cudaStreamSynchronize(st));
+            x_cost = h[SC_COST];
+            have_cost = true;
+            if (iteration == 0) out->initial_cost = x_cost;
+        }
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (step_successful && x_cost < minimum_cost) minimum_cost = x_cost;
+        if (iteration >= max_iters) { out->termination = 1; break; }
+        if (radius <= 1e-32) { out->termination = 0; break; }
+        iteration++;
+        // ---- ComputeTrustRegionStep
+        OV2_CUDA(ctx, cudaMemsetAsync(D.S, 0, sizeof(double) * (size_t)n * n, st));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.rhs, 0, sizeof(double) * n, st));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.gcam, 0, sizeof(double) * n, st));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.cn_cam, 0, sizeof(double) * n, st));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_CAND_COST, 0, sizeof(double) * (SC_COUNT - 1), st));
+        OV2_LAUNCH(ctx, "ba_schur_kernel", ba_schur_kernel<<<div_up(D.npts, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(D, radius, first_iter));
+        OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
+                   ba_reduced_solve_kernel<<<1, 1024, use_smem ? smem_need : 0, st>>>(D, radius, first_iter, use_smem, pose, cand_pose));
+        OV2_LAUNCH(ctx, "ba_backsub_kernel", ba_backsub_kernel<<<div_up(D.npts, 4), 128, 0, st>>>(D, invd, cand_invd));
+        OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<div_up(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
+        first_iter = 0;
+        OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        OV2_CUDA(ctx, cudaStreamSynchronize(st));
+        if (iteration == 1 || step_successful) {
+            // GradientToleranceReached() for the point this system was assembled at (its gradient
+            // F'r / E'r is a by-product of the Schur pass): Ceres would have stopped before this
+            // iteration, so the iteration does not count.
+            gmax = fmax(h[SC_GMAX_LM], h[SC_GMAX_CAM]);
+            if (gmax <= 1e-10) { out->termination = 0; iteration--; break; }
+        }
+        const double model_cost_change = h[SC_MCC];
+        double cand_cost = h[SC_CAND_COST];
+        if (getenv("OV2_BA_DEBUG"))
+            fprintf(stderr, "[ba] it %d x_cost %.10g cand %.10g mcc %.10g radius %.4g step %.6g gmax %.4g chol_fail %g ncv %d\n",
+                    iteration, x_cost, cand_cost, model_cost_change, radius, sqrt(h[SC_STEP2]), gmax, h[SC_CHOL_FAIL], D.ncv);
+        bool step_valid = h[SC_CHOL_FAIL] == 0.0 && isfinite(model_cost_change) && model_cost_change > 0.0;
+        if (!step_valid) {
+            // HandleInvalidStep
+            if (++num_invalid >= 5) { out->termination = 2; break; }
+            radius /= decrease_factor;
+            decrease_factor *= 2.0;
+            step_successful = false;
+            need_system = false;
+            continue;
+        }
+        num_invalid = 0;
+        if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
+        // ---- ParameterToleranceReached / FunctionToleranceReached (candidate NOT adopted on exit)
+        const double step_norm = sqrt(h[SC_STEP2]);
+        if (step_norm <= 1e-8 * (xnorm + 1e-8)) { out->termination = 0; break; }
+        const double cost_change = x_cost - cand_cost;
+        if (fabs(cost_change) <= function_tolerance * x_cost) { out->termination = 0; break; }
+        // ---- IsStepSuccessful
+        const double rel = cand_cost >= DBL_MAX ? -DBL_MAX : cost_change / model_cost_change;
+        if (rel > 1e-3) {
+            // HandleSuccessfulStep: x = candidate, re-evaluate residuals + Jacobians there
+            double* t = pose; pose = cand_pose; cand_pose = t;
+            t = invd; invd = cand_invd; cand_invd = t;
+            xnorm = sqrt(h[SC_CANDX2]);
+            // keep the non-variable entries of the new candidate buffers identical to x
+            OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
+            OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, invd, sizeof(double) * D.npts, cudaMemcpyDeviceToDevice, st));
+            if ((s = eval_jac()) != OV2_OK) return s;
+            have_cost = false;
+            need_system = true;
+            step_successful = true;
+            radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3));
+            radius = fmin(1e16, radius);
+            decrease_factor = 2.0;
+        } else {
+            step_successful = false;
+            radius /= decrease_factor;
+            decrease_factor *= 2.0;
+            need_system = false;
+        }
+    }
+    out->iterations = iteration;
+    out->final_cost = minimum_cost < DBL_MAX ? minimum_cost : x_cost;
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                        ov2_ba_result* res, uint8_t* outlier_out) {
+    if (!ctx || !pb || !opts || !res || pb->ncam <= 0 || pb->npts <= 0 || pb->nobs < 0)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: bad arguments");
+    memset(res, 0, sizeof(*res));
+    if (pb->nobs == 0) return OV2_OK;
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    const int ncam = pb->ncam, npts = pb->npts, nobs = pb->nobs;
+    // host-side: K, CSR pointers (observations must be sorted by landmark)
+    double Kh[4];
+    std::vector<int32_t> obs_lm_h(nobs), lm_ptr(npts + 1, 0);
+    if (ov2_is_device_ptr(pb->K)) OV2_CUDA(ctx, cudaMemcpy(Kh, pb->K, sizeof(Kh), cudaMemcpyDeviceToHost));
+    else memcpy(Kh, pb->K, sizeof(Kh));
+    if (ov2_is_device_ptr(pb->obs_lm)) OV2_CUDA(ctx, cudaMemcpy(obs_lm_h.data(), pb->obs_lm, sizeof(int32_t) * nobs, cudaMemcpyDeviceToHost));
+    else memcpy(obs_lm_h.data(), pb->obs_lm, sizeof(int32_t) * nobs);
+    for (int i = 0; i < nobs; ++i) {
+        const int l = obs_lm_h[i];
+        if (l < 0 || l >= npts || (i > 0 && l < obs_lm_h[i - 1]))
+            return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_lm must be sorted ascending and in range");
+        lm_ptr[l + 1]++;
+    }
+    for (int l = 0; l < npts; ++l) lm_ptr[l + 1] += lm_ptr[l];
+
+    BaDev D;
+    memset(&D, 0, sizeof(D));
+    D.ncam = ncam; D.npts = npts; D.nobs = nobs;
+    D.fx = Kh[0]; D.fy = Kh[1]; D.cx = Kh[2]; D.cy = Kh[3];
+    const float th_f = (float)opts->huber_th;                 // const float mono_th (optimizer.cpp:47)
+    D.huber_a = (double)sqrtf(th_f);                          // HuberLoss(std::sqrt(mono_th))
+    D.huber_b = D.huber_a * D.huber_a;
+    D.use_huber = opts->use_robust ? 1 : 0;
+    const void* d = nullptr;
+    void* o = nullptr;
+#define IN(field, bytes) do { if ((st = ov2_stage_in(ctx, pb->field, (bytes), &d)) != OV2_OK) return st; } while (0)
+    IN(pose_const, (size_t)ncam); D.pose_const = (const uint8_t*)d;
+    IN(lm_anchor_cam, sizeof(int32_t) * (size_t)npts); D.lm_anchor_cam = (const int32_t*)d;
+    IN(lm_anchor_px, sizeof(double) * 2 * (size_t)npts); D.lm_anchor_px = (const double*)d;
+    IN(obs_cam, sizeof(int32_t) * (size_t)nobs); D.obs_cam = (const int32_t*)d;
+    IN(obs_lm, sizeof(int32_t) * (size_t)nobs); D.obs_lm = (const int32_t*)d;
+    IN(obs_px, sizeof(double) * 2 * (size_t)nobs); D.obs_px = (const double*)d;
+#undef IN
+    double *pose = nullptr, *cand_pose = nullptr, *invd = nullptr, *cand_invd = nullptr;
+#define SCR(ptr, type, count) do { if ((st = ov2_scratch(ctx, sizeof(type) * (size_t)(count), &o)) != OV2_OK) return st; ptr = (type*)o; } while (0)
+    SCR(pose, double, 7 * ncam); SCR(cand_pose, double, 7 * ncam);
+    SCR(invd, double, npts); SCR(cand_invd, double, npts);
+    int32_t* d_lmptr = nullptr;
+    SCR(d_lmptr, int32_t, npts + 1);
+    SCR(D.active, uint8_t, nobs); SCR(D.cam_slot, int32_t, ncam); SCR(D.cam_used, uint8_t, ncam);
+    SCR(D.Jr, double, 2 * (size_t)nobs); SCR(D.Ja, double, 12 * (size_t)nobs); SCR(D.Jo, double, 12 * (size_t)nobs);
+    SCR(D.Jl, double, 2 * (size_t)nobs); SCR(D.chi2, double, nobs); SCR(D.dpos, uint8_t, nobs);
+    SCR(D.cn_cam, double, MAX_N); SCR(D.sc_cam, double, MAX_N); SCR(D.sc_lm, double, npts);
+    SCR(D.S, double, (size_t)MAX_N * MAX_N); SCR(D.rhs, double, MAX_N); SCR(D.z, double, MAX_N); SCR(D.gcam, double, MAX_N);
+    SCR(D.ete, double, npts); SCR(D.ge, double, npts); SCR(D.scal, double, SC_COUNT); SCR(D.flags, uint8_t, nobs);
+#undef SCR
+    D.lm_ptr = d_lmptr;
+    cudaStream_t s = ctx->stream;
+    OV2_CUDA(ctx, cudaMemcpyAsync(d_lmptr, lm_ptr.data(), sizeof(int32_t) * (npts + 1), cudaMemcpyHostToDevice, s));
+    const cudaMemcpyKind kp = ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind ki = ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    OV2_CUDA(ctx, cudaMemcpyAsync(pose, pb->pose, sizeof(double) * 7 * ncam, kp, s));
+    OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pb->pose, sizeof(double) * 7 * ncam, kp, s));
+    OV2_CUDA(ctx, cudaMemcpyAsync(invd, pb->lm_invdepth, sizeof(double) * npts, ki, s));
+    OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, pb->lm_invdepth, sizeof(double) * npts, ki, s));
+    OV2_CUDA(ctx, cudaMemsetAsync(D.active, 1, nobs, s));
+    OV2_CUDA(ctx, cudaMemsetAsync(D.flags, 0, nobs, s));
+    OV2_CUDA(ctx, cudaMemsetAsync(D.sc_lm, 0, sizeof(double) * npts, s));
+    OV2_CUDA(ctx, cudaMemsetAsync(D.sc_cam, 0, sizeof(double) * MAX_N, s));
+
+    Summary s1, s2;
+    if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_robust, opts->function_tolerance, &s1)) != OV2_OK)
+        return st;
+    // outlier scan on the values the LAST Evaluate() left behind (optimizer.cpp:500-530)
+    double h[SC_COUNT];
+    OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, sizeof(double), s));
+    const int deact = opts->apply_l2_after_robust ? 1 : 0;
+    OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 1, deact));
+    OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
+    OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    res->iters_robust = s1.iterations;
+    res->initial_cost = s1.initial_cost;
+    res->final_cost = s1.final_cost;
+    res->termination = s1.termination;
+    res->n_outliers_first = (int)h[SC_NBAD];
+    if (opts->apply_l2_after_robust && opts->use_robust && res->n_outliers_first > 0) {
+        // mono windows keep the Huber loss in the refinement (optimizer.cpp:606-608)
+        if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_refine, opts->function_tolerance, &s2)) != OV2_OK)
+            return st;
+        OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, sizeof(double), s));
+        OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 2, 0));
+        OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
+        OV2_CUDA(ctx, cudaStreamSynchronize(s));
+        res->iters_refine = s2.iterations;
+        res->initial_cost = s2.initial_cost;
+        res->final_cost = s2.final_cost;
+        res->termination = s2.termination;
+        res->n_outliers_second = (int)h[SC_NBAD];
+    }
+    // write-back of the states (the map update itself, optimizer.cpp:741-897, stays on the host)
+    OV2_CUDA(ctx, cudaMemcpyAsync(pb->pose, pose, sizeof(double) * 7 * ncam,
+                                  ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    OV2_CUDA(ctx, cudaMemcpyAsync(pb->lm_invdepth, invd, sizeof(double) * npts,
+                                  ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (outlier_out)
+        OV2_CUDA(ctx, cudaMemcpyAsync(outlier_out, D.flags, nobs,
+                                      ov2_is_device_ptr(outlier_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    if (res->termination == 2) return ov2_fail(ctx, OV2_ERR_NUMERIC, "ov2_localba_solve: 5 consecutive invalid steps");
+    return OV2_OK;
 }
