@@ -279,20 +279,50 @@ class Workload:
         self.fe.describe_brief(self.pyr_cur_d, self.d_pri, self.d_desc_t, self.d_val_t, n=n, per_frame=NKP)
         self.fe.describe_brief(self.pyr_cur_d, self.d_new, self.d_desc_n, self.d_val_n, n=B * self.ncell, per_frame=self.ncell)
 
+    # ---- end-to-end arm: the batch is cut into chunks, each chunk goes through the same C-ABI calls
+    # with HOST pointers on its own context (= its own stream) from its own host thread, so the
+    # H2D/D2H copies of one chunk overlap the kernels of another (the reference itself runs its
+    # front-end and mapper in separate threads; one ov2_ctx per thread is the documented usage).
+    def init_e2e(self, nchunks: int):
+        import concurrent.futures as cf
+        api, torch = self.api, self.torch
+        self.nchunks = nchunks
+        self.cs = self.B // nchunks
+        assert self.cs * nchunks == self.B
+        self.ectx, self.epp, self.ecp, self.eft, self.efe = [], [], [], [], []
+        for k in range(nchunks):
+            c = api.Context(torch.cuda.current_device())
+            self.ectx.append(c)
+            self.epp.append(api.Pyramid(c, self.cs, W_IMG, H_IMG, 3))
+            self.ecp.append(api.Pyramid(c, self.cs, W_IMG, H_IMG, 3))
+            self.eft.append(api.FeatureTracker(c, 30, 0.01))
+            self.efe.append(api.FeatureExtractor(c, nmaxdist=CELL, nfast_th=FAST_TH))
+        self.pool = cf.ThreadPoolExecutor(max_workers=nchunks)
+
+    def _e2e_chunk(self, k: int):
+        cs, nk, nc = self.cs, self.cs * NKP, self.cs * self.ncell
+        f0, k0, c0 = k * cs, k * cs * NKP, k * cs * self.ncell
+        np_ = lambda t, a, b: t[a:b].numpy()
+        self.epp[k].build(np_(self.h_prev, f0, f0 + cs))          # H2D inside
+        self.ecp[k].build(np_(self.h_cur, f0, f0 + cs))
+        self.h_pri[k0:k0 + nk].copy_(self.h_pri0[k0:k0 + nk])
+        self.h_th[f0:f0 + cs].fill_(FAST_TH)
+        self.eft[k].fb_klt_tracking(self.epp[k], self.ecp[k], 9, np_(self.h_lv, k0, k0 + nk), 30.0, 0.5,
+                                    np_(self.h_kps, k0, k0 + nk), np_(self.h_pri, k0, k0 + nk),
+                                    np_(self.h_status, k0, k0 + nk), n=nk, per_frame=NKP)
+        self.efe[k].detect_grid_fast(self.ecp[k], CELL, 0, cs, np_(self.h_th, f0, f0 + cs), np_(self.h_new, c0, c0 + nc),
+                                     np_(self.h_cnt, f0, f0 + cs), max_per_frame=self.ncell)
+        self.efe[k].describe_brief(self.ecp[k], np_(self.h_pri, k0, k0 + nk), np_(self.h_desc_t, k0, k0 + nk),
+                                   np_(self.h_val_t, k0, k0 + nk), n=nk, per_frame=NKP)
+        self.efe[k].describe_brief(self.ecp[k], np_(self.h_new, c0, c0 + nc), np_(self.h_desc_n, c0, c0 + nc),
+                                   np_(self.h_val_n, c0, c0 + nc), n=nc, per_frame=self.ncell)
+
     def step_e2e(self):
-        B, n = self.B, self.B * NKP
-        self.pyr_prev_h.build(self.h_prev.numpy())       # H2D inside
-        self.pyr_cur_h.build(self.h_cur.numpy())
-        self.h_pri.copy_(self.h_pri0)
-        self.h_th.fill_(FAST_TH)
-        self.ft.fb_klt_tracking(self.pyr_prev_h, self.pyr_cur_h, 9, self.h_lv.numpy(), 30.0, 0.5, self.h_kps.numpy(),
-                                self.h_pri.numpy(), self.h_status.numpy(), n=n, per_frame=NKP)
-        self.fe.detect_grid_fast(self.pyr_cur_h, CELL, 0, B, self.h_th.numpy(), self.h_new.numpy(), self.h_cnt.numpy(),
-                                 max_per_frame=self.ncell)
-        self.fe.describe_brief(self.pyr_cur_h, self.h_pri.numpy(), self.h_desc_t.numpy(), self.h_val_t.numpy(), n=n, per_frame=NKP)
-        self.fe.describe_brief(self.pyr_cur_h, self.h_new.numpy(), self.h_desc_n.numpy(), self.h_val_n.numpy(),
-                               n=B * self.ncell, per_frame=self.ncell)
+        list(self.pool.map(self._e2e_chunk, range(self.nchunks)))
         return int(self.h_status.sum()), int(self.h_cnt.sum())
+
+    def e2e_launches(self):
+        return sum(c.launch_count() for c in self.ectx)
 
 
 # SURVEY.md 8(d) algorithmic bytes per unit (stated in DESIGN.md)
@@ -364,6 +394,7 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     ms_res, wall_res, launches = timed(wl.step_resident, args.steps, args.warmup)
+    wl.init_e2e(args.e2e_chunks)
     ms_e2e_dev, wall_e2e, _ = timed(wl.step_e2e, args.steps, max(1, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
     # device events miss host-side staging of the last D2H sync; use the larger of event/wall time for e2e
@@ -414,7 +445,7 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32",
             "data": "synthetic", "config": _config(args.batch, "per-GPU batch fixed (weak scaling); no data-path collective"),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "chunks": args.e2e_chunks},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
         if world == 1 and not args.no_ba:
@@ -439,22 +470,54 @@ def _ncu_traffic(kernel: str):
 
 
 def ba_bench(torch, api, ctx):
-    """local-BA solves/s on the C3 problem (10 KF x 2k pts x 8k obs), second half of the metric."""
+    """local-BA solves/s on the C3 problem (10 KF x 2000 pts x 8000 obs) - the second half of
+    BASELINE.json's metric - through the C ABI with HOST buffers (upload of the flattened window,
+    two-stage solve, download of poses / inverse depths / outlier flags all inside the timed region),
+    next to the single-threaded C restatement of the reference's Ceres path (oracle/ba_ref_c.c;
+    "restatement, not Ceres": Ceres cannot be built offline; the reference runs it with
+    num_threads = 1, optimizer.cpp:460)."""
     from ov2slam_b200 import synth
     opt = api.Optimizer(ctx)
     pb0 = synth.make_ba_problem(3, 10, 2000, 8000)
-    reps = 20
-    its = 0
-    pb = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
-    opt.local_ba(pb)
+    clone = lambda: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
+    reps, its = 50, 0
+    for _ in range(3):
+        opt.local_ba(clone())
+    pbs = [clone() for _ in range(reps)]
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(reps):
-        pb = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
+    for pb in pbs:
         res, _ = opt.local_ba(pb)
         its += res["iters_robust"] + res["iters_refine"]
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"metric": "local-BA solves/sec", "value": reps / dt, "unit": "solves/s", "config": "C3: 10 KF x 2000 pts x 8000 obs",
-            "lm_iterations_per_solve": its / reps, "e2e": True, "final_cost": res["final_cost"]}
+    ctx.profile(True)
+    opt.local_ba(clone())
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    tot = sum(v[0] for v in rep.values()) or 1.0
+    out = {"metric": "local-BA solves/sec", "value": reps / dt, "unit": "solves/s", "ms_per_solve": 1e3 * dt / reps,
+           "config": {"workload": "C3: localBA 10 KF x 2000 inverse-depth pts x 8000 obs, 5 % gross outliers, two-stage solve"},
+           "lm_iterations_per_solve": its / reps, "final_cost": res["final_cost"], "dtype": "f64",
+           "kernel_time_shares": {k: round(v[0] / tot, 4) for k, v in rep.items()},
+           "kernel_launches_per_solve": int(sum(v[1] for v in rep.values())),
+           "gpu_kernel_ms_per_solve": tot,
+           "roofline_note": "one C3 solve touches ~0.66 MB per LM iteration and lives in L2: it is launch/sync-latency bound "
+                            "(SURVEY.md 7 'hard parts'), the HBM roofline applies to batched / C5-size problems"}
+    try:
+        from oracle import ba_ref_c
+        ts = []
+        for _ in range(10):
+            pb = clone()
+            t = time.perf_counter()
+            r = ba_ref_c.local_ba(pb)
+            ts.append(time.perf_counter() - t)
+        out["cpu_baseline"] = {"value": 1.0 / float(np.median(ts)), "unit": "solves/s", "cores": 1, "kind": "port",
+                               "sample": "10 solves of the same C3 problem, oracle/ba_ref_c.c single thread (restatement, not Ceres; "
+                                         "the reference sets num_threads = 1)", "lm_iterations": r["iters_robust"] + r["iters_refine"]}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": str(e)[:120]}
+    return out
 
 
 def main():
@@ -464,6 +527,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks (host threads x contexts) of the e2e arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA leg")
     args = ap.parse_args()

@@ -70,5 +70,28 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return SO
 
 
+def build_host_shims(verbose: bool = False) -> Path:
+    """Compile the drop-in C++ classes (host/feature_extractor.cpp, host/feature_tracker.cpp) against
+    the stand-in OpenCV headers and link them + a self-test driver against libov2b200.so.
+    On a box with real OpenCV, compile the same .cpp files with the real headers instead."""
+    host = ROOT / "host"
+    build()
+    objs = []
+    for name in ("feature_extractor.cpp", "feature_tracker.cpp", "shim_selftest.cpp"):
+        obj = LIB / "obj" / (name + ".o")
+        src = host / name
+        if _newer(src, obj) or any(_newer(h, obj) for h in host.glob("*.hpp")):
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", str(host / "standin"), "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        objs.append(str(obj))
+    exe = LIB / "shim_selftest"
+    subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread",
+                           "-Wl,-rpath,$ORIGIN"])
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host_shims(verbose=True))

@@ -94,10 +94,19 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
 
         // ---- 8-bit neighbourhood rows iy-1.., cols ix-1.. (reflect-101 = the padded level)
         __syncwarp();
-        for (int i = lane; i < PW * PW; i += 32) {
-            int r = i / PW, c = i - r * PW;
-            int y = reflect101_safe(iy - 1 + r, lh), x = reflect101_safe(ix - 1 + c, lw);
-            sP[i] = __ldg(Iimg + (size_t)y * Ipitch + x);
+        if (ix >= 1 && iy >= 1 && ix + PW - 1 <= lw && iy + PW - 1 <= lh) {
+            // interior (warp-uniform): no border handling
+            const uint8_t* src = Iimg + (size_t)(iy - 1) * Ipitch + (ix - 1);
+            for (int i = lane; i < PW * PW; i += 32) {
+                int r = i / PW, c = i - r * PW;
+                sP[i] = __ldg(src + r * Ipitch + c);
+            }
+        } else {
+            for (int i = lane; i < PW * PW; i += 32) {
+                int r = i / PW, c = i - r * PW;
+                int y = reflect101_safe(iy - 1 + r, lh), x = reflect101_safe(ix - 1 + c, lw);
+                sP[i] = __ldg(Iimg + (size_t)y * Ipitch + x);
+            }
         }
         __syncwarp();
         // ---- Scharr at the DWxDW bilinear footprint; 0 outside the image (BORDER_CONSTANT)
@@ -167,24 +176,42 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
             iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
             iw10 = __float2int_rn((1.f - a) * b * 16384.f);
             iw11 = 16384 - iw00 - iw01 - iw10;
-            __syncwarp();
-            for (int i = lane; i < DW * DW; i += 32) {
-                int r = i / DW, c = i - r * DW;
-                int y = reflect101_safe(jy + r, lh), x = reflect101_safe(jx + c, lw);
-                sP[i] = __ldg(Jimg + (size_t)y * Jpitch + x);
-            }
-            __syncwarp();
             int sb1 = 0, sb2 = 0;
+            if (jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
+                // interior (warp-uniform): every lane gathers its own 4 taps straight from L1/L2
+                const uint8_t* src = Jimg + (size_t)jy * Jpitch + jx;
 #pragma unroll
-            for (int k = 0; k < PER_LANE; ++k) {
-                int p = lane + 32 * k;
-                if (p < NPX) {
-                    int y = p / WIN, x = p - y * WIN;
-                    const uint8_t* q = sP + y * DW + x;
-                    int jval = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[DW] * iw10 + (int)q[DW + 1] * iw11 + (1 << 8)) >> 9;
-                    int diff = jval - (int)Iv[k];
-                    sb1 += diff * (int)Ixv[k];
-                    sb2 += diff * (int)Iyv[k];
+                for (int k = 0; k < PER_LANE; ++k) {
+                    int p = lane + 32 * k;
+                    if (p < NPX) {
+                        int y = p / WIN, x = p - y * WIN;
+                        const uint8_t* q = src + y * Jpitch + x;
+                        int jval = ((int)__ldg(q) * iw00 + (int)__ldg(q + 1) * iw01 + (int)__ldg(q + Jpitch) * iw10 +
+                                    (int)__ldg(q + Jpitch + 1) * iw11 + (1 << 8)) >> 9;
+                        int diff = jval - (int)Iv[k];
+                        sb1 += diff * (int)Ixv[k];
+                        sb2 += diff * (int)Iyv[k];
+                    }
+                }
+            } else {
+                __syncwarp();
+                for (int i = lane; i < DW * DW; i += 32) {
+                    int r = i / DW, c = i - r * DW;
+                    int y = reflect101_safe(jy + r, lh), x = reflect101_safe(jx + c, lw);
+                    sP[i] = __ldg(Jimg + (size_t)y * Jpitch + x);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < PER_LANE; ++k) {
+                    int p = lane + 32 * k;
+                    if (p < NPX) {
+                        int y = p / WIN, x = p - y * WIN;
+                        const uint8_t* q = sP + y * DW + x;
+                        int jval = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[DW] * iw10 + (int)q[DW + 1] * iw11 + (1 << 8)) >> 9;
+                        int diff = jval - (int)Iv[k];
+                        sb1 += diff * (int)Ixv[k];
+                        sb2 += diff * (int)Iyv[k];
+                    }
                 }
             }
             float b1 = __ll2float_rn(warp_sum64(sb1)) * FLT_SCALE;

@@ -170,3 +170,20 @@ def test_unused_and_constant_blocks_drop_out():
     res = B.local_ba(pb)
     assert np.array_equal(pb["pose"], p0)
     assert res["final_cost"] <= res["summaries"][0]["initial_cost"]
+
+
+@pytest.mark.parametrize("seed,ncam,npts,nobs", [(3, 10, 2000, 8000), (11, 6, 300, 1200), (5, 6, 100, 300)])
+def test_c_port_matches_numpy_oracle(seed, ncam, npts, nobs):
+    """oracle/ba_ref_c.c (the single-threaded CPU baseline bench.py times) == oracle/ba_ref.py."""
+    from oracle import ba_ref_c
+    pb = synth.make_ba_problem(seed, ncam, npts, nobs)
+    a = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    b = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    ra = B.local_ba(a)
+    rb = ba_ref_c.local_ba(b)
+    for k in ("iters_robust", "iters_refine", "n_outliers_first", "n_outliers_second", "termination"):
+        assert ra[k] == rb[k], k
+    assert abs(ra["final_cost"] - rb["final_cost"]) <= 1e-9 * max(1.0, ra["final_cost"])
+    assert np.abs(a["pose"] - b["pose"]).max() <= 1e-9
+    assert np.abs(a["lm_invdepth"] - b["lm_invdepth"]).max() <= 1e-9
+    assert np.array_equal(ra["flags"], rb["flags"])
