@@ -87,6 +87,14 @@ OV2_API ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* pyr, const uint8_t* imag
 OV2_API ov2_status ov2_pyr_download(ov2_ctx* ctx, const ov2_pyr* pyr, int frame, int level, uint8_t* out,
                             int* level_w, int* level_h);
 
+/* ------------------------------------------------------------------ C: CLAHE
+ * Replaces pclahe_->apply(img, img) with cv::createCLAHE(fclahe_val, Size(W/50, H/50))
+ * (/root/reference/src/ov2slam.cpp:85-89; src/visual_front_end.cpp:1158-1160; src/mapper.cpp:75-76;
+ * `use_clahe: 1`, the accurate/ configurations).  `count` 8-bit images, host or device; dst may
+ * alias src only for host buffers (the device path reads src while writing dst). */
+OV2_API ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride,
+                     size_t frame_stride, int count, double clip_limit, int tiles_x, int tiles_y);
+
 /* ------------------------------------------------------------------ K: forward/backward KLT
  * Replaces FeatureTracker::fbKltTracking(vprevpyr, vcurpyr, nwinsize, nbpyrlvl, ferr,
  * fmax_fbklt_dist, vkps, vpriorkps, vkpstatus) (/root/reference/src/feature_tracker.cpp:35-137;
@@ -183,6 +191,20 @@ typedef struct {
 /* outlier_out (optional): [nobs] bytes, bit0 = flagged after solve #1, bit1 = after solve #2. */
 OV2_API ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
                              ov2_ba_result* res, uint8_t* outlier_out);
+
+/* Multi-GPU localBA (BASELINE.json configs[4]): landmarks (with all their observations) are
+ * partitioned over ranks, every rank holds all keyframe poses.  `pb` describes THIS rank's shard
+ * (ncam / pose / pose_const identical on all ranks; npts / nobs local, may be 0 observations).
+ * Per LM iteration the partial reduced camera system [cost, rhs, F'r, column norms, S] is summed
+ * over ranks by ONE call of `allreduce` (the caller wires it to ncclAllReduce / torch.distributed
+ * over NVLink), followed by a 4-double collective for the candidate cost and model decrease; all
+ * ranks then solve the same reduced system and take identical LM decisions (no broadcast).
+ * allreduce(user, device_buf, count, cuda_stream): in-place SUM of `count` doubles on the given
+ * stream (or synchronously); returns 0 on success.  Result counts (outliers) are per shard. */
+typedef int (*ov2_allreduce_fn)(void* user, double* device_buf, size_t count, void* cuda_stream);
+OV2_API ov2_status ov2_localba_solve_sharded(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                     ov2_ba_result* res, uint8_t* outlier_out, ov2_allreduce_fn allreduce,
+                                     void* user, int rank);
 
 #ifdef __cplusplus
 }

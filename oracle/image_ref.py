@@ -651,6 +651,61 @@ def fb_klt_ref(prev, cur, kps, priors, win=9, nbpyrlvl=3, ferr=30.0, fb_dist=0.5
     return _fb_klt(_lk_ref, prev, cur, kps, priors, win, nbpyrlvl, ferr, fb_dist, maxit, eps)
 
 
+# ------------------------------------------------------------------ C: CLAHE
+def clahe_cv2(im: np.ndarray, clip: float = 3.0, tiles=None) -> np.ndarray:
+    """pclahe_->apply with cv::createCLAHE(fclahe_val, Size(W/50, H/50)) (ov2slam.cpp:85-89)."""
+    h, w = im.shape
+    tx, ty = tiles if tiles is not None else (w // 50, h // 50)
+    return cv2.createCLAHE(clip, (tx, ty)).apply(im)
+
+
+def clahe_ref(im: np.ndarray, clip: float = 3.0, tiles=None) -> np.ndarray:
+    """numpy restatement of cv::CLAHE (SURVEY.md A.6)."""
+    f32 = np.float32
+    h, w = im.shape
+    tx, ty = tiles if tiles is not None else (w // 50, h // 50)
+    ew, eh = w, h
+    if w % tx != 0 or h % ty != 0:
+        ew, eh = w + (tx - w % tx), h + (ty - h % ty)
+    ext = im[np.ix_(_reflect101(np.arange(eh), h), _reflect101(np.arange(ew), w))]
+    tw, th = ew // tx, eh // ty
+    area = tw * th
+    cl = max(int(clip * area / 256), 1) if clip > 0 else 1 << 30
+    lut = np.zeros((ty, tx, 256), np.uint8)
+    scale = f32(255) / f32(area)
+    for j in range(ty):
+        for i in range(tx):
+            hist = np.bincount(ext[j * th:(j + 1) * th, i * tw:(i + 1) * tw].ravel(), minlength=256).astype(np.int64)
+            excess = int(np.maximum(hist - cl, 0).sum())
+            hist = np.minimum(hist, cl)
+            batch = excess // 256
+            resid = excess - batch * 256
+            hist += batch
+            if resid:
+                step = max(256 // resid, 1)
+                idx = np.arange(0, 256, step)[:resid]
+                hist[idx] += 1
+            lut[j, i] = np.clip(np.rint(np.cumsum(hist).astype(f32) * scale), 0, 255).astype(np.uint8)
+    inv_tw, inv_th = f32(1.0) / f32(tw), f32(1.0) / f32(th)
+    txf = (np.arange(w, dtype=f32) * inv_tw - f32(0.5)).astype(f32)
+    tyf = (np.arange(h, dtype=f32) * inv_th - f32(0.5)).astype(f32)
+    tx1 = np.floor(txf).astype(np.int64)
+    ty1 = np.floor(tyf).astype(np.int64)
+    xa = (txf - tx1.astype(f32)).astype(f32)[None, :]
+    ya = (tyf - ty1.astype(f32)).astype(f32)[:, None]
+    tx2 = np.minimum(tx1 + 1, tx - 1)
+    ty2 = np.minimum(ty1 + 1, ty - 1)
+    tx1 = np.maximum(tx1, 0)
+    ty1 = np.maximum(ty1, 0)
+    v = im.astype(np.int64)
+    g = lambda a, b: lut[a[:, None], b[None, :], v].astype(f32)
+    xa1, ya1 = (f32(1) - xa).astype(f32), (f32(1) - ya).astype(f32)
+    top = ((g(ty1, tx1) * xa1).astype(f32) + (g(ty1, tx2) * xa).astype(f32)).astype(f32)
+    bot = ((g(ty2, tx1) * xa1).astype(f32) + (g(ty2, tx2) * xa).astype(f32)).astype(f32)
+    res = ((top * ya1).astype(f32) + (bot * ya).astype(f32)).astype(f32)
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)
+
+
 # ------------------------------------------------------------------ whole per-frame sequence
 def detect_grid_fast_cv2(im, cellsize, curkps, fast_th):
     """detectGridFAST including cornerSubPix; returns (pts float32[N,2], int pts, new_th)."""

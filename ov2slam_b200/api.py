@@ -28,8 +28,8 @@ STATUS_NAMES = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "CAPACITY",
 ABI_SYMBOLS = [
     "ov2_create", "ov2_destroy", "ov2_last_error", "ov2_version", "ov2_set_stream", "ov2_sync",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
-    "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_localba_solve",
+    "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_localba_solve", "ov2_localba_solve_sharded",
 ]
 
 
@@ -58,6 +58,9 @@ class BaResult(C.Structure):
     _fields_ = [("iters_robust", C.c_int), ("iters_refine", C.c_int), ("initial_cost", C.c_double),
                 ("final_cost", C.c_double), ("n_outliers_first", C.c_int), ("n_outliers_second", C.c_int),
                 ("termination", C.c_int)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
 def lib_path() -> Path:
@@ -93,11 +96,14 @@ def load():
     lib.ov2_pyr_destroy.restype = None
     lib.ov2_pyr_build.argtypes = [vp, vp, vp, sz, sz, i32, i32]
     lib.ov2_pyr_download.argtypes = [vp, vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.ov2_clahe.argtypes = [vp, vp, vp, i32, i32, sz, sz, i32, C.c_double, i32, i32]
     lib.ov2_fb_klt.argtypes = [vp, vp, vp, C.POINTER(KltParams), i32, vp, i32, i32, vp, i32, vp, vp, vp]
     lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
+    lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
+                                              ALLREDUCE_FN, vp, i32]
     _lib = lib
     return lib
 
@@ -222,6 +228,16 @@ class Pyramid:
             pass
 
 
+def clahe(ctx: Context, src, dst, width: int, height: int, count: int = 1, clip_limit: float = 3.0,
+          tiles=None, row_stride=None, frame_stride=None):
+    """cv::CLAHE::apply on `count` images (numpy or CUDA tensors); tiles default to the reference's
+    Size(W/50, H/50) (ov2slam.cpp:85-89)."""
+    tx, ty = tiles if tiles is not None else (width // 50, height // 50)
+    rs = int(row_stride if row_stride is not None else width)
+    fs = int(frame_stride if frame_stride is not None else rs * height)
+    ctx.check(ctx.lib.ov2_clahe(ctx.h, _ptr(src), _ptr(dst), width, height, rs, fs, count, float(clip_limit), tx, ty))
+
+
 class FeatureTracker:
     """Mirror of the reference's FeatureTracker (include/feature_tracker.hpp:33-56)."""
 
@@ -332,3 +348,83 @@ class Optimizer:
         pb["pose"][...] = keep["pose"]
         pb["lm_invdepth"][...] = keep["lm_invdepth"]
         return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags
+
+
+# ----------------------------------------------------------------------------- multi-GPU local BA
+def partition_ba_problem(pb: dict, world: int):
+    """Split a flat localBA window into `world` shards by LANDMARK (all observations of a landmark
+    stay on one rank, so the per-landmark Schur elimination is local), balancing the
+    number of observations greedily.  Every shard keeps all cameras.  Returns a list of
+    (shard dict, landmark index array, observation index array)."""
+    npts, nobs = len(pb["lm_invdepth"]), len(pb["obs_cam"])
+    counts = np.bincount(pb["obs_lm"], minlength=npts)
+    order = np.argsort(-counts, kind="stable")
+    load = np.zeros(world, np.int64)
+    owner = np.empty(npts, np.int64)
+    for l in order:                      # longest-processing-time greedy
+        r = int(np.argmin(load))
+        owner[l] = r
+        load[r] += counts[l] + 1
+    shards = []
+    for r in range(world):
+        lms = np.nonzero(owner == r)[0]                      # ascending -> observations stay sorted
+        remap = -np.ones(npts, np.int64)
+        remap[lms] = np.arange(len(lms))
+        obs = np.nonzero(owner[pb["obs_lm"]] == r)[0]
+        sh = dict(K=pb["K"].copy(), pose=pb["pose"].copy(), pose_const=pb["pose_const"].copy(),
+                  lm_anchor_cam=np.ascontiguousarray(pb["lm_anchor_cam"][lms]),
+                  lm_anchor_px=np.ascontiguousarray(pb["lm_anchor_px"][lms]),
+                  lm_invdepth=np.ascontiguousarray(pb["lm_invdepth"][lms]),
+                  obs_cam=np.ascontiguousarray(pb["obs_cam"][obs]),
+                  obs_lm=np.ascontiguousarray(remap[pb["obs_lm"][obs]].astype(np.int32)),
+                  obs_px=np.ascontiguousarray(pb["obs_px"][obs]))
+        shards.append((sh, lms, obs))
+    return shards
+
+
+class _CudaView:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def make_torch_allreduce(dist, torch, group=None):
+    """ov2_allreduce_fn that sums the buffer over the process group with torch.distributed
+    (NCCL over NVLink for device buffers; gloo for the CPU tests, where `buf` is host memory)."""
+    def _fn(user, buf, count, stream):
+        try:
+            if torch.cuda.is_available() and dist.get_backend(group) == "nccl":
+                t = torch.as_tensor(_CudaView(buf, count), device="cuda")
+                s = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+                with torch.cuda.stream(s):
+                    dist.all_reduce(t, group=group)
+            else:
+                a = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(count,))
+                t = torch.from_numpy(a)
+                dist.all_reduce(t, group=group)
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            print("[ov2b200] allreduce callback failed:", e, flush=True)
+            return 1
+    return ALLREDUCE_FN(_fn)
+
+
+def local_ba_sharded(ctx: Context, shard: dict, allreduce_cb, rank: int, **opts):
+    """ov2_localba_solve_sharded on this rank's shard; poses come back identical on every rank,
+    inverse depths / flags are the shard's own."""
+    o = dict(DEFAULT_BA_OPTS)
+    o.update(opts)
+    bo = BaOpts(**o)
+    keep = {k: np.ascontiguousarray(shard[k]) for k in
+            ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px")}
+    p = BaProblem(len(keep["pose"]), len(keep["lm_invdepth"]), len(keep["obs_cam"]),
+                  *[keep[k].ctypes.data for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
+                                                  "obs_cam", "obs_lm", "obs_px")])
+    res = BaResult()
+    flags = np.zeros(max(len(keep["obs_cam"]), 1), np.uint8)
+    ctx.check(ctx.lib.ov2_localba_solve_sharded(ctx.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data,
+                                                allreduce_cb, None, int(rank)))
+    shard["pose"][...] = keep["pose"]
+    shard["lm_invdepth"][...] = keep["lm_invdepth"]
+    return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags[:len(keep["obs_cam"])]

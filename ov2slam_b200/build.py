@@ -26,6 +26,7 @@ SOURCES = {
     "frontend_klt.cu": ["-fmad=false"],
     "frontend_fast.cu": ["-fmad=false"],
     "frontend_desc.cu": ["-fmad=false"],
+    "frontend_clahe.cu": ["-fmad=false"],
     "ba_solver.cu": [],
 }
 

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
     if (lane == 0) {
         D.ete[l] = ete;
         D.ge[l] = ge;
-        atomic_max_pos(D.scal + SC_GMAX_LM, fabs(ge));
+        atomic_max_pos(D.scal + SC_GMAX_LM, fabs(ge));   // per-rank maximum; summed over ranks when sharded (upper bound)
     }
     // touching variable cameras: entry 0 = anchor, then one per active observation
     const int sa = D.cam_slot[D.lm_anchor_cam[l]];
@@ -330,14 +330,14 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
 }
 
 // ------------------------------------------------------------------ reduced camera system (one CTA)
-__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int use_smem,
+__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int use_smem, int add_cam_norms,
                                                                 const double* __restrict__ pose, double* __restrict__ cand) {
     extern __shared__ double sA[];
-    __shared__ double s_piv;
     __shared__ int s_fail;
     const int n = D.n, tid = threadIdx.x, nt = blockDim.x;
     double* A = use_smem ? sA : D.S;
-    double* w = D.z;   // solution vector (global, n doubles)
+    __shared__ double s_w[MAX_N];
+    double* w = s_w;   // rhs -> solution vector (shared: the triangular solves are latency chains)
     if (tid == 0) s_fail = 0;
     // Jacobi scaling (iteration 0), LM damping, rhs = F'r - (Schur part already accumulated)
     for (int i = tid; i < n; i += nt) {
@@ -356,48 +356,49 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
         for (int e = tid; e < n * n; e += nt) sA[e] = D.S[e];
         __syncthreads();
     }
-    // Cholesky A = U'U on the upper triangle, right-looking
+    // Cholesky A = U'U on the upper triangle, right-looking, ONE barrier per column: row j is only
+    // ever read in step j, so its scaling by 1/sqrt(d_j) is folded into the trailing update and into
+    // the triangular solves (U[j][c] = A[j][c] * s_ipiv[j], U[j][j] = 1 / s_ipiv[j]).
+    __shared__ double s_ipiv[MAX_N];
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
     for (int j = 0; j < n; ++j) {
-        if (tid == 0) {
-            const double d = A[(size_t)j * n + j];
-            if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; s_piv = 1.0; }
-            else s_piv = sqrt(d);
-        }
-        __syncthreads();
-        if (s_fail) break;
-        const double piv = s_piv;
-        for (int c = j + tid; c < n; c += nt) A[(size_t)j * n + c] = (c == j) ? piv : A[(size_t)j * n + c] / piv;
-        __syncthreads();
-        const int rem = n - j - 1;
-        // trailing update A[r][c] -= U[j][r] U[j][c] for j < r <= c
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int rr = e / rem, cc = e - rr * rem;
-            if (cc < rr) continue;
-            const int r = j + 1 + rr, c = j + 1 + cc;
-            A[(size_t)r * n + c] -= A[(size_t)j * n + r] * A[(size_t)j * n + c];
+        const double d = A[(size_t)j * n + j];          // final since the previous barrier
+        if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) s_fail = 1; break; }   // uniform
+        const double inv_d = 1.0 / d;
+        if (tid == 0) s_ipiv[j] = rsqrt(d);
+        // trailing update A[r][c] -= A[j][r] A[j][c] / d for j < r <= c: one warp per row, lanes over columns
+        for (int r = j + 1 + warp; r < n; r += nwarp) {
+            const double ajr = A[(size_t)j * n + r] * inv_d;
+            for (int c = r + lane; c < n; c += 32) A[(size_t)r * n + c] -= ajr * A[(size_t)j * n + c];
         }
         __syncthreads();
     }
+    __syncthreads();
     if (s_fail) {
         if (tid == 0) D.scal[SC_CHOL_FAIL] = 1.0;
         return;
     }
-    // forward: U' y = b   (column-oriented: after fixing y_j subtract U[j][c] y_j from b_c)
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) w[j] = w[j] / A[(size_t)j * n + j];
-        __syncthreads();
-        const double yj = w[j];
-        for (int c = j + 1 + tid; c < n; c += nt) w[c] -= A[(size_t)j * n + c] * yj;
-        __syncthreads();
+    // triangular solves U' y = b, U z = y by warp 0 alone (n sequential steps each; __syncwarp is far
+    // cheaper than a block barrier); w[] is global, A may be shared or global
+    if (tid < 32) {
+        for (int j = 0; j < n; ++j) {
+            const double ip = s_ipiv[j];
+            const double yj = w[j] * ip;                 // / U[j][j]
+            __syncwarp();
+            if (tid == 0) w[j] = yj;
+            for (int c = j + 1 + tid; c < n; c += 32) w[c] -= A[(size_t)j * n + c] * ip * yj;
+            __syncwarp();
+        }
+        for (int j = n - 1; j >= 0; --j) {
+            const double zj = w[j] * s_ipiv[j];
+            __syncwarp();
+            if (tid == 0) w[j] = zj;
+            for (int r = tid; r < j; r += 32) w[r] -= A[(size_t)r * n + j] * s_ipiv[r] * zj;
+            __syncwarp();
+        }
     }
-    // backward: U z = y
-    for (int j = n - 1; j >= 0; --j) {
-        if (tid == 0) w[j] = w[j] / A[(size_t)j * n + j];
-        __syncthreads();
-        const double zj = w[j];
-        for (int r = tid; r < j; r += nt) w[r] -= A[(size_t)r * n + j] * zj;
-        __syncthreads();
-    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) D.z[i] = w[i];   // the back-substitution kernel reads z from global
     // candidate camera poses: Plus(x, delta), delta = -z ; step / candidate norms ; gradient max norm
     double st2 = 0.0, cx2 = 0.0, gm = 0.0;
     for (int c = tid; c < D.ncam; c += nt) {
@@ -419,8 +420,9 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
     cx2 = warp_sum(cx2);
     for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(FULL, gm, o));
     if ((tid & 31) == 0) {
-        if (st2 != 0.0) atomicAdd(D.scal + SC_STEP2, st2);
-        if (cx2 != 0.0) atomicAdd(D.scal + SC_CANDX2, cx2);
+        // sharded solve: every rank solves the same reduced system; only rank 0 contributes the camera norms
+        if (add_cam_norms && st2 != 0.0) atomicAdd(D.scal + SC_STEP2, st2);
+        if (add_cam_norms && cx2 != 0.0) atomicAdd(D.scal + SC_CANDX2, cx2);
         atomic_max_pos(D.scal + SC_GMAX_CAM, gm);
     }
 }
@@ -503,17 +505,34 @@ __global__ void ba_cam_used_kernel(BaDev D) {
 
 struct Summary { int iterations; double initial_cost, final_cost; int termination; };
 
+// multi-GPU sharding (landmarks partitioned over ranks): sum-allreduce hook, NULL = single GPU
+struct Shard { ov2_allreduce_fn fn; void* user; int rank; };
+
 }  // namespace
 
 // One ceres::Solve on the currently active residual blocks.
 static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*& cand_pose, double*& invd,
-                                 double*& cand_invd, int max_iters, double function_tolerance, Summary* out) {
+                                 double*& cand_invd, int max_iters, double function_tolerance, Summary* out, const Shard* sh) {
     cudaStream_t st = ctx->stream;
     const int nobs = D.nobs;
     // Program::RemoveFixedBlocks: cameras that are constant or touch no active residual drop out
     OV2_CUDA(ctx, cudaMemsetAsync(D.cam_used, 0, D.ncam, st));
     OV2_LAUNCH(ctx, "ba_cam_used_kernel", ba_cam_used_kernel<<<div_up(nobs, 256), 256, 0, st>>>(D));
     std::vector<uint8_t> used(D.ncam), cst(D.ncam);
+    if (sh && sh->fn) {
+        // a camera is in the program if ANY rank has an active residual touching it
+        std::vector<uint8_t> lu(D.ncam);
+        OV2_CUDA(ctx, cudaMemcpyAsync(lu.data(), D.cam_used, D.ncam, cudaMemcpyDeviceToHost, st));
+        OV2_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<double> ud(D.ncam);
+        for (int c = 0; c < D.ncam; ++c) ud[c] = lu[c];
+        OV2_CUDA(ctx, cudaMemcpyAsync(D.scal, ud.data(), sizeof(double) * D.ncam, cudaMemcpyHostToDevice, st));
+        if (sh->fn(sh->user, D.scal, (size_t)D.ncam, (void*)st) != 0) return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
+        OV2_CUDA(ctx, cudaMemcpyAsync(ud.data(), D.scal, sizeof(double) * D.ncam, cudaMemcpyDeviceToHost, st));
+        OV2_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int c = 0; c < D.ncam; ++c) lu[c] = ud[c] > 0.0;
+        OV2_CUDA(ctx, cudaMemcpyAsync(D.cam_used, lu.data(), D.ncam, cudaMemcpyHostToDevice, st));
+    }
     OV2_CUDA(ctx, cudaMemcpyAsync(used.data(), D.cam_used, D.ncam, cudaMemcpyDeviceToHost, st));
     OV2_CUDA(ctx, cudaMemcpyAsync(cst.data(), D.pose_const, D.ncam, cudaMemcpyDeviceToHost, st));
     OV2_CUDA(ctx, cudaStreamSynchronize(st));
@@ -527,14 +546,19 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     out->iterations = 0;
     out->initial_cost = out->final_cost = 0.0;
     out->termination = 0;
-    if (!any) return OV2_OK;   // no residual blocks
+    if (!any) return OV2_OK;   // no residual blocks (on any rank, when sharded)
     if (ncv > MAX_VAR_CAMS) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: more than 64 optimised keyframes");
     D.ncv = ncv;
     D.n = 6 * ncv;
     const int n = D.n;
     OV2_CUDA(ctx, cudaMemcpyAsync(D.cam_slot, slot.data(), sizeof(int32_t) * D.ncam, cudaMemcpyHostToDevice, st));
+    D.rhs = D.scal + SC_COUNT;
+    D.gcam = D.rhs + n;
+    D.cn_cam = D.gcam + n;
+    D.S = D.cn_cam + n;
     const size_t smem_need = (size_t)n * n * sizeof(double);
     const int use_smem = smem_need <= 200 * 1024 ? 1 : 0;
+    const int solve_threads = n <= 96 ? 256 : 1024;
     if (use_smem && smem_need > 48 * 1024)
         OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
 
@@ -542,54 +566,56 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     // (constant / unused) must keep their current value through pointer swaps
     OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
     OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, invd, sizeof(double) * D.npts, cudaMemcpyDeviceToDevice, st));
+    // One accumulation buffer [scal | rhs | gcam | cn_cam | S] -> one memset per LM iteration.
+    // Per iteration: memset, (Jacobian evaluation if x is new), Schur, reduced solve, back-substitution,
+    // candidate cost, ONE readback of the scalars; the controller below replays Ceres' decisions.
+    const size_t accum_bytes = sizeof(double) * ((size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n);
     double h[SC_COUNT];
-    auto eval_jac = [&]() -> ov2_status {
-        OV2_CUDA(ctx, cudaMemsetAsync(D.scal, 0, sizeof(double) * SC_COUNT, st));
-        OV2_LAUNCH(ctx, "ba_eval_kernel<jac>", ba_eval_kernel<true><<<div_up(nobs, 128), 128, 0, st>>>(D, pose, invd));
-        return OV2_OK;
-    };
-    ov2_status s = eval_jac();
-    if (s != OV2_OK) return s;
     double x_cost = 0.0, minimum_cost = DBL_MAX, xnorm = -1.0, gmax = DBL_MAX;
     double radius = 1e4, decrease_factor = 2.0;
-    bool step_successful = true, have_cost = false;
+    bool step_successful = true, x_is_new = true, cost_known = false;
     int iteration = 0, num_invalid = 0, first_iter = 1;
-    bool need_system = true;   // S / rhs must be (re)assembled for the current J
     for (;;) {
-        if (need_system && !have_cost) {
-            // cost of the Jacobian evaluation is needed before the controller can continue
-            OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
-            OV2_CUDA(ctx, cudaStreamSynchronize(st));
-            x_cost = h[SC_COST];
-            have_cost = true;
-            if (iteration == 0) out->initial_cost = x_cost;
-        }
-        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue
-        if (step_successful && x_cost < minimum_cost) minimum_cost = x_cost;
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue (x_cost of a just-accepted point equals
+        //      its candidate cost; the re-evaluated value replaces it at the next readback)
+        if (step_successful && cost_known && x_cost < minimum_cost) minimum_cost = x_cost;
         if (iteration >= max_iters) { out->termination = 1; break; }
         if (radius <= 1e-32) { out->termination = 0; break; }
         iteration++;
         // ---- ComputeTrustRegionStep
-        OV2_CUDA(ctx, cudaMemsetAsync(D.S, 0, sizeof(double) * (size_t)n * n, st));
-        OV2_CUDA(ctx, cudaMemsetAsync(D.rhs, 0, sizeof(double) * n, st));
-        OV2_CUDA(ctx, cudaMemsetAsync(D.gcam, 0, sizeof(double) * n, st));
-        OV2_CUDA(ctx, cudaMemsetAsync(D.cn_cam, 0, sizeof(double) * n, st));
-        OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_CAND_COST, 0, sizeof(double) * (SC_COUNT - 1), st));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.scal, 0, accum_bytes, st));
+        if (x_is_new)
+            OV2_LAUNCH(ctx, "ba_eval_kernel<jac>", ba_eval_kernel<true><<<div_up(nobs, 128), 128, 0, st>>>(D, pose, invd));
         OV2_LAUNCH(ctx, "ba_schur_kernel", ba_schur_kernel<<<div_up(D.npts, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(D, radius, first_iter));
+        if (sh && sh->fn) {
+            // the ONE bulk collective per LM iteration: [cost, gmax, rhs, F'r, column norms, S] summed over
+            // ranks (NVLink / NVSwitch via NCCL in the caller); every rank then solves the same system
+            if (sh->fn(sh->user, D.scal, (size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n, (void*)st) != 0)
+                return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
+        }
         OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
-                   ba_reduced_solve_kernel<<<1, 1024, use_smem ? smem_need : 0, st>>>(D, radius, first_iter, use_smem, pose, cand_pose));
+                   ba_reduced_solve_kernel<<<1, solve_threads, use_smem ? smem_need : 0, st>>>(D, radius, first_iter, use_smem, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
         OV2_LAUNCH(ctx, "ba_backsub_kernel", ba_backsub_kernel<<<div_up(D.npts, 4), 128, 0, st>>>(D, invd, cand_invd));
         OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<div_up(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
         first_iter = 0;
+        if (sh && sh->fn) {
+            // tiny second collective: candidate cost, model cost change, landmark step / candidate norms
+            if (sh->fn(sh->user, D.scal + SC_CAND_COST, 4, (void*)st) != 0) return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
+        }
         OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
         OV2_CUDA(ctx, cudaStreamSynchronize(st));
-        if (iteration == 1 || step_successful) {
+        if (x_is_new) {
+            x_cost = h[SC_COST];          // cost of the (re-)evaluation at x, as Ceres uses it
+            cost_known = true;
+            if (iteration == 1) out->initial_cost = x_cost;
+            if (x_cost < minimum_cost) minimum_cost = x_cost;
             // GradientToleranceReached() for the point this system was assembled at (its gradient
             // F'r / E'r is a by-product of the Schur pass): Ceres would have stopped before this
             // iteration, so the iteration does not count.
             gmax = fmax(h[SC_GMAX_LM], h[SC_GMAX_CAM]);
             if (gmax <= 1e-10) { out->termination = 0; iteration--; break; }
         }
+        x_is_new = false;
         const double model_cost_change = h[SC_MCC];
         double cand_cost = h[SC_CAND_COST];
         if (getenv("OV2_BA_DEBUG"))
@@ -602,7 +628,6 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             radius /= decrease_factor;
             decrease_factor *= 2.0;
             step_successful = false;
-            need_system = false;
             continue;
         }
         num_invalid = 0;
@@ -615,16 +640,15 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
         // ---- IsStepSuccessful
         const double rel = cand_cost >= DBL_MAX ? -DBL_MAX : cost_change / model_cost_change;
         if (rel > 1e-3) {
-            // HandleSuccessfulStep: x = candidate, re-evaluate residuals + Jacobians there
+            // HandleSuccessfulStep: x = candidate; residuals + Jacobians are re-evaluated there at the
+            // start of the next iteration (Ceres does it now; the values are the same)
             double* t = pose; pose = cand_pose; cand_pose = t;
             t = invd; invd = cand_invd; cand_invd = t;
             xnorm = sqrt(h[SC_CANDX2]);
-            // keep the non-variable entries of the new candidate buffers identical to x
             OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
             OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, invd, sizeof(double) * D.npts, cudaMemcpyDeviceToDevice, st));
-            if ((s = eval_jac()) != OV2_OK) return s;
-            have_cost = false;
-            need_system = true;
+            x_cost = cand_cost;
+            x_is_new = true;
             step_successful = true;
             radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3));
             radius = fmin(1e16, radius);
@@ -633,7 +657,6 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             step_successful = false;
             radius /= decrease_factor;
             decrease_factor *= 2.0;
-            need_system = false;
         }
     }
     out->iterations = iteration;
@@ -641,12 +664,12 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     return OV2_OK;
 }
 
-extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
-                                        ov2_ba_result* res, uint8_t* outlier_out) {
+static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                               ov2_ba_result* res, uint8_t* outlier_out, const Shard* sh) {
     if (!ctx || !pb || !opts || !res || pb->ncam <= 0 || pb->npts <= 0 || pb->nobs < 0)
         return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: bad arguments");
     memset(res, 0, sizeof(*res));
-    if (pb->nobs == 0) return OV2_OK;
+    if (pb->nobs == 0 && !sh) return OV2_OK;
     ov2_status st = ov2_begin(ctx);
     if (st != OV2_OK) return st;
     const int ncam = pb->ncam, npts = pb->npts, nobs = pb->nobs;
@@ -675,14 +698,58 @@ extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, 
     D.use_huber = opts->use_robust ? 1 : 0;
     const void* d = nullptr;
     void* o = nullptr;
+    const bool all_host = !ov2_is_device_ptr(pb->pose) && !ov2_is_device_ptr(pb->lm_invdepth) && !ov2_is_device_ptr(pb->pose_const) &&
+                          !ov2_is_device_ptr(pb->lm_anchor_cam) && !ov2_is_device_ptr(pb->lm_anchor_px) &&
+                          !ov2_is_device_ptr(pb->obs_cam) && !ov2_is_device_ptr(pb->obs_lm) && !ov2_is_device_ptr(pb->obs_px) &&
+                          (!outlier_out || !ov2_is_device_ptr(outlier_out));
+    // Host problem description: pack everything into one pinned staging block -> ONE H2D copy
+    // (a dozen small pageable copies cost more than the solve's kernels at C3 size).
+    size_t off_apx = 0, off_opx = 0, off_pose = 0, off_invd = 0, off_lac = 0, off_oc = 0, off_ol = 0, off_lp = 0, off_pc = 0, pack_bytes = 0;
+    char* dpack = nullptr;
+    if (all_host) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o_ = off; off += (bytes + 15) & ~(size_t)15; return o_; };
+        off_pose = take(sizeof(double) * 7 * ncam); off_invd = take(sizeof(double) * npts);
+        off_apx = take(sizeof(double) * 2 * npts); off_opx = take(sizeof(double) * 2 * nobs);
+        off_lac = take(sizeof(int32_t) * npts); off_oc = take(sizeof(int32_t) * nobs); off_ol = take(sizeof(int32_t) * nobs);
+        off_lp = take(sizeof(int32_t) * (npts + 1)); off_pc = take((size_t)ncam);
+        pack_bytes = off;
+        if (ctx->ba_ws_cap < pack_bytes) {
+            if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);
+            ctx->ba_ws = nullptr;
+            ctx->ba_ws_cap = 0;
+            OV2_CUDA(ctx, cudaHostAlloc(&ctx->ba_ws, pack_bytes * 2, cudaHostAllocDefault));
+            ctx->ba_ws_cap = pack_bytes * 2;
+        }
+        char* hp = (char*)ctx->ba_ws;
+        memcpy(hp + off_pose, pb->pose, sizeof(double) * 7 * ncam);
+        memcpy(hp + off_invd, pb->lm_invdepth, sizeof(double) * npts);
+        memcpy(hp + off_apx, pb->lm_anchor_px, sizeof(double) * 2 * npts);
+        memcpy(hp + off_opx, pb->obs_px, sizeof(double) * 2 * nobs);
+        memcpy(hp + off_lac, pb->lm_anchor_cam, sizeof(int32_t) * npts);
+        memcpy(hp + off_oc, pb->obs_cam, sizeof(int32_t) * nobs);
+        memcpy(hp + off_ol, pb->obs_lm, sizeof(int32_t) * nobs);
+        memcpy(hp + off_lp, lm_ptr.data(), sizeof(int32_t) * (npts + 1));
+        memcpy(hp + off_pc, pb->pose_const, (size_t)ncam);
+        if ((st = ov2_scratch(ctx, pack_bytes, &o)) != OV2_OK) return st;
+        dpack = (char*)o;
+        OV2_CUDA(ctx, cudaMemcpyAsync(dpack, hp, pack_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        D.pose_const = (const uint8_t*)(dpack + off_pc);
+        D.lm_anchor_cam = (const int32_t*)(dpack + off_lac);
+        D.lm_anchor_px = (const double*)(dpack + off_apx);
+        D.obs_cam = (const int32_t*)(dpack + off_oc);
+        D.obs_lm = (const int32_t*)(dpack + off_ol);
+        D.obs_px = (const double*)(dpack + off_opx);
+    } else {
 #define IN(field, bytes) do { if ((st = ov2_stage_in(ctx, pb->field, (bytes), &d)) != OV2_OK) return st; } while (0)
-    IN(pose_const, (size_t)ncam); D.pose_const = (const uint8_t*)d;
-    IN(lm_anchor_cam, sizeof(int32_t) * (size_t)npts); D.lm_anchor_cam = (const int32_t*)d;
-    IN(lm_anchor_px, sizeof(double) * 2 * (size_t)npts); D.lm_anchor_px = (const double*)d;
-    IN(obs_cam, sizeof(int32_t) * (size_t)nobs); D.obs_cam = (const int32_t*)d;
-    IN(obs_lm, sizeof(int32_t) * (size_t)nobs); D.obs_lm = (const int32_t*)d;
-    IN(obs_px, sizeof(double) * 2 * (size_t)nobs); D.obs_px = (const double*)d;
+        IN(pose_const, (size_t)ncam); D.pose_const = (const uint8_t*)d;
+        IN(lm_anchor_cam, sizeof(int32_t) * (size_t)npts); D.lm_anchor_cam = (const int32_t*)d;
+        IN(lm_anchor_px, sizeof(double) * 2 * (size_t)npts); D.lm_anchor_px = (const double*)d;
+        IN(obs_cam, sizeof(int32_t) * (size_t)nobs); D.obs_cam = (const int32_t*)d;
+        IN(obs_lm, sizeof(int32_t) * (size_t)nobs); D.obs_lm = (const int32_t*)d;
+        IN(obs_px, sizeof(double) * 2 * (size_t)nobs); D.obs_px = (const double*)d;
 #undef IN
+    }
     double *pose = nullptr, *cand_pose = nullptr, *invd = nullptr, *cand_invd = nullptr;
 #define SCR(ptr, type, count) do { if ((st = ov2_scratch(ctx, sizeof(type) * (size_t)(count), &o)) != OV2_OK) return st; ptr = (type*)o; } while (0)
     SCR(pose, double, 7 * ncam); SCR(cand_pose, double, 7 * ncam);
@@ -692,26 +759,31 @@ extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, 
     SCR(D.active, uint8_t, nobs); SCR(D.cam_slot, int32_t, ncam); SCR(D.cam_used, uint8_t, ncam);
     SCR(D.Jr, double, 2 * (size_t)nobs); SCR(D.Ja, double, 12 * (size_t)nobs); SCR(D.Jo, double, 12 * (size_t)nobs);
     SCR(D.Jl, double, 2 * (size_t)nobs); SCR(D.chi2, double, nobs); SCR(D.dpos, uint8_t, nobs);
-    SCR(D.cn_cam, double, MAX_N); SCR(D.sc_cam, double, MAX_N); SCR(D.sc_lm, double, npts);
-    SCR(D.S, double, (size_t)MAX_N * MAX_N); SCR(D.rhs, double, MAX_N); SCR(D.z, double, MAX_N); SCR(D.gcam, double, MAX_N);
-    SCR(D.ete, double, npts); SCR(D.ge, double, npts); SCR(D.scal, double, SC_COUNT); SCR(D.flags, uint8_t, nobs);
+    SCR(D.sc_cam, double, MAX_N); SCR(D.sc_lm, double, npts); SCR(D.z, double, MAX_N);
+    // accumulation buffer, zeroed once per LM iteration: [scal | rhs | gcam | cn_cam | S] (re-pointed per solve)
+    SCR(D.scal, double, (size_t)SC_COUNT + 3 * (size_t)MAX_N + (size_t)MAX_N * MAX_N);
+    SCR(D.ete, double, npts); SCR(D.ge, double, npts); SCR(D.flags, uint8_t, nobs);
 #undef SCR
-    D.lm_ptr = d_lmptr;
     cudaStream_t s = ctx->stream;
-    OV2_CUDA(ctx, cudaMemcpyAsync(d_lmptr, lm_ptr.data(), sizeof(int32_t) * (npts + 1), cudaMemcpyHostToDevice, s));
-    const cudaMemcpyKind kp = ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    const cudaMemcpyKind ki = ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    OV2_CUDA(ctx, cudaMemcpyAsync(pose, pb->pose, sizeof(double) * 7 * ncam, kp, s));
-    OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pb->pose, sizeof(double) * 7 * ncam, kp, s));
-    OV2_CUDA(ctx, cudaMemcpyAsync(invd, pb->lm_invdepth, sizeof(double) * npts, ki, s));
-    OV2_CUDA(ctx, cudaMemcpyAsync(cand_invd, pb->lm_invdepth, sizeof(double) * npts, ki, s));
+    if (all_host) {
+        D.lm_ptr = (const int32_t*)(dpack + off_lp);
+        OV2_CUDA(ctx, cudaMemcpyAsync(pose, dpack + off_pose, sizeof(double) * 7 * ncam, cudaMemcpyDeviceToDevice, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(invd, dpack + off_invd, sizeof(double) * npts, cudaMemcpyDeviceToDevice, s));
+    } else {
+        D.lm_ptr = d_lmptr;
+        OV2_CUDA(ctx, cudaMemcpyAsync(d_lmptr, lm_ptr.data(), sizeof(int32_t) * (npts + 1), cudaMemcpyHostToDevice, s));
+        const cudaMemcpyKind kp = ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        const cudaMemcpyKind ki = ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        OV2_CUDA(ctx, cudaMemcpyAsync(pose, pb->pose, sizeof(double) * 7 * ncam, kp, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(invd, pb->lm_invdepth, sizeof(double) * npts, ki, s));
+    }
     OV2_CUDA(ctx, cudaMemsetAsync(D.active, 1, nobs, s));
     OV2_CUDA(ctx, cudaMemsetAsync(D.flags, 0, nobs, s));
     OV2_CUDA(ctx, cudaMemsetAsync(D.sc_lm, 0, sizeof(double) * npts, s));
     OV2_CUDA(ctx, cudaMemsetAsync(D.sc_cam, 0, sizeof(double) * MAX_N, s));
 
     Summary s1, s2;
-    if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_robust, opts->function_tolerance, &s1)) != OV2_OK)
+    if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_robust, opts->function_tolerance, &s1, sh)) != OV2_OK)
         return st;
     // outlier scan on the values the LAST Evaluate() left behind (optimizer.cpp:500-530)
     double h[SC_COUNT];
@@ -725,9 +797,16 @@ extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, 
     res->final_cost = s1.final_cost;
     res->termination = s1.termination;
     res->n_outliers_first = (int)h[SC_NBAD];
-    if (opts->apply_l2_after_robust && opts->use_robust && res->n_outliers_first > 0) {
+    double nbad_global = h[SC_NBAD];
+    if (sh && sh->fn) {
+        // every rank must take the same branch: the refinement runs if ANY rank removed an observation
+        if (sh->fn(sh->user, D.scal + SC_NBAD, 1, (void*)s) != 0) return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
+        OV2_CUDA(ctx, cudaMemcpyAsync(&nbad_global, D.scal + SC_NBAD, sizeof(double), cudaMemcpyDeviceToHost, s));
+        OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    if (opts->apply_l2_after_robust && opts->use_robust && nbad_global > 0) {
         // mono windows keep the Huber loss in the refinement (optimizer.cpp:606-608)
-        if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_refine, opts->function_tolerance, &s2)) != OV2_OK)
+        if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_refine, opts->function_tolerance, &s2, sh)) != OV2_OK)
             return st;
         OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, sizeof(double), s));
         OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 2, 0));
@@ -740,14 +819,42 @@ extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, 
         res->n_outliers_second = (int)h[SC_NBAD];
     }
     // write-back of the states (the map update itself, optimizer.cpp:741-897, stays on the host)
-    OV2_CUDA(ctx, cudaMemcpyAsync(pb->pose, pose, sizeof(double) * 7 * ncam,
-                                  ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    OV2_CUDA(ctx, cudaMemcpyAsync(pb->lm_invdepth, invd, sizeof(double) * npts,
-                                  ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    if (outlier_out)
-        OV2_CUDA(ctx, cudaMemcpyAsync(outlier_out, D.flags, nobs,
-                                      ov2_is_device_ptr(outlier_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
-    OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    if (all_host) {
+        // one D2H: [pose | invd | flags] gathered on the device into the pack block's head
+        char* hp = (char*)ctx->ba_ws;
+        const size_t o_pose = 0, o_invd = sizeof(double) * 7 * ncam, o_fl = o_invd + sizeof(double) * npts;
+        const size_t out_bytes = o_fl + (size_t)nobs;
+        OV2_CUDA(ctx, cudaMemcpyAsync(dpack + o_pose, pose, sizeof(double) * 7 * ncam, cudaMemcpyDeviceToDevice, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(dpack + o_invd, invd, sizeof(double) * npts, cudaMemcpyDeviceToDevice, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(dpack + o_fl, D.flags, nobs, cudaMemcpyDeviceToDevice, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(hp, dpack, out_bytes, cudaMemcpyDeviceToHost, s));
+        OV2_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(pb->pose, hp + o_pose, sizeof(double) * 7 * ncam);
+        memcpy(pb->lm_invdepth, hp + o_invd, sizeof(double) * npts);
+        if (outlier_out) memcpy(outlier_out, hp + o_fl, nobs);
+    } else {
+        OV2_CUDA(ctx, cudaMemcpyAsync(pb->pose, pose, sizeof(double) * 7 * ncam,
+                                      ov2_is_device_ptr(pb->pose) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        OV2_CUDA(ctx, cudaMemcpyAsync(pb->lm_invdepth, invd, sizeof(double) * npts,
+                                      ov2_is_device_ptr(pb->lm_invdepth) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        if (outlier_out)
+            OV2_CUDA(ctx, cudaMemcpyAsync(outlier_out, D.flags, nobs,
+                                          ov2_is_device_ptr(outlier_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    }
     if (res->termination == 2) return ov2_fail(ctx, OV2_ERR_NUMERIC, "ov2_localba_solve: 5 consecutive invalid steps");
     return OV2_OK;
+}
+
+extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                        ov2_ba_result* res, uint8_t* outlier_out) {
+    return localba_impl(ctx, pb, opts, res, outlier_out, nullptr);
+}
+
+extern "C" ov2_status ov2_localba_solve_sharded(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                                ov2_ba_result* res, uint8_t* outlier_out, ov2_allreduce_fn allreduce,
+                                                void* user, int rank) {
+    if (!allreduce) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve_sharded: allreduce callback is NULL");
+    Shard sh{allreduce, user, rank};
+    return localba_impl(ctx, pb, opts, res, outlier_out, &sh);
 }

@@ -1,0 +1,160 @@
+// C: contrast-limited adaptive histogram equalisation (cv::CLAHE semantics), bit-exact.
+//
+// Reference behaviour replaced: pclahe_->apply(img, img) with cv::createCLAHE(fclahe_val = 3,
+// Size(W/50, H/50)) (/root/reference/src/ov2slam.cpp:85-89, applied at src/visual_front_end.cpp:
+// 1158-1160 and src/mapper.cpp:75-76; `use_clahe: 1`, i.e. the accurate/ configurations).
+// Algorithm (pinned against cv2 by oracle/image_ref.py::clahe_ref):
+//   * if W % tx or H % ty != 0 the image is extended right by tx - W % tx AND bottom by ty - H % ty
+//     (both, REFLECT_101); tile = extended size / tiles
+//   * per tile 256-bin histogram, clip = max(int(clip * area / 256), 1), excess redistributed
+//     (uniform batch + one each to bins 0, step, 2 step, ...), LUT = rint(cumsum * (255 / area))
+//   * per pixel float32 bilinear blend of the four neighbouring tile LUTs, rint.
+// clahe_lut_kernel: one CTA per (tile, frame), shared-memory histogram.  clahe_apply_kernel:
+// streaming pass, 4 pixels per thread (HBM-bound: reads W*H, writes W*H per frame; the LUTs
+// live in L2).
+#include "ov2_common.cuh"
+
+namespace {
+
+struct ClaheArgs {
+    const uint8_t* src; uint8_t* dst;
+    int w, h, spitch, dpitch;
+    long long sfstride, dfstride;
+    int tx, ty, tw, th, clip;
+    float lut_scale, inv_tw, inv_th;
+    uint8_t* lut;   // [count][ty][tx][256]
+};
+
+__device__ __forceinline__ int refl(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
+    __shared__ int hist[256];
+    __shared__ int s_excess;
+    const int tile = blockIdx.x, fr = blockIdx.y;
+    const int tyi = tile / A.tx, txi = tile - tyi * A.tx;
+    const uint8_t* src = A.src + A.sfstride * fr;
+    hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_excess = 0;
+    __syncthreads();
+    const int x0 = txi * A.tw, y0 = tyi * A.th, area = A.tw * A.th;
+    for (int i = threadIdx.x; i < area; i += 256) {
+        int yy = i / A.tw, xx = i - yy * A.tw;
+        int x = refl(x0 + xx, A.w), y = refl(y0 + yy, A.h);
+        atomicAdd(&hist[__ldg(src + (size_t)y * A.spitch + x)], 1);
+    }
+    __syncthreads();
+    int v = hist[threadIdx.x];
+    if (v > A.clip) { atomicAdd(&s_excess, v - A.clip); v = A.clip; }
+    __syncthreads();
+    const int clipped = s_excess;
+    const int batch = clipped / 256;
+    int residual = clipped - batch * 256;
+    v += batch;
+    if (residual != 0) {
+        const int step = max(256 / residual, 1);
+        // bins 0, step, 2*step, ... (the first `residual` of them, while index < 256)
+        if (threadIdx.x % step == 0 && threadIdx.x / step < residual) v++;
+    }
+    hist[threadIdx.x] = v;
+    __syncthreads();
+    // inclusive prefix sum (256 entries) by warp 0: 8 values per lane + warp scan
+    __shared__ int cum[256];
+    if (threadIdx.x < 32) {
+        int loc[8], s = 0;
+        for (int k = 0; k < 8; ++k) { s += hist[threadIdx.x * 8 + k]; loc[k] = s; }
+        int incl = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += t;
+        }
+        const int base = incl - s;
+        for (int k = 0; k < 8; ++k) cum[threadIdx.x * 8 + k] = base + loc[k];
+    }
+    __syncthreads();
+    int q = __float2int_rn((float)cum[threadIdx.x] * A.lut_scale);
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    A.lut[(((size_t)fr * A.ty + tyi) * A.tx + txi) * 256 + threadIdx.x] = (uint8_t)q;
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
+    const int fr = blockIdx.z;
+    const int y = blockIdx.y;
+    const int xq = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (xq >= A.w) return;
+    const uint8_t* srow = A.src + A.sfstride * fr + (size_t)y * A.spitch;
+    uint8_t* drow = A.dst + A.dfstride * fr + (size_t)y * A.dpitch;
+    const uint8_t* lut = A.lut + (size_t)fr * A.ty * A.tx * 256;
+    const float tyf = (float)y * A.inv_th - 0.5f;
+    int ty1 = __float2int_rd(tyf);
+    const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+    int ty2 = ty1 + 1;
+    ty1 = max(ty1, 0);
+    ty2 = min(ty2, A.ty - 1);
+    const uint8_t* l1 = lut + (size_t)ty1 * A.tx * 256;
+    const uint8_t* l2 = lut + (size_t)ty2 * A.tx * 256;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = xq + k;
+        if (x >= A.w) break;
+        const float txf = (float)x * A.inv_tw - 0.5f;
+        int tx1 = __float2int_rd(txf);
+        const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+        int tx2 = tx1 + 1;
+        tx1 = max(tx1, 0);
+        tx2 = min(tx2, A.tx - 1);
+        const int v = srow[x];
+        const float r = ((float)l1[tx1 * 256 + v] * xa1 + (float)l1[tx2 * 256 + v] * xa) * ya1 +
+                        ((float)l2[tx1 * 256 + v] * xa1 + (float)l2[tx2 * 256 + v] * xa) * ya;
+        int q = __float2int_rn(r);
+        drow[x] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+    }
+}
+
+}  // namespace
+
+extern "C" ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride,
+                                size_t frame_stride, int count, double clip_limit, int tiles_x, int tiles_y) {
+    if (!ctx || !src || !dst || width <= 0 || height <= 0 || count <= 0 || tiles_x <= 0 || tiles_y <= 0 ||
+        row_stride < (size_t)width)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_clahe: bad arguments");
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    const size_t bytes = frame_stride * (size_t)(count - 1) + row_stride * (size_t)(height - 1) + (size_t)width;
+    const void* d = nullptr;
+    void* o = nullptr;
+    if ((st = ov2_stage_in(ctx, src, bytes, &d)) != OV2_OK) return st;
+    if ((st = ov2_stage_out(ctx, dst, bytes, &o)) != OV2_OK) return st;
+    ClaheArgs A;
+    A.src = (const uint8_t*)d; A.dst = (uint8_t*)o;
+    A.w = width; A.h = height; A.spitch = A.dpitch = (int)row_stride;
+    A.sfstride = A.dfstride = (long long)frame_stride;
+    A.tx = tiles_x; A.ty = tiles_y;
+    int ew = width, eh = height;
+    if (width % tiles_x != 0 || height % tiles_y != 0) {      // OpenCV extends BOTH dimensions
+        ew = width + (tiles_x - width % tiles_x);
+        eh = height + (tiles_y - height % tiles_y);
+    }
+    A.tw = ew / tiles_x; A.th = eh / tiles_y;
+    const int area = A.tw * A.th;
+    int clip = 0;
+    if (clip_limit > 0.0) {
+        clip = (int)(clip_limit * area / 256);
+        if (clip < 1) clip = 1;
+    } else {
+        clip = 1 << 30;
+    }
+    A.clip = clip;
+    A.lut_scale = (float)255 / (float)area;
+    A.inv_tw = 1.0f / (float)A.tw;
+    A.inv_th = 1.0f / (float)A.th;
+    if ((st = ov2_scratch(ctx, (size_t)count * tiles_x * tiles_y * 256, &o)) != OV2_OK) return st;
+    A.lut = (uint8_t*)o;
+    OV2_LAUNCH(ctx, "clahe_lut_kernel", clahe_lut_kernel<<<dim3(tiles_x * tiles_y, count), 256, 0, ctx->stream>>>(A));
+    OV2_LAUNCH(ctx, "clahe_apply_kernel",
+               clahe_apply_kernel<<<dim3(div_up(width, 1024), height, count), 256, 0, ctx->stream>>>(A));
+    return ov2_end(ctx);
+}

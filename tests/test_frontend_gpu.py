@@ -284,3 +284,20 @@ def test_against_committed_goldens(ctx):
         assert np.abs(out - g[f"klt_{lvl}_tracked"]).max() <= KLT_TOL
     pp.close()
     cp.close()
+
+
+@pytest.mark.parametrize("w,h", [(1280, 720), (752, 480), (640, 480)])
+def test_clahe_bit_exact(ctx, w, h):
+    """ov2_clahe vs cv::CLAHE(3, Size(W/50, H/50)) (ov2slam.cpp:85-89): bit-exact, host and device buffers."""
+    imgs = np.stack([synth.make_frame(70 + i, w, h) for i in range(2)])
+    out = np.empty_like(imgs)
+    api.clahe(ctx, imgs, out, w, h, count=2)
+    for f in range(2):
+        ref = R.clahe_cv2(imgs[f]) if R.HAVE_CV2 else R.clahe_ref(imgs[f])
+        assert np.array_equal(out[f], ref), int((out[f] != ref).sum())
+    torch = pytest.importorskip("torch")
+    d_in = torch.from_numpy(imgs).cuda()
+    d_out = torch.empty_like(d_in)
+    api.clahe(ctx, d_in, d_out, w, h, count=2)
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy(), out)

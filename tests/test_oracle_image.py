@@ -161,3 +161,10 @@ def test_klt_vs_cv2():
         tb, sb = R.fb_klt_ref(prev, cur, kps, pri, 9, lvl)
         assert np.array_equal(sa, sb)
         assert np.abs(ta - tb).max() <= 1e-3
+
+
+@needs_cv2
+@pytest.mark.parametrize("w,h", [(1280, 720), (752, 480), (640, 480), (1000, 720)])
+def test_clahe_vs_cv2(w, h):
+    im = synth.make_frame(3, w, h)
+    assert np.array_equal(R.clahe_ref(im), R.clahe_cv2(im))
