@@ -56,6 +56,24 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(float(q[0]) / float(q[1]) + 0.5)))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = max(1, min(n, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -170,7 +188,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     nframes = int(min(max(6 * cores, 64), 1536))
     # warm-up steps (page in cv2, fork pool once) then K timed steps, each a bounded sample
     for _ in range(max(1, min(args.warmup, 1))):
@@ -425,7 +443,7 @@ def gpu_arm(args):
                 "frac": achieved / peak, "traffic": _ncu_traffic(dname), "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg, "kernel_time_shares": shares,
                 "note": "KLT is gather/iteration bound by construction (SURVEY.md 8d-ii): HBM fraction is low by design"}
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         cpu = None
         if world == 1 and not args.no_cpu:
             nfr = int(min(max(6 * cores, 64), 1536))

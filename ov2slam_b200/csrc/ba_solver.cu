@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_pose(const double* p, double t[3], double q
 }
 
 // SE3LeftParameterization::Plus: out = Sophus::SE3d::exp(delta) * (q, t)
-__device__ void pose_plus(const double* pose, const double* d, double* out) {
+__device__ __noinline__ void pose_plus(const double* pose, const double* d, double* out) {
     double t[3], q[4];
     load_pose(pose, t, q);
     const double ox = d[3], oy = d[4], oz = d[5];
@@ -330,12 +330,15 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
 }
 
 // ------------------------------------------------------------------ reduced camera system (one CTA)
-__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int use_smem, int add_cam_norms,
+template <bool SMEM>
+__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int add_cam_norms,
                                                                 const double* __restrict__ pose, double* __restrict__ cand) {
     extern __shared__ double sA[];
     __shared__ int s_fail;
     const int n = D.n, tid = threadIdx.x, nt = blockDim.x;
-    double* A = use_smem ? sA : D.S;
+    // SMEM is a template parameter so the small-system path compiles to LDS/STS, not generic loads
+    double* A;
+    if (SMEM) A = sA; else A = D.S;
     __shared__ double s_w[MAX_N];
     double* w = s_w;   // rhs -> solution vector (shared: the triangular solves are latency chains)
     if (tid == 0) s_fail = 0;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
         w[i] = D.gcam[i] + D.rhs[i];
     }
     __syncthreads();
-    if (use_smem) {
+    if (SMEM) {
         for (int e = tid; e < n * n; e += nt) sA[e] = D.S[e];
         __syncthreads();
     }
@@ -364,7 +367,11 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
     for (int j = 0; j < n; ++j) {
         const double d = A[(size_t)j * n + j];          // final since the previous barrier
         if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) s_fail = 1; break; }   // uniform
-        const double inv_d = 1.0 / d;
+        // 1/d sits on the per-column critical path: float reciprocal + two Newton steps in double
+        // (relative error ~2^-92 before rounding) instead of the ~300-cycle IEEE division routine
+        double inv_d = (double)__frcp_rn((float)d);
+        inv_d = inv_d * (2.0 - d * inv_d);
+        inv_d = inv_d * (2.0 - d * inv_d);
         if (tid == 0) s_ipiv[j] = rsqrt(d);
         // trailing update A[r][c] -= A[j][r] A[j][c] / d for j < r <= c: one warp per row, lanes over columns
         for (int r = j + 1 + warp; r < n; r += nwarp) {
@@ -558,9 +565,9 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     D.S = D.cn_cam + n;
     const size_t smem_need = (size_t)n * n * sizeof(double);
     const int use_smem = smem_need <= 200 * 1024 ? 1 : 0;
-    const int solve_threads = n <= 96 ? 256 : 1024;
+    const int solve_threads = 1024;   // one warp per trailing row: the per-column step is a latency chain, more warps = fewer rows each
     if (use_smem && smem_need > 48 * 1024)
-        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
 
     // candidate buffers start equal to x: parameter blocks that are not in this solve's program
     // (constant / unused) must keep their current value through pointer swaps
@@ -593,8 +600,12 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             if (sh->fn(sh->user, D.scal, (size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n, (void*)st) != 0)
                 return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
         }
-        OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
-                   ba_reduced_solve_kernel<<<1, solve_threads, use_smem ? smem_need : 0, st>>>(D, radius, first_iter, use_smem, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
+        if (use_smem)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
+                       ba_reduced_solve_kernel<true><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
+        else
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
+                       ba_reduced_solve_kernel<false><<<1, solve_threads, 0, st>>>(D, radius, first_iter, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
         OV2_LAUNCH(ctx, "ba_backsub_kernel", ba_backsub_kernel<<<div_up(D.npts, 4), 128, 0, st>>>(D, invd, cand_invd));
         OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<div_up(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
         first_iter = 0;
