@@ -38,6 +38,7 @@ enum { SC_COST = 0, SC_CAND_COST, SC_MCC, SC_STEP2, SC_CANDX2, SC_GMAX_LM, SC_GM
 
 struct BaDev {
     int ncam, npts, nobs, ncv, n;
+    int ncopy; long long copy_stride;   // privatised accumulation copies (atomic contention), in doubles
     double fx, fy, cx, cy;
     double huber_a, huber_b;
     int use_huber;
@@ -74,8 +75,8 @@ __device__ __forceinline__ void quat_to_rot(const double* q, double R[9]) {
 
 __device__ __forceinline__ void load_pose(const double* p, double t[3], double q[4]) {
     t[0] = p[0]; t[1] = p[1]; t[2] = p[2];
-    const double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);  // SE3d(q, t) normalises
-    q[0] = p[3] / n; q[1] = p[4] / n; q[2] = p[5] / n; q[3] = p[6] / n;
+    const double n = 1.0 / sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);  // SE3d(q, t) normalises
+    q[0] = p[3] * n; q[1] = p[4] * n; q[2] = p[5] * n; q[3] = p[6] * n;
 }
 
 // SE3LeftParameterization::Plus: out = Sophus::SE3d::exp(delta) * (q, t)
@@ -92,9 +93,10 @@ __device__ __noinline__ void pose_plus(const double* pose, const double* d, doub
         real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
     } else {
         theta = sqrt(th2);
-        const double h = 0.5 * theta;
-        imag = sin(h) / theta;
-        real = cos(h);
+        double sh_, ch_;
+        sincos(0.5 * theta, &sh_, &ch_);
+        imag = sh_ / theta;
+        real = ch_;
     }
     const double e[4] = {imag * ox, imag * oy, imag * oz, real};
     double Re[9];
@@ -120,11 +122,11 @@ __device__ __noinline__ void pose_plus(const double* pose, const double* d, doub
     r[0] = e[3] * q[0] + e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
     r[1] = e[3] * q[1] + e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
     r[2] = e[3] * q[2] + e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
-    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    const double n = 1.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
     out[0] = et[0] + Re[0] * t[0] + Re[1] * t[1] + Re[2] * t[2];
     out[1] = et[1] + Re[3] * t[0] + Re[4] * t[1] + Re[5] * t[2];
     out[2] = et[2] + Re[6] * t[0] + Re[7] * t[1] + Re[8] * t[2];
-    out[3] = r[0] / n; out[4] = r[1] / n; out[5] = r[2] / n; out[6] = r[3] / n;
+    out[3] = r[0] * n; out[4] = r[1] * n; out[5] = r[2] * n; out[6] = r[3] * n;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -224,6 +226,11 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
     if (l >= D.npts) return;
     const int p0 = D.lm_ptr[l], p1 = D.lm_ptr[l + 1];
     const int n = D.n;
+    // privatised accumulation copy of this CTA: the (6 Ncv)^2 system has few addresses, thousands of
+    // fp64 REDs per address serialise in L2; ncopy copies divide that contention, the reduced-solve
+    // kernel sums them when it loads the system
+    const long long coff = (long long)(blockIdx.x % D.ncopy) * D.copy_stride;
+    double* const cS = D.S + coff; double* const cRhs = D.rhs + coff; double* const cG = D.gcam + coff; double* const cCn = D.cn_cam + coff;
     // E'E, E'r
     double cnl = 0.0, ge = 0.0;
     int nact = 0;
@@ -275,22 +282,22 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
             // anchor block: F'F (upper triangle of the 6x6), F'r, column norms, E'F
             for (int e = lane; e < 36; e += 32) {
                 const int a = e / 6, b = e - 6 * a;
-                if (a <= b) atomicAdd(D.S + (size_t)(6 * sa + a) * n + 6 * sa + b, Ja[a] * Ja[b] + Ja[6 + a] * Ja[6 + b]);
+                if (a <= b) atomicAdd(cS + (size_t)(6 * sa + a) * n + 6 * sa + b, Ja[a] * Ja[b] + Ja[6 + a] * Ja[6 + b]);
             }
             if (lane < 6) {
-                atomicAdd(D.gcam + 6 * sa + lane, Ja[lane] * r0 + Ja[6 + lane] * r1);
-                atomicAdd(D.cn_cam + 6 * sa + lane, Ja[lane] * Ja[lane] + Ja[6 + lane] * Ja[6 + lane]);
+                atomicAdd(cG + 6 * sa + lane, Ja[lane] * r0 + Ja[6 + lane] * r1);
+                atomicAdd(cCn + 6 * sa + lane, Ja[lane] * Ja[lane] + Ja[6 + lane] * Ja[6 + lane]);
                 s_etf[warp][0][lane] += jl0 * Ja[lane] + jl1 * Ja[6 + lane];
             }
         }
         if (so >= 0) {
             for (int e = lane; e < 36; e += 32) {
                 const int a = e / 6, b = e - 6 * a;
-                if (a <= b) atomicAdd(D.S + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
+                if (a <= b) atomicAdd(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
             }
             if (lane < 6) {
-                atomicAdd(D.gcam + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
-                atomicAdd(D.cn_cam + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
+                atomicAdd(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
+                atomicAdd(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
                 s_etf[warp][m][lane] = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
             }
             if (lane == 0) s_slot[warp][m] = so;
@@ -299,8 +306,8 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
                 for (int e = lane; e < 36; e += 32) {
                     const int a = e / 6, b = e - 6 * a;   // a: anchor column, b: observer column
                     const double v = Ja[a] * Jo[b] + Ja[6 + a] * Jo[6 + b];
-                    if (sa < so) atomicAdd(D.S + (size_t)(6 * sa + a) * n + 6 * so + b, v);
-                    else atomicAdd(D.S + (size_t)(6 * so + b) * n + 6 * sa + a, v);
+                    if (sa < so) atomicAdd(cS + (size_t)(6 * sa + a) * n + 6 * so + b, v);
+                    else atomicAdd(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
                 }
             }
             m++;
@@ -321,27 +328,37 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
             // cannot happen (a camera observes a landmark once, and the anchor is never an observer)
             v *= 2.0;
         }
-        atomicAdd(D.S + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
+        atomicAdd(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
     }
     for (int e = lane; e < m * 6; e += 32) {
         const int i = e / 6, a = e - 6 * i;
-        atomicAdd(D.rhs + 6 * s_slot[warp][i] + a, -s_etf[warp][i][a] * ge * inv_ete);
+        atomicAdd(cRhs + 6 * s_slot[warp][i] + a, -s_etf[warp][i][a] * ge * inv_ete);
     }
 }
 
 // ------------------------------------------------------------------ reduced camera system (one CTA)
-template <bool SMEM>
-__global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter, int add_cam_norms,
-                                                                const double* __restrict__ pose, double* __restrict__ cand) {
+template <int MODE>   // 0: Cholesky in global/L2 (large n), 1: Cholesky in shared memory, 2 / 3: Gauss-Jordan in registers (n <= 63 / n <= 96)
+__global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter) {
     extern __shared__ double sA[];
     __shared__ int s_fail;
     const int n = D.n, tid = threadIdx.x, nt = blockDim.x;
-    // SMEM is a template parameter so the small-system path compiles to LDS/STS, not generic loads
+    constexpr bool SMEM = MODE == 1;
     double* A;
     if (SMEM) A = sA; else A = D.S;
     __shared__ double s_w[MAX_N];
     double* w = s_w;   // rhs -> solution vector (shared: the triangular solves are latency chains)
     if (tid == 0) s_fail = 0;
+    // fold the privatised accumulation copies into copy 0
+    if (D.ncopy > 1) {
+        const int blk = 3 * n + n * n;
+        for (int e = tid; e < blk; e += nt) {
+            double acc = D.rhs[e];
+#pragma unroll 8
+            for (int k = 1; k < D.ncopy; ++k) acc += D.rhs[e + (long long)k * D.copy_stride];   // independent loads in flight
+            D.rhs[e] = acc;
+        }
+        __syncthreads();
+    }
     // Jacobi scaling (iteration 0), LM damping, rhs = F'r - (Schur part already accumulated)
     for (int i = tid; i < n; i += nt) {
         const double cn = D.cn_cam[i];
@@ -355,6 +372,83 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
         w[i] = D.gcam[i] + D.rhs[i];
     }
     __syncthreads();
+    if (MODE >= 2) {
+        // Gauss-Jordan elimination on the augmented system [S | b] held in REGISTERS: warp w owns rows
+        // w*RPW .. w*RPW+RPW-1, lane l owns columns l + 32 k.  Each pivot step the owners publish pivot
+        // row j and column j through a double-buffered shared-memory line, then everyone updates its
+        // registers: ONE barrier per pivot and no substitution passes afterwards (a Cholesky + two
+        // triangular solves is 3n dependent steps).  The block has only ceil(n / RPW) warps: ncu showed
+        // the 32-warp version issue-bound on per-warp overhead (331 k warp-instructions for a 48 x 48
+        // system), not latency-bound.  Pivots equal those of the LDL' / Cholesky factorisation, so
+        // "pivot <= 0" is the failure test Ceres' LLT applies.  No pivoting: S is SPD after LM damping.
+        constexpr int RPW = MODE == 2 ? 4 : 6;   // rows per warp     (n <= 63 -> <= 16 warps | n <= 96 -> 16 warps)
+        constexpr int CPL = MODE == 2 ? 2 : 4;   // columns per lane  (n + 1 <= 64 | n + 1 <= 128)
+        __shared__ double s_row[2][MAX_N + 8];
+        __shared__ double s_col[2][MAX_N + 8];
+        const int wp = tid >> 5, ln = tid & 31;
+        double a[RPW][CPL];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int r = wp * RPW + i, c = ln + 32 * k;
+                double v = 0.0;
+                if (r < n && c <= n) v = c == n ? w[r] : (r <= c ? D.S[(size_t)r * n + c] : D.S[(size_t)c * n + r]);
+                a[i][k] = v;
+            }
+        for (int j = 0; j < n; ++j) {
+            const int b = j & 1, jw = j / RPW, ji = j - jw * RPW, jl = j & 31, jk = j >> 5;
+            if (wp == jw) {
+#pragma unroll
+                for (int i = 0; i < RPW; ++i)
+                    if (i == ji) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) if (ln + 32 * k <= n) s_row[b][ln + 32 * k] = a[i][k];
+                    }
+            }
+            if (ln == jl) {
+#pragma unroll
+                for (int k = 0; k < CPL; ++k)
+                    if (k == jk) {
+#pragma unroll
+                        for (int i = 0; i < RPW; ++i) if (wp * RPW + i < n) s_col[b][wp * RPW + i] = a[i][k];
+                    }
+            }
+            __syncthreads();
+            const double p = s_row[b][j];
+            if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) s_fail = 1; break; }   // uniform
+            double ip = (double)__frcp_rn((float)p);
+            ip = ip * (2.0 - p * ip);
+            ip = ip * (2.0 - p * ip);
+            double cj[RPW];
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) cj[i] = s_col[b][min(wp * RPW + i, n - 1)];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c = ln + 32 * k;
+                const double ajc = c <= n ? s_row[b][c] * ip : 0.0;
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    const int r = wp * RPW + i;
+                    a[i][k] = r == j ? ajc : a[i][k] - cj[i] * ajc;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_fail) {
+            if (tid == 0) D.scal[SC_CHOL_FAIL] = 1.0;
+            return;
+        }
+        if (ln == (n & 31)) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+                if (k == (n >> 5)) {
+#pragma unroll
+                    for (int i = 0; i < RPW; ++i) if (wp * RPW + i < n) w[wp * RPW + i] = a[i][k];
+                }
+        }
+        __syncthreads();
+    } else {
     if (SMEM) {
         for (int e = tid; e < n * n; e += nt) sA[e] = D.S[e];
         __syncthreads();
@@ -405,37 +499,46 @@ __global__ void __launch_bounds__(1024) ba_reduced_solve_kernel(BaDev D, double 
         }
     }
     __syncthreads();
+    }   // Cholesky modes
     for (int i = tid; i < n; i += nt) D.z[i] = w[i];   // the back-substitution kernel reads z from global
-    // candidate camera poses: Plus(x, delta), delta = -z ; step / candidate norms ; gradient max norm
-    double st2 = 0.0, cx2 = 0.0, gm = 0.0;
-    for (int c = tid; c < D.ncam; c += nt) {
-        const int s = D.cam_slot[c];
-        if (s < 0) continue;
-        double d[6], g[6], out[7], pg[7];
-        for (int k = 0; k < 6; ++k) { d[k] = -w[6 * s + k]; g[k] = -D.gcam[6 * s + k]; }
-        pose_plus(pose + 7 * c, d, out);
-        pose_plus(pose + 7 * c, g, pg);
-        for (int k = 0; k < 7; ++k) {
-            cand[7 * c + k] = out[k];
-            const double df = pose[7 * c + k] - out[k];
-            st2 += df * df;
-            cx2 += out[k] * out[k];
-            gm = fmax(gm, fabs(pose[7 * c + k] - pg[k]));
-        }
-    }
-    st2 = warp_sum(st2);
-    cx2 = warp_sum(cx2);
-    for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(FULL, gm, o));
-    if ((tid & 31) == 0) {
-        // sharded solve: every rank solves the same reduced system; only rank 0 contributes the camera norms
-        if (add_cam_norms && st2 != 0.0) atomicAdd(D.scal + SC_STEP2, st2);
-        if (add_cam_norms && cx2 != 0.0) atomicAdd(D.scal + SC_CANDX2, cx2);
-        atomic_max_pos(D.scal + SC_GMAX_CAM, gm);
-    }
 }
 
 // ------------------------------------------------------------------ back-substitution (warp / landmark)
-__global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* __restrict__ invd, double* __restrict__ cand_invd) {
+// The camera-side Plus() work rides along as two extra CTAs (candidate poses; gradient projection):
+// SE3 exp is a long chain of fp64 software routines (sqrt, division, sincos), ~20 us of pure latency
+// for a handful of threads - here it overlaps the landmark CTAs instead of extending the
+// single-CTA reduced solve.
+__global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* __restrict__ pose, double* __restrict__ cand_pose,
+                                                         const double* __restrict__ invd, double* __restrict__ cand_invd,
+                                                         int nlm_blocks, int add_cam_norms, int want_gmax) {
+    if ((int)blockIdx.x >= nlm_blocks) {
+        const int which = blockIdx.x - nlm_blocks;      // 0: candidate = Plus(x, -z), 1: |x - Plus(x, -g)|_inf
+        if (which == 1 && !want_gmax) return;
+        double st2 = 0.0, cx2 = 0.0, gm = 0.0;
+        for (int c = threadIdx.x; c < D.ncam; c += blockDim.x) {
+            const int s = D.cam_slot[c];
+            if (s < 0) continue;
+            double d[6], out[7];
+            const double* v = which == 0 ? D.z : D.gcam;
+            for (int k = 0; k < 6; ++k) d[k] = -v[6 * s + k];
+            pose_plus(pose + 7 * c, d, out);
+            for (int k = 0; k < 7; ++k) {
+                const double df = pose[7 * c + k] - out[k];
+                if (which == 0) { cand_pose[7 * c + k] = out[k]; st2 += df * df; cx2 += out[k] * out[k]; }
+                else gm = fmax(gm, fabs(df));
+            }
+        }
+        st2 = warp_sum(st2);
+        cx2 = warp_sum(cx2);
+        for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(FULL, gm, o));
+        if ((threadIdx.x & 31) == 0) {
+            // sharded solve: every rank solves the same reduced system; only rank 0 contributes the camera norms
+            if (which == 0 && add_cam_norms && st2 != 0.0) atomicAdd(D.scal + SC_STEP2, st2);
+            if (which == 0 && add_cam_norms && cx2 != 0.0) atomicAdd(D.scal + SC_CANDX2, cx2);
+            if (which == 1) atomic_max_pos(D.scal + SC_GMAX_CAM, gm);
+        }
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int l = blockIdx.x * 4 + warp;
     if (l >= D.npts) return;
@@ -563,12 +666,28 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     D.gcam = D.rhs + n;
     D.cn_cam = D.gcam + n;
     D.S = D.cn_cam + n;
-    const size_t smem_need = (size_t)n * n * sizeof(double);
-    const int use_smem = smem_need <= 200 * 1024 ? 1 : 0;
-    const int solve_threads = 1024;   // one warp per trailing row: the per-column step is a latency chain, more warps = fewer rows each
-    if (use_smem && smem_need > 48 * 1024)
-        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
-
+    D.copy_stride = 3 * (long long)n + (long long)n * n;
+    {
+        // as many copies as fit the scratch block (sized for one MAX_N system), at most 8; the sharded
+        // path keeps one copy because the block is what gets all-reduced
+        long long cap = 3LL * MAX_N + (long long)MAX_N * MAX_N;
+        long long k = D.copy_stride > 0 ? cap / D.copy_stride : 1;
+        D.ncopy = (int)(k < 1 ? 1 : (k > 8 ? 8 : k));
+        if (sh && sh->fn) D.ncopy = 1;
+        if (getenv("OV2_BA_NCOPY")) { int e = atoi(getenv("OV2_BA_NCOPY")); if (e >= 1 && e <= D.ncopy) D.ncopy = e; }
+    }
+    // reduced-system solver: Gauss-Jordan in shared memory for small windows, Cholesky in shared memory
+    // while it fits, Cholesky in global/L2 beyond (C5: 288 x 288)
+    int solve_mode = n <= 63 ? 2 : (n <= 96 ? 3 : ((size_t)n * n * sizeof(double) <= 200 * 1024 ? 1 : 0));
+    if (getenv("OV2_BA_SOLVER")) {
+        const int e = atoi(getenv("OV2_BA_SOLVER"));   // 0/1 force the Cholesky paths (tests)
+        if (e == 0 || (e == 1 && (size_t)n * n * sizeof(double) <= 200 * 1024)) solve_mode = e;
+    }
+    const size_t smem_need = solve_mode == 1 ? (size_t)n * n * sizeof(double) : 0;   // modes 2/3 live in registers
+    int solve_threads = solve_mode == 2 ? 32 * div_up(n, 4) : (solve_mode == 3 ? 32 * div_up(n, 6) : 1024);
+    if (solve_threads < 32) solve_threads = 32;   // n == 0: every pose constant, only landmarks move
+    if (smem_need > 48 * 1024)
+        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
     // candidate buffers start equal to x: parameter blocks that are not in this solve's program
     // (constant / unused) must keep their current value through pointer swaps
     OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
@@ -576,7 +695,7 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     // One accumulation buffer [scal | rhs | gcam | cn_cam | S] -> one memset per LM iteration.
     // Per iteration: memset, (Jacobian evaluation if x is new), Schur, reduced solve, back-substitution,
     // candidate cost, ONE readback of the scalars; the controller below replays Ceres' decisions.
-    const size_t accum_bytes = sizeof(double) * ((size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n);
+    const size_t accum_bytes = sizeof(double) * ((size_t)SC_COUNT + (size_t)D.ncopy * (size_t)D.copy_stride);
     double h[SC_COUNT];
     double x_cost = 0.0, minimum_cost = DBL_MAX, xnorm = -1.0, gmax = DBL_MAX;
     double radius = 1e4, decrease_factor = 2.0;
@@ -600,13 +719,20 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             if (sh->fn(sh->user, D.scal, (size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n, (void*)st) != 0)
                 return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
         }
-        if (use_smem)
-            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
-                       ba_reduced_solve_kernel<true><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
+        if (solve_mode == 2)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<2><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
+        else if (solve_mode == 3)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<3><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
+        else if (solve_mode == 1)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<1><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter));
         else
-            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel",
-                       ba_reduced_solve_kernel<false><<<1, solve_threads, 0, st>>>(D, radius, first_iter, (!sh || sh->rank == 0) ? 1 : 0, pose, cand_pose));
-        OV2_LAUNCH(ctx, "ba_backsub_kernel", ba_backsub_kernel<<<div_up(D.npts, 4), 128, 0, st>>>(D, invd, cand_invd));
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<0><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
+        {
+            const int nlm_blocks = div_up(D.npts, 4);
+            OV2_LAUNCH(ctx, "ba_backsub_kernel",
+                       ba_backsub_kernel<<<nlm_blocks + 2, 128, 0, st>>>(D, pose, cand_pose, invd, cand_invd, nlm_blocks,
+                                                                         (!sh || sh->rank == 0) ? 1 : 0, x_is_new ? 1 : 0));
+        }
         OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<div_up(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
         first_iter = 0;
         if (sh && sh->fn) {

@@ -20,6 +20,7 @@
 #include "stdsort_emul.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -38,6 +39,7 @@ struct FastArgs {
     uint32_t* cand;             // [count][ncells][cap]  (resp << 16) | (ky << 8) | kx
     int32_t* cand_n;            // [count][ncells]
     int32_t* overflow;          // set to 1 if a cell had more than cap candidates
+    int score_mode;             // 0: bisection on the 9-run bit test, 1: sliding-window min (sparse table)
 };
 
 // ---------------------------------------------------------------------------------- F1
@@ -105,7 +107,34 @@ __global__ void fast_cells_kernel(FastArgs A) {
         int d[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) d[k] = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
-        int lo = th + 1, hi = 256;   // P(lo) holds (corner at th), P(256) cannot
+        int lo;
+        if (A.score_mode == 1) {
+            // s = max_k min(d[k..k+8]) (bright) / max_k min(-d[k..k+8]) (dark) with a sparse table:
+            // m2 = windows of 2, m4 of 4, m8 of 8, then one more element -> 9.  inline PTX min/max keeps
+            // this as written (a naive 16x8 min/max nest was folded into VIMNMX3 chains
+            // that returned max(d)).
+            int best = 0;
+#pragma unroll
+            for (int pol = 0; pol < 2; ++pol) {
+                int e[16], m2[16], m4[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) e[k] = pol ? -d[k] : d[k];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) asm("min.s32 %0, %1, %2;" : "=r"(m2[k]) : "r"(e[k]), "r"(e[(k + 1) & 15]));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) asm("min.s32 %0, %1, %2;" : "=r"(m4[k]) : "r"(m2[k]), "r"(m2[(k + 2) & 15]));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    int m8, m9;
+                    asm("min.s32 %0, %1, %2;" : "=r"(m8) : "r"(m4[k]), "r"(m4[(k + 4) & 15]));
+                    asm("min.s32 %0, %1, %2;" : "=r"(m9) : "r"(m8), "r"(e[(k + 8) & 15]));
+                    asm("max.s32 %0, %1, %2;" : "=r"(best) : "r"(best), "r"(m9));
+                }
+            }
+            lo = best;
+        } else {
+        lo = th + 1;
+        int hi = 256;   // P(lo) holds (corner at th), P(256) cannot
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             unsigned bm = 0, dm = 0;
@@ -118,6 +147,7 @@ __global__ void fast_cells_kernel(FastArgs A) {
             bm &= bm >> 1; bm &= bm >> 2; bm &= bm >> 4; bm &= bm >> 1;
             dm &= dm >> 1; dm &= dm >> 2; dm &= dm >> 4; dm &= dm >> 1;
             if ((bm | dm) & 0xFFFFu) lo = mid; else hi = mid;
+        }
         }
         sc[pi] = (uint8_t)lo;   // th < s <= 255
     }
@@ -497,6 +527,7 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     FA.img = pyr->l0; FA.w = W; FA.h = H; FA.pitch = (int)pyr->l0_pitch; FA.fstride = (long long)pyr->l0_fstride;
     FA.first = first; FA.cs = cellsize; FA.nwc = nwc; FA.nhc = nhc; FA.cap = cap;
     FA.th = d_th; FA.cand = d_cand; FA.cand_n = d_candn; FA.overflow = d_ovf;
+    FA.score_mode = getenv("OV2_FAST_SCORE") ? atoi(getenv("OV2_FAST_SCORE")) : 1;
     {
         int threads = cellsize > 24 ? 128 : 32;
         size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
@@ -577,6 +608,7 @@ extern "C" ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int
     if ((st = ov2_scratch(ctx, sizeof(int32_t), &o)) != OV2_OK) return st;
     FA.overflow = (int32_t*)o;
     OV2_CUDA(ctx, cudaMemsetAsync(FA.overflow, 0, sizeof(int32_t), ctx->stream));
+    FA.score_mode = getenv("OV2_FAST_SCORE") ? atoi(getenv("OV2_FAST_SCORE")) : 1;
     int threads = cellsize > 24 ? 128 : 32;
     size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
     OV2_LAUNCH(ctx, "fast_cells_kernel", fast_cells_kernel<<<dim3(ncells, 1), threads, smem, ctx->stream>>>(FA));

@@ -15,6 +15,16 @@ constexpr int OUT_H = TY;               // 8 output rows
 constexpr int IN_ROWS = 2 * OUT_H + 3;  // 19
 constexpr int IN_WORDS = 66;            // 264 bytes: input cols [2*x0-4, 2*x0+260)
 
+// 5-tap [1 4 6 4 1] on packed bytes with dp4a: the four outputs of a thread read input bytes
+// 2*x0-2 .. 2*x0+8, i.e. bytes 2.. of word W0 up to byte 0 of word W3 (W0 = tile word 2*tx)
+__device__ __forceinline__ void hrow4(const uint32_t* w, int& h0, int& h1, int& h2, int& h3) {
+    const uint32_t W0 = w[0], W1 = w[1], W2 = w[2], W3 = w[3];
+    h0 = (int)__dp4a(W0, 0x04010000u, __dp4a(W1, 0x00010406u, 0u));   // bytes: W0[2]*1 + W0[3]*4 + W1[0]*6 + W1[1]*4 + W1[2]*1
+    h1 = (int)__dp4a(W1, 0x04060401u, __dp4a(W2, 0x00000001u, 0u));   // W1[0..3]*(1,4,6,4) + W2[0]*1
+    h2 = (int)__dp4a(W1, 0x04010000u, __dp4a(W2, 0x00010406u, 0u));
+    h3 = (int)__dp4a(W2, 0x04060401u, __dp4a(W3, 0x00000001u, 0u));
+}
+
 __global__ void __launch_bounds__(TX* TY)
 pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, long long sfstride,
                 uint8_t* __restrict__ dst, int dw, int dh, int dpitch, long long dfstride, int first) {
@@ -23,26 +33,35 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, lon
     src += sfstride * frame;
     dst += dfstride * frame;
     const int ox0 = blockIdx.x * OUT_W, oy0 = blockIdx.y * OUT_H;
-    const int ix0 = 2 * ox0 - 4;  // input column of tile byte 0 (multiple of 4 minus 4)
+    const int ix0 = 2 * ox0 - 4;  // input column of tile byte 0 (multiple of 4)
     const int iy0 = 2 * oy0 - 2;
-    const int tid = threadIdx.y * TX + threadIdx.x;
 
-    const bool interior = ix0 >= 0 && ix0 + IN_WORDS * 4 <= sw && iy0 >= 0 && iy0 + IN_ROWS <= sh &&
-                          ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch) & 3) == 0;
-    if (interior) {
-        for (int i = tid; i < IN_ROWS * IN_WORDS; i += TX * TY) {
-            int r = i / IN_WORDS, c = i - r * IN_WORDS;
-            tile[r][c] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(iy0 + r) * spitch + ix0) + c);
-        }
-    } else {
-        uint8_t* tb = reinterpret_cast<uint8_t*>(&tile[0][0]);
-        for (int i = tid; i < IN_ROWS * IN_WORDS * 4; i += TX * TY) {
-            int r = i / (IN_WORDS * 4), c = i - r * (IN_WORDS * 4);
-            int y = reflect101(iy0 + r, sh), x = reflect101(ix0 + c, sw);
-            // far outside (only beyond what any in-range output needs): clamp for safety
-            y = clampi(y, 0, sh - 1);
-            x = clampi(x, 0, sw - 1);
-            tb[i] = __ldg(src + (size_t)y * spitch + x);
+    // Fixed 2-D mapping (no divisions): rows ty, ty+8, ty+16; words tx, tx+32 and the 2 tail words.
+    // BORDER_REFLECT_101 in y only changes which row is read, so whole words are still loaded;
+    // only words that stick out of [0, sw) in x are assembled byte by byte.
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch) & 3) == 0;
+    for (int r = threadIdx.y; r < IN_ROWS; r += TY) {
+        int y = reflect101(iy0 + r, sh);
+        y = clampi(y, 0, sh - 1);
+        const uint8_t* grow = src + (size_t)y * spitch;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = threadIdx.x + 32 * k;
+            if (c >= IN_WORDS) break;
+            const int x0 = ix0 + 4 * c;
+            uint32_t wv;
+            if (aligned && x0 >= 0 && x0 + 4 <= sw) {
+                wv = __ldg(reinterpret_cast<const uint32_t*>(grow + x0));
+            } else {
+                wv = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    int x = reflect101(x0 + b, sw);
+                    x = clampi(x, 0, sw - 1);   // far outside: only beyond what any in-range output needs
+                    wv |= (uint32_t)__ldg(grow + x) << (8 * b);
+                }
+            }
+            tile[r][c] = wv;
         }
     }
     __syncthreads();
@@ -50,28 +69,18 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, lon
     const int oy = oy0 + threadIdx.y;
     const int ox = ox0 + 4 * threadIdx.x;
     if (oy >= dh || ox >= dw) return;
-    // vertical 5-tap on the 11 input columns this thread needs: tile bytes 8*tx+2 .. 8*tx+12
-    int v[16];
+    // horizontal pass per input row (dp4a), vertical [1 4 6 4 1] on the four running sums
     const int r0 = 2 * threadIdx.y;
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
 #pragma unroll
-    for (int wq = 0; wq < 4; ++wq) {
-        uint32_t a = tile[r0][2 * threadIdx.x + wq], b = tile[r0 + 1][2 * threadIdx.x + wq],
-                 c = tile[r0 + 2][2 * threadIdx.x + wq], d = tile[r0 + 3][2 * threadIdx.x + wq],
-                 e = tile[r0 + 4][2 * threadIdx.x + wq];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int sh8 = 8 * k;
-            v[4 * wq + k] = (int)((a >> sh8) & 255) + 4 * (int)((b >> sh8) & 255) + 6 * (int)((c >> sh8) & 255) +
-                            4 * (int)((d >> sh8) & 255) + (int)((e >> sh8) & 255);
-        }
+    for (int r = 0; r < 5; ++r) {
+        int h0, h1, h2, h3;
+        hrow4(&tile[r0 + r][2 * threadIdx.x], h0, h1, h2, h3);
+        const int kw = (r == 0 || r == 4) ? 1 : ((r == 2) ? 6 : 4);
+        v0 += kw * h0; v1 += kw * h1; v2 += kw * h2; v3 += kw * h3;
     }
-    uint32_t packed = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int b = 2 + 2 * j;  // v index of input col 2*(ox+j)-2
-        int s = v[b] + 4 * v[b + 1] + 6 * v[b + 2] + 4 * v[b + 3] + v[b + 4];
-        packed |= (uint32_t)((s + 128) >> 8) << (8 * j);
-    }
+    const uint32_t packed = (uint32_t)((v0 + 128) >> 8) | ((uint32_t)((v1 + 128) >> 8) << 8) |
+                            ((uint32_t)((v2 + 128) >> 8) << 16) | ((uint32_t)((v3 + 128) >> 8) << 24);
     uint8_t* drow = dst + (size_t)oy * dpitch + ox;
     if (ox + 3 < dw && ((reinterpret_cast<uintptr_t>(drow)) & 3) == 0) {
         *reinterpret_cast<uint32_t*>(drow) = packed;
