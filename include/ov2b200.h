@@ -170,6 +170,14 @@ typedef struct {
     const int32_t* obs_cam;        /* [nobs] observing camera (non-anchor observations) */
     const int32_t* obs_lm;         /* [nobs] landmark index, sorted ascending (CSR by landmark) */
     const double*  obs_px;         /* [nobs][2] */
+    /* stereo windows (NULL / ignored for mono): residual type per observation -
+     *   0 left camera, other keyframe    ReprojectionErrorKSE3AnchInvDepth             (ceres_parametrization.cpp:361-473)
+     *   1 right camera, other keyframe   ReprojectionErrorRightCamKSE3AnchInvDepth     (:579-712)
+     *   2 right camera, anchor keyframe  ReprojectionErrorRightAnchCamKSE3AnchInvDepth (:476-577; obs_cam = anchor)
+     * Kr = right calibration [4], Trl = constant right-from-left extrinsic [7] (tx..tz, qx..qw). */
+    const uint8_t* obs_type;       /* [nobs] or NULL */
+    const double*  Kr;             /* [4] or NULL */
+    const double*  Trl;            /* [7] or NULL */
 } ov2_ba_problem;
 
 typedef struct {
@@ -179,6 +187,9 @@ typedef struct {
     double function_tolerance; /* 1e-3 (:463) */
     int    use_robust;         /* buse_robust_cost */
     int    apply_l2_after_robust; /* (:603) */
+    int    refine_loss;        /* refinement loss: -1 = as the reference decides (trivial loss iff left-camera AND
+                                * other-frame right-camera residuals both survive the first scan, :606-608; i.e.
+                                * mono windows keep Huber), 0 = keep the robust loss, 1 = trivial loss */
 } ov2_ba_opts;
 
 typedef struct {

@@ -146,40 +146,65 @@ def lm_step_rejected(radius, decrease_factor):
 # ------------------------------------------------------------------ residuals
 def evaluate(pb, pose, invd, idx, need_jac=True):
     """All residual blocks `idx` at (pose, invd).  Returns dict with r (n,2), chi2, depth_pos and,
-    if need_jac, Ja (n,2,6) anchor, Jo (n,2,6) observer, Jl (n,2) inverse depth."""
+    if need_jac, Ja (n,2,6) anchor, Jo (n,2,6) observer, Jl (n,2) inverse depth.
+
+    obs_type (optional, default all 0):
+      0  left-camera observation in another keyframe    ReprojectionErrorKSE3AnchInvDepth        (:361-473)
+      1  right-camera observation in another keyframe   ReprojectionErrorRightCamKSE3AnchInvDepth (:579-712)
+      2  right-camera observation in the anchor frame   ReprojectionErrorRightAnchCamKSE3AnchInvDepth (:476-577)
+         (depends on the inverse depth only: calibrations and the extrinsic are constant blocks)
+    """
     fx, fy, cx, cy = pb["K"]
     lm = pb["obs_lm"][idx]
     ca = pb["lm_anchor_cam"][lm]
     co = pb["obs_cam"][idx]
+    typ = pb["obs_type"][idx] if pb.get("obs_type") is not None else np.zeros(len(idx), np.uint8)
+    n = len(lm)
     ta, qa = pose[ca, :3], quat_normalize(pose[ca, 3:])
     to, qo = pose[co, :3], quat_normalize(pose[co, 3:])
     Rwa, Rwc = quat_to_rot(qa), quat_to_rot(qo)
     zanch = 1.0 / invd[lm]
     ua = pb["lm_anchor_px"][lm]
     # invK * [u, v, 1]
-    bearing = np.stack([(ua[:, 0] - cx) / fx, (ua[:, 1] - cy) / fy, np.ones(len(lm))], -1)
+    bearing = np.stack([(ua[:, 0] - cx) / fx, (ua[:, 1] - cy) / fy, np.ones(n)], -1)
     anchpt = zanch[:, None] * bearing
-    wpt = (Rwa @ anchpt[..., None])[..., 0] + ta
+    rot_ap = (Rwa @ anchpt[..., None])[..., 0]
+    wpt = rot_ap + ta
     Rcw = np.swapaxes(Rwc, -1, -2)
     lcam = (Rcw @ (wpt - to)[..., None])[..., 0]
-    linvz = 1.0 / lcam[:, 2]
-    pred = np.stack([fx * lcam[:, 0] * linvz + cx, fy * lcam[:, 1] * linvz + cy], -1)
+    right = typ > 0
+    campt = lcam.copy()
+    kfx, kfy, kcx, kcy = (np.full(n, v) for v in (fx, fy, cx, cy))
+    M = Rcw.copy()                      # d(campt)/d(wpt)
+    if right.any():
+        rfx, rfy, rcx, rcy = pb["Kr"]
+        trl = np.asarray(pb["Trl"], np.float64)
+        Rrl = quat_to_rot(quat_normalize(trl[3:]))
+        src = np.where((typ == 2)[:, None], anchpt, lcam)          # anchor-frame right obs: Trl * anchpt
+        rc = (Rrl @ src[..., None])[..., 0] + trl[:3]
+        campt = np.where(right[:, None], rc, campt)
+        kfx, kfy = np.where(right, rfx, kfx), np.where(right, rfy, kfy)
+        kcx, kcy = np.where(right, rcx, kcx), np.where(right, rcy, kcy)
+        M = np.where((typ == 1)[:, None, None], Rrl @ Rcw, M)
+        M = np.where((typ == 2)[:, None, None], np.broadcast_to(Rrl, M.shape), M)
+    linvz = 1.0 / campt[:, 2]
+    pred = np.stack([kfx * campt[:, 0] * linvz + kcx, kfy * campt[:, 1] * linvz + kcy], -1)
     r = pred - pb["obs_px"][idx]
-    out = dict(r=r, chi2=(r * r).sum(-1), depth_pos=lcam[:, 2] > 0, lm=lm, ca=ca, co=co)
+    out = dict(r=r, chi2=(r * r).sum(-1), depth_pos=campt[:, 2] > 0, lm=lm, ca=ca, co=co, typ=typ)
     if need_jac:
-        n = len(lm)
         linvz2 = linvz * linvz
         Jc = np.zeros((n, 2, 3))
-        Jc[:, 0, 0] = linvz * fx
-        Jc[:, 0, 2] = -lcam[:, 0] * linvz2 * fx
-        Jc[:, 1, 1] = linvz * fy
-        Jc[:, 1, 2] = -lcam[:, 1] * linvz2 * fy
-        JR = Jc @ Rcw
+        Jc[:, 0, 0] = linvz * kfx
+        Jc[:, 0, 2] = -campt[:, 0] * linvz2 * kfx
+        Jc[:, 1, 1] = linvz * kfy
+        Jc[:, 1, 2] = -campt[:, 1] * linvz2 * kfy
+        JR = Jc @ M
         sk = hat(wpt)
         JRs = JR @ sk
-        out["Ja"] = np.concatenate([JR, -JRs], -1)
-        out["Jo"] = np.concatenate([-JR, JRs], -1)
-        Jlam = -zanch[:, None] * (Rwa @ anchpt[..., None])[..., 0]
+        pose_dep = (typ != 2)[:, None, None]
+        out["Ja"] = np.where(pose_dep, np.concatenate([JR, -JRs], -1), 0.0)
+        out["Jo"] = np.where(pose_dep, np.concatenate([-JR, JRs], -1), 0.0)
+        Jlam = -zanch[:, None] * np.where((typ == 2)[:, None], anchpt, rot_ap)
         out["Jl"] = (JR @ Jlam[..., None])[..., 0]
     return out
 
@@ -211,9 +236,11 @@ def ceres_solve(pb, pose, invd, active, max_iters, huber_a, function_tolerance=1
     co_i = pb["obs_cam"][idx]
     const = pb["pose_const"].astype(bool)
     # Program::RemoveFixedBlocks: constant blocks and blocks no residual uses drop out
+    typ_i = pb["obs_type"][idx] if pb.get("obs_type") is not None else np.zeros(nobs, np.uint8)
+    pose_dep = typ_i != 2                  # anchor-frame right-camera residuals depend on lambda only
     cam_used = np.zeros(ncam, bool)
-    cam_used[ca_i] = True
-    cam_used[co_i] = True
+    cam_used[ca_i[pose_dep]] = True
+    cam_used[co_i[pose_dep]] = True
     cam_var = cam_used & ~const
     lm_var = np.zeros(npts, bool)
     lm_var[lm_i] = True
@@ -224,6 +251,8 @@ def ceres_solve(pb, pose, invd, active, max_iters, huber_a, function_tolerance=1
     lm_slot[lm_var] = np.arange(lm_var.sum())
     nlv = int(lm_var.sum())
     sa, so, sl = cam_slot[ca_i], cam_slot[co_i], lm_slot[lm_i]
+    sa = np.where(pose_dep, sa, -1)
+    so = np.where(pose_dep, so, -1)
     ma, mo = sa >= 0, so >= 0
 
     def cost_and_corr(ev):
@@ -444,7 +473,7 @@ def ceres_solve(pb, pose, invd, active, max_iters, huber_a, function_tolerance=1
 
 # ------------------------------------------------------------------ Optimizer::localBA solve part
 def local_ba(pb, max_iters_robust=5, max_iters_refine=10, huber_th=5.9915, function_tolerance=1e-3,
-             use_robust=True, apply_l2_after_robust=True, log=None):
+             use_robust=True, apply_l2_after_robust=True, log=None, refine_trivial_loss=None):
     """Solve section of Optimizer::localBA (optimizer.cpp:436-735), mono residual blocks.
     Updates pb["pose"], pb["lm_invdepth"] in place.  Returns a result dict incl. `flags`
     (uint8[nobs]: bit0 = outlier after solve #1, bit1 = after solve #2)."""
@@ -463,9 +492,14 @@ def local_ba(pb, max_iters_robust=5, max_iters_refine=10, huber_th=5.9915, funct
                termination=s1["termination"], summaries=[s1])
     if apply_l2_after_robust and use_robust and bad1.any():
         active = active & ~bad1                      # problem.RemoveResidualBlock (optimizer.cpp:518-521)
-        # mono windows keep the Huber loss in the refinement (the wrapper is only reset when both the
-        # mono and the right-camera lists are non-empty, optimizer.cpp:606-608)
-        pose, invd, s2, last2 = ceres_solve(pb, pose, invd, active, max_iters_refine, a, function_tolerance, log)
+        # mono windows keep the Huber loss in the refinement: the wrapper is only reset to the trivial
+        # loss when both the left-camera and the other-frame right-camera residual lists are still
+        # non-empty after the first outlier scan (optimizer.cpp:606-608)
+        if refine_trivial_loss is None:
+            typ = pb["obs_type"] if pb.get("obs_type") is not None else np.zeros(nobs, np.uint8)
+            refine_trivial_loss = bool((active & (typ == 0)).any() and (active & (typ == 1)).any())
+        pose, invd, s2, last2 = ceres_solve(pb, pose, invd, active, max_iters_refine,
+                                            None if refine_trivial_loss else a, function_tolerance, log)
         bad2 = active & ((last2["chi2"] > th) | ~last2["depth_pos"])
         flags[bad2] |= 2
         res.update(iters_refine=s2["iterations"], initial_cost=s2["initial_cost"], final_cost=s2["final_cost"],

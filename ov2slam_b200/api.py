@@ -46,12 +46,14 @@ class BaProblem(C.Structure):
     _fields_ = [("ncam", C.c_int32), ("npts", C.c_int32), ("nobs", C.c_int32),
                 ("K", C.c_void_p), ("pose", C.c_void_p), ("pose_const", C.c_void_p),
                 ("lm_anchor_cam", C.c_void_p), ("lm_anchor_px", C.c_void_p), ("lm_invdepth", C.c_void_p),
-                ("obs_cam", C.c_void_p), ("obs_lm", C.c_void_p), ("obs_px", C.c_void_p)]
+                ("obs_cam", C.c_void_p), ("obs_lm", C.c_void_p), ("obs_px", C.c_void_p),
+                ("obs_type", C.c_void_p), ("Kr", C.c_void_p), ("Trl", C.c_void_p)]
 
 
 class BaOpts(C.Structure):
     _fields_ = [("max_iters_robust", C.c_int), ("max_iters_refine", C.c_int), ("huber_th", C.c_double),
-                ("function_tolerance", C.c_double), ("use_robust", C.c_int), ("apply_l2_after_robust", C.c_int)]
+                ("function_tolerance", C.c_double), ("use_robust", C.c_int), ("apply_l2_after_robust", C.c_int),
+                ("refine_loss", C.c_int)]
 
 
 class BaResult(C.Structure):
@@ -318,8 +320,18 @@ class FeatureExtractor:
                                                  int(per_frame or 0), _ptr(pts), _ptr(desc_out), _ptr(valid_out)))
 
 
+def _stereo_ptrs(pb: dict, keep: dict):
+    """(obs_type, Kr, Trl) pointers for a stereo window, (None, None, None) for a mono one."""
+    if pb.get("obs_type") is None:
+        return None, None, None
+    keep["obs_type"] = np.ascontiguousarray(pb["obs_type"], np.uint8)
+    keep["Kr"] = np.ascontiguousarray(pb["Kr"], np.float64)
+    keep["Trl"] = np.ascontiguousarray(pb["Trl"], np.float64)
+    return keep["obs_type"].ctypes.data, keep["Kr"].ctypes.data, keep["Trl"].ctypes.data
+
+
 DEFAULT_BA_OPTS = dict(max_iters_robust=5, max_iters_refine=10, huber_th=5.9915, function_tolerance=1e-3,
-                       use_robust=1, apply_l2_after_robust=1)
+                       use_robust=1, apply_l2_after_robust=1, refine_loss=-1)
 
 
 class Optimizer:
@@ -341,7 +353,7 @@ class Optimizer:
         assert keep["obs_cam"].dtype == np.int32 and keep["pose_const"].dtype == np.uint8
         p = BaProblem(ncam, npts, nobs, *[keep[k].ctypes.data for k in
                                           ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
-                                           "obs_cam", "obs_lm", "obs_px")])
+                                           "obs_cam", "obs_lm", "obs_px")], *_stereo_ptrs(pb, keep))
         res = BaResult()
         flags = np.zeros(nobs, np.uint8)
         self.ctx.check(self.ctx.lib.ov2_localba_solve(self.ctx.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data))
@@ -378,6 +390,8 @@ def partition_ba_problem(pb: dict, world: int):
                   obs_cam=np.ascontiguousarray(pb["obs_cam"][obs]),
                   obs_lm=np.ascontiguousarray(remap[pb["obs_lm"][obs]].astype(np.int32)),
                   obs_px=np.ascontiguousarray(pb["obs_px"][obs]))
+        if pb.get("obs_type") is not None:
+            sh.update(obs_type=np.ascontiguousarray(pb["obs_type"][obs]), Kr=pb["Kr"].copy(), Trl=pb["Trl"].copy())
         shards.append((sh, lms, obs))
     return shards
 
@@ -420,7 +434,7 @@ def local_ba_sharded(ctx: Context, shard: dict, allreduce_cb, rank: int, **opts)
             ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px")}
     p = BaProblem(len(keep["pose"]), len(keep["lm_invdepth"]), len(keep["obs_cam"]),
                   *[keep[k].ctypes.data for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
-                                                  "obs_cam", "obs_lm", "obs_px")])
+                                                  "obs_cam", "obs_lm", "obs_px")], *_stereo_ptrs(shard, keep))
     res = BaResult()
     flags = np.zeros(max(len(keep["obs_cam"]), 1), np.uint8)
     ctx.check(ctx.lib.ov2_localba_solve_sharded(ctx.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data,

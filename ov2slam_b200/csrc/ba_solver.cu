@@ -34,12 +34,15 @@ constexpr int MAX_VAR_CAMS = 64;
 constexpr int MAX_N = 6 * MAX_VAR_CAMS;
 constexpr double SOPHUS_EPS = 1e-10;
 
-enum { SC_COST = 0, SC_CAND_COST, SC_MCC, SC_STEP2, SC_CANDX2, SC_GMAX_LM, SC_GMAX_CAM, SC_CHOL_FAIL, SC_NBAD, SC_COUNT = 16 };
+enum { SC_COST = 0, SC_CAND_COST, SC_MCC, SC_STEP2, SC_CANDX2, SC_GMAX_LM, SC_GMAX_CAM, SC_CHOL_FAIL, SC_NBAD, SC_NLEFT, SC_NRIGHT, SC_COUNT = 16 };
 
 struct BaDev {
     int ncam, npts, nobs, ncv, n;
     int ncopy; long long copy_stride;   // privatised accumulation copies (atomic contention), in doubles
     double fx, fy, cx, cy;
+    double rfx, rfy, rcx, rcy;          // right calibration (stereo residual blocks)
+    double Rrl[9], trl[3];              // constant right-from-left extrinsic
+    const uint8_t* obs_type;            // NULL: all left-camera blocks
     double huber_a, huber_b;
     int use_huber;
     const uint8_t* pose_const;
@@ -164,12 +167,23 @@ __global__ void __launch_bounds__(128) ba_eval_kernel(BaDev D, const double* __r
         // Rcw = Rwc^T
         const double lc[3] = {Rwc[0] * dv[0] + Rwc[3] * dv[1] + Rwc[6] * dv[2], Rwc[1] * dv[0] + Rwc[4] * dv[1] + Rwc[7] * dv[2],
                               Rwc[2] * dv[0] + Rwc[5] * dv[1] + Rwc[8] * dv[2]};
-        const double linvz = 1.0 / lc[2];
-        double r0 = D.fx * lc[0] * linvz + D.cx - D.obs_px[2 * i];
-        double r1 = D.fy * lc[1] * linvz + D.cy - D.obs_px[2 * i + 1];
+        // residual type (stereo windows): 0 left camera, 1 right camera in another keyframe
+        // (ceres_parametrization.cpp:579-712), 2 right camera in the anchor frame itself (:476-577, a
+        // function of the inverse depth only)
+        const int typ = D.obs_type ? (int)D.obs_type[i] : 0;
+        double cp[3] = {lc[0], lc[1], lc[2]};
+        double kfx = D.fx, kfy = D.fy, kcx = D.cx, kcy = D.cy;
+        if (typ != 0) {
+            const double* sv = typ == 2 ? ap : lc;
+            for (int k = 0; k < 3; ++k) cp[k] = D.Rrl[3 * k] * sv[0] + D.Rrl[3 * k + 1] * sv[1] + D.Rrl[3 * k + 2] * sv[2] + D.trl[k];
+            kfx = D.rfx; kfy = D.rfy; kcx = D.rcx; kcy = D.rcy;
+        }
+        const double linvz = 1.0 / cp[2];
+        double r0 = kfx * cp[0] * linvz + kcx - D.obs_px[2 * i];
+        double r1 = kfy * cp[1] * linvz + kcy - D.obs_px[2 * i + 1];
         const double s = r0 * r0 + r1 * r1;
         D.chi2[i] = s;
-        D.dpos[i] = lc[2] > 0.0 ? 1 : 0;
+        D.dpos[i] = cp[2] > 0.0 ? 1 : 0;
         double w = 1.0;
         if (D.use_huber && s > D.huber_b) {
             const double rs = sqrt(s);
@@ -181,11 +195,23 @@ __global__ void __launch_bounds__(128) ba_eval_kernel(BaDev D, const double* __r
         }
         if (JAC) {
             const double linvz2 = linvz * linvz;
-            const double jc[6] = {linvz * D.fx, 0.0, -lc[0] * linvz2 * D.fx, 0.0, linvz * D.fy, -lc[1] * linvz2 * D.fy};
-            double JR[6];  // J_lcam * Rcw  (2x3)
+            const double jc[6] = {linvz * kfx, 0.0, -cp[0] * linvz2 * kfx, 0.0, linvz * kfy, -cp[1] * linvz2 * kfy};
+            // M = d(camera point)/d(world point): Rcw (left), Rrl Rcw (right, other frame), Rrl (right, anchor frame)
+            double M[9];
+            if (typ == 0) {
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) M[3 * a + b] = Rwc[3 * b + a];
+            } else if (typ == 1) {
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        M[3 * a + b] = D.Rrl[3 * a] * Rwc[3 * b] + D.Rrl[3 * a + 1] * Rwc[3 * b + 1] + D.Rrl[3 * a + 2] * Rwc[3 * b + 2];
+            } else {
+                for (int k = 0; k < 9; ++k) M[k] = D.Rrl[k];
+            }
+            double JR[6];  // J_cam * M  (2x3)
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 3; ++b)
-                    JR[3 * a + b] = jc[3 * a] * Rwc[3 * b] + jc[3 * a + 1] * Rwc[3 * b + 1] + jc[3 * a + 2] * Rwc[3 * b + 2];  // Rcw = Rwc^T
+                    JR[3 * a + b] = jc[3 * a] * M[b] + jc[3 * a + 1] * M[3 + b] + jc[3 * a + 2] * M[6 + b];
             // JR * hat(wpt)
             double JS[6];
             for (int a = 0; a < 2; ++a) {
@@ -196,15 +222,17 @@ __global__ void __launch_bounds__(128) ba_eval_kernel(BaDev D, const double* __r
             }
             double* Ja = D.Ja + 12 * (size_t)i;
             double* Jo = D.Jo + 12 * (size_t)i;
+            const double wp_ = typ == 2 ? 0.0 : w;   // anchor-frame right-camera block: no pose block at all
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 3; ++b) {
-                    Ja[6 * a + b] = w * JR[3 * a + b];
-                    Ja[6 * a + 3 + b] = -w * JS[3 * a + b];
-                    Jo[6 * a + b] = -w * JR[3 * a + b];
-                    Jo[6 * a + 3 + b] = w * JS[3 * a + b];
+                    Ja[6 * a + b] = wp_ * JR[3 * a + b];
+                    Ja[6 * a + 3 + b] = -wp_ * JS[3 * a + b];
+                    Jo[6 * a + b] = -wp_ * JR[3 * a + b];
+                    Jo[6 * a + 3 + b] = wp_ * JS[3 * a + b];
                 }
-            // J_lambda = -zanch * Rwanch * anchpt
-            const double jl[3] = {-zanch * rp[0], -zanch * rp[1], -zanch * rp[2]};
+            // J_lambda = -zanch * Rwanch * anchpt   (type 2: -zanch * anchpt, the point never leaves the anchor frame)
+            const double* lp = typ == 2 ? ap : rp;
+            const double jl[3] = {-zanch * lp[0], -zanch * lp[1], -zanch * lp[2]};
             D.Jl[2 * (size_t)i] = w * (JR[0] * jl[0] + JR[1] * jl[1] + JR[2] * jl[2]);
             D.Jl[2 * (size_t)i + 1] = w * (JR[3] * jl[0] + JR[4] * jl[1] + JR[5] * jl[2]);
             D.Jr[2 * (size_t)i] = w * r0;
@@ -273,6 +301,8 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
     // per observation (serial over the landmark's observations, lanes over matrix entries)
     for (int p = p0; p < p1; ++p) {
         if (!D.active[p]) continue;
+        const bool lm_only = D.obs_type && D.obs_type[p] == 2;   // e-block-only row (schur_eliminator_impl.h:196-217)
+        if (lm_only) continue;
         const int so = D.cam_slot[D.obs_cam[p]];
         const double* Ja = D.Ja + 12 * (size_t)p;
         const double* Jo = D.Jo + 12 * (size_t)p;
@@ -295,12 +325,21 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
                 const int a = e / 6, b = e - 6 * a;
                 if (a <= b) atomicAdd(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
             }
+            // E'F row of this camera: a stereo keyframe contributes two residual blocks (left and right
+            // camera) to the same pose block, so look the slot up before appending a new entry
+            int idx = -1;
+            for (int q = lane; q < m; q += 32)
+                if (s_slot[warp][q] == so) idx = q;
+            idx = __reduce_max_sync(FULL, idx);
+            const bool fresh = idx < 0;
+            if (fresh) idx = m;
             if (lane < 6) {
                 atomicAdd(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
                 atomicAdd(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
-                s_etf[warp][m][lane] = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
+                const double e = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
+                s_etf[warp][idx][lane] = fresh ? e : s_etf[warp][idx][lane] + e;
             }
-            if (lane == 0) s_slot[warp][m] = so;
+            if (lane == 0 && fresh) s_slot[warp][idx] = so;
             if (sa >= 0) {
                 // cross block Ja' Jo into the upper block (min slot, max slot)
                 for (int e = lane; e < 36; e += 32) {
@@ -310,7 +349,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
                     else atomicAdd(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
                 }
             }
-            m++;
+            if (fresh) m++;
         }
         __syncwarp();
     }
@@ -323,11 +362,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
         if (si > sj || (si == sj && i > j)) continue;   // upper block triangle; (i,i) once
         const int a = q / 6, b = q - 6 * a;
         if (si == sj && a > b) continue;
-        double v = s_etf[warp][i][a] * s_etf[warp][j][b] * inv_ete;
-        if (si == sj && i != j) {
-            // cannot happen (a camera observes a landmark once, and the anchor is never an observer)
-            v *= 2.0;
-        }
+        const double v = s_etf[warp][i][a] * s_etf[warp][j][b] * inv_ete;   // slots are unique in the list
         atomicAdd(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
     }
     for (int e = lane; e < m * 6; e += 32) {
@@ -553,7 +588,7 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* 
     double acc = 0.0;
     for (int p = p0 + lane; p < p1; p += 32) {
         if (!D.active[p]) continue;
-        const int so = D.cam_slot[D.obs_cam[p]];
+        const int so = (D.obs_type && D.obs_type[p] == 2) ? -1 : D.cam_slot[D.obs_cam[p]];
         const double* Ja = D.Ja + 12 * (size_t)p;
         const double* Jo = D.Jo + 12 * (size_t)p;
         double f0 = 0.0, f1 = 0.0;
@@ -571,7 +606,7 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* 
     double mcc = 0.0;
     for (int p = p0 + lane; p < p1; p += 32) {
         if (!D.active[p]) continue;
-        const int so = D.cam_slot[D.obs_cam[p]];
+        const int so = (D.obs_type && D.obs_type[p] == 2) ? -1 : D.cam_slot[D.obs_cam[p]];
         const double* Ja = D.Ja + 12 * (size_t)p;
         const double* Jo = D.Jo + 12 * (size_t)p;
         double f0 = D.Jl[2 * (size_t)p] * dl, f1 = D.Jl[2 * (size_t)p + 1] * dl;
@@ -593,21 +628,29 @@ __global__ void __launch_bounds__(128) ba_backsub_kernel(BaDev D, const double* 
 // ------------------------------------------------------------------ outlier scan (optimizer.cpp:500-530)
 __global__ void ba_flag_kernel(BaDev D, double th, int bit, int deactivate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int bad = 0;
+    int bad = 0, left = 0, right = 0;
     if (i < D.nobs && D.active[i]) {
         bad = (D.chi2[i] > th) || !D.dpos[i];
         if (bad) {
             D.flags[i] |= (uint8_t)bit;
             if (deactivate) D.active[i] = 0;   // problem.RemoveResidualBlock
+        } else {
+            const int typ = D.obs_type ? (int)D.obs_type[i] : 0;
+            left = typ == 0;
+            right = typ == 1;
         }
     }
-    const int nb = __reduce_add_sync(FULL, bad);
-    if ((threadIdx.x & 31) == 0 && nb) atomicAdd(D.scal + SC_NBAD, (double)nb);
+    const int nb = __reduce_add_sync(FULL, bad), nl = __reduce_add_sync(FULL, left), nr = __reduce_add_sync(FULL, right);
+    if ((threadIdx.x & 31) == 0) {
+        if (nb) atomicAdd(D.scal + SC_NBAD, (double)nb);
+        if (nl) atomicAdd(D.scal + SC_NLEFT, (double)nl);     // surviving vreprojerr_kfid_lmid entries
+        if (nr) atomicAdd(D.scal + SC_NRIGHT, (double)nr);    // surviving vright_reprojerr_kfid_lmid entries
+    }
 }
 
 __global__ void ba_cam_used_kernel(BaDev D) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < D.nobs && D.active[i]) {
+    if (i < D.nobs && D.active[i] && !(D.obs_type && D.obs_type[i] == 2)) {
         D.cam_used[D.obs_cam[i]] = 1;
         D.cam_used[D.lm_anchor_cam[D.obs_lm[i]]] = 1;
     }
@@ -833,15 +876,32 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
     D.huber_a = (double)sqrtf(th_f);                          // HuberLoss(std::sqrt(mono_th))
     D.huber_b = D.huber_a * D.huber_a;
     D.use_huber = opts->use_robust ? 1 : 0;
+    D.rfx = D.fx; D.rfy = D.fy; D.rcx = D.cx; D.rcy = D.cy;
+    for (int k = 0; k < 9; ++k) D.Rrl[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    D.trl[0] = D.trl[1] = D.trl[2] = 0.0;
+    if (pb->obs_type) {
+        if (!pb->Kr || !pb->Trl) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_type given without Kr / Trl");
+        double kr[4], t7[7];
+        if (ov2_is_device_ptr(pb->Kr)) OV2_CUDA(ctx, cudaMemcpy(kr, pb->Kr, sizeof(kr), cudaMemcpyDeviceToHost)); else memcpy(kr, pb->Kr, sizeof(kr));
+        if (ov2_is_device_ptr(pb->Trl)) OV2_CUDA(ctx, cudaMemcpy(t7, pb->Trl, sizeof(t7), cudaMemcpyDeviceToHost)); else memcpy(t7, pb->Trl, sizeof(t7));
+        D.rfx = kr[0]; D.rfy = kr[1]; D.rcx = kr[2]; D.rcy = kr[3];
+        const double qn = sqrt(t7[3] * t7[3] + t7[4] * t7[4] + t7[5] * t7[5] + t7[6] * t7[6]);
+        const double x = t7[3] / qn, y = t7[4] / qn, z = t7[5] / qn, w = t7[6] / qn;
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                             2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                             2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int k = 0; k < 9; ++k) D.Rrl[k] = R[k];
+        D.trl[0] = t7[0]; D.trl[1] = t7[1]; D.trl[2] = t7[2];
+    }
     const void* d = nullptr;
     void* o = nullptr;
     const bool all_host = !ov2_is_device_ptr(pb->pose) && !ov2_is_device_ptr(pb->lm_invdepth) && !ov2_is_device_ptr(pb->pose_const) &&
                           !ov2_is_device_ptr(pb->lm_anchor_cam) && !ov2_is_device_ptr(pb->lm_anchor_px) &&
                           !ov2_is_device_ptr(pb->obs_cam) && !ov2_is_device_ptr(pb->obs_lm) && !ov2_is_device_ptr(pb->obs_px) &&
-                          (!outlier_out || !ov2_is_device_ptr(outlier_out));
+                          (!outlier_out || !ov2_is_device_ptr(outlier_out)) && (!pb->obs_type || !ov2_is_device_ptr(pb->obs_type));
     // Host problem description: pack everything into one pinned staging block -> ONE H2D copy
     // (a dozen small pageable copies cost more than the solve's kernels at C3 size).
-    size_t off_apx = 0, off_opx = 0, off_pose = 0, off_invd = 0, off_lac = 0, off_oc = 0, off_ol = 0, off_lp = 0, off_pc = 0, pack_bytes = 0;
+    size_t off_apx = 0, off_opx = 0, off_pose = 0, off_invd = 0, off_lac = 0, off_oc = 0, off_ol = 0, off_lp = 0, off_pc = 0, off_ty = 0, pack_bytes = 0;
     char* dpack = nullptr;
     if (all_host) {
         size_t off = 0;
@@ -850,6 +910,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         off_apx = take(sizeof(double) * 2 * npts); off_opx = take(sizeof(double) * 2 * nobs);
         off_lac = take(sizeof(int32_t) * npts); off_oc = take(sizeof(int32_t) * nobs); off_ol = take(sizeof(int32_t) * nobs);
         off_lp = take(sizeof(int32_t) * (npts + 1)); off_pc = take((size_t)ncam);
+        off_ty = take(pb->obs_type ? (size_t)nobs : 0);
         pack_bytes = off;
         if (ctx->ba_ws_cap < pack_bytes) {
             if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);
@@ -868,6 +929,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         memcpy(hp + off_ol, pb->obs_lm, sizeof(int32_t) * nobs);
         memcpy(hp + off_lp, lm_ptr.data(), sizeof(int32_t) * (npts + 1));
         memcpy(hp + off_pc, pb->pose_const, (size_t)ncam);
+        if (pb->obs_type) memcpy(hp + off_ty, pb->obs_type, (size_t)nobs);
         if ((st = ov2_scratch(ctx, pack_bytes, &o)) != OV2_OK) return st;
         dpack = (char*)o;
         OV2_CUDA(ctx, cudaMemcpyAsync(dpack, hp, pack_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -877,6 +939,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         D.obs_cam = (const int32_t*)(dpack + off_oc);
         D.obs_lm = (const int32_t*)(dpack + off_ol);
         D.obs_px = (const double*)(dpack + off_opx);
+        D.obs_type = pb->obs_type ? (const uint8_t*)(dpack + off_ty) : nullptr;
     } else {
 #define IN(field, bytes) do { if ((st = ov2_stage_in(ctx, pb->field, (bytes), &d)) != OV2_OK) return st; } while (0)
         IN(pose_const, (size_t)ncam); D.pose_const = (const uint8_t*)d;
@@ -885,6 +948,8 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         IN(obs_cam, sizeof(int32_t) * (size_t)nobs); D.obs_cam = (const int32_t*)d;
         IN(obs_lm, sizeof(int32_t) * (size_t)nobs); D.obs_lm = (const int32_t*)d;
         IN(obs_px, sizeof(double) * 2 * (size_t)nobs); D.obs_px = (const double*)d;
+        D.obs_type = nullptr;
+        if (pb->obs_type) { IN(obs_type, (size_t)nobs); D.obs_type = (const uint8_t*)d; }
 #undef IN
     }
     double *pose = nullptr, *cand_pose = nullptr, *invd = nullptr, *cand_invd = nullptr;
@@ -924,7 +989,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         return st;
     // outlier scan on the values the LAST Evaluate() left behind (optimizer.cpp:500-530)
     double h[SC_COUNT];
-    OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, sizeof(double), s));
+    OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, 3 * sizeof(double), s));
     const int deact = opts->apply_l2_after_robust ? 1 : 0;
     OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 1, deact));
     OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
@@ -942,10 +1007,15 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         OV2_CUDA(ctx, cudaStreamSynchronize(s));
     }
     if (opts->apply_l2_after_robust && opts->use_robust && nbad_global > 0) {
-        // mono windows keep the Huber loss in the refinement (optimizer.cpp:606-608)
+        // mono windows keep the Huber loss in the refinement; the wrapper is reset to the trivial loss only
+        // when left-camera and other-frame right-camera residual lists are both non-empty (optimizer.cpp:606-608)
+        // (sharded windows: the counts are per shard, so pass refine_loss explicitly there)
+        int trivial = opts->refine_loss;
+        if (trivial < 0) trivial = (h[SC_NLEFT] > 0.0 && h[SC_NRIGHT] > 0.0) ? 1 : 0;
+        D.use_huber = trivial ? 0 : 1;
         if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_refine, opts->function_tolerance, &s2, sh)) != OV2_OK)
             return st;
-        OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, sizeof(double), s));
+        OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, 3 * sizeof(double), s));
         OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 2, 0));
         OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
         OV2_CUDA(ctx, cudaStreamSynchronize(s));

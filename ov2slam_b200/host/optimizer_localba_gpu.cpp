@@ -65,7 +65,7 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     ov2_ctx* ctx = ba_context();
     if (!ctx) { std::cerr << "[ov2b200] localBA: no CUDA device (no CPU fallback)\n"; return; }
     if (pslamstate_->stereo_) {
-        std::cerr << "[ov2b200] localBA: stereo residual blocks are a 'next' row (SURVEY.md 8a R); mono only\n";
+        std::cerr << "[ov2b200] localBA: the stereo window flattening of this shim is not written yet (the ABI and kernels take obs_type/Kr/Trl); mono only\n";
         return;
     }
 
@@ -142,11 +142,13 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     pb.lm_anchor_cam = win.lm_anchor_cam.data(); pb.lm_anchor_px = win.lm_anchor_px.data();
     pb.lm_invdepth = win.lm_invdepth.data();
     pb.obs_cam = win.obs_cam.data(); pb.obs_lm = win.obs_lm.data(); pb.obs_px = win.obs_px.data();
+    pb.obs_type = nullptr; pb.Kr = nullptr; pb.Trl = nullptr;      // mono window (stereo flattening: next)
     ov2_ba_opts op;
     op.max_iters_robust = 5; op.max_iters_refine = 10;                // optimizer.cpp:462, :610
     op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-3;
     op.use_robust = buse_robust_cost ? 1 : 0;
     op.apply_l2_after_robust = (pslamstate_->apply_l2_after_robust_ && !stopLocalBA()) ? 1 : 0;
+    op.refine_loss = -1;                                              // as optimizer.cpp:606-608 decides
     ov2_ba_result res;
     std::vector<uint8_t> flags(win.obs_cam.size(), 0);
     if (ov2_localba_solve(ctx, &pb, &op, &res, flags.data()) != OV2_OK) {

@@ -143,7 +143,7 @@ def _rot_to_quat_xyzw(R: np.ndarray) -> np.ndarray:
 
 def make_ba_problem(seed: int, ncam: int = 10, npts: int = 2000, nobs: int = 8000,
                     nconst: int = 2, outlier_frac: float = 0.05, px_noise: float = 0.5,
-                    w: int = 752, h: int = 480):
+                    w: int = 752, h: int = 480, stereo: bool = False, baseline: float = 0.11):
     """Synthetic localBA window as a dict of flat arrays:
 
       K[4]            fx, fy, cx, cy  (EuRoC, euroc_mono.yaml:21-24)
@@ -157,6 +157,12 @@ def make_ba_problem(seed: int, ncam: int = 10, npts: int = 2000, nobs: int = 800
     Every landmark is anchored in its lowest-index observing camera; `nobs` counts the
     non-anchor observations (= residual blocks, the anchor observation itself carries no
     residual in the anchored inverse-depth parametrisation, optimizer.cpp:258-290).
+
+    stereo=True adds, as the reference does for stereo keypoints (optimizer.cpp:270-330): one
+    right-camera residual in the anchor frame (obs_type 2) and one right-camera residual next to
+    every left-camera residual in the other frames (obs_type 1), a right calibration Kr and the
+    constant extrinsic Trl (right-from-left; rectified rig, `baseline` metres along +x).  The
+    residual-block count becomes npts + 2 * nobs.
     """
     rng = np.random.default_rng(seed)
     fx = fy = 458.654
@@ -242,6 +248,41 @@ def make_ba_problem(seed: int, ncam: int = 10, npts: int = 2000, nobs: int = 800
             pose[i, :3] = twc[i] + rng.normal(0, 0.01, size=3)
             pose[i, 3:] = _rot_to_quat_xyzw(dR @ Rwc[i])
     lm_invdepth = lm_invdepth_true * (1 + rng.normal(0, 0.05, size=npts))
+    if stereo:
+        Kr = K.copy()
+        Trl = np.array([-baseline, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0])
+        o_cam, o_lm, o_px, o_typ = [], [], [], []
+        mono_cam = np.array(obs_cam, np.int32)
+        mono_lm = np.array(obs_lm, np.int32)
+        mono_px = np.array(obs_px, np.float64).reshape(-1, 2)
+        k = 0
+
+        def right_px(pc):
+            pr = pc + Trl[:3]
+            uv = np.array([fx * pr[0] / pr[2] + cx, fy * pr[1] / pr[2] + cy]) + rng.normal(0, px_noise, size=2)
+            if rng.random() < outlier_frac:
+                ang = rng.uniform(0, 2 * np.pi)
+                uv = uv + rng.uniform(10, 50) * np.array([np.cos(ang), np.sin(ang)])
+            return uv.astype(np.float32).astype(np.float64)
+
+        for l in range(npts):
+            a = lm_anchor_cam[l]
+            za = 1.0 / lm_invdepth_true[l]
+            pc_a = np.array([(lm_anchor_px[l, 0] - cx) / fx * za, (lm_anchor_px[l, 1] - cy) / fy * za, za])
+            pw = Rwc[a] @ pc_a + twc[a]
+            o_cam.append(a); o_lm.append(l); o_px.append(right_px(pc_a)); o_typ.append(2)
+            while k < len(mono_lm) and mono_lm[k] == l:
+                c = int(mono_cam[k])
+                o_cam.append(c); o_lm.append(l); o_px.append(mono_px[k]); o_typ.append(0)
+                o_cam.append(c); o_lm.append(l); o_px.append(right_px(Rwc[c].T @ (pw - twc[c]))); o_typ.append(1)
+                k += 1
+        return dict(
+            K=K, Kr=Kr, Trl=Trl, pose=pose, pose_const=pose_const,
+            lm_anchor_cam=lm_anchor_cam, lm_anchor_px=lm_anchor_px, lm_invdepth=lm_invdepth,
+            obs_cam=np.array(o_cam, np.int32), obs_lm=np.array(o_lm, np.int32),
+            obs_px=np.array(o_px, np.float64).reshape(-1, 2), obs_type=np.array(o_typ, np.uint8),
+            truth_pose=truth_pose, truth_invdepth=lm_invdepth_true,
+        )
     return dict(
         K=K, pose=pose, pose_const=pose_const,
         lm_anchor_cam=lm_anchor_cam, lm_anchor_px=lm_anchor_px, lm_invdepth=lm_invdepth,

@@ -21,7 +21,10 @@ def _check(ctx, pb, **opts):
     ref = _clone(pb)
     rres = B.local_ba(ref, **{k: v for k, v in opts.items()})
     gpu = _clone(pb)
-    gres, flags = api.Optimizer(ctx).local_ba(gpu, **{k: (int(v) if isinstance(v, bool) else v) for k, v in opts.items()})
+    gopts = {k: (int(v) if isinstance(v, bool) else v) for k, v in opts.items()}
+    if "refine_trivial_loss" in gopts:
+        gopts["refine_loss"] = gopts.pop("refine_trivial_loss")
+    gres, flags = api.Optimizer(ctx).local_ba(gpu, **gopts)
     assert gres["iters_robust"] == rres["iters_robust"], (gres, {k: v for k, v in rres.items() if k not in ("flags", "summaries")})
     assert gres["iters_refine"] == rres["iters_refine"]
     term = {"CONVERGENCE": 0, "NO_CONVERGENCE": 1, "FAILURE": 2}[rres["termination"]]
@@ -72,3 +75,26 @@ def test_localba_rejects_unsorted_observations(ctx):
     pb["obs_lm"] = pb["obs_lm"][::-1].copy()
     with pytest.raises(api.Ov2Error):
         api.Optimizer(ctx).local_ba(pb)
+
+
+@pytest.mark.parametrize("seed,ncam,npts,nobs", [(41, 8, 400, 1600), (42, 10, 1000, 4000)])
+def test_localba_stereo_window_matches_oracle(ctx, seed, ncam, npts, nobs):
+    """Stereo windows: left + right-camera residual blocks (ceres_parametrization.cpp:361-712), the
+    refinement drops to the trivial loss as optimizer.cpp:606-608 decides."""
+    pb = synth.make_ba_problem(seed, ncam, npts, nobs, stereo=True)
+    assert set(pb["obs_type"].tolist()) == {0, 1, 2}
+    g, r = _check(ctx, pb)
+    assert g["n_outliers_first"] > 0
+
+
+def test_localba_stereo_noise_free_recovers_truth(ctx):
+    pb = synth.make_ba_problem(43, 8, 300, 1200, stereo=True, outlier_frac=0.0, px_noise=0.0)
+    gpu = _clone(pb)
+    api.Optimizer(ctx).local_ba(gpu, max_iters_robust=30, function_tolerance=1e-12)
+    assert np.abs(gpu["pose"][:, :3] - pb["truth_pose"][:, :3]).max() < 2e-3
+    assert np.abs(gpu["lm_invdepth"] - pb["truth_invdepth"]).max() < 5e-3
+
+
+def test_localba_refine_loss_override(ctx):
+    pb = synth.make_ba_problem(44, 8, 400, 1600)
+    _check(ctx, pb, refine_trivial_loss=True)

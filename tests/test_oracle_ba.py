@@ -187,3 +187,46 @@ def test_c_port_matches_numpy_oracle(seed, ncam, npts, nobs):
     assert np.abs(a["pose"] - b["pose"]).max() <= 1e-9
     assert np.abs(a["lm_invdepth"] - b["lm_invdepth"]).max() <= 1e-9
     assert np.array_equal(ra["flags"], rb["flags"])
+
+
+def test_stereo_jacobians_vs_central_differences():
+    """The two right-camera residual blocks (ceres_parametrization.cpp:476-577, :579-712)."""
+    pb = synth.make_ba_problem(2, 5, 60, 200, stereo=True)
+    pose, invd = pb["pose"].copy(), pb["lm_invdepth"].copy()
+    idx = np.arange(0, len(pb["obs_cam"]), 3)
+    ev = B.evaluate(pb, pose, invd, idx, True)
+    assert set(ev["typ"].tolist()) == {0, 1, 2}
+    h = 1e-6
+    for which, J, cams in (("a", ev["Ja"], ev["ca"]), ("o", ev["Jo"], ev["co"])):
+        num = np.zeros_like(J)
+        for k in range(6):
+            d = np.zeros(6)
+            d[k] = h
+            for j, (i, c) in enumerate(zip(idx, cams)):
+                if ev["typ"][j] == 2:
+                    continue       # no pose dependence by construction (the pose is not a parameter block)
+                pp, pm = pose.copy(), pose.copy()
+                pp[c] = B.pose_plus(pose[c][None], d[None])[0]
+                pm[c] = B.pose_plus(pose[c][None], -d[None])[0]
+                num[j, :, k] = (B.evaluate(pb, pp, invd, np.array([i]), False)["r"][0] -
+                                B.evaluate(pb, pm, invd, np.array([i]), False)["r"][0]) / (2 * h)
+        assert np.abs(num - J).max() <= 1e-5 * max(1.0, np.abs(J).max()), which
+    num = np.zeros_like(ev["Jl"])
+    for j, i in enumerate(idx):
+        l = pb["obs_lm"][i]
+        ip, im = invd.copy(), invd.copy()
+        ip[l] += 1e-7
+        im[l] -= 1e-7
+        num[j] = (B.evaluate(pb, pose, ip, np.array([i]), False)["r"][0] -
+                  B.evaluate(pb, pose, im, np.array([i]), False)["r"][0]) / 2e-7
+    assert np.abs(num - ev["Jl"]).max() <= 1e-5 * max(1.0, np.abs(ev["Jl"]).max())
+
+
+def test_stereo_window_converges_and_refines_with_trivial_loss():
+    pb = synth.make_ba_problem(9, 8, 300, 1200, stereo=True)
+    res = B.local_ba(pb)
+    assert res["final_cost"] > 0 and res["n_outliers_first"] > 20
+    pb2 = synth.make_ba_problem(9, 8, 300, 1200, stereo=True, outlier_frac=0.0, px_noise=0.0)
+    r2 = B.local_ba(pb2, max_iters_robust=30, function_tolerance=1e-12)
+    assert np.abs(pb2["pose"][:, :3] - pb2["truth_pose"][:, :3]).max() < 2e-3
+    assert np.abs(pb2["lm_invdepth"] - pb2["truth_invdepth"]).max() < 5e-3
