@@ -316,28 +316,38 @@ class Workload:
             self.eft.append(api.FeatureTracker(c, 30, 0.01))
             self.efe.append(api.FeatureExtractor(c, nmaxdist=CELL, nfast_th=FAST_TH))
         self.pool = cf.ThreadPoolExecutor(max_workers=nchunks)
+        self._e2e_prepare()
+
+    def _e2e_prepare(self):
+        """Per-chunk raw host addresses, computed once: the timed loop then only makes ctypes calls
+        (which release the GIL) - no numpy/torch view construction under the GIL per step."""
+        self._cargs = []
+        for k in range(self.nchunks):
+            cs, nk, nc = self.cs, self.cs * NKP, self.cs * self.ncell
+            f0, k0, c0 = k * cs, k * cs * NKP, k * cs * self.ncell
+            adr = lambda t, a: t[a:a + 1].data_ptr() if t.numel() else 0
+            self._cargs.append(dict(
+                prev=adr(self.h_prev, f0), cur=adr(self.h_cur, f0), lv=adr(self.h_lv, k0), kps=adr(self.h_kps, k0),
+                pri=adr(self.h_pri, k0), pri0=adr(self.h_pri0, k0), status=adr(self.h_status, k0), th=adr(self.h_th, f0),
+                new=adr(self.h_new, c0), cnt=adr(self.h_cnt, f0), desc_t=adr(self.h_desc_t, k0), val_t=adr(self.h_val_t, k0),
+                desc_n=adr(self.h_desc_n, c0), val_n=adr(self.h_val_n, c0), nk=nk, nc=nc, cs=cs,
+                th_view=self.h_th[f0:f0 + cs], pri_view=self.h_pri[k0:k0 + nk], pri0_view=self.h_pri0[k0:k0 + nk]))
+            c = self._cargs[-1]
+            c["step_args"] = self.api.FrontendStepArgs(
+                c["prev"], c["cur"], W_IMG, W_IMG * H_IMG, cs, self.api.KltParams(9, 30, float(np.float32(0.01)), 30.0, 0.5),
+                nk, NKP, c["lv"], 0, c["kps"], c["pri"], c["status"], CELL, c["th"], self.ncell, c["new"], c["cnt"],
+                c["desc_t"], c["val_t"], c["desc_n"], c["val_n"])
 
     def _e2e_chunk(self, k: int):
-        cs, nk, nc = self.cs, self.cs * NKP, self.cs * self.ncell
-        f0, k0, c0 = k * cs, k * cs * NKP, k * cs * self.ncell
-        np_ = lambda t, a, b: t[a:b].numpy()
-        self.epp[k].build(np_(self.h_prev, f0, f0 + cs))          # H2D inside
-        self.ecp[k].build(np_(self.h_cur, f0, f0 + cs))
-        self.h_pri[k0:k0 + nk].copy_(self.h_pri0[k0:k0 + nk])
-        self.h_th[f0:f0 + cs].fill_(FAST_TH)
-        self.eft[k].fb_klt_tracking(self.epp[k], self.ecp[k], 9, np_(self.h_lv, k0, k0 + nk), 30.0, 0.5,
-                                    np_(self.h_kps, k0, k0 + nk), np_(self.h_pri, k0, k0 + nk),
-                                    np_(self.h_status, k0, k0 + nk), n=nk, per_frame=NKP)
-        self.efe[k].detect_grid_fast(self.ecp[k], CELL, 0, cs, np_(self.h_th, f0, f0 + cs), np_(self.h_new, c0, c0 + nc),
-                                     np_(self.h_cnt, f0, f0 + cs), max_per_frame=self.ncell)
-        self.efe[k].describe_brief(self.ecp[k], np_(self.h_pri, k0, k0 + nk), np_(self.h_desc_t, k0, k0 + nk),
-                                   np_(self.h_val_t, k0, k0 + nk), n=nk, per_frame=NKP)
-        self.efe[k].describe_brief(self.ecp[k], np_(self.h_new, c0, c0 + nc), np_(self.h_desc_n, c0, c0 + nc),
-                                   np_(self.h_val_n, c0, c0 + nc), n=nc, per_frame=self.ncell)
+        a = self._cargs[k]
+        pp, cp, ft, fe = self.epp[k], self.ecp[k], self.eft[k], self.efe[k]
+        a["pri_view"].copy_(a["pri0_view"])         # vpriorkps is in/out: fresh guess every step
+        a["th_view"].fill_(FAST_TH)
+        self.api.frontend_step(self.ectx[k], pp, cp, a["step_args"])   # one ABI call: H2D, kernels, D2H, one sync
 
     def step_e2e(self):
         list(self.pool.map(self._e2e_chunk, range(self.nchunks)))
-        return int(self.h_status.sum()), int(self.h_cnt.sum())
+        return int(self.h_cnt.sum())          # the step's result is read on the host (new keypoint counts)
 
     def e2e_launches(self):
         return sum(c.launch_count() for c in self.ectx)
@@ -412,6 +422,10 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     ms_res, wall_res, launches = timed(wl.step_resident, args.steps, args.warmup)
+    if args.e2e_chunks <= 0:
+        args.e2e_chunks = 8 if world == 1 else max(2, min(8, 16 // world))
+    while args.batch % args.e2e_chunks:
+        args.e2e_chunks -= 1
     wl.init_e2e(args.e2e_chunks)
     ms_e2e_dev, wall_e2e, _ = timed(wl.step_e2e, args.steps, max(1, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
@@ -545,7 +559,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks (host threads x contexts) of the e2e arm")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="chunks (host threads x contexts) of the e2e arm; 0 = 8 on one GPU, fewer per rank when several "
+                         "ranks share the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA leg")
     args = ap.parse_args()

@@ -57,6 +57,14 @@ OV2_API const char* ov2_version(void);
 /* Run the context's work on an existing stream (e.g. torch's current stream). NULL = own stream. */
 OV2_API ov2_status ov2_set_stream(ov2_ctx* ctx, void* cuda_stream);
 OV2_API ov2_status ov2_sync(ov2_ctx* ctx);
+/* Batch mode: between ov2_batch_begin and ov2_batch_end every call on the context only ENQUEUES
+ * (H2D of host inputs, kernels); host outputs are copied back and the stream is synchronised once,
+ * in ov2_batch_end.  A host buffer written by one call of the batch and read by a later one (e.g.
+ * the tracked positions fbKltTracking returns and describeBRIEF consumes) is served from its device
+ * staging copy, so operator chains keep host-pointer semantics without round trips.  Host outputs
+ * must not be read before ov2_batch_end.  (ov2_grid_fast's capacity check is skipped in a batch.) */
+OV2_API ov2_status ov2_batch_begin(ov2_ctx* ctx);
+OV2_API ov2_status ov2_batch_end(ov2_ctx* ctx);
 /* Pinned host memory helpers (for callers that want true async H2D/D2H). */
 OV2_API ov2_status ov2_host_alloc(ov2_ctx* ctx, size_t bytes, void** out);
 OV2_API ov2_status ov2_host_free(ov2_ctx* ctx, void* p);
@@ -151,6 +159,20 @@ OV2_API ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int fr
  * descriptor, mirroring the empty cv::Mat the reference returns for them. */
 OV2_API ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, const int32_t* frame_idx, int first_frame, int per_frame,
                         const float* pts, uint8_t* desc32_out, uint8_t* valid_out);
+
+/* ------------------------------------------------------------------ composite: one front-end step
+ * P(prev), P(cur), K, F+S on cur (no existing keypoints), B(tracked), B(new) for `count` frame pairs in
+ * ONE call (batch mode inside): what VisualFrontEnd::trackMono + MapManager::extractKeypoints do per
+ * frame (/root/reference/src/visual_front_end.cpp:65-128, src/map_manager.cpp:286-341).  Pointers
+ * host or device as everywhere; n_kps = count * kps_per_frame; cellsize <= 0 skips F/B(new). */
+typedef struct {
+    const uint8_t* prev_images; const uint8_t* cur_images; size_t row_stride, frame_stride; int count;
+    ov2_klt_params klt; int n_kps, kps_per_frame; const uint8_t* nbpyrlvl; int nbpyrlvl_all;
+    const float* kps; float* priors_inout; uint8_t* status_out;
+    int cellsize; int32_t* fast_th_inout; int max_per_frame; float* new_pts; int32_t* new_counts;
+    uint8_t* desc_tracked; uint8_t* valid_tracked; uint8_t* desc_new; uint8_t* valid_new;
+} ov2_frontend_step_args;
+OV2_API ov2_status ov2_frontend_step(ov2_ctx* ctx, ov2_pyr* prev, ov2_pyr* cur, const ov2_frontend_step_args* args);
 
 /* ------------------------------------------------------------------ L: local bundle adjustment
  * Replaces the solve sections of Optimizer::localBA(Frame&, bool)

@@ -27,9 +27,10 @@ STATUS_NAMES = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "INVALID", 4: "CAPACITY",
 
 ABI_SYMBOLS = [
     "ov2_create", "ov2_destroy", "ov2_last_error", "ov2_version", "ov2_set_stream", "ov2_sync",
+    "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_localba_solve", "ov2_localba_solve_sharded",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
 ]
 
 
@@ -40,6 +41,15 @@ class Ov2Error(RuntimeError):
 class KltParams(C.Structure):
     _fields_ = [("win", C.c_int), ("max_iter", C.c_int), ("eps", C.c_float), ("ferr", C.c_float),
                 ("fb_dist", C.c_float)]
+
+
+class FrontendStepArgs(C.Structure):
+    _fields_ = [("prev_images", C.c_void_p), ("cur_images", C.c_void_p), ("row_stride", C.c_size_t), ("frame_stride", C.c_size_t),
+                ("count", C.c_int), ("klt", KltParams), ("n_kps", C.c_int), ("kps_per_frame", C.c_int),
+                ("nbpyrlvl", C.c_void_p), ("nbpyrlvl_all", C.c_int), ("kps", C.c_void_p), ("priors_inout", C.c_void_p),
+                ("status_out", C.c_void_p), ("cellsize", C.c_int), ("fast_th_inout", C.c_void_p), ("max_per_frame", C.c_int),
+                ("new_pts", C.c_void_p), ("new_counts", C.c_void_p), ("desc_tracked", C.c_void_p), ("valid_tracked", C.c_void_p),
+                ("desc_new", C.c_void_p), ("valid_new", C.c_void_p)]
 
 
 class BaProblem(C.Structure):
@@ -87,6 +97,8 @@ def load():
     lib.ov2_version.restype = C.c_char_p
     lib.ov2_set_stream.argtypes = [vp, vp]
     lib.ov2_sync.argtypes = [vp]
+    lib.ov2_batch_begin.argtypes = [vp]
+    lib.ov2_batch_end.argtypes = [vp]
     lib.ov2_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     lib.ov2_host_free.argtypes = [vp, vp]
     lib.ov2_launch_count.argtypes = [vp]
@@ -103,6 +115,7 @@ def load():
     lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
                                               ALLREDUCE_FN, vp, i32]
@@ -150,6 +163,12 @@ class Context:
 
     def sync(self):
         self.check(self.lib.ov2_sync(self.h))
+
+    def batch_begin(self):
+        self.check(self.lib.ov2_batch_begin(self.h))
+
+    def batch_end(self):
+        self.check(self.lib.ov2_batch_end(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.ov2_launch_count(self.h))
@@ -200,7 +219,7 @@ class Pyramid:
     def build(self, images, first: int = 0, count: int | None = None, row_stride=None, frame_stride=None):
         """images: (count, H, W) uint8 numpy array (host) or CUDA torch tensor (used in place)."""
         if count is None:
-            count = images.shape[0] if images.ndim == 3 else 1
+            count = images.shape[0] if images.ndim == 3 else 1   # (raw int addresses need an explicit count)
         rs = int(row_stride if row_stride is not None else self.w)
         fs = int(frame_stride if frame_stride is not None else rs * self.h)
         self.ctx.check(self.ctx.lib.ov2_pyr_build(self.ctx.h, self.h_, _ptr(images), rs, fs, first, count))
@@ -230,6 +249,12 @@ class Pyramid:
             pass
 
 
+def frontend_step(ctx: Context, prev: "Pyramid", cur: "Pyramid", args: FrontendStepArgs):
+    """ov2_frontend_step: pyramids, fb-KLT, grid FAST + subpix and both descriptor passes for a batch of
+    frame pairs in one call (one sync)."""
+    ctx.check(ctx.lib.ov2_frontend_step(ctx.h, prev.h_, cur.h_, C.byref(args)))
+
+
 def clahe(ctx: Context, src, dst, width: int, height: int, count: int = 1, clip_limit: float = 3.0,
           tiles=None, row_stride=None, frame_stride=None):
     """cv::CLAHE::apply on `count` images (numpy or CUDA tensors); tiles default to the reference's
@@ -256,8 +281,8 @@ class FeatureTracker:
         if n is None:
             n = int(kps.shape[0])
         prm = KltParams(int(nwinsize), int(self.nmax_iter), self.fmax_px_precision, float(ferr), float(fmax_fbklt_dist))
-        if isinstance(nbpyrlvl, (int, np.integer)):
-            lv_ptr, lv_all = None, int(nbpyrlvl)
+        if isinstance(nbpyrlvl, (int, np.integer)) and int(nbpyrlvl) < 64:
+            lv_ptr, lv_all = None, int(nbpyrlvl)       # a pyramid depth; larger ints are raw addresses
         else:
             lv_ptr, lv_all = _ptr(nbpyrlvl), 0
         if frame_idx is None and per_frame is None:

@@ -43,6 +43,9 @@ extern "C" void ov2_destroy(ov2_ctx* ctx) {
     for (auto& ch : ctx->chunks) cudaFree(ch.p);
     if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);   // pinned staging block of the BA path
     if (ctx->pe0) { cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1); }
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
+    for (auto& g : ctx->step_graphs) if (g.state == 1 && g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -125,11 +128,14 @@ extern "C" uint64_t ov2_launch_count(const ov2_ctx* ctx) { return ctx ? ctx->lau
 ov2_status ov2_begin(ov2_ctx* ctx) {
     if (!ctx) return OV2_ERR_INVALID;
     OV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->batch) return OV2_OK;     // batch mode: keep the arena and the pending outputs of earlier calls
     ctx->pending.clear();
     if (ctx->chunks.size() > 1) {
         // consolidate: previous call outgrew the arena
         OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         size_t total = 0;
+        // captured step graphs hold arena addresses: drop them before the arena moves
+        for (auto& g : ctx->step_graphs) { if (g.state == 1 && g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.state = 0; }
         for (auto& ch : ctx->chunks) { total += ch.cap; cudaFree(ch.p); }
         ctx->chunks.clear();
         char* p = nullptr;
@@ -168,6 +174,11 @@ bool ov2_is_device_ptr(const void* p) {
 ov2_status ov2_stage_in(ov2_ctx* ctx, const void* p, size_t bytes, const void** dev) {
     if (!p || bytes == 0) { *dev = nullptr; return OV2_OK; }
     if (ov2_is_device_ptr(p)) { *dev = p; return OV2_OK; }
+    if (ctx->batch) {
+        // produced by an earlier call of this batch? then its device staging buffer IS the data
+        for (auto it = ctx->pending.rbegin(); it != ctx->pending.rend(); ++it)
+            if (it->host == p && it->bytes >= bytes) { *dev = it->dev; return OV2_OK; }
+    }
     void* d = nullptr;
     ov2_status st = ov2_scratch(ctx, bytes, &d);
     if (st != OV2_OK) return st;
@@ -179,6 +190,11 @@ ov2_status ov2_stage_in(ov2_ctx* ctx, const void* p, size_t bytes, const void** 
 ov2_status ov2_stage_out(ov2_ctx* ctx, void* p, size_t bytes, void** dev, bool copy_in) {
     if (!p || bytes == 0) { *dev = nullptr; return OV2_OK; }
     if (ov2_is_device_ptr(p)) { *dev = p; return OV2_OK; }
+    if (ctx->batch) {
+        // in/out buffer already staged by an earlier call of the batch: keep working on that copy
+        for (auto it = ctx->pending.rbegin(); it != ctx->pending.rend(); ++it)
+            if (it->host == p && it->bytes >= bytes) { *dev = const_cast<void*>(it->dev); return OV2_OK; }
+    }
     void* d = nullptr;
     ov2_status st = ov2_scratch(ctx, bytes, &d);
     if (st != OV2_OK) return st;
@@ -188,13 +204,54 @@ ov2_status ov2_stage_out(ov2_ctx* ctx, void* p, size_t bytes, void** dev, bool c
     return OV2_OK;
 }
 
+ov2_status ov2_wait_stream(ov2_ctx* ctx) {
+    // sleep-wait (blocking-sync event) so many host threads can drive many contexts without burning
+    // a core each in a spin loop
+    if (!ctx->sync_ev) OV2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    OV2_CUDA(ctx, cudaEventRecord(ctx->sync_ev, ctx->stream));
+    OV2_CUDA(ctx, cudaEventSynchronize(ctx->sync_ev));
+    return OV2_OK;
+}
+
 ov2_status ov2_end(ov2_ctx* ctx) {
+    if (ctx->batch) return OV2_OK;     // deferred to ov2_batch_end
     if (ctx->pending.empty()) return OV2_OK;
     for (auto& pd : ctx->pending)
         OV2_CUDA(ctx, cudaMemcpyAsync(pd.host, pd.dev, pd.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->pending.clear();
-    OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ov2_wait_stream(ctx);
+}
+
+extern "C" ov2_status ov2_batch_begin(ov2_ctx* ctx) {
+    if (!ctx) return OV2_ERR_INVALID;
+    if (ctx->batch) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_batch_begin: batch already open");
+    ov2_status st = ov2_begin(ctx);    // resets the arena / pending list
+    if (st != OV2_OK) return st;
+    ctx->batch = true;
     return OV2_OK;
+}
+
+// D2H copies of everything the open batch produced into host buffers (no wait)
+ov2_status ov2_batch_flush_outputs(ov2_ctx* ctx) {
+    for (size_t i = 0; i < ctx->pending.size(); ++i) {
+        bool superseded = false;
+        for (size_t j = i + 1; j < ctx->pending.size(); ++j)
+            if (ctx->pending[j].host == ctx->pending[i].host && ctx->pending[j].bytes >= ctx->pending[i].bytes) superseded = true;
+        if (superseded) continue;
+        auto& pd = ctx->pending[i];
+        OV2_CUDA(ctx, cudaMemcpyAsync(pd.host, pd.dev, pd.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->pending.clear();
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_batch_end(ov2_ctx* ctx) {
+    if (!ctx) return OV2_ERR_INVALID;
+    if (!ctx->batch) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_batch_end: no batch open");
+    ctx->batch = false;
+    ov2_status fst = ov2_batch_flush_outputs(ctx);
+    if (fst != OV2_OK) return fst;
+    return ov2_wait_stream(ctx);
 }
 
 // ------------------------------------------------------------------------ pyramid storage

@@ -565,7 +565,7 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     OV2_LAUNCH(ctx, "subpix_kernel", subpix_kernel<<<div_up(PA.n, 4), 128, 0, ctx->stream>>>(PA));
     // capacity overflow is an error, never a silent truncation
     int ovf = 0;
-    bool host_out = !ctx->pending.empty();
+    bool host_out = !ctx->pending.empty() && !ctx->batch;   // batch mode: nothing has been synchronised yet
     st = ov2_end(ctx);
     if (st != OV2_OK) return st;
     if (host_out) {

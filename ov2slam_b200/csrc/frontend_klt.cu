@@ -234,7 +234,7 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) fb_klt_kernel(KltArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fb_klt_kernel(KltArgs A) {
     __shared__ __align__(16) uint8_t sPall[WARPS_PER_CTA][((WIN + 3) * (WIN + 3) + 15) & ~15];
     __shared__ int sDall[WARPS_PER_CTA][(WIN + 1) * (WIN + 1)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

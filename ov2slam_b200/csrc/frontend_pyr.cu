@@ -50,7 +50,9 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, lon
             if (c >= IN_WORDS) break;
             const int x0 = ix0 + 4 * c;
             uint32_t wv;
-            if (aligned && x0 >= 0 && x0 + 4 <= sw) {
+            if (x0 > sw + 1) {
+                wv = 0;   // beyond the last column any existing output reads (2*(dw-1)+2 <= sw+1)
+            } else if (aligned && x0 >= 0 && x0 + 4 <= sw) {
                 wv = __ldg(reinterpret_cast<const uint32_t*>(grow + x0));
             } else {
                 wv = 0;
@@ -91,19 +93,16 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, lon
 
 }  // namespace
 
-extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* images, size_t row_stride,
-                                    size_t frame_stride, int first, int count) {
+// level 0: alias device images / upload host images (H2D on the context's stream)
+ov2_status ov2_pyr_load_level0(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* images, size_t row_stride, size_t frame_stride,
+                               int first, int count) {
     if (!ctx || !p || !images || first < 0 || count <= 0 || first + count > p->batch ||
         row_stride < (size_t)p->w[0])
         return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_build: bad arguments");
-    ov2_status st = ov2_begin(ctx);
-    if (st != OV2_OK) return st;
     if (ov2_is_device_ptr(images)) {
         const uint8_t* base = images - (ptrdiff_t)frame_stride * first;
-        if (p->l0_mode == 1 || (p->l0_mode == 2 && (p->l0 != base || p->l0_pitch != row_stride ||
-                                                      p->l0_fstride != frame_stride)))
-            if (p->l0_mode == 1)
-                return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_build: pyramid already owns level 0 (host images)");
+        if (p->l0_mode == 1)
+            return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_pyr_build: pyramid already owns level 0 (host images)");
         p->l0 = base;
         p->l0_pitch = row_stride;
         p->l0_fstride = frame_stride;
@@ -118,7 +117,12 @@ extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* ima
             p->l0_fstride = p->fstride[0];
             p->l0_mode = 1;
         }
-        if (frame_stride == row_stride * (size_t)p->h[0]) {
+        if (frame_stride == row_stride * (size_t)p->h[0] && row_stride == p->pitch[0]) {
+            // fully contiguous on both sides: ONE linear copy (a pitched copy is issued as W-byte rows and
+            // reaches a fraction of the PCIe bandwidth)
+            OV2_CUDA(ctx, cudaMemcpyAsync(p->own[0] + p->fstride[0] * (size_t)first, images, frame_stride * (size_t)count,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        } else if (frame_stride == row_stride * (size_t)p->h[0]) {
             OV2_CUDA(ctx, cudaMemcpy2DAsync(p->own[0] + p->fstride[0] * (size_t)first, p->pitch[0], images, row_stride,
                                             p->w[0], (size_t)p->h[0] * count, cudaMemcpyHostToDevice, ctx->stream));
         } else {
@@ -128,6 +132,11 @@ extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* ima
                                                 cudaMemcpyHostToDevice, ctx->stream));
         }
     }
+    return OV2_OK;
+}
+
+// levels 1.. from level 0 (kernels only)
+ov2_status ov2_pyr_make_levels(ov2_ctx* ctx, ov2_pyr* p, int first, int count) {
     for (int l = 1; l < p->nlev; ++l) {
         const uint8_t* s = l == 1 ? p->l0 : p->own[l - 1];
         int spitch = (int)(l == 1 ? p->l0_pitch : p->pitch[l - 1]);
@@ -137,5 +146,15 @@ extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* ima
                                                                p->w[l], p->h[l], (int)p->pitch[l],
                                                                (long long)p->fstride[l], first));
     }
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_pyr_build(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* images, size_t row_stride,
+                                    size_t frame_stride, int first, int count) {
+    if (!ctx) return OV2_ERR_INVALID;
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    if ((st = ov2_pyr_load_level0(ctx, p, images, row_stride, frame_stride, first, count)) != OV2_OK) return st;
+    if ((st = ov2_pyr_make_levels(ctx, p, first, count)) != OV2_OK) return st;
     return ov2_end(ctx);
 }

@@ -26,6 +26,16 @@ struct ov2_ctx {
     // pending device->host copies of the current call
     struct Pending { void* host; const void* dev; size_t bytes; };
     std::vector<Pending> pending;
+    // batch mode (ov2_batch_begin / ov2_batch_end): calls only enqueue; host outputs are copied back and
+    // the stream is synchronised ONCE at batch end; a host pointer written by an earlier call of the
+    // batch and read by a later one is served from its device staging buffer (no round trip)
+    bool batch = false;
+    // CUDA graphs of ov2_frontend_step (one per distinct argument block): the whole step - H2D copies,
+    // kernels, D2H copies - is captured on its second call and replayed with one cudaGraphLaunch afterwards
+    struct StepGraph { std::vector<unsigned char> key; cudaGraphExec_t exec; uint64_t launches; int state; };  // state 0 seen once, 1 captured, -1 not capturable
+    std::vector<StepGraph> step_graphs;
+    cudaEvent_t sync_ev = nullptr;   // blocking-sync event: waiting threads sleep instead of spinning
+    cudaEvent_t upload_ev = nullptr; // "images of this step are on the device" (ov2_frontend_step's upload token)
     // persistent small device blocks (tables)
     void* ba_ws = nullptr; size_t ba_ws_cap = 0;
     // optional per-kernel CUDA-event timing (ov2_profile_enable): serialises launches
@@ -108,6 +118,13 @@ ov2_status ov2_stage_in(ov2_ctx* ctx, const void* p, size_t bytes, const void** 
 // output: returns a device pointer to write; host destinations are copied back by ov2_end()
 ov2_status ov2_stage_out(ov2_ctx* ctx, void* p, size_t bytes, void** dev, bool copy_in = false);
 ov2_status ov2_end(ov2_ctx* ctx);                                 // D2H of pending outputs + sync if any
+ov2_status ov2_wait_stream(ov2_ctx* ctx);                         // sleep-wait for the context's stream
+ov2_status ov2_batch_flush_outputs(ov2_ctx* ctx);                 // batch mode: enqueue the D2H copies (no wait)
+
+// pyramid build in two halves (frontend_step.cu orders the uploads of concurrent contexts)
+ov2_status ov2_pyr_load_level0(ov2_ctx* ctx, ov2_pyr* p, const uint8_t* images, size_t row_stride, size_t frame_stride,
+                               int first, int count);
+ov2_status ov2_pyr_make_levels(ov2_ctx* ctx, ov2_pyr* p, int first, int count);
 
 // --- device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int i, int n) {

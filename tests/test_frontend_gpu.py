@@ -301,3 +301,138 @@ def test_clahe_bit_exact(ctx, w, h):
     api.clahe(ctx, d_in, d_out, w, h, count=2)
     ctx.sync()
     assert np.array_equal(d_out.cpu().numpy(), out)
+
+
+def test_batch_mode_chains_through_host_pointers(ctx):
+    """ov2_batch_begin/end: calls only enqueue, one D2H + sync at the end, and a host buffer written by
+    fbKltTracking and read by describeBRIEF in the same batch is served from its device staging copy.
+    Results must equal the call-by-call path."""
+    w, h = 640, 480
+    prev, cur, flow, kps, is3d, pri = _klt_inputs(9, w, h, 20)
+    lv = np.where(is3d, 1, 3).astype(np.uint8)
+    n = len(kps)
+    ncell = (h // 50) * (w // 50)
+
+    def run(batched):
+        pp = api.Pyramid(ctx, 1, w, h, 3)
+        cp = api.Pyramid(ctx, 1, w, h, 3)
+        out = dict(pri=pri.copy(), st=np.zeros(n, np.uint8), th=np.array([10], np.int32), new=np.empty((ncell, 2), np.float32),
+                   cnt=np.zeros(1, np.int32), dt=np.zeros((n, 32), np.uint8), vt=np.zeros(n, np.uint8),
+                   dn=np.zeros((ncell, 32), np.uint8), vn=np.zeros(ncell, np.uint8))
+        ft, fe = api.FeatureTracker(ctx, 30, 0.01), api.FeatureExtractor(ctx)
+        if batched:
+            ctx.batch_begin()
+        pp.build(prev[None])
+        cp.build(cur[None])
+        ft.fb_klt_tracking(pp, cp, 9, lv, 30.0, 0.5, kps, out["pri"], out["st"])
+        fe.detect_grid_fast(cp, 50, 0, 1, out["th"], out["new"], out["cnt"])
+        fe.describe_brief(cp, out["pri"], out["dt"], out["vt"])
+        fe.describe_brief(cp, out["new"], out["dn"], out["vn"])
+        if batched:
+            ctx.batch_end()
+        pp.close()
+        cp.close()
+        return out
+
+    a, b = run(False), run(True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert a["st"].sum() > 100 and a["cnt"][0] > 50
+
+
+def test_frontend_step_composite_equals_operator_calls(ctx):
+    """ov2_frontend_step (one call, one sync) == the operator entry points called one by one."""
+    w, h, nfr, nk = 640, 480, 2, 256
+    data = [synth.make_pair(90 + f, w, h) for f in range(nfr)]
+    prevs = np.stack([d[0] for d in data])
+    curs = np.stack([d[1] for d in data])
+    rng = np.random.default_rng(3)
+    kps = np.stack([rng.uniform(12, w - 12, nfr * nk), rng.uniform(12, h - 12, nfr * nk)], axis=1).astype(np.float32)
+    pri0 = kps.copy()
+    lv = rng.integers(0, 2, nfr * nk).astype(np.uint8) * 2 + 1
+    ncell = (h // 50) * (w // 50)
+
+    def outputs():
+        return dict(pri=pri0.copy(), st=np.zeros(nfr * nk, np.uint8), th=np.full(nfr, 10, np.int32),
+                    new=np.empty((nfr * ncell, 2), np.float32), cnt=np.zeros(nfr, np.int32),
+                    dt=np.zeros((nfr * nk, 32), np.uint8), vt=np.zeros(nfr * nk, np.uint8),
+                    dn=np.zeros((nfr * ncell, 32), np.uint8), vn=np.zeros(nfr * ncell, np.uint8))
+
+    pp = api.Pyramid(ctx, nfr, w, h, 3)
+    cp = api.Pyramid(ctx, nfr, w, h, 3)
+    a = outputs()
+    pp.build(prevs)
+    cp.build(curs)
+    ft, fe = api.FeatureTracker(ctx, 30, 0.01), api.FeatureExtractor(ctx)
+    ft.fb_klt_tracking(pp, cp, 9, lv, 30.0, 0.5, kps, a["pri"], a["st"], per_frame=nk)
+    fe.detect_grid_fast(cp, 50, 0, nfr, a["th"], a["new"], a["cnt"], max_per_frame=ncell)
+    fe.describe_brief(cp, a["pri"], a["dt"], a["vt"], per_frame=nk)
+    fe.describe_brief(cp, a["new"], a["dn"], a["vn"], per_frame=ncell)
+    b = outputs()
+    args = api.FrontendStepArgs(prevs.ctypes.data, curs.ctypes.data, w, w * h, nfr, api.KltParams(9, 30, float(np.float32(0.01)), 30.0, 0.5),
+                                nfr * nk, nk, lv.ctypes.data, 0, kps.ctypes.data, b["pri"].ctypes.data, b["st"].ctypes.data, 50,
+                                b["th"].ctypes.data, ncell, b["new"].ctypes.data, b["cnt"].ctypes.data, b["dt"].ctypes.data,
+                                b["vt"].ctypes.data, b["dn"].ctypes.data, b["vn"].ctypes.data)
+    for rep in range(3):           # call 1 eager, call 2 tries the CUDA-graph capture, call 3 replays / falls back
+        b["pri"][...] = pri0
+        b["th"][...] = 10
+        api.frontend_step(ctx, pp, cp, args)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (rep, k)
+    # pinned host buffers: the captured graph is really replayed
+    torch = pytest.importorskip("torch")
+    pin = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in outputs().items()}
+    hp, hc = torch.from_numpy(prevs).pin_memory(), torch.from_numpy(curs).pin_memory()
+    hk, hl = torch.from_numpy(kps).pin_memory(), torch.from_numpy(lv).pin_memory()
+    args2 = api.FrontendStepArgs(hp.data_ptr(), hc.data_ptr(), w, w * h, nfr, api.KltParams(9, 30, float(np.float32(0.01)), 30.0, 0.5),
+                                 nfr * nk, nk, hl.data_ptr(), 0, hk.data_ptr(), pin["pri"].data_ptr(), pin["st"].data_ptr(), 50,
+                                 pin["th"].data_ptr(), ncell, pin["new"].data_ptr(), pin["cnt"].data_ptr(), pin["dt"].data_ptr(),
+                                 pin["vt"].data_ptr(), pin["dn"].data_ptr(), pin["vn"].data_ptr())
+    l0 = ctx.launch_count()
+    for rep in range(4):
+        pin["pri"].copy_(torch.from_numpy(pri0))
+        pin["th"].fill_(10)
+        api.frontend_step(ctx, pp, cp, args2)
+        for k in a:
+            assert np.array_equal(a[k], pin[k].numpy()), (rep, k)
+    assert ctx.launch_count() - l0 == 4 * 12      # 6 pyramid + KLT + 3 FAST/subpix + 2 descriptor launches per step
+    pp.close()
+    cp.close()
+
+
+def test_c4_resolution_1280x720_cell35(ctx):
+    """BASELINE.json configs[3] geometry: 1280x720, accurate-config cell size 35 (720 cells), CLAHE on
+    the tracking image, descriptors on the raw image (map_manager.cpp:301-303): every operator at that
+    size against the oracle (the FAST sweep's mask bitmap needs 115 KB of shared memory here)."""
+    w, h, cs = 1280, 720, 35
+    prev, cur, flow = synth.make_pair(500, w, h)
+    eq_prev = np.empty_like(prev)
+    eq_cur = np.empty_like(cur)
+    api.clahe(ctx, prev[None], eq_prev[None], w, h)
+    api.clahe(ctx, cur[None], eq_cur[None], w, h)
+    ref_eq = R.clahe_cv2(prev) if R.HAVE_CV2 else R.clahe_ref(prev)
+    assert np.array_equal(eq_prev, ref_eq)
+    pp = api.Pyramid(ctx, 1, w, h, 3)
+    cp = api.Pyramid(ctx, 1, w, h, 3)
+    raw = api.Pyramid(ctx, 1, w, h, 0)
+    pp.build(eq_prev[None])
+    cp.build(eq_cur[None])
+    raw.build(prev[None])
+    fe = api.FeatureExtractor(ctx, nmaxdist=cs, nfast_th=10)
+    pts, ipts = fe.detect_grid_fast_frame(pp, 0, cs, np.zeros((0, 2), np.float32))
+    ref_i, ref_th, _ = _oracle_detect(eq_prev, cs, np.zeros((0, 2)), 10)
+    assert np.array_equal(ipts, ref_i) and fe.nfast_th_ == ref_th and len(ipts) > 400
+    assert np.abs(pts - _subpix(eq_prev, ref_i.astype(np.float32))).max() <= SUBPIX_TOL
+    d = np.zeros((len(pts), 32), np.uint8)
+    v = np.zeros(len(pts), np.uint8)
+    fe.describe_brief(raw, pts, d, v)
+    rd, rv = (R.describe_cv2 if R.HAVE_CV2 else R.describe_ref)(prev, pts)
+    assert np.array_equal(v, rv) and np.array_equal(d, rd)
+    _, pri = synth.make_priors(500, pts, flow)
+    out = pri.copy()
+    st = np.zeros(len(pts), np.uint8)
+    api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, 3, 30.0, 0.5, pts, out, st)
+    rp, rs = (R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref)(eq_prev, eq_cur, pts, pri, 9, 3)
+    assert np.array_equal(st, rs) and np.abs(out - rp).max() <= KLT_TOL
+    for p in (pp, cp, raw):
+        p.close()
