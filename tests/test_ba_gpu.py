@@ -98,3 +98,21 @@ def test_localba_stereo_noise_free_recovers_truth(ctx):
 def test_localba_refine_loss_override(ctx):
     pb = synth.make_ba_problem(44, 8, 400, 1600)
     _check(ctx, pb, refine_trivial_loss=True)
+
+
+@pytest.mark.parametrize("ncam,npts,nobs", [(16, 1200, 7000), (22, 1500, 9000), (50, 4000, 30000)])
+def test_localba_all_reduced_solver_paths(ctx, ncam, npts, nobs):
+    """Reduced camera systems of 84, 120 and 288 unknowns: register Gauss-Jordan (n <= 96), Cholesky in
+    shared memory (n^2 doubles <= 200 KB) and Cholesky in global/L2 (C5-sized windows), each against
+    the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to oracle/ba_ref.py)."""
+    from oracle import ba_ref_c
+    pb = synth.make_ba_problem(70 + ncam, ncam, npts, nobs)
+    ref = _clone(pb)
+    r = ba_ref_c.local_ba(ref)
+    gpu = _clone(pb)
+    g, flags = api.Optimizer(ctx).local_ba(gpu)
+    assert (g["iters_robust"], g["iters_refine"]) == (r["iters_robust"], r["iters_refine"])
+    assert abs(g["final_cost"] - r["final_cost"]) <= 1e-8 * max(1.0, r["final_cost"])
+    assert np.abs(gpu["pose"] - ref["pose"]).max() <= 1e-6
+    assert np.abs(gpu["lm_invdepth"] - ref["lm_invdepth"]).max() <= 1e-6
+    assert (flags != r["flags"]).sum() <= 2
