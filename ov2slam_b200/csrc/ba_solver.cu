@@ -372,7 +372,16 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
 }
 
 // ------------------------------------------------------------------ reduced camera system (one CTA)
-template <int MODE>   // 0: Cholesky in global/L2 (large n), 1: Cholesky in shared memory, 2 / 3: Gauss-Jordan in registers (n <= 63 / n <= 96)
+// FP64 tensor-core tile product (DMMA): D(8x8) = A(8x4) B(4x8) + C.  Fragment layout (PTX ISA,
+// mma.m8n8k4 .f64): lane = 4 g + t; A: (row g, col t); B: (row t, col g); C/D: (row g, cols 2t, 2t+1).
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int CH_NB = 32;   // block size of the blocked Cholesky (mode 4)
+
+template <int MODE>   // 0: Cholesky in global/L2, 1: Cholesky in shared memory, 2 / 3: Gauss-Jordan in registers (n <= 63 / n <= 96),
+                      // 4: blocked Cholesky, trailing update on the FP64 tensor cores (n > 96)
 __global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kernel(BaDev D, double radius, int first_iter) {
     extern __shared__ double sA[];
     __shared__ int s_fail;
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kerne
         w[i] = D.gcam[i] + D.rhs[i];
     }
     __syncthreads();
-    if (MODE >= 2) {
+    if (MODE == 2 || MODE == 3) {
         // Gauss-Jordan elimination on the augmented system [S | b] held in REGISTERS: warp w owns rows
         // w*RPW .. w*RPW+RPW-1, lane l owns columns l + 32 k.  Each pivot step the owners publish pivot
         // row j and column j through a double-buffered shared-memory line, then everyone updates its
@@ -483,6 +492,163 @@ __global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kerne
                 }
         }
         __syncthreads();
+    } else if (MODE == 4) {
+        // Blocked right-looking Cholesky S = U'U (upper triangle, in global/L2), block size 32, on the
+        // augmented system [S | b] so the forward substitution U'y = b comes out of the panel step:
+        //   (1) warp 0 factors the 32 x 32 diagonal block in REGISTERS (lane = column, shuffles only);
+        //   (2) one thread per trailing column solves U11' x = a  (panel row block U12, and y_k for b);
+        //   (3) A22 -= U12' U12 is a true contraction (k = 32): 16 x 16 warp tiles on the FP64 tensor
+        //       cores (mma.sync m8n8k4 -> DMMA), operands staged in shared memory (sP);
+        // then the backward substitution runs block by block (GEMV by all warps + a 32-step register
+        // solve by warp 0).  9 block steps for the C5 window (n = 288) instead of 288 column steps,
+        // each of which cost an L2 round trip in mode 0.
+        const int PW = ((n + 15) & ~15) + 8;                 // sP row pitch (doubles): bank-spread for the fragment loads
+        double* sP = sA;                                     // [32][PW]  current row panel U12
+        __shared__ double sU[CH_NB][CH_NB + 1];              // diagonal block U11
+        __shared__ double s_idiag_all[MAX_N + CH_NB];        // 1 / U[j][j] (identity padding of the last block included)
+        __shared__ double s_t[CH_NB];
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        for (int kb = 0; kb < n; kb += CH_NB) {
+            const int nb = min(CH_NB, n - kb), c1 = kb + nb, m = n - c1;
+            double* s_idiag = s_idiag_all + kb;
+            // ---- (1) diagonal block: load, factor in registers
+            for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+                const int i = e >> 5, j = e & 31;
+                sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // lane = column c of the block; row j is final when step j starts.  The trailing rows are
+                // updated in shared memory (row pitch 33: conflict-free), 31 - j independent FMAs per step.
+                bool bad = false;
+                for (int j = 0; j < CH_NB; ++j) {
+                    const double d = sU[j][j];
+                    // pivots of the Jacobi-scaled, damped system are O(1); outside the float range the
+                    // factorisation is reported as failed (Ceres' LLT would return a useless step there)
+                    bad = bad || !(d > 1e-30) || !(d < 1e30);
+                    double is = (double)rsqrtf((float)d);                    // MUFU seed + 2 Newton steps in double:
+                    is = is * (1.5 - 0.5 * d * is * is);                     // no library call on the 32-step
+                    is = is * (1.5 - 0.5 * d * is * is);                     // critical path, error < 1 ulp
+                    const double ujc = lane >= j ? sU[j][lane] * is : 0.0;   // row j of U (diagonal: d / sqrt(d))
+                    __syncwarp();
+                    sU[j][lane] = ujc;
+                    if (lane == j) s_idiag[j] = is;
+                    __syncwarp();
+#pragma unroll 4
+                    for (int r = j + 1; r < CH_NB; ++r)
+                        if (lane >= r) sU[r][lane] -= sU[j][r] * ujc;
+                    __syncwarp();
+                }
+                if (bad && lane == 0) s_fail = 1;
+            }
+            __syncthreads();
+            if (s_fail) break;                                               // uniform
+            for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+                const int i = e >> 5, j = e & 31;
+                if (i < nb && j < nb && i <= j) A[(size_t)(kb + i) * n + kb + j] = sU[i][j];
+            }
+            // ---- (2) panel: thread per column c in (c1 .. n-1) and the rhs column (c == n)
+            const int m16 = (m + 15) & ~15;
+            for (int cc = tid; cc <= m16; cc += nt) {
+                if (cc >= m && cc < m16) {                                   // zero padding of the operand panel
+#pragma unroll
+                    for (int i = 0; i < CH_NB; ++i) sP[i * PW + cc] = 0.0;
+                    continue;
+                }
+                const bool is_rhs = cc == m16;
+                if (!is_rhs && cc >= m) continue;
+                double a[CH_NB];
+#pragma unroll
+                for (int i = 0; i < CH_NB; ++i)
+                    a[i] = i < nb ? (is_rhs ? w[kb + i] : A[(size_t)(kb + i) * n + c1 + cc]) : 0.0;
+#pragma unroll
+                for (int k = 0; k < CH_NB; ++k) {
+                    const double x = a[k] * s_idiag[k];
+                    a[k] = x;
+#pragma unroll
+                    for (int i = k + 1; i < CH_NB; ++i) a[i] -= sU[k][i] * x;
+                }
+                if (is_rhs) {
+#pragma unroll
+                    for (int i = 0; i < CH_NB; ++i) if (i < nb) { w[kb + i] = a[i]; s_t[i] = a[i]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CH_NB; ++i) {
+                        sP[i * PW + cc] = a[i];
+                        if (i < nb) A[(size_t)(kb + i) * n + c1 + cc] = a[i];
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- (3) trailing update.  rhs: w[c1 + r] -= sum_k U12[k][r] y_k
+            for (int r = tid; r < m; r += nt) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < CH_NB; ++k) acc += sP[k * PW + r] * s_t[k];
+                w[c1 + r] -= acc;
+            }
+            // A22[r][c] -= sum_k U12[k][r] U12[k][c], r <= c: 16 x 16 tiles per warp, 4 DMMA accumulators
+            {
+                const int mt = m16 >> 4, g = lane >> 2, t = lane & 3;
+                for (int idx = warp; idx < mt * mt; idx += nwarp) {
+                    const int tr = idx / mt, tc = idx - tr * mt;
+                    if (tr > tc) continue;
+                    const int r0 = tr * 16, q0 = tc * 16;
+                    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+                    for (int k0 = 0; k0 < CH_NB; k0 += 4) {
+                        const double* pk = sP + (k0 + t) * PW;
+                        const double a0 = pk[r0 + g], a1 = pk[r0 + 8 + g];
+                        const double b0 = pk[q0 + g], b1 = pk[q0 + 8 + g];
+                        dmma_884(acc[0][0][0], acc[0][0][1], a0, b0);
+                        dmma_884(acc[0][1][0], acc[0][1][1], a0, b1);
+                        dmma_884(acc[1][0][0], acc[1][0][1], a1, b0);
+                        dmma_884(acc[1][1][0], acc[1][1][1], a1, b1);
+                    }
+#pragma unroll
+                    for (int hi = 0; hi < 2; ++hi)
+#pragma unroll
+                        for (int hj = 0; hj < 2; ++hj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int r = r0 + 8 * hi + g, c = q0 + 8 * hj + 2 * t + e;
+                                if (r <= c && c < m) A[(size_t)(c1 + r) * n + c1 + c] -= acc[hi][hj][e];
+                            }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (s_fail) {
+            if (tid == 0) D.scal[SC_CHOL_FAIL] = 1.0;
+            return;
+        }
+        // ---- backward substitution U z = y, last block first
+        for (int kb = ((n - 1) / CH_NB) * CH_NB; kb >= 0; kb -= CH_NB) {
+            const int nb = min(CH_NB, n - kb), c1 = kb + nb;
+            for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+                const int i = e >> 5, j = e & 31;
+                sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
+            }
+            for (int i = warp; i < nb; i += nwarp) {                         // t_i = y_i - U12[i][:] z_rest
+                double acc = 0.0;
+                for (int c = c1 + lane; c < n; c += 32) acc += A[(size_t)(kb + i) * n + c] * w[c];
+                acc = warp_sum(acc);
+                if (lane == 0) s_t[i] = w[kb + i] - acc;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double ti = lane < nb ? s_t[lane] : 0.0;
+                const double idg = lane < nb ? s_idiag_all[kb + lane] : 1.0;
+#pragma unroll
+                for (int j = CH_NB - 1; j >= 0; --j) {
+                    const double zj = __shfl_sync(FULL, ti * idg, j);
+                    if (lane < j) ti -= sU[lane][j] * zj;
+                    if (lane == j && j < nb) w[kb + j] = zj;
+                }
+            }
+            __syncthreads();
+        }
     } else {
     if (SMEM) {
         for (int e = tid; e < n * n; e += nt) sA[e] = D.S[e];
@@ -719,18 +885,23 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
         if (sh && sh->fn) D.ncopy = 1;
         if (getenv("OV2_BA_NCOPY")) { int e = atoi(getenv("OV2_BA_NCOPY")); if (e >= 1 && e <= D.ncopy) D.ncopy = e; }
     }
-    // reduced-system solver: Gauss-Jordan in shared memory for small windows, Cholesky in shared memory
-    // while it fits, Cholesky in global/L2 beyond (C5: 288 x 288)
-    int solve_mode = n <= 63 ? 2 : (n <= 96 ? 3 : ((size_t)n * n * sizeof(double) <= 200 * 1024 ? 1 : 0));
+    // reduced-system solver: register Gauss-Jordan for small windows, blocked tensor-core Cholesky beyond
+    // (C5: 288 x 288); the unblocked Cholesky paths (0: global/L2, 1: shared memory) stay selectable
+    int solve_mode = n <= 63 ? 2 : (n <= 96 ? 3 : 4);
     if (getenv("OV2_BA_SOLVER")) {
-        const int e = atoi(getenv("OV2_BA_SOLVER"));   // 0/1 force the Cholesky paths (tests)
-        if (e == 0 || (e == 1 && (size_t)n * n * sizeof(double) <= 200 * 1024)) solve_mode = e;
+        const int e = atoi(getenv("OV2_BA_SOLVER"));   // 0 / 1 / 4 force a Cholesky path (tests, comparisons)
+        if (e == 0 || (e == 4 && n > 0) || (e == 1 && (size_t)n * n * sizeof(double) <= 200 * 1024)) solve_mode = e;
     }
-    const size_t smem_need = solve_mode == 1 ? (size_t)n * n * sizeof(double) : 0;   // modes 2/3 live in registers
-    int solve_threads = solve_mode == 2 ? 32 * div_up(n, 4) : (solve_mode == 3 ? 32 * div_up(n, 6) : 1024);
+    const size_t smem_need = solve_mode == 1 ? (size_t)n * n * sizeof(double)             // modes 2/3 live in registers
+                           : (solve_mode == 4 ? (size_t)CH_NB * (((n + 15) & ~15) + 8) * sizeof(double) : 0);
+    int solve_threads = solve_mode == 2 ? 32 * div_up(n, 4) : (solve_mode == 3 ? 32 * div_up(n, 6) : (solve_mode == 4 ? 512 : 1024));
     if (solve_threads < 32) solve_threads = 32;   // n == 0: every pose constant, only landmarks move
-    if (smem_need > 48 * 1024)
-        OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+    if (smem_need > 24 * 1024) {   // static (up to ~15 KB) + dynamic beyond 48 KB needs the opt-in
+        if (solve_mode == 1)
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+        else
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+    }
     // candidate buffers start equal to x: parameter blocks that are not in this solve's program
     // (constant / unused) must keep their current value through pointer swaps
     OV2_CUDA(ctx, cudaMemcpyAsync(cand_pose, pose, sizeof(double) * 7 * D.ncam, cudaMemcpyDeviceToDevice, st));
@@ -766,6 +937,8 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<2><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
         else if (solve_mode == 3)
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<3><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
+        else if (solve_mode == 4)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<4><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter));
         else if (solve_mode == 1)
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<1><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter));
         else

@@ -19,6 +19,8 @@
 #include "ov2_common.cuh"
 #include "stdsort_emul.h"
 
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include <math.h>
 #include <stdlib.h>
 
@@ -42,15 +44,45 @@ struct FastArgs {
     int score_mode;             // 0: bisection on the 9-run bit test, 1: sliding-window min (sparse table)
 };
 
+// ---- TMA staging (sm_90+/sm_100a): one elected thread issues a single cp.async.bulk.tensor that lands
+// the whole cell ROI (box BOXW x cs bytes of frame z) in shared memory and completes on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------------- F1
-__global__ void fast_cells_kernel(FastArgs A) {
-    extern __shared__ uint8_t smem[];
+// roi pitch `rp`: cs on the plain-load path, the TMA box width (64 / 128) when the tile is staged by TMA
+__global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMap tmap, int use_tma, int rp) {
+    extern __shared__ __align__(128) uint8_t smem[];
     const int cs = A.cs;
-    uint8_t* roi = smem;                       // cs*cs
-    uint8_t* sc = smem + cs * cs;              // cs*cs: score s (0 = not a corner at th)
-    uint8_t* keep = sc + cs * cs;              // cs*cs
-    uint16_t* clist = (uint16_t*)(keep + ((cs * cs + 1) & ~1));   // corner pixel indices (compacted)
+    const uint8_t* roi = smem;                              // rp * cs (TMA destination: 128-byte aligned)
+    const int roi_bytes = (rp * cs + 127) & ~127;
+    uint8_t* sc = smem + roi_bytes;                         // cs*cs: score s (0 = not a corner at th)
+    uint8_t* keep = sc + cs * cs;                           // cs*cs
+    uint16_t* clist = (uint16_t*)(smem + roi_bytes + ((2 * cs * cs + 1) & ~1));   // corner pixel indices (compacted), 2-byte aligned
     __shared__ int s_ncorner;
+    __shared__ __align__(8) uint64_t s_bar;
     const int cell = blockIdx.x, fr = blockIdx.y;
     const int r = cell / A.nwc, c = cell - r * A.nwc;
     const int x0 = c * cs, y0 = r * cs;
@@ -61,12 +93,28 @@ __global__ void fast_cells_kernel(FastArgs A) {
         return;
     }
     const int th = A.th[fr];
-    const uint8_t* img = A.img + A.fstride * (A.first + fr) + (size_t)y0 * A.pitch + x0;
-    for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) {
-        int yy = i / cs, xx = i - yy * cs;
-        roi[i] = __ldg(img + (size_t)yy * A.pitch + xx);
-        sc[i] = 0;
-        keep[i] = 0;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)(rp * cs));
+            // measured on B200: a uint8 tiled box must START on a 16-byte boundary in the innermost
+            // dimension (any other x faults with "illegal instruction"), so the box starts at x0 & ~15
+            // and the cell's ROI begins (x0 & 15) bytes into each staged row.  Box columns beyond the
+            // image are zero-filled and never read.
+            tma_load_3d(smem, &tmap, &s_bar, x0 & ~15, y0, A.first + fr);
+        }
+        roi = smem + (x0 & 15);
+        for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) { sc[i] = 0; keep[i] = 0; }
+        __syncthreads();             // barrier init visible to every waiter
+        mbar_wait(&s_bar, 0);
+    } else {
+        const uint8_t* img = A.img + A.fstride * (A.first + fr) + (size_t)y0 * A.pitch + x0;
+        for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) {
+            int yy = i / cs, xx = i - yy * cs;
+            smem[yy * rp + xx] = __ldg(img + (size_t)yy * A.pitch + xx);
+            sc[i] = 0;
+            keep[i] = 0;
+        }
     }
     if (threadIdx.x == 0) s_ncorner = 0;
     __syncthreads();
@@ -75,16 +123,16 @@ __global__ void fast_cells_kernel(FastArgs A) {
     // 16-ring contains at least two of the compass points {0,4,8,12}.
     for (int i = threadIdx.x; i < in_w * in_w; i += blockDim.x) {
         int yy = 3 + i / in_w, xx = 3 + i % in_w;
-        const uint8_t* p = roi + yy * cs + xx;
+        const uint8_t* p = roi + yy * rp + xx;
         const int v = *p;
-        const int c0 = v - (int)p[-3 * cs], c4 = v - (int)p[3], c8 = v - (int)p[3 * cs], c12 = v - (int)p[-3];
+        const int c0 = v - (int)p[-3 * rp], c4 = v - (int)p[3], c8 = v - (int)p[3 * rp], c12 = v - (int)p[-3];
         const int nb = (c0 > th) + (c4 > th) + (c8 > th) + (c12 > th);
         const int nd = (c0 < -th) + (c4 < -th) + (c8 < -th) + (c12 < -th);
         if (nb < 2 && nd < 2) continue;
         unsigned bright = 0, dark = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            int dk_ = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
+            int dk_ = v - (int)p[c_ring_dy[k] * rp + c_ring_dx[k]];
             bright |= (unsigned)(dk_ > th) << k;
             dark |= (unsigned)(dk_ < -th) << k;
         }
@@ -102,11 +150,11 @@ __global__ void fast_cells_kernel(FastArgs A) {
     const int ncorner = s_ncorner;
     for (int i = threadIdx.x; i < ncorner; i += blockDim.x) {
         const int pi = clist[i];
-        const uint8_t* p = roi + pi;
+        const uint8_t* p = roi + (pi / cs) * rp + (pi % cs);
         const int v = *p;
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)p[c_ring_dy[k] * cs + c_ring_dx[k]];
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)p[c_ring_dy[k] * rp + c_ring_dx[k]];
         int lo;
         if (A.score_mode == 1) {
             // s = max_k min(d[k..k+8]) (bright) / max_k min(-d[k..k+8]) (dark) with a sparse table:
@@ -455,6 +503,53 @@ void circle_halfwidths(int radius, int* hw) {
 
 }  // namespace
 
+// Host side of the TMA staging: a 3-D tiled tensor map {W, H, frames} over the level-0 images, box
+// {rp, cs, 1} (rp = cs + 15 rounded up to 16 bytes: the box starts on the 16-byte boundary at or below the cell).  Falls back to plain loads
+// when the images do not meet the TMA alignment rules (user-aliased level 0 with an odd pitch).
+typedef CUresult (*ov2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ov2_encode_tiled_fn tma_encoder() {
+    static ov2_encode_tiled_fn fn = []() -> ov2_encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (ov2_encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+static ov2_status launch_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, const FastArgs& FA, int nframes_grid) {
+    const int cs = FA.cs;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tma = 0, rp = cs;
+    const char* env = getenv("OV2_NO_TMA");
+    ov2_encode_tiled_fn enc = (env && atoi(env)) ? nullptr : tma_encoder();
+    if (enc && ((uintptr_t)FA.img % 16) == 0 && FA.pitch % 16 == 0 && FA.fstride % 16 == 0) {
+        const int box_w = (cs + 15 + 15) & ~15;
+        cuuint64_t dims[3] = {(cuuint64_t)FA.w, (cuuint64_t)FA.h, (cuuint64_t)pyr->batch};
+        cuuint64_t strides[2] = {(cuuint64_t)FA.pitch, (cuuint64_t)FA.fstride};
+        cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)cs, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)FA.img, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) { use_tma = 1; rp = box_w; }
+    }
+    const int threads = cs > 24 ? 128 : 32;
+    const size_t roi_bytes = ((size_t)rp * cs + 127) & ~(size_t)127;
+    const size_t smem = roi_bytes + (size_t)2 * cs * cs + 2 + (size_t)2 * (cs - 6) * (cs - 6);
+    if (smem > 48 * 1024)
+        OV2_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OV2_LAUNCH(ctx, "fast_cells_kernel",
+               fast_cells_kernel<<<dim3(FA.nwc * FA.nhc, nframes_grid), threads, smem, ctx->stream>>>(FA, tmap, use_tma, rp));
+    return OV2_OK;
+}
+
+
 extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int cellsize,
                                     const int32_t* curkp_offsets, const float* curkps, int32_t* fast_th_inout,
                                     int max_per_frame, float* out_pts, int32_t* out_counts, int32_t* out_pts_int,
@@ -528,13 +623,7 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     FA.first = first; FA.cs = cellsize; FA.nwc = nwc; FA.nhc = nhc; FA.cap = cap;
     FA.th = d_th; FA.cand = d_cand; FA.cand_n = d_candn; FA.overflow = d_ovf;
     FA.score_mode = getenv("OV2_FAST_SCORE") ? atoi(getenv("OV2_FAST_SCORE")) : 1;
-    {
-        int threads = cellsize > 24 ? 128 : 32;
-        size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
-        if (smem > 48 * 1024)
-            OV2_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OV2_LAUNCH(ctx, "fast_cells_kernel", fast_cells_kernel<<<dim3(ncells, count), threads, smem, ctx->stream>>>(FA));
-    }
+    if ((st = launch_fast_cells(ctx, pyr, FA, count)) != OV2_OK) return st;
     SweepArgs SA;
     SA.w = W; SA.h = H; SA.cs = cellsize; SA.nwc = nwc; SA.nhc = nhc; SA.cap = cap;
     SA.radius = cellsize / 4; SA.max_per_frame = max_per_frame;
@@ -609,8 +698,6 @@ extern "C" ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int
     FA.overflow = (int32_t*)o;
     OV2_CUDA(ctx, cudaMemsetAsync(FA.overflow, 0, sizeof(int32_t), ctx->stream));
     FA.score_mode = getenv("OV2_FAST_SCORE") ? atoi(getenv("OV2_FAST_SCORE")) : 1;
-    int threads = cellsize > 24 ? 128 : 32;
-    size_t smem = (size_t)3 * cellsize * cellsize + 2 + (size_t)2 * (cellsize - 6) * (cellsize - 6);
-    OV2_LAUNCH(ctx, "fast_cells_kernel", fast_cells_kernel<<<dim3(ncells, 1), threads, smem, ctx->stream>>>(FA));
+    if ((st = launch_fast_cells(ctx, pyr, FA, 1)) != OV2_OK) return st;
     return ov2_end(ctx);
 }

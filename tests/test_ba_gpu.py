@@ -100,11 +100,20 @@ def test_localba_refine_loss_override(ctx):
     _check(ctx, pb, refine_trivial_loss=True)
 
 
-@pytest.mark.parametrize("ncam,npts,nobs", [(16, 1200, 7000), (22, 1500, 9000), (50, 4000, 30000)])
-def test_localba_all_reduced_solver_paths(ctx, ncam, npts, nobs):
-    """Reduced camera systems of 84, 120 and 288 unknowns: register Gauss-Jordan (n <= 96), Cholesky in
-    shared memory (n^2 doubles <= 200 KB) and Cholesky in global/L2 (C5-sized windows), each against
-    the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to oracle/ba_ref.py)."""
+@pytest.mark.parametrize("ncam,npts,nobs,solver", [
+    (16, 1200, 7000, None), (16, 1200, 7000, "4"),
+    (22, 1500, 9000, None), (22, 1500, 9000, "1"), (22, 1500, 9000, "0"),
+    (50, 4000, 30000, None), (50, 4000, 30000, "0")])
+def test_localba_all_reduced_solver_paths(ctx, monkeypatch, ncam, npts, nobs, solver):
+    """Reduced camera systems of 84, 120 and 288 unknowns through every solver path: register
+    Gauss-Jordan (default for n <= 96), blocked Cholesky with the FP64 tensor-core trailing update
+    (default beyond; forced with OV2_BA_SOLVER=4), unblocked Cholesky in shared memory (=1) and in
+    global/L2 (=0), each against the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to
+    oracle/ba_ref.py)."""
+    if solver is None:
+        monkeypatch.delenv("OV2_BA_SOLVER", raising=False)
+    else:
+        monkeypatch.setenv("OV2_BA_SOLVER", solver)
     from oracle import ba_ref_c
     pb = synth.make_ba_problem(70 + ncam, ncam, npts, nobs)
     ref = _clone(pb)
