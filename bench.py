@@ -349,6 +349,21 @@ class Workload:
         list(self.pool.map(self._e2e_chunk, range(self.nchunks)))
         return int(self.h_cnt.sum())          # the step's result is read on the host (new keypoint counts)
 
+    def _e2e_chunk_stream(self, k: int, steps: int):
+        a = self._cargs[k]
+        f0, cs = k * self.cs, self.cs
+        total = 0
+        for _ in range(steps):
+            self._e2e_chunk(k)
+            total += int(self.h_cnt[f0:f0 + cs].sum())   # this chunk's result of this step, read on the host
+        return total
+
+    def stream_e2e(self, steps: int):
+        """`steps` steps, pipelined: every chunk thread runs its share of each step back to back, so the
+        uploads of step s+1 overlap the kernels of step s (a streaming front-end; no barrier between
+        steps).  Every step still uploads all its inputs and reads all its results on the host."""
+        return sum(self.pool.map(lambda k: self._e2e_chunk_stream(k, steps), range(self.nchunks)))
+
     def e2e_launches(self):
         return sum(c.launch_count() for c in self.ectx)
 
@@ -422,15 +437,38 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     ms_res, wall_res, launches = timed(wl.step_resident, args.steps, args.warmup)
+    if args.kernels_only:
+        # profiler runs (ncu serialises kernels; the multi-threaded e2e arm must not run under it)
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"kernels_only": True, "ms_per_step": ms_res / args.steps, "batch": args.batch,
+                              "note": "not a bench line: resident steps only, for ncu"}), flush=True)
+        return 0
     if args.e2e_chunks <= 0:
         args.e2e_chunks = 8 if world == 1 else max(2, min(8, 16 // world))
     while args.batch % args.e2e_chunks:
         args.e2e_chunks -= 1
     wl.init_e2e(args.e2e_chunks)
     ms_e2e_dev, wall_e2e, _ = timed(wl.step_e2e, args.steps, max(1, args.warmup))
-    clocks = sampler.stop() if rank == 0 else None
     # device events miss host-side staging of the last D2H sync; use the larger of event/wall time for e2e
-    ms_e2e = max(ms_e2e_dev, wall_e2e)
+    ms_e2e_stepped = max(ms_e2e_dev, wall_e2e)
+    # pipelined variant (the headline e2e): same K steps, same copies, no barrier between steps.
+    # The K-step region is timed three times and the MEDIAN is reported (host-thread scheduling on the
+    # box's CPU quota makes single regions of ~0.1 s noisy); all three are kept in the JSON line.
+    wl.stream_e2e(max(1, args.warmup))
+    stream_ms = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        wl.stream_e2e(args.steps)
+        torch.cuda.synchronize()
+        tp = torch.tensor([(time.perf_counter() - t0) * 1000.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        stream_ms.append(float(tp[0]))
+    ms_e2e_stream = sorted(stream_ms)[1]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = ms_e2e_stepped if args.e2e_stepped else ms_e2e_stream
     frames = world * args.batch * args.steps
     value = frames / (ms_res / 1000.0)
     e2e = frames / (ms_e2e / 1000.0)
@@ -477,7 +515,11 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32",
             "data": "synthetic", "config": _config(args.batch, "per-GPU batch fixed (weak scaling); no data-path collective"),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
-                    "ms_per_step": ms_e2e / args.steps, "chunks": args.e2e_chunks},
+                    "ms_per_step": ms_e2e / args.steps, "chunks": args.e2e_chunks,
+                    "mode": "stepped (barrier after every step)" if args.e2e_stepped else
+                            "pipelined (chunk threads stream through the K steps; every step uploads its inputs and reads its results)",
+                    "stepped_value": frames / (ms_e2e_stepped / 1000.0), "pipelined_value": frames / (ms_e2e_stream / 1000.0),
+                    "pipelined_repeats": [frames / (m / 1000.0) for m in stream_ms]},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
         if world == 1 and not args.no_ba:
@@ -559,6 +601,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frame pairs per GPU per step")
+    ap.add_argument("--e2e-stepped", action="store_true", help="headline e2e with a barrier after every step (default: pipelined)")
+    ap.add_argument("--kernels-only", action="store_true", help="run the resident steps only and exit (for ncu captures)")
     ap.add_argument("--e2e-chunks", type=int, default=0,
                     help="chunks (host threads x contexts) of the e2e arm; 0 = 8 on one GPU, fewer per rank when several "
                          "ranks share the host cores")

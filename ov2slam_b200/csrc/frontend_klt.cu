@@ -19,7 +19,6 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct KltArgs {
@@ -34,6 +33,7 @@ struct KltArgs {
     uint8_t* status;
     int max_iter;
     float eps, ferr, fb_dist;
+    int* work_counter;   // persistent launch: warps pull keypoint indices from this counter (null: one warp per index)
 };
 
 __device__ __forceinline__ int reflect101_safe(int i, int n) {
@@ -43,6 +43,19 @@ __device__ __forceinline__ int reflect101_safe(int i, int n) {
         if (i >= n) i = 2 * (n - 1) - i;
     }
     return i;
+}
+
+// dp2a with SIGNED 16-bit halves of a (bilinear weights: iw11 = 16384 - others can round to -1) and
+// UNSIGNED bytes of b (pixels): lo uses bytes 0,1 of b, hi bytes 2,3
+__device__ __forceinline__ int dp2a_lo_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 // exact 64-bit warp sum of per-lane int32 partials via two 32-bit redux ops
@@ -61,6 +74,11 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
                          int max_iter, double eps2, float& err_out, uint8_t* sP, int* sD, int lane) {
     constexpr int NPX = WIN * WIN;
     constexpr int PER_LANE = (NPX + 31) / 32;
+    // window pixel owned by (lane, k).  WIN = 9: lane l < 27 owns the three horizontally adjacent pixels
+    // 3l .. 3l+2 (row l / 3, columns 3 (l % 3) ..), so the search-image taps of a lane are 4 consecutive
+    // bytes on two rows (packed fast path below); the integer window sums are order independent.
+    constexpr bool PACK3 = (WIN == 9);
+#define PIX(lane_, k_) (PACK3 ? ((lane_) < 27 ? 3 * (lane_) + (k_) : NPX) : (lane_) + 32 * (k_))
     constexpr int PW = WIN + 3;  // u8 neighbourhood (WIN+1 bilinear footprint + 1-px Scharr halo each side)
     constexpr int DW = WIN + 1;  // derivative / search patch width
     const float half = (WIN - 1) * 0.5f;
@@ -73,6 +91,8 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         const uint8_t* Iimg = Ipyr.lvl[level] + Ipyr.fstride[level] * frame;
         const uint8_t* Jimg = Jpyr.lvl[level] + Jpyr.fstride[level] * frame;
         const int Ipitch = Ipyr.pitch[level], Jpitch = Jpyr.pitch[level];
+        const bool packed_ok = ((reinterpret_cast<uintptr_t>(Jimg) | (uintptr_t)Jpitch) & 3) == 0;   // aliased level 0 may be unaligned
+        const int lane_row = lane / 3, lane_col = 3 * (lane - 3 * (lane / 3));
         const float sc = 1.f / (float)(1 << level);
         float2 prevPt = make_float2(pt.x * sc, pt.y * sc);
         float2 nextPt;
@@ -132,7 +152,7 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         int sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
         for (int k = 0; k < PER_LANE; ++k) {
-            int p = lane + 32 * k;
+            int p = PIX(lane, k);
             Iv[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
             if (p < NPX) {
                 int y = p / WIN, x = p - y * WIN;
@@ -177,12 +197,36 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
             iw10 = __float2int_rn((1.f - a) * b * 16384.f);
             iw11 = 16384 - iw00 - iw01 - iw10;
             int sb1 = 0, sb2 = 0;
-            if (jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
+            if (PACK3 && packed_ok && jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
+                // interior, word-aligned level (warp-uniform): the lane's 4 + 4 taps come from two aligned
+                // 32-bit words per row (funnel shift), the 14-bit bilinear weights are applied with
+                // dp2a (u16 x u8 pairs): 4 loads + 6 dp2a per lane instead of 12 byte loads + 12 IMADs.
+                // Same integers as the byte path (signed 16-bit weights x unsigned bytes, exact in int32).
+                if (lane < 27) {
+                    const uint8_t* q = Jimg + (size_t)(jy + lane_row) * Jpitch + (jx + lane_col);
+                    const uintptr_t qa = reinterpret_cast<uintptr_t>(q);
+                    const unsigned sh = (unsigned)(qa & 3) * 8u;
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(qa & ~(uintptr_t)3);
+                    const uint32_t* wb = reinterpret_cast<const uint32_t*>((qa & ~(uintptr_t)3) + Jpitch);
+                    const unsigned t0 = __ldg(w), b0 = __ldg(wb);
+                    unsigned t1 = 0, b1w = 0;
+                    if (sh) { t1 = __ldg(w + 1); b1w = __ldg(wb + 1); }
+                    const unsigned top = __funnelshift_r(t0, t1, sh), bot = __funnelshift_r(b0, b1w, sh);
+                    const unsigned W01 = ((unsigned)iw00 & 0xFFFFu) | ((unsigned)iw01 << 16);
+                    const unsigned W23 = ((unsigned)iw10 & 0xFFFFu) | ((unsigned)iw11 << 16);
+                    const int j0 = dp2a_lo_su(W01, top, dp2a_lo_su(W23, bot, 256)) >> 9;
+                    const int j1 = dp2a_lo_su(W01, top >> 8, dp2a_lo_su(W23, bot >> 8, 256)) >> 9;
+                    const int j2 = dp2a_hi_su(W01, top, dp2a_hi_su(W23, bot, 256)) >> 9;
+                    const int d0 = j0 - (int)Iv[0], d1 = j1 - (int)Iv[1], d2 = j2 - (int)Iv[2];
+                    sb1 = d0 * (int)Ixv[0] + d1 * (int)Ixv[1] + d2 * (int)Ixv[2];
+                    sb2 = d0 * (int)Iyv[0] + d1 * (int)Iyv[1] + d2 * (int)Iyv[2];
+                }
+            } else if (jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
                 // interior (warp-uniform): every lane gathers its own 4 taps straight from L1/L2
                 const uint8_t* src = Jimg + (size_t)jy * Jpitch + jx;
 #pragma unroll
                 for (int k = 0; k < PER_LANE; ++k) {
-                    int p = lane + 32 * k;
+                    int p = PIX(lane, k);
                     if (p < NPX) {
                         int y = p / WIN, x = p - y * WIN;
                         const uint8_t* q = src + y * Jpitch + x;
@@ -203,7 +247,7 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < PER_LANE; ++k) {
-                    int p = lane + 32 * k;
+                    int p = PIX(lane, k);
                     if (p < NPX) {
                         int y = p / WIN, x = p - y * WIN;
                         const uint8_t* q = sP + y * DW + x;
@@ -231,14 +275,23 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
     }
     err_out = err;
     return status;
+#undef PIX
 }
 
-template <int WIN>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fb_klt_kernel(KltArgs A) {
+// Keypoints need very different iteration counts (1 .. 30 per level), so a static warp <-> keypoint
+// assignment leaves SM slots idle while the slowest warp of a CTA finishes.  The persistent variant
+// fills the GPU once (resident CTAs only) and every warp pulls the next keypoint from a global counter.
+template <int WIN, int WARPS_PER_CTA>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt_kernel(KltArgs A) {
     __shared__ __align__(16) uint8_t sPall[WARPS_PER_CTA][((WIN + 3) * (WIN + 3) + 15) & ~15];
     __shared__ int sDall[WARPS_PER_CTA][(WIN + 1) * (WIN + 1)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * WARPS_PER_CTA + warp;
+    for (int i = blockIdx.x * WARPS_PER_CTA + warp;;) {
+    if (A.work_counter) {
+        int nxt_i = 0;
+        if (lane == 0) nxt_i = atomicAdd(A.work_counter, 1);
+        i = __shfl_sync(FULL, nxt_i, 0);
+    }
     if (i >= A.n) return;
     const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
     int maxlevel = A.lvls ? (int)A.lvls[i] : A.lvl_all;
@@ -271,6 +324,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) fb_klt_kernel(KltArgs A
         A.priors[i] = fwd;
         A.status[i] = ok ? 1 : 0;
     }
+    if (!A.work_counter) return;
+    __syncwarp();
+    }
+}
+
+template <int WPC>
+ov2_status launch_klt(ov2_ctx* ctx, KltArgs& A, bool persistent) {
+    int grid = div_up(A.n, WPC);
+    A.work_counter = nullptr;
+    if (persistent) {
+        int per_sm = 0, dev = 0, sms = 0;
+        OV2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fb_klt_kernel<9, WPC>, WPC * 32, 0));
+        OV2_CUDA(ctx, cudaGetDevice(&dev));
+        OV2_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int resident = per_sm * sms;
+        if (grid > resident) {
+            void* o = nullptr;
+            ov2_status st = ov2_scratch(ctx, sizeof(int), &o);
+            if (st != OV2_OK) return st;
+            A.work_counter = (int*)o;
+            OV2_CUDA(ctx, cudaMemsetAsync(A.work_counter, 0, sizeof(int), ctx->stream));
+            grid = resident;
+        }
+    }
+    OV2_LAUNCH(ctx, "fb_klt_kernel", (fb_klt_kernel<9, WPC><<<grid, WPC * 32, 0, ctx->stream>>>(A)));
+    return OV2_OK;
 }
 
 }  // namespace
@@ -312,6 +391,15 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
     A.priors = (float2*)o;
     if ((st = ov2_stage_out(ctx, status_out, (size_t)n, &o)) != OV2_OK) return st;
     A.status = (uint8_t*)o;
-    OV2_LAUNCH(ctx, "fb_klt_kernel", fb_klt_kernel<9><<<div_up(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, ctx->stream>>>(A));
+    {
+        const char* e = getenv("OV2_KLT_WPC");
+        const int wpc = e ? atoi(e) : 8;
+        const char* pe = getenv("OV2_KLT_PERSIST");
+        const bool persistent = pe ? atoi(pe) != 0 : true;
+        if (wpc == 2) st = launch_klt<2>(ctx, A, persistent);
+        else if (wpc == 4) st = launch_klt<4>(ctx, A, persistent);
+        else st = launch_klt<8>(ctx, A, persistent);
+        if (st != OV2_OK) return st;
+    }
     return ov2_end(ctx);
 }
