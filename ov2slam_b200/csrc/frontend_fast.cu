@@ -78,9 +78,12 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
     const int cs = A.cs;
     const uint8_t* roi = smem;                              // rp * cs (TMA destination: 128-byte aligned)
     const int roi_bytes = (rp * cs + 127) & ~127;
+    const int cs2p = (cs * cs + 3) & ~3;                    // padded to whole words (the emission scans keep[] as words)
     uint8_t* sc = smem + roi_bytes;                         // cs*cs: score s (0 = not a corner at th)
-    uint8_t* keep = sc + cs * cs;                           // cs*cs
-    uint16_t* clist = (uint16_t*)(smem + roi_bytes + ((2 * cs * cs + 1) & ~1));   // corner pixel indices (compacted), 2-byte aligned
+    uint8_t* keep = sc + cs2p;                              // cs*cs: NMS survivor under the mask rule
+    uint16_t* clist = (uint16_t*)(keep + cs2p);             // corners, (y << 8) | x cell-local (compacted)
+    uint16_t* qlist = clist + (cs - 6) * (cs - 6);          // pixels that pass the compass pre-test (compacted)
+    __shared__ int s_nq;
     __shared__ int s_ncorner;
     __shared__ __align__(8) uint64_t s_bar;
     const int cell = blockIdx.x, fr = blockIdx.y;
@@ -104,31 +107,61 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
             tma_load_3d(smem, &tmap, &s_bar, x0 & ~15, y0, A.first + fr);
         }
         roi = smem + (x0 & 15);
-        for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) { sc[i] = 0; keep[i] = 0; }
+        for (int i = threadIdx.x; i < cs2p; i += blockDim.x) { sc[i] = 0; keep[i] = 0; }
         __syncthreads();             // barrier init visible to every waiter
         mbar_wait(&s_bar, 0);
     } else {
         const uint8_t* img = A.img + A.fstride * (A.first + fr) + (size_t)y0 * A.pitch + x0;
-        for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) {
+        for (int i = threadIdx.x; i < cs2p; i += blockDim.x) {
             int yy = i / cs, xx = i - yy * cs;
-            smem[yy * rp + xx] = __ldg(img + (size_t)yy * A.pitch + xx);
+            if (i < cs * cs) smem[yy * rp + xx] = __ldg(img + (size_t)yy * A.pitch + xx);
             sc[i] = 0;
             keep[i] = 0;
         }
     }
-    if (threadIdx.x == 0) s_ncorner = 0;
+    if (threadIdx.x == 0) { s_ncorner = 0; s_nq = 0; }
     __syncthreads();
     const int in_w = cs - 6;
-    // pass 1: corner test for every interior pixel.  Quick reject first: every 9-arc of the
-    // 16-ring contains at least two of the compass points {0,4,8,12}.
-    for (int i = threadIdx.x; i < in_w * in_w; i += blockDim.x) {
-        int yy = 3 + i / in_w, xx = 3 + i % in_w;
-        const uint8_t* p = roi + yy * rp + xx;
+    // pass 1a (every interior pixel): compass pre-test, survivors compacted into qlist.  Every 9-arc of
+    // the 16-ring contains two ADJACENT compass points {0,4,8,12}, so a corner needs two adjacent compass
+    // pixels brighter than v + th (or darker than v - th).  Doing the full ring test here instead would
+    // run it for nearly every warp (one passing lane is enough): ncu showed the 180-instruction ring block
+    // executed by 92 % of the warp iterations.  (y, x) advance incrementally: no division per pixel.
+    {
+        const int npx = in_w * in_w, lane = threadIdx.x & 31;
+        int i = threadIdx.x;
+        int yy = i / in_w, xx = i - yy * in_w;
+        const int sy = (int)blockDim.x / in_w, sx = (int)blockDim.x - sy * in_w;
+        for (int base = 0; base < npx; base += blockDim.x) {      // uniform trip count: ballots below
+            bool pass = false;
+            if (i < npx) {
+                const uint8_t* p = roi + (yy + 3) * rp + (xx + 3);
+                const int v = *p;
+                const int c0 = v - (int)p[-3 * rp], c4 = v - (int)p[3], c8 = v - (int)p[3 * rp], c12 = v - (int)p[-3];
+                const bool b0 = c0 > th, b4 = c4 > th, b8 = c8 > th, b12 = c12 > th;
+                const bool d0 = c0 < -th, d4 = c4 < -th, d8 = c8 < -th, d12 = c12 < -th;
+                pass = ((b0 || b8) && (b4 || b12)) || ((d0 || d8) && (d4 || d12));   // two adjacent compass points
+            }
+            const unsigned m = __ballot_sync(FULL, pass);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int slot = 0;
+                if (lane == leader) slot = atomicAdd(&s_nq, __popc(m));
+                slot = __shfl_sync(FULL, slot, leader);
+                if (pass) qlist[slot + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(((yy + 3) << 8) | (xx + 3));
+            }
+            i += blockDim.x;
+            xx += sx; yy += sy;
+            if (xx >= in_w) { xx -= in_w; yy++; }
+        }
+    }
+    __syncthreads();
+    // pass 1b (dense over the survivors): the 16-pixel ring test
+    const int nq = s_nq;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int yx = qlist[q];
+        const uint8_t* p = roi + (yx >> 8) * rp + (yx & 255);
         const int v = *p;
-        const int c0 = v - (int)p[-3 * rp], c4 = v - (int)p[3], c8 = v - (int)p[3 * rp], c12 = v - (int)p[-3];
-        const int nb = (c0 > th) + (c4 > th) + (c8 > th) + (c12 > th);
-        const int nd = (c0 < -th) + (c4 < -th) + (c8 < -th) + (c12 < -th);
-        if (nb < 2 && nd < 2) continue;
         unsigned bright = 0, dark = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -141,7 +174,7 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
         dk &= dk >> 1; dk &= dk >> 2; dk &= dk >> 4; dk &= dk >> 1;
         if ((b | dk) & 0xFFFFu) {
             int pos = atomicAdd(&s_ncorner, 1);
-            clist[pos] = (uint16_t)(yy * cs + xx);
+            clist[pos] = (uint16_t)yx;
         }
     }
     __syncthreads();
@@ -149,8 +182,9 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
     // = the largest t for which a 9-run of (d >= t) or (d <= -t) exists: bisection on t.
     const int ncorner = s_ncorner;
     for (int i = threadIdx.x; i < ncorner; i += blockDim.x) {
-        const int pi = clist[i];
-        const uint8_t* p = roi + (pi / cs) * rp + (pi % cs);
+        const int yx = clist[i];
+        const int pi = (yx >> 8) * cs + (yx & 255);
+        const uint8_t* p = roi + (yx >> 8) * rp + (yx & 255);
         const int v = *p;
         int d[16];
 #pragma unroll
@@ -202,8 +236,8 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
     __syncthreads();
     // 3x3 NMS on response = s - 1 (non-corners count 0): strictly greater than all 8 neighbours
     for (int i = threadIdx.x; i < ncorner; i += blockDim.x) {
-        const int pi = clist[i];
-        const int xx = pi % cs;
+        const int yx = clist[i];
+        const int xx = yx & 255, pi = (yx >> 8) * cs + xx;
         const int resp = (int)sc[pi] - 1;
         bool ok = true;
 #pragma unroll
@@ -219,26 +253,35 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
         if (ok && (xx & 2)) keep[pi] = 1;
     }
     __syncthreads();
-    // ordered emission (row-major scan order) by warp 0
+    // ordered emission (row-major scan order) by warp 0: keep[] is scanned as 32-bit words (almost all
+    // zero); the few non-zero words are expanded serially, so the output order is the scan order
     if (threadIdx.x < 32) {
         uint32_t* out = A.cand + ((size_t)fr * (A.nwc * A.nhc) + cell) * A.cap;
+        const uint32_t* kw = reinterpret_cast<const uint32_t*>(keep);
+        const int nw = cs2p >> 2, lane = threadIdx.x;
         int n = 0;
-        for (int base = 0; base < in_w * in_w; base += 32) {
-            int i = base + threadIdx.x;
-            bool k = false;
-            int yy = 0, xx = 0;
-            if (i < in_w * in_w) {
-                yy = 3 + i / in_w; xx = 3 + i % in_w;
-                k = keep[yy * cs + xx] != 0;
+        for (int base = 0; base < nw; base += 32) {
+            const int wi = base + lane;
+            const uint32_t w = wi < nw ? kw[wi] : 0u;
+            unsigned m = __ballot_sync(FULL, w != 0u);
+            while (m) {                                    // uniform
+                const int L = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t ww = __shfl_sync(FULL, w, L);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if ((ww >> (8 * b)) & 0xFFu) {
+                        if (lane == 0 && n < A.cap) {
+                            const int pi = (base + L) * 4 + b;
+                            const int yy = pi / cs, xx = pi - yy * cs;
+                            out[n] = ((uint32_t)(sc[pi] - 1) << 16) | ((uint32_t)yy << 8) | (uint32_t)xx;
+                        }
+                        n++;
+                    }
+                }
             }
-            unsigned m = __ballot_sync(FULL, k);
-            if (k) {
-                int pos = n + __popc(m & ((1u << threadIdx.x) - 1));
-                if (pos < A.cap) out[pos] = ((uint32_t)(sc[yy * cs + xx] - 1) << 16) | ((uint32_t)yy << 8) | (uint32_t)xx;
-            }
-            n += __popc(m);
         }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             if (n > A.cap) { atomicExch(A.overflow, 1); n = A.cap; }
             *out_n = n;
         }
@@ -541,7 +584,7 @@ static ov2_status launch_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, const Fast
     }
     const int threads = cs > 24 ? 128 : 32;
     const size_t roi_bytes = ((size_t)rp * cs + 127) & ~(size_t)127;
-    const size_t smem = roi_bytes + (size_t)2 * cs * cs + 2 + (size_t)2 * (cs - 6) * (cs - 6);
+    const size_t smem = roi_bytes + (size_t)2 * ((cs * cs + 3) & ~3) + (size_t)4 * (cs - 6) * (cs - 6);
     if (smem > 48 * 1024)
         OV2_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OV2_LAUNCH(ctx, "fast_cells_kernel",

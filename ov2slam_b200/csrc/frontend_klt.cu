@@ -16,6 +16,7 @@
 // the image edge, constant 0 outside the image - exactly the planes buildOpticalFlowPyramid
 // would have materialised), so the tracker reads only the 8-bit pyramid.
 #include "ov2_common.cuh"
+#include "klt_setup.cuh"
 
 namespace {
 
@@ -79,7 +80,6 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
     // bytes on two rows (packed fast path below); the integer window sums are order independent.
     constexpr bool PACK3 = (WIN == 9);
 #define PIX(lane_, k_) (PACK3 ? ((lane_) < 27 ? 3 * (lane_) + (k_) : NPX) : (lane_) + 32 * (k_))
-    constexpr int PW = WIN + 3;  // u8 neighbourhood (WIN+1 bilinear footprint + 1-px Scharr halo each side)
     constexpr int DW = WIN + 1;  // derivative / search patch width
     const float half = (WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -112,67 +112,24 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
         int iw11 = 16384 - iw00 - iw01 - iw10;
 
-        // ---- 8-bit neighbourhood rows iy-1.., cols ix-1.. (reflect-101 = the padded level)
+        // ---- level set-up (klt_setup.cuh): 12 x 12 neighbourhood -> shared memory (aligned words on the
+        //      interior path), Scharr at the 10 x 10 bilinear footprint, int16 template window + exact
+        //      integer normal-equation sums.  Lane l < 27 owns window pixels 3l .. 3l+2.
+        static_assert(WIN == kltsetup::WIN, "the level set-up is written for the 9 x 9 window");
         __syncwarp();
-        if (ix >= 1 && iy >= 1 && ix + PW - 1 <= lw && iy + PW - 1 <= lh) {
-            // interior (warp-uniform): no border handling
-            const uint8_t* src = Iimg + (size_t)(iy - 1) * Ipitch + (ix - 1);
-            for (int i = lane; i < PW * PW; i += 32) {
-                int r = i / PW, c = i - r * PW;
-                sP[i] = __ldg(src + r * Ipitch + c);
-            }
-        } else {
-            for (int i = lane; i < PW * PW; i += 32) {
-                int r = i / PW, c = i - r * PW;
-                int y = reflect101_safe(iy - 1 + r, lh), x = reflect101_safe(ix - 1 + c, lw);
-                sP[i] = __ldg(Iimg + (size_t)y * Ipitch + x);
-            }
-        }
+        const bool tmpl_aligned = ((reinterpret_cast<uintptr_t>(Iimg) | (uintptr_t)Ipitch) & 3) == 0;
+        const int off = kltsetup::stage_patch(lane, Iimg, Ipitch, lw, lh, ix, iy, tmpl_aligned, sP);
         __syncwarp();
-        // ---- Scharr at the DWxDW bilinear footprint; 0 outside the image (BORDER_CONSTANT)
-        for (int i = lane; i < DW * DW; i += 32) {
-            int r = i / DW, c = i - r * DW;
-            int y = iy + r, x = ix + c;
-            int dx = 0, dy = 0;
-            if (x >= 0 && x < lw && y >= 0 && y < lh) {
-                const uint8_t* p0 = sP + r * PW + c;  // row y-1, col x-1
-                const uint8_t* p1 = p0 + PW;
-                const uint8_t* p2 = p1 + PW;
-                int t0l = ((int)p0[0] + (int)p2[0]) * 3 + (int)p1[0] * 10;
-                int t0r = ((int)p0[2] + (int)p2[2]) * 3 + (int)p1[2] * 10;
-                dx = t0r - t0l;
-                int t1l = (int)p2[0] - (int)p0[0], t1c = (int)p2[1] - (int)p0[1], t1r = (int)p2[2] - (int)p0[2];
-                dy = (t1l + t1r) * 3 + t1c * 10;
-            }
-            sD[i] = (int)(((unsigned)dx & 0xFFFFu) | ((unsigned)dy << 16));
-        }
+        kltsetup::scharr_rows(lane, sP, off, ix, iy, lw, lh, sD);
         __syncwarp();
-        // ---- template patch (int16 semantics) + exact integer normal-equation sums
         short Iv[PER_LANE], Ixv[PER_LANE], Iyv[PER_LANE];
-        int sA11 = 0, sA12 = 0, sA22 = 0;
-#pragma unroll
-        for (int k = 0; k < PER_LANE; ++k) {
-            int p = PIX(lane, k);
-            Iv[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
-            if (p < NPX) {
-                int y = p / WIN, x = p - y * WIN;
-                const uint8_t* q = sP + (y + 1) * PW + (x + 1);
-                int ival = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[PW] * iw10 + (int)q[PW + 1] * iw11 + (1 << 8)) >> 9;
-                const int* d = sD + y * DW + x;
-                int d00 = d[0], d01 = d[1], d10 = d[DW], d11 = d[DW + 1];
-                int ixval = ((int)(short)(d00 & 0xFFFF) * iw00 + (int)(short)(d01 & 0xFFFF) * iw01 +
-                             (int)(short)(d10 & 0xFFFF) * iw10 + (int)(short)(d11 & 0xFFFF) * iw11 + (1 << 13)) >> 14;
-                int iyval = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
-                Iv[k] = (short)ival; Ixv[k] = (short)ixval; Iyv[k] = (short)iyval;
-                sA11 += ixval * ixval;
-                sA12 += ixval * iyval;
-                sA22 += iyval * iyval;
-            }
-        }
-        // |sums| <= 81 * 4080^2 = 1.35e9 < 2^31 for WIN = 9; use the 64-bit path to be safe for any WIN
-        float A11 = __ll2float_rn(warp_sum64(sA11)) * FLT_SCALE;
-        float A12 = __ll2float_rn(warp_sum64(sA12)) * FLT_SCALE;
-        float A22 = __ll2float_rn(warp_sum64(sA22)) * FLT_SCALE;
+        int sA11, sA12, sA22;
+        kltsetup::template_rows(lane, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22);
+        // |window sums| <= 81 * 4080^2 = 1.35e9 < 2^31 for the 9 x 9 window: one exact 32-bit redux each
+        // (the b sums of the iterations can reach 2.7e9 and keep the split 64-bit reduction)
+        float A11 = __int2float_rn(__reduce_add_sync(FULL, sA11)) * FLT_SCALE;
+        float A12 = __int2float_rn(__reduce_add_sync(FULL, sA12)) * FLT_SCALE;
+        float A22 = __int2float_rn(__reduce_add_sync(FULL, sA22)) * FLT_SCALE;
         float D = A11 * A22 - A12 * A12;
         float minEig = (A22 + A11 - __fsqrt_rn((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
         err = minEig;
@@ -283,8 +240,8 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
 // fills the GPU once (resident CTAs only) and every warp pulls the next keypoint from a global counter.
 template <int WIN, int WARPS_PER_CTA>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt_kernel(KltArgs A) {
-    __shared__ __align__(16) uint8_t sPall[WARPS_PER_CTA][((WIN + 3) * (WIN + 3) + 15) & ~15];
-    __shared__ int sDall[WARPS_PER_CTA][(WIN + 1) * (WIN + 1)];
+    __shared__ __align__(16) uint8_t sPall[WARPS_PER_CTA][kltsetup::SP_BYTES];
+    __shared__ __align__(16) int sDall[WARPS_PER_CTA][kltsetup::SD_INTS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = blockIdx.x * WARPS_PER_CTA + warp;;) {
     if (A.work_counter) {

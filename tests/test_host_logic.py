@@ -84,3 +84,80 @@ def test_product_never_imports_oracle():
             txt = p.read_text()
             assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), p
             assert not re.search(r'#include\s+"[^"]*oracle/', txt), p
+
+
+def test_klt_level_setup_lane_code_matches_definition(tmp_path):
+    """ov2slam_b200/csrc/klt_setup.cuh (the per-lane staging / Scharr / template code the KLT kernel
+    runs) compiled for the host and checked against the definition (reflect-101 neighbourhood, Scharr
+    with zero planes outside the image, OpenCV's fixed-point bilinear template) on random images and
+    window positions: interior, every border, word-aligned and unaligned rows."""
+    src = tmp_path / "k.cpp"
+    src.write_text(r'''
+#include "%s/ov2slam_b200/csrc/klt_setup.cuh"
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+using namespace kltsetup;
+static int refl(int i, int n) { return reflect101_any(i, n); }
+int main() {
+  std::mt19937 rng(11); long bad = 0, n_int = 0, n_brd = 0;
+  for (int it = 0; it < 20000; ++it) {
+    int lw = 14 + rng() %% 50, lh = 14 + rng() %% 40;
+    bool al = rng() %% 4 != 0;
+    int pitch = al ? ((lw + 3) & ~3) + 4 * (rng() %% 3) : lw + (rng() %% 3);
+    std::vector<uint32_t> store((size_t)(pitch * lh + 64) / 4 + 4);
+    uint8_t* img = reinterpret_cast<uint8_t*>(store.data()) + (al ? 0 : 1 + rng() %% 3);
+    for (int i = 0; i < pitch * lh; ++i) img[i] = (uint8_t)(rng() >> 7);
+    bool aligned = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 3) == 0;
+    int ix = (int)(rng() %% (lw + WIN)) - WIN, iy = (int)(rng() %% (lh + WIN)) - WIN;   // the kernel's admissible range
+    if (it %% 3 == 0) { ix = 1 + rng() %% (lw - 11); iy = 1 + rng() %% (lh - 11); }
+    (patch_interior(ix, iy, lw, lh) ? n_int : n_brd)++;
+    float a = (rng() %% 1000) / 1000.f, b = (rng() %% 1000) / 1000.f;
+    int iw00 = (int)((1.f - a) * (1.f - b) * 16384.f + .5f), iw01 = (int)(a * (1.f - b) * 16384.f + .5f),
+        iw10 = (int)((1.f - a) * b * 16384.f + .5f), iw11 = 16384 - iw00 - iw01 - iw10;
+    if (it %% 50 == 0) { iw11 = -1; iw00 += 1; }
+    alignas(16) uint8_t sP[SP_BYTES]; int sD[SD_INTS];
+    memset(sP, 0xCD, sizeof sP); memset(sD, 0x5A, sizeof sD);
+    int off = 0;
+    for (int l = 0; l < 32; ++l) off = stage_patch(l, img, pitch, lw, lh, ix, iy, aligned, sP);
+    for (int l = 0; l < 32; ++l) scharr_rows(l, sP, off, ix, iy, lw, lh, sD);
+    // definition
+    auto P = [&](int r, int c) { return (int)img[(size_t)refl(iy - 1 + r, lh) * pitch + refl(ix - 1 + c, lw)]; };
+    for (int r = 0; r < PW; ++r) for (int c = 0; c < PW; ++c) if (sP[r * SP_PITCH + off + c] != P(r, c)) bad++;
+    int dxr[DW][DW], dyr[DW][DW];
+    for (int r = 0; r < DW; ++r) for (int c = 0; c < DW; ++c) {
+      int y = iy + r, x = ix + c, dx = 0, dy = 0;
+      if (x >= 0 && x < lw && y >= 0 && y < lh) {
+        dx = (P(r, c + 2) + P(r + 2, c + 2)) * 3 + P(r + 1, c + 2) * 10 - ((P(r, c) + P(r + 2, c)) * 3 + P(r + 1, c) * 10);
+        dy = ((P(r + 2, c) - P(r, c)) + (P(r + 2, c + 2) - P(r, c + 2))) * 3 + (P(r + 2, c + 1) - P(r, c + 1)) * 10;
+      }
+      dxr[r][c] = dx; dyr[r][c] = dy;
+      int v = sD[r * SD_PITCH + c];
+      if ((int)(short)(v & 0xFFFF) != dx || (v >> 16) != dy) bad++;
+    }
+    long A11 = 0, A12 = 0, A22 = 0, g11 = 0, g12 = 0, g22 = 0;
+    for (int l = 0; l < 32; ++l) {
+      short Iv[3], Ix[3], Iy[3]; int s11, s12, s22;
+      template_rows(l, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ix, Iy, s11, s12, s22);
+      g11 += s11; g12 += s12; g22 += s22;
+      for (int k = 0; k < 3; ++k) {
+        int p = 3 * l + k;
+        if (p >= WIN * WIN) { if (Iv[k] || Ix[k] || Iy[k]) bad++; continue; }
+        int y = p / WIN, x = p %% WIN;
+        int iv = (P(y + 1, x + 1) * iw00 + P(y + 1, x + 2) * iw01 + P(y + 2, x + 1) * iw10 + P(y + 2, x + 2) * iw11 + 256) >> 9;
+        int ixv = (dxr[y][x] * iw00 + dxr[y][x + 1] * iw01 + dxr[y + 1][x] * iw10 + dxr[y + 1][x + 1] * iw11 + 8192) >> 14;
+        int iyv = (dyr[y][x] * iw00 + dyr[y][x + 1] * iw01 + dyr[y + 1][x] * iw10 + dyr[y + 1][x + 1] * iw11 + 8192) >> 14;
+        if (Iv[k] != (short)iv || Ix[k] != (short)ixv || Iy[k] != (short)iyv) bad++;
+        A11 += (long)ixv * ixv; A12 += (long)ixv * iyv; A22 += (long)iyv * iyv;
+      }
+    }
+    if (A11 != g11 || A12 != g12 || A22 != g22) bad++;
+  }
+  printf("%%ld bad, %%ld interior, %%ld border\n", bad, n_int, n_brd);
+  return (bad || n_int < 1000 || n_brd < 1000) ? 1 : 0;
+}''' % ROOT)
+    exe = tmp_path / "k"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
