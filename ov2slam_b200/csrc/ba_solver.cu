@@ -910,7 +910,9 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     // Per iteration: memset, (Jacobian evaluation if x is new), Schur, reduced solve, back-substitution,
     // candidate cost, ONE readback of the scalars; the controller below replays Ceres' decisions.
     const size_t accum_bytes = sizeof(double) * ((size_t)SC_COUNT + (size_t)D.ncopy * (size_t)D.copy_stride);
-    double h[SC_COUNT];
+    // pinned readback target: a pageable one makes every per-iteration D2H a staged, blocking copy
+    if (!ctx->ba_hscal) OV2_CUDA(ctx, cudaHostAlloc((void**)&ctx->ba_hscal, sizeof(double) * 2 * SC_COUNT, cudaHostAllocDefault));
+    double* h = ctx->ba_hscal;
     double x_cost = 0.0, minimum_cost = DBL_MAX, xnorm = -1.0, gmax = DBL_MAX;
     double radius = 1e4, decrease_factor = 2.0;
     bool step_successful = true, x_is_new = true, cost_known = false;
@@ -1161,7 +1163,8 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
     if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_robust, opts->function_tolerance, &s1, sh)) != OV2_OK)
         return st;
     // outlier scan on the values the LAST Evaluate() left behind (optimizer.cpp:500-530)
-    double h[SC_COUNT];
+    if (!ctx->ba_hscal) OV2_CUDA(ctx, cudaHostAlloc((void**)&ctx->ba_hscal, sizeof(double) * 2 * SC_COUNT, cudaHostAllocDefault));
+    double* h = ctx->ba_hscal + SC_COUNT;   // second half: the LM controller uses the first
     OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, 3 * sizeof(double), s));
     const int deact = opts->apply_l2_after_robust ? 1 : 0;
     OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 1, deact));

@@ -30,8 +30,7 @@ struct DescArgs {
 };
 
 __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
-    __shared__ float sraw[WARPS][32 * 33];   // 32x32 raw window as float (+1 pad: conflict-free rows)
-    __shared__ float srow[WARPS][32 * 27];   // row-filtered: 32 rows x 26 cols (+1 pad)
+    __shared__ float sraw[WARPS][32 * 33];   // 32x32 raw window as float (+1 pad: conflict-free rows); row-filtered IN PLACE
     __shared__ uint8_t ssm[WARPS][26 * 28];  // 26 x 26 smoothed (+2 pad)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * WARPS + warp;
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
     const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
     const uint8_t* img = A.img + A.fstride * frame + (size_t)(cy - 16) * A.pitch + (cx - 16);
     float* raw = sraw[warp];
-    float* row = srow[warp];
+    float* row = raw;   // the row filter overwrites column c only after its taps c..c+6 sit in registers
     uint8_t* sm = ssm[warp];
     // raw window rows cy-16..cy+15, cols cx-16..cx+15 (lane = column): 32 coalesced 32-byte reads
 #pragma unroll 8
@@ -70,7 +69,7 @@ __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
             acc = __fmaf_rn(x4, k2, acc);
             acc = __fmaf_rn(x5, k1, acc);
             acc = __fmaf_rn(x6, k0, acc);
-            row[lane * 27 + c] = acc;
+            row[lane * 33 + c] = acc;
             x0 = x1; x1 = x2; x2 = x3; x3 = x4; x4 = x5; x5 = x6;
         }
     }
@@ -79,10 +78,10 @@ __global__ void __launch_bounds__(WARPS * 32) describe_kernel(DescArgs A) {
     // (centre q+3), symmetric pairs + FMA as OpenCV's float column filter, rint -> u8
     if (lane < 26) {
         const float* p = row + lane;
-        float y0 = p[0], y1 = p[27], y2 = p[2 * 27], y3 = p[3 * 27], y4 = p[4 * 27], y5 = p[5 * 27];
+        float y0 = p[0], y1 = p[33], y2 = p[2 * 33], y3 = p[3 * 33], y4 = p[4 * 33], y5 = p[5 * 33];
 #pragma unroll
         for (int q = 0; q < 26; ++q) {
-            const float y6 = p[(q + 6) * 27];
+            const float y6 = p[(q + 6) * 33];
             float acc = y3 * k3;
             acc = __fmaf_rn(y2 + y4, k2, acc);
             acc = __fmaf_rn(y1 + y5, k1, acc);

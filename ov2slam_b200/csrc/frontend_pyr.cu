@@ -9,9 +9,9 @@
 
 namespace {
 
-constexpr int TX = 32, TY = 8;          // threads
+constexpr int TX = 32, TY = 4;          // threads: each computes 4 pixels of TWO output rows
 constexpr int OUT_W = TX * 4;           // 128 output pixels per tile row
-constexpr int OUT_H = TY;               // 8 output rows
+constexpr int OUT_H = 2 * TY;           // 8 output rows
 constexpr int IN_ROWS = 2 * OUT_H + 3;  // 19
 constexpr int IN_WORDS = 66;            // 264 bytes: input cols [2*x0-4, 2*x0+260)
 
@@ -68,26 +68,30 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, lon
     }
     __syncthreads();
 
-    const int oy = oy0 + threadIdx.y;
+    // two output rows per thread (oy, oy+1) share 3 of their 5 input rows: 7 horizontal passes (dp4a)
+    // instead of 10, then the vertical [1 4 6 4 1] on the running sums
+    const int oy = oy0 + 2 * threadIdx.y;
     const int ox = ox0 + 4 * threadIdx.x;
     if (oy >= dh || ox >= dw) return;
-    // horizontal pass per input row (dp4a), vertical [1 4 6 4 1] on the four running sums
-    const int r0 = 2 * threadIdx.y;
-    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    const int r0 = 4 * threadIdx.y;
+    int h[7][4];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        int h0, h1, h2, h3;
-        hrow4(&tile[r0 + r][2 * threadIdx.x], h0, h1, h2, h3);
-        const int kw = (r == 0 || r == 4) ? 1 : ((r == 2) ? 6 : 4);
-        v0 += kw * h0; v1 += kw * h1; v2 += kw * h2; v3 += kw * h3;
-    }
-    const uint32_t packed = (uint32_t)((v0 + 128) >> 8) | ((uint32_t)((v1 + 128) >> 8) << 8) |
-                            ((uint32_t)((v2 + 128) >> 8) << 16) | ((uint32_t)((v3 + 128) >> 8) << 24);
-    uint8_t* drow = dst + (size_t)oy * dpitch + ox;
-    if (ox + 3 < dw && ((reinterpret_cast<uintptr_t>(drow)) & 3) == 0) {
-        *reinterpret_cast<uint32_t*>(drow) = packed;
-    } else {
-        for (int j = 0; j < 4 && ox + j < dw; ++j) drow[j] = (uint8_t)(packed >> (8 * j));
+    for (int r = 0; r < 7; ++r) hrow4(&tile[r0 + r][2 * threadIdx.x], h[r][0], h[r][1], h[r][2], h[r][3]);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        if (oy + o >= dh) break;
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            v[j] = h[2 * o][j] + 4 * h[2 * o + 1][j] + 6 * h[2 * o + 2][j] + 4 * h[2 * o + 3][j] + h[2 * o + 4][j];
+        const uint32_t packed = (uint32_t)((v[0] + 128) >> 8) | ((uint32_t)((v[1] + 128) >> 8) << 8) |
+                                ((uint32_t)((v[2] + 128) >> 8) << 16) | ((uint32_t)((v[3] + 128) >> 8) << 24);
+        uint8_t* drow = dst + (size_t)(oy + o) * dpitch + ox;
+        if (ox + 3 < dw && ((reinterpret_cast<uintptr_t>(drow)) & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(drow) = packed;
+        } else {
+            for (int j = 0; j < 4 && ox + j < dw; ++j) drow[j] = (uint8_t)(packed >> (8 * j));
+        }
     }
 }
 
