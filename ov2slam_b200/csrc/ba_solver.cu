@@ -371,6 +371,20 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) ba_schur_kernel(BaDev D, dou
     }
 }
 
+// ------------------------------------------------------------------ fold of the privatised copies
+// The Schur kernel accumulates into ncopy private copies of [rhs | F'r | column norms | S] to spread the
+// fp64 atomics; this grid-wide pass sums them into copy 0.  (Inside the single-CTA reduced solve the same
+// fold cost ~30 % of that kernel's time: one SM cannot keep enough L2 loads in flight.)
+__global__ void __launch_bounds__(256) ba_fold_kernel(BaDev D) {
+    const int blk = 3 * D.n + D.n * D.n;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= blk) return;
+    double acc = D.rhs[e];
+#pragma unroll 8
+    for (int k = 1; k < D.ncopy; ++k) acc += D.rhs[e + (long long)k * D.copy_stride];
+    D.rhs[e] = acc;
+}
+
 // ------------------------------------------------------------------ reduced camera system (one CTA)
 // FP64 tensor-core tile product (DMMA): D(8x8) = A(8x4) B(4x8) + C.  Fragment layout (PTX ISA,
 // mma.m8n8k4 .f64): lane = 4 g + t; A: (row g, col t); B: (row t, col g); C/D: (row g, cols 2t, 2t+1).
@@ -392,17 +406,6 @@ __global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kerne
     __shared__ double s_w[MAX_N];
     double* w = s_w;   // rhs -> solution vector (shared: the triangular solves are latency chains)
     if (tid == 0) s_fail = 0;
-    // fold the privatised accumulation copies into copy 0
-    if (D.ncopy > 1) {
-        const int blk = 3 * n + n * n;
-        for (int e = tid; e < blk; e += nt) {
-            double acc = D.rhs[e];
-#pragma unroll 8
-            for (int k = 1; k < D.ncopy; ++k) acc += D.rhs[e + (long long)k * D.copy_stride];   // independent loads in flight
-            D.rhs[e] = acc;
-        }
-        __syncthreads();
-    }
     // Jacobi scaling (iteration 0), LM damping, rhs = F'r - (Schur part already accumulated)
     for (int i = tid; i < n; i += nt) {
         const double cn = D.cn_cam[i];
@@ -935,6 +938,8 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             if (sh->fn(sh->user, D.scal, (size_t)SC_COUNT + 3 * (size_t)n + (size_t)n * n, (void*)st) != 0)
                 return ov2_fail(ctx, OV2_ERR_CUDA, "allreduce callback failed");
         }
+        if (D.ncopy > 1 && n > 0)
+            OV2_LAUNCH(ctx, "ba_fold_kernel", ba_fold_kernel<<<div_up(3 * n + n * n, 256), 256, 0, st>>>(D));
         if (solve_mode == 2)
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<2><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
         else if (solve_mode == 3)
