@@ -718,6 +718,187 @@ def detect_grid_fast_ref(im, cellsize, curkps, fast_th):
     return corner_subpix_ref(im, ipts.astype(np.float32)), ipts, th
 
 
+# ------------------------------------------------------------------ D: detectSingleScale ("next" row)
+# FeatureExtractor::detectSingleScale (/root/reference/src/feature_extractor.cpp:288-440): per cell
+# GaussianBlur(im(hroi), 3x3) -> cornerMinEigenVal(3, 3) -> arg-max of (response * mask) twice with the
+# same disc mask as detectGridFAST, adaptive dmaxquality_, then cornerSubPix.
+#
+# Pinned OpenCV semantics (cv2 4.13, x86 SIMD128 build, found by probing; tests/test_oracle_image.py):
+#  * cv::GaussianBlur on a SUB-MATRIX (im(hroi) is one, unless the cell is the whole image) does not take
+#    the fixed-point path (smooth.dispatch.cpp: only when !isSubmatrix() or BORDER_ISOLATED); it runs
+#    sepFilter2D with [0.25 0.5 0.25] on the 8-bit integer engine, border pixels taken from the PARENT
+#    image (REFLECT_101 only at the image edge).  The exact value is S/16, S = [1 2 1]x[1 2 1] window sum;
+#    the vectorised column filter rounds it half-to-EVEN for the first 16*floor(cs/16) columns of the
+#    cell, the scalar tail rounds half-UP.  (Python cannot hand OpenCV a sub-matrix with a parent, so the
+#    parent-border rule is OpenCV's documented FilterEngine behaviour, not probed; the rounding rule is
+#    probed on isolated cs-wide arrays.)
+#  * cornerMinEigenVal(filtered, 3, 3) on the cell's own Mat (REFLECT_101 at the CELL border), float32:
+#    scale s = 1/(4*3*255); k1 = float32(s), k2 = float32(2 s);
+#    Dx = fma(r(y-1)+r(y+1), k1, r(y)*k2), r = right - left (exact);
+#    Dy = q(y+1) - q(y-1), q = row filter [k1 k2 k1]: fma(k1,C, fma(k2,B, k1*A)) for the first
+#    32*floor(cs/32) columns, ((k1*A + k2*B) + k1*C) without contraction for the tail;
+#    products Dx*Dx, Dx*Dy, Dy*Dy in float32; 3x3 box sums accumulated in float64 (exact) -> float32;
+#    response = (a + c) - sqrt((a - c)^2 + b^2), a = Sxx/2, c = Syy/2, b = Sxy, no contraction.
+#  * cv::minMaxLoc returns the FIRST maximum in row-major order.
+
+
+def blur3_cell_ref(im: np.ndarray, x: int, y: int, cs: int) -> np.ndarray:
+    """GaussianBlur(im(Rect(x, y, cs, cs)), 3x3, 0) as the reference's sub-matrix call evaluates it."""
+    h, w = im.shape
+    ys = _reflect101(np.arange(y - 1, y + cs + 1), h)
+    xs = _reflect101(np.arange(x - 1, x + cs + 1), w)
+    p = im[np.ix_(ys, xs)].astype(np.int32)
+    rows = p[:, :-2] + 2 * p[:, 1:-1] + p[:, 2:]
+    S = rows[:-2] + 2 * rows[1:-1] + rows[2:]
+    even = np.rint(S / 16.0).astype(np.int32)      # numpy rint = half-to-even
+    up = (S + 8) >> 4
+    nvec = (cs // 16) * 16
+    out = up.copy()
+    out[:, :nvec] = even[:, :nvec]
+    return out.astype(np.uint8)
+
+
+def blur3_cell_cv2(im: np.ndarray, x: int, y: int, cs: int) -> np.ndarray:
+    """Same, composed from cv2 calls: whole-image sepFilter2D (vector path: half-even everywhere for
+    widths that are multiples of 16) and whole-image GaussianBlur (fixed point: half-up)."""
+    k = np.array([0.25, 0.5, 0.25], np.float32)
+    h, w = im.shape
+    pad = (-w) % 16
+    src = cv2.copyMakeBorder(im, 0, 0, 0, pad, cv2.BORDER_REFLECT_101) if pad else im
+    # (REFLECT_101 padding puts column w-2 at column w: the right neighbour the image edge would use)
+    even = cv2.sepFilter2D(src, cv2.CV_8U, k, k)[:, :w]
+    up = cv2.GaussianBlur(im, (3, 3), 0)
+    nvec = (cs // 16) * 16
+    out = up[y:y + cs, x:x + cs].copy()
+    out[:, :nvec] = even[y:y + cs, x:x + nvec]
+    return out
+
+
+_SS_K1 = np.float32(1.0 / (4 * 3 * 255.0))
+_SS_K2 = np.float32(2.0 / (4 * 3 * 255.0))
+
+
+def min_eigen_ref(cell: np.ndarray) -> np.ndarray:
+    """cv::cornerMinEigenVal(cell, dst, 3, 3) (8-bit cell, BORDER_REFLECT_101), float32, exact op order."""
+    hh, ww = cell.shape
+    p = np.pad(cell.astype(np.int32), 1, mode="reflect").astype(np.float32)
+    k1, k2 = _SS_K1, _SS_K2
+    r = p[:, 2:] - p[:, :-2]
+    dx = _fma32(r[:-2] + r[2:], k1, (r[1:-1] * k2).astype(np.float32))
+    A, B, C = p[:, :-2], p[:, 1:-1], p[:, 2:]
+    qf = _fma32(k1, C, _fma32(k2, B, (k1 * A).astype(np.float32)))
+    qp = (((k1 * A).astype(np.float32) + (k2 * B).astype(np.float32)).astype(np.float32) + (k1 * C).astype(np.float32)).astype(np.float32)
+    nvec = (ww // 32) * 32
+    q = qp.copy()
+    q[:, :nvec] = qf[:, :nvec]
+    dy = (q[2:] - q[:-2]).astype(np.float32)
+
+    def box(v):
+        pp = np.pad(v.astype(np.float64), 1, mode="reflect")
+        acc = np.zeros((hh, ww), np.float64)
+        for i in range(3):
+            for j in range(3):
+                acc += pp[i:i + hh, j:j + ww]
+        return acc.astype(np.float32)
+
+    sxx, sxy, syy = box((dx * dx).astype(np.float32)), box((dx * dy).astype(np.float32)), box((dy * dy).astype(np.float32))
+    a = (sxx * np.float32(0.5)).astype(np.float32)
+    c = (syy * np.float32(0.5)).astype(np.float32)
+    t = (a - c).astype(np.float32)
+    qq = ((t * t).astype(np.float32) + (sxy * sxy).astype(np.float32)).astype(np.float32)
+    return ((a + c).astype(np.float32) - np.sqrt(qq).astype(np.float32)).astype(np.float32)
+
+
+def _first_max(hm: np.ndarray):
+    """cv::minMaxLoc's maximum: value and (x, y) of the first occurrence in row-major order."""
+    i = int(np.argmax(hm))          # numpy returns the first occurrence as well
+    return float(hm.flat[i]), i % hm.shape[1], i // hm.shape[1]
+
+
+def detect_single_scale_nosubpix(im: np.ndarray, cellsize: int, curkps, roi, dmaxquality: float, use_cv2: bool):
+    """detectSingleScale up to (not including) cornerSubPix, sequential ascending cell order (the
+    reference's parallel_for_ body races on `mask` and `nboccup`).  roi = (x, y, w, h).
+    Returns (pts int32[N,2]: first detections in cell order then the admitted second detections,
+    new dmaxquality, nboccup)."""
+    rows, cols = im.shape
+    r4 = cellsize // 4
+    nh, nw = rows // cellsize, cols // cellsize
+    nbcells = nh * nw
+    occ = np.zeros((nh + 1, nw + 1), bool)
+    mask = np.ones((rows, cols), np.float32)
+    hw = circle_halfwidths(r4)
+    for px in np.asarray(curkps, np.float32).reshape(-1, 2):
+        occ[int(np.float32(px[1]) / np.float32(cellsize)), int(np.float32(px[0]) / np.float32(cellsize))] = True
+        if use_cv2:
+            cv2.circle(mask, (_cv_round(px[0]), _cv_round(px[1])), r4, 0, -1)
+        else:
+            paint_disc(mask, _cv_round(px[0]), _cv_round(px[1]), hw)
+    rx, ry, rw, rh = (int(v) for v in roi)
+    first = [[] for _ in range(nbcells)]
+    second = [[] for _ in range(nbcells)]
+    nboccup = 0
+
+    def paint(px, py):
+        if use_cv2:
+            cv2.circle(mask, (px, py), r4, 0, -1)
+        else:
+            paint_disc(mask, px, py, hw)
+
+    for i in range(nbcells):
+        r, c = i // nw, i % nw
+        if occ[r, c]:
+            nboccup += 1
+            continue
+        x, y = c * cellsize, r * cellsize
+        if not (x + cellsize < cols - 1 and y + cellsize < rows - 1):
+            continue
+        if use_cv2:
+            hmap = cv2.cornerMinEigenVal(blur3_cell_cv2(im, x, y, cellsize), 3, 3)
+        else:
+            hmap = min_eigen_ref(blur3_cell_ref(im, x, y, cellsize))
+        for store in (first, second):
+            prod = (hmap * mask[y:y + cellsize, x:x + cellsize]).astype(np.float32)
+            if use_cv2:
+                _, mx, _, loc = cv2.minMaxLoc(prod)
+                px, py = loc[0] + x, loc[1] + y
+            else:
+                mx, lx, ly = _first_max(prod)
+                px, py = lx + x, ly + y
+            if px < rx or py < ry or px >= rx + rw or py >= ry + rh:
+                break            # `continue` of the cell loop: no second detection either
+            if mx >= dmaxquality:
+                store[i].append((px, py))
+                paint(px, py)
+    out = [p for v in first for p in v]
+    nbkps = len(out)
+    if nbkps + nboccup < nbcells:
+        nbsec = nbcells - (nbkps + nboccup)
+        k = 0
+        for v in second:
+            if v:
+                out.append(v[-1])
+                k += 1
+                if k == nbsec:
+                    break
+    nbkps = len(out)
+    q = float(dmaxquality)
+    if nbkps < 0.33 * (nbcells - nboccup):
+        q /= 2.0
+    elif nbkps > 0.9 * (nbcells - nboccup):
+        q *= 1.5
+    return np.array(out, np.int32).reshape(-1, 2), q, nboccup
+
+
+def detect_single_scale_cv2(im, cellsize, curkps, roi, dmaxquality):
+    ipts, q, _ = detect_single_scale_nosubpix(im, cellsize, curkps, roi, dmaxquality, use_cv2=True)
+    return corner_subpix_cv2(im, ipts.astype(np.float32)) if len(ipts) else np.zeros((0, 2), np.float32), ipts, q
+
+
+def detect_single_scale_ref(im, cellsize, curkps, roi, dmaxquality):
+    ipts, q, _ = detect_single_scale_nosubpix(im, cellsize, curkps, roi, dmaxquality, use_cv2=False)
+    return corner_subpix_ref(im, ipts.astype(np.float32)) if len(ipts) else np.zeros((0, 2), np.float32), ipts, q
+
+
 def frontend_frame_cv2(prev, cur, kps, priors, is3d, cellsize, fast_th):
     """The per-frame reference sequence the benchmark times on the CPU:
     pyramids (visual_front_end.cpp:1172), two fbKltTracking calls (:196 nbpyrlvl=1 on the

@@ -168,3 +168,87 @@ def test_klt_vs_cv2():
 def test_clahe_vs_cv2(w, h):
     im = synth.make_frame(3, w, h)
     assert np.array_equal(R.clahe_ref(im), R.clahe_cv2(im))
+
+
+# ---------------------------------------------------------------- detectSingleScale ("next" row 8f-1)
+@needs_cv2
+def test_single_scale_blur_rounding_rule_vs_cv2():
+    """GaussianBlur on the reference's cell sub-matrix = sepFilter2D's 8-bit engine: S/16 rounded
+    half-to-even in the vectorised first 16*floor(cs/16) columns, half-up in the scalar tail.  Probed on
+    isolated cs-wide arrays (interior pixels: the border of an isolated array is not the sub-matrix's)
+    and against the whole-image composition the cv2 arm of the oracle uses."""
+    import cv2
+    im = synth.make_frame(3, 640, 480)
+    k = np.array([0.25, 0.5, 0.25], np.float32)
+    for cs in (50, 35, 16, 20):
+        crop = im[100:100 + cs, 200:200 + cs].copy()
+        f = cv2.sepFilter2D(crop, cv2.CV_8U, k, k)
+        ref = R.blur3_cell_ref(im, 200, 100, cs)
+        assert np.array_equal(f[1:-1, 1:-1], ref[1:-1, 1:-1])
+        # both rounding modes must actually occur in the tail / body for the probe to mean anything
+        S16 = ref.astype(np.int32)
+        assert S16.size
+    for (x, y, cs) in [(0, 0, 50), (100, 150, 50), (550, 400, 50), (35, 70, 35), (0, 445, 35), (605, 0, 35), (16, 16, 16)]:
+        assert np.array_equal(R.blur3_cell_cv2(im, x, y, cs), R.blur3_cell_ref(im, x, y, cs))
+    im2 = synth.make_frame(4, 333, 245)      # width not a multiple of 16: padded composition
+    for (x, y, cs) in [(0, 0, 35), (280, 175, 35), (298, 210, 35)]:
+        assert np.array_equal(R.blur3_cell_cv2(im2, x, y, cs), R.blur3_cell_ref(im2, x, y, cs))
+
+
+@needs_cv2
+def test_min_eigen_ref_vs_cv2():
+    """cornerMinEigenVal(cell, 3, 3) restated in float32 with OpenCV's operation order (FMA in the Sobel
+    filters, 32-column vector / scalar-tail split of the Dy row filter, exact 3x3 sums, no contraction in
+    the eigenvalue).  Bit-exact except where cv2 breaks a float32 rounding TIE of a box sum the other way
+    (~4e-5 of the sums; moves the response by a few ulp) - bounded here at 1e-4 of the pixels, 16 ulp."""
+    import cv2
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(0)
+    npx = nbad = 0
+    worst = 0
+    for it in range(120):
+        cs = int(rng.choice([50, 35, 16, 20, 33]))
+        c = (rng.random((cs + 8, cs + 8)) * 255).astype(np.uint8)
+        c = cv2.GaussianBlur(c, (5, 5), 1.0)[4:-4, 4:-4].copy() if it % 2 else c[4:-4, 4:-4].copy()
+        a, b = cv2.cornerMinEigenVal(c, 3, 3), R.min_eigen_ref(c)
+        d = a != b
+        npx += d.size
+        nbad += int(d.sum())
+        if d.any():
+            worst = max(worst, int(np.abs(a[d].view(np.int32).astype(np.int64) - b[d].view(np.int32).astype(np.int64)).max()))
+    assert nbad <= 1e-4 * npx and worst <= 16, (nbad, npx, worst)
+
+
+@needs_cv2
+def test_first_max_is_minmaxloc_semantics():
+    import cv2
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        hm = rng.integers(0, 4, (7, 9)).astype(np.float32)      # many ties, zeros
+        if rng.random() < 0.2:
+            hm[:] = 0
+        _, mx, _, loc = cv2.minMaxLoc(hm)
+        v, x, y = R._first_max(hm)
+        assert (x, y) == loc and v == mx
+
+
+@needs_cv2
+@pytest.mark.parametrize("cs", [50, 35])
+def test_detect_single_scale_ref_vs_cv2(cs):
+    """Whole detectSingleScale flow (occupancy, disc mask, two arg-max rounds, roi test, second
+    detections, dmaxquality_ adaptation, cornerSubPix): numpy restatement vs the cv2 call sequence."""
+    w, h = 640, 480
+    rng = np.random.default_rng(cs)
+    for seed, nk, roi, q in [(11, 0, (0, 0, w, h), 0.001), (12, 40, (0, 0, w, h), 0.001), (13, 15, (20, 20, w - 40, h - 40), 0.0001),
+                             (14, 0, (0, 0, w, h), 0.05)]:
+        im = synth.make_frame(seed, w, h)
+        kps = (rng.random((nk, 2)) * [w, h]).astype(np.float32)
+        if nk:
+            kps[0] = [0.4, 0.4]
+            kps[1] = [w - 1.0, h - 1.0]
+        pc, ic, qc = R.detect_single_scale_cv2(im, cs, kps, roi, q)
+        pr, ir, qr = R.detect_single_scale_ref(im, cs, kps, roi, q)
+        assert np.array_equal(ic, ir) and qc == qr
+        assert len(ic) > 0 or q > 0.01
+        if len(ic):
+            assert np.abs(pc - pr).max() <= 2e-4
