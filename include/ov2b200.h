@@ -145,6 +145,20 @@ OV2_API ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first, in
                          int32_t* fast_th_inout, int max_per_frame,
                          float* out_pts, int32_t* out_counts, int32_t* out_pts_int, int do_subpix);
 
+/* ------------------------------------------------------------------ D + S: single-scale detector + cornerSubPix
+ * ("next" row; the detector of the accurate/ and average/ configurations)
+ * Replaces FeatureExtractor::detectSingleScale(im, ncellsize, vcurkps, roi)
+ * (/root/reference/src/feature_extractor.cpp:288-440; include/feature_extractor.hpp:38-39): per cell
+ * cv::GaussianBlur(3x3) + cv::cornerMinEigenVal(3, 3), first maximum of response * mask twice with the
+ * disc mask, second detections admitted while cells stayed empty (:400-412), the adaptive dmaxquality_
+ * update (:418-423) and cv::cornerSubPix (:424-436); sequential ascending cell order as the defined
+ * semantics.  Arguments as ov2_grid_fast; roi_xywh = {x, y, width, height} on the HOST (NULL = whole
+ * image); quality_inout[k] is the per-stream dmaxquality_ state (double, in/out); cellsize in [8, 64]. */
+OV2_API ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int cellsize,
+                         const int32_t* curkp_offsets, const float* curkps, const int32_t* roi_xywh,
+                         double* quality_inout, int max_per_frame,
+                         float* out_pts, int32_t* out_counts, int32_t* out_pts_int, int do_subpix);
+
 /* Test hook: stage F1 alone (per-cell FAST-9/16 + NMS candidates of one frame, pre-filtered by the
  * mask byte rule), for cell-by-cell parity against cv::FastFeatureDetector. */
 OV2_API ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int frame, int cellsize, int fast_th,

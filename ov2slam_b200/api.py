@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.ov2_clahe.argtypes = [vp, vp, vp, i32, i32, sz, sz, i32, C.c_double, i32, i32]
     lib.ov2_fb_klt.argtypes = [vp, vp, vp, C.POINTER(KltParams), i32, vp, i32, i32, vp, i32, vp, vp, vp]
     lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
+    lib.ov2_detect_single_scale.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
@@ -309,6 +310,32 @@ class FeatureExtractor:
                                                   _ptr(curkp_offsets), _ptr(curkps), _ptr(fast_th_inout),
                                                   int(max_per_frame), _ptr(out_pts), _ptr(out_counts),
                                                   _ptr(out_pts_int), 1 if do_subpix else 0))
+
+    def detect_single_scale(self, pyr: Pyramid, ncellsize: int, first: int, count: int, quality_inout,
+                            out_pts, out_counts, curkp_offsets=None, curkps=None, roi=None, out_pts_int=None,
+                            max_per_frame=None, do_subpix=True):
+        """detectSingleScale (feature_extractor.cpp:288-440) for frames [first, first+count); quality_inout is
+        the float64 dmaxquality_ state per frame stream; roi = (x, y, w, h) or None (whole image)."""
+        if max_per_frame is None:
+            max_per_frame = (pyr.h // ncellsize) * (pyr.w // ncellsize)
+        roi_arr = None if roi is None else np.ascontiguousarray(roi, np.int32)
+        self.ctx.check(self.ctx.lib.ov2_detect_single_scale(self.ctx.h, pyr.h_, first, count, ncellsize,
+                                                            _ptr(curkp_offsets), _ptr(curkps), _ptr(roi_arr),
+                                                            _ptr(quality_inout), int(max_per_frame), _ptr(out_pts),
+                                                            _ptr(out_counts), _ptr(out_pts_int), 1 if do_subpix else 0))
+
+    def detect_single_scale_frame(self, pyr: Pyramid, frame: int, ncellsize: int, vcurkps, roi=None):
+        """Single-frame convenience with the reference's signature shape; carries dmaxquality_ like the class."""
+        ncell = (pyr.h // ncellsize) * (pyr.w // ncellsize)
+        cur = np.ascontiguousarray(vcurkps, np.float32).reshape(-1, 2)
+        off = np.array([0, len(cur)], np.int32)
+        q = np.array([self.dmaxquality_], np.float64)
+        pts = np.empty((ncell, 2), np.float32)
+        ipts = np.empty((ncell, 2), np.int32)
+        cnt = np.zeros(1, np.int32)
+        self.detect_single_scale(pyr, ncellsize, frame, 1, q, pts, cnt, off, cur if len(cur) else None, roi, ipts)
+        self.dmaxquality_ = float(q[0])
+        return pts[:cnt[0]].copy(), ipts[:cnt[0]].copy()
 
     def detect_grid_fast_frame(self, pyr: Pyramid, frame: int, ncellsize: int, vcurkps):
         """Single-frame convenience with the reference's signature shape:

@@ -27,6 +27,7 @@ SOURCES = {
     "frontend_fast.cu": ["-fmad=false"],
     "frontend_desc.cu": ["-fmad=false"],
     "frontend_clahe.cu": ["-fmad=false"],
+    "frontend_sscale.cu": ["-fmad=false"],
     "frontend_step.cu": [],
     "ba_solver.cu": [],
 }

@@ -744,3 +744,23 @@ extern "C" ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int
     if ((st = launch_fast_cells(ctx, pyr, FA, 1)) != OV2_OK) return st;
     return ov2_end(ctx);
 }
+
+// Internal (not part of the C ABI): cornerSubPix stage S on integer points produced by another detector
+// (frontend_sscale.cu).  Same launch as inside ov2_grid_fast; slots holding (-1, -1) stay empty.
+ov2_status ov2_subpix_launch(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int max_per_frame, const int2* d_int,
+                             float2* d_out, int do_subpix) {
+    SubpixArgs PA;
+    PA.img = pyr->l0; PA.w = pyr->w[0]; PA.h = pyr->h[0]; PA.pitch = (int)pyr->l0_pitch; PA.fstride = (long long)pyr->l0_fstride;
+    PA.first = first; PA.max_per_frame = max_per_frame; PA.n = count * max_per_frame;
+    PA.in_int = d_int; PA.out = d_out; PA.do_subpix = do_subpix;
+    for (int i = 0; i < 7; ++i) {
+        float y = (float)(i - 3) / 3;
+        float vy = expf(-y * y);
+        for (int j = 0; j < 7; ++j) {
+            float x = (float)(j - 3) / 3;
+            PA.mask[i * 7 + j] = (float)(vy * expf(-x * x));
+        }
+    }
+    OV2_LAUNCH(ctx, "subpix_kernel", subpix_kernel<<<div_up(PA.n, 4), 128, 0, ctx->stream>>>(PA));
+    return OV2_OK;
+}

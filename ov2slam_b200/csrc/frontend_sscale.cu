@@ -1,0 +1,313 @@
+// D ("next" row): FeatureExtractor::detectSingleScale
+// (/root/reference/src/feature_extractor.cpp:288-440): per cell GaussianBlur 3x3 -> cornerMinEigenVal(3, 3)
+// -> arg-max of (response * mask) twice with the disc mask of detectGridFAST, second detections fill the
+// cells that stayed empty, adaptive dmaxquality_ (:418-423), cornerSubPix (:424-436, stage S).
+//
+// OpenCV semantics implemented here are the ones oracle/image_ref.py pins against cv2 4.13
+// (blur3_cell_ref / min_eigen_ref / _first_max; tests/test_oracle_image.py):
+//   * the blur of a cell SUB-MATRIX takes its border pixels from the parent image and rounds S/16
+//     half-to-even in the first 16*floor(cs/16) columns, half-up in the rest;
+//   * Sobel / products / eigenvalue in float32 with OpenCV's operation order (every float operation below
+//     is an explicit __f*_rn intrinsic: nothing is contracted), 3x3 sums exact (double) then one rounding;
+//   * arg-max = first maximum in row-major order; the sequential cell order is the semantics (the
+//     reference's parallel_for_ body races on the mask).
+//
+// Two kernels: ss_response_kernel (one CTA per cell and frame, everything in shared memory, response map
+// to HBM: 4 B/pixel written once, read at most twice) and ss_sweep_kernel (one CTA per frame walks the
+// cells in order with the 1 bit/pixel mask in shared memory).
+#include "ov2_common.cuh"
+#include "sscale_math.cuh"
+
+ov2_status ov2_subpix_launch(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int max_per_frame, const int2* d_int,
+                             float2* d_out, int do_subpix);   // frontend_fast.cu
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SS_MAX_CELL = 64;
+constexpr int SS_MAX_RADIUS = SS_MAX_CELL / 4;
+
+struct RespArgs {
+    const uint8_t* img; int w, h, pitch; long long fstride;
+    int first, cs, nwc, nhc;
+    float* resp;            // [count][ncells][cs*cs]
+};
+
+__global__ void __launch_bounds__(256) ss_response_kernel(RespArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int cs = A.cs, cell = blockIdx.x, fr = blockIdx.y;
+    const int r = cell / A.nwc, c = cell - r * A.nwc;
+    const int x0 = c * cs, y0 = r * cs;
+    if (!(x0 + cs < A.w - 1 && y0 + cs < A.h - 1)) return;      // never searched (feature_extractor.cpp:346)
+    const int rw = cs + 2;
+    uint8_t* raw = smem;                                          // (cs+2)^2: cell + 1-px halo from the PARENT image
+    uint8_t* bl = raw + sscale::raw_bytes(cs);                    // cs^2 blurred
+    float* cxx = reinterpret_cast<float*>(bl + sscale::blur_bytes(cs));
+    float* cxy = cxx + cs * cs;
+    float* cyy = cxy + cs * cs;
+    const uint8_t* img = A.img + A.fstride * (A.first + fr);
+    for (int i = threadIdx.x; i < rw * rw; i += blockDim.x) {
+        const int yy = i / rw, xx = i - yy * rw;
+        const int gy = sscale::refl(y0 - 1 + yy, A.h), gx = sscale::refl(x0 - 1 + xx, A.w);
+        raw[i] = __ldg(img + (size_t)gy * A.pitch + gx);
+    }
+    __syncthreads();
+    sscale::phase_blur(threadIdx.x, blockDim.x, raw, bl, cs);
+    __syncthreads();
+    sscale::phase_cov(threadIdx.x, blockDim.x, bl, cxx, cxy, cyy, cs);
+    __syncthreads();
+    sscale::phase_response(threadIdx.x, blockDim.x, cxx, cxy, cyy,
+                           A.resp + ((size_t)fr * (A.nwc * A.nhc) + cell) * (size_t)(cs * cs), cs);
+}
+
+struct SweepArgs {
+    int w, h, cs, nwc, nhc, radius, max_per_frame;
+    int hw[SS_MAX_RADIUS + 1];       // cv::circle half-widths per |dy|
+    int roi_x, roi_y, roi_w, roi_h;
+    const int32_t* kp_off;           // [count+1] or NULL
+    const float2* kps;
+    const float* resp;               // [count][ncells][cs*cs]
+    double* quality;                 // in/out per frame
+    int2* out_int;                   // [count][max_per_frame]
+    int32_t* out_n;                  // [count]
+};
+
+__device__ __forceinline__ void paint_row(uint32_t* bm, int wpr, int W, int H, int y, int xa, int xb) {
+    if (y < 0 || y >= H) return;
+    xa = max(xa, 0);
+    xb = min(xb, W - 1);
+    if (xa > xb) return;
+    uint32_t* row = bm + (size_t)y * wpr;
+    const int wa = xa >> 5, wb = xb >> 5;
+    for (int wi = wa; wi <= wb; ++wi) {
+        uint32_t m = 0xffffffffu;
+        if (wi == wa) m &= 0xffffffffu << (xa & 31);
+        if (wi == wb) m &= 0xffffffffu >> (31 - (xb & 31));
+        atomicOr(row + wi, m);
+    }
+}
+
+constexpr int SWEEP_THREADS = 256;
+
+// first maximum (row-major) of resp * mask over one cell; every thread returns the same (value, index)
+__device__ __forceinline__ void cell_argmax(const float* __restrict__ resp, const uint32_t* bm, int wpr, int x0, int y0, int cs,
+                                            float* s_val, int* s_idx, float& best_v, int& best_i) {
+    const int tid = threadIdx.x, npx = cs * cs;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    int yy = tid / cs, xx = tid - yy * cs;
+    const int sy = SWEEP_THREADS / cs, sx = SWEEP_THREADS - sy * cs;
+    for (int i = tid; i < npx; i += SWEEP_THREADS) {
+        const int gx = x0 + xx, gy = y0 + yy;
+        const bool masked = (bm[(size_t)gy * wpr + (gx >> 5)] >> (gx & 31)) & 1u;
+        const float v = masked ? 0.0f : __ldg(resp + i);           // response * 0.0f compares equal to 0
+        if (v > bv) { bv = v; bi = i; }                           // strict: the earliest index of this thread wins
+        xx += sx; yy += sy;
+        if (xx >= cs) { xx -= cs; yy++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    bv = s_val[0]; bi = s_idx[0];
+#pragma unroll
+    for (int k = 1; k < SWEEP_THREADS / 32; ++k) {
+        const float ov = s_val[k];
+        const int oi = s_idx[k];
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();                                              // s_val / s_idx are reused by the next call
+    best_v = bv; best_i = bi;
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS) ss_sweep_kernel(SweepArgs A) {
+    extern __shared__ uint32_t sm[];
+    __shared__ float s_val[SWEEP_THREADS / 32];
+    __shared__ int s_idx[SWEEP_THREADS / 32];
+    const int tid = threadIdx.x, fr = blockIdx.x;
+    const int wpr = (A.w + 31) >> 5, ncells = A.nwc * A.nhc, cs = A.cs;
+    uint32_t* bm = sm;                                            // h * wpr words, bit = 1: mask is 0.0f there
+    int2* firstd = reinterpret_cast<int2*>(sm + (((size_t)A.h * wpr + 1) & ~(size_t)1));   // per cell, x < 0: none (8-byte aligned)
+    int2* secondd = firstd + ncells;
+    uint8_t* occ = reinterpret_cast<uint8_t*>(secondd + ncells);  // (nhc+1)*(nwc+1)
+    for (int i = tid; i < A.h * wpr; i += SWEEP_THREADS) bm[i] = 0;
+    for (int i = tid; i < ncells; i += SWEEP_THREADS) { firstd[i] = make_int2(-1, -1); secondd[i] = make_int2(-1, -1); }
+    const int nocc = (A.nhc + 1) * (A.nwc + 1);
+    for (int i = tid; i < nocc; i += SWEEP_THREADS) occ[i] = 0;
+    __syncthreads();
+    const int nrows = 2 * A.radius + 1;
+    // existing keypoints: occupancy + discs (feature_extractor.cpp:316-319); painting commutes (atomicOr)
+    if (A.kp_off) {
+        const int k0 = A.kp_off[fr], k1 = A.kp_off[fr + 1];
+        for (int k = k0 + tid; k < k1; k += SWEEP_THREADS) {
+            const float2 px = A.kps[k];
+            const int rr = (int)(px.y / (float)cs), cc = (int)(px.x / (float)cs);
+            if (rr >= 0 && rr <= A.nhc && cc >= 0 && cc <= A.nwc) occ[rr * (A.nwc + 1) + cc] = 1;
+            const int cx = __float2int_rn(px.x), cy = __float2int_rn(px.y);
+            for (int rI = 0; rI < nrows; ++rI) {
+                const int dy = rI - A.radius;
+                const int hwv = A.hw[dy < 0 ? -dy : dy];
+                paint_row(bm, wpr, A.w, A.h, cy + dy, cx - hwv, cx + hwv);
+            }
+        }
+    }
+    __syncthreads();
+    const double quality = A.quality[fr];
+    const float* resp = A.resp + (size_t)fr * ncells * (size_t)(cs * cs);
+    int nboccup = 0;
+    for (int cell = 0; cell < ncells; ++cell) {                   // uniform control flow: every branch below is block-uniform
+        const int r = cell / A.nwc, c = cell - r * A.nwc;
+        if (occ[r * (A.nwc + 1) + c]) { nboccup++; continue; }
+        const int x0 = c * cs, y0 = r * cs;
+        if (!(x0 + cs < A.w - 1 && y0 + cs < A.h - 1)) continue;
+        const float* rc = resp + (size_t)cell * (cs * cs);
+        for (int round = 0; round < 2; ++round) {
+            float mx; int idx;
+            cell_argmax(rc, bm, wpr, x0, y0, cs, s_val, s_idx, mx, idx);
+            const int ly = idx / cs, lx = idx - ly * cs;
+            const int px = x0 + lx, py = y0 + ly;
+            if (px < A.roi_x || py < A.roi_y || px >= A.roi_x + A.roi_w || py >= A.roi_y + A.roi_h) break;   // `continue` of the cell loop
+            if ((double)mx >= quality) {
+                if (tid == 0) (round == 0 ? firstd : secondd)[cell] = make_int2(px, py);
+                for (int rI = tid; rI < nrows; rI += SWEEP_THREADS) {
+                    const int dy = rI - A.radius;
+                    const int hwv = A.hw[dy < 0 ? -dy : dy];
+                    paint_row(bm, wpr, A.w, A.h, py + dy, px - hwv, px + hwv);
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    // assembly (feature_extractor.cpp:393-423): first detections in cell order, then second detections
+    // while cells stayed empty; quality adaptation; unused slots = (-1, -1)
+    int2* out = A.out_int + (size_t)fr * A.max_per_frame;
+    if (tid == 0) {
+        int n = 0;
+        for (int cell = 0; cell < ncells; ++cell)
+            if (firstd[cell].x >= 0 && n < A.max_per_frame) out[n++] = firstd[cell];
+        if (n + nboccup < ncells) {
+            const int nbsec = ncells - (n + nboccup);
+            int k = 0;
+            for (int cell = 0; cell < ncells && k < nbsec; ++cell)
+                if (secondd[cell].x >= 0) {
+                    if (n < A.max_per_frame) out[n++] = secondd[cell];
+                    k++;
+                }
+        }
+        double q = quality;
+        if ((double)n < 0.33 * (double)(ncells - nboccup)) q /= 2.0;
+        else if ((double)n > 0.9 * (double)(ncells - nboccup)) q *= 1.5;
+        A.quality[fr] = q;
+        A.out_n[fr] = n;
+        s_idx[0] = n;
+    }
+    __syncthreads();
+    for (int i = s_idx[0] + tid; i < A.max_per_frame; i += SWEEP_THREADS) out[i] = make_int2(-1, -1);
+}
+
+void circle_halfwidths(int radius, int* hw) {   // cv::circle(filled) rasterisation, as in frontend_fast.cu
+    for (int i = 0; i <= radius; ++i) hw[i] = -1;
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        if (hw[dy] < dx) hw[dy] = dx;
+        if (hw[dx] < dy) hw[dx] = dy;
+        dy++;
+        err += plus;
+        plus += 2;
+        const int mask = (err <= 0) - 1;
+        err -= minus & mask;
+        dx += mask;
+        minus -= mask & 2;
+    }
+}
+
+}  // namespace
+
+extern "C" ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, int first, int count, int cellsize,
+                                              const int32_t* curkp_offsets, const float* curkps, const int32_t* roi_xywh,
+                                              double* quality_inout, int max_per_frame, float* out_pts, int32_t* out_counts,
+                                              int32_t* out_pts_int, int do_subpix) {
+    if (!ctx || !pyr || !pyr->l0 || first < 0 || count <= 0 || first + count > pyr->batch || !quality_inout || !out_pts ||
+        !out_counts)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_detect_single_scale: bad arguments");
+    if (cellsize < 8 || cellsize > SS_MAX_CELL)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_detect_single_scale: cellsize must be in [8, 64]");
+    const int W = pyr->w[0], H = pyr->h[0];
+    const int nwc = W / cellsize, nhc = H / cellsize, ncells = nwc * nhc;
+    if (ncells == 0 || max_per_frame < ncells)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_detect_single_scale: max_per_frame < number of cells");
+    int roi[4] = {0, 0, W, H};
+    if (roi_xywh) {
+        if (ov2_is_device_ptr(roi_xywh)) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_detect_single_scale: roi must be a host pointer");
+        for (int i = 0; i < 4; ++i) roi[i] = roi_xywh[i];
+    }
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    const void* d = nullptr;
+    void* o = nullptr;
+    int nkp_total = 0;
+    const int32_t* d_off = nullptr;
+    const float2* d_kps = nullptr;
+    if (curkp_offsets) {
+        if ((st = ov2_stage_in(ctx, curkp_offsets, sizeof(int32_t) * (size_t)(count + 1), &d)) != OV2_OK) return st;
+        d_off = (const int32_t*)d;
+        if (ov2_is_device_ptr(curkp_offsets)) {
+            OV2_CUDA(ctx, cudaMemcpyAsync(&nkp_total, curkp_offsets + count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            nkp_total = curkp_offsets[count];
+        }
+        if (nkp_total > 0) {
+            if (!curkps) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_detect_single_scale: curkps is NULL");
+            if ((st = ov2_stage_in(ctx, curkps, sizeof(float) * 2 * (size_t)nkp_total, &d)) != OV2_OK) return st;
+            d_kps = (const float2*)d;
+        }
+    }
+    if ((st = ov2_stage_out(ctx, quality_inout, sizeof(double) * (size_t)count, &o, true)) != OV2_OK) return st;
+    double* d_q = (double*)o;
+    if ((st = ov2_stage_out(ctx, out_pts, sizeof(float) * 2 * (size_t)count * max_per_frame, &o)) != OV2_OK) return st;
+    float2* d_out = (float2*)o;
+    if ((st = ov2_stage_out(ctx, out_counts, sizeof(int32_t) * (size_t)count, &o)) != OV2_OK) return st;
+    int32_t* d_cnt = (int32_t*)o;
+    if (out_pts_int) {
+        if ((st = ov2_stage_out(ctx, out_pts_int, sizeof(int32_t) * 2 * (size_t)count * max_per_frame, &o)) != OV2_OK) return st;
+    } else {
+        if ((st = ov2_scratch(ctx, sizeof(int32_t) * 2 * (size_t)count * max_per_frame, &o)) != OV2_OK) return st;
+    }
+    int2* d_int = (int2*)o;
+    const size_t cell_px = (size_t)cellsize * cellsize;
+    if ((st = ov2_scratch(ctx, sizeof(float) * (size_t)count * ncells * cell_px, &o)) != OV2_OK) return st;
+    float* d_resp = (float*)o;
+
+    RespArgs RA;
+    RA.img = pyr->l0; RA.w = W; RA.h = H; RA.pitch = (int)pyr->l0_pitch; RA.fstride = (long long)pyr->l0_fstride;
+    RA.first = first; RA.cs = cellsize; RA.nwc = nwc; RA.nhc = nhc; RA.resp = d_resp;
+    {
+        const size_t smem = sscale::smem_bytes(cellsize);
+        if (smem > 48 * 1024)
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ss_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OV2_LAUNCH(ctx, "ss_response_kernel", ss_response_kernel<<<dim3(ncells, count), 256, smem, ctx->stream>>>(RA));
+    }
+    SweepArgs SA;
+    SA.w = W; SA.h = H; SA.cs = cellsize; SA.nwc = nwc; SA.nhc = nhc; SA.radius = cellsize / 4; SA.max_per_frame = max_per_frame;
+    circle_halfwidths(SA.radius, SA.hw);
+    SA.roi_x = roi[0]; SA.roi_y = roi[1]; SA.roi_w = roi[2]; SA.roi_h = roi[3];
+    SA.kp_off = d_off; SA.kps = d_kps; SA.resp = d_resp; SA.quality = d_q; SA.out_int = d_int; SA.out_n = d_cnt;
+    {
+        const size_t wpr = (size_t)(W + 31) / 32;
+        size_t smem = (((size_t)H * wpr + 1) & ~(size_t)1) * 4 + (size_t)ncells * sizeof(int2) * 2 + (size_t)(nhc + 1) * (nwc + 1);
+        smem = (smem + 15) & ~(size_t)15;
+        if (smem > 227 * 1024)
+            return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_detect_single_scale: image too large for the shared-memory mask bitmap");
+        if (smem > 48 * 1024)
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ss_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OV2_LAUNCH(ctx, "ss_sweep_kernel", ss_sweep_kernel<<<count, SWEEP_THREADS, smem, ctx->stream>>>(SA));
+    }
+    if ((st = ov2_subpix_launch(ctx, pyr, first, count, max_per_frame, d_int, d_out, do_subpix)) != OV2_OK) return st;
+    return ov2_end(ctx);
+}

@@ -436,3 +436,49 @@ def test_c4_resolution_1280x720_cell35(ctx):
     assert np.array_equal(st, rs) and np.abs(out - rp).max() <= KLT_TOL
     for p in (pp, cp, raw):
         p.close()
+
+
+# ---------------------------------------------------------------- D: detectSingleScale ("next" row 8f-1)
+@pytest.mark.parametrize("cs", [50, 35])
+def test_single_scale_detector_bit_exact(ctx, cs):
+    """ov2_detect_single_scale vs the oracle restatement of detectSingleScale (blur rounding rule,
+    float32 minimal-eigenvalue response, first-maximum arg-max twice per cell, disc mask, roi test, second
+    detections, dmaxquality_ update, cornerSubPix): integer positions and quality state identical,
+    refined positions within the cornerSubPix tolerance.  Batch of frames with different existing
+    keypoints and per-frame quality states; one call with a roi smaller than the image."""
+    w, h = 640, 480
+    nfr = 4
+    imgs = np.stack([synth.make_frame(80 + i, w, h) for i in range(nfr)])
+    pyr = api.Pyramid(ctx, nfr, w, h, 0)
+    pyr.build(imgs)
+    fe = api.FeatureExtractor(ctx)
+    ncell = (h // cs) * (w // cs)
+    rng = np.random.default_rng(100 + cs)
+    for roi in (None, (20, 24, w - 45, h - 50)):
+        kps_list = []
+        for f in range(nfr):
+            n = [0, 30, 5, 60][f]
+            k = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+            if n:
+                k[0] = [0.4, 0.4]
+                k[1] = [w - 1.0, h - 1.0]
+            kps_list.append(k)
+        off = np.concatenate([[0], np.cumsum([len(k) for k in kps_list])]).astype(np.int32)
+        allk = np.concatenate(kps_list).astype(np.float32)
+        q = np.array([0.001, 0.001, 0.0001, 0.05], np.float64)
+        q_in = q.copy()
+        pts = np.empty((nfr, ncell, 2), np.float32)
+        ipts = np.empty((nfr, ncell, 2), np.int32)
+        cnt = np.zeros(nfr, np.int32)
+        fe.detect_single_scale(pyr, cs, 0, nfr, q, pts, cnt, off, allk, roi, ipts)
+        for f in range(nfr):
+            ref_i, ref_q, _ = R.detect_single_scale_nosubpix(imgs[f], cs, kps_list[f], roi or (0, 0, w, h), float(q_in[f]),
+                                                             use_cv2=False)
+            assert cnt[f] == len(ref_i), (f, cnt[f], len(ref_i))
+            assert np.array_equal(ipts[f, :cnt[f]], ref_i), f
+            assert q[f] == ref_q, (f, q[f], ref_q)
+            assert (pts[f, cnt[f]:] == -1).all()
+            if cnt[f]:
+                ref_s = _subpix(imgs[f], ref_i.astype(np.float32))
+                assert np.abs(pts[f, :cnt[f]] - ref_s).max() <= SUBPIX_TOL
+    pyr.close()

@@ -161,3 +161,37 @@ int main() {
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), str(src)])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_single_scale_cell_math_matches_oracle(tmp_path):
+    """ov2slam_b200/csrc/sscale_math.cuh (the per-cell blur / Sobel / minimal-eigenvalue phases the
+    ss_response_kernel runs) compiled for the host with contraction off and run thread by thread, vs
+    oracle min_eigen_ref(blur3_cell_ref(.)): bit-exact float32 responses for every reference cell size."""
+    import numpy as np
+    from oracle import image_ref as R
+    src = tmp_path / "s.cpp"
+    src.write_text(r'''
+#include "%s/ov2slam_b200/csrc/sscale_math.cuh"
+#include <vector>
+extern "C" void cell_response(const unsigned char* raw, int cs, float* out) {
+    std::vector<unsigned char> bl(cs * cs);
+    std::vector<float> cxx(cs * cs), cxy(cs * cs), cyy(cs * cs);
+    const int nt = 256;
+    for (int t = 0; t < nt; ++t) sscale::phase_blur(t, nt, raw, bl.data(), cs);
+    for (int t = 0; t < nt; ++t) sscale::phase_cov(t, nt, bl.data(), cxx.data(), cxy.data(), cyy.data(), cs);
+    for (int t = 0; t < nt; ++t) sscale::phase_response(t, nt, cxx.data(), cxy.data(), cyy.data(), out, cs);
+}''' % ROOT)
+    so = tmp_path / "libs.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(so), str(src)])
+    lib = ctypes.CDLL(str(so))
+    lib.cell_response.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    rng = np.random.default_rng(21)
+    for it in range(60):
+        cs = int(rng.choice([50, 35, 16, 20, 33, 64, 8]))
+        raw = (rng.random((cs + 2, cs + 2)) * 255).astype(np.uint8)
+        if it % 2:
+            raw = np.clip(raw.astype(np.int32) // 8 + 100, 0, 255).astype(np.uint8)    # low contrast: many exact ties / zeros
+        out = np.empty((cs, cs), np.float32)
+        lib.cell_response(raw.ctypes.data, cs, out.ctypes.data)
+        ref = R.min_eigen_ref(R.blur3_cell_ref(raw, 1, 1, cs))
+        assert np.array_equal(out.view(np.int32), ref.view(np.int32)), (it, cs, int((out != ref).sum()))
