@@ -1,6 +1,7 @@
 // FeatureExtractor on the GPU: host shim over the C ABI (include/ov2b200.h).
 // Behaviour mirrored: /root/reference/src/feature_extractor.cpp:443-570 (detectGridFAST incl.
-// cornerSubPix and the nfast_th_ adaptation), :224-285 (describeBRIEF, non-contrib branch), :575-584
+// cornerSubPix and the nfast_th_ adaptation), :288-440 (detectSingleScale incl. the dmaxquality_
+// adaptation), :224-285 (describeBRIEF, non-contrib branch), :575-584
 // (setMask).  The front-end thread is the only caller (under map_mutex_, visual_front_end.cpp:42),
 // so one lazily created context per process is enough.  No OpenCV on the hot path, no CPU fallback.
 #include "feature_extractor.hpp"
@@ -100,14 +101,34 @@ std::vector<cv::Mat> FeatureExtractor::describeBRIEF(const cv::Mat &im, const st
 
 std::vector<cv::Point2f> FeatureExtractor::detectGFTT(const cv::Mat &, const std::vector<cv::Point2f> &, const cv::Mat &, int) const
 {
-    fprintf(stderr, "[ov2b200] detectGFTT is not built (SURVEY.md 8f 'next' row); use use_fast: 1 configs\n");
+    fprintf(stderr, "[ov2b200] detectGFTT is not built; use use_fast: 1 or use_singlescale_detector: 1 configs\n");
     return std::vector<cv::Point2f>();
 }
 
-std::vector<cv::Point2f> FeatureExtractor::detectSingleScale(const cv::Mat &, const int, const std::vector<cv::Point2f> &, const cv::Rect &)
+std::vector<cv::Point2f> FeatureExtractor::detectSingleScale(const cv::Mat &im, const int ncellsize,
+        const std::vector<cv::Point2f> &vcurkps, const cv::Rect &roi)
 {
-    fprintf(stderr, "[ov2b200] detectSingleScale is not built (SURVEY.md 8f 'next' row); use use_fast: 1 configs\n");
-    return std::vector<cv::Point2f>();
+    if (im.empty()) return std::vector<cv::Point2f>();           // feature_extractor.cpp:290-293
+    State& s = st();
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!load_image(s, im)) return std::vector<cv::Point2f>();
+    const int ncells = (im.rows / ncellsize) * (im.cols / ncellsize);
+    if (ncells <= 0) return std::vector<cv::Point2f>();
+    std::vector<cv::Point2f> out((size_t)ncells);
+    int32_t offsets[2] = {0, (int32_t)vcurkps.size()};
+    const int32_t roi_xywh[4] = {roi.x, roi.y, roi.width, roi.height};
+    double quality = dmaxquality_;
+    int32_t count = 0;
+    ov2_status rc = ov2_detect_single_scale(s.ctx, s.pyr, 0, 1, ncellsize, vcurkps.empty() ? nullptr : offsets,
+                                            vcurkps.empty() ? nullptr : reinterpret_cast<const float*>(vcurkps.data()),
+                                            roi_xywh, &quality, ncells, reinterpret_cast<float*>(out.data()), &count, nullptr, 1);
+    if (rc != OV2_OK) {
+        fprintf(stderr, "[ov2b200] detectSingleScale: %s\n", ov2_last_error(s.ctx));
+        return std::vector<cv::Point2f>();
+    }
+    dmaxquality_ = quality;                                      // adaptive quality state (:418-423)
+    out.resize((size_t)count);
+    return out;
 }
 
 // Host utility (not on the hot path): 8-bit mask with filled discs, OpenCV's midpoint rasterisation.

@@ -1,8 +1,8 @@
 // Drop-in replacement of the reference's include/feature_extractor.hpp (:31-55): same class, same
 // public members and signatures, so map_manager.cpp compiles and links against it unchanged.
-// detectGridFAST and describeBRIEF run on the GPU through the C ABI (include/ov2b200.h).
-// detectGFTT / detectSingleScale are "next" rows of the scope table: they are
-// declared so callers link, and report loudly that they are not built.
+// detectGridFAST, detectSingleScale and describeBRIEF run on the GPU through the C ABI
+// (include/ov2b200.h).  detectGFTT (use_shi_tomasi: 1, no reference configuration enables it) is
+// declared so callers link, and reports loudly that it is not built.
 #pragma once
 
 #include <opencv2/core.hpp>
