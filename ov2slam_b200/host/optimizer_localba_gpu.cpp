@@ -7,6 +7,9 @@
 // NOT COMPILE-CHECKED IN THIS CONTAINER: it needs the reference's headers and their dependencies
 // (Eigen, Sophus, OpenCV, PCL), none of which exist here.  It is compiled
 // only when OV2_WITH_REFERENCE_HEADERS is defined, on a box that can build the reference.
+// Mono and stereo windows (inverse-depth parametrisation, buse_inv_depth_ = 1: every shipped
+// configuration); the XYZ parametrisation (buse_inv_depth_ = 0) is not flattened and falls through
+// with a diagnostic.
 //
 // What stays on the host is exactly the part SURVEY.md 8a row G scopes out of acceleration: walking
 // the covisibility graph / hash maps to FLATTEN the window into the SoA arrays ov2_localba_solve
@@ -36,7 +39,13 @@ struct Window {
     std::vector<double> pose;  std::vector<uint8_t> pose_const;
     std::vector<int> lmids;  std::vector<std::shared_ptr<MapPoint>> lms;
     std::vector<int32_t> lm_anchor_cam;  std::vector<double> lm_anchor_px, lm_invdepth;
-    std::vector<int32_t> obs_cam, obs_lm;  std::vector<double> obs_px;
+    std::vector<int32_t> obs_cam, obs_lm;  std::vector<double> obs_px;  std::vector<uint8_t> obs_type;
+
+    // residual type as include/ov2b200.h: 0 left camera / other keyframe, 1 right camera / other keyframe,
+    // 2 right camera / anchor keyframe (obs_cam = anchor)
+    void add_obs(int cam, int lm, double u, double v, uint8_t type) {
+        obs_cam.push_back(cam); obs_lm.push_back(lm); obs_px.push_back(u); obs_px.push_back(v); obs_type.push_back(type);
+    }
 
     int add_camera(int kfid, const std::shared_ptr<Frame>& kf, bool constant) {
         auto it = cam_of_kf.find(kfid);
@@ -64,8 +73,9 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     if ((int)newframe.nb3dkps_ < nmincov) return;
     ov2_ctx* ctx = ba_context();
     if (!ctx) { std::cerr << "[ov2b200] localBA: no CUDA device (no CPU fallback)\n"; return; }
-    if (pslamstate_->stereo_) {
-        std::cerr << "[ov2b200] localBA: the stereo window flattening of this shim is not written yet (the ABI and kernels take obs_type/Kr/Trl); mono only\n";
+    const bool stereo = pslamstate_->stereo_;
+    if (!pslamstate_->buse_inv_depth_) {
+        std::cerr << "[ov2b200] localBA: only the anchored inverse-depth parametrisation (buse_inv_depth: 1) is built\n";
         return;
     }
 
@@ -107,6 +117,8 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
             const int cam = win.add_camera(kfid, kf, /*constant=*/cit == win.cam_of_kf.end());
             const auto kp = kf->getKeypointById(lmid);
             if (kp.lmid_ != lmid) { pmap_->removeMapPointObs(lmid, kfid); continue; }
+            // kp.scale_ is 0 for every keypoint the reference's front-end creates (map_manager.cpp adds
+            // keypoints without a scale), so the residuals' information matrix 2^-scale * I is the identity
             if (anchor_cam < 0) {
                 anchor_cam = cam;
                 win.lmids.push_back(lmid);
@@ -115,20 +127,23 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
                 win.lm_anchor_px.push_back(kp.unpx_.x);
                 win.lm_anchor_px.push_back(kp.unpx_.y);
                 win.lm_invdepth.push_back(1.0 / (kf->getTcw() * lm->getPoint()).z());
+                // the anchor's own right-camera observation constrains the inverse depth alone (optimizer.cpp:268-284)
+                if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 2);
                 continue;
             }
-            win.obs_cam.push_back(cam);
-            win.obs_lm.push_back(l);               // appended landmark by landmark: already sorted
-            win.obs_px.push_back(kp.unpx_.x);
-            win.obs_px.push_back(kp.unpx_.y);
+            win.add_obs(cam, l, kp.unpx_.x, kp.unpx_.y, 0);            // appended landmark by landmark: already sorted
+            if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 1);   // (optimizer.cpp:295-324)
         }
     }
-    // ---- 3. gauge: at least two constant keyframes in mono (optimizer.cpp:396-407), oldest first
+    // ---- 3. gauge: at least two constant keyframes in mono, one in stereo (optimizer.cpp:65-69, 396-407).
+    //         The reference walks its unordered_map of local keyframes (unspecified order); ascending
+    //         keyframe id is used here.
     size_t nconst = 0;
     for (uint8_t c : win.pose_const) nconst += c;
     {
+        const size_t nmincst = stereo ? 1 : 2;
         std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
-        for (auto it = by_id.begin(); nconst < 2 && it != by_id.end(); ++it)
+        for (auto it = by_id.begin(); nconst < nmincst && it != by_id.end(); ++it)
             if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
     }
     if (win.obs_cam.empty()) return;
@@ -142,7 +157,18 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     pb.lm_anchor_cam = win.lm_anchor_cam.data(); pb.lm_anchor_px = win.lm_anchor_px.data();
     pb.lm_invdepth = win.lm_invdepth.data();
     pb.obs_cam = win.obs_cam.data(); pb.obs_lm = win.obs_lm.data(); pb.obs_px = win.obs_px.data();
-    pb.obs_type = nullptr; pb.Kr = nullptr; pb.Trl = nullptr;      // mono window (stereo flattening: next)
+    double Kr[4] = {0, 0, 0, 0}, Trl[7] = {0, 0, 0, 0, 0, 0, 1};
+    pb.obs_type = nullptr; pb.Kr = nullptr; pb.Trl = nullptr;
+    if (stereo) {
+        auto calr = newframe.pcalib_rightcam_;
+        Kr[0] = calr->fx_; Kr[1] = calr->fy_; Kr[2] = calr->cx_; Kr[3] = calr->cy_;
+        const Sophus::SE3d T = calr->getExtrinsic().inverse();          // Trl (optimizer.cpp:112-114)
+        const Eigen::Quaterniond q = T.unit_quaternion();
+        const Eigen::Vector3d t = T.translation();
+        const double e[7] = {t.x(), t.y(), t.z(), q.x(), q.y(), q.z(), q.w()};
+        for (int i = 0; i < 7; ++i) Trl[i] = e[i];
+        pb.obs_type = win.obs_type.data(); pb.Kr = Kr; pb.Trl = Trl;
+    }
     ov2_ba_opts op;
     op.max_iters_robust = 5; op.max_iters_refine = 10;                // optimizer.cpp:462, :610
     op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-3;
@@ -159,8 +185,15 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     // ---- 5. apply to the map under map_mutex_ (optimizer.cpp:741-897)
     std::lock_guard<std::mutex> lock(pmap_->map_mutex_);
     std::unordered_map<int, int> suspicious;                           // lmid -> had a rejected observation
+    // rejected right-camera observations only lose their stereo half (removeStereoKeypointById,
+    // optimizer.cpp:742-750); rejected left-camera observations are removed from the map (:752-763)
     for (size_t i = 0; i < flags.size(); ++i) {
-        if (!flags[i]) continue;
+        if (!flags[i] || win.obs_type[i] == 0) continue;
+        win.kfs[win.obs_cam[i]]->removeStereoKeypointById(win.lmids[win.obs_lm[i]]);
+        suspicious.emplace(win.lmids[win.obs_lm[i]], 1);
+    }
+    for (size_t i = 0; i < flags.size(); ++i) {
+        if (!flags[i] || win.obs_type[i] != 0) continue;
         const int kfid = win.kfids[win.obs_cam[i]], lmid = win.lmids[win.obs_lm[i]];
         pmap_->removeMapPointObs(lmid, kfid);
         if (kfid == pmap_->pcurframe_->kfid_) pmap_->removeObsFromCurFrameById(lmid);
