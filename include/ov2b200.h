@@ -164,6 +164,25 @@ OV2_API ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, int
 OV2_API ov2_status ov2_debug_fast_cells(ov2_ctx* ctx, const ov2_pyr* pyr, int frame, int cellsize, int fast_th,
                                 uint32_t* cand_out, int32_t* cand_n_out, int cap_in, int* cap_out);
 
+/* ------------------------------------------------------------------ ceresPnP (motion-only BA), "next" row 2
+ * Replaces MultiViewGeometry::ceresPnP(vunkps, vwpts, vscales, Twc, nmaxiter, chi2th, buse_robust,
+ * bapply_l2_after_robust, fx, fy, cx, cy, voutliersidx)
+ * (/root/reference/src/multi_view_geometry.cpp:492-588; called per frame at src/visual_front_end.cpp:791-801),
+ * batched: problem k owns points [offsets[k], offsets[k+1]) of unpx ([N][2] undistorted pixels), wpts ([N][3]
+ * world points) and scales (pyramid level per point or NULL), calibration K[k] = fx, fy, cx, cy and pose
+ * Twc[k] = tx,ty,tz,qx,qy,qz,qw (in: initial guess, out: refined; unchanged when every block is rejected).
+ * ReprojectionErrorSE3 residuals with SE3LeftParameterization, HuberLoss(sqrt(chi2th)), Ceres' Levenberg-
+ * Marquardt loop (DENSE_QR in the reference; 6x6 damped normal equations here), max nmaxiter iterations,
+ * function tolerance 1e-3; blocks with chi2 > chi2th or non-positive depth after the first solve are flagged
+ * in outlier_flags (and removed before an L2 re-solve when apply_l2_after_robust).  success_out[k] = the
+ * reference's return value.  The 5 ms wall-clock cap of the reference (:538) is not modelled.
+ * offsets must be a HOST pointer; iterations_out (optional) = LM iterations of the last solve of each problem.
+ * STATUS (round 1): validated on the host against the oracle; not yet run on a B200. */
+OV2_API ov2_status ov2_pnp_solve(ov2_ctx* ctx, int nprob, const int32_t* offsets, const double* unpx, const double* wpts,
+                         const int32_t* scales, const double* K, double* pose_inout, int nmaxiter, float chi2th,
+                         int use_robust, int apply_l2_after_robust, uint8_t* outlier_flags, uint8_t* success_out,
+                         int32_t* iterations_out);
+
 /* ------------------------------------------------------------------ B: descriptors
  * Replaces FeatureExtractor::describeBRIEF(im, vpts)
  * (/root/reference/src/feature_extractor.cpp:224-285), non-contrib branch

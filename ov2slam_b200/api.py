@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
 ]
 
 
@@ -114,6 +114,7 @@ def load():
     lib.ov2_fb_klt.argtypes = [vp, vp, vp, C.POINTER(KltParams), i32, vp, i32, i32, vp, i32, vp, vp, vp]
     lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.ov2_detect_single_scale.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32]
+    lib.ov2_pnp_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, C.c_float, i32, i32, vp, vp, vp]
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
@@ -384,6 +385,41 @@ def _stereo_ptrs(pb: dict, keep: dict):
 
 DEFAULT_BA_OPTS = dict(max_iters_robust=5, max_iters_refine=10, huber_th=5.9915, function_tolerance=1e-3,
                        use_robust=1, apply_l2_after_robust=1, refine_loss=-1)
+
+
+class MultiViewGeometry:
+    """Mirror of the reference's static MultiViewGeometry::ceresPnP (multi_view_geometry.cpp:492-588), batched."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+
+    def ceres_pnp_batch(self, offsets, unpx, wpts, K, poses_inout, nmaxiter=5, chi2th=5.9915, use_robust=True,
+                        apply_l2_after_robust=True, scales=None):
+        """offsets int32[nprob+1] (host), unpx float64[N,2], wpts float64[N,3], K float64[nprob,4],
+        poses_inout float64[nprob,7] (Twc = t, q xyzw).  Returns (success uint8[nprob], outlier flags uint8[N],
+        LM iterations int32[nprob])."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        nprob = len(offsets) - 1
+        n = int(offsets[-1])
+        flags = np.zeros(max(n, 1), np.uint8)
+        success = np.zeros(max(nprob, 1), np.uint8)
+        its = np.zeros(max(nprob, 1), np.int32)
+        self.ctx.check(self.ctx.lib.ov2_pnp_solve(self.ctx.h, nprob, offsets.ctypes.data, _ptr(unpx), _ptr(wpts), _ptr(scales),
+                                                  _ptr(K), _ptr(poses_inout), int(nmaxiter), float(chi2th),
+                                                  1 if use_robust else 0, 1 if apply_l2_after_robust else 0,
+                                                  flags.ctypes.data, success.ctypes.data, its.ctypes.data))
+        return success[:nprob], flags[:n], its[:nprob]
+
+    def ceres_pnp(self, vunkps, vwpts, Twc, nmaxiter, chi2th, buse_robust, bapply_l2_after_robust, fx, fy, cx, cy, vscales=None):
+        """Single problem with the reference's argument order.  Returns (success, Twc_out, voutliersidx)."""
+        unpx = np.ascontiguousarray(vunkps, np.float64).reshape(-1, 2)
+        wpts = np.ascontiguousarray(vwpts, np.float64).reshape(-1, 3)
+        pose = np.ascontiguousarray(Twc, np.float64).reshape(1, 7).copy()
+        K = np.array([[fx, fy, cx, cy]], np.float64)
+        sc = None if vscales is None else np.ascontiguousarray(vscales, np.int32)
+        ok, flags, _ = self.ceres_pnp_batch(np.array([0, len(unpx)], np.int32), unpx, wpts, K, pose, nmaxiter, chi2th,
+                                            buse_robust, bapply_l2_after_robust, sc)
+        return bool(ok[0]), pose[0], np.nonzero(flags)[0]
 
 
 class Optimizer:

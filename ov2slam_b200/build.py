@@ -30,6 +30,7 @@ SOURCES = {
     "frontend_sscale.cu": ["-fmad=false"],
     "frontend_step.cu": [],
     "ba_solver.cu": [],
+    "pnp_solver.cu": [],
 }
 
 

@@ -195,3 +195,59 @@ extern "C" void cell_response(const unsigned char* raw, int cs, float* out) {
         lib.cell_response(raw.ctypes.data, cs, out.ctypes.data)
         ref = R.min_eigen_ref(R.blur3_cell_ref(raw, 1, 1, cs))
         assert np.array_equal(out.view(np.int32), ref.view(np.int32)), (it, cs, int((out != ref).sum()))
+
+
+def test_pnp_solver_code_matches_oracle(tmp_path):
+    """ov2slam_b200/csrc/pnp_math.cuh (the ceresPnP solve the GPU kernel instantiates with a thread-block
+    context) compiled for the host with the single-lane context, vs oracle/pnp_ref.py: same success flag,
+    same rejected blocks, same LM iteration count, pose to 1e-9 (normal equations vs the oracle's QR)."""
+    import numpy as np
+    from oracle import ba_ref, pnp_ref
+    src = tmp_path / "p.cpp"
+    src.write_text(r'''
+#include "%s/ov2slam_b200/csrc/pnp_math.cuh"
+#include <vector>
+extern "C" int pnp_host(int n, const double* unpx, const double* wpts, const double* K, double* pose, int nmaxiter,
+                        float chi2th, int use_robust, int apply_l2, unsigned char* flags, int* iterations) {
+    pnp::Problem P; P.n = n; P.unpx = unpx; P.wpts = wpts; P.scales = nullptr;
+    for (int i = 0; i < 4; ++i) P.K[i] = K[i];
+    std::vector<double> chi2(n); std::vector<unsigned char> dep(n), work(n);
+    pnp::SerialPar par; pnp::Summary S;
+    bool ok = pnp::ceres_pnp(par, P, pose, nmaxiter, chi2th, use_robust != 0, apply_l2 != 0, chi2.data(), dep.data(), flags, work.data(), S);
+    *iterations = S.iterations;
+    return ok ? 1 : 0;
+}''' % ROOT)
+    so = tmp_path / "libp.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(so), str(src)])
+    lib = ctypes.CDLL(str(so))
+    vp = ctypes.c_void_p
+    lib.pnp_host.argtypes = [ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp, vp]
+    K = np.array([458.0, 457.0, 367.0, 248.0])
+    rng = np.random.default_rng(3)
+    for case in range(12):
+        n = int(rng.integers(30, 400))
+        axis = rng.standard_normal(3); axis /= np.linalg.norm(axis)
+        ang = 0.3 * rng.random()
+        pose = np.concatenate([rng.standard_normal(3) * 0.5, axis * np.sin(ang / 2), [np.cos(ang / 2)]])
+        R = ba_ref.quat_to_rot(pose[3:])
+        pc = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2, 10, n)], 1)
+        wpts = np.ascontiguousarray(pc @ R.T + pose[:3])
+        px = np.stack([K[0] * pc[:, 0] / pc[:, 2] + K[2], K[1] * pc[:, 1] / pc[:, 2] + K[3]], 1)
+        px += rng.standard_normal(px.shape) * (0.0 if case % 3 == 0 else 0.6)
+        nbad = 0 if case % 2 == 0 else n // 8
+        bad = rng.choice(n, nbad, replace=False)
+        px[bad] += rng.uniform(15, 60, (nbad, 2))
+        if case == 11:
+            px += 500.0                                            # everything is an outlier
+        px = np.ascontiguousarray(px)
+        start = ba_ref.pose_plus(pose, np.concatenate([rng.standard_normal(3) * 0.05, rng.standard_normal(3) * 0.02]))
+        for apply_l2 in (1, 0):
+            ok_r, est_r, out_r = pnp_ref.ceres_pnp(px, wpts, start, K, 5, 5.9915, True, bool(apply_l2))
+            est = start.copy()
+            flags = np.zeros(n, np.uint8)
+            its = ctypes.c_int()
+            ok = lib.pnp_host(n, px.ctypes.data, wpts.ctypes.data, K.ctypes.data, est.ctypes.data, 5, 5.9915, 1, apply_l2,
+                              flags.ctypes.data, ctypes.byref(its))
+            assert bool(ok) == ok_r, case
+            assert np.array_equal(np.nonzero(flags)[0], out_r), case
+            assert np.abs(est - est_r).max() <= 1e-9, (case, np.abs(est - est_r).max())
