@@ -482,3 +482,11 @@ def test_single_scale_detector_bit_exact(ctx, cs):
                 ref_s = _subpix(imgs[f], ref_i.astype(np.float32))
                 assert np.abs(pts[f, :cnt[f]] - ref_s).max() <= SUBPIX_TOL
     pyr.close()
+
+
+def test_grid_fast_without_tma_staging(ctx, monkeypatch):
+    """The plain-load fallback of the FAST cell staging (level-0 images that do not meet the TMA alignment
+    rules, or a driver without cuTensorMapEncodeTiled) gives the same bit-exact result (OV2_NO_TMA=1)."""
+    monkeypatch.setenv("OV2_NO_TMA", "1")
+    test_grid_fast_bit_exact(ctx, 35, True)
+    test_grid_fast_bit_exact(ctx, 50, False)
