@@ -490,3 +490,22 @@ def test_grid_fast_without_tma_staging(ctx, monkeypatch):
     monkeypatch.setenv("OV2_NO_TMA", "1")
     test_grid_fast_bit_exact(ctx, 35, True)
     test_grid_fast_bit_exact(ctx, 50, False)
+
+
+@pytest.mark.parametrize("cs", [50, 35])
+def test_single_scale_against_committed_goldens(ctx, cs):
+    """ov2_detect_single_scale vs tests/golden/single_scale_golden.npz (generated from the real cv2 call
+    sequence): same integer positions and quality state, refined points within the cornerSubPix tolerance."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "single_scale_golden.npz")
+    w, h = int(g["w"]), int(g["h"])
+    im = synth.make_frame(int(g["seed"]), w, h)
+    pyr = api.Pyramid(ctx, 1, w, h, 0)
+    pyr.build(im[None])
+    for tag in ("empty", "kps_roi"):
+        fe = api.FeatureExtractor(ctx, dmaxquality=float(g[f"ss_{cs}_{tag}_q"][0]))
+        pts, ipts = fe.detect_single_scale_frame(pyr, 0, cs, g[f"ss_{cs}_{tag}_in"], tuple(int(v) for v in g[f"ss_{cs}_{tag}_roi"]))
+        assert np.array_equal(ipts, g[f"ss_{cs}_{tag}_int"]), tag
+        assert fe.dmaxquality_ == float(g[f"ss_{cs}_{tag}_q"][1])
+        assert np.abs(pts - g[f"ss_{cs}_{tag}_subpix"]).max() <= SUBPIX_TOL
+    pyr.close()

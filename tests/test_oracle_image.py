@@ -252,3 +252,20 @@ def test_detect_single_scale_ref_vs_cv2(cs):
         assert len(ic) > 0 or q > 0.01
         if len(ic):
             assert np.abs(pc - pr).max() <= 2e-4
+
+
+SS_GOLD = Path(__file__).parent / "golden" / "single_scale_golden.npz"
+
+
+@pytest.mark.parametrize("cs", [50, 35])
+@pytest.mark.parametrize("tag", ["empty", "kps_roi"])
+def test_golden_single_scale(cs, tag):
+    """Oracle restatement vs the committed cv2-generated vectors (scripts/make_golden_single_scale.py)."""
+    g = np.load(SS_GOLD)
+    im = synth.make_frame(int(g["seed"]), int(g["w"]), int(g["h"]))
+    assert hashlib.sha256(im.tobytes()).hexdigest() == str(g["img_sha"]), "synthetic generator drifted"
+    sp, ip, qn = R.detect_single_scale_ref(im, cs, g[f"ss_{cs}_{tag}_in"], tuple(int(v) for v in g[f"ss_{cs}_{tag}_roi"]),
+                                           float(g[f"ss_{cs}_{tag}_q"][0]))
+    assert np.array_equal(ip, g[f"ss_{cs}_{tag}_int"])
+    assert qn == float(g[f"ss_{cs}_{tag}_q"][1])
+    assert np.abs(sp - g[f"ss_{cs}_{tag}_subpix"]).max() <= 2e-4
