@@ -3,12 +3,20 @@
 The solve code (ov2slam_b200/csrc/pnp_math.cuh) is validated on the host against the oracle
 (tests/test_host_logic.py::test_pnp_solver_code_matches_oracle); the thread-block instantiation below was
 written after the round's GPU budget was spent and has not run on a B200 yet, hence the non-strict xfail:
-it is expected to pass, and must not turn the suite red if the untested block reduction has a defect."""
-import numpy as np
-import pytest
+it is expected to pass, and must not turn the suite red if the untested block reduction has a defect.
+The comparison runs in a CHILD process (python tests/test_pnp_gpu.py <apply_l2>) so that a device fault or a
+hang in the unvalidated kernel cannot poison the CUDA context of the main pytest process."""
+import os
+import subprocess
+import sys
 
-from ov2slam_b200 import api
-from oracle import ba_ref, pnp_ref
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # child-process entry (see below)
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+
+from ov2slam_b200 import api  # noqa: E402
+from oracle import ba_ref, pnp_ref  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -33,12 +41,11 @@ def _scene(rng, n, noise, nbad, all_bad=False):
     return np.ascontiguousarray(px), np.ascontiguousarray(wpts), start
 
 
-@pytest.mark.xfail(strict=False, reason="GPU instantiation written after the round's GPU budget was spent: not yet run on a B200")
-@pytest.mark.parametrize("apply_l2", [True, False])
-def test_pnp_batch_matches_oracle(ctx, apply_l2):
+def _compare(apply_l2: bool) -> None:
     """A ragged batch of pose problems (30..700 points, clean / noisy / gross outliers / everything rejected /
-    empty): success flag, rejected blocks and LM iteration count identical to the oracle, pose to 1e-7
-    (tolerance: normal equations + FMA contraction on the device vs QR in float64 numpy)."""
+    empty): success flag and rejected blocks identical to the oracle, pose to 1e-7 (tolerance: normal
+    equations + FMA contraction on the device vs QR in float64 numpy)."""
+    ctx = api.Context(0)
     rng = np.random.default_rng(9)
     probs = [_scene(rng, n, noise, nbad, ab) for n, noise, nbad, ab in
              [(200, 0.0, 0, False), (700, 0.6, 80, False), (30, 0.6, 3, False), (120, 0.6, 0, False), (64, 0.3, 0, True),
@@ -60,3 +67,16 @@ def test_pnp_batch_matches_oracle(ctx, apply_l2):
         assert bool(ok[k]) == ok_r, k
         assert np.array_equal(np.nonzero(flags[off[k]:off[k + 1]])[0], out_r), k
         assert np.abs(poses[k] - est_r).max() <= 1e-7, (k, np.abs(poses[k] - est_r).max())
+    ctx.close()
+
+
+@pytest.mark.xfail(strict=False, reason="GPU instantiation written after the round's GPU budget was spent: not yet run on a B200")
+@pytest.mark.parametrize("apply_l2", [True, False])
+def test_pnp_batch_matches_oracle(apply_l2):
+    out = subprocess.run([sys.executable, __file__, "1" if apply_l2 else "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-1500:]
+
+
+if __name__ == "__main__":
+    _compare(sys.argv[1] == "1")
+    print("PNP GPU OK")
