@@ -21,6 +21,7 @@
 // Jacobi scaling is applied algebraically (damping_i = clamp(s_i^2 c_i)/(radius s_i^2) on the
 // unscaled system), which is the same linear system Ceres solves after ScaleColumns.
 #include "ov2_common.cuh"
+#include "ge_warp.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -495,6 +496,28 @@ __global__ void __launch_bounds__(MODE >= 2 ? 512 : 1024) ba_reduced_solve_kerne
                 }
         }
         __syncthreads();
+    } else if (MODE == 5) {
+        // ONE warp, Gauss-Jordan on the augmented system in shared memory (ge_warp.cuh): no block barrier,
+        // one __syncwarp per pivot.  Launched with 32 threads; selected with OV2_BA_SOLVER=5 (candidate
+        // replacement of modes 2/3, not yet measured on a B200).
+        const int P = gewarp::pitch(n);
+        for (int e = tid; e < n * n; e += nt) {
+            const int r = e / n, c = e - r * n;
+            sA[r * P + c] = r <= c ? D.S[(size_t)r * n + c] : D.S[(size_t)c * n + r];
+        }
+        for (int i = tid; i < n; i += nt) sA[i * P + n] = w[i];
+        __syncwarp();
+        bool ok = true;
+        for (int j = 0; j < n && ok; ++j) {
+            ok = gewarp::step(tid, sA, n, P, j);            // uniform: every lane reads the same pivot
+            __syncwarp();
+        }
+        if (!ok) {
+            if (tid == 0) D.scal[SC_CHOL_FAIL] = 1.0;
+            return;
+        }
+        gewarp::finish(tid, sA, n, P, w);
+        __syncwarp();
     } else if (MODE == 4) {
         // Blocked right-looking Cholesky S = U'U (upper triangle, in global/L2), block size 32, on the
         // augmented system [S | b] so the forward substitution U'y = b comes out of the panel step:
@@ -893,15 +916,18 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     int solve_mode = n <= 63 ? 2 : (n <= 96 ? 3 : 4);
     if (getenv("OV2_BA_SOLVER")) {
         const int e = atoi(getenv("OV2_BA_SOLVER"));   // 0 / 1 / 4 force a Cholesky path (tests, comparisons)
-        if (e == 0 || (e == 4 && n > 0) || (e == 1 && (size_t)n * n * sizeof(double) <= 200 * 1024)) solve_mode = e;
+        if (e == 0 || (e == 4 && n > 0) || (e == 1 && (size_t)n * n * sizeof(double) <= 200 * 1024) || (e == 5 && n > 0 && n <= 96)) solve_mode = e;
     }
     const size_t smem_need = solve_mode == 1 ? (size_t)n * n * sizeof(double)             // modes 2/3 live in registers
-                           : (solve_mode == 4 ? (size_t)CH_NB * (((n + 15) & ~15) + 8) * sizeof(double) : 0);
-    int solve_threads = solve_mode == 2 ? 32 * div_up(n, 4) : (solve_mode == 3 ? 32 * div_up(n, 6) : (solve_mode == 4 ? 512 : 1024));
+                           : (solve_mode == 4 ? (size_t)CH_NB * (((n + 15) & ~15) + 8) * sizeof(double)
+                           : (solve_mode == 5 ? (size_t)n * gewarp::pitch(n) * sizeof(double) : 0));
+    int solve_threads = solve_mode == 2 ? 32 * div_up(n, 4) : (solve_mode == 3 ? 32 * div_up(n, 6) : (solve_mode == 4 ? 512 : (solve_mode == 5 ? 32 : 1024)));
     if (solve_threads < 32) solve_threads = 32;   // n == 0: every pose constant, only landmarks move
     if (smem_need > 24 * 1024) {   // static (up to ~15 KB) + dynamic beyond 48 KB needs the opt-in
         if (solve_mode == 1)
             OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+        else if (solve_mode == 5)
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
         else
             OV2_CUDA(ctx, cudaFuncSetAttribute(ba_reduced_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
     }
@@ -944,6 +970,8 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<2><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
         else if (solve_mode == 3)
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<3><<<1, solve_threads, 0, st>>>(D, radius, first_iter));
+        else if (solve_mode == 5)
+            OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<5><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter));
         else if (solve_mode == 4)
             OV2_LAUNCH(ctx, "ba_reduced_solve_kernel", ba_reduced_solve_kernel<4><<<1, solve_threads, smem_need, st>>>(D, radius, first_iter));
         else if (solve_mode == 1)

@@ -102,13 +102,15 @@ def test_localba_refine_loss_override(ctx):
 
 @pytest.mark.parametrize("ncam,npts,nobs,solver", [
     (16, 1200, 7000, None), (16, 1200, 7000, "4"),
+    pytest.param(16, 1200, 7000, "5", marks=pytest.mark.xfail(strict=False, reason="one-warp Gauss-Jordan (mode 5): host-validated, not yet run on a B200")),
+    pytest.param(10, 2000, 8000, "5", marks=pytest.mark.xfail(strict=False, reason="one-warp Gauss-Jordan (mode 5): host-validated, not yet run on a B200")),
     (22, 1500, 9000, None), (22, 1500, 9000, "1"), (22, 1500, 9000, "0"),
     (50, 4000, 30000, None), (50, 4000, 30000, "0")])
 def test_localba_all_reduced_solver_paths(ctx, monkeypatch, ncam, npts, nobs, solver):
     """Reduced camera systems of 84, 120 and 288 unknowns through every solver path: register
     Gauss-Jordan (default for n <= 96), blocked Cholesky with the FP64 tensor-core trailing update
     (default beyond; forced with OV2_BA_SOLVER=4), unblocked Cholesky in shared memory (=1) and in
-    global/L2 (=0), each against the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to
+    global/L2 (=0), the one-warp shared-memory Gauss-Jordan candidate (=5, n <= 96), each against the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to
     oracle/ba_ref.py)."""
     if solver is None:
         monkeypatch.delenv("OV2_BA_SOLVER", raising=False)
