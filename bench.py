@@ -148,9 +148,11 @@ def _cpu_worker(args):
 
 
 def _cpu_frame(R, cv2, prev, cur, kps, pri, is3d):
-    """Same work as one GPU-arm frame: P(prev), P(cur), K (two calls), F + S (empty vcurkps), B."""
-    cv2.buildOpticalFlowPyramid(prev, (9, 9), 3)
-    cv2.buildOpticalFlowPyramid(cur, (9, 9), 3)
+    """Same work as one GPU-arm frame: P(prev), P(cur), K (two calls), F + S (empty vcurkps), B.
+    The Python binding of calcOpticalFlowPyrLK cannot take a prebuilt pyramid, so every LK call builds the
+    pyramids it needs internally (2 per forward call; the reference builds each image's pyramid ONCE,
+    visual_front_end.cpp:1172): no explicit buildOpticalFlowPyramid on top of that - the arm already does
+    about twice the reference's pyramid work (~0.9 ms of ~12 ms per frame on one core)."""
     tracked = pri.copy()
     status = np.zeros(len(kps), np.uint8)
     i3 = np.nonzero(is3d)[0]
@@ -184,12 +186,17 @@ def run_cpu_reference(nframes: int, nproc: int, first_seed: int = 1000):
     return n / tmax, tmax, n
 
 
+def cpu_sample_frames(cores: int) -> int:
+    """frame pairs per CPU-arm step: 32 per worker process (6 per worker gave +-40 % run to run), capped."""
+    return int(min(max(32 * cores, 64), 3072))
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = usable_cores()
-    nframes = int(min(max(6 * cores, 64), 1536))
+    nframes = cpu_sample_frames(cores)
     # warm-up steps (page in cv2, fork pool once) then K timed steps, each a bounded sample
     for _ in range(max(1, min(args.warmup, 1))):
         run_cpu_reference(min(nframes, cores), cores)
@@ -210,7 +217,8 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
-        "config": _config(nframes, "reference CPU arm: one step = %d frame pairs" % nframes),
+        "config": _config(args.batch, "reference CPU arm: one step = a bounded sample of %d frame pairs of the same workload "
+                                      "(frames/s is per frame, independent of the sample size)" % nframes),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{nframes} frame pairs/step, OpenCV {ver} call sequence of feature_tracker.cpp/"
                                    f"feature_extractor.cpp via cv2 (oracle/image_ref.py), {cores} processes x 1 cv2 thread"},
@@ -367,6 +375,14 @@ class Workload:
     def e2e_launches(self):
         return sum(c.launch_count() for c in self.ectx)
 
+    def close(self):
+        if hasattr(self, "pool"):
+            self.pool.shutdown(wait=True)
+        for p in getattr(self, "epp", []) + getattr(self, "ecp", []) + [self.pyr_prev_d, self.pyr_cur_d, self.pyr_prev_h, self.pyr_cur_h]:
+            p.close()
+        for c in getattr(self, "ectx", []):
+            c.close()
+
 
 # SURVEY.md 8(d) algorithmic bytes per unit (stated in DESIGN.md)
 def algorithmic_bytes(kernel: str, batch: int) -> float:
@@ -498,7 +514,7 @@ def gpu_arm(args):
         cores = usable_cores()
         cpu = None
         if world == 1 and not args.no_cpu:
-            nfr = int(min(max(6 * cores, 64), 1536))
+            nfr = cpu_sample_frames(cores)
             fps, t, n = run_cpu_reference(nfr, cores)
             fps1, t1, n1 = run_cpu_reference(16, 1)
             try:
@@ -506,9 +522,14 @@ def gpu_arm(args):
                 ver = cv2.__version__
             except Exception:
                 ver = "?"
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            try:
+                simd = [l.strip() for l in cv2.getBuildInformation().splitlines() if "CPU/HW features" in l or "Baseline:" in l or "Dispatched" in l][:3]
+            except Exception:
+                simd = []
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "single_core_value": fps1,
                    "sample": f"{n} frame pairs, OpenCV {ver} call sequence (oracle/image_ref.py) in {cores} processes x 1 cv2 thread; "
-                             f"single core: {fps1:.1f} frames/s on {n1} pairs"}
+                             f"single core: {fps1:.1f} frames/s on {n1} pairs; LK rebuilds its pyramids per call (about 2x the "
+                             f"reference's pyramid work)", "opencv_simd": simd}
         line = {
             "metric": "front-end frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
@@ -522,10 +543,33 @@ def gpu_arm(args):
                     "pipelined_repeats": [frames / (m / 1000.0) for m in stream_ms]},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
+    # free the C2 workload before the other legs allocate theirs
+    wl.close()
+    del wl
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- C4 (stereo 1280x720, accurate parameters) and C5 (localBA 150k observations, N-way) legs: every rank takes part
+    import bench_legs as L
+    legs = {}
+    if not args.no_c4:
+        try:
+            legs["c4"] = L.c4_leg(torch, api, dist, ctx, stream, rank, world, args, _peaks(), usable_cores, _ncu_traffic)
+        except Exception as e:  # a leg must never take the front-end line down
+            import traceback
+            legs["c4"] = {"error": (str(e) + " | " + traceback.format_exc().splitlines()[-2])[:400]}
+    if not args.no_c5:
+        try:
+            legs["c5"] = L.c5_leg(torch, api, dist, ctx, rank, world, args, _peaks())
+        except Exception as e:
+            import traceback
+            legs["c5"] = {"error": (str(e) + " | " + traceback.format_exc().splitlines()[-2])[:400]}
+    if rank == 0:
+        line.update(legs)
         if world == 1 and not args.no_ba:
             try:
                 line["localba"] = ba_bench(torch, api, ctx)
-            except Exception as e:  # the BA leg must never take the front-end line down
+            except Exception as e:
                 line["localba"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -607,7 +651,14 @@ def main():
                     help="chunks (host threads x contexts) of the e2e arm; 0 = 8 on one GPU, fewer per rank when several "
                          "ranks share the host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-ba", action="store_true", help="skip the local-BA leg")
+    ap.add_argument("--no-ba", action="store_true", help="skip the local-BA (C3) leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (stereo 1280x720) leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (localBA 150k observations) leg")
+    ap.add_argument("--c4-batch", type=int, default=64, help="stereo units per GPU per C4 step")
+    ap.add_argument("--c4-unique", type=int, default=16, help="generated C4 units (the rest of the batch are flips / repeats)")
+    ap.add_argument("--c4-steps", type=int, default=10)
+    ap.add_argument("--c5-reps", type=int, default=5)
+    ap.add_argument("--c5-small", action="store_true", help="20 KF x 3000 pts x 18000 obs instead of the C5 window (debugging)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -103,6 +103,15 @@ OV2_API ov2_status ov2_pyr_download(ov2_ctx* ctx, const ov2_pyr* pyr, int frame,
 OV2_API ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride,
                      size_t frame_stride, int count, double clip_limit, int tiles_x, int tiles_y);
 
+/* preprocessImage as one call: VisualFrontEnd::preprocessImage (/root/reference/src/visual_front_end.cpp:1143-1177:
+ * optional pclahe_->apply, prev/cur swap, cv::buildOpticalFlowPyramid) and the right-image path of Mapper::run
+ * (src/mapper.cpp:75-81).  `raw` holds the untouched images (loaded with ov2_pyr_build; describeBRIEF reads the
+ * raw image, src/map_manager.cpp:301-303,326-329); frames [first, first+count) of `out` receive the equalised level 0
+ * (own storage) and levels 1.. built from it.  use_clahe = 0 (fast/ and average/ configurations): `out` aliases the raw
+ * level 0.  The image is uploaded once however many operators read it. */
+OV2_API ov2_status ov2_preprocess(ov2_ctx* ctx, const ov2_pyr* raw, ov2_pyr* out, int first, int count, int use_clahe,
+                          double clip_limit, int tiles_x, int tiles_y);
+
 /* ------------------------------------------------------------------ K: forward/backward KLT
  * Replaces FeatureTracker::fbKltTracking(vprevpyr, vcurpyr, nwinsize, nbpyrlvl, ferr,
  * fmax_fbklt_dist, vkps, vpriorkps, vkpstatus) (/root/reference/src/feature_tracker.cpp:35-137;
@@ -120,7 +129,9 @@ typedef struct {
 /* n keypoints.  nbpyrlvl: per-keypoint pyramid depth (the reference's two calls, nbpyrlvl 1 for
  * keypoints with a 3D prior and 3 for the rest, visual_front_end.cpp:196,242, become one launch),
  * or NULL to use nbpyrlvl_all for every keypoint.  kps = vkps (n x 2 float), priors_inout =
- * vpriorkps (in: initial guess, out: forward result), status_out = vkpstatus (n bytes, 0/1). */
+ * vpriorkps (in: initial guess, out: forward result), status_out = vkpstatus (n bytes, 0/1).
+ * Keypoints with x < 0 are empty-slot markers of fixed-stride batches (the detectors pad with (-1, -1)):
+ * status 0, prior untouched. */
 OV2_API ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_pyr* cur, const ov2_klt_params* prm,
                       int n, const int32_t* frame_idx, int first_frame, int per_frame,
                       const uint8_t* nbpyrlvl, int nbpyrlvl_all,

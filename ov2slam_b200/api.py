@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "ov2_create", "ov2_destroy", "ov2_last_error", "ov2_version", "ov2_set_stream", "ov2_sync",
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
-    "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe",
+    "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe", "ov2_preprocess",
     "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
 ]
 
@@ -111,6 +111,7 @@ def load():
     lib.ov2_pyr_build.argtypes = [vp, vp, vp, sz, sz, i32, i32]
     lib.ov2_pyr_download.argtypes = [vp, vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
     lib.ov2_clahe.argtypes = [vp, vp, vp, i32, i32, sz, sz, i32, C.c_double, i32, i32]
+    lib.ov2_preprocess.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, i32, i32]
     lib.ov2_fb_klt.argtypes = [vp, vp, vp, C.POINTER(KltParams), i32, vp, i32, i32, vp, i32, vp, vp, vp]
     lib.ov2_grid_fast.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.ov2_detect_single_scale.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32]
@@ -265,6 +266,15 @@ def clahe(ctx: Context, src, dst, width: int, height: int, count: int = 1, clip_
     rs = int(row_stride if row_stride is not None else width)
     fs = int(frame_stride if frame_stride is not None else rs * height)
     ctx.check(ctx.lib.ov2_clahe(ctx.h, _ptr(src), _ptr(dst), width, height, rs, fs, count, float(clip_limit), tx, ty))
+
+
+def preprocess(ctx: Context, raw: "Pyramid", out: "Pyramid", first: int = 0, count: int | None = None, use_clahe: bool = True,
+               clip_limit: float = 3.0, tiles=None):
+    """VisualFrontEnd::preprocessImage (visual_front_end.cpp:1143-1177): CLAHE of the raw level 0 into `out`
+    (tiles default to the reference's Size(W/50, H/50)) + the pyramid levels of `out`."""
+    tx, ty = tiles if tiles is not None else (raw.w // 50, raw.h // 50)
+    ctx.check(ctx.lib.ov2_preprocess(ctx.h, raw.h_, out.h_, int(first), int(raw.batch if count is None else count),
+                                     1 if use_clahe else 0, float(clip_limit), int(tx), int(ty)))
 
 
 class FeatureTracker:
@@ -530,3 +540,18 @@ def local_ba_sharded(ctx: Context, shard: dict, allreduce_cb, rank: int, **opts)
     shard["pose"][...] = keep["pose"]
     shard["lm_invdepth"][...] = keep["lm_invdepth"]
     return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags[:len(keep["obs_cam"])]
+
+
+class ShardedOptimizer:
+    """Multi-GPU Optimizer::localBA (BASELINE.json configs[4]): this rank's landmark shard, poses replicated."""
+
+    def __init__(self, ctx: Context, dist, torch, rank: int, world: int, group=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._cb = make_torch_allreduce(dist, torch, group)
+        self._mode = "ncclAllReduce through the ov2_allreduce_fn callback (torch.distributed)"
+
+    def local_ba(self, shard: dict, **opts):
+        return local_ba_sharded(self.ctx, shard, self._cb, self.rank, **opts)
+
+    def describe(self) -> str:
+        return self._mode

@@ -116,22 +116,13 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
 
 }  // namespace
 
-extern "C" ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride,
-                                size_t frame_stride, int count, double clip_limit, int tiles_x, int tiles_y) {
-    if (!ctx || !src || !dst || width <= 0 || height <= 0 || count <= 0 || tiles_x <= 0 || tiles_y <= 0 ||
-        row_stride < (size_t)width)
-        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_clahe: bad arguments");
-    ov2_status st = ov2_begin(ctx);
-    if (st != OV2_OK) return st;
-    const size_t bytes = frame_stride * (size_t)(count - 1) + row_stride * (size_t)(height - 1) + (size_t)width;
-    const void* d = nullptr;
-    void* o = nullptr;
-    if ((st = ov2_stage_in(ctx, src, bytes, &d)) != OV2_OK) return st;
-    if ((st = ov2_stage_out(ctx, dst, bytes, &o)) != OV2_OK) return st;
+// shared by ov2_clahe and ov2_preprocess: everything on the device already
+static ov2_status clahe_device(ov2_ctx* ctx, const uint8_t* src, int spitch, long long sfstride, uint8_t* dst, int dpitch,
+                               long long dfstride, int width, int height, int count, double clip_limit, int tiles_x, int tiles_y) {
     ClaheArgs A;
-    A.src = (const uint8_t*)d; A.dst = (uint8_t*)o;
-    A.w = width; A.h = height; A.spitch = A.dpitch = (int)row_stride;
-    A.sfstride = A.dfstride = (long long)frame_stride;
+    A.src = src; A.dst = dst;
+    A.w = width; A.h = height; A.spitch = spitch; A.dpitch = dpitch;
+    A.sfstride = sfstride; A.dfstride = dfstride;
     A.tx = tiles_x; A.ty = tiles_y;
     int ew = width, eh = height;
     if (width % tiles_x != 0 || height % tiles_y != 0) {      // OpenCV extends BOTH dimensions
@@ -151,10 +142,61 @@ extern "C" ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, 
     A.lut_scale = (float)255 / (float)area;
     A.inv_tw = 1.0f / (float)A.tw;
     A.inv_th = 1.0f / (float)A.th;
+    void* o = nullptr;
+    ov2_status st;
     if ((st = ov2_scratch(ctx, (size_t)count * tiles_x * tiles_y * 256, &o)) != OV2_OK) return st;
     A.lut = (uint8_t*)o;
     OV2_LAUNCH(ctx, "clahe_lut_kernel", clahe_lut_kernel<<<dim3(tiles_x * tiles_y, count), 256, 0, ctx->stream>>>(A));
     OV2_LAUNCH(ctx, "clahe_apply_kernel",
                clahe_apply_kernel<<<dim3(div_up(width, 1024), height, count), 256, 0, ctx->stream>>>(A));
+    return OV2_OK;
+}
+
+extern "C" ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride,
+                                size_t frame_stride, int count, double clip_limit, int tiles_x, int tiles_y) {
+    if (!ctx || !src || !dst || width <= 0 || height <= 0 || count <= 0 || tiles_x <= 0 || tiles_y <= 0 ||
+        row_stride < (size_t)width)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_clahe: bad arguments");
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    const size_t bytes = frame_stride * (size_t)(count - 1) + row_stride * (size_t)(height - 1) + (size_t)width;
+    const void* d = nullptr;
+    void* o = nullptr;
+    if ((st = ov2_stage_in(ctx, src, bytes, &d)) != OV2_OK) return st;
+    if ((st = ov2_stage_out(ctx, dst, bytes, &o)) != OV2_OK) return st;
+    if ((st = clahe_device(ctx, (const uint8_t*)d, (int)row_stride, (long long)frame_stride, (uint8_t*)o, (int)row_stride,
+                           (long long)frame_stride, width, height, count, clip_limit, tiles_x, tiles_y)) != OV2_OK)
+        return st;
+    return ov2_end(ctx);
+}
+
+// VisualFrontEnd::preprocessImage (/root/reference/src/visual_front_end.cpp:1143-1177; the right image:
+// src/mapper.cpp:75-81): optional CLAHE of the raw image, then buildOpticalFlowPyramid.  `raw` keeps the
+// untouched image (describeBRIEF reads it, src/map_manager.cpp:301-303,326-329), `out` receives the
+// equalised level 0 in its own storage and levels 1.. built from it: the image crosses PCIe once.
+extern "C" ov2_status ov2_preprocess(ov2_ctx* ctx, const ov2_pyr* raw, ov2_pyr* out, int first, int count, int use_clahe,
+                                     double clip_limit, int tiles_x, int tiles_y) {
+    if (!ctx || !raw || !out || first < 0 || count <= 0 || first + count > raw->batch || first + count > out->batch ||
+        raw->w[0] != out->w[0] || raw->h[0] != out->h[0] || !raw->l0)
+        return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_preprocess: bad arguments / raw pyramid not loaded");
+    if (use_clahe && (tiles_x <= 0 || tiles_y <= 0)) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_preprocess: bad tile grid");
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    if (!use_clahe) {
+        // no equalisation: the tracking image IS the raw image -> alias it
+        if (out->l0_mode == 1) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_preprocess: output pyramid owns level 0");
+        out->l0 = raw->l0; out->l0_pitch = raw->l0_pitch; out->l0_fstride = raw->l0_fstride; out->l0_mode = 2;
+    } else {
+        if (out->l0_mode == 2) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_preprocess: output pyramid aliases device images");
+        if (!out->own[0]) {
+            OV2_CUDA(ctx, cudaMalloc(&out->own[0], out->fstride[0] * (size_t)out->batch));
+            out->l0 = out->own[0]; out->l0_pitch = out->pitch[0]; out->l0_fstride = out->fstride[0]; out->l0_mode = 1;
+        }
+        if ((st = clahe_device(ctx, raw->l0 + raw->l0_fstride * (size_t)first, (int)raw->l0_pitch, (long long)raw->l0_fstride,
+                               out->own[0] + out->fstride[0] * (size_t)first, (int)out->pitch[0], (long long)out->fstride[0],
+                               raw->w[0], raw->h[0], count, clip_limit, tiles_x, tiles_y)) != OV2_OK)
+            return st;
+    }
+    if ((st = ov2_pyr_make_levels(ctx, out, first, count)) != OV2_OK) return st;
     return ov2_end(ctx);
 }

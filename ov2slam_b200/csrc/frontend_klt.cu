@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt
     float2 fwd = A.priors[i];
     const double eps2 = (double)A.eps * (double)A.eps;
     float err = 0.f;
-    bool ok = lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, eps2, err, sPall[warp], sDall[warp], lane);
+    // x < 0 marks an empty slot of a fixed-stride batch (the detectors pad their output with (-1, -1),
+    // ov2_describe uses the same rule): status 0, prior untouched, no work
+    bool ok = kp.x >= 0.f &&
+              lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, eps2, err, sPall[warp], sDall[warp], lane);
     // feature_tracker.cpp:79-101
     if (ok && err > A.ferr) ok = false;
     if (ok) {

@@ -179,6 +179,7 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     std::vector<uint8_t> flags(win.obs_cam.size(), 0);
     if (ov2_localba_solve(ctx, &pb, &op, &res, flags.data()) != OV2_OK) {
         std::cerr << "[ov2b200] localBA: " << ov2_last_error(ctx) << "\n";
+        bstop_localba_ = false;
         return;                                                        // map untouched
     }
 
@@ -226,6 +227,7 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
         auto lm = pmap_->getMapPoint(s.first);
         if (lm) cull_if_weak(s.first, lm);
     }
+    bstop_localba_ = false;                                            // optimizer.cpp:896: a stop request is consumed by the BA it interrupted
 }
 
 #endif  // OV2_WITH_REFERENCE_HEADERS

@@ -102,8 +102,7 @@ def test_localba_refine_loss_override(ctx):
 
 @pytest.mark.parametrize("ncam,npts,nobs,solver", [
     (16, 1200, 7000, None), (16, 1200, 7000, "4"),
-    pytest.param(16, 1200, 7000, "5", marks=pytest.mark.xfail(strict=False, reason="one-warp Gauss-Jordan (mode 5): host-validated, not yet run on a B200")),
-    pytest.param(10, 2000, 8000, "5", marks=pytest.mark.xfail(strict=False, reason="one-warp Gauss-Jordan (mode 5): host-validated, not yet run on a B200")),
+    (16, 1200, 7000, "5"), (10, 2000, 8000, "5"),
     (22, 1500, 9000, None), (22, 1500, 9000, "1"), (22, 1500, 9000, "0"),
     (50, 4000, 30000, None), (50, 4000, 30000, "0")])
 def test_localba_all_reduced_solver_paths(ctx, monkeypatch, ncam, npts, nobs, solver):
@@ -127,3 +126,39 @@ def test_localba_all_reduced_solver_paths(ctx, monkeypatch, ncam, npts, nobs, so
     assert np.abs(gpu["pose"] - ref["pose"]).max() <= 1e-6
     assert np.abs(gpu["lm_invdepth"] - ref["lm_invdepth"]).max() <= 1e-6
     assert (flags != r["flags"]).sum() <= 2
+
+
+def test_localba_c5_size_150k_observations(ctx):
+    """BASELINE.json configs[4] size on one GPU: 50 KF x 20 000 landmarks x 150 000 observations (288 x 288 reduced
+    system) against the C restatement of the oracle: same LM decisions, cost 1e-8, states 1e-6, flags equal up to
+    threshold-borderline observations."""
+    from oracle import ba_ref_c
+    pb = synth.make_ba_problem(5, 50, 20000, 150000)
+    ref = _clone(pb)
+    r = ba_ref_c.local_ba(ref)
+    gpu = _clone(pb)
+    g, flags = api.Optimizer(ctx).local_ba(gpu)
+    assert (g["iters_robust"], g["iters_refine"]) == (r["iters_robust"], r["iters_refine"])
+    assert abs(g["final_cost"] - r["final_cost"]) <= 1e-8 * max(1.0, r["final_cost"])
+    assert np.abs(gpu["pose"] - ref["pose"]).max() <= 1e-6
+    assert np.abs(gpu["lm_invdepth"] - ref["lm_invdepth"]).max() <= 1e-6
+    assert (flags != r["flags"]).sum() <= 4
+    assert g["n_outliers_first"] > 5000
+
+
+def test_localba_stereo_150k_blocks_matches_golden(ctx):
+    """Stereo window with 150 000 residual blocks (all three residual types) against the committed result of the numpy
+    oracle (tests/golden/ba_stereo_150k.npz, scripts/make_golden_ba.py; the oracle needs about a minute for it)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "ba_stereo_150k.npz")
+    pb = synth.make_ba_problem(int(g["seed"]), int(g["ncam"]), int(g["npts"]), int(g["nobs"]), stereo=True)
+    assert len(pb["obs_cam"]) == 150000
+    res, flags = api.Optimizer(ctx).local_ba(pb)
+    assert [res["iters_robust"], res["iters_refine"]] == g["iters"].tolist()
+    assert res["termination"] == int(g["termination"][0])
+    assert abs(res["final_cost"] - g["costs"][1]) <= 1e-8 * max(1.0, g["costs"][1])
+    assert np.abs(pb["pose"] - g["pose"]).max() <= 1e-6
+    assert np.abs(pb["lm_invdepth"] - g["lm_invdepth"]).max() <= 1e-6
+    f1 = np.unpackbits(g["flags"])[:150000]
+    assert ((flags & 1) != f1).sum() <= 4
+    assert abs(res["n_outliers_first"] - int(g["n_outliers"][0])) <= 4

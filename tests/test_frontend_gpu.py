@@ -509,3 +509,95 @@ def test_single_scale_against_committed_goldens(ctx, cs):
         assert fe.dmaxquality_ == float(g[f"ss_{cs}_{tag}_q"][1])
         assert np.abs(pts - g[f"ss_{cs}_{tag}_subpix"]).max() <= SUBPIX_TOL
     pyr.close()
+
+
+# ---------------------------------------------------------------- C4: 1280x720, accurate parameters, full chain
+def test_single_scale_detector_1280x720_cell35(ctx):
+    """BASELINE.json configs[3] geometry for the detector the accurate/ configurations really use: detectSingleScale at
+    1280x720, cell 35 (720 cells), on the CLAHE-equalised image with existing keypoints: integer positions and the
+    dmaxquality_ state identical to the oracle, refined positions within the cornerSubPix tolerance."""
+    w, h, cs = 1280, 720, 35
+    im = synth.make_frame(510, w, h)
+    eq = R.clahe_cv2(im) if R.HAVE_CV2 else R.clahe_ref(im)
+    rng = np.random.default_rng(77)
+    kps = np.stack([rng.uniform(5, w - 5, 300), rng.uniform(5, h - 5, 300)], 1).astype(np.float32)
+    pyr = api.Pyramid(ctx, 1, w, h, 0)
+    pyr.build(eq[None])
+    for q0, kk in ((0.001, kps), (0.001, np.zeros((0, 2), np.float32)), (0.05, kps[:40])):
+        fe = api.FeatureExtractor(ctx, dmaxquality=q0)
+        pts, ipts = fe.detect_single_scale_frame(pyr, 0, cs, kk, (0, 0, w, h))
+        ref_i, ref_q, _ = R.detect_single_scale_nosubpix(eq, cs, kk, (0, 0, w, h), q0, use_cv2=False)
+        assert np.array_equal(ipts, ref_i), (q0, len(ipts), len(ref_i))
+        assert fe.dmaxquality_ == ref_q
+        assert len(ipts) > 100
+        assert np.abs(pts - _subpix(eq, ref_i.astype(np.float32))).max() <= SUBPIX_TOL
+    pyr.close()
+
+
+def test_c4_full_chain_stereo_1280x720(ctx):
+    """The C4 step of bench.py stage by stage against the oracle (every stage is fed the GPU's own previous outputs, so
+    tolerances do not compound): ov2_preprocess (CLAHE + pyramid, raw image kept), temporal fb-KLT with mixed pyramid
+    depths, detectSingleScale with the tracked points as vcurkps, descriptors on the RAW image, stereo fb-KLT
+    left -> right including the (-1, -1) empty-slot markers of the detector's fixed-stride output."""
+    import bench_legs as L
+    w, h, cs = L.C4_W, L.C4_H, L.C4_CELL
+    prev, cur, right, kps, pri, lv, soff, slv = L.make_stereo_unit(4321)
+    clahe = R.clahe_cv2 if R.HAVE_CV2 else R.clahe_ref
+    klt = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
+    eq = {k: clahe(v) for k, v in (("prev", prev), ("cur", cur), ("right", right))}
+    raw = {k: api.Pyramid(ctx, 1, w, h, 0) for k in eq}
+    pyr = {k: api.Pyramid(ctx, 1, w, h, 3) for k in eq}
+    for k, im in (("prev", prev), ("cur", cur), ("right", right)):
+        raw[k].build(im[None])
+        api.preprocess(ctx, raw[k], pyr[k], 0, 1, True, 3.0, L.C4_TILES)
+        ref = R.build_pyramid_ref(eq[k], 3)
+        for lvl in range(4):
+            assert np.array_equal(pyr[k].download(0, lvl), ref[lvl]), (k, lvl)
+        assert np.array_equal(raw[k].download(0, 0), im)
+    ft = api.FeatureTracker(ctx, 30, 0.01)
+    out = pri.copy()
+    st = np.zeros(len(kps), np.uint8)
+    ft.fb_klt_tracking(pyr["prev"], pyr["cur"], 9, lv, 30.0, 0.5, kps, out, st)
+    for lvl in (1, 3):
+        idx = np.nonzero(lv == lvl)[0]
+        rp, rs = klt(eq["prev"], eq["cur"], kps[idx], pri[idx], 9, lvl)
+        assert np.array_equal(st[idx], rs) and np.abs(out[idx] - rp).max() <= KLT_TOL
+    assert st.mean() > 0.7
+    fe = api.FeatureExtractor(ctx, nmaxdist=cs, dmaxquality=L.C4_Q)
+    ncell = L.C4_NCELL
+    newp = np.empty((ncell, 2), np.float32)
+    newi = np.empty((ncell, 2), np.int32)
+    cnt = np.zeros(1, np.int32)
+    q = np.array([L.C4_Q])
+    fe.detect_single_scale(pyr["cur"], cs, 0, 1, q, newp, cnt, np.array([0, len(out)], np.int32), out, None, newi)
+    ref_i, ref_q, _ = R.detect_single_scale_nosubpix(eq["cur"], cs, out, (0, 0, w, h), L.C4_Q, use_cv2=False)
+    n = int(cnt[0])
+    assert n == len(ref_i) and np.array_equal(newi[:n], ref_i) and q[0] == ref_q and n > 150
+    assert (newp[n:] == -1).all()
+    assert np.abs(newp[:n] - _subpix(eq["cur"], ref_i.astype(np.float32))).max() <= SUBPIX_TOL
+    allp = np.concatenate([out, newp])
+    d = np.zeros((len(allp), 32), np.uint8)
+    v = np.zeros(len(allp), np.uint8)
+    fe.describe_brief(raw["cur"], allp, d, v)
+    good = allp[:, 0] >= 0
+    rd, rv = (R.describe_cv2 if R.HAVE_CV2 else R.describe_ref)(cur, allp[good])
+    assert np.array_equal(v[good], rv) and np.array_equal(d[good], rd) and not v[~good].any()
+    # stereo: tracked keypoints with their disparity priors, then the detector's fixed-stride output (markers included)
+    spri = out + soff
+    sout = spri.copy()
+    sst = np.zeros(len(out), np.uint8)
+    ft.fb_klt_tracking(pyr["cur"], pyr["right"], 9, slv, 30.0, 0.5, out, sout, sst)
+    inside = (out[:, 0] >= 0) & (out[:, 0] < w) & (out[:, 1] >= 0) & (out[:, 1] < h)
+    for lvl in (1, 3):
+        idx = np.nonzero((slv == lvl) & inside)[0]
+        rp, rs = klt(eq["cur"], eq["right"], out[idx], spri[idx], 9, lvl)
+        assert np.array_equal(sst[idx], rs) and np.abs(sout[idx] - rp).max() <= KLT_TOL
+    nout = newp.copy()
+    nst = np.full(ncell, 7, np.uint8)
+    ft.fb_klt_tracking(pyr["cur"], pyr["right"], 9, 3, 30.0, 0.5, newp, nout, nst)
+    rp, rs = klt(eq["cur"], eq["right"], newp[:n], newp[:n].copy(), 9, 3)
+    assert np.array_equal(nst[:n], rs) and np.abs(nout[:n] - rp).max() <= KLT_TOL
+    assert not nst[n:].any() and np.array_equal(nout[n:], newp[n:])      # empty slots: status 0, prior untouched
+    assert sst.mean() > 0.5 and nst[:n].mean() > 0.5
+    for p in list(raw.values()) + list(pyr.values()):
+        p.close()
