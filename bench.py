@@ -421,6 +421,22 @@ def gpu_arm(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = api.Context(local, stream=stream.cuda_stream)
+    if args.kernels_only and args.only in ("c4", "c5"):
+        # profiler runs of the other legs: resident steps only (no host threads under ncu)
+        import bench_legs as L
+        if args.only == "c4":
+            w4 = L.C4Workload(torch, api, ctx, rank, args.c4_batch, args.c4_unique, min(usable_cores(), 16))
+            for _ in range(args.warmup + args.steps):
+                w4.step_resident()
+            torch.cuda.synchronize()
+        else:
+            from ov2slam_b200 import synth
+            pb = synth.make_ba_problem(5, *(L.C5 if not args.c5_small else (20, 3000, 18000)))
+            opt = api.Optimizer(ctx)
+            for _ in range(args.warmup + args.steps):
+                opt.local_ba({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()})
+        print(json.dumps({"kernels_only": True, "only": args.only, "note": "not a bench line: for ncu"}), flush=True)
+        return 0
     wl = Workload(torch, api, ctx, rank, args.batch)
 
     def barrier():
@@ -588,40 +604,71 @@ def _ncu_traffic(kernel: str):
 
 
 def ba_bench(torch, api, ctx):
-    """local-BA solves/s on the C3 problem (10 KF x 2000 pts x 8000 obs) - the second half of
-    BASELINE.json's metric - through the C ABI with HOST buffers (upload of the flattened window,
-    two-stage solve, download of poses / inverse depths / outlier flags all inside the timed region),
-    next to the single-threaded C restatement of the reference's Ceres path (oracle/ba_ref_c.c;
-    "restatement, not Ceres": Ceres cannot be built offline; the reference runs it with
-    num_threads = 1, optimizer.cpp:460)."""
+    """local-BA solves/s on the C3 problem (10 KF x 2000 pts x 8000 obs) - the second half of BASELINE.json's metric -
+    through the C ABI with HOST buffers (upload of the flattened window, two-stage solve, download of poses / inverse
+    depths / outlier flags all inside the timed region): one window per call (`value`) and K independent windows per
+    launch (`batched`), next to the single-threaded C restatement of the reference's Ceres path (oracle/ba_ref_c.c;
+    "restatement, not Ceres": Ceres cannot be built offline; the reference runs it with num_threads = 1,
+    optimizer.cpp:460)."""
     from ov2slam_b200 import synth
+    import bench_legs as L
     opt = api.Optimizer(ctx)
     pb0 = synth.make_ba_problem(3, 10, 2000, 8000)
-    clone = lambda: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb0.items()}
+    clone = lambda d=pb0: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in d.items()}
     reps, its = 50, 0
     for _ in range(3):
         opt.local_ba(clone())
     pbs = [clone() for _ in range(reps)]
     torch.cuda.synchronize()
+    l0 = ctx.launch_count()
     t0 = time.perf_counter()
     for pb in pbs:
         res, _ = opt.local_ba(pb)
         its += res["iters_robust"] + res["iters_refine"]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    launches = (ctx.launch_count() - l0) / reps
     ctx.profile(True)
     opt.local_ba(clone())
     rep = ctx.profile_report()
     ctx.profile(False)
     tot = sum(v[0] for v in rep.values()) or 1.0
+    peak, peak_src = _peaks()
+    bpi = L.ba_bytes_per_iteration(8000, 2000)
     out = {"metric": "local-BA solves/sec", "value": reps / dt, "unit": "solves/s", "ms_per_solve": 1e3 * dt / reps,
            "config": {"workload": "C3: localBA 10 KF x 2000 inverse-depth pts x 8000 obs, 5 % gross outliers, two-stage solve"},
            "lm_iterations_per_solve": its / reps, "final_cost": res["final_cost"], "dtype": "f64",
            "kernel_time_shares": {k: round(v[0] / tot, 4) for k, v in rep.items()},
-           "kernel_launches_per_solve": int(sum(v[1] for v in rep.values())),
-           "gpu_kernel_ms_per_solve": tot,
-           "roofline_note": "one C3 solve touches ~0.66 MB per LM iteration and lives in L2: it is launch/sync-latency bound "
-                            "(SURVEY.md 7 'hard parts'), the HBM roofline applies to batched / C5-size problems"}
+           "kernel_launches_per_solve": launches, "gpu_kernel_ms_per_solve": tot,
+           "roofline": {"bound": "hbm", "kernel": "ba_lm_kernel (whole two-stage solve, one launch)", "achieved": (its / reps) * bpi / (dt / reps) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": (its / reps) * bpi / (dt / reps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "note": "one C3 window is 0.66 MB per LM iteration and lives in L2: a single solve is barrier/latency bound "
+                                "(SURVEY.md 7 'hard parts'); the HBM roofline is meaningful for the batched and C5 legs"}}
+    # ---- batched: K independent windows per launch (8 distinct windows tiled)
+    try:
+        K = 128
+        base = [synth.make_ba_problem(100 + i, 10, 2000, 8000) for i in range(8)]
+        mk = lambda: [clone(base[i % 8]) for i in range(K)]
+        for _ in range(2):
+            api.local_ba_batch(ctx, mk())
+        breps = 5
+        sets = [mk() for _ in range(breps)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bits = 0
+        for st in sets:
+            rs, _ = api.local_ba_batch(ctx, st)
+            bits += sum(r["iters_robust"] + r["iters_refine"] for r in rs)
+        torch.cuda.synchronize()
+        bdt = time.perf_counter() - t0
+        ach = bits * bpi / bdt / 1e9
+        out["batched"] = {"value": K * breps / bdt, "unit": "solves/s", "windows_per_launch": K, "ms_per_launch": 1e3 * bdt / breps,
+                          "lm_iterations_per_solve": bits / (K * breps),
+                          "roofline": {"bound": "hbm", "kernel": "ba_lm_kernel (K windows per launch)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                       "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                                       "algorithmic_bytes": "67 N_obs + 64 N_pts per LM iteration x iterations run (SURVEY 8d)"}}
+    except Exception as e:
+        out["batched"] = {"error": str(e)[:200]}
     try:
         from oracle import ba_ref_c
         ts = []
@@ -650,6 +697,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=0,
                     help="chunks (host threads x contexts) of the e2e arm; 0 = 8 on one GPU, fewer per rank when several "
                          "ranks share the host cores")
+    ap.add_argument("--only", default="c2", choices=["c2", "c4", "c5"], help="with --kernels-only: which leg's resident steps to run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA (C3) leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (stereo 1280x720) leg")

@@ -265,11 +265,45 @@ typedef struct {
     int    termination;                 /* 0 convergence, 1 max iterations, 2 failure */
 } ov2_ba_result;
 
-/* outlier_out (optional): [nobs] bytes, bit0 = flagged after solve #1, bit1 = after solve #2. */
+/* outlier_out (optional): [nobs] bytes, bit0 = flagged after solve #1, bit1 = after solve #2.
+ * The whole two-stage solve (both Ceres solves, every LM iteration, both outlier scans) is ONE kernel launch with the
+ * trust-region controller on the device (csrc/ba_lm.cu); OV2_BA_LEGACY=1 selects the round-1 path (one launch per phase,
+ * controller on the host) as a cross-check.  At most 64 optimised and 256 total keyframes per window. */
 OV2_API ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
                              ov2_ba_result* res, uint8_t* outlier_out);
 
-/* Multi-GPU localBA (BASELINE.json configs[4]): landmarks (with all their observations) are
+/* K independent windows in ONE launch (the solves/s metric; SURVEY.md 7 "hard parts" (ii)): window k is pbs[k] with results[k]
+ * and outlier_outs[k] (NULL entries / NULL array allowed); the same options for every window.  Groups of thread blocks pull
+ * windows round-robin, every group runs the whole two-stage solve of its window on the device. */
+OV2_API ov2_status ov2_localba_solve_batch(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const ov2_ba_opts* opts,
+                                   ov2_ba_result* results, uint8_t* const* outlier_outs);
+
+/* Optimizer::signalStopLocalBA / stopLocalBA (/root/reference/src/optimizer.cpp:2334-2343, raised by Estimator::addNewKf,
+ * src/estimator.cpp:228-232): stop = 1 asks the solve running (or about to run) on `ctx` to skip the L2 refinement; the
+ * solve kernel polls the flag where the reference does (optimizer.cpp:603-604).  May be called from another host thread
+ * while ov2_localba_solve runs; the caller clears it (stop = 0) as optimizer.cpp:896 does. */
+OV2_API ov2_status ov2_localba_request_stop(ov2_ctx* ctx, int stop);
+
+/* Multi-GPU localBA over PEER MEMORY (BASELINE.json configs[4]).  One process per GPU (or several contexts in one
+ * process): every rank creates a communicator (it allocates the rank's exchange buffer), the 64-byte CUDA IPC handles are
+ * exchanged by the caller (torch.distributed.all_gather, MPI, a pipe ...) and handed to ov2_ba_comm_connect.  The solve is
+ * collective: every rank calls ov2_localba_solve_p2p with ITS shard (landmarks with all their observations partitioned over
+ * the ranks, every rank holds all keyframe poses; a shard may be empty).  Inside the solve kernel every LM iteration sums
+ * the ranks' partial reduced camera systems [cost, rhs, F'r, column norms, S] straight out of peer memory over NVLink
+ * (rank order, so every rank holds bit-identical sums, solves the same system and takes the same decisions): no NCCL call
+ * and no host round trip between iterations.  Poses come back identical on all ranks, inverse depths / flags / outlier
+ * counts are the shard's own. */
+typedef struct ov2_ba_comm ov2_ba_comm;
+OV2_API ov2_status ov2_ba_comm_create(ov2_ctx* ctx, int rank, int world, ov2_ba_comm** out);       /* world <= 8 */
+OV2_API ov2_status ov2_ba_comm_handle(ov2_ba_comm* comm, void* handle_out, size_t handle_bytes);    /* >= 64 bytes */
+OV2_API ov2_status ov2_ba_comm_connect(ov2_ba_comm* comm, const void* handles, size_t handle_stride);   /* world handles, rank order */
+OV2_API ov2_status ov2_ba_comm_connect_local(ov2_ba_comm* comm, ov2_ba_comm* const* all);            /* all ranks in this process */
+OV2_API void       ov2_ba_comm_destroy(ov2_ba_comm* comm);
+OV2_API ov2_status ov2_localba_solve_p2p(ov2_ctx* ctx, ov2_ba_comm* comm, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                 ov2_ba_result* res, uint8_t* outlier_out);
+
+/* Multi-GPU localBA, callback variant (round 1; the collective is whatever the caller wires in, e.g. ncclAllReduce):
+ * landmarks (with all their observations) are
  * partitioned over ranks, every rank holds all keyframe poses.  `pb` describes THIS rank's shard
  * (ncam / pose / pose_const identical on all ranks; npts / nobs local, may be 0 observations).
  * Per LM iteration the partial reduced camera system [cost, rhs, F'r, column norms, S] is summed

@@ -413,6 +413,9 @@ def ceres_solve(pb, pose, invd, active, max_iters, huber_a, function_tolerance=1
                      + Jl * step_l[sl][:, None])
             model_cost_change = -(Jstep * (r + Jstep / 2.0)).sum()
             step_valid = model_cost_change > 0.0
+        if log is not None and not step_valid:
+            log.append(dict(ctl=True, it=iteration, x_cost=x_cost, cand_cost=0.0, mcc=model_cost_change, step2=0.0, candx2=0.0,
+                            gmax=gmax, invalid=True))
         if not step_valid:
             num_invalid += 1
             if num_invalid >= 5:
@@ -439,6 +442,11 @@ def ceres_solve(pb, pose, invd, active, max_iters, huber_a, function_tolerance=1
         # ---- ParameterToleranceReached / FunctionToleranceReached
         step_norm = np.sqrt(((pose[cam_var] - cand_pose[cam_var]) ** 2).sum() +
                             ((invd[lm_var] - cand_invd[lm_var]) ** 2).sum())
+        if log is not None:
+            # everything the trust-region controller consumes this iteration (tests/test_host_logic.py replays the device
+            # controller, csrc/ba_lm_ctl.cuh, on these records)
+            log.append(dict(ctl=True, it=iteration, x_cost=x_cost, cand_cost=cand_cost, mcc=model_cost_change, step2=step_norm ** 2,
+                            candx2=x_norm(cand_pose, cand_invd) ** 2, gmax=gmax, invalid=False))
         if step_norm <= 1e-8 * (xnorm + 1e-8):
             summ["termination"] = "CONVERGENCE"
             break

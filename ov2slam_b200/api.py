@@ -30,7 +30,8 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe", "ov2_preprocess",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
+    "ov2_ba_comm_create", "ov2_ba_comm_handle", "ov2_ba_comm_connect", "ov2_ba_comm_connect_local", "ov2_ba_comm_destroy", "ov2_localba_solve_p2p",
 ]
 
 
@@ -122,6 +123,15 @@ def load():
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
                                               ALLREDUCE_FN, vp, i32]
+    lib.ov2_localba_solve_batch.argtypes = [vp, i32, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
+    lib.ov2_localba_request_stop.argtypes = [vp, i32]
+    lib.ov2_ba_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.ov2_ba_comm_handle.argtypes = [vp, vp, sz]
+    lib.ov2_ba_comm_connect.argtypes = [vp, vp, sz]
+    lib.ov2_ba_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
+    lib.ov2_ba_comm_destroy.argtypes = [vp]
+    lib.ov2_ba_comm_destroy.restype = None
+    lib.ov2_localba_solve_p2p.argtypes = [vp, vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     _lib = lib
     return lib
 
@@ -460,7 +470,106 @@ class Optimizer:
         return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags
 
 
+def _ba_problem_struct(pb: dict, keep: dict) -> BaProblem:
+    for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px"):
+        keep[k] = np.ascontiguousarray(pb[k])
+    assert keep["pose"].dtype == np.float64 and keep["obs_px"].dtype == np.float64 and keep["lm_invdepth"].dtype == np.float64
+    assert keep["obs_cam"].dtype == np.int32 and keep["obs_lm"].dtype == np.int32 and keep["pose_const"].dtype == np.uint8
+    return BaProblem(len(keep["pose"]), len(keep["lm_invdepth"]), len(keep["obs_cam"]),
+                     *[keep[k].ctypes.data for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
+                                                     "obs_cam", "obs_lm", "obs_px")], *_stereo_ptrs(pb, keep))
+
+
+def local_ba_batch(ctx: Context, pbs: list, **opts):
+    """ov2_localba_solve_batch: K windows (dicts as Optimizer.local_ba takes) in one launch; poses / inverse depths are
+    updated in place.  Returns (list of result dicts, list of flag arrays)."""
+    o = dict(DEFAULT_BA_OPTS)
+    o.update(opts)
+    bo = BaOpts(**o)
+    n = len(pbs)
+    keeps = [dict() for _ in pbs]
+    arr = (BaProblem * n)(*[_ba_problem_struct(pb, kp) for pb, kp in zip(pbs, keeps)])
+    res = (BaResult * n)()
+    flags = [np.zeros(max(len(kp["obs_cam"]), 1), np.uint8) for kp in keeps]
+    fl = (C.c_void_p * n)(*[f.ctypes.data for f in flags])
+    ctx.check(ctx.lib.ov2_localba_solve_batch(ctx.h, n, arr, C.byref(bo), res, fl))
+    for pb, kp in zip(pbs, keeps):
+        pb["pose"][...] = kp["pose"]
+        pb["lm_invdepth"][...] = kp["lm_invdepth"]
+    return ([{f: getattr(r, f) for f, _ in BaResult._fields_} for r in res],
+            [f[:len(kp["obs_cam"])] for f, kp in zip(flags, keeps)])
+
+
+def request_stop_local_ba(ctx: Context, stop: bool = True):
+    """Optimizer::signalStopLocalBA (optimizer.cpp:2334-2343): ask the solve on `ctx` to skip the refinement."""
+    ctx.check(ctx.lib.ov2_localba_request_stop(ctx.h, 1 if stop else 0))
+
+
 # ----------------------------------------------------------------------------- multi-GPU local BA
+class BaComm:
+    """ov2_ba_comm: this rank's exchange buffer + the peers' buffers (CUDA IPC between processes, direct pointers inside
+    one process).  connect_torch() exchanges the IPC handles with torch.distributed (any backend)."""
+
+    HANDLE = 64
+
+    def __init__(self, ctx: Context, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ov2_ba_comm_create(ctx.h, rank, world, C.byref(h)))
+        self.h = h
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(self.HANDLE)
+        self.ctx.check(self.ctx.lib.ov2_ba_comm_handle(self.h, buf, self.HANDLE))
+        return buf.raw
+
+    def connect(self, handles: list):
+        assert len(handles) == self.world and all(len(x) == self.HANDLE for x in handles)
+        blob = b"".join(handles)
+        self.ctx.check(self.ctx.lib.ov2_ba_comm_connect(self.h, blob, self.HANDLE))
+
+    def connect_torch(self, dist, torch, group=None):
+        if self.world == 1:
+            return
+        mine = torch.frombuffer(bytearray(self.handle()), dtype=torch.uint8).clone()
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        mine = mine.to(dev)
+        got = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(got, mine, group=group)
+        self.connect([bytes(g.cpu().numpy().tobytes()) for g in got])
+
+    @staticmethod
+    def connect_local(comms: list):
+        arr = (C.c_void_p * len(comms))(*[c.h for c in comms])
+        for c in comms:
+            c.ctx.check(c.ctx.lib.ov2_ba_comm_connect_local(c.h, arr))
+
+    def local_ba(self, shard: dict, **opts):
+        """ov2_localba_solve_p2p on this rank's shard (collective)."""
+        o = dict(DEFAULT_BA_OPTS)
+        o.update(opts)
+        bo = BaOpts(**o)
+        keep = {}
+        p = _ba_problem_struct(shard, keep)
+        res = BaResult()
+        flags = np.zeros(max(len(keep["obs_cam"]), 1), np.uint8)
+        self.ctx.check(self.ctx.lib.ov2_localba_solve_p2p(self.ctx.h, self.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data))
+        shard["pose"][...] = keep["pose"]
+        shard["lm_invdepth"][...] = keep["lm_invdepth"]
+        return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags[:len(keep["obs_cam"])]
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.ov2_ba_comm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def partition_ba_problem(pb: dict, world: int):
     """Split a flat localBA window into `world` shards by LANDMARK (all observations of a landmark
     stay on one rank, so the per-landmark Schur elimination is local), balancing the
@@ -543,15 +652,23 @@ def local_ba_sharded(ctx: Context, shard: dict, allreduce_cb, rank: int, **opts)
 
 
 class ShardedOptimizer:
-    """Multi-GPU Optimizer::localBA (BASELINE.json configs[4]): this rank's landmark shard, poses replicated."""
+    """Multi-GPU Optimizer::localBA (BASELINE.json configs[4]): this rank's landmark shard, poses replicated.
+    mode "p2p" (default): the per-iteration sum of the reduced camera system happens inside the solve kernel over peer
+    memory (ov2_localba_solve_p2p); mode "callback": round-1 path, ncclAllReduce through torch.distributed per iteration."""
 
-    def __init__(self, ctx: Context, dist, torch, rank: int, world: int, group=None):
-        self.ctx, self.rank, self.world = ctx, rank, world
-        self._cb = make_torch_allreduce(dist, torch, group)
-        self._mode = "ncclAllReduce through the ov2_allreduce_fn callback (torch.distributed)"
+    def __init__(self, ctx: Context, dist, torch, rank: int, world: int, group=None, mode: str = "p2p"):
+        self.ctx, self.rank, self.world, self.mode = ctx, rank, world, mode
+        if mode == "p2p":
+            self.comm = BaComm(ctx, rank, world)
+            self.comm.connect_torch(dist, torch, group)
+        else:
+            self._cb = make_torch_allreduce(dist, torch, group)
 
     def local_ba(self, shard: dict, **opts):
+        if self.mode == "p2p":
+            return self.comm.local_ba(shard, **opts)
         return local_ba_sharded(self.ctx, shard, self._cb, self.rank, **opts)
 
     def describe(self) -> str:
-        return self._mode
+        return ("in-kernel sum of the partial reduced systems over NVLink peer memory (CUDA IPC), one persistent kernel per solve"
+                if self.mode == "p2p" else "ncclAllReduce through the ov2_allreduce_fn callback (torch.distributed), host LM controller")

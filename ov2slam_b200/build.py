@@ -30,6 +30,8 @@ SOURCES = {
     "frontend_sscale.cu": ["-fmad=false"],
     "frontend_step.cu": [],
     "ba_solver.cu": [],
+    "ba_lm.cu": [],
+    "ba_comm.cu": [],
     "pnp_solver.cu": [],
 }
 

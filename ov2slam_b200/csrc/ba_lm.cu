@@ -1,0 +1,1372 @@
+// L: local bundle adjustment as ONE persistent kernel per solve (float64), device-side LM controller.
+//
+// Reference behaviour replaced: the solve sections of Optimizer::localBA
+// (/root/reference/src/optimizer.cpp:436-479 robust solve, :492-594 outlier scan, :603-627 refinement,
+// :637-735 second scan), i.e. Ceres 2.0's TrustRegionMinimizer (trust_region_minimizer.cc:67-134) +
+// LevenbergMarquardtStrategy (levenberg_marquardt_strategy.cc:66-160) + Schur linear solver
+// (schur_eliminator_impl.h:179-377) on the anchored inverse-depth residual blocks
+// (src/ceres_parametrization.cpp:361-712) with SE3LeftParameterization (se3left_parametrization.hpp:41-60).
+//
+// Design (B200): a solve is launch/sync-latency bound (C3: 0.66 MB per LM iteration, all of it L2 resident), so
+// the whole two-stage solve - both Ceres solves, both outlier scans, every LM iteration - is ONE cooperative
+// launch.  A "group" of G CTAs works on one window; the phases of an LM iteration are separated by a group
+// barrier (monotonic counter in global memory, release/acquire), not by kernel boundaries:
+//
+//   A  residual blocks + analytic Jacobians at x (thread per observation, keyframe rotations staged in shared
+//      memory), cost                                                       [only when x changed]
+//   B  Schur elimination, one warp per landmark, fp64 RED into the reduced camera system
+//   B2 fold of the privatised accumulation copies (multi-GPU: the partial systems of all ranks are summed here
+//      straight out of peer memory over NVLink - no NCCL call, no host round trip)
+//   C  reduced camera system: LM damping + solve by CTA 0 (n <= 96: Gauss-Jordan in shared memory; larger:
+//      blocked Cholesky with the FP64 tensor-core trailing update), gradient projection by CTA 1
+//   D  back-substitution + candidate point + candidate cost (warp per landmark; candidate poses are computed
+//      redundantly by every CTA into shared memory)
+//   E  the trust-region controller (ba_lm_ctl.cuh) replayed by every CTA from the same reduced scalars: all CTAs
+//      take the same accept / reject / stop decision without a broadcast and without the host.
+//
+// K windows can be solved by one launch (ov2_localba_solve_batch): groups pull windows round-robin.
+#include "ov2_common.cuh"
+#include "ba_lm.cuh"
+#include "ba_lm_ctl.cuh"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace balm {
+
+// ------------------------------------------------------------------ small SE3 helpers
+__device__ __forceinline__ void quat_to_rot(const double* q, double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+__device__ __forceinline__ void load_pose(const double* p, double t[3], double q[4]) {
+    t[0] = p[0]; t[1] = p[1]; t[2] = p[2];
+    const double n = 1.0 / sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);  // SE3d(q, t) normalises
+    q[0] = p[3] * n; q[1] = p[4] * n; q[2] = p[5] * n; q[3] = p[6] * n;
+}
+
+// SE3LeftParameterization::Plus: out = Sophus::SE3d::exp(delta) * (q, t)   (sophus/se3.hpp:763-784, so3.hpp:585-620)
+__device__ __noinline__ void pose_plus(const double* pose, const double* d, double* out) {
+    double t[3], q[4];
+    load_pose(pose, t, q);
+    const double ox = d[3], oy = d[4], oz = d[5];
+    const double th2 = ox * ox + oy * oy + oz * oz;
+    double imag, real, theta;
+    if (th2 < SOPHUS_EPS * SOPHUS_EPS) {
+        theta = 0.0;
+        const double th4 = th2 * th2;
+        imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+        real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+    } else {
+        theta = sqrt(th2);
+        double sh_, ch_;
+        sincos(0.5 * theta, &sh_, &ch_);
+        imag = sh_ / theta;
+        real = ch_;
+    }
+    const double e[4] = {imag * ox, imag * oy, imag * oz, real};
+    double Re[9];
+    quat_to_rot(e, Re);
+    double V[9];
+    if (theta < SOPHUS_EPS) {
+        for (int i = 0; i < 9; ++i) V[i] = Re[i];
+    } else {
+        const double a = (1.0 - cos(theta)) / th2;
+        const double b = (theta - sin(theta)) / (th2 * theta);
+        const double O[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+        double O2[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+        for (int i = 0; i < 9; ++i) V[i] = a * O[i] + b * O2[i];
+        V[0] += 1.0; V[4] += 1.0; V[8] += 1.0;
+    }
+    const double et[3] = {V[0] * d[0] + V[1] * d[1] + V[2] * d[2], V[3] * d[0] + V[4] * d[1] + V[5] * d[2],
+                          V[6] * d[0] + V[7] * d[1] + V[8] * d[2]};
+    double r[4];   // quaternion product (so3.hpp:338-342), then normalisation
+    r[3] = e[3] * q[3] - e[0] * q[0] - e[1] * q[1] - e[2] * q[2];
+    r[0] = e[3] * q[0] + e[0] * q[3] + e[1] * q[2] - e[2] * q[1];
+    r[1] = e[3] * q[1] + e[1] * q[3] + e[2] * q[0] - e[0] * q[2];
+    r[2] = e[3] * q[2] + e[2] * q[3] + e[0] * q[1] - e[1] * q[0];
+    const double n = 1.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    out[0] = et[0] + Re[0] * t[0] + Re[1] * t[1] + Re[2] * t[2];
+    out[1] = et[1] + Re[3] * t[0] + Re[4] * t[1] + Re[5] * t[2];
+    out[2] = et[2] + Re[6] * t[0] + Re[7] * t[1] + Re[8] * t[2];
+    out[3] = r[0] * n; out[4] = r[1] * n; out[5] = r[2] * n; out[6] = r[3] * n;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+    // for non-negative doubles the bit pattern orders like an unsigned integer
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------ barriers
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Group barrier: monotonic arrival counter (zeroed by the host before the launch); barrier k completes when the
+// counter reaches k * G.  Thread 0 arrives / spins, the rest of the CTA waits at the block barrier.  The gpu-scope
+// fences publish this CTA's writes and invalidate its L1 (same construction as cooperative-groups grid.sync()).
+// A spin that lasts ~seconds means a peer died: it raises `abort` (sticky) so that every later barrier falls
+// through and the kernel drains instead of hanging the device.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long BARRIER_TIMEOUT_NS = 4000000000ull;   // 4 s: a peer CTA / rank that never arrives
+
+struct GroupBar {
+    unsigned* count; unsigned* abort; unsigned G; unsigned epoch;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (G > 1) {
+            if (threadIdx.x == 0) {
+                epoch += G;
+                __threadfence();
+                atomicAdd(count, 1u);
+                unsigned spins = 0;
+                unsigned long long t0 = 0;
+                while (ld_acquire_gpu(count) < epoch) {
+                    if ((++spins & 1023u) == 0) {
+                        if (ld_acquire_gpu(abort)) break;
+                        const unsigned long long t = global_ns();
+                        if (t0 == 0) t0 = t;
+                        else if (t - t0 > BARRIER_TIMEOUT_NS) { atomicExch(abort, 1u); break; }
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+};
+
+// ------------------------------------------------------------------ keyframe staging
+// Rwc (9) + twc (3) of every keyframe of the window in shared memory: one normalisation + quaternion-to-rotation
+// per keyframe and CTA instead of two per residual block.
+__device__ __forceinline__ void stage_cams(const Prob& P, const double* __restrict__ pose, double* s_cam) {
+    for (int c = threadIdx.x; c < P.ncam; c += blockDim.x) {
+        double t[3], q[4], R[9];
+        load_pose(pose + 7 * c, t, q);
+        quat_to_rot(q, R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_cam[12 * c + k] = R[k];
+        s_cam[12 * c + 9] = t[0]; s_cam[12 * c + 10] = t[1]; s_cam[12 * c + 11] = t[2];
+    }
+}
+
+// ------------------------------------------------------------------ residual blocks
+// One residual block (src/ceres_parametrization.cpp:361-473 left camera; :579-712 right camera, other keyframe;
+// :476-577 right camera in the anchor keyframe).  Returns the robustified cost 1/2 rho(s); writes chi2 / depth flag
+// (the mutable members the reference's outlier scan reads afterwards) and, with JAC, the corrected Jacobian rows.
+template <bool JAC>
+__device__ __forceinline__ double eval_block(const Prob& P, int i, int lm, const double* __restrict__ s_cam, double lam, int use_huber) {
+    const int ca = P.lm_anchor_cam[lm], co = P.obs_cam[i];
+    const double* Rwa = s_cam + 12 * ca; const double* ta = Rwa + 9;
+    const double* Rwc = s_cam + 12 * co; const double* to = Rwc + 9;
+    const double zanch = 1.0 / lam;
+    const double bx = (P.lm_anchor_px[2 * lm] - P.cx) / P.fx, by = (P.lm_anchor_px[2 * lm + 1] - P.cy) / P.fy;
+    const double ap[3] = {zanch * bx, zanch * by, zanch};
+    const double rp[3] = {Rwa[0] * ap[0] + Rwa[1] * ap[1] + Rwa[2] * ap[2], Rwa[3] * ap[0] + Rwa[4] * ap[1] + Rwa[5] * ap[2],
+                          Rwa[6] * ap[0] + Rwa[7] * ap[1] + Rwa[8] * ap[2]};  // Rwanch * anchpt
+    const double wp[3] = {rp[0] + ta[0], rp[1] + ta[1], rp[2] + ta[2]};
+    const double dv[3] = {wp[0] - to[0], wp[1] - to[1], wp[2] - to[2]};
+    const double lc[3] = {Rwc[0] * dv[0] + Rwc[3] * dv[1] + Rwc[6] * dv[2], Rwc[1] * dv[0] + Rwc[4] * dv[1] + Rwc[7] * dv[2],
+                          Rwc[2] * dv[0] + Rwc[5] * dv[1] + Rwc[8] * dv[2]};   // Rcw = Rwc^T
+    const int typ = P.obs_type ? (int)P.obs_type[i] : 0;
+    double cp[3] = {lc[0], lc[1], lc[2]};
+    double kfx = P.fx, kfy = P.fy, kcx = P.cx, kcy = P.cy;
+    if (typ != 0) {
+        const double* sv = typ == 2 ? ap : lc;
+        for (int k = 0; k < 3; ++k) cp[k] = P.Rrl[3 * k] * sv[0] + P.Rrl[3 * k + 1] * sv[1] + P.Rrl[3 * k + 2] * sv[2] + P.trl[k];
+        kfx = P.rfx; kfy = P.rfy; kcx = P.rcx; kcy = P.rcy;
+    }
+    const double linvz = 1.0 / cp[2];
+    const double r0 = kfx * cp[0] * linvz + kcx - P.obs_px[2 * i];
+    const double r1 = kfy * cp[1] * linvz + kcy - P.obs_px[2 * i + 1];
+    const double s = r0 * r0 + r1 * r1;
+    P.chi2[i] = s;
+    P.dpos[i] = cp[2] > 0.0 ? 1 : 0;
+    double w = 1.0, cost;
+    if (use_huber && s > P.huber_b) {
+        const double rs = sqrt(s);
+        const double rho1 = fmax(DBL_MIN, P.huber_a / rs);
+        cost = 0.5 * (2.0 * P.huber_a * rs - P.huber_b);
+        w = sqrt(rho1);
+    } else {
+        cost = 0.5 * s;
+    }
+    if (JAC) {
+        const double linvz2 = linvz * linvz;
+        const double jc[6] = {linvz * kfx, 0.0, -cp[0] * linvz2 * kfx, 0.0, linvz * kfy, -cp[1] * linvz2 * kfy};
+        // M = d(camera point)/d(world point): Rcw (left), Rrl Rcw (right, other frame), Rrl (right, anchor frame)
+        double M[9];
+        if (typ == 0) {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) M[3 * a + b] = Rwc[3 * b + a];
+        } else if (typ == 1) {
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    M[3 * a + b] = P.Rrl[3 * a] * Rwc[3 * b] + P.Rrl[3 * a + 1] * Rwc[3 * b + 1] + P.Rrl[3 * a + 2] * Rwc[3 * b + 2];
+        } else {
+            for (int k = 0; k < 9; ++k) M[k] = P.Rrl[k];
+        }
+        double JR[6];  // J_cam * M  (2x3)
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 3; ++b)
+                JR[3 * a + b] = jc[3 * a] * M[b] + jc[3 * a + 1] * M[3 + b] + jc[3 * a + 2] * M[6 + b];
+        double JS[6];  // JR * hat(wpt)
+        for (int a = 0; a < 2; ++a) {
+            const double j0 = JR[3 * a], j1 = JR[3 * a + 1], j2 = JR[3 * a + 2];
+            JS[3 * a] = j1 * wp[2] - j2 * wp[1];
+            JS[3 * a + 1] = j2 * wp[0] - j0 * wp[2];
+            JS[3 * a + 2] = j0 * wp[1] - j1 * wp[0];
+        }
+        double* Ja = P.Ja + 12 * (size_t)i;
+        double* Jo = P.Jo + 12 * (size_t)i;
+        const double wp_ = typ == 2 ? 0.0 : w;   // anchor-frame right-camera block: no pose block at all
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 3; ++b) {
+                Ja[6 * a + b] = wp_ * JR[3 * a + b];
+                Ja[6 * a + 3 + b] = -wp_ * JS[3 * a + b];
+                Jo[6 * a + b] = -wp_ * JR[3 * a + b];
+                Jo[6 * a + 3 + b] = wp_ * JS[3 * a + b];
+            }
+        // J_lambda = -zanch * Rwanch * anchpt   (type 2: -zanch * anchpt, the point never leaves the anchor frame)
+        const double* lp = typ == 2 ? ap : rp;
+        const double jl[3] = {-zanch * lp[0], -zanch * lp[1], -zanch * lp[2]};
+        P.Jl[2 * (size_t)i] = w * (JR[0] * jl[0] + JR[1] * jl[1] + JR[2] * jl[2]);
+        P.Jl[2 * (size_t)i + 1] = w * (JR[3] * jl[0] + JR[4] * jl[1] + JR[5] * jl[2]);
+        P.Jr[2 * (size_t)i] = w * r0;
+        P.Jr[2 * (size_t)i + 1] = w * r1;
+    }
+    return cost;
+}
+
+// ------------------------------------------------------------------ Schur elimination (warp / landmark)
+// schur_eliminator_impl.h:179-308 for a scalar e-block: E'E, E'r, F'F, F'r, E'F per touching keyframe, then
+// S -= (E'F)' (E'E)^-1 (E'F), rhs -= (E'F)' (E'E)^-1 E'r.  The anchor keyframe's F'F / F'r / column norms are summed
+// over the landmark's observations in registers and leave the warp once.
+__device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot,
+                                               int l, int lane, double radius, int first_iter, double* acc, int n, double* scal) {
+    const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
+    double* const cRhs = acc; double* const cG = acc + n; double* const cCn = acc + 2 * n; double* const cS = acc + 3 * n;
+    double cnl = 0.0, ge = 0.0;
+    int nact = 0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!P.active[p]) continue;
+        const double a = P.Jl[2 * (size_t)p], b = P.Jl[2 * (size_t)p + 1];
+        cnl += a * a + b * b;
+        ge += a * P.Jr[2 * (size_t)p] + b * P.Jr[2 * (size_t)p + 1];
+        nact++;
+    }
+    cnl = warp_sum(cnl);
+    ge = warp_sum(ge);
+    nact = __reduce_add_sync(FULL, nact);
+    if (nact == 0) {   // unused parameter block: dropped from the program (program.cc:305-387)
+        if (lane == 0) { P.ete[l] = 0.0; P.ge[l] = 0.0; }
+        return;
+    }
+    double sc = P.sc_lm[l];
+    if (first_iter) {
+        sc = 1.0 / (1.0 + sqrt(cnl));
+        if (lane == 0) P.sc_lm[l] = sc;
+    }
+    const double diag = fmin(fmax(cnl * sc * sc, 1e-6), 1e32);
+    const double ete = cnl + diag / (radius * sc * sc);
+    const double inv_ete = 1.0 / ete;
+    if (lane == 0) {
+        P.ete[l] = ete;
+        P.ge[l] = ge;
+        atomic_max_pos(scal + SC_GMAX_LM, fabs(ge));
+    }
+    const int sa = s_slot[P.lm_anchor_cam[l]];
+    int m = 0;   // number of E'F entries (uniform across the warp); entry 0 = anchor
+    if (sa >= 0) {
+        if (lane < 6) s_etf[lane] = 0.0;
+        if (lane == 0) s_eslot[0] = sa;
+        m = 1;
+    }
+    __syncwarp();
+    // anchor accumulators: lane owns entries e = lane and lane + 32 of the 6x6 (a = e / 6, b = e % 6, a <= b kept)
+    double aFF0 = 0.0, aFF1 = 0.0, aG = 0.0, aCn = 0.0;
+    const int e0a = lane / 6, e0b = lane - 6 * e0a;
+    const int e1 = lane + 32, e1a = e1 / 6, e1b = e1 - 6 * e1a;
+    for (int p = p0; p < p1; ++p) {
+        if (!P.active[p]) continue;
+        if (P.obs_type && P.obs_type[p] == 2) continue;   // e-block-only row (schur_eliminator_impl.h:196-217)
+        const int so = s_slot[P.obs_cam[p]];
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        const double* Jo = P.Jo + 12 * (size_t)p;
+        const double jl0 = P.Jl[2 * (size_t)p], jl1 = P.Jl[2 * (size_t)p + 1];
+        const double r0 = P.Jr[2 * (size_t)p], r1 = P.Jr[2 * (size_t)p + 1];
+        if (sa >= 0) {
+            aFF0 += Ja[e0a] * Ja[e0b] + Ja[6 + e0a] * Ja[6 + e0b];
+            if (e1 < 36) aFF1 += Ja[e1a] * Ja[e1b] + Ja[6 + e1a] * Ja[6 + e1b];
+            if (lane < 6) {
+                aG += Ja[lane] * r0 + Ja[6 + lane] * r1;
+                aCn += Ja[lane] * Ja[lane] + Ja[6 + lane] * Ja[6 + lane];
+                s_etf[lane] += jl0 * Ja[lane] + jl1 * Ja[6 + lane];
+            }
+        }
+        if (so >= 0) {
+            for (int e = lane; e < 36; e += 32) {
+                const int a = e / 6, b = e - 6 * a;
+                if (a <= b) atomicAdd(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
+            }
+            // E'F row of this keyframe: a stereo keyframe contributes two residual blocks (left and right camera) to the
+            // same pose block, so look the slot up before appending a new entry
+            int idx = -1;
+            for (int q = lane; q < m; q += 32)
+                if (s_eslot[q] == so) idx = q;
+            idx = __reduce_max_sync(FULL, idx);
+            const bool fresh = idx < 0;
+            if (fresh) idx = m;
+            if (lane < 6) {
+                atomicAdd(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
+                atomicAdd(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
+                const double e = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
+                s_etf[6 * idx + lane] = fresh ? e : s_etf[6 * idx + lane] + e;
+            }
+            if (lane == 0 && fresh) s_eslot[idx] = so;
+            if (sa >= 0) {
+                // cross block Ja' Jo into the upper block (min slot, max slot)
+                for (int e = lane; e < 36; e += 32) {
+                    const int a = e / 6, b = e - 6 * a;   // a: anchor column, b: observer column
+                    const double v = Ja[a] * Jo[b] + Ja[6 + a] * Jo[6 + b];
+                    if (sa < so) atomicAdd(cS + (size_t)(6 * sa + a) * n + 6 * so + b, v);
+                    else atomicAdd(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
+                }
+            }
+            if (fresh) m++;
+        }
+        __syncwarp();
+    }
+    if (sa >= 0) {
+        if (e0a <= e0b) atomicAdd(cS + (size_t)(6 * sa + e0a) * n + 6 * sa + e0b, aFF0);
+        if (e1 < 36 && e1a <= e1b) atomicAdd(cS + (size_t)(6 * sa + e1a) * n + 6 * sa + e1b, aFF1);
+        if (lane < 6) { atomicAdd(cG + 6 * sa + lane, aG); atomicAdd(cCn + 6 * sa + lane, aCn); }
+    }
+    // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i -= EtF_i ge / ete
+    const int npair = m * m;
+    for (int e = lane; e < npair * 36; e += 32) {
+        const int pr = e / 36, q = e - 36 * pr;
+        const int i = pr / m, j = pr - m * i;
+        const int si = s_eslot[i], sj = s_eslot[j];
+        if (si > sj || (si == sj && i > j)) continue;   // upper block triangle; (i,i) once
+        const int a = q / 6, b = q - 6 * a;
+        if (si == sj && a > b) continue;
+        const double v = s_etf[6 * i + a] * s_etf[6 * j + b] * inv_ete;   // slots are unique in the list
+        atomicAdd(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
+    }
+    for (int e = lane; e < m * 6; e += 32) {
+        const int i = e / 6, a = e - 6 * i;
+        atomicAdd(cRhs + 6 * s_eslot[i] + a, -s_etf[6 * i + a] * ge * inv_ete);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ reduced camera system, n <= 96: CTA-wide Gauss-Jordan in shared memory
+// Augmented system [S + D | b] in shared memory (row pitch n + 2, odd multiple keeps column reads conflict-light);
+// pivot step j updates every row r != j for the columns c > j: A[r][c] -= (A[r][j] / A[j][j]) A[j][c].  Row j and
+// column j are not written in step j, so ONE block barrier per pivot suffices and no substitution passes follow
+// (a Cholesky + two triangular solves is 3n dependent steps).  Pivots equal those of the LDL' / Cholesky
+// factorisation (no pivoting: S is SPD after LM damping), so "pivot <= 0" is the failure test Ceres' LLT applies.
+__device__ void reduced_solve_small(const Prob& P, double* T, int n, double radius, int first_iter, double* sA, double* scal) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int PIT = n + 2;
+    double* cRhs = T; double* cG = T + n; double* cCn = T + 2 * n; double* cS = T + 3 * n;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    for (int e = tid; e < n * n; e += nt) {
+        const int r = e / n, c = e - r * n;
+        sA[r * PIT + c] = r <= c ? cS[(size_t)r * n + c] : cS[(size_t)c * n + r];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const double cn = cCn[i];
+        double sc = P.sc_cam[i];
+        if (first_iter) {
+            sc = 1.0 / (1.0 + sqrt(cn));
+            P.sc_cam[i] = sc;
+        }
+        const double diag = fmin(fmax(cn * sc * sc, 1e-6), 1e32);
+        sA[i * PIT + i] += diag / (radius * sc * sc);
+        sA[i * PIT + n] = cG[i] + cRhs[i];
+    }
+    __syncthreads();
+    // thread -> (row group, column phase): TPR threads per row
+    const int TPR = nt / n >= 4 ? 4 : (nt / n >= 2 ? 2 : 1);
+    const int rows_per_pass = nt / TPR;
+    for (int j = 0; j < n; ++j) {
+        const double p = sA[j * PIT + j];
+        if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same pivot
+        double ip = (double)__frcp_rn((float)p);
+        ip = ip * (2.0 - p * ip);
+        ip = ip * (2.0 - p * ip);
+        const int sub = tid % TPR;
+        for (int r = tid / TPR; r < n; r += rows_per_pass) {
+            if (r == j) continue;
+            const double f = sA[r * PIT + j] * ip;
+            for (int c = j + 1 + sub; c <= n; c += TPR) sA[r * PIT + c] -= f * sA[j * PIT + c];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (tid == 0) scal[SC_CHOL_FAIL] = 1.0;
+        return;
+    }
+    for (int i = tid; i < n; i += nt) P.z[i] = sA[i * PIT + n] / sA[i * PIT + i];
+}
+
+// ------------------------------------------------------------------ reduced camera system, n > 96: blocked Cholesky (one CTA)
+// FP64 tensor-core tile product (DMMA): D(8x8) = A(8x4) B(4x8) + C.  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+// lane = 4 g + t; A: (row g, col t); B: (row t, col g); C/D: (row g, cols 2t, 2t+1).
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Blocked right-looking Cholesky S = U'U (upper triangle, in global/L2), block 32, on the augmented system [S | b]:
+// (1) warp 0 factors the 32 x 32 diagonal block in shared memory; (2) one thread per trailing column solves
+// U11' x = a (row panel U12, and y for b); (3) A22 -= U12' U12 on the FP64 tensor cores (DMMA), operands staged in
+// shared memory; then the backward substitution block by block.
+__device__ void reduced_solve_blocked(const Prob& P, double* T, int n, double radius, int first_iter, double* sP, double* scal) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* cRhs = T; double* cG = T + n; double* cCn = T + 2 * n; double* A = T + 3 * n;
+    __shared__ int s_fail;
+    __shared__ double s_w[MAX_N];
+    __shared__ double sU[CH_NB][CH_NB + 1];
+    __shared__ double s_idiag_all[MAX_N + CH_NB];
+    __shared__ double s_t[CH_NB];
+    double* w = s_w;
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < n; i += nt) {
+        const double cn = cCn[i];
+        double sc = P.sc_cam[i];
+        if (first_iter) {
+            sc = 1.0 / (1.0 + sqrt(cn));
+            P.sc_cam[i] = sc;
+        }
+        const double diag = fmin(fmax(cn * sc * sc, 1e-6), 1e32);
+        A[(size_t)i * n + i] += diag / (radius * sc * sc);
+        w[i] = cG[i] + cRhs[i];
+    }
+    __syncthreads();
+    const int PW = ((n + 15) & ~15) + 8;                 // sP row pitch (doubles): bank-spread for the fragment loads
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+    for (int kb = 0; kb < n; kb += CH_NB) {
+        const int nb = min(CH_NB, n - kb), c1 = kb + nb, m = n - c1;
+        double* s_idiag = s_idiag_all + kb;
+        for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+            const int i = e >> 5, j = e & 31;
+            sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            bool bad = false;
+            for (int j = 0; j < CH_NB; ++j) {
+                const double d = sU[j][j];
+                // pivots of the Jacobi-scaled, damped system are O(1); outside the float range the factorisation is
+                // reported as failed (Ceres' LLT would return a useless step there)
+                bad = bad || !(d > 1e-30) || !(d < 1e30);
+                double is = (double)rsqrtf((float)d);                    // MUFU seed + 2 Newton steps in double
+                is = is * (1.5 - 0.5 * d * is * is);
+                is = is * (1.5 - 0.5 * d * is * is);
+                const double ujc = lane >= j ? sU[j][lane] * is : 0.0;   // row j of U (diagonal: d / sqrt(d))
+                __syncwarp();
+                sU[j][lane] = ujc;
+                if (lane == j) s_idiag[j] = is;
+                __syncwarp();
+#pragma unroll 4
+                for (int r = j + 1; r < CH_NB; ++r)
+                    if (lane >= r) sU[r][lane] -= sU[j][r] * ujc;
+                __syncwarp();
+            }
+            if (bad && lane == 0) s_fail = 1;
+        }
+        __syncthreads();
+        if (s_fail) break;                                               // uniform
+        for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+            const int i = e >> 5, j = e & 31;
+            if (i < nb && j < nb && i <= j) A[(size_t)(kb + i) * n + kb + j] = sU[i][j];
+        }
+        const int m16 = (m + 15) & ~15;
+        for (int cc = tid; cc <= m16; cc += nt) {
+            if (cc >= m && cc < m16) {                                   // zero padding of the operand panel
+#pragma unroll
+                for (int i = 0; i < CH_NB; ++i) sP[i * PW + cc] = 0.0;
+                continue;
+            }
+            const bool is_rhs = cc == m16;
+            if (!is_rhs && cc >= m) continue;
+            double a[CH_NB];
+#pragma unroll
+            for (int i = 0; i < CH_NB; ++i)
+                a[i] = i < nb ? (is_rhs ? w[kb + i] : A[(size_t)(kb + i) * n + c1 + cc]) : 0.0;
+#pragma unroll
+            for (int k = 0; k < CH_NB; ++k) {
+                const double x = a[k] * s_idiag[k];
+                a[k] = x;
+#pragma unroll
+                for (int i = k + 1; i < CH_NB; ++i) a[i] -= sU[k][i] * x;
+            }
+            if (is_rhs) {
+#pragma unroll
+                for (int i = 0; i < CH_NB; ++i) if (i < nb) { w[kb + i] = a[i]; s_t[i] = a[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < CH_NB; ++i) {
+                    sP[i * PW + cc] = a[i];
+                    if (i < nb) A[(size_t)(kb + i) * n + c1 + cc] = a[i];
+                }
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < m; r += nt) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < CH_NB; ++k) acc += sP[k * PW + r] * s_t[k];
+            w[c1 + r] -= acc;
+        }
+        {
+            const int mt = m16 >> 4, g = lane >> 2, t = lane & 3;
+            for (int idx = warp; idx < mt * mt; idx += nwarp) {
+                const int tr = idx / mt, tc = idx - tr * mt;
+                if (tr > tc) continue;
+                const int r0 = tr * 16, q0 = tc * 16;
+                double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+                for (int k0 = 0; k0 < CH_NB; k0 += 4) {
+                    const double* pk = sP + (k0 + t) * PW;
+                    const double a0 = pk[r0 + g], a1 = pk[r0 + 8 + g];
+                    const double b0 = pk[q0 + g], b1 = pk[q0 + 8 + g];
+                    dmma_884(acc[0][0][0], acc[0][0][1], a0, b0);
+                    dmma_884(acc[0][1][0], acc[0][1][1], a0, b1);
+                    dmma_884(acc[1][0][0], acc[1][0][1], a1, b0);
+                    dmma_884(acc[1][1][0], acc[1][1][1], a1, b1);
+                }
+#pragma unroll
+                for (int hi = 0; hi < 2; ++hi)
+#pragma unroll
+                    for (int hj = 0; hj < 2; ++hj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = r0 + 8 * hi + g, c = q0 + 8 * hj + 2 * t + e;
+                            if (r <= c && c < m) A[(size_t)(c1 + r) * n + c1 + c] -= acc[hi][hj][e];
+                        }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (tid == 0) scal[SC_CHOL_FAIL] = 1.0;
+        return;
+    }
+    for (int kb = ((n - 1) / CH_NB) * CH_NB; kb >= 0; kb -= CH_NB) {
+        const int nb = min(CH_NB, n - kb), c1 = kb + nb;
+        for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+            const int i = e >> 5, j = e & 31;
+            sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
+        }
+        for (int i = warp; i < nb; i += nwarp) {                         // t_i = y_i - U12[i][:] z_rest
+            double acc = 0.0;
+            for (int c = c1 + lane; c < n; c += 32) acc += A[(size_t)(kb + i) * n + c] * w[c];
+            acc = warp_sum(acc);
+            if (lane == 0) s_t[i] = w[kb + i] - acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double ti = lane < nb ? s_t[lane] : 0.0;
+            const double idg = lane < nb ? s_idiag_all[kb + lane] : 1.0;
+#pragma unroll
+            for (int j = CH_NB - 1; j >= 0; --j) {
+                const double zj = __shfl_sync(FULL, ti * idg, j);
+                if (lane < j) ti -= sU[lane][j] * zj;
+                if (lane == j && j < nb) w[kb + j] = zj;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) P.z[i] = w[i];
+}
+
+// ------------------------------------------------------------------ back-substitution + candidate cost (warp / landmark)
+// schur_eliminator_impl.h:311-377: y_e = (E'E)^-1 (E'r - sum_k (E'F_k) z_k); model cost change
+// -(J delta)'(r + J delta / 2) (trust_region_minimizer.cc:424-427); candidate inverse depth; then the residual blocks of
+// the landmark at the candidate point (cost only).
+__device__ __forceinline__ void backsub_landmark(const Prob& P, const int* __restrict__ s_slot, const double* __restrict__ s_cam,
+                                                 int l, int lane, const double* __restrict__ invd, double* __restrict__ cand_invd,
+                                                 int use_huber, double& mcc_out, double& st2_out, double& cx2_out, double& cost_out) {
+    const double ete = P.ete[l];
+    if (ete == 0.0) return;   // landmark not in the program: candidate stays equal
+    const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
+    const int sa = s_slot[P.lm_anchor_cam[l]];
+    double za[6] = {0, 0, 0, 0, 0, 0};
+    if (sa >= 0)
+        for (int k = 0; k < 6; ++k) za[k] = P.z[6 * sa + k];
+    double acc = 0.0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!P.active[p]) continue;
+        const int so = (P.obs_type && P.obs_type[p] == 2) ? -1 : s_slot[P.obs_cam[p]];
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        const double* Jo = P.Jo + 12 * (size_t)p;
+        double f0 = 0.0, f1 = 0.0;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 += Ja[k] * za[k]; f1 += Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = P.z[6 * so + k]; f0 += Jo[k] * zk; f1 += Jo[6 + k] * zk; }
+        acc += P.Jl[2 * (size_t)p] * f0 + P.Jl[2 * (size_t)p + 1] * f1;
+    }
+    acc = warp_sum(acc);
+    const double y = (P.ge[l] - acc) / ete;
+    const double dl = -y;
+    const double cl = invd[l] + dl;
+    double mcc = 0.0, cost = 0.0;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        if (!P.active[p]) continue;
+        const int so = (P.obs_type && P.obs_type[p] == 2) ? -1 : s_slot[P.obs_cam[p]];
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        const double* Jo = P.Jo + 12 * (size_t)p;
+        double f0 = P.Jl[2 * (size_t)p] * dl, f1 = P.Jl[2 * (size_t)p + 1] * dl;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 -= Ja[k] * za[k]; f1 -= Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = P.z[6 * so + k]; f0 -= Jo[k] * zk; f1 -= Jo[6 + k] * zk; }
+        mcc -= f0 * (P.Jr[2 * (size_t)p] + 0.5 * f0) + f1 * (P.Jr[2 * (size_t)p + 1] + 0.5 * f1);
+        cost += eval_block<false>(P, p, l, s_cam, cl, use_huber);
+    }
+    if (lane == 0) {
+        cand_invd[l] = cl;
+        st2_out += dl * dl;
+        cx2_out += cl * cl;
+    }
+    mcc_out += mcc;
+    cost_out += cost;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange (peer memory over NVLink)
+// Every rank exports one buffer (see ba_lm.cuh); xsync() is a barrier between the ranks' kernels: CTA 0 / thread 0
+// writes its epoch into slot `rank` of every peer's flag array (release, system scope) and waits until every peer
+// has written the same epoch into ours.  Must be bracketed by group barriers.
+__device__ __forceinline__ void xsync(const Peers& X, unsigned long long& xepoch, unsigned* abort) {
+    xepoch++;
+    __threadfence_system();
+    for (int r = 0; r < X.world; ++r)
+        if (r != X.rank) st_release_sys(reinterpret_cast<unsigned long long*>(X.base[r]) + X.rank, xepoch);
+    for (int r = 0; r < X.world; ++r) {
+        if (r == X.rank) continue;
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(X.base[X.rank]) + r;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (ld_acquire_sys(f) < xepoch) {
+            if ((++spins & 255u) == 0) {
+                if (ld_acquire_gpu(abort)) break;
+                const unsigned long long t = global_ns();
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 2 * BARRIER_TIMEOUT_NS) { atomicExch(abort, 1u); break; }
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+__device__ __forceinline__ double ld_peer(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ------------------------------------------------------------------ the persistent solve kernel
+struct SolveOut { int iterations; double initial_cost, final_cost; int termination; };
+
+__global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restrict__ probs, int nprob, int G, Peers X) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ lmctl::State S;
+    __shared__ int s_action, s_ncv, s_any, s_refine, s_trivial;
+    __shared__ double s_red[WARPS][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = blockIdx.x / G, bid = blockIdx.x - group * G, ngroups = gridDim.x / G;
+    if (group >= ngroups) return;
+    unsigned long long xepoch = X.epoch0;
+    __shared__ Prob sProb;
+    for (int pi = group; pi < nprob; pi += ngroups) {
+        __syncthreads();
+        for (int i = tid; i < (int)(sizeof(Prob) / sizeof(int)); i += THREADS)
+            reinterpret_cast<int*>(&sProb)[i] = reinterpret_cast<const int*>(probs + pi)[i];
+        __syncthreads();
+        const Prob& P = sProb;
+        GroupBar bar{P.bar, P.bar + 1, (unsigned)G, 0u};
+        // shared memory carve-up
+        double* s_cam = reinterpret_cast<double*>(smem_raw);                       // [ncam][12]
+        int* s_slot = reinterpret_cast<int*>(s_cam + 12 * (size_t)P.ncam);         // [ncam]
+        double* s_work = reinterpret_cast<double*>(smem_raw + P.smem_work_off);    // Schur scratch / solve area (union)
+        const int etf_stride = 6 * (P.ncv_max + 1);
+        double* s_etf = s_work + (size_t)warp * etf_stride;
+        int* s_eslot = reinterpret_cast<int*>(s_work + (size_t)WARPS * etf_stride) + warp * (P.ncv_max + 1);
+        const int gthreads = G * THREADS, gtid = bid * THREADS + tid;
+        const int gwarps = G * WARPS, gwarp = bid * WARPS + warp;
+        const size_t blk = P.blk;                                                  // doubles per accumulation copy (n_max based)
+        int xi = 0;                                                                // index of the buffer holding x
+        int use_huber = P.use_robust;
+        int n_out1 = 0, n_out2 = 0;
+        SolveOut so[2];
+        so[0] = SolveOut{0, 0.0, 0.0, 0};
+        so[1] = SolveOut{0, 0.0, 0.0, 0};
+        int ran_refine = 0;
+        for (int stage = 0; stage < 2; ++stage) {
+            const int max_iters = stage == 0 ? P.max_it1 : P.max_it2;
+            uint8_t* cam_used = P.cam_used + (size_t)stage * P.ncam;
+            double* x_pose = P.pose[xi]; double* c_pose = P.pose[xi ^ 1];
+            double* x_invd = P.invd[xi]; double* c_invd = P.invd[xi ^ 1];
+            // ---- set-up: Program::RemoveFixedBlocks (keyframes that are constant or touch no active residual drop out),
+            //      candidate := x for the blocks that are not in this solve's program, accumulators zeroed
+            for (int i = gtid; i < P.nobs; i += gthreads)
+                if (P.active[i] && !(P.obs_type && P.obs_type[i] == 2)) {
+                    cam_used[P.obs_cam[i]] = 1;
+                    cam_used[P.lm_anchor_cam[P.obs_lm[i]]] = 1;
+                }
+            for (int i = gtid; i < 7 * P.ncam; i += gthreads) c_pose[i] = x_pose[i];
+            for (int i = gtid; i < P.npts; i += gthreads) c_invd[i] = x_invd[i];
+            for (size_t i = gtid; i < (size_t)P.ncopy * blk; i += gthreads) P.acc[i] = 0.0;
+            for (int i = gtid; i < 2 * SC_COUNT; i += gthreads) P.scal[i] = 0.0;
+            bar.sync();
+            if (X.world > 1) {
+                // a keyframe is in the program if ANY rank has an active residual touching it
+                uint8_t* mine = reinterpret_cast<uint8_t*>(X.base[X.rank]) + XB_CAMUSED + (size_t)stage * MAX_CAMS;
+                for (int i = gtid; i < P.ncam; i += gthreads) mine[i] = cam_used[i];
+                bar.sync();
+                if (bid == 0 && tid == 0) xsync(X, xepoch, P.bar + 1);
+                bar.sync();
+                for (int c = tid; c < P.ncam; c += THREADS) {
+                    int u = 0;
+                    for (int r = 0; r < X.world; ++r)
+                        u |= *reinterpret_cast<volatile const uint8_t*>(reinterpret_cast<const uint8_t*>(X.base[r]) + XB_CAMUSED + (size_t)stage * MAX_CAMS + c);
+                    s_slot[c] = (u ? 1 : 0) | (P.pose_const[c] ? 2 : 0);          // temporarily: used / constant flags
+                }
+            } else {
+                for (int c = tid; c < P.ncam; c += THREADS) s_slot[c] = (cam_used[c] ? 1 : 0) | (P.pose_const[c] ? 2 : 0);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int ncv = 0, any = 0;
+                for (int c = 0; c < P.ncam; ++c) {
+                    const int u = s_slot[c];
+                    any |= u & 1;
+                    s_slot[c] = u == 1 ? ncv++ : -1;
+                }
+                s_ncv = ncv; s_any = any;
+                lmctl::init(S);
+            }
+            __syncthreads();
+            const int ncv = s_ncv, n = 6 * ncv;
+            if (!s_any) { if (stage == 0) break; else continue; }   // no residual blocks (on any rank)
+            if (bid == 0)
+                for (int c = tid; c < P.ncam; c += THREADS) P.cam_slot[c] = s_slot[c];
+            double* T = (P.ncopy > 1 || X.world > 1) ? P.total : P.acc;      // the system the solve reads
+            // ---- LM iterations
+            for (;;) {
+                if (tid == 0) s_action = lmctl::begin_iteration(S, max_iters) ? 1 : 0;
+                __syncthreads();
+                if (!s_action) break;
+                const int par = S.iteration & 1, first_iter = S.first_iter, x_is_new = S.x_is_new;
+                const double radius = S.radius;
+                double* scal = P.scal + par * SC_COUNT;
+                // ---- A: residual blocks + Jacobians at x
+                if (x_is_new) {
+                    stage_cams(P, x_pose, s_cam);
+                    __syncthreads();
+                    double cost = 0.0;
+                    for (int i = gtid; i < P.nobs; i += gthreads)
+                        if (P.active[i]) cost += eval_block<true>(P, i, P.obs_lm[i], s_cam, x_invd[P.obs_lm[i]], use_huber);
+                    cost = warp_sum(cost);
+                    if (lane == 0 && cost != 0.0) atomicAdd(scal + SC_COST, cost);
+                }
+                bar.sync();
+                // ---- B: Schur elimination into this CTA's accumulation copy
+                {
+                    double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, l, lane, radius, first_iter, acc, n, scal);
+                }
+                bar.sync();
+                // ---- B2: fold the copies; multi-GPU: sum the ranks' partial systems out of peer memory
+                const int live = 3 * n + n * n;
+                if (X.world > 1) {
+                    double* mine = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(X.base[X.rank]) + XB_PARTIAL) + (size_t)par * (SC_COUNT + blk);
+                    for (int e = gtid; e < live; e += gthreads) {
+                        double a = P.acc[e];
+                        for (int k = 1; k < P.ncopy; ++k) a += P.acc[e + (size_t)k * blk];
+                        mine[SC_COUNT + e] = a;
+                    }
+                    if (gtid < SC_COUNT) mine[gtid] = scal[gtid];
+                    bar.sync();
+                    if (bid == 0 && tid == 0) xsync(X, xepoch, P.bar + 1);
+                    bar.sync();
+                    for (int e = gtid; e < live; e += gthreads) {
+                        double a = 0.0;
+                        for (int r = 0; r < X.world; ++r)
+                            a += ld_peer(reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(X.base[r]) + XB_PARTIAL) + (size_t)par * (SC_COUNT + blk) + SC_COUNT + e);
+                        T[e] = a;
+                    }
+                    if (gtid == 0) {
+                        double c = 0.0, g = 0.0;
+                        for (int r = 0; r < X.world; ++r) {
+                            const double* pr = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(X.base[r]) + XB_PARTIAL) + (size_t)par * (SC_COUNT + blk);
+                            c += ld_peer(pr + SC_COST);
+                            g = fmax(g, ld_peer(pr + SC_GMAX_LM));
+                        }
+                        scal[SC_COST] = c;        // the whole window's cost / gradient bound, identical on every rank
+                        scal[SC_GMAX_LM] = g;
+                    }
+                    bar.sync();
+                } else if (P.ncopy > 1) {
+                    for (int e = gtid; e < live; e += gthreads) {
+                        double a = P.acc[e];
+                        for (int k = 1; k < P.ncopy; ++k) a += P.acc[e + (size_t)k * blk];
+                        T[e] = a;
+                    }
+                    bar.sync();
+                }
+                // ---- C: reduced camera system (CTA 0); gradient projection |x - Plus(x, -g)|_inf (last CTA); the other
+                //      CTAs clear the accumulation copies for the next iteration (T is separate whenever ncopy > 1)
+                if (bid == 0) {
+                    if (n > 0) {
+                        if (P.solve_blocked) reduced_solve_blocked(P, T, n, radius, first_iter, s_work, scal);
+                        else reduced_solve_small(P, T, n, radius, first_iter, s_work, scal);
+                    }
+                }
+                if (bid == G - 1 && x_is_new && n > 0) {
+                    if (bid == 0) __syncthreads();
+                    double gm = 0.0;
+                    for (int c = tid; c < P.ncam; c += THREADS) {
+                        const int s = s_slot[c];
+                        if (s < 0) continue;
+                        double d[6], out[7];
+                        for (int k = 0; k < 6; ++k) d[k] = -T[n + 6 * s + k];
+                        pose_plus(x_pose + 7 * c, d, out);
+                        for (int k = 0; k < 7; ++k) gm = fmax(gm, fabs(x_pose[7 * c + k] - out[k]));
+                    }
+                    gm = warp_max(gm);
+                    if (lane == 0) atomic_max_pos(scal + SC_GMAX_CAM, gm);
+                }
+                bar.sync();
+                // ---- D: candidate keyframe poses (every CTA, into shared memory), back-substitution, candidate cost
+                {
+                    double st2 = 0.0, cx2 = 0.0;
+                    for (int c = tid; c < P.ncam; c += THREADS) {
+                        const int s = s_slot[c];
+                        double out[7];
+                        if (s >= 0) {
+                            double d[6];
+                            for (int k = 0; k < 6; ++k) d[k] = -P.z[6 * s + k];
+                            pose_plus(x_pose + 7 * c, d, out);
+                            for (int k = 0; k < 7; ++k) {
+                                const double df = x_pose[7 * c + k] - out[k];
+                                st2 += df * df; cx2 += out[k] * out[k];
+                            }
+                            if (bid == 0)
+                                for (int k = 0; k < 7; ++k) c_pose[7 * c + k] = out[k];
+                        } else {
+                            for (int k = 0; k < 7; ++k) out[k] = x_pose[7 * c + k];
+                        }
+                        double t[3], q[4], R[9];
+                        load_pose(out, t, q);
+                        quat_to_rot(q, R);
+                        for (int k = 0; k < 9; ++k) s_cam[12 * c + k] = R[k];
+                        s_cam[12 * c + 9] = t[0]; s_cam[12 * c + 10] = t[1]; s_cam[12 * c + 11] = t[2];
+                    }
+                    __syncthreads();
+                    double mcc = 0.0, cost = 0.0, lst2 = 0.0, lcx2 = 0.0;
+                    for (int l = gwarp; l < P.npts; l += gwarps)
+                        backsub_landmark(P, s_slot, s_cam, l, lane, x_invd, c_invd, use_huber, mcc, lst2, lcx2, cost);
+                    // the keyframe part of the norms counts once per window (rank 0, CTA 0)
+                    if (bid == 0 && X.rank == 0) { lst2 += st2; lcx2 += cx2; }
+                    mcc = warp_sum(mcc); cost = warp_sum(cost); lst2 = warp_sum(lst2); lcx2 = warp_sum(lcx2);
+                    if (lane == 0) { s_red[warp][0] = cost; s_red[warp][1] = mcc; s_red[warp][2] = lst2; s_red[warp][3] = lcx2; }
+                    __syncthreads();
+                    if (tid < 4) {
+                        double a = 0.0;
+                        for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][tid];
+                        if (a != 0.0) atomicAdd(scal + SC_CAND_COST + tid, a);
+                    }
+                    // clear for the next iteration: accumulation copies and the other parity's scalars
+                    for (size_t i = gtid; i < (size_t)P.ncopy * blk; i += gthreads) P.acc[i] = 0.0;
+                    double* oscal = P.scal + (par ^ 1) * SC_COUNT;
+                    if (gtid < SC_COUNT) oscal[gtid] = 0.0;
+                }
+                bar.sync();
+                if (X.world > 1) {
+                    // second, tiny exchange: candidate cost, model cost change, step / candidate norms (rank order sum)
+                    double* mine = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(X.base[X.rank]) + XB_SC4) + par * 8;
+                    if (gtid < 4) mine[gtid] = scal[SC_CAND_COST + gtid];
+                    bar.sync();
+                    if (bid == 0 && tid == 0) xsync(X, xepoch, P.bar + 1);
+                    bar.sync();
+                }
+                // ---- E: trust-region controller, replayed by every CTA
+                if (tid == 0) {
+                    double v[4];
+                    if (X.world > 1) {
+                        for (int k = 0; k < 4; ++k) {
+                            double a = 0.0;
+                            for (int r = 0; r < X.world; ++r)
+                                a += ld_peer(reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(X.base[r]) + XB_SC4) + par * 8 + k);
+                            v[k] = a;
+                        }
+                    } else {
+                        for (int k = 0; k < 4; ++k) v[k] = scal[SC_CAND_COST + k];
+                    }
+                    const double gmax = fmax(scal[SC_GMAX_LM], scal[SC_GMAX_CAM]);
+                    s_action = (int)lmctl::end_iteration(S, scal[SC_COST], v[0], v[1], v[2], v[3], gmax, scal[SC_CHOL_FAIL] != 0.0, P.ftol);
+                }
+                __syncthreads();
+                const int action = s_action;
+                if (action == lmctl::ACT_CONTINUE_ACCEPTED) {
+                    xi ^= 1;
+                    x_pose = P.pose[xi]; c_pose = P.pose[xi ^ 1];
+                    x_invd = P.invd[xi]; c_invd = P.invd[xi ^ 1];
+                }
+                if (action == lmctl::ACT_STOP) break;
+            }
+            so[stage].iterations = S.iteration;
+            so[stage].initial_cost = S.initial_cost;
+            so[stage].final_cost = lmctl::final_cost(S);
+            so[stage].termination = S.termination;
+            if (stage == 1) ran_refine = 1;
+            // a stop while a candidate was pending leaves buffers unequal for out-of-program blocks only at the
+            // next set-up (which copies x over the candidate), so nothing to repair here
+            bar.sync();
+            // ---- outlier scan on the values the LAST evaluation left behind (optimizer.cpp:500-530, :637-735)
+            {
+                double* cnt = P.counts + 4 * stage;
+                const int bit = stage == 0 ? 1 : 2;
+                const int deact = stage == 0 && P.apply_l2;
+                int bad_t = 0, left_t = 0, right_t = 0;
+                for (int i = gtid; i < P.nobs; i += gthreads) {
+                    if (!P.active[i]) continue;
+                    const bool bad = (P.chi2[i] > (double)P.th_f) || !P.dpos[i];
+                    if (bad) {
+                        P.flags[i] |= (uint8_t)bit;
+                        if (deact) P.active[i] = 0;   // problem.RemoveResidualBlock
+                        bad_t++;
+                    } else {
+                        const int typ = P.obs_type ? (int)P.obs_type[i] : 0;
+                        left_t += typ == 0;
+                        right_t += typ == 1;
+                    }
+                }
+                bad_t = __reduce_add_sync(FULL, bad_t); left_t = __reduce_add_sync(FULL, left_t); right_t = __reduce_add_sync(FULL, right_t);
+                if (lane == 0) {
+                    if (bad_t) atomicAdd(cnt + 0, (double)bad_t);
+                    if (left_t) atomicAdd(cnt + 1, (double)left_t);
+                    if (right_t) atomicAdd(cnt + 2, (double)right_t);
+                }
+                bar.sync();
+                if (stage == 0) {
+                    double nbad = cnt[0], nleft = cnt[1], nright = cnt[2];
+                    n_out1 = (int)nbad;
+                    if (X.world > 1) {
+                        // every rank must take the same branch: counts summed over the ranks
+                        double* mine = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(X.base[X.rank]) + XB_SC4) + 16;
+                        if (gtid < 3) mine[gtid] = cnt[gtid];
+                        bar.sync();
+                        if (bid == 0 && tid == 0) xsync(X, xepoch, P.bar + 1);
+                        bar.sync();
+                        nbad = nleft = nright = 0.0;
+                        for (int r = 0; r < X.world; ++r) {
+                            const double* pr = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(X.base[r]) + XB_SC4) + 16;
+                            nbad += ld_peer(pr); nleft += ld_peer(pr + 1); nright += ld_peer(pr + 2);
+                        }
+                    }
+                    // solve #2 only if residual blocks were removed and no stop was requested meanwhile (optimizer.cpp:603-604)
+                    int refine = P.apply_l2 && P.use_robust && nbad > 0.0;
+                    if (refine && P.stop_flag && *reinterpret_cast<volatile const int*>(P.stop_flag) != 0) refine = 0;
+                    if (X.world > 1 && P.stop_flag) refine = refine;   // (sharded callers pass no stop flag: ranks could disagree)
+                    // mono windows keep the Huber loss in the refinement; the wrapper is reset to the trivial loss only when
+                    // left-camera and other-frame right-camera residual lists are both non-empty (optimizer.cpp:606-608)
+                    int trivial = P.refine_loss;
+                    if (trivial < 0) trivial = (nleft > 0.0 && nright > 0.0) ? 1 : 0;
+                    if (tid == 0) { s_refine = refine; s_trivial = trivial; }
+                    __syncthreads();
+                    if (!s_refine) break;
+                    use_huber = s_trivial ? 0 : 1;
+                } else {
+                    n_out2 = (int)cnt[0];
+                }
+            }
+        }
+        // ---- write-back: x into buffer 0, result record
+        bar.sync();
+        if (xi == 1) {
+            for (int i = gtid; i < 7 * P.ncam; i += gthreads) P.pose[0][i] = P.pose[1][i];
+            for (int i = gtid; i < P.npts; i += gthreads) P.invd[0][i] = P.invd[1][i];
+        }
+        if (bid == 0 && tid == 0) {
+            Result* R = P.result;
+            R->iters_robust = so[0].iterations;
+            R->iters_refine = ran_refine ? so[1].iterations : 0;
+            const SolveOut& last = ran_refine ? so[1] : so[0];
+            R->initial_cost = last.initial_cost;
+            R->final_cost = last.final_cost;
+            R->termination = last.termination;
+            R->n_outliers_first = n_out1;
+            R->n_outliers_second = n_out2;
+            R->aborted = (int)ld_acquire_gpu(P.bar + 1);
+        }
+    }
+}
+
+}  // namespace balm
+
+// ====================================================================== host side
+using namespace balm;
+
+namespace {
+
+struct HostPlan {
+    size_t off_prob, off_pose, off_invd, off_apx, off_opx, off_lac, off_oc, off_ol, off_lp, off_pc, off_ty, in_bytes;   // uploaded block
+    // device-only work areas (offsets into the work block)
+    size_t w_pose1, w_invd1, w_active, w_flags, w_camused, w_camslot, w_Jr, w_Ja, w_Jo, w_Jl, w_chi2, w_dpos, w_sclm, w_ete, w_ge,
+           w_acc, w_total, w_scal, w_z, w_sccam, w_counts, w_bar, w_result, work_bytes, zero_off, zero_bytes;
+    int ncv_max, n_max, ncopy, solve_blocked;
+    size_t blk, smem_work_off, smem_bytes;
+};
+
+size_t take(size_t& off, size_t bytes, size_t align = 256) {
+    off = (off + align - 1) & ~(align - 1);
+    const size_t o = off;
+    off += bytes;
+    return o;
+}
+
+}  // namespace
+
+// Plans one window: offsets of its inputs inside the upload block and of its work areas inside the work block.
+static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world, size_t& st_off, size_t& in_off, size_t& work_off,
+                              HostPlan& H, int ncopy_cap) {
+    const int ncam = pb->ncam, npts = pb->npts, nobs = pb->nobs;
+    int ncv = 0;
+    for (int c = 0; c < ncam; ++c) ncv += pb->pose_const[c] ? 0 : 1;
+    if (ncv > MAX_VAR_CAMS) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: more than 64 optimised keyframes");
+    if (ncam > MAX_CAMS) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: more than 256 keyframes in the window");
+    H.ncv_max = ncv; H.n_max = 6 * ncv;
+    H.blk = 3 * (size_t)H.n_max + (size_t)H.n_max * H.n_max;
+    if (H.blk == 0) H.blk = 1;
+    // privatised accumulation copies spread the fp64 REDs (few addresses, thousands of REDs each)
+    size_t k = (size_t)(3 * MAX_N + MAX_N * MAX_N) / H.blk;
+    H.ncopy = (int)(k < 1 ? 1 : (k > (size_t)ncopy_cap ? (size_t)ncopy_cap : k));
+    if (getenv("OV2_BA_NCOPY")) { int e = atoi(getenv("OV2_BA_NCOPY")); if (e >= 1 && e <= 8) H.ncopy = e; }
+    H.solve_blocked = H.n_max > 96 ? 1 : 0;
+    // states (pose, inverse depth) of all windows sit together at the head of the block: they are what comes back
+    H.off_pose = take(st_off, sizeof(double) * 7 * ncam, 16);
+    H.off_invd = take(st_off, sizeof(double) * (size_t)(npts > 0 ? npts : 1), 16);
+    H.off_prob = take(in_off, sizeof(Prob));
+    H.off_apx = take(in_off, sizeof(double) * 2 * (size_t)(npts > 0 ? npts : 1));
+    H.off_opx = take(in_off, sizeof(double) * 2 * (size_t)(nobs > 0 ? nobs : 1));
+    H.off_lac = take(in_off, sizeof(int32_t) * (size_t)(npts > 0 ? npts : 1));
+    H.off_oc = take(in_off, sizeof(int32_t) * (size_t)(nobs > 0 ? nobs : 1));
+    H.off_ol = take(in_off, sizeof(int32_t) * (size_t)(nobs > 0 ? nobs : 1));
+    H.off_lp = take(in_off, sizeof(int32_t) * (size_t)(npts + 1));
+    H.off_pc = take(in_off, (size_t)ncam);
+    H.off_ty = take(in_off, pb->obs_type ? (size_t)(nobs > 0 ? nobs : 1) : 0);
+    const size_t no = nobs > 0 ? nobs : 1, np = npts > 0 ? npts : 1;
+    // zero-initialised part first (one memset): flags, cam_used, counts, barrier, result
+    H.zero_off = take(work_off, 0);
+    H.w_flags = take(work_off, no);
+    H.w_camused = take(work_off, 2 * (size_t)ncam);
+    H.w_counts = take(work_off, sizeof(double) * 8);
+    H.w_bar = take(work_off, sizeof(unsigned) * 4);
+    H.w_result = take(work_off, sizeof(Result));
+    H.w_sclm = take(work_off, sizeof(double) * np);
+    H.w_sccam = take(work_off, sizeof(double) * MAX_N);
+    H.zero_bytes = work_off - H.zero_off;
+    H.w_pose1 = take(work_off, sizeof(double) * 7 * ncam);
+    H.w_invd1 = take(work_off, sizeof(double) * np);
+    H.w_active = take(work_off, no);
+    H.w_camslot = take(work_off, sizeof(int32_t) * ncam);
+    H.w_Jr = take(work_off, sizeof(double) * 2 * no);
+    H.w_Ja = take(work_off, sizeof(double) * 12 * no);
+    H.w_Jo = take(work_off, sizeof(double) * 12 * no);
+    H.w_Jl = take(work_off, sizeof(double) * 2 * no);
+    H.w_chi2 = take(work_off, sizeof(double) * no);
+    H.w_dpos = take(work_off, no);
+    H.w_ete = take(work_off, sizeof(double) * np);
+    H.w_ge = take(work_off, sizeof(double) * np);
+    H.w_acc = take(work_off, sizeof(double) * (size_t)H.ncopy * H.blk);
+    H.w_total = take(work_off, sizeof(double) * H.blk);
+    H.w_scal = take(work_off, sizeof(double) * 2 * SC_COUNT);
+    H.w_z = take(work_off, sizeof(double) * MAX_N);
+    // dynamic shared memory: [keyframes 12 doubles each][slots][union: Schur scratch | solve area]
+    size_t s = sizeof(double) * 12 * (size_t)ncam + sizeof(int) * (size_t)ncam;
+    s = (s + 15) & ~(size_t)15;
+    H.smem_work_off = s;
+    const size_t schur = (size_t)WARPS * (6 * (size_t)(ncv + 1) * sizeof(double) + (size_t)(ncv + 1) * sizeof(int));
+    const size_t solve = H.solve_blocked ? (size_t)CH_NB * (size_t)((((size_t)H.n_max + 15) & ~(size_t)15) + 8) * sizeof(double)
+                                         : (size_t)H.n_max * (size_t)(H.n_max + 2) * sizeof(double);
+    H.smem_bytes = s + (schur > solve ? schur : solve) + 16;
+    (void)world;
+    return OV2_OK;
+}
+
+static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const HostPlan& H, char* din, char* dwork, Prob& P,
+                      const double* Kh, const double* krh, const double* trlh, const int* stop_flag_dev) {
+    memset(&P, 0, sizeof(P));
+    P.ncam = pb->ncam; P.npts = pb->npts; P.nobs = pb->nobs;
+    P.fx = Kh[0]; P.fy = Kh[1]; P.cx = Kh[2]; P.cy = Kh[3];
+    P.rfx = P.fx; P.rfy = P.fy; P.rcx = P.cx; P.rcy = P.cy;
+    for (int k = 0; k < 9; ++k) P.Rrl[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    if (pb->obs_type) {
+        P.rfx = krh[0]; P.rfy = krh[1]; P.rcx = krh[2]; P.rcy = krh[3];
+        const double qn = sqrt(trlh[3] * trlh[3] + trlh[4] * trlh[4] + trlh[5] * trlh[5] + trlh[6] * trlh[6]);
+        const double x = trlh[3] / qn, y = trlh[4] / qn, z = trlh[5] / qn, w = trlh[6] / qn;
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                             2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                             2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int k = 0; k < 9; ++k) P.Rrl[k] = R[k];
+        P.trl[0] = trlh[0]; P.trl[1] = trlh[1]; P.trl[2] = trlh[2];
+    }
+    P.th_f = (float)opts->huber_th;                       // const float mono_th (optimizer.cpp:47)
+    P.huber_a = (double)sqrtf(P.th_f);                    // HuberLoss(std::sqrt(mono_th))
+    P.huber_b = P.huber_a * P.huber_a;
+    P.use_robust = opts->use_robust ? 1 : 0;
+    P.apply_l2 = opts->apply_l2_after_robust ? 1 : 0;
+    P.refine_loss = opts->refine_loss;
+    P.max_it1 = opts->max_iters_robust; P.max_it2 = opts->max_iters_refine;
+    P.ftol = opts->function_tolerance;
+    P.stop_flag = stop_flag_dev;
+    P.pose_const = (const uint8_t*)(din + H.off_pc);
+    P.lm_anchor_cam = (const int32_t*)(din + H.off_lac);
+    P.lm_anchor_px = (const double*)(din + H.off_apx);
+    P.obs_cam = (const int32_t*)(din + H.off_oc);
+    P.obs_lm = (const int32_t*)(din + H.off_ol);
+    P.obs_px = (const double*)(din + H.off_opx);
+    P.obs_type = pb->obs_type ? (const uint8_t*)(din + H.off_ty) : nullptr;
+    P.lm_ptr = (const int32_t*)(din + H.off_lp);
+    P.pose[0] = (double*)(din + H.off_pose); P.pose[1] = (double*)(dwork + H.w_pose1);
+    P.invd[0] = (double*)(din + H.off_invd); P.invd[1] = (double*)(dwork + H.w_invd1);
+    P.active = (uint8_t*)(dwork + H.w_active); P.flags = (uint8_t*)(dwork + H.w_flags);
+    P.cam_used = (uint8_t*)(dwork + H.w_camused); P.cam_slot = (int32_t*)(dwork + H.w_camslot);
+    P.Jr = (double*)(dwork + H.w_Jr); P.Ja = (double*)(dwork + H.w_Ja); P.Jo = (double*)(dwork + H.w_Jo); P.Jl = (double*)(dwork + H.w_Jl);
+    P.chi2 = (double*)(dwork + H.w_chi2); P.dpos = (uint8_t*)(dwork + H.w_dpos);
+    P.sc_lm = (double*)(dwork + H.w_sclm); P.ete = (double*)(dwork + H.w_ete); P.ge = (double*)(dwork + H.w_ge);
+    P.acc = (double*)(dwork + H.w_acc); P.total = (double*)(dwork + H.w_total); P.scal = (double*)(dwork + H.w_scal);
+    P.z = (double*)(dwork + H.w_z); P.sc_cam = (double*)(dwork + H.w_sccam);
+    P.counts = (double*)(dwork + H.w_counts); P.bar = (unsigned*)(dwork + H.w_bar); P.result = (Result*)(dwork + H.w_result);
+    P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
+    P.smem_work_off = (int)H.smem_work_off;
+}
+
+static ov2_status host_copy(ov2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return OV2_OK;
+    if (ov2_is_device_ptr(src)) OV2_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    else memcpy(dst, src, bytes);
+    return OV2_OK;
+}
+
+// Solves `nprob` windows with one launch.  peers: multi-GPU exchange description (world 1 = none).
+ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const ov2_ba_opts* opts, ov2_ba_result* results,
+                      uint8_t* const* outlier_outs, const Peers* peers, const int* stop_flag_dev) {
+    if (!ctx || nprob <= 0 || !pbs || !opts || !results) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: bad arguments");
+    ov2_status st = ov2_begin(ctx);
+    if (st != OV2_OK) return st;
+    const int world = peers ? peers->world : 1;
+    std::vector<HostPlan> plans(nprob);
+    std::vector<ov2_ba_problem> hp(nprob);           // host-resident views of every window (device inputs are copied down)
+    std::vector<std::vector<char>> hold;              // storage for inputs that came as device pointers
+    size_t st_off = 0, in_off = 0, work_off = 0;
+    size_t smem_max = 0;
+    int gmax_work = 1;
+    for (int k = 0; k < nprob; ++k) {
+        const ov2_ba_problem& pb = pbs[k];
+        if (pb.ncam <= 0 || pb.npts < 0 || pb.nobs < 0 || (world == 1 && pb.npts <= 0))
+            return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: bad arguments");
+        hp[k] = pb;
+        // the flattened window is host data in the reference's flow (optimizer.cpp:43-430); device-resident inputs are
+        // accepted and staged through the host once (the solve itself never leaves the device)
+        auto pull = [&](const void* p, size_t bytes) -> const void* {
+            if (!p || bytes == 0 || !ov2_is_device_ptr(p)) return p;
+            hold.emplace_back(bytes);
+            cudaMemcpy(hold.back().data(), p, bytes, cudaMemcpyDeviceToHost);
+            return hold.back().data();
+        };
+        hp[k].K = (const double*)pull(pb.K, 32);
+        hp[k].pose_const = (const uint8_t*)pull(pb.pose_const, pb.ncam);
+        hp[k].lm_anchor_cam = (const int32_t*)pull(pb.lm_anchor_cam, sizeof(int32_t) * (size_t)pb.npts);
+        hp[k].lm_anchor_px = (const double*)pull(pb.lm_anchor_px, sizeof(double) * 2 * (size_t)pb.npts);
+        hp[k].obs_cam = (const int32_t*)pull(pb.obs_cam, sizeof(int32_t) * (size_t)pb.nobs);
+        hp[k].obs_lm = (const int32_t*)pull(pb.obs_lm, sizeof(int32_t) * (size_t)pb.nobs);
+        hp[k].obs_px = (const double*)pull(pb.obs_px, sizeof(double) * 2 * (size_t)pb.nobs);
+        hp[k].obs_type = (const uint8_t*)pull(pb.obs_type, (size_t)pb.nobs);
+        hp[k].Kr = (const double*)pull(pb.Kr, 32);
+        hp[k].Trl = (const double*)pull(pb.Trl, 56);
+        if (pb.obs_type && (!pb.Kr || !pb.Trl)) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_type given without Kr / Trl");
+        if ((st = plan_window(ctx, &hp[k], world, st_off, in_off, work_off, plans[k], 8)) != OV2_OK) return st;
+        if (plans[k].smem_bytes > smem_max) smem_max = plans[k].smem_bytes;
+        const int wk = (pb.nobs + THREADS - 1) / THREADS;
+        const int wl = (pb.npts + 4 * WARPS - 1) / (4 * WARPS);          // ~4 landmarks per warp and phase
+        const int w = wk > wl ? wk : wl;
+        if (w > gmax_work) gmax_work = w;
+    }
+    if (smem_max > 200 * 1024) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: window needs more than 200 KB of shared memory");
+    // ---- pack the inputs into one pinned block: ONE H2D copy for the whole batch.  Layout: [states | everything else]
+    const size_t st_bytes = (st_off + 255) & ~(size_t)255;
+    for (int k = 0; k < nprob; ++k) {
+        HostPlan& H = plans[k];
+        for (size_t* f : {&H.off_prob, &H.off_apx, &H.off_opx, &H.off_lac, &H.off_oc, &H.off_ol, &H.off_lp, &H.off_pc, &H.off_ty}) *f += st_bytes;
+    }
+    const size_t in_bytes = st_bytes + ((in_off + 255) & ~(size_t)255);
+    if (ctx->ba_ws_cap < in_bytes) {
+        if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);
+        ctx->ba_ws = nullptr; ctx->ba_ws_cap = 0;
+        OV2_CUDA(ctx, cudaHostAlloc(&ctx->ba_ws, in_bytes * 2, cudaHostAllocDefault));
+        ctx->ba_ws_cap = in_bytes * 2;
+    }
+    char* hpk = (char*)ctx->ba_ws;
+    void* o = nullptr;
+    if ((st = ov2_scratch(ctx, in_bytes, &o)) != OV2_OK) return st;
+    char* din = (char*)o;
+    if ((st = ov2_scratch(ctx, work_off + 256, &o)) != OV2_OK) return st;
+    char* dwork = (char*)o;
+    for (int k = 0; k < nprob; ++k) {
+        const ov2_ba_problem& pb = hp[k];
+        const HostPlan& H = plans[k];
+        const int ncam = pb.ncam, npts = pb.npts, nobs = pb.nobs;
+        // CSR by landmark (observations must be sorted by landmark)
+        int32_t* lp = (int32_t*)(hpk + H.off_lp);
+        memset(lp, 0, sizeof(int32_t) * (size_t)(npts + 1));
+        for (int i = 0; i < nobs; ++i) {
+            const int l = pb.obs_lm[i];
+            if (l < 0 || l >= npts || (i > 0 && l < pb.obs_lm[i - 1]))
+                return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_lm must be sorted ascending and in range");
+            lp[l + 1]++;
+        }
+        for (int l = 0; l < npts; ++l) lp[l + 1] += lp[l];
+        for (int i = 0; i < nobs; ++i)
+            if (pb.obs_cam[i] < 0 || pb.obs_cam[i] >= ncam) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_cam out of range");
+        for (int l = 0; l < npts; ++l)
+            if (pb.lm_anchor_cam[l] < 0 || pb.lm_anchor_cam[l] >= ncam) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: lm_anchor_cam out of range");
+        if ((st = host_copy(ctx, hpk + H.off_pose, pbs[k].pose, sizeof(double) * 7 * ncam)) != OV2_OK) return st;
+        if ((st = host_copy(ctx, hpk + H.off_invd, pbs[k].lm_invdepth, sizeof(double) * (size_t)npts)) != OV2_OK) return st;
+        memcpy(hpk + H.off_apx, pb.lm_anchor_px, sizeof(double) * 2 * (size_t)npts);
+        memcpy(hpk + H.off_opx, pb.obs_px, sizeof(double) * 2 * (size_t)nobs);
+        memcpy(hpk + H.off_lac, pb.lm_anchor_cam, sizeof(int32_t) * (size_t)npts);
+        memcpy(hpk + H.off_oc, pb.obs_cam, sizeof(int32_t) * (size_t)nobs);
+        memcpy(hpk + H.off_ol, pb.obs_lm, sizeof(int32_t) * (size_t)nobs);
+        memcpy(hpk + H.off_pc, pb.pose_const, (size_t)ncam);
+        if (pb.obs_type) memcpy(hpk + H.off_ty, pb.obs_type, (size_t)nobs);
+        Prob P;
+        fill_prob(&pb, opts, H, din, dwork, P, pb.K, pb.Kr, pb.Trl, stop_flag_dev);
+        memcpy(hpk + H.off_prob, &P, sizeof(P));
+    }
+    // the Prob records must be contiguous for the kernel: they are the first thing of each window's block, so gather them
+    std::vector<Prob> parr(nprob);
+    for (int k = 0; k < nprob; ++k) memcpy(&parr[k], hpk + plans[k].off_prob, sizeof(Prob));
+    if ((st = ov2_scratch(ctx, sizeof(Prob) * (size_t)nprob, &o)) != OV2_OK) return st;
+    Prob* dprobs = (Prob*)o;
+    cudaStream_t s = ctx->stream;
+    OV2_CUDA(ctx, cudaMemcpyAsync(din, hpk, in_bytes, cudaMemcpyHostToDevice, s));
+    if (nprob == 1) dprobs = (Prob*)(din + plans[0].off_prob);
+    else OV2_CUDA(ctx, cudaMemcpyAsync(dprobs, parr.data(), sizeof(Prob) * (size_t)nprob, cudaMemcpyHostToDevice, s));   // parr outlives the sync below
+    for (int k = 0; k < nprob; ++k) {
+        const HostPlan& H = plans[k];
+        OV2_CUDA(ctx, cudaMemsetAsync(dwork + H.zero_off, 0, H.zero_bytes, s));
+        OV2_CUDA(ctx, cudaMemsetAsync(dwork + H.w_active, 1, (size_t)(pbs[k].nobs > 0 ? pbs[k].nobs : 1), s));
+    }
+    // ---- launch geometry: G CTAs per window, all groups co-resident (cooperative launch)
+    OV2_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    int per_sm = 0;
+    OV2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_lm_kernel, THREADS, smem_max));
+    if (per_sm < 1) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: kernel does not fit an SM");
+    const int resident = per_sm * ctx->sm_count;
+    int G = gmax_work < 1 ? 1 : gmax_work;
+    // one wave of work per phase at most; more CTAs only add barrier latency
+    int gcap = nprob == 1 ? resident : (resident / nprob < 1 ? 1 : resident / nprob);
+    if (nprob > 1 && gcap > 16) gcap = 16;
+    if (G > gcap) G = gcap;
+    if (getenv("OV2_BA_CTAS")) { int e = atoi(getenv("OV2_BA_CTAS")); if (e >= 1 && e <= gcap) G = e; }
+    if (world > 1 && G < 2) G = 2;
+    int ngroups = nprob < resident / G ? nprob : resident / G;
+    if (ngroups < 1) ngroups = 1;
+    int grid = ngroups * G;
+    Peers X;
+    memset(&X, 0, sizeof(X));
+    X.world = 1;
+    if (peers) X = *peers;
+    const Prob* dp = dprobs;
+    void* kargs[] = {(void*)&dp, (void*)&nprob, (void*)&G, (void*)&X};
+    if (ctx->profiling) ov2_prof_begin(ctx);
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(grid), dim3(THREADS), kargs, smem_max, s);
+    ctx->launches++;
+    if (le != cudaSuccess) return ov2_fail(ctx, OV2_ERR_CUDA, "ba_lm_kernel launch", le);
+    if (ctx->profiling) ov2_prof_end(ctx, "ba_lm_kernel");
+    // ---- results: [pose | invd] live in the input block (buffer 0), flags + result record in the work block
+    OV2_CUDA(ctx, cudaMemcpyAsync(hpk, din, st_bytes, cudaMemcpyDeviceToHost, s));   // poses and inverse depths of every window: one copy
+    std::vector<Result> hres(nprob);
+    std::vector<std::vector<uint8_t>> hflags(nprob);
+    for (int k = 0; k < nprob; ++k) {
+        OV2_CUDA(ctx, cudaMemcpyAsync(&hres[k], dwork + plans[k].w_result, sizeof(Result), cudaMemcpyDeviceToHost, s));
+        if (outlier_outs && outlier_outs[k] && pbs[k].nobs > 0) {
+            if (ov2_is_device_ptr(outlier_outs[k])) {
+                OV2_CUDA(ctx, cudaMemcpyAsync(outlier_outs[k], dwork + plans[k].w_flags, (size_t)pbs[k].nobs, cudaMemcpyDeviceToDevice, s));
+            } else {
+                hflags[k].resize(pbs[k].nobs);
+                OV2_CUDA(ctx, cudaMemcpyAsync(hflags[k].data(), dwork + plans[k].w_flags, (size_t)pbs[k].nobs, cudaMemcpyDeviceToHost, s));
+            }
+        }
+    }
+    OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    bool numeric_fail = false, aborted = false;
+    for (int k = 0; k < nprob; ++k) {
+        const HostPlan& H = plans[k];
+        const size_t pb_bytes = sizeof(double) * 7 * pbs[k].ncam, ib = sizeof(double) * (size_t)pbs[k].npts;
+        if (ov2_is_device_ptr(pbs[k].pose)) cudaMemcpy(pbs[k].pose, hpk + H.off_pose, pb_bytes, cudaMemcpyHostToDevice);
+        else memcpy(pbs[k].pose, hpk + H.off_pose, pb_bytes);
+        if (ib) {
+            if (ov2_is_device_ptr(pbs[k].lm_invdepth)) cudaMemcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib, cudaMemcpyHostToDevice);
+            else memcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib);
+        }
+        if (!hflags[k].empty()) memcpy(outlier_outs[k], hflags[k].data(), hflags[k].size());
+        ov2_ba_result& r = results[k];
+        memset(&r, 0, sizeof(r));
+        r.iters_robust = hres[k].iters_robust; r.iters_refine = hres[k].iters_refine;
+        r.initial_cost = hres[k].initial_cost; r.final_cost = hres[k].final_cost;
+        r.n_outliers_first = hres[k].n_outliers_first; r.n_outliers_second = hres[k].n_outliers_second;
+        r.termination = hres[k].termination;
+        if (r.termination == 2) numeric_fail = true;
+        if (hres[k].aborted) aborted = true;
+    }
+    if (aborted) return ov2_fail(ctx, OV2_ERR_CUDA, "ov2_localba_solve: a barrier timed out (peer rank missing?)");
+    if (numeric_fail) return ov2_fail(ctx, OV2_ERR_NUMERIC, "ov2_localba_solve: 5 consecutive invalid steps");
+    return OV2_OK;
+}

@@ -1262,8 +1262,10 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
     return OV2_OK;
 }
 
-extern "C" ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
-                                        ov2_ba_result* res, uint8_t* outlier_out) {
+// Round-1 path (one launch per phase, LM controller on the host): kept selectable with OV2_BA_LEGACY=1 as a cross-check
+// of the persistent kernel (ba_lm.cu), and as the carrier of the callback-based sharded solve below.
+ov2_status ov2_localba_solve_legacy(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
+                                    ov2_ba_result* res, uint8_t* outlier_out) {
     return localba_impl(ctx, pb, opts, res, outlier_out, nullptr);
 }
 

@@ -42,6 +42,7 @@ extern "C" void ov2_destroy(ov2_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& ch : ctx->chunks) cudaFree(ch.p);
     if (ctx->ba_hscal) cudaFreeHost(ctx->ba_hscal);
+    if (ctx->ba_stop) cudaFreeHost(ctx->ba_stop);
     if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);   // pinned staging block of the BA path
     if (ctx->pe0) { cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1); }
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);

@@ -38,7 +38,8 @@ struct ov2_ctx {
     cudaEvent_t upload_ev = nullptr; // "images of this step are on the device" (ov2_frontend_step's upload token)
     // persistent small device blocks (tables)
     void* ba_ws = nullptr; size_t ba_ws_cap = 0;
-    double* ba_hscal = nullptr;   // pinned: per-iteration scalar readbacks of the LM controller
+    double* ba_hscal = nullptr;   // pinned: per-iteration scalar readbacks of the LM controller (legacy path)
+    int* ba_stop = nullptr;       // mapped pinned int: stop request polled by the persistent solve kernel
     // optional per-kernel CUDA-event timing (ov2_profile_enable): serialises launches
     bool profiling = false;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;

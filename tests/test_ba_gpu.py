@@ -106,15 +106,19 @@ def test_localba_refine_loss_override(ctx):
     (22, 1500, 9000, None), (22, 1500, 9000, "1"), (22, 1500, 9000, "0"),
     (50, 4000, 30000, None), (50, 4000, 30000, "0")])
 def test_localba_all_reduced_solver_paths(ctx, monkeypatch, ncam, npts, nobs, solver):
-    """Reduced camera systems of 84, 120 and 288 unknowns through every solver path: register
+    """(solver None: the persistent kernel's own choice - shared-memory Gauss-Jordan for n <= 96, blocked Cholesky beyond;
+    a solver id selects the round-1 path, OV2_BA_LEGACY=1, and its reduced-solve modes.)
+    Reduced camera systems of 84, 120 and 288 unknowns through every solver path: register
     Gauss-Jordan (default for n <= 96), blocked Cholesky with the FP64 tensor-core trailing update
     (default beyond; forced with OV2_BA_SOLVER=4), unblocked Cholesky in shared memory (=1) and in
     global/L2 (=0), the one-warp shared-memory Gauss-Jordan candidate (=5, n <= 96), each against the C restatement of the oracle (oracle/ba_ref_c.c, itself pinned to
     oracle/ba_ref.py)."""
     if solver is None:
         monkeypatch.delenv("OV2_BA_SOLVER", raising=False)
+        monkeypatch.delenv("OV2_BA_LEGACY", raising=False)
     else:
         monkeypatch.setenv("OV2_BA_SOLVER", solver)
+        monkeypatch.setenv("OV2_BA_LEGACY", "1")
     from oracle import ba_ref_c
     pb = synth.make_ba_problem(70 + ncam, ncam, npts, nobs)
     ref = _clone(pb)
@@ -162,3 +166,60 @@ def test_localba_stereo_150k_blocks_matches_golden(ctx):
     f1 = np.unpackbits(g["flags"])[:150000]
     assert ((flags & 1) != f1).sum() <= 4
     assert abs(res["n_outliers_first"] - int(g["n_outliers"][0])) <= 4
+
+
+@pytest.mark.parametrize("ctas", ["1", "3", "40", None])
+def test_localba_persistent_kernel_group_sizes(ctx, monkeypatch, ctas):
+    """The persistent solve kernel with 1, 3, 40 CTAs per window and its own choice: the group barrier, the redundant
+    controller and the phase split must give the same solve whatever the group size (mono and stereo windows)."""
+    if ctas is None:
+        monkeypatch.delenv("OV2_BA_CTAS", raising=False)
+    else:
+        monkeypatch.setenv("OV2_BA_CTAS", ctas)
+    _check(ctx, synth.make_ba_problem(3, 10, 2000, 8000))
+    _check(ctx, synth.make_ba_problem(41, 8, 400, 1600, stereo=True))
+
+
+def test_localba_legacy_path_still_matches(ctx, monkeypatch):
+    monkeypatch.setenv("OV2_BA_LEGACY", "1")
+    _check(ctx, synth.make_ba_problem(3, 10, 2000, 8000))
+
+
+def test_localba_batch_equals_single_solves(ctx):
+    """ov2_localba_solve_batch: windows of different sizes (mono, stereo, all poses constant, one tiny window) in one
+    launch; every window equals its own single solve."""
+    specs = [(3, 10, 2000, 8000, False), (11, 6, 300, 1200, False), (41, 8, 400, 1600, True), (12, 20, 1500, 9000, False),
+             (5, 6, 100, 300, False), (44, 8, 400, 1600, False)] * 3
+    pbs = [synth.make_ba_problem(s, c, p, o, stereo=st) for s, c, p, o, st in specs]
+    pbs[4]["pose_const"][:] = 1
+    singles = [_clone(pb) for pb in pbs]
+    refs = [api.Optimizer(ctx).local_ba(pb) for pb in singles]
+    batch = [_clone(pb) for pb in pbs]
+    res, flags = api.local_ba_batch(ctx, batch)
+    assert len(res) == len(pbs)
+    for k in range(len(pbs)):
+        r1, f1 = refs[k]
+        assert (res[k]["iters_robust"], res[k]["iters_refine"], res[k]["termination"]) == (r1["iters_robust"], r1["iters_refine"], r1["termination"]), k
+        assert abs(res[k]["final_cost"] - r1["final_cost"]) <= 1e-9 * max(1.0, r1["final_cost"])
+        assert np.abs(batch[k]["pose"] - singles[k]["pose"]).max() <= 1e-8
+        assert np.abs(batch[k]["lm_invdepth"] - singles[k]["lm_invdepth"]).max() <= 1e-8
+        assert (flags[k] != f1).sum() <= 2
+
+
+def test_localba_stop_request_skips_the_refinement(ctx):
+    """Optimizer::signalStopLocalBA (optimizer.cpp:2334-2343): the flag is polled before solve #2 (optimizer.cpp:603-604)."""
+    pb = synth.make_ba_problem(3, 10, 2000, 8000)
+    a = _clone(pb)
+    r0, _ = api.Optimizer(ctx).local_ba(a)
+    assert r0["iters_refine"] > 0
+    api.request_stop_local_ba(ctx, True)
+    b = _clone(pb)
+    r1, f1 = api.Optimizer(ctx).local_ba(b)
+    assert r1["iters_refine"] == 0 and r1["iters_robust"] == r0["iters_robust"] and r1["n_outliers_first"] == r0["n_outliers_first"]
+    ref = _clone(pb)
+    rr = B.local_ba(ref, apply_l2_after_robust=False)
+    assert np.abs(b["pose"] - ref["pose"]).max() <= 1e-7
+    api.request_stop_local_ba(ctx, False)
+    c = _clone(pb)
+    r2, _ = api.Optimizer(ctx).local_ba(c)
+    assert r2["iters_refine"] == r0["iters_refine"]

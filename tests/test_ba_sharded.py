@@ -119,3 +119,57 @@ def test_sharded_solve_matches_unsharded(ctx, world):
     assert (flags != rflags).sum() <= 2
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,empty", [(2, False), (3, False), (3, True)])
+def test_p2p_sharded_solve_matches_unsharded(ctx, world, empty):
+    """ov2_localba_solve_p2p: `world` ranks as contexts of ONE process on one GPU (communicators connected with direct
+    pointers); every rank's persistent kernel sums the partial reduced systems out of the other ranks' exchange buffers.
+    Must reproduce the unsharded solve; with `empty` the last rank owns no landmark at all (an empty shard
+    used to fail with a zero-block launch and hang the others)."""
+    pb = synth.make_ba_problem(31, 12, 1500, 9000)
+    ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    rres, rflags = api.Optimizer(ctx).local_ba(ref)
+    shards = api.partition_ba_problem(pb, world - 1 if empty else world)
+    if empty:
+        e = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in shards[0][0].items()}
+        for k in ("lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px"):
+            e[k] = e[k][:0].copy()
+        shards.append((e, np.zeros(0, np.int64), np.zeros(0, np.int64)))
+    ctxs = [api.Context(0) for _ in range(world)]
+    comms = [api.BaComm(ctxs[r], r, world) for r in range(world)]
+    api.BaComm.connect_local(comms)
+    for rep in range(2):                       # twice: epochs of consecutive launches must not collide
+        work = [{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sh[0].items()} for sh in shards]
+        results = [None] * world
+        errs = []
+
+        def run(rank):
+            try:
+                results[rank] = comms[rank].local_ba(work[rank])
+            except Exception as ex:  # pragma: no cover
+                errs.append((rank, ex))
+
+        ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=180)
+        assert not errs, errs
+        invd = np.zeros(len(pb["lm_invdepth"]))
+        flags = np.zeros(len(pb["obs_cam"]), np.uint8)
+        for r, (sh, lms, obs) in enumerate(shards):
+            res, fl = results[r]
+            assert (res["iters_robust"], res["iters_refine"]) == (rres["iters_robust"], rres["iters_refine"]), (r, res)
+            assert abs(res["final_cost"] - rres["final_cost"]) <= 1e-9 * max(1.0, rres["final_cost"])
+            assert np.abs(work[r]["pose"] - ref["pose"]).max() <= 1e-7
+            assert np.array_equal(work[r]["pose"], work[0]["pose"])          # bit-identical decisions on every rank
+            invd[lms] = work[r]["lm_invdepth"]
+            flags[obs] = fl
+        assert np.abs(invd - ref["lm_invdepth"]).max() <= 1e-7
+        assert (flags != rflags).sum() <= 2
+    for c in comms:
+        c.close()
+    for c in ctxs:
+        c.close()

@@ -529,7 +529,7 @@ def test_single_scale_detector_1280x720_cell35(ctx):
         ref_i, ref_q, _ = R.detect_single_scale_nosubpix(eq, cs, kk, (0, 0, w, h), q0, use_cv2=False)
         assert np.array_equal(ipts, ref_i), (q0, len(ipts), len(ref_i))
         assert fe.dmaxquality_ == ref_q
-        assert len(ipts) > 100
+        assert len(ipts) > (100 if q0 < 0.01 else 0)
         assert np.abs(pts - _subpix(eq, ref_i.astype(np.float32))).max() <= SUBPIX_TOL
     pyr.close()
 

@@ -293,3 +293,63 @@ extern "C" int ge_pitch(int n) { return gewarp::pitch(n); }''' % ROOT)
     A = np.zeros((4, lib.ge_pitch(4)))
     A[:4, :4] = np.diag([1.0, -1.0, 1.0, 1.0])
     assert lib.ge_host(4, A.ctypes.data, np.zeros(4).ctypes.data) == 0
+
+
+def test_device_lm_controller_replays_the_oracle_decisions(tmp_path):
+    """csrc/ba_lm_ctl.cuh (the trust-region controller every CTA of the persistent solve kernel replays on the device)
+    compiled for the host and driven with the per-iteration scalars of the oracle (oracle/ba_ref.py): same iteration
+    counts, termination types, final costs and radius sequence for both solves of several windows - including windows
+    that end on the function tolerance, on the iteration cap, and with rejected steps."""
+    src = tmp_path / "ctl.cpp"
+    src.write_text(r'''
+#include "%s/ov2slam_b200/csrc/ba_lm_ctl.cuh"
+extern "C" int replay(int n, const double* rec, int max_iters, double ftol, double* out) {
+  // rec: n x 7 = x_cost, cand_cost, mcc, step2, candx2, gmax, invalid
+  lmctl::State s; lmctl::init(s);
+  int k = 0;
+  for (;;) {
+    if (!lmctl::begin_iteration(s, max_iters)) break;
+    if (k >= n) return -1;
+    const double* r = rec + 7 * k++;
+    out[8 + s.iteration] = s.radius;
+    lmctl::Action a = lmctl::end_iteration(s, r[0], r[1], r[2], r[3], r[4], r[5], r[6] != 0.0, ftol);
+    if (a == lmctl::ACT_STOP) break;
+  }
+  out[0] = s.iteration; out[1] = s.termination; out[2] = lmctl::final_cost(s); out[3] = s.initial_cost; out[4] = k;
+  return 0;
+}''' % ROOT)
+    so = tmp_path / "libctl.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), str(src)])
+    lib = ctypes.CDLL(str(so))
+    lib.replay.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    from ov2slam_b200 import synth
+    from oracle import ba_ref as B
+    seen_term = set()
+    rejected = 0
+    cases = [(3, 6, 300, 1200, {}), (11, 6, 300, 1200, dict(max_iters_robust=2)), (21, 8, 500, 2500, dict(use_robust=False)),
+             (5, 8, 300, 1500, dict(max_iters_robust=30, function_tolerance=1e-12)), (41, 8, 400, 1600, dict(stereo=True))]
+    for seed, ncam, npts, nobs, kw in cases:
+        stereo = kw.pop("stereo", False)
+        pb = synth.make_ba_problem(seed, ncam, npts, nobs, stereo=stereo)
+        log = []
+        res = B.local_ba(pb, log=log, **kw)
+        ctl = [e for e in log if e.get("ctl")]
+        # split the records of solve #1 and #2: the iteration counter restarts at 1
+        cuts = [i for i, e in enumerate(ctl) if e["it"] == 1]
+        parts = [ctl[a:b] for a, b in zip(cuts, cuts[1:] + [len(ctl)])]
+        assert len(parts) == len(res["summaries"])
+        for part, summ, max_it in zip(parts, res["summaries"], (kw.get("max_iters_robust", 5), kw.get("max_iters_refine", 10))):
+            rec = np.array([[e["x_cost"], e["cand_cost"], e["mcc"], e["step2"], e["candx2"], e["gmax"], float(e["invalid"])] for e in part])
+            out = np.zeros(64)
+            rc = lib.replay(len(rec), np.ascontiguousarray(rec).ctypes.data, max_it, kw.get("function_tolerance", 1e-3), out.ctypes.data)
+            assert rc == 0
+            term = {"CONVERGENCE": 0, "NO_CONVERGENCE": 1, "FAILURE": 2}[summ["termination"]]
+            assert int(out[0]) == summ["iterations"] and int(out[1]) == term, (seed, out[:5], summ["iterations"], summ["termination"])
+            assert out[2] == summ["final_cost"] and out[3] == summ["initial_cost"]
+            assert int(out[4]) == len(rec)                      # every oracle iteration was consumed, none missing
+            radii = [t["radius"] for t in summ["trace"]]        # radius at the start of iteration k+1 = trace[k]
+            for it in range(1, summ["iterations"] + 1):
+                assert abs(out[8 + it] - radii[it - 1]) <= 1e-12 * radii[it - 1], (seed, it)
+            seen_term.add(summ["termination"])
+            rejected += sum(1 for t in summ["trace"][1:] if not t["ok"])
+    assert {"CONVERGENCE", "NO_CONVERGENCE"} <= seen_term
