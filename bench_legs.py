@@ -42,7 +42,7 @@ def make_stereo_unit(seed: int):
     rng = np.random.default_rng(seed + 31)
     disp = float(rng.uniform(5.0, 30.0))
     right = synth.shift_image(cur, -disp, 0.0) + rng.normal(0.0, 1.5, size=cur.shape)
-    right = np.clip(np.rint(right), 0, 255).astype(np.uint8)
+    right = np.ascontiguousarray(np.clip(np.rint(right), 0, 255).astype(np.uint8))
     kps = np.stack([rng.uniform(40, C4_W - 40, C4_NTRK), rng.uniform(40, C4_H - 40, C4_NTRK)], axis=1).astype(np.float32)
     is3d, pri = synth.make_priors(seed, kps, flow, C4_FRAC3D)
     lv = np.where(is3d, 1, 3).astype(np.uint8)
@@ -343,7 +343,7 @@ def c4_leg(torch, api, dist, ctx, stream, rank, world, args, peaks, usable_cores
     ntracked = float(wl.d["st"].float().mean().item())
     nstereo = float(wl.d["sst"].float().mean().item())
     # e2e: stepped once for warm-up, then the pipelined stream timed three times (median)
-    nch = args.e2e_chunks if args.e2e_chunks > 0 else (8 if world == 1 else max(2, min(8, 32 // world)))
+    nch = args.e2e_chunks if args.e2e_chunks > 0 else (8 if world == 1 else max(4, min(8, usable_cores())))
     wl.init_e2e(nch)
     for _ in range(2):
         wl.step_e2e()

@@ -728,6 +728,11 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
         __syncthreads();
         const Prob& P = sProb;
         GroupBar bar{P.bar, P.bar + 1, (unsigned)G, 0u};
+        // optional phase trace (CTA 0 / thread 0): time since the previous mark is charged to phase k
+        unsigned long long tr_last = 0, tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const bool tracing = P.trace != nullptr && bid == 0 && tid == 0;
+        if (tracing) tr_last = global_ns();
+#define TR(k) do { if (tracing) { const unsigned long long t_ = global_ns(); tr_acc[k] += t_ - tr_last; tr_last = t_; } } while (0)
         // shared memory carve-up
         double* s_cam = reinterpret_cast<double*>(smem_raw);                       // [ncam][12]
         int* s_slot = reinterpret_cast<int*>(s_cam + 12 * (size_t)P.ncam);         // [ncam]
@@ -795,6 +800,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
             if (bid == 0)
                 for (int c = tid; c < P.ncam; c += THREADS) P.cam_slot[c] = s_slot[c];
             double* T = (P.ncopy > 1 || X.world > 1) ? P.total : P.acc;      // the system the solve reads
+            TR(0);
             // ---- LM iterations
             for (;;) {
                 if (tid == 0) s_action = lmctl::begin_iteration(S, max_iters) ? 1 : 0;
@@ -814,12 +820,14 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                     if (lane == 0 && cost != 0.0) atomicAdd(scal + SC_COST, cost);
                 }
                 bar.sync();
+                TR(1);
                 // ---- B: Schur elimination into this CTA's accumulation copy
                 {
                     double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
                     for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, l, lane, radius, first_iter, acc, n, scal);
                 }
                 bar.sync();
+                TR(2);
                 // ---- B2: fold the copies; multi-GPU: sum the ranks' partial systems out of peer memory
                 const int live = 3 * n + n * n;
                 if (X.world > 1) {
@@ -858,6 +866,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                     }
                     bar.sync();
                 }
+                TR(3);
                 // ---- C: reduced camera system (CTA 0); gradient projection |x - Plus(x, -g)|_inf (last CTA); the other
                 //      CTAs clear the accumulation copies for the next iteration (T is separate whenever ncopy > 1)
                 if (bid == 0) {
@@ -880,7 +889,9 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                     gm = warp_max(gm);
                     if (lane == 0) atomic_max_pos(scal + SC_GMAX_CAM, gm);
                 }
+                TR(4);
                 bar.sync();
+                TR(5);
                 // ---- D: candidate keyframe poses (every CTA, into shared memory), back-substitution, candidate cost
                 {
                     double st2 = 0.0, cx2 = 0.0;
@@ -926,6 +937,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                     if (gtid < SC_COUNT) oscal[gtid] = 0.0;
                 }
                 bar.sync();
+                TR(6);
                 if (X.world > 1) {
                     // second, tiny exchange: candidate cost, model cost change, step / candidate norms (rank order sum)
                     double* mine = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(X.base[X.rank]) + XB_SC4) + par * 8;
@@ -952,6 +964,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                 }
                 __syncthreads();
                 const int action = s_action;
+                TR(7);
                 if (action == lmctl::ACT_CONTINUE_ACCEPTED) {
                     xi ^= 1;
                     x_pose = P.pose[xi]; c_pose = P.pose[xi ^ 1];
@@ -1027,6 +1040,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
             }
         }
         // ---- write-back: x into buffer 0, result record
+        TR(8);
         bar.sync();
         if (xi == 1) {
             for (int i = gtid; i < 7 * P.ncam; i += gthreads) P.pose[0][i] = P.pose[1][i];
@@ -1044,6 +1058,10 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
             R->n_outliers_second = n_out2;
             R->aborted = (int)ld_acquire_gpu(P.bar + 1);
         }
+        TR(9);
+        if (tracing)
+            for (int k = 0; k < 12; ++k) P.trace[k] = tr_acc[k];
+#undef TR
     }
 }
 
@@ -1058,7 +1076,7 @@ struct HostPlan {
     size_t off_prob, off_pose, off_invd, off_apx, off_opx, off_lac, off_oc, off_ol, off_lp, off_pc, off_ty, in_bytes;   // uploaded block
     // device-only work areas (offsets into the work block)
     size_t w_pose1, w_invd1, w_active, w_flags, w_camused, w_camslot, w_Jr, w_Ja, w_Jo, w_Jl, w_chi2, w_dpos, w_sclm, w_ete, w_ge,
-           w_acc, w_total, w_scal, w_z, w_sccam, w_counts, w_bar, w_result, work_bytes, zero_off, zero_bytes;
+           w_acc, w_total, w_scal, w_z, w_sccam, w_counts, w_bar, w_result, w_trace, work_bytes, zero_off, zero_bytes;
     int ncv_max, n_max, ncopy, solve_blocked;
     size_t blk, smem_work_off, smem_bytes;
 };
@@ -1108,6 +1126,7 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     H.w_counts = take(work_off, sizeof(double) * 8);
     H.w_bar = take(work_off, sizeof(unsigned) * 4);
     H.w_result = take(work_off, sizeof(Result));
+    H.w_trace = take(work_off, sizeof(unsigned long long) * 16);
     H.w_sclm = take(work_off, sizeof(double) * np);
     H.w_sccam = take(work_off, sizeof(double) * MAX_N);
     H.zero_bytes = work_off - H.zero_off;
@@ -1183,6 +1202,7 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.acc = (double*)(dwork + H.w_acc); P.total = (double*)(dwork + H.w_total); P.scal = (double*)(dwork + H.w_scal);
     P.z = (double*)(dwork + H.w_z); P.sc_cam = (double*)(dwork + H.w_sccam);
     P.counts = (double*)(dwork + H.w_counts); P.bar = (unsigned*)(dwork + H.w_bar); P.result = (Result*)(dwork + H.w_result);
+    P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
     P.smem_work_off = (int)H.smem_work_off;
 }
@@ -1346,6 +1366,14 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         }
     }
     OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    if (getenv("OV2_BA_TRACE")) {
+        unsigned long long tr[16];
+        cudaMemcpy(tr, dwork + plans[0].w_trace, sizeof(tr), cudaMemcpyDeviceToHost);
+        static const char* names[10] = {"setup", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb"};
+        fprintf(stderr, "[ba trace] G=%d grid=%d smem=%zu ncopy=%d |", G, grid, smem_max, plans[0].ncopy);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
+        fprintf(stderr, "\n");
+    }
     bool numeric_fail = false, aborted = false;
     for (int k = 0; k < nprob; ++k) {
         const HostPlan& H = plans[k];

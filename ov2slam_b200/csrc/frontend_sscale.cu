@@ -13,8 +13,8 @@
 //     reference's parallel_for_ body races on the mask).
 //
 // Two kernels: ss_response_kernel (one CTA per cell and frame, everything in shared memory, response map
-// to HBM: 4 B/pixel written once, read at most twice) and ss_sweep_kernel (one CTA per frame walks the
-// cells in order with the 1 bit/pixel mask in shared memory).
+// to HBM: 4 B/pixel written once, read at most twice) and ss_sweep_kernel (one CTA per frame, one warp per cell row in a
+// wavefront that reproduces the sequential cell order, 1 bit/pixel mask in shared memory).
 #include "ov2_common.cuh"
 #include "sscale_math.cuh"
 
@@ -87,21 +87,21 @@ __device__ __forceinline__ void paint_row(uint32_t* bm, int wpr, int W, int H, i
     }
 }
 
-constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_MAX_WARPS = 32;
 
-// first maximum (row-major) of resp * mask over one cell; every thread returns the same (value, index)
-__device__ __forceinline__ void cell_argmax(const float* __restrict__ resp, const uint32_t* bm, int wpr, int x0, int y0, int cs,
-                                            float* s_val, int* s_idx, float& best_v, int& best_i) {
-    const int tid = threadIdx.x, npx = cs * cs;
+// First maximum (row-major) of resp * mask over one cell by ONE warp; every lane returns the same (value, index).
+__device__ __forceinline__ void cell_argmax_warp(const float* __restrict__ resp, const uint32_t* bm, int wpr, int x0, int y0, int cs,
+                                                 int lane, float& best_v, int& best_i) {
+    const int npx = cs * cs;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    int yy = tid / cs, xx = tid - yy * cs;
-    const int sy = SWEEP_THREADS / cs, sx = SWEEP_THREADS - sy * cs;
-    for (int i = tid; i < npx; i += SWEEP_THREADS) {
+    int yy = lane / cs, xx = lane - yy * cs;
+    const int sy = 32 / cs, sx = 32 - sy * cs;
+    for (int i = lane; i < npx; i += 32) {
         const int gx = x0 + xx, gy = y0 + yy;
         const bool masked = (bm[(size_t)gy * wpr + (gx >> 5)] >> (gx & 31)) & 1u;
         const float v = masked ? 0.0f : __ldg(resp + i);           // response * 0.0f compares equal to 0
-        if (v > bv) { bv = v; bi = i; }                           // strict: the earliest index of this thread wins
+        if (v > bv) { bv = v; bi = i; }                           // strict: the earliest index of this lane wins
         xx += sx; yy += sy;
         if (xx >= cs) { xx -= cs; yy++; }
     }
@@ -111,39 +111,37 @@ __device__ __forceinline__ void cell_argmax(const float* __restrict__ resp, cons
         const int oi = __shfl_xor_sync(FULL, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
-    __syncthreads();
-    bv = s_val[0]; bi = s_idx[0];
-#pragma unroll
-    for (int k = 1; k < SWEEP_THREADS / 32; ++k) {
-        const float ov = s_val[k];
-        const int oi = s_idx[k];
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    __syncthreads();                                              // s_val / s_idx are reused by the next call
     best_v = bv; best_i = bi;
 }
 
-__global__ void __launch_bounds__(SWEEP_THREADS) ss_sweep_kernel(SweepArgs A) {
+// The reference walks the cells in row-major order and every detection paints a disc of radius cs / 4 into the mask, so a
+// cell depends on the cells before it - but a disc reaches at most cs / 4 pixels into the NEIGHBOURING cells.  Cell (r, c)
+// therefore only needs (r, c-1), (r-1, c-1), (r-1, c) and (r-1, c+1) to be finished: one WARP per cell row, row r trailing
+// row r-1 by two cells (wavefront), gives exactly the sequential result in (nwc + 2 nhc) cell times instead of nwc * nhc.
+// progress[r] = number of cells of row r that are finished (volatile shared memory; discs are painted with shared atomics
+// before the counter moves).
+__global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) ss_sweep_kernel(SweepArgs A) {
     extern __shared__ uint32_t sm[];
-    __shared__ float s_val[SWEEP_THREADS / 32];
-    __shared__ int s_idx[SWEEP_THREADS / 32];
-    const int tid = threadIdx.x, fr = blockIdx.x;
+    __shared__ int s_n;
+    const int tid = threadIdx.x, fr = blockIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int wpr = (A.w + 31) >> 5, ncells = A.nwc * A.nhc, cs = A.cs;
     uint32_t* bm = sm;                                            // h * wpr words, bit = 1: mask is 0.0f there
     int2* firstd = reinterpret_cast<int2*>(sm + (((size_t)A.h * wpr + 1) & ~(size_t)1));   // per cell, x < 0: none (8-byte aligned)
     int2* secondd = firstd + ncells;
-    uint8_t* occ = reinterpret_cast<uint8_t*>(secondd + ncells);  // (nhc+1)*(nwc+1)
-    for (int i = tid; i < A.h * wpr; i += SWEEP_THREADS) bm[i] = 0;
-    for (int i = tid; i < ncells; i += SWEEP_THREADS) { firstd[i] = make_int2(-1, -1); secondd[i] = make_int2(-1, -1); }
+    volatile int* progress = reinterpret_cast<volatile int*>(secondd + ncells);             // [nhc]
+    uint8_t* occ = reinterpret_cast<uint8_t*>(const_cast<int*>(progress) + A.nhc);          // (nhc+1)*(nwc+1)
+    for (int i = tid; i < A.h * wpr; i += nthreads) bm[i] = 0;
+    for (int i = tid; i < ncells; i += nthreads) { firstd[i] = make_int2(-1, -1); secondd[i] = make_int2(-1, -1); }
+    for (int i = tid; i < A.nhc; i += nthreads) progress[i] = 0;
     const int nocc = (A.nhc + 1) * (A.nwc + 1);
-    for (int i = tid; i < nocc; i += SWEEP_THREADS) occ[i] = 0;
+    for (int i = tid; i < nocc; i += nthreads) occ[i] = 0;
     __syncthreads();
     const int nrows = 2 * A.radius + 1;
     // existing keypoints: occupancy + discs (feature_extractor.cpp:316-319); painting commutes (atomicOr)
     if (A.kp_off) {
         const int k0 = A.kp_off[fr], k1 = A.kp_off[fr + 1];
-        for (int k = k0 + tid; k < k1; k += SWEEP_THREADS) {
+        for (int k = k0 + tid; k < k1; k += nthreads) {
             const float2 px = A.kps[k];
             const int rr = (int)(px.y / (float)cs), cc = (int)(px.x / (float)cs);
             if (rr >= 0 && rr <= A.nhc && cc >= 0 && cc <= A.nwc) occ[rr * (A.nwc + 1) + cc] = 1;
@@ -158,28 +156,38 @@ __global__ void __launch_bounds__(SWEEP_THREADS) ss_sweep_kernel(SweepArgs A) {
     __syncthreads();
     const double quality = A.quality[fr];
     const float* resp = A.resp + (size_t)fr * ncells * (size_t)(cs * cs);
-    int nboccup = 0;
-    for (int cell = 0; cell < ncells; ++cell) {                   // uniform control flow: every branch below is block-uniform
-        const int r = cell / A.nwc, c = cell - r * A.nwc;
-        if (occ[r * (A.nwc + 1) + c]) { nboccup++; continue; }
-        const int x0 = c * cs, y0 = r * cs;
-        if (!(x0 + cs < A.w - 1 && y0 + cs < A.h - 1)) continue;
-        const float* rc = resp + (size_t)cell * (cs * cs);
-        for (int round = 0; round < 2; ++round) {
-            float mx; int idx;
-            cell_argmax(rc, bm, wpr, x0, y0, cs, s_val, s_idx, mx, idx);
-            const int ly = idx / cs, lx = idx - ly * cs;
-            const int px = x0 + lx, py = y0 + ly;
-            if (px < A.roi_x || py < A.roi_y || px >= A.roi_x + A.roi_w || py >= A.roi_y + A.roi_h) break;   // `continue` of the cell loop
-            if ((double)mx >= quality) {
-                if (tid == 0) (round == 0 ? firstd : secondd)[cell] = make_int2(px, py);
-                for (int rI = tid; rI < nrows; rI += SWEEP_THREADS) {
-                    const int dy = rI - A.radius;
-                    const int hwv = A.hw[dy < 0 ? -dy : dy];
-                    paint_row(bm, wpr, A.w, A.h, py + dy, px - hwv, px + hwv);
-                }
-                __syncthreads();
+    for (int r = warp; r < A.nhc; r += nwarps) {
+        for (int c = 0; c < A.nwc; ++c) {
+            if (r > 0) {
+                // wait until row r-1 has finished cell c+1 (or its last cell)
+                const int need = min(c + 2, A.nwc);
+                while (progress[r - 1] < need) { }
+                __threadfence_block();
             }
+            const int cell = r * A.nwc + c;
+            const int x0 = c * cs, y0 = r * cs;
+            if (!occ[r * (A.nwc + 1) + c] && (x0 + cs < A.w - 1 && y0 + cs < A.h - 1)) {
+                const float* rc = resp + (size_t)cell * (cs * cs);
+                for (int round = 0; round < 2; ++round) {
+                    float mx; int idx;
+                    cell_argmax_warp(rc, bm, wpr, x0, y0, cs, lane, mx, idx);
+                    const int ly = idx / cs, lx = idx - ly * cs;
+                    const int px = x0 + lx, py = y0 + ly;
+                    if (px < A.roi_x || py < A.roi_y || px >= A.roi_x + A.roi_w || py >= A.roi_y + A.roi_h) break;   // `continue` of the cell loop
+                    if ((double)mx >= quality) {
+                        if (lane == 0) (round == 0 ? firstd : secondd)[cell] = make_int2(px, py);
+                        for (int rI = lane; rI < nrows; rI += 32) {
+                            const int dy = rI - A.radius;
+                            const int hwv = A.hw[dy < 0 ? -dy : dy];
+                            paint_row(bm, wpr, A.w, A.h, py + dy, px - hwv, px + hwv);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __threadfence_block();                                // discs before the counter
+            __syncwarp();
+            if (lane == 0) progress[r] = c + 1;
         }
     }
     __syncthreads();
@@ -187,6 +195,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) ss_sweep_kernel(SweepArgs A) {
     // while cells stayed empty; quality adaptation; unused slots = (-1, -1)
     int2* out = A.out_int + (size_t)fr * A.max_per_frame;
     if (tid == 0) {
+        int nboccup = 0;
+        for (int cell = 0; cell < ncells; ++cell) {
+            const int r = cell / A.nwc, c = cell - r * A.nwc;
+            nboccup += occ[r * (A.nwc + 1) + c] ? 1 : 0;
+        }
         int n = 0;
         for (int cell = 0; cell < ncells; ++cell)
             if (firstd[cell].x >= 0 && n < A.max_per_frame) out[n++] = firstd[cell];
@@ -204,10 +217,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) ss_sweep_kernel(SweepArgs A) {
         else if ((double)n > 0.9 * (double)(ncells - nboccup)) q *= 1.5;
         A.quality[fr] = q;
         A.out_n[fr] = n;
-        s_idx[0] = n;
+        s_n = n;
     }
     __syncthreads();
-    for (int i = s_idx[0] + tid; i < A.max_per_frame; i += SWEEP_THREADS) out[i] = make_int2(-1, -1);
+    for (int i = s_n + tid; i < A.max_per_frame; i += nthreads) out[i] = make_int2(-1, -1);
 }
 
 void circle_halfwidths(int radius, int* hw) {   // cv::circle(filled) rasterisation, as in frontend_fast.cu
@@ -300,13 +313,15 @@ extern "C" ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, 
     SA.kp_off = d_off; SA.kps = d_kps; SA.resp = d_resp; SA.quality = d_q; SA.out_int = d_int; SA.out_n = d_cnt;
     {
         const size_t wpr = (size_t)(W + 31) / 32;
-        size_t smem = (((size_t)H * wpr + 1) & ~(size_t)1) * 4 + (size_t)ncells * sizeof(int2) * 2 + (size_t)(nhc + 1) * (nwc + 1);
+        size_t smem = (((size_t)H * wpr + 1) & ~(size_t)1) * 4 + (size_t)ncells * sizeof(int2) * 2 + (size_t)nhc * sizeof(int) +
+                      (size_t)(nhc + 1) * (nwc + 1);
         smem = (smem + 15) & ~(size_t)15;
         if (smem > 227 * 1024)
             return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_detect_single_scale: image too large for the shared-memory mask bitmap");
         if (smem > 48 * 1024)
             OV2_CUDA(ctx, cudaFuncSetAttribute(ss_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OV2_LAUNCH(ctx, "ss_sweep_kernel", ss_sweep_kernel<<<count, SWEEP_THREADS, smem, ctx->stream>>>(SA));
+        const int nw = nhc < SWEEP_MAX_WARPS ? nhc : SWEEP_MAX_WARPS;       // one warp per cell row (wavefront)
+        OV2_LAUNCH(ctx, "ss_sweep_kernel", ss_sweep_kernel<<<count, nw * 32, smem, ctx->stream>>>(SA));
     }
     if ((st = ov2_subpix_launch(ctx, pyr, first, count, max_per_frame, d_int, d_out, do_subpix)) != OV2_OK) return st;
     return ov2_end(ctx);

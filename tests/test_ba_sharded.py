@@ -123,11 +123,13 @@ def test_sharded_solve_matches_unsharded(ctx, world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,empty", [(2, False), (3, False), (3, True)])
-def test_p2p_sharded_solve_matches_unsharded(ctx, world, empty):
-    """ov2_localba_solve_p2p: `world` ranks as contexts of ONE process on one GPU (communicators connected with direct
+def test_p2p_sharded_solve_matches_unsharded(ctx, monkeypatch, world, empty):
+    """(All ranks share ONE GPU here, so their persistent kernels must be co-resident: 24 CTAs each.)
+    ov2_localba_solve_p2p: `world` ranks as contexts of ONE process on one GPU (communicators connected with direct
     pointers); every rank's persistent kernel sums the partial reduced systems out of the other ranks' exchange buffers.
     Must reproduce the unsharded solve; with `empty` the last rank owns no landmark at all (an empty shard
     used to fail with a zero-block launch and hang the others)."""
+    monkeypatch.setenv("OV2_BA_CTAS", "24")
     pb = synth.make_ba_problem(31, 12, 1500, 9000)
     ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
     rres, rflags = api.Optimizer(ctx).local_ba(ref)
