@@ -17,8 +17,9 @@
 //   B  Schur elimination, one warp per landmark, fp64 RED into the reduced camera system
 //   B2 fold of the privatised accumulation copies (multi-GPU: the partial systems of all ranks are summed here
 //      straight out of peer memory over NVLink - no NCCL call, no host round trip)
-//   C  reduced camera system: LM damping + solve by CTA 0 (n <= 96: Gauss-Jordan in shared memory; larger:
-//      blocked Cholesky with the FP64 tensor-core trailing update), gradient projection by CTA 1
+//   C  reduced camera system: LM damping + solve (n <= 96: Gauss-Jordan in CTA 0's shared memory; larger: blocked
+//      Cholesky, sequential part on CTA 0, FP64 tensor-core trailing update spread over the group), gradient
+//      projection by the last CTA
 //   D  back-substitution + candidate point + candidate cost (warp per landmark; candidate poses are computed
 //      redundantly by every CTA into shared memory)
 //   E  the trust-region controller (ba_lm_ctl.cuh) replayed by every CTA from the same reduced scalars: all CTAs
@@ -143,7 +144,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-constexpr unsigned long long BARRIER_TIMEOUT_NS = 4000000000ull;   // 4 s: a peer CTA / rank that never arrives
+constexpr unsigned long long BARRIER_TIMEOUT_NS = 30000000000ull;   // 30 s: a CTA that never arrives (includes waiting for CTA 0 inside a rank exchange)
+constexpr unsigned long long XSYNC_TIMEOUT_NS = 20000000000ull;     // 20 s: a peer rank that never arrives
 
 struct GroupBar {
     unsigned* count; unsigned* abort; unsigned G; unsigned epoch;
@@ -425,20 +427,33 @@ __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radi
         sA[i * PIT + n] = cG[i] + cRhs[i];
     }
     __syncthreads();
-    // thread -> (row group, column phase): TPR threads per row
+    // thread -> (row, column phase): TPR threads per row, each owning the columns c = j + 1 + sub (mod TPR).  The inner
+    // loop has a fixed trip count (predicated) so that its shared-memory loads are issued back to back.
     const int TPR = nt / n >= 4 ? 4 : (nt / n >= 2 ? 2 : 1);
     const int rows_per_pass = nt / TPR;
+    const int sub = tid % TPR, r0 = tid / TPR;
+    constexpr int QMAX = (96 + 1 + 3) / 4 + 1;      // columns per thread at TPR = 4 and n = 96
     for (int j = 0; j < n; ++j) {
         const double p = sA[j * PIT + j];
         if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same pivot
         double ip = (double)__frcp_rn((float)p);
         ip = ip * (2.0 - p * ip);
         ip = ip * (2.0 - p * ip);
-        const int sub = tid % TPR;
-        for (int r = tid / TPR; r < n; r += rows_per_pass) {
+        const double* rowj = sA + j * PIT;
+        for (int r = r0; r < n; r += rows_per_pass) {
             if (r == j) continue;
-            const double f = sA[r * PIT + j] * ip;
-            for (int c = j + 1 + sub; c <= n; c += TPR) sA[r * PIT + c] -= f * sA[j * PIT + c];
+            double* rowr = sA + r * PIT;
+            const double f = rowr[j] * ip;
+            if (TPR == 4) {
+                const int nq = (n - j + 3 - sub) >> 2;      // number of columns c = j + 1 + sub + 4 q <= n
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) {
+                    const int c = j + 1 + sub + 4 * q;
+                    if (q < nq) rowr[c] -= f * rowj[c];
+                }
+            } else {
+                for (int c = j + 1 + sub; c <= n; c += TPR) rowr[c] -= f * rowj[c];
+            }
         }
         __syncthreads();
     }
@@ -457,118 +472,129 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Blocked right-looking Cholesky S = U'U (upper triangle, in global/L2), block 32, on the augmented system [S | b]:
-// (1) warp 0 factors the 32 x 32 diagonal block in shared memory; (2) one thread per trailing column solves
-// U11' x = a (row panel U12, and y for b); (3) A22 -= U12' U12 on the FP64 tensor cores (DMMA), operands staged in
-// shared memory; then the backward substitution block by block.
-__device__ void reduced_solve_blocked(const Prob& P, double* T, int n, double radius, int first_iter, double* sP, double* scal) {
+// ------------------------------------------------------------------ reduced camera system, n > 96: blocked Cholesky across the group
+// Same factorisation as reduced_solve_blocked, but only the sequential part of a block step stays on CTA 0 (diagonal
+// block, row panel, forward substitution); the trailing update A22 -= U12' U12 - the one real contraction, (n - c1)^2 x 32
+// flops - is spread over every warp of the group (FP64 tensor cores, operands read from the row panel in L2).  Two group
+// barriers per block step; 9 steps for the 288 x 288 system of a 48-keyframe window.
+__device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, double radius, int first_iter, double* sP, double* scal,
+                                            GroupBar& bar, int bid, int G) {
     const int tid = threadIdx.x, nt = blockDim.x;
     double* cRhs = T; double* cG = T + n; double* cCn = T + 2 * n; double* A = T + 3 * n;
-    __shared__ int s_fail;
     __shared__ double s_w[MAX_N];
     __shared__ double sU[CH_NB][CH_NB + 1];
     __shared__ double s_idiag_all[MAX_N + CH_NB];
     __shared__ double s_t[CH_NB];
+    __shared__ int s_bad;
     double* w = s_w;
-    if (tid == 0) s_fail = 0;
-    for (int i = tid; i < n; i += nt) {
-        const double cn = cCn[i];
-        double sc = P.sc_cam[i];
-        if (first_iter) {
-            sc = 1.0 / (1.0 + sqrt(cn));
-            P.sc_cam[i] = sc;
-        }
-        const double diag = fmin(fmax(cn * sc * sc, 1e-6), 1e32);
-        A[(size_t)i * n + i] += diag / (radius * sc * sc);
-        w[i] = cG[i] + cRhs[i];
-    }
-    __syncthreads();
-    const int PW = ((n + 15) & ~15) + 8;                 // sP row pitch (doubles): bank-spread for the fragment loads
+    const int PW = ((n + 15) & ~15) + 8;                 // row pitch of the panel (doubles)
+    double* Pan = P.panel;                               // [CH_NB][PW] in global memory: what the other CTAs read
     const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+    const int gwarps = G * nwarp, gwarp = bid * nwarp + warp;
+    if (bid == 0) {
+        if (tid == 0) s_bad = 0;
+        for (int i = tid; i < n; i += nt) {
+            const double cn = cCn[i];
+            double sc = P.sc_cam[i];
+            if (first_iter) {
+                sc = 1.0 / (1.0 + sqrt(cn));
+                P.sc_cam[i] = sc;
+            }
+            const double diag = fmin(fmax(cn * sc * sc, 1e-6), 1e32);
+            A[(size_t)i * n + i] += diag / (radius * sc * sc);
+            w[i] = cG[i] + cRhs[i];
+        }
+        __syncthreads();
+    }
     for (int kb = 0; kb < n; kb += CH_NB) {
         const int nb = min(CH_NB, n - kb), c1 = kb + nb, m = n - c1;
-        double* s_idiag = s_idiag_all + kb;
-        for (int e = tid; e < CH_NB * CH_NB; e += nt) {
-            const int i = e >> 5, j = e & 31;
-            sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            bool bad = false;
-            for (int j = 0; j < CH_NB; ++j) {
-                const double d = sU[j][j];
-                // pivots of the Jacobi-scaled, damped system are O(1); outside the float range the factorisation is
-                // reported as failed (Ceres' LLT would return a useless step there)
-                bad = bad || !(d > 1e-30) || !(d < 1e30);
-                double is = (double)rsqrtf((float)d);                    // MUFU seed + 2 Newton steps in double
-                is = is * (1.5 - 0.5 * d * is * is);
-                is = is * (1.5 - 0.5 * d * is * is);
-                const double ujc = lane >= j ? sU[j][lane] * is : 0.0;   // row j of U (diagonal: d / sqrt(d))
-                __syncwarp();
-                sU[j][lane] = ujc;
-                if (lane == j) s_idiag[j] = is;
-                __syncwarp();
-#pragma unroll 4
-                for (int r = j + 1; r < CH_NB; ++r)
-                    if (lane >= r) sU[r][lane] -= sU[j][r] * ujc;
-                __syncwarp();
-            }
-            if (bad && lane == 0) s_fail = 1;
-        }
-        __syncthreads();
-        if (s_fail) break;                                               // uniform
-        for (int e = tid; e < CH_NB * CH_NB; e += nt) {
-            const int i = e >> 5, j = e & 31;
-            if (i < nb && j < nb && i <= j) A[(size_t)(kb + i) * n + kb + j] = sU[i][j];
-        }
         const int m16 = (m + 15) & ~15;
-        for (int cc = tid; cc <= m16; cc += nt) {
-            if (cc >= m && cc < m16) {                                   // zero padding of the operand panel
-#pragma unroll
-                for (int i = 0; i < CH_NB; ++i) sP[i * PW + cc] = 0.0;
-                continue;
+        if (bid == 0) {
+            double* s_idiag = s_idiag_all + kb;
+            for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+                const int i = e >> 5, j = e & 31;
+                sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
             }
-            const bool is_rhs = cc == m16;
-            if (!is_rhs && cc >= m) continue;
-            double a[CH_NB];
-#pragma unroll
-            for (int i = 0; i < CH_NB; ++i)
-                a[i] = i < nb ? (is_rhs ? w[kb + i] : A[(size_t)(kb + i) * n + c1 + cc]) : 0.0;
-#pragma unroll
-            for (int k = 0; k < CH_NB; ++k) {
-                const double x = a[k] * s_idiag[k];
-                a[k] = x;
-#pragma unroll
-                for (int i = k + 1; i < CH_NB; ++i) a[i] -= sU[k][i] * x;
+            __syncthreads();
+            if (warp == 0) {
+                bool bad = false;
+                for (int j = 0; j < CH_NB; ++j) {
+                    const double d = sU[j][j];
+                    bad = bad || !(d > 1e-30) || !(d < 1e30);
+                    double is = (double)rsqrtf((float)d);
+                    is = is * (1.5 - 0.5 * d * is * is);
+                    is = is * (1.5 - 0.5 * d * is * is);
+                    const double ujc = lane >= j ? sU[j][lane] * is : 0.0;
+                    __syncwarp();
+                    sU[j][lane] = ujc;
+                    if (lane == j) s_idiag[j] = is;
+                    __syncwarp();
+#pragma unroll 4
+                    for (int r = j + 1; r < CH_NB; ++r)
+                        if (lane >= r) sU[r][lane] -= sU[j][r] * ujc;
+                    __syncwarp();
+                }
+                if (bad && lane == 0) { s_bad = 1; scal[SC_CHOL_FAIL] = 1.0; }
             }
-            if (is_rhs) {
+            __syncthreads();
+            if (!s_bad) {
+                for (int e = tid; e < CH_NB * CH_NB; e += nt) {
+                    const int i = e >> 5, j = e & 31;
+                    if (i < nb && j < nb && i <= j) A[(size_t)(kb + i) * n + kb + j] = sU[i][j];
+                }
+                for (int cc = tid; cc <= m16; cc += nt) {
+                    if (cc >= m && cc < m16) {                                   // zero padding of the operand panel
 #pragma unroll
-                for (int i = 0; i < CH_NB; ++i) if (i < nb) { w[kb + i] = a[i]; s_t[i] = a[i]; }
-            } else {
+                        for (int i = 0; i < CH_NB; ++i) { sP[i * PW + cc] = 0.0; Pan[i * PW + cc] = 0.0; }
+                        continue;
+                    }
+                    const bool is_rhs = cc == m16;
+                    if (!is_rhs && cc >= m) continue;
+                    double a[CH_NB];
 #pragma unroll
-                for (int i = 0; i < CH_NB; ++i) {
-                    sP[i * PW + cc] = a[i];
-                    if (i < nb) A[(size_t)(kb + i) * n + c1 + cc] = a[i];
+                    for (int i = 0; i < CH_NB; ++i)
+                        a[i] = i < nb ? (is_rhs ? w[kb + i] : A[(size_t)(kb + i) * n + c1 + cc]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < CH_NB; ++k) {
+                        const double x = a[k] * s_idiag[k];
+                        a[k] = x;
+#pragma unroll
+                        for (int i = k + 1; i < CH_NB; ++i) a[i] -= sU[k][i] * x;
+                    }
+                    if (is_rhs) {
+#pragma unroll
+                        for (int i = 0; i < CH_NB; ++i) if (i < nb) { w[kb + i] = a[i]; s_t[i] = a[i]; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CH_NB; ++i) {
+                            sP[i * PW + cc] = a[i];
+                            Pan[i * PW + cc] = a[i];
+                            if (i < nb) A[(size_t)(kb + i) * n + c1 + cc] = a[i];
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();
-        for (int r = tid; r < m; r += nt) {
-            double acc = 0.0;
+        bar.sync();
+        if (scal[SC_CHOL_FAIL] != 0.0) return;                           // uniform across the group (written before the barrier)
+        if (bid == 0) {
+            for (int r = tid; r < m; r += nt) {
+                double acc = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < CH_NB; ++k) acc += sP[k * PW + r] * s_t[k];
-            w[c1 + r] -= acc;
+                for (int k = 0; k < CH_NB; ++k) acc += sP[k * PW + r] * s_t[k];
+                w[c1 + r] -= acc;
+            }
         }
         {
             const int mt = m16 >> 4, g = lane >> 2, t = lane & 3;
-            for (int idx = warp; idx < mt * mt; idx += nwarp) {
+            for (int idx = gwarp; idx < mt * mt; idx += gwarps) {
                 const int tr = idx / mt, tc = idx - tr * mt;
                 if (tr > tc) continue;
                 const int r0 = tr * 16, q0 = tc * 16;
                 double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
                 for (int k0 = 0; k0 < CH_NB; k0 += 4) {
-                    const double* pk = sP + (k0 + t) * PW;
+                    const double* pk = Pan + (size_t)(k0 + t) * PW;
                     const double a0 = pk[r0 + g], a1 = pk[r0 + 8 + g];
                     const double b0 = pk[q0 + g], b1 = pk[q0 + 8 + g];
                     dmma_884(acc[0][0][0], acc[0][0][1], a0, b0);
@@ -587,20 +613,17 @@ __device__ void reduced_solve_blocked(const Prob& P, double* T, int n, double ra
                         }
             }
         }
-        __syncthreads();
+        bar.sync();
     }
-    __syncthreads();
-    if (s_fail) {
-        if (tid == 0) scal[SC_CHOL_FAIL] = 1.0;
-        return;
-    }
+    if (bid != 0) return;
+    // ---- backward substitution U z = y, last block first (CTA 0)
     for (int kb = ((n - 1) / CH_NB) * CH_NB; kb >= 0; kb -= CH_NB) {
         const int nb = min(CH_NB, n - kb), c1 = kb + nb;
         for (int e = tid; e < CH_NB * CH_NB; e += nt) {
             const int i = e >> 5, j = e & 31;
             sU[i][j] = (i < nb && j < nb && i <= j) ? A[(size_t)(kb + i) * n + kb + j] : (i == j ? 1.0 : 0.0);
         }
-        for (int i = warp; i < nb; i += nwarp) {                         // t_i = y_i - U12[i][:] z_rest
+        for (int i = warp; i < nb; i += nwarp) {
             double acc = 0.0;
             for (int c = c1 + lane; c < n; c += 32) acc += A[(size_t)(kb + i) * n + c] * w[c];
             acc = warp_sum(acc);
@@ -695,7 +718,7 @@ __device__ __forceinline__ void xsync(const Peers& X, unsigned long long& xepoch
                 if (ld_acquire_gpu(abort)) break;
                 const unsigned long long t = global_ns();
                 if (t0 == 0) t0 = t;
-                else if (t - t0 > 2 * BARRIER_TIMEOUT_NS) { atomicExch(abort, 1u); break; }
+                else if (t - t0 > XSYNC_TIMEOUT_NS) { atomicExch(abort, 1u); break; }
             }
         }
     }
@@ -711,7 +734,7 @@ __device__ __forceinline__ double ld_peer(const double* p) {
 // ------------------------------------------------------------------ the persistent solve kernel
 struct SolveOut { int iterations; double initial_cost, final_cost; int termination; };
 
-__global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restrict__ probs, int nprob, int G, Peers X) {
+__global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restrict__ probs, int nprob, int G, Peers X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ lmctl::State S;
     __shared__ int s_action, s_ncv, s_any, s_refine, s_trivial;
@@ -757,11 +780,18 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
             double* x_invd = P.invd[xi]; double* c_invd = P.invd[xi ^ 1];
             // ---- set-up: Program::RemoveFixedBlocks (keyframes that are constant or touch no active residual drop out),
             //      candidate := x for the blocks that are not in this solve's program, accumulators zeroed
+            // (flags are collected per CTA in shared memory first: thousands of stores from every SM to the same few bytes
+            //  serialise in L2 - measured 7 us per CTA of the group)
+            for (int c = tid; c < P.ncam; c += THREADS) s_slot[c] = 0;
+            __syncthreads();
             for (int i = gtid; i < P.nobs; i += gthreads)
                 if (P.active[i] && !(P.obs_type && P.obs_type[i] == 2)) {
-                    cam_used[P.obs_cam[i]] = 1;
-                    cam_used[P.lm_anchor_cam[P.obs_lm[i]]] = 1;
+                    s_slot[P.obs_cam[i]] = 1;
+                    s_slot[P.lm_anchor_cam[P.obs_lm[i]]] = 1;
                 }
+            __syncthreads();
+            for (int c = tid; c < P.ncam; c += THREADS)
+                if (s_slot[c]) cam_used[c] = 1;
             for (int i = gtid; i < 7 * P.ncam; i += gthreads) c_pose[i] = x_pose[i];
             for (int i = gtid; i < P.npts; i += gthreads) c_invd[i] = x_invd[i];
             for (size_t i = gtid; i < (size_t)P.ncopy * blk; i += gthreads) P.acc[i] = 0.0;
@@ -869,12 +899,8 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                 TR(3);
                 // ---- C: reduced camera system (CTA 0); gradient projection |x - Plus(x, -g)|_inf (last CTA); the other
                 //      CTAs clear the accumulation copies for the next iteration (T is separate whenever ncopy > 1)
-                if (bid == 0) {
-                    if (n > 0) {
-                        if (P.solve_blocked) reduced_solve_blocked(P, T, n, radius, first_iter, s_work, scal);
-                        else reduced_solve_small(P, T, n, radius, first_iter, s_work, scal);
-                    }
-                }
+                const bool group_solve = P.solve_blocked && n > 0;
+                if (bid == 0 && !group_solve && n > 0) reduced_solve_small(P, T, n, radius, first_iter, s_work, scal);
                 if (bid == G - 1 && x_is_new && n > 0) {
                     if (bid == 0) __syncthreads();
                     double gm = 0.0;
@@ -889,6 +915,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_lm_kernel(const Prob* __restric
                     gm = warp_max(gm);
                     if (lane == 0) atomic_max_pos(scal + SC_GMAX_CAM, gm);
                 }
+                if (group_solve) reduced_solve_blocked_group(P, T, n, radius, first_iter, s_work, scal, bar, bid, G);
                 TR(4);
                 bar.sync();
                 TR(5);
@@ -1076,7 +1103,7 @@ struct HostPlan {
     size_t off_prob, off_pose, off_invd, off_apx, off_opx, off_lac, off_oc, off_ol, off_lp, off_pc, off_ty, in_bytes;   // uploaded block
     // device-only work areas (offsets into the work block)
     size_t w_pose1, w_invd1, w_active, w_flags, w_camused, w_camslot, w_Jr, w_Ja, w_Jo, w_Jl, w_chi2, w_dpos, w_sclm, w_ete, w_ge,
-           w_acc, w_total, w_scal, w_z, w_sccam, w_counts, w_bar, w_result, w_trace, work_bytes, zero_off, zero_bytes;
+           w_acc, w_total, w_scal, w_z, w_panel, w_sccam, w_counts, w_bar, w_result, w_trace, work_bytes, zero_off, zero_bytes;
     int ncv_max, n_max, ncopy, solve_blocked;
     size_t blk, smem_work_off, smem_bytes;
 };
@@ -1146,6 +1173,7 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     H.w_total = take(work_off, sizeof(double) * H.blk);
     H.w_scal = take(work_off, sizeof(double) * 2 * SC_COUNT);
     H.w_z = take(work_off, sizeof(double) * MAX_N);
+    H.w_panel = take(work_off, sizeof(double) * CH_NB * (size_t)(MAX_N + 24));
     // dynamic shared memory: [keyframes 12 doubles each][slots][union: Schur scratch | solve area]
     size_t s = sizeof(double) * 12 * (size_t)ncam + sizeof(int) * (size_t)ncam;
     s = (s + 15) & ~(size_t)15;
@@ -1200,7 +1228,7 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.chi2 = (double*)(dwork + H.w_chi2); P.dpos = (uint8_t*)(dwork + H.w_dpos);
     P.sc_lm = (double*)(dwork + H.w_sclm); P.ete = (double*)(dwork + H.w_ete); P.ge = (double*)(dwork + H.w_ge);
     P.acc = (double*)(dwork + H.w_acc); P.total = (double*)(dwork + H.w_total); P.scal = (double*)(dwork + H.w_scal);
-    P.z = (double*)(dwork + H.w_z); P.sc_cam = (double*)(dwork + H.w_sccam);
+    P.z = (double*)(dwork + H.w_z); P.sc_cam = (double*)(dwork + H.w_sccam); P.panel = (double*)(dwork + H.w_panel);
     P.counts = (double*)(dwork + H.w_counts); P.bar = (unsigned*)(dwork + H.w_bar); P.result = (Result*)(dwork + H.w_result);
     P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;

@@ -42,6 +42,7 @@ struct Prob {
     double* total;                     // [blk]: folded / all-rank system
     double* scal;                      // [2][SC_COUNT]
     double *z, *sc_cam, *counts;
+    double* panel;                     // [CH_NB][n + 24]: row panel of the blocked Cholesky (read by every CTA of the group)
     unsigned* bar;                     // [0] group barrier counter, [1] abort flag
     Result* result;
     unsigned long long* trace;         // optional [16] per-phase nanoseconds (OV2_BA_TRACE=1), NULL otherwise

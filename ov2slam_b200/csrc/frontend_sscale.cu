@@ -156,21 +156,61 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) ss_sweep_kernel(Sweep
     __syncthreads();
     const double quality = A.quality[fr];
     const float* resp = A.resp + (size_t)fr * ncells * (size_t)(cs * cs);
+    constexpr int NV = 40;                                        // register-resident cells: cs * cs <= 1280 (cs <= 35)
+    const int npx = cs * cs;
+    const bool in_regs = npx <= NV * 32;
+    const int sy = 32 / cs, sx = 32 - sy * cs;
     for (int r = warp; r < A.nhc; r += nwarps) {
         for (int c = 0; c < A.nwc; ++c) {
+            const int cell = r * A.nwc + c;
+            const int x0 = c * cs, y0 = r * cs;
+            const bool search = !occ[r * (A.nwc + 1) + c] && (x0 + cs < A.w - 1 && y0 + cs < A.h - 1);
+            const float* rc = resp + (size_t)cell * npx;
+            // the cell's responses do not depend on any other cell: fetch them (all loads in flight at once) BEFORE waiting
+            // for the neighbours, so the L2 latency hides behind the wavefront dependency
+            float v[NV];
+            if (search && in_regs) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int i = lane + 32 * q;
+                    v[q] = i < npx ? __ldg(rc + i) : -INFINITY;
+                }
+            }
             if (r > 0) {
                 // wait until row r-1 has finished cell c+1 (or its last cell)
                 const int need = min(c + 2, A.nwc);
                 while (progress[r - 1] < need) { }
                 __threadfence_block();
             }
-            const int cell = r * A.nwc + c;
-            const int x0 = c * cs, y0 = r * cs;
-            if (!occ[r * (A.nwc + 1) + c] && (x0 + cs < A.w - 1 && y0 + cs < A.h - 1)) {
-                const float* rc = resp + (size_t)cell * (cs * cs);
+            if (search) {
                 for (int round = 0; round < 2; ++round) {
                     float mx; int idx;
-                    cell_argmax_warp(rc, bm, wpr, x0, y0, cs, lane, mx, idx);
+                    if (in_regs) {
+                        float bv = -INFINITY;
+                        int bi = 0x7fffffff;
+                        int yy = lane / cs, xx = lane - yy * cs;
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) {
+                            const int i = lane + 32 * q;
+                            if (i < npx) {
+                                const int gx = x0 + xx, gy = y0 + yy;
+                                const bool masked = (bm[(size_t)gy * wpr + (gx >> 5)] >> (gx & 31)) & 1u;
+                                const float val = masked ? 0.0f : v[q];          // response * 0.0f compares equal to 0
+                                if (val > bv) { bv = val; bi = i; }
+                                xx += sx; yy += sy;
+                                if (xx >= cs) { xx -= cs; yy++; }
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(FULL, bv, o);
+                            const int oi = __shfl_xor_sync(FULL, bi, o);
+                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                        }
+                        mx = bv; idx = bi;
+                    } else {
+                        cell_argmax_warp(rc, bm, wpr, x0, y0, cs, lane, mx, idx);
+                    }
                     const int ly = idx / cs, lx = idx - ly * cs;
                     const int px = x0 + lx, py = y0 + ly;
                     if (px < A.roi_x || py < A.roi_y || px >= A.roi_x + A.roi_w || py >= A.roi_y + A.roi_h) break;   // `continue` of the cell loop

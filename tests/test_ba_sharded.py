@@ -140,6 +140,11 @@ def test_p2p_sharded_solve_matches_unsharded(ctx, monkeypatch, world, empty):
             e[k] = e[k][:0].copy()
         shards.append((e, np.zeros(0, np.int64), np.zeros(0, np.int64)))
     ctxs = [api.Context(0) for _ in range(world)]
+    for c in ctxs:
+        # every context allocates its arenas / pinned staging on its first solve; do that BEFORE the concurrent solves: a
+        # cudaMalloc / cudaHostAlloc issued while another rank's kernel spins in a rank barrier on the SAME device can block
+        # behind that kernel (ranks on different devices, the real configuration, do not share this hazard)
+        api.Optimizer(c).local_ba({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()})
     comms = [api.BaComm(ctxs[r], r, world) for r in range(world)]
     api.BaComm.connect_local(comms)
     for rep in range(2):                       # twice: epochs of consecutive launches must not collide

@@ -13,7 +13,7 @@ from oracle import image_ref as R
 
 pytestmark = pytest.mark.gpu
 
-SUBPIX_TOL = 2e-4   # px; cv2-vs-restatement itself differs by up to 3e-5 (double summation order)
+SUBPIX_TOL = 1e-5   # px; observed on a B200 vs cv2 4.13: 6 135 points, 100 % bit-equal (scripts/parity_stats.py, profiles/r2_parity_stats.json)
 KLT_TOL = 1e-3      # px; see test_klt_parity
 
 
@@ -569,8 +569,10 @@ def test_c4_full_chain_stereo_1280x720(ctx):
     newi = np.empty((ncell, 2), np.int32)
     cnt = np.zeros(1, np.int32)
     q = np.array([L.C4_Q])
-    fe.detect_single_scale(pyr["cur"], cs, 0, 1, q, newp, cnt, np.array([0, len(out)], np.int32), out, None, newi)
-    ref_i, ref_q, _ = R.detect_single_scale_nosubpix(eq["cur"], cs, out, (0, 0, w, h), L.C4_Q, use_cv2=False)
+    # vcurkps = the surviving tracks, as VisualFrontEnd hands them on (failed tracks may lie outside the image)
+    alive = np.ascontiguousarray(out[st.astype(bool)])
+    fe.detect_single_scale(pyr["cur"], cs, 0, 1, q, newp, cnt, np.array([0, len(alive)], np.int32), alive, None, newi)
+    ref_i, ref_q, _ = R.detect_single_scale_nosubpix(eq["cur"], cs, alive, (0, 0, w, h), L.C4_Q, use_cv2=False)
     n = int(cnt[0])
     assert n == len(ref_i) and np.array_equal(newi[:n], ref_i) and q[0] == ref_q and n > 150
     assert (newp[n:] == -1).all()
