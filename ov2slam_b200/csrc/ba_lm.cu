@@ -279,7 +279,8 @@ __device__ __forceinline__ double eval_block(const Prob& P, int i, int lm, const
 // schur_eliminator_impl.h:179-308 for a scalar e-block: E'E, E'r, F'F, F'r, E'F per touching keyframe, then
 // S -= (E'F)' (E'E)^-1 (E'F), rhs -= (E'F)' (E'E)^-1 E'r.  The anchor keyframe's F'F / F'r / column norms are summed
 // over the landmark's observations in registers and leave the warp once.
-__device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot,
+constexpr int SCH = 8;   // observations staged per chunk (C3: 4 per landmark, C5: 7.5)
+__device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot, double* sJ, int* smeta,
                                                int l, int lane, double radius, int first_iter, double* acc, int n, double* scal) {
     const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
     double* const cRhs = acc; double* const cG = acc + n; double* const cCn = acc + 2 * n; double* const cS = acc + 3 * n;
@@ -324,14 +325,29 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
     double aFF0 = 0.0, aFF1 = 0.0, aG = 0.0, aCn = 0.0;
     const int e0a = lane / 6, e0b = lane - 6 * e0a;
     const int e1 = lane + 32, e1a = e1 / 6, e1b = e1 - 6 * e1a;
-    for (int p = p0; p < p1; ++p) {
-        if (!P.active[p]) continue;
-        if (P.obs_type && P.obs_type[p] == 2) continue;   // e-block-only row (schur_eliminator_impl.h:196-217)
-        const int so = s_slot[P.obs_cam[p]];
-        const double* Ja = P.Ja + 12 * (size_t)p;
-        const double* Jo = P.Jo + 12 * (size_t)p;
-        const double jl0 = P.Jl[2 * (size_t)p], jl1 = P.Jl[2 * (size_t)p + 1];
-        const double r0 = P.Jr[2 * (size_t)p], r1 = P.Jr[2 * (size_t)p + 1];
+    // The Jacobian rows of the landmark's observations are staged in this warp's shared-memory slice SCH at a time (coalesced
+    // loads, all in flight together): the per-observation loop below then never waits on L2 (with one dependent global
+    // load chain per observation and 8-16 warps per SM the phase was latency bound, 2.4x slower than the RED issue rate).
+    double* sJa = sJ; double* sJo = sJ + 12 * SCH; double* sJl = sJ + 24 * SCH; double* sJr = sJ + 26 * SCH;
+    for (int pb = p0; pb < p1; pb += SCH) {
+        const int cnt = min(SCH, p1 - pb);
+        __syncwarp();
+        for (int e = lane; e < 12 * cnt; e += 32) { sJa[e] = P.Ja[12 * (size_t)pb + e]; sJo[e] = P.Jo[12 * (size_t)pb + e]; }
+        if (lane < 2 * cnt) { sJl[lane] = P.Jl[2 * (size_t)pb + lane]; sJr[lane] = P.Jr[2 * (size_t)pb + lane]; }
+        if (lane < cnt) {
+            const int p = pb + lane;
+            int mt = -3;                                         // inactive
+            if (P.active[p]) mt = (P.obs_type && P.obs_type[p] == 2) ? -2 : s_slot[P.obs_cam[p]];   // -2: e-block-only row (schur_eliminator_impl.h:196-217)
+            smeta[lane] = mt;
+        }
+        __syncwarp();
+    for (int q = 0; q < cnt; ++q) {
+        const int so = smeta[q];
+        if (so < -1) continue;
+        const double* Ja = sJa + 12 * q;
+        const double* Jo = sJo + 12 * q;
+        const double jl0 = sJl[2 * q], jl1 = sJl[2 * q + 1];
+        const double r0 = sJr[2 * q], r1 = sJr[2 * q + 1];
         if (sa >= 0) {
             aFF0 += Ja[e0a] * Ja[e0b] + Ja[6 + e0a] * Ja[6 + e0b];
             if (e1 < 36) aFF1 += Ja[e1a] * Ja[e1b] + Ja[6 + e1a] * Ja[6 + e1b];
@@ -349,8 +365,8 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             // E'F row of this keyframe: a stereo keyframe contributes two residual blocks (left and right camera) to the
             // same pose block, so look the slot up before appending a new entry
             int idx = -1;
-            for (int q = lane; q < m; q += 32)
-                if (s_eslot[q] == so) idx = q;
+            for (int qq = lane; qq < m; qq += 32)
+                if (s_eslot[qq] == so) idx = qq;
             idx = __reduce_max_sync(FULL, idx);
             const bool fresh = idx < 0;
             if (fresh) idx = m;
@@ -373,6 +389,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             if (fresh) m++;
         }
         __syncwarp();
+    }
     }
     if (sa >= 0) {
         if (e0a <= e0b) atomicAdd(cS + (size_t)(6 * sa + e0a) * n + 6 * sa + e0b, aFF0);
@@ -399,11 +416,45 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
 }
 
 // ------------------------------------------------------------------ reduced camera system, n <= 96: CTA-wide Gauss-Jordan in shared memory
-// Augmented system [S + D | b] in shared memory (row pitch n + 2, odd multiple keeps column reads conflict-light);
-// pivot step j updates every row r != j for the columns c > j: A[r][c] -= (A[r][j] / A[j][j]) A[j][c].  Row j and
-// column j are not written in step j, so ONE block barrier per pivot suffices and no substitution passes follow
-// (a Cholesky + two triangular solves is 3n dependent steps).  Pivots equal those of the LDL' / Cholesky
-// factorisation (no pivoting: S is SPD after LM damping), so "pivot <= 0" is the failure test Ceres' LLT applies.
+// Augmented system [S + D | b] in shared memory (row pitch n + 2); pivot step j updates every row r != j for the columns
+// c > j: A[r][c] -= (A[r][j] / A[j][j]) A[j][c].  Row j and column j are not written in step j, so ONE block barrier per
+// pivot suffices and no substitution passes follow (a Cholesky + two triangular solves is 3n dependent steps).  Pivots
+// equal those of the LDL' / Cholesky factorisation (no pivoting: S is SPD after LM damping), so "pivot <= 0" is the
+// failure test Ceres' LLT applies.  Four threads per row; a thread stages the pivot-row and own-row entries of its
+// columns in registers first (all shared-memory loads in flight together), then updates and stores.
+template <int QMAX>
+__device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fail) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int sub = tid & 3, r0 = tid >> 2, rows_per_pass = nt >> 2;
+    for (int j = 0; j < n; ++j) {
+        const double p = sA[j * PIT + j];
+        if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) *s_fail = 1; break; }   // uniform: every thread reads the same pivot
+        double ip = (double)__frcp_rn((float)p);
+        ip = ip * (2.0 - p * ip);
+        ip = ip * (2.0 - p * ip);
+        const double* rowj = sA + j * PIT;
+        const int c0 = j + 1 + sub;
+        const int nq = (n - j + 3 - sub) >> 2;              // columns c = c0 + 4 q <= n
+        double pj[QMAX];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) pj[q] = q < nq ? rowj[c0 + 4 * q] : 0.0;
+        for (int r = r0; r < n; r += rows_per_pass) {
+            if (r == j) continue;
+            double* rowr = sA + r * PIT;
+            const double f = rowr[j] * ip;
+            double a[QMAX];
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) a[q] = q < nq ? rowr[c0 + 4 * q] : 0.0;
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) a[q] -= f * pj[q];
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q)
+                if (q < nq) rowr[c0 + 4 * q] = a[q];
+        }
+        __syncthreads();
+    }
+}
+
 __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radius, int first_iter, double* sA, double* scal) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int PIT = n + 2;
@@ -427,36 +478,9 @@ __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radi
         sA[i * PIT + n] = cG[i] + cRhs[i];
     }
     __syncthreads();
-    // thread -> (row, column phase): TPR threads per row, each owning the columns c = j + 1 + sub (mod TPR).  The inner
-    // loop has a fixed trip count (predicated) so that its shared-memory loads are issued back to back.
-    const int TPR = nt / n >= 4 ? 4 : (nt / n >= 2 ? 2 : 1);
-    const int rows_per_pass = nt / TPR;
-    const int sub = tid % TPR, r0 = tid / TPR;
-    constexpr int QMAX = (96 + 1 + 3) / 4 + 1;      // columns per thread at TPR = 4 and n = 96
-    for (int j = 0; j < n; ++j) {
-        const double p = sA[j * PIT + j];
-        if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same pivot
-        double ip = (double)__frcp_rn((float)p);
-        ip = ip * (2.0 - p * ip);
-        ip = ip * (2.0 - p * ip);
-        const double* rowj = sA + j * PIT;
-        for (int r = r0; r < n; r += rows_per_pass) {
-            if (r == j) continue;
-            double* rowr = sA + r * PIT;
-            const double f = rowr[j] * ip;
-            if (TPR == 4) {
-                const int nq = (n - j + 3 - sub) >> 2;      // number of columns c = j + 1 + sub + 4 q <= n
-#pragma unroll
-                for (int q = 0; q < QMAX; ++q) {
-                    const int c = j + 1 + sub + 4 * q;
-                    if (q < nq) rowr[c] -= f * rowj[c];
-                }
-            } else {
-                for (int c = j + 1 + sub; c <= n; c += TPR) rowr[c] -= f * rowj[c];
-            }
-        }
-        __syncthreads();
-    }
+    if (n <= 48) gj_pivots<13>(sA, n, PIT, &s_fail);         // (n + 1 + 3) / 4 columns per thread
+    else if (n <= 64) gj_pivots<17>(sA, n, PIT, &s_fail);
+    else gj_pivots<25>(sA, n, PIT, &s_fail);
     __syncthreads();
     if (s_fail) {
         if (tid == 0) scal[SC_CHOL_FAIL] = 1.0;
@@ -763,6 +787,8 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
         const int etf_stride = 6 * (P.ncv_max + 1);
         double* s_etf = s_work + (size_t)warp * etf_stride;
         int* s_eslot = reinterpret_cast<int*>(s_work + (size_t)WARPS * etf_stride) + warp * (P.ncv_max + 1);
+        double* sJ = s_work + (size_t)WARPS * etf_stride + (((size_t)WARPS * (P.ncv_max + 1) + 1) >> 1) + (size_t)warp * (28 * SCH);
+        int* smeta = reinterpret_cast<int*>(s_work + (size_t)WARPS * etf_stride + (((size_t)WARPS * (P.ncv_max + 1) + 1) >> 1) + (size_t)WARPS * (28 * SCH)) + warp * SCH;
         const int gthreads = G * THREADS, gtid = bid * THREADS + tid;
         const int gwarps = G * WARPS, gwarp = bid * WARPS + warp;
         const size_t blk = P.blk;                                                  // doubles per accumulation copy (n_max based)
@@ -854,7 +880,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 // ---- B: Schur elimination into this CTA's accumulation copy
                 {
                     double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
-                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, l, lane, radius, first_iter, acc, n, scal);
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, acc, n, scal);
                 }
                 bar.sync();
                 TR(2);
@@ -1178,7 +1204,8 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     size_t s = sizeof(double) * 12 * (size_t)ncam + sizeof(int) * (size_t)ncam;
     s = (s + 15) & ~(size_t)15;
     H.smem_work_off = s;
-    const size_t schur = (size_t)WARPS * (6 * (size_t)(ncv + 1) * sizeof(double) + (size_t)(ncv + 1) * sizeof(int));
+    const size_t schur = (size_t)WARPS * 6 * (size_t)(ncv + 1) * sizeof(double) + ((((size_t)WARPS * (ncv + 1) + 1) >> 1) << 3) +
+                         (size_t)WARPS * 28 * SCH * sizeof(double) + (size_t)WARPS * SCH * sizeof(int) + 16;
     const size_t solve = H.solve_blocked ? (size_t)CH_NB * (size_t)((((size_t)H.n_max + 15) & ~(size_t)15) + 8) * sizeof(double)
                                          : (size_t)H.n_max * (size_t)(H.n_max + 2) * sizeof(double);
     H.smem_bytes = s + (schur > solve ? schur : solve) + 16;
@@ -1374,7 +1401,19 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     const Prob* dp = dprobs;
     void* kargs[] = {(void*)&dp, (void*)&nprob, (void*)&G, (void*)&X};
     if (ctx->profiling) ov2_prof_begin(ctx);
-    cudaError_t le = cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(grid), dim3(THREADS), kargs, smem_max, s);
+    // grid <= resident capacity, so on a GPU this process owns every CTA starts at once whichever launch API is used.  The
+    // plain launch is the default: cooperative launches were measured to start their CTAs one after the other (~4 us each)
+    // and are not run concurrently with another cooperative kernel (ranks sharing one GPU in the tests); OV2_BA_COOP=1
+    // selects cudaLaunchCooperativeKernel (co-residency guaranteed by the driver).  A CTA that never arrives trips the
+    // barrier timeout instead of hanging the device.
+    const char* coop = getenv("OV2_BA_COOP");
+    cudaError_t le;
+    if (coop && atoi(coop) != 0) {
+        le = cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(grid), dim3(THREADS), kargs, smem_max, s);
+    } else {
+        ba_lm_kernel<<<grid, THREADS, smem_max, s>>>(dp, nprob, G, X);
+        le = cudaGetLastError();
+    }
     ctx->launches++;
     if (le != cudaSuccess) return ov2_fail(ctx, OV2_ERR_CUDA, "ba_lm_kernel launch", le);
     if (ctx->profiling) ov2_prof_end(ctx, "ba_lm_kernel");

@@ -227,7 +227,6 @@ __device__ __forceinline__ void store_owned(const uint8_t* t, int c0, int r0, in
 __global__ void __launch_bounds__(FUSED_THREADS, 2) pyr_levels_kernel(FusedArgs A, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
-    uint8_t* l0buf[2] = {smem + OFF_L0A, smem + OFF_L0B};
     uint8_t* t1 = smem + OFF_L1; uint8_t* t2 = smem + OFF_L2; uint8_t* t3 = smem + OFF_L3;
     const int tiles_per_frame = A.ntx * A.nty, ntiles = tiles_per_frame * A.count;
     if (threadIdx.x == 0) { tma::mbar_init(&s_bar[0], 1); tma::mbar_init(&s_bar[1], 1); }
@@ -236,7 +235,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pyr_levels_kernel(FusedArgs 
         const int fr = tile / tiles_per_frame, rem = tile - fr * tiles_per_frame;
         const int ty = rem / A.ntx, tx = rem - ty * A.ntx;
         tma::mbar_expect_tx(&s_bar[buf], (uint32_t)L0_BYTES);
-        tma::load_3d(l0buf[buf], &tmap, &s_bar[buf], 8 * tx * T3W - 16, 8 * ty * T3H - 14, A.first + fr);
+        tma::load_3d(smem + (buf ? OFF_L0B : OFF_L0A), &tmap, &s_bar[buf], 8 * tx * T3W - 16, 8 * ty * T3H - 14, A.first + fr);
     };
     int it = 0;
     if ((int)blockIdx.x < ntiles && threadIdx.x == 0) issue(blockIdx.x, 0);
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pyr_levels_kernel(FusedArgs 
         const int ty = rem / A.ntx, tx = rem - ty * A.ntx;
         const int x3 = tx * T3W, y3 = ty * T3H;
         tma::mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
-        uint8_t* t0 = l0buf[buf];
+        uint8_t* t0 = smem + (buf ? OFF_L0B : OFF_L0A);      // (no pointer array: keeps the accesses LDS, not generic LD)
         // ---- level 0 -> 1
         reflect_cols<P0, W0T, H0T>(t0, 8 * x3 - 14, A.w[0]);
         __syncthreads();

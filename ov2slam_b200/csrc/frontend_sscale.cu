@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) ss_sweep_kernel(Sweep
             if (r > 0) {
                 // wait until row r-1 has finished cell c+1 (or its last cell)
                 const int need = min(c + 2, A.nwc);
-                while (progress[r - 1] < need) { }
+                while (progress[r - 1] < need) __nanosleep(40);   // yield the issue slots to the rows that are working
                 __threadfence_block();
             }
             if (search) {

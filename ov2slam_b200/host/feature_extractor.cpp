@@ -13,17 +13,20 @@
 #include <mutex>
 
 #include "../../include/ov2b200.h"
+#include "pyr_cache.hpp"
 
 namespace {
 struct State {
     ov2_ctx* ctx = nullptr;
-    ov2_pyr* pyr = nullptr;
-    int w = 0, h = 0;
+    ov2_pyr* pyr = nullptr;                 // the image of the current call (a slot of `cache`)
+    // the tracking image and the raw image of a keyframe (map_manager.cpp:286-341: detect on `im`, describe on `imraw`,
+    // twice): each is uploaded once, whatever the number of calls (pyr_cache.hpp)
+    ov2shim::PyrCache<3> cache;
     std::mutex mu;
 };
 State& st() { static State s; return s; }
 
-// (re)load the image into the single-frame device slot; returns false (and reports) on failure
+// make `im` the current device image (uploaded only if it is not already there); false (and reports) on failure
 bool load_image(State& s, const cv::Mat& im) {
     if (!s.ctx) {
         const char* e = getenv("OV2_DEVICE");
@@ -33,13 +36,8 @@ bool load_image(State& s, const cv::Mat& im) {
             return false;
         }
     }
-    if (!s.pyr || s.w != im.cols || s.h != im.rows) {
-        if (s.pyr) ov2_pyr_destroy(s.pyr);
-        s.pyr = nullptr;
-        if (ov2_pyr_create(s.ctx, 1, im.cols, im.rows, 0, &s.pyr) != OV2_OK) return false;
-        s.w = im.cols; s.h = im.rows;
-    }
-    if (ov2_pyr_build(s.ctx, s.pyr, im.data, im.step, im.step * im.rows, 0, 1) != OV2_OK) {
+    s.pyr = s.cache.get(s.ctx, im, 0);
+    if (!s.pyr) {
         fprintf(stderr, "[ov2b200] FeatureExtractor: %s\n", ov2_last_error(s.ctx));
         return false;
     }

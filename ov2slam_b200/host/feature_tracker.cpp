@@ -11,17 +11,18 @@
 #include <mutex>
 #include <thread>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/ov2b200.h"
+#include "pyr_cache.hpp"
 
 struct FeatureTracker::ThreadState {
     ov2_ctx* ctx = nullptr;
-    ov2_pyr* prev = nullptr;
-    ov2_pyr* cur = nullptr;
-    int w = 0, h = 0, nlev = 0;
+    // prev-left, cur-left, right + one spare: every image is uploaded (and its levels built) once, however many
+    // fbKltTracking calls read it (pyr_cache.hpp)
+    ov2shim::PyrCache<4> cache;
     ~ThreadState() {
-        if (prev) ov2_pyr_destroy(prev);
-        if (cur) ov2_pyr_destroy(cur);
+        cache.clear();
         if (ctx) ov2_destroy(ctx);
     }
 };
@@ -71,17 +72,9 @@ void FeatureTracker::fbKltTracking(const std::vector<cv::Mat> &vprevpyr, const s
     const cv::Mat& p0 = vprevpyr[0];
     const cv::Mat& c0 = vcurpyr[0];
     const int nlev_extra = (int)vprevpyr.size() / 2 - 1;
-    if (!s->prev || s->w != p0.cols || s->h != p0.rows || s->nlev != nlev_extra) {
-        if (s->prev) ov2_pyr_destroy(s->prev);
-        if (s->cur) ov2_pyr_destroy(s->cur);
-        s->prev = s->cur = nullptr;
-        if (ov2_pyr_create(s->ctx, 1, p0.cols, p0.rows, nlev_extra, &s->prev) != OV2_OK ||
-            ov2_pyr_create(s->ctx, 1, p0.cols, p0.rows, nlev_extra, &s->cur) != OV2_OK) { fail_all(); return; }
-        s->w = p0.cols; s->h = p0.rows; s->nlev = nlev_extra;
-    }
-    // level-0 Mats are ROIs of border-padded buffers: honour their row step
-    if (ov2_pyr_build(s->ctx, s->prev, p0.data, p0.step, p0.step * p0.rows, 0, 1) != OV2_OK ||
-        ov2_pyr_build(s->ctx, s->cur, c0.data, c0.step, c0.step * c0.rows, 0, 1) != OV2_OK) {
+    ov2_pyr* dprev = s->cache.get(s->ctx, p0, nlev_extra);
+    ov2_pyr* dcur = dprev ? s->cache.get(s->ctx, c0, nlev_extra) : nullptr;
+    if (!dprev || !dcur) {
         fprintf(stderr, "[ov2b200] fbKltTracking: %s\n", ov2_last_error(s->ctx));
         fail_all();
         return;
@@ -94,7 +87,7 @@ void FeatureTracker::fbKltTracking(const std::vector<cv::Mat> &vprevpyr, const s
     prm.fb_dist = fmax_fbklt_dist;
     std::vector<uint8_t> status(nbkps, 0);
     static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "Point2f layout");
-    ov2_status st = ov2_fb_klt(s->ctx, s->prev, s->cur, &prm, (int)nbkps, nullptr, 0, (int)nbkps, nullptr, nbpyrlvl,
+    ov2_status st = ov2_fb_klt(s->ctx, dprev, dcur, &prm, (int)nbkps, nullptr, 0, (int)nbkps, nullptr, nbpyrlvl,
                                reinterpret_cast<const float*>(vkps.data()), reinterpret_cast<float*>(vpriorkps.data()),
                                status.data());
     if (st != OV2_OK) {
@@ -105,31 +98,83 @@ void FeatureTracker::fbKltTracking(const std::vector<cv::Mat> &vprevpyr, const s
     for (size_t i = 0; i < nbkps; ++i) vkpstatus.push_back(status[i] != 0);
 }
 
-// Outside the hot-path scope: line search for rectified stereo priors.
+// ---------------------------------------------------------------------------------------------------------------
+// cv::getRectSubPix for 8-bit source and destination as OpenCV's own template evaluates it (imgproc/samplers.cpp,
+// getRectSubPix_Cn_<uchar, uchar, int, scale_fixpt, cast_8u>): bilinear weights in 16-bit fixed point
+// (cvRound(w * 65536)), result (sum + 2^15) >> 16, window centred on `center`, pixels outside the image replicated from
+// the border.  (OpenCV builds WITH Intel IPP route this call to ippiCopySubpix, which differs from the template by one
+// grey level on ~0.7 % of the pixels: the reference's result depends on how its OpenCV was built; the template is what
+// distribution / ROS builds run.)
+namespace {
+inline int cv_round(float v) { return (int)lrintf(v); }
+void get_rect_subpix_u8(const cv::Mat& src, int ww, int wh, float cx, float cy, std::vector<unsigned char>& dst) {
+    dst.resize((size_t)ww * wh);
+    cx -= (ww - 1) * 0.5f;
+    cy -= (wh - 1) * 0.5f;
+    const int ipx = (int)floorf(cx), ipy = (int)floorf(cy);
+    const float a = cx - ipx, b = cy - ipy;
+    const int a11 = cv_round((1.f - a) * (1.f - b) * 65536.f), a12 = cv_round(a * (1.f - b) * 65536.f);
+    const int a21 = cv_round((1.f - a) * b * 65536.f), a22 = cv_round(a * b * 65536.f);
+    auto px = [&](int x, int y) -> int {
+        x = x < 0 ? 0 : (x >= src.cols ? src.cols - 1 : x);
+        y = y < 0 ? 0 : (y >= src.rows ? src.rows - 1 : y);
+        return src.ptr(y)[x];
+    };
+    for (int i = 0; i < wh; ++i)
+        for (int j = 0; j < ww; ++j) {
+            const int x = ipx + j, y = ipy + i;
+            const int v = px(x, y) * a11 + px(x + 1, y) * a12 + px(x, y + 1) * a21 + px(x + 1, y + 1) * a22;
+            dst[(size_t)i * ww + j] = (unsigned char)((v + (1 << 15)) >> 16);
+        }
+}
+}  // namespace
+
+// FeatureTracker::getLineMinSAD (/root/reference/src/feature_tracker.cpp:138-204), statement by statement: the window
+// shrink near the borders (including its float-to-int arithmetic), the sub-pixel patch / target sampling, the scan from
+// x downwards (bgoleft) or upwards in unit steps - so ties resolve to the same column - and the mean absolute
+// difference in float.  Host code: it is the stereo prior of the `bdo_stereo_rect` configurations, one short line
+// search per keypoint.
 void FeatureTracker::getLineMinSAD(const cv::Mat &iml, const cv::Mat &imr, const cv::Point2f &pt, const int nwinsize,
         float &xprior, float &l1err, bool bgoleft) const
 {
     xprior = -1;
-    if (nwinsize % 2 == 0) return;
-    const float x = std::round(pt.x), y = std::round(pt.y);
-    const int half = nwinsize / 2;
-    if (x - half < 0) return;
-    const int px = (int)x, py = (int)y;
-    if (py - half < 0 || py + half >= iml.rows || px - half < 0 || px + half >= iml.cols) return;
-    const int nwinsizesq = nwinsize * nwinsize;
-    float minsad = 255.f;
-    int best = -1;
-    const int xstart = bgoleft ? half : px, xend = bgoleft ? px + 1 : imr.cols - half;
-    for (int c = xstart; c < xend; ++c) {
-        if (c - half < 0 || c + half >= imr.cols) continue;
-        long sad = 0;
-        for (int dy = -half; dy <= half; ++dy)
-            for (int dx = -half; dx <= half; ++dx)
-                sad += std::abs((int)iml.ptr(py + dy)[px + dx] - (int)imr.ptr(py + dy)[c + dx]);
-        const float v = (float)sad / nwinsizesq;
-        if (v < minsad) { minsad = v; best = c; }
+    if (nwinsize % 2 == 0) {
+        fprintf(stderr, "\ngetLineMinSAD requires an odd window size\n");
+        return;
     }
-    if (best >= 0) xprior = (float)best;
+    const float x = pt.x;
+    const float y = pt.y;
+    int halfwin = nwinsize / 2;
+    // (the reference's compound assignments convert int + float back to int by truncation)
+    if (x - halfwin < 0) halfwin = (int)(halfwin + (x - halfwin));
+    if (x + halfwin >= imr.cols) halfwin = (int)(halfwin + (x + halfwin - imr.cols - 1));
+    if (y - halfwin < 0) halfwin = (int)(halfwin + (y - halfwin));
+    if (y + halfwin >= imr.rows) halfwin = (int)(halfwin + (y + halfwin - imr.rows - 1));
+    if (halfwin <= 0) return;
+    const int ws = 2 * halfwin + 1;
+    const int nbwinpx = ws * ws;
+    float minsad = 255.f;
+    std::vector<unsigned char> patch, target;
+    get_rect_subpix_u8(iml, ws, ws, pt.x, pt.y, patch);
+    auto sad_at = [&](float c) {
+        get_rect_subpix_u8(imr, ws, ws, c, y, target);
+        long s = 0;
+        for (size_t k = 0; k < patch.size(); ++k) s += std::abs((int)patch[k] - (int)target[k]);
+        float e = (float)(double)s;          // l1err = cv::norm(patch, target, NORM_L1)  (double -> float)
+        e /= nbwinpx;
+        return e;
+    };
+    if (bgoleft) {
+        for (float c = x; c >= halfwin; c -= 1.f) {
+            l1err = sad_at(c);
+            if (l1err < minsad) { minsad = l1err; xprior = c; }
+        }
+    } else {
+        for (float c = x; c < imr.cols - halfwin; c += 1.f) {
+            l1err = sad_at(c);
+            if (l1err < minsad) { minsad = l1err; xprior = c; }
+        }
+    }
     l1err = minsad;
 }
 

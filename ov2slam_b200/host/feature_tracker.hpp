@@ -1,8 +1,8 @@
 // Drop-in replacement of the reference's include/feature_tracker.hpp (:33-56): same class, same
 // public members and signatures, so visual_front_end.cpp / map_manager.cpp / mapper.cpp compile
 // and link against it unchanged.  fbKltTracking and inBorder run through the C ABI
-// (include/ov2b200.h); getLineMinSAD is outside the hot-path scope (only used when
-// bdo_stereo_rect = 1) and keeps a plain C++ implementation.
+// (include/ov2b200.h); getLineMinSAD (only used when bdo_stereo_rect = 1) is a statement-by-statement host port of
+// the reference's function, OpenCV's 8-bit getRectSubPix template included.
 #pragma once
 
 #include <opencv2/core.hpp>

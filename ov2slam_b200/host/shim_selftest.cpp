@@ -5,12 +5,32 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "feature_extractor.hpp"
 #include "feature_tracker.hpp"
 
+// --sad left.raw right.raw W H n x0 y0 win goleft ... : FeatureTracker::getLineMinSAD on a list of points (host code only:
+// runs without a GPU); prints "xprior l1err" per point.
+static int sad_mode(int argc, char** argv) {
+    if (argc < 7) return 2;
+    const int W = atoi(argv[4]), H = atoi(argv[5]), n = atoi(argv[6]);
+    cv::Mat l(H, W, CV_8UC1), r(H, W, CV_8UC1);
+    FILE* f = fopen(argv[2], "rb"); if (!f || fread(l.data, 1, (size_t)W * H, f) != (size_t)W * H) return 3; fclose(f);
+    f = fopen(argv[3], "rb"); if (!f || fread(r.data, 1, (size_t)W * H, f) != (size_t)W * H) return 3; fclose(f);
+    FeatureTracker ft(30, 0.01f, cv::Ptr<cv::CLAHE>());
+    for (int k = 0; k < n; ++k) {
+        const char* const* a = argv + 7 + 4 * k;
+        float xp = 0.f, err = -1.f;
+        ft.getLineMinSAD(l, r, cv::Point2f((float)atof(a[0]), (float)atof(a[1])), atoi(a[2]), xp, err, atoi(a[3]) != 0);
+        printf("%.9g %.9g\n", xp, err);
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "--sad") return sad_mode(argc, argv);
     if (argc < 4) { fprintf(stderr, "usage: shim_selftest prev.raw cur.raw W H\n"); return 2; }
     const int W = atoi(argv[3]), H = argc > 4 ? atoi(argv[4]) : 480;
     cv::Mat prev(H, W, CV_8UC1), cur(H, W, CV_8UC1);
