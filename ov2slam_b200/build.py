@@ -95,6 +95,29 @@ def build_host_shims(verbose: bool = False) -> Path:
     exe = LIB / "shim_selftest"
     subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread",
                            "-Wl,-rpath,$ORIGIN"])
+    build_optimizer_shim(verbose)
+    return exe
+
+
+def build_optimizer_shim(verbose: bool = False) -> Path:
+    """Compile the drop-in Optimizer::localBA (host/optimizer_localba_gpu.cpp) against the stand-in headers that mirror
+    the reference's map / optimizer interfaces (host/standin/ref) and link its self-test driver."""
+    host = ROOT / "host"
+    build()
+    objs = []
+    deps = list(host.glob("*.hpp")) + list((host / "standin" / "ref").rglob("*"))
+    for name in ("optimizer_localba_gpu.cpp", "multi_view_geometry_pnp_gpu.cpp", "optimizer_selftest.cpp"):
+        obj = LIB / "obj" / (name + ".o")
+        src = host / name
+        if _newer(src, obj) or any(d.is_file() and _newer(d, obj) for d in deps):
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", str(host / "standin" / "ref"), "-I", str(host / "standin"),
+                   "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        objs.append(str(obj))
+    exe = LIB / "optimizer_selftest"
+    subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return exe
 
 

@@ -281,7 +281,7 @@ __device__ __forceinline__ double eval_block(const Prob& P, int i, int lm, const
 // over the landmark's observations in registers and leave the warp once.
 constexpr int SCH = 8;   // observations staged per chunk (C3: 4 per landmark, C5: 7.5)
 __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot, double* sJ, int* smeta,
-                                               int l, int lane, double radius, int first_iter, double* acc, int n, double* scal) {
+                                               int l, int lane, double radius, int first_iter, double* acc, int n, double& gmax_lm) {
     const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
     double* const cRhs = acc; double* const cG = acc + n; double* const cCn = acc + 2 * n; double* const cS = acc + 3 * n;
     double cnl = 0.0, ge = 0.0;
@@ -311,8 +311,8 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
     if (lane == 0) {
         P.ete[l] = ete;
         P.ge[l] = ge;
-        atomic_max_pos(scal + SC_GMAX_LM, fabs(ge));
     }
+    gmax_lm = fmax(gmax_lm, fabs(ge));      // one atomicMax per warp and phase (per landmark they all hit ONE address: ~20 cycles each, serialised in L2)
     const int sa = s_slot[P.lm_anchor_cam[l]];
     int m = 0;   // number of E'F entries (uniform across the warp); entry 0 = anchor
     if (sa >= 0) {
@@ -822,7 +822,9 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
             for (int i = gtid; i < P.npts; i += gthreads) c_invd[i] = x_invd[i];
             for (size_t i = gtid; i < (size_t)P.ncopy * blk; i += gthreads) P.acc[i] = 0.0;
             for (int i = gtid; i < 2 * SC_COUNT; i += gthreads) P.scal[i] = 0.0;
+            TR(stage == 0 ? 0 : 10);
             bar.sync();
+            TR(stage == 0 ? 11 : 10);
             if (X.world > 1) {
                 // a keyframe is in the program if ANY rank has an active residual touching it
                 uint8_t* mine = reinterpret_cast<uint8_t*>(X.base[X.rank]) + XB_CAMUSED + (size_t)stage * MAX_CAMS;
@@ -873,14 +875,22 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     for (int i = gtid; i < P.nobs; i += gthreads)
                         if (P.active[i]) cost += eval_block<true>(P, i, P.obs_lm[i], s_cam, x_invd[P.obs_lm[i]], use_huber);
                     cost = warp_sum(cost);
-                    if (lane == 0 && cost != 0.0) atomicAdd(scal + SC_COST, cost);
+                    if (lane == 0) s_red[warp][0] = cost;
+                    __syncthreads();
+                    if (tid == 0) {                               // one atomic per CTA: they all hit one address
+                        double a = 0.0;
+                        for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][0];
+                        if (a != 0.0) atomicAdd(scal + SC_COST, a);
+                    }
                 }
                 bar.sync();
                 TR(1);
                 // ---- B: Schur elimination into this CTA's accumulation copy
                 {
                     double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
-                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, acc, n, scal);
+                    double gmax_lm = 0.0;
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, acc, n, gmax_lm);
+                    if (lane == 0 && gmax_lm > 0.0) atomic_max_pos(scal + SC_GMAX_LM, gmax_lm);
                 }
                 bar.sync();
                 TR(2);
@@ -1379,7 +1389,16 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         OV2_CUDA(ctx, cudaMemsetAsync(dwork + H.w_active, 1, (size_t)(pbs[k].nobs > 0 ? pbs[k].nobs : 1), s));
     }
     // ---- launch geometry: G CTAs per window, all groups co-resident (cooperative launch)
-    OV2_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    {
+        // raised only when a window needs more than any before (a function-attribute change while another stream runs the
+        // kernel may serialise with it)
+        static size_t attr_smem[16] = {0};
+        const int dv = ctx->device & 15;
+        if (smem_max > attr_smem[dv]) {
+            OV2_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            attr_smem[dv] = smem_max;
+        }
+    }
     int per_sm = 0;
     OV2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_lm_kernel, THREADS, smem_max));
     if (per_sm < 1) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_localba_solve: kernel does not fit an SM");
@@ -1436,9 +1455,9 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     if (getenv("OV2_BA_TRACE")) {
         unsigned long long tr[16];
         cudaMemcpy(tr, dwork + plans[0].w_trace, sizeof(tr), cudaMemcpyDeviceToHost);
-        static const char* names[10] = {"setup", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb"};
+        static const char* names[12] = {"setup0", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb", "setup1", "bar0"};
         fprintf(stderr, "[ba trace] G=%d grid=%d smem=%zu ncopy=%d |", G, grid, smem_max, plans[0].ncopy);
-        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
+        for (int k = 0; k < 12; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
         fprintf(stderr, "\n");
     }
     bool numeric_fail = false, aborted = false;

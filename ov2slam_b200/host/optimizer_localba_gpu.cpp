@@ -4,9 +4,12 @@
 // reference's own optimizer.cpp built with -DOV2_EXTERNAL_LOCALBA (one #ifndef around its localBA
 // body).
 //
-// NOT COMPILE-CHECKED IN THIS CONTAINER: it needs the reference's headers and their dependencies
-// (Eigen, Sophus, OpenCV, PCL), none of which exist here.  It is compiled
-// only when OV2_WITH_REFERENCE_HEADERS is defined, on a box that can build the reference.
+// Compile-checked and self-tested in this container against stand-in headers that mirror the reference's class
+// interfaces (host/standin/ref/: optimizer.hpp, map_manager.hpp, sophus/se3.hpp, Eigen/Dense) - the reference's own
+// headers need ROS, PCL, OpenCV, Eigen and Sophus, none of which exist here;
+// host/optimizer_selftest.cpp builds a synthetic map, runs this localBA and tests/test_host_shim.py compares the
+// map it leaves behind with the flat solve of the same window.  On a box that builds the reference, compile this file
+// with the reference's include path instead of the stand-ins.
 // Mono and stereo windows (inverse-depth parametrisation, buse_inv_depth_ = 1: every shipped
 // configuration); the XYZ parametrisation (buse_inv_depth_ = 0) is not flattened and falls through
 // with a diagnostic.
@@ -14,10 +17,12 @@
 // What stays on the host is exactly the part SURVEY.md 8a row G scopes out of acceleration: walking
 // the covisibility graph / hash maps to FLATTEN the window into the SoA arrays ov2_localba_solve
 // takes, and applying the result to the map.  The numerical work (Ceres in the reference,
-// optimizer.cpp:436-735) is one ABI call.
-#ifdef OV2_WITH_REFERENCE_HEADERS
-
+// optimizer.cpp:436-735) is one ABI call = one kernel launch.
+#include <atomic>
+#include <chrono>
+#include <iostream>
 #include <map>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -147,6 +152,19 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
             if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
     }
     if (win.obs_cam.empty()) return;
+    // ov2_localba_solve optimises at most 64 keyframes per window (MAX_VAR_CAMS): beyond that the OLDEST optimised
+    // keyframes are held constant (the reference has no such limit; windows that large do not occur with the shipped
+    // nmin_covscore / covisibility settings - said once on stderr if it ever happens)
+    {
+        size_t nvar = win.pose_const.size() - nconst;
+        if (nvar > 64) {
+            static bool told = false;
+            if (!told) { std::cerr << "[ov2b200] localBA: " << nvar << " optimised keyframes, the oldest " << nvar - 64 << " are held constant\n"; told = true; }
+            std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
+            for (auto it = by_id.begin(); nvar > 64 && it != by_id.end(); ++it)
+                if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nvar--; }
+        }
+    }
 
     // ---- 4. solve on the GPU (replaces ceres::Solve x2 + the two outlier scans)
     auto cal = newframe.pcalib_leftcam_;
@@ -173,11 +191,27 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     op.max_iters_robust = 5; op.max_iters_refine = 10;                // optimizer.cpp:462, :610
     op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-3;
     op.use_robust = buse_robust_cost ? 1 : 0;
-    op.apply_l2_after_robust = (pslamstate_->apply_l2_after_robust_ && !stopLocalBA()) ? 1 : 0;
+    op.apply_l2_after_robust = pslamstate_->apply_l2_after_robust_ ? 1 : 0;
     op.refine_loss = -1;                                              // as optimizer.cpp:606-608 decides
     ov2_ba_result res;
     std::vector<uint8_t> flags(win.obs_cam.size(), 0);
-    if (ov2_localba_solve(ctx, &pb, &op, &res, flags.data()) != OV2_OK) {
+    // The reference polls stopLocalBA() once, between the robust solve and the refinement (optimizer.cpp:603-604); the
+    // stop request arrives from the mapper thread (estimator.cpp:228-232) while the solve is running.  The solve kernel
+    // polls a flag at exactly that point (ov2_localba_request_stop); a watcher forwards bstop_localba_ to it, so the
+    // reference's signalStopLocalBA() needs no edit.
+    ov2_localba_request_stop(ctx, stopLocalBA() ? 1 : 0);
+    std::atomic<bool> solve_done{false};
+    std::thread watcher([&]() {
+        while (!solve_done.load(std::memory_order_acquire)) {
+            if (bstop_localba_) { ov2_localba_request_stop(ctx, 1); return; }
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+    });
+    const ov2_status solve_rc = ov2_localba_solve(ctx, &pb, &op, &res, flags.data());
+    solve_done.store(true, std::memory_order_release);
+    watcher.join();
+    ov2_localba_request_stop(ctx, 0);
+    if (solve_rc != OV2_OK) {
         std::cerr << "[ov2b200] localBA: " << ov2_last_error(ctx) << "\n";
         bstop_localba_ = false;
         return;                                                        // map untouched
@@ -230,4 +264,3 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     bstop_localba_ = false;                                            // optimizer.cpp:896: a stop request is consumed by the BA it interrupted
 }
 
-#endif  // OV2_WITH_REFERENCE_HEADERS

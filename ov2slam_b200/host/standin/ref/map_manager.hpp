@@ -1,0 +1,105 @@
+// Minimal STAND-INS for the map classes Optimizer::localBA reads and writes (the reference's include/map_manager.hpp,
+// frame.hpp, map_point.hpp, camera_calibration.hpp, slam_params.hpp): same member / method names and signatures for the
+// subset the shim uses, trivial in-memory implementations.  Only for compile-checking and self-testing
+// ov2slam_b200/host/optimizer_localba_gpu.cpp in a container without the reference's dependencies (ROS, PCL, OpenCV,
+// Eigen, Sophus); on a box that builds the reference, its own headers are used instead.
+#pragma once
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+#include <opencv2/core.hpp>
+#include <sophus/se3.hpp>
+
+struct SlamParams {
+    int nmin_covscore_ = 25;
+    bool stereo_ = false, buse_inv_depth_ = true, apply_l2_after_robust_ = true;
+    float robust_mono_th_ = 5.9915f;
+};
+
+class CameraCalibration {
+public:
+    double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0;
+    Eigen::Matrix3d iK_;
+    Sophus::SE3d Tc0ci_;
+    void setK(double fx, double fy, double cx, double cy) {
+        fx_ = fx; fy_ = fy; cx_ = cx; cy_ = cy;
+        iK_ = Eigen::Matrix3d();
+        iK_.m[0] = 1.0 / fx; iK_.m[2] = -cx / fx; iK_.m[4] = 1.0 / fy; iK_.m[5] = -cy / fy;
+    }
+    Sophus::SE3d getExtrinsic() const { return Tc0ci_; }
+};
+
+struct Keypoint {
+    int lmid_ = -1;
+    cv::Point2f unpx_, runpx_;
+    int scale_ = 0;
+    bool is3d_ = false, is_stereo_ = false;
+};
+
+class Frame {
+public:
+    int id_ = 0, kfid_ = 0;
+    size_t nbkps_ = 0, nb2dkps_ = 0, nb3dkps_ = 0, nb_stereo_kps_ = 0;
+    std::shared_ptr<CameraCalibration> pcalib_leftcam_, pcalib_rightcam_;
+    std::unordered_map<int, Keypoint> mapkps_;
+    std::map<int, int> covkfs_;
+    Sophus::SE3d Twc_;
+
+    std::vector<Keypoint> getKeypoints3d() const {
+        std::vector<Keypoint> v;
+        for (const auto& kv : mapkps_) if (kv.second.is3d_) v.push_back(kv.second);
+        return v;
+    }
+    Keypoint getKeypointById(const int lmid) const { auto it = mapkps_.find(lmid); return it == mapkps_.end() ? Keypoint() : it->second; }
+    void removeStereoKeypointById(const int lmid) { auto it = mapkps_.find(lmid); if (it != mapkps_.end()) it->second.is_stereo_ = false; }
+    Sophus::SE3d getTcw() const { return Twc_.inverse(); }
+    Sophus::SE3d getTwc() const { return Twc_; }
+    void setTwc(const Sophus::SE3d& Twc) { Twc_ = Twc; }
+    std::map<int, int> getCovisibleKfMap() const { return covkfs_; }
+    void removeCovisibleKf(const int kfid) { covkfs_.erase(kfid); }
+};
+
+class MapPoint {
+public:
+    int lmid_ = -1, kfid_ = -1;
+    bool isobs_ = true, bad_ = false;
+    double invdepth_ = -1;
+    Eigen::Vector3d ptxyz_;
+    std::set<int> set_kfids_;
+    bool isBad() const { return bad_; }
+    std::set<int> getKfObsSet() const { return set_kfids_; }
+    Eigen::Vector3d getPoint() const { return ptxyz_; }
+};
+
+class MapManager {
+public:
+    std::unordered_map<int, std::shared_ptr<Frame>> map_pkfs_;
+    std::unordered_map<int, std::shared_ptr<MapPoint>> map_plms_;
+    std::shared_ptr<Frame> pcurframe_;
+    std::mutex map_mutex_, optim_mutex_;
+    std::vector<std::pair<int, int>> removed_obs_;      // (lmid, kfid) - for the self-test's report
+    std::vector<int> removed_points_;
+
+    std::shared_ptr<Frame> getKeyframe(const int kfid) const { auto it = map_pkfs_.find(kfid); return it == map_pkfs_.end() ? nullptr : it->second; }
+    std::shared_ptr<MapPoint> getMapPoint(const int lmid) const { auto it = map_plms_.find(lmid); return it == map_plms_.end() ? nullptr : it->second; }
+    void removeMapPointObs(const int lmid, const int kfid) {
+        removed_obs_.emplace_back(lmid, kfid);
+        auto lm = getMapPoint(lmid);
+        if (lm) lm->set_kfids_.erase(kfid);
+        auto kf = getKeyframe(kfid);
+        if (kf) kf->mapkps_.erase(lmid);
+    }
+    void removeObsFromCurFrameById(const int lmid) { if (pcurframe_) pcurframe_->mapkps_.erase(lmid); }
+    void removeMapPoint(const int lmid) { removed_points_.push_back(lmid); map_plms_.erase(lmid); }
+    void updateMapPoint(const int lmid, const Eigen::Vector3d& wpt, const double kfanch_invdepth = -1.) {
+        auto lm = getMapPoint(lmid);
+        if (!lm) return;
+        lm->ptxyz_ = wpt;
+        if (kfanch_invdepth >= 0.) lm->invdepth_ = kfanch_invdepth;
+    }
+};

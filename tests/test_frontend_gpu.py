@@ -395,7 +395,7 @@ def test_frontend_step_composite_equals_operator_calls(ctx):
         api.frontend_step(ctx, pp, cp, args2)
         for k in a:
             assert np.array_equal(a[k], pin[k].numpy()), (rep, k)
-    assert ctx.launch_count() - l0 == 4 * 12      # 6 pyramid + KLT + 3 FAST/subpix + 2 descriptor launches per step
+    assert ctx.launch_count() - l0 == 4 * 8       # 2 fused pyramid + KLT + 3 FAST/subpix + 2 descriptor launches per step
     pp.close()
     cp.close()
 

@@ -138,3 +138,72 @@ def test_get_line_min_sad_matches_the_reference_function():
             agree += np.float32(gx) == np.float32(cx)
     if cv_sub is not None:
         assert agree >= 0.8 * len(pts)
+
+
+def _write_window(path, pb):
+    import struct
+    stereo = pb.get("obs_type") is not None
+    ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
+    with open(path, "wb") as f:
+        f.write(struct.pack("4i", ncam, npts, nobs, int(stereo)))
+        f.write(np.asarray(pb["K"], np.float64).tobytes())
+        f.write(np.asarray(pb["Kr"] if stereo else pb["K"], np.float64).tobytes())
+        f.write(np.asarray(pb["Trl"] if stereo else [0, 0, 0, 0, 0, 0, 1], np.float64).tobytes())
+        for k, dt in (("pose", np.float64), ("pose_const", np.uint8), ("lm_anchor_cam", np.int32), ("lm_anchor_px", np.float64),
+                      ("lm_invdepth", np.float64), ("obs_cam", np.int32), ("obs_lm", np.int32), ("obs_px", np.float64)):
+            f.write(np.ascontiguousarray(pb[k], dt).tobytes())
+        f.write(np.ascontiguousarray(pb["obs_type"] if stereo else np.zeros(nobs), np.uint8).tobytes())
+
+
+def _drop_landmarks_seen_only_by_constant_keyframes(pb):
+    """Optimizer::localBA collects its landmarks from the 3D keypoints of the OPTIMISED keyframes (optimizer.cpp:178-180): a
+    landmark whose anchor and observers are all constant keyframes is not part of the reference's window."""
+    const = pb["pose_const"].astype(bool)
+    npts = len(pb["lm_invdepth"])
+    seen = ~const[pb["lm_anchor_cam"]]
+    np.logical_or.at(seen, pb["obs_lm"], ~const[pb["obs_cam"]])
+    keep_l = np.nonzero(seen)[0]
+    remap = -np.ones(npts, np.int64)
+    remap[keep_l] = np.arange(len(keep_l))
+    keep_o = np.nonzero(seen[pb["obs_lm"]])[0]
+    out = dict(pb)
+    for k in ("lm_anchor_cam", "lm_anchor_px", "lm_invdepth"):
+        out[k] = np.ascontiguousarray(pb[k][keep_l])
+    for k in ("obs_cam", "obs_px") + (("obs_type",) if pb.get("obs_type") is not None else ()):
+        out[k] = np.ascontiguousarray(pb[k][keep_o])
+    out["obs_lm"] = np.ascontiguousarray(remap[pb["obs_lm"][keep_o]].astype(np.int32))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stereo,stop", [(False, False), (True, False), (False, True)])
+def test_optimizer_localba_shim_updates_the_map_like_the_flat_solve(ctx, tmp_path, stereo, stop):
+    """The drop-in Optimizer::localBA (host/optimizer_localba_gpu.cpp, compiled against the stand-in map classes) on a
+    synthetic map: window selection over the covisibility map, anchored inverse-depth flattening (mono / stereo), GPU solve,
+    write-back - the keyframe poses and landmark inverse depths left in the map equal ov2_localba_solve on the flat window;
+    a stop request raised before the call skips the refinement and is consumed (bstop_localba_ was never cleared)."""
+    exe = build.build_optimizer_shim()
+    pb = _drop_landmarks_seen_only_by_constant_keyframes(synth.make_ba_problem(61 + stereo, 9, 600, 2400, stereo=stereo))
+    _write_window(tmp_path / "w.bin", pb)
+    out = subprocess.run([str(exe), str(tmp_path / "w.bin"), str(tmp_path / "r.bin")] + (["stop"] if stop else []),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ncam, npts = len(pb["pose"]), len(pb["lm_invdepth"])
+    raw = np.fromfile(tmp_path / "r.bin", np.uint8)
+    pose = raw[:ncam * 56].view(np.float64).reshape(ncam, 7)
+    invd = raw[ncam * 56:ncam * 56 + npts * 8].view(np.float64)
+    ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    if stop:
+        api.request_stop_local_ba(ctx, True)
+    res, flags = api.Optimizer(ctx).local_ba(ref)
+    api.request_stop_local_ba(ctx, False)
+    if stop:
+        assert res["iters_refine"] == 0
+    # the shim stores unit quaternions through Sophus (sign / normalisation): compare rotations up to sign
+    for c in range(ncam):
+        assert np.abs(pose[c, :3] - ref["pose"][c, :3]).max() <= 1e-7
+        q, r = pose[c, 3:], ref["pose"][c, 3:] / np.linalg.norm(ref["pose"][c, 3:])
+        assert min(np.abs(q - r).max(), np.abs(q + r).max()) <= 1e-7
+    alive = invd >= 0
+    assert alive.mean() > 0.9
+    assert np.abs(invd[alive] - ref["lm_invdepth"][alive]).max() <= 1e-7
