@@ -629,6 +629,11 @@ def gpu_arm(args):
                 line["localba"] = ba_bench(torch, api, ctx)
             except Exception as e:
                 line["localba"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_cpu:
+            try:
+                line["class_path"] = class_path_bench()
+            except Exception as e:
+                line["class_path"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -725,6 +730,37 @@ def ba_bench(torch, api, ctx):
     except Exception as e:
         out["cpu_baseline"] = {"error": str(e)[:120]}
     return out
+
+
+def class_path_bench():
+    """The reference-facing CLASS boundary, one frame per call (host/shim_selftest --bench): what a single live camera
+    stream sees through FeatureTracker / FeatureExtractor on one GPU (every call synchronises; each image uploaded once
+    thanks to the shims' device-pyramid cache).  Latency bound by construction - the batch ABI above is the throughput path."""
+    from ov2slam_b200 import build, synth
+    exe = build.LIB / "shim_selftest"
+    if not exe.exists():
+        return {"error": "shim_selftest not built"}
+    n = 24
+    frames = [synth.make_frame(900, W_IMG, H_IMG)]
+    rng = np.random.default_rng(9)
+    for k in range(1, n):                                   # a smooth synthetic sequence: small translations + noise
+        sh = synth.shift_image(frames[-1], float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3))) + rng.normal(0, 1.5, (H_IMG, W_IMG))
+        frames.append(np.clip(np.rint(sh), 0, 255).astype(np.uint8))
+    with tempfile.NamedTemporaryFile(suffix=".raw", delete=False) as f:
+        f.write(np.ascontiguousarray(np.stack(frames)).tobytes())
+        path = f.name
+    try:
+        out = subprocess.run([str(exe), "--bench", path, str(W_IMG), str(H_IMG), str(n), "20"], capture_output=True, text=True, timeout=300)
+    finally:
+        os.unlink(path)
+    if out.returncode != 0:
+        return {"error": (out.stderr or out.stdout)[-200:]}
+    tok = out.stdout.split()
+    d = {tok[i]: float(tok[i + 1]) for i in range(1, len(tok) - 1, 2)}
+    return {"value": d.get("fps"), "unit": "frames/s", "frames": int(d.get("frames", 0)), "tracked_per_frame": d.get("tracked_per_frame"),
+            "detected_per_frame": d.get("detected_per_frame"),
+            "what": "FeatureTracker::fbKltTracking x2 + describeBRIEF + detectGridFAST + describeBRIEF per 640x480 frame through the C++ drop-in "
+                    "classes, one stream, one frame per call"}
 
 
 def main():

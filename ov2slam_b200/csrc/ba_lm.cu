@@ -280,8 +280,29 @@ __device__ __forceinline__ double eval_block(const Prob& P, int i, int lm, const
 // S -= (E'F)' (E'E)^-1 (E'F), rhs -= (E'F)' (E'E)^-1 E'r.  The anchor keyframe's F'F / F'r / column norms are summed
 // over the landmark's observations in registers and leave the warp once.
 constexpr int SCH = 8;   // observations staged per chunk (C3: 4 per landmark, C5: 7.5)
+
+// CTA-local lock for the shared-memory accumulation mode: lane 0 spins on a shared-memory CAS, the warp follows.
+__device__ __forceinline__ void warp_lock(int* lock, int lane) {
+    if (lane == 0)
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(20);
+    __syncwarp();
+    __threadfence_block();
+}
+__device__ __forceinline__ void warp_unlock(int* lock, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(lock, 0);
+}
+
+// SM = false: contributions leave the warp as fp64 RED into the (privatised) global accumulation block.  B200 retires an
+// fp64 RED at ~2.4-3.6 cycles per lane and SM (measured: the phase scales 1/SMs and not with warps per SM), which bounds
+// this phase at ~900 REDs per landmark.  SM = true (reduced systems that fit shared memory, n <= ~100): the CTA keeps ONE
+// copy of [rhs | F'r | column norms | S] in shared memory, warps commit under a CTA-local lock with plain
+// read-modify-writes (shared-memory fp64 atomics are CAS loops, slower than RED) and the CTA flushes the non-zeros once.
+template <bool SM>
 __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot, double* sJ, int* smeta,
-                                               int l, int lane, double radius, int first_iter, double* acc, int n, double& gmax_lm) {
+                                               int l, int lane, double radius, int first_iter, double* acc, int n, double& gmax_lm, int* lock) {
+#define ACC(ptr, v) do { if (SM) *(ptr) += (v); else atomicAdd((ptr), (v)); } while (0)
     const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
     double* const cRhs = acc; double* const cG = acc + n; double* const cCn = acc + 2 * n; double* const cS = acc + 3 * n;
     double cnl = 0.0, ge = 0.0;
@@ -341,6 +362,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             smeta[lane] = mt;
         }
         __syncwarp();
+        if (SM) warp_lock(lock, lane);
     for (int q = 0; q < cnt; ++q) {
         const int so = smeta[q];
         if (so < -1) continue;
@@ -360,7 +382,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
         if (so >= 0) {
             for (int e = lane; e < 36; e += 32) {
                 const int a = e / 6, b = e - 6 * a;
-                if (a <= b) atomicAdd(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
+                if (a <= b) ACC(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
             }
             // E'F row of this keyframe: a stereo keyframe contributes two residual blocks (left and right camera) to the
             // same pose block, so look the slot up before appending a new entry
@@ -371,8 +393,8 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             const bool fresh = idx < 0;
             if (fresh) idx = m;
             if (lane < 6) {
-                atomicAdd(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
-                atomicAdd(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
+                ACC(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
+                ACC(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
                 const double e = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
                 s_etf[6 * idx + lane] = fresh ? e : s_etf[6 * idx + lane] + e;
             }
@@ -382,19 +404,21 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
                 for (int e = lane; e < 36; e += 32) {
                     const int a = e / 6, b = e - 6 * a;   // a: anchor column, b: observer column
                     const double v = Ja[a] * Jo[b] + Ja[6 + a] * Jo[6 + b];
-                    if (sa < so) atomicAdd(cS + (size_t)(6 * sa + a) * n + 6 * so + b, v);
-                    else atomicAdd(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
+                    if (sa < so) ACC(cS + (size_t)(6 * sa + a) * n + 6 * so + b, v);
+                    else ACC(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
                 }
             }
             if (fresh) m++;
         }
         __syncwarp();
     }
+        if (SM) warp_unlock(lock, lane);
     }
+    if (SM) warp_lock(lock, lane);
     if (sa >= 0) {
-        if (e0a <= e0b) atomicAdd(cS + (size_t)(6 * sa + e0a) * n + 6 * sa + e0b, aFF0);
-        if (e1 < 36 && e1a <= e1b) atomicAdd(cS + (size_t)(6 * sa + e1a) * n + 6 * sa + e1b, aFF1);
-        if (lane < 6) { atomicAdd(cG + 6 * sa + lane, aG); atomicAdd(cCn + 6 * sa + lane, aCn); }
+        if (e0a <= e0b) ACC(cS + (size_t)(6 * sa + e0a) * n + 6 * sa + e0b, aFF0);
+        if (e1 < 36 && e1a <= e1b) ACC(cS + (size_t)(6 * sa + e1a) * n + 6 * sa + e1b, aFF1);
+        if (lane < 6) { ACC(cG + 6 * sa + lane, aG); ACC(cCn + 6 * sa + lane, aCn); }
     }
     // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i -= EtF_i ge / ete
     const int npair = m * m;
@@ -406,13 +430,15 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
         const int a = q / 6, b = q - 6 * a;
         if (si == sj && a > b) continue;
         const double v = s_etf[6 * i + a] * s_etf[6 * j + b] * inv_ete;   // slots are unique in the list
-        atomicAdd(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
+        ACC(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
     }
     for (int e = lane; e < m * 6; e += 32) {
         const int i = e / 6, a = e - 6 * i;
-        atomicAdd(cRhs + 6 * s_eslot[i] + a, -s_etf[6 * i + a] * ge * inv_ete);
+        ACC(cRhs + 6 * s_eslot[i] + a, -s_etf[6 * i + a] * ge * inv_ete);
     }
+    if (SM) warp_unlock(lock, lane);
     __syncwarp();
+#undef ACC
 }
 
 // ------------------------------------------------------------------ reduced camera system, n <= 96: CTA-wide Gauss-Jordan in shared memory
@@ -761,7 +787,7 @@ struct SolveOut { int iterations; double initial_cost, final_cost; int terminati
 __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restrict__ probs, int nprob, int G, Peers X) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ lmctl::State S;
-    __shared__ int s_action, s_ncv, s_any, s_refine, s_trivial;
+    __shared__ int s_action, s_ncv, s_any, s_refine, s_trivial, s_lock;
     __shared__ double s_red[WARPS][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = blockIdx.x / G, bid = blockIdx.x - group * G, ngroups = gridDim.x / G;
@@ -885,11 +911,25 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 }
                 bar.sync();
                 TR(1);
-                // ---- B: Schur elimination into this CTA's accumulation copy
-                {
+                // ---- B: Schur elimination into this CTA's accumulation copy (global, RED) or shared-memory block (lock)
+                if (P.schur_smem) {
+                    double* sS = s_work + P.smem_sacc_off;
+                    const int live_s = 3 * n + n * n;
+                    for (int e = tid; e < live_s; e += THREADS) sS[e] = 0.0;
+                    if (tid == 0) s_lock = 0;
+                    __syncthreads();
+                    double gmax_lm = 0.0;
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark<true>(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, sS, n, gmax_lm, &s_lock);
+                    if (lane == 0 && gmax_lm > 0.0) atomic_max_pos(scal + SC_GMAX_LM, gmax_lm);
+                    __syncthreads();
+                    for (int e = tid; e < live_s; e += THREADS) {
+                        const double v = sS[e];
+                        if (v != 0.0) atomicAdd(P.acc + e, v);
+                    }
+                } else {
                     double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
                     double gmax_lm = 0.0;
-                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, acc, n, gmax_lm);
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark<false>(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, acc, n, gmax_lm, nullptr);
                     if (lane == 0 && gmax_lm > 0.0) atomic_max_pos(scal + SC_GMAX_LM, gmax_lm);
                 }
                 bar.sync();
@@ -1063,11 +1103,17 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     }
                 }
                 bad_t = __reduce_add_sync(FULL, bad_t); left_t = __reduce_add_sync(FULL, left_t); right_t = __reduce_add_sync(FULL, right_t);
-                if (lane == 0) {
-                    if (bad_t) atomicAdd(cnt + 0, (double)bad_t);
-                    if (left_t) atomicAdd(cnt + 1, (double)left_t);
-                    if (right_t) atomicAdd(cnt + 2, (double)right_t);
+                if (lane == 0) { s_red[warp][0] = (double)bad_t; s_red[warp][1] = (double)left_t; s_red[warp][2] = (double)right_t; }
+                __syncthreads();
+                if (tid < 3) {                                   // one atomic per CTA and counter
+                    double a = 0.0;
+                    for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][tid];
+                    if (a != 0.0) atomicAdd(cnt + tid, a);
                 }
+                // the stop request lives in mapped HOST memory: ONE thread of the group reads it (every thread of every CTA
+                // polling it over PCIe cost 7 us per CTA of the group) and publishes it next to the counters
+                if (stage == 0 && bid == 0 && tid == 0)
+                    cnt[3] = (P.stop_flag && *reinterpret_cast<volatile const int*>(P.stop_flag) != 0) ? 1.0 : 0.0;
                 bar.sync();
                 if (stage == 0) {
                     double nbad = cnt[0], nleft = cnt[1], nright = cnt[2];
@@ -1087,8 +1133,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     }
                     // solve #2 only if residual blocks were removed and no stop was requested meanwhile (optimizer.cpp:603-604)
                     int refine = P.apply_l2 && P.use_robust && nbad > 0.0;
-                    if (refine && P.stop_flag && *reinterpret_cast<volatile const int*>(P.stop_flag) != 0) refine = 0;
-                    if (X.world > 1 && P.stop_flag) refine = refine;   // (sharded callers pass no stop flag: ranks could disagree)
+                    if (refine && cnt[3] != 0.0) refine = 0;        // (sharded callers pass no stop flag: ranks could disagree)
                     // mono windows keep the Huber loss in the refinement; the wrapper is reset to the trivial loss only when
                     // left-camera and other-frame right-camera residual lists are both non-empty (optimizer.cpp:606-608)
                     int trivial = P.refine_loss;
@@ -1140,8 +1185,8 @@ struct HostPlan {
     // device-only work areas (offsets into the work block)
     size_t w_pose1, w_invd1, w_active, w_flags, w_camused, w_camslot, w_Jr, w_Ja, w_Jo, w_Jl, w_chi2, w_dpos, w_sclm, w_ete, w_ge,
            w_acc, w_total, w_scal, w_z, w_panel, w_sccam, w_counts, w_bar, w_result, w_trace, work_bytes, zero_off, zero_bytes;
-    int ncv_max, n_max, ncopy, solve_blocked;
-    size_t blk, smem_work_off, smem_bytes;
+    int ncv_max, n_max, ncopy, solve_blocked, schur_smem;
+    size_t blk, smem_work_off, smem_bytes, smem_sacc_off;
 };
 
 size_t take(size_t& off, size_t bytes, size_t align = 256) {
@@ -1214,10 +1259,21 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     size_t s = sizeof(double) * 12 * (size_t)ncam + sizeof(int) * (size_t)ncam;
     s = (s + 15) & ~(size_t)15;
     H.smem_work_off = s;
-    const size_t schur = (size_t)WARPS * 6 * (size_t)(ncv + 1) * sizeof(double) + ((((size_t)WARPS * (ncv + 1) + 1) >> 1) << 3) +
-                         (size_t)WARPS * 28 * SCH * sizeof(double) + (size_t)WARPS * SCH * sizeof(int) + 16;
+    size_t schur = (size_t)WARPS * 6 * (size_t)(ncv + 1) * sizeof(double) + ((((size_t)WARPS * (ncv + 1) + 1) >> 1) << 3) +
+                   (size_t)WARPS * 28 * SCH * sizeof(double) + (size_t)WARPS * SCH * sizeof(int) + 16;
+    schur = (schur + 15) & ~(size_t)15;
     const size_t solve = H.solve_blocked ? (size_t)CH_NB * (size_t)((((size_t)H.n_max + 15) & ~(size_t)15) + 8) * sizeof(double)
                                          : (size_t)H.n_max * (size_t)(H.n_max + 2) * sizeof(double);
+    // shared-memory accumulation of the reduced system (behind the Schur scratch) when the whole block fits next to it
+    // with two CTAs per SM still possible
+    H.smem_sacc_off = schur / sizeof(double);
+    H.schur_smem = 0;
+    const char* ssm = getenv("OV2_BA_SCHUR_SMEM");
+    if (H.n_max > 0 && s + schur + H.blk * sizeof(double) <= 100 * 1024 && !(ssm && atoi(ssm) == 0)) {
+        H.schur_smem = 1;
+        H.ncopy = 1;
+        schur += H.blk * sizeof(double);
+    }
     H.smem_bytes = s + (schur > solve ? schur : solve) + 16;
     (void)world;
     return OV2_OK;
@@ -1269,6 +1325,7 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.counts = (double*)(dwork + H.w_counts); P.bar = (unsigned*)(dwork + H.w_bar); P.result = (Result*)(dwork + H.w_result);
     P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
+    P.schur_smem = H.schur_smem; P.smem_sacc_off = (int)H.smem_sacc_off;
     P.smem_work_off = (int)H.smem_work_off;
 }
 

@@ -46,7 +46,7 @@ struct Prob {
     unsigned* bar;                     // [0] group barrier counter, [1] abort flag
     Result* result;
     unsigned long long* trace;         // optional [16] per-phase nanoseconds (OV2_BA_TRACE=1), NULL otherwise
-    int ncv_max, ncopy, solve_blocked, smem_work_off;
+    int ncv_max, ncopy, solve_blocked, smem_work_off, schur_smem, smem_sacc_off;
     size_t blk;
 };
 

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -29,8 +31,60 @@ static int sad_mode(int argc, char** argv) {
     return 0;
 }
 
+// --bench frames.raw W H N reps : the CLASS path as the reference's live loop drives it, one frame per call
+// (VisualFrontEnd::trackMono -> kltTracking's two fbKltTracking calls, src/visual_front_end.cpp:196,242; then
+// MapManager::extractKeypoints: describeBRIEF, detectGridFAST, describeBRIEF, src/map_manager.cpp:286-341), prev / cur
+// pyramid vectors swapped and the current one refilled in place every frame (:1168-1172).  Prints frames/s.
+static int bench_mode(int argc, char** argv) {
+    if (argc < 7) return 2;
+    const int W = atoi(argv[3]), H = atoi(argv[4]), N = atoi(argv[5]), reps = atoi(argv[6]);
+    std::vector<unsigned char> all((size_t)W * H * N);
+    FILE* f = fopen(argv[2], "rb"); if (!f || fread(all.data(), 1, all.size(), f) != all.size()) return 3; fclose(f);
+    FeatureExtractor fe(0, 50, 0.0, 10);
+    FeatureTracker ft(30, 0.01f, cv::Ptr<cv::CLAHE>());
+    std::vector<cv::Mat> prevpyr(8), curpyr(8);
+    prevpyr[0] = cv::Mat(H, W, CV_8UC1); curpyr[0] = cv::Mat(H, W, CV_8UC1);
+    memcpy(curpyr[0].data, all.data(), (size_t)W * H);
+    std::vector<cv::Point2f> kps = fe.detectGridFAST(curpyr[0], 50, std::vector<cv::Point2f>(), cv::Rect());
+    long tracked = 0, detected = 0;
+    struct timespec t0, t1;
+    int frames = 0;
+    for (int rep = -1; rep < reps; ++rep) {                // rep -1: warm-up pass
+        if (rep == 0) { clock_gettime(CLOCK_MONOTONIC, &t0); frames = 0; tracked = detected = 0; }
+        for (int k = 1; k < N; ++k) {
+            prevpyr.swap(curpyr);                                                      // visual_front_end.cpp:1168-1170
+            memcpy(curpyr[0].data, all.data() + (size_t)k * W * H, (size_t)W * H);     // buildOpticalFlowPyramid refills cur in place
+            // kltTracking: keypoints with a 3D prior first (nbpyrlvl 1), the rest with the full pyramid
+            std::vector<cv::Point2f> k3, p3, k2, p2;
+            for (size_t i = 0; i < kps.size(); ++i) ((i % 5) < 3 ? k3 : k2).push_back(kps[i]);
+            p3 = k3; p2 = k2;
+            std::vector<bool> s3, s2;
+            ft.fbKltTracking(prevpyr, curpyr, 9, 1, 30.f, 0.5f, k3, p3, s3);
+            ft.fbKltTracking(prevpyr, curpyr, 9, 3, 30.f, 0.5f, k2, p2, s2);
+            std::vector<cv::Point2f> alive;
+            for (size_t i = 0; i < s3.size(); ++i) if (s3[i]) alive.push_back(p3[i]);
+            for (size_t i = 0; i < s2.size(); ++i) if (s2[i]) alive.push_back(p2[i]);
+            tracked += (long)alive.size();
+            // createKeyframe -> extractKeypoints on the current image
+            std::vector<cv::Mat> d0 = fe.describeBRIEF(curpyr[0], alive);
+            std::vector<cv::Point2f> fresh = fe.detectGridFAST(curpyr[0], 50, alive, cv::Rect());
+            std::vector<cv::Mat> d1 = fe.describeBRIEF(curpyr[0], fresh);
+            detected += (long)fresh.size();
+            kps = alive;
+            kps.insert(kps.end(), fresh.begin(), fresh.end());
+            frames++;
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    printf("class_path frames %d seconds %.6f fps %.2f tracked_per_frame %.1f detected_per_frame %.1f\n", frames, dt, frames / dt,
+           (double)tracked / frames, (double)detected / frames);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "--sad") return sad_mode(argc, argv);
+    if (argc > 1 && std::string(argv[1]) == "--bench") return bench_mode(argc, argv);
     if (argc < 4) { fprintf(stderr, "usage: shim_selftest prev.raw cur.raw W H\n"); return 2; }
     const int W = atoi(argv[3]), H = argc > 4 ? atoi(argv[4]) : 480;
     cv::Mat prev(H, W, CV_8UC1), cur(H, W, CV_8UC1);

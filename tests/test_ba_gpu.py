@@ -223,3 +223,23 @@ def test_localba_stop_request_skips_the_refinement(ctx):
     c = _clone(pb)
     r2, _ = api.Optimizer(ctx).local_ba(c)
     assert r2["iters_refine"] == r0["iters_refine"]
+
+
+def test_localba_bal_structure_fixture(ctx):
+    """GPU vs the C restatement on the window built from Ceres' BAL test problem's observation graph (tests/ba_fixture.py:
+    16 keyframes, 22 106 landmarks with 2 .. 14 views, 61 612 residual blocks, 84 x 84 reduced system)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).parent))
+    import ba_fixture as F
+    from oracle import ba_ref_c
+    pb = F.bal_window(seed=0)
+    ref = _clone(pb)
+    r = ba_ref_c.local_ba(ref)
+    gpu = _clone(pb)
+    g, flags = api.Optimizer(ctx).local_ba(gpu)
+    assert (g["iters_robust"], g["iters_refine"]) == (r["iters_robust"], r["iters_refine"])
+    assert abs(g["final_cost"] - r["final_cost"]) <= 1e-8 * max(1.0, r["final_cost"])
+    assert np.abs(gpu["pose"] - ref["pose"]).max() <= 1e-6
+    assert np.abs(gpu["lm_invdepth"] - ref["lm_invdepth"]).max() <= 1e-6
+    assert (flags != r["flags"]).sum() <= 3
