@@ -780,7 +780,7 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="skip the local-BA (C3) leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (stereo 1280x720) leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 (localBA 150k observations) leg")
-    ap.add_argument("--c4-batch", type=int, default=64, help="stereo units per GPU per C4 step")
+    ap.add_argument("--c4-batch", type=int, default=144, help="stereo units per GPU per C4 step (144: every SM has a frame in the one-CTA-per-frame detector sweep)")
     ap.add_argument("--c4-unique", type=int, default=16, help="generated C4 units (the rest of the batch are flips / repeats)")
     ap.add_argument("--c4-steps", type=int, default=10)
     ap.add_argument("--c5-reps", type=int, default=5)

@@ -484,6 +484,9 @@ __device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fai
 __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radius, int first_iter, double* sA, double* scal) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int PIT = n + 2;
+    const bool tr = P.trace != nullptr && tid == 0;          // (CTA 0 only runs this) trace slots 12: load + damping, 13: pivots, 14: solution
+    unsigned long long tr_t = tr ? global_ns() : 0;
+#define TRS(k) do { if (tr) { const unsigned long long t_ = global_ns(); P.trace[k] += t_ - tr_t; tr_t = t_; } } while (0)
     double* cRhs = T; double* cG = T + n; double* cCn = T + 2 * n; double* cS = T + 3 * n;
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
@@ -504,15 +507,19 @@ __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radi
         sA[i * PIT + n] = cG[i] + cRhs[i];
     }
     __syncthreads();
+    TRS(12);
     if (n <= 48) gj_pivots<13>(sA, n, PIT, &s_fail);         // (n + 1 + 3) / 4 columns per thread
     else if (n <= 64) gj_pivots<17>(sA, n, PIT, &s_fail);
     else gj_pivots<25>(sA, n, PIT, &s_fail);
     __syncthreads();
+    TRS(13);
     if (s_fail) {
         if (tid == 0) scal[SC_CHOL_FAIL] = 1.0;
         return;
     }
     for (int i = tid; i < n; i += nt) P.z[i] = sA[i * PIT + n] / sA[i * PIT + i];
+    TRS(14);
+#undef TRS
 }
 
 // ------------------------------------------------------------------ reduced camera system, n > 96: blocked Cholesky (one CTA)
@@ -541,6 +548,9 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
     double* Pan = P.panel;                               // [CH_NB][PW] in global memory: what the other CTAs read
     const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
     const int gwarps = G * nwarp, gwarp = bid * nwarp + warp;
+    const bool tr = P.trace != nullptr && bid == 0 && tid == 0;
+    unsigned long long tr_t = tr ? global_ns() : 0;
+#define TRS(k) do { if (tr) { const unsigned long long t_ = global_ns(); P.trace[k] += t_ - tr_t; tr_t = t_; } } while (0)
     if (bid == 0) {
         if (tid == 0) s_bad = 0;
         for (int i = tid; i < n; i += nt) {
@@ -625,7 +635,9 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
                 }
             }
         }
+        TRS(12);
         bar.sync();
+        TRS(13);
         if (scal[SC_CHOL_FAIL] != 0.0) return;                           // uniform across the group (written before the barrier)
         if (bid == 0) {
             for (int r = tid; r < m; r += nt) {
@@ -663,7 +675,9 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
                         }
             }
         }
+        TRS(14);
         bar.sync();
+        TRS(13);
     }
     if (bid != 0) return;
     // ---- backward substitution U z = y, last block first (CTA 0)
@@ -693,6 +707,8 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt) P.z[i] = w[i];
+    TRS(15);
+#undef TRS
 }
 
 // ------------------------------------------------------------------ back-substitution + candidate cost (warp / landmark)
@@ -1209,10 +1225,12 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     H.ncv_max = ncv; H.n_max = 6 * ncv;
     H.blk = 3 * (size_t)H.n_max + (size_t)H.n_max * H.n_max;
     if (H.blk == 0) H.blk = 1;
-    // privatised accumulation copies spread the fp64 REDs (few addresses, thousands of REDs each)
-    size_t k = (size_t)(3 * MAX_N + MAX_N * MAX_N) / H.blk;
-    H.ncopy = (int)(k < 1 ? 1 : (k > (size_t)ncopy_cap ? (size_t)ncopy_cap : k));
-    if (getenv("OV2_BA_NCOPY")) { int e = atoi(getenv("OV2_BA_NCOPY")); if (e >= 1 && e <= 8) H.ncopy = e; }
+    // ONE accumulation block: privatised copies (round 1 used up to 8) do not pay on a B200 - the phase is bound by the
+    // rate at which an SM retires fp64 REDs, not by same-address contention (measured: identical time with 1 and 8 copies)
+    // - and a single copy needs no fold phase.  OV2_BA_NCOPY = 2..8 brings the copies back for experiments.
+    (void)ncopy_cap;
+    H.ncopy = 1;
+    if (getenv("OV2_BA_NCOPY")) { int e = atoi(getenv("OV2_BA_NCOPY")); if (e >= 1 && e <= 8 && (size_t)e * H.blk <= (size_t)(3 * MAX_N + MAX_N * MAX_N)) H.ncopy = e; }
     H.solve_blocked = H.n_max > 96 ? 1 : 0;
     // states (pose, inverse depth) of all windows sit together at the head of the block: they are what comes back
     H.off_pose = take(st_off, sizeof(double) * 7 * ncam, 16);
@@ -1268,8 +1286,11 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     // with two CTAs per SM still possible
     H.smem_sacc_off = schur / sizeof(double);
     H.schur_smem = 0;
+    // (opt-in, OV2_BA_SCHUR_SMEM=1: measured 6x SLOWER than the RED path on a B200 - C3, 64 CTAs: 317 us vs 53 us per
+    //  Schur phase; the lock serialises the eight warps of a CTA for the whole commit.  Kept because it is tested and
+    //  documents the negative result.)
     const char* ssm = getenv("OV2_BA_SCHUR_SMEM");
-    if (H.n_max > 0 && s + schur + H.blk * sizeof(double) <= 100 * 1024 && !(ssm && atoi(ssm) == 0)) {
+    if (H.n_max > 0 && s + schur + H.blk * sizeof(double) <= 100 * 1024 && ssm && atoi(ssm) != 0) {
         H.schur_smem = 1;
         H.ncopy = 1;
         schur += H.blk * sizeof(double);
@@ -1512,9 +1533,10 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     if (getenv("OV2_BA_TRACE")) {
         unsigned long long tr[16];
         cudaMemcpy(tr, dwork + plans[0].w_trace, sizeof(tr), cudaMemcpyDeviceToHost);
-        static const char* names[12] = {"setup0", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb", "setup1", "bar0"};
-        fprintf(stderr, "[ba trace] G=%d grid=%d smem=%zu ncopy=%d |", G, grid, smem_max, plans[0].ncopy);
-        for (int k = 0; k < 12; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
+        static const char* names[16] = {"setup0", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb", "setup1", "bar0",
+                                        "chol:P1", "chol:bar", "chol:P2", "chol:back"};
+        fprintf(stderr, "[ba trace] G=%d grid=%d smem=%zu ncopy=%d smemS=%d |", G, grid, smem_max, plans[0].ncopy, plans[0].schur_smem);
+        for (int k = 0; k < 16; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
         fprintf(stderr, "\n");
     }
     bool numeric_fail = false, aborted = false;

@@ -9,9 +9,9 @@
 //   * per tile 256-bin histogram, clip = max(int(clip * area / 256), 1), excess redistributed
 //     (uniform batch + one each to bins 0, step, 2 step, ...), LUT = rint(cumsum * (255 / area))
 //   * per pixel float32 bilinear blend of the four neighbouring tile LUTs, rint.
-// clahe_lut_kernel: one CTA per (tile, frame), shared-memory histogram.  clahe_apply_kernel:
-// streaming pass, 4 pixels per thread (HBM-bound: reads W*H, writes W*H per frame; the LUTs
-// live in L2).
+// clahe_lut_kernel: one CTA per (tile, frame), per-warp shared-memory histograms from 32-bit loads.
+// clahe_apply_kernel: one CTA per (band of rows between two tile-centre lines, frame), its two LUT rows staged in
+// shared memory, streaming pass with 32-bit loads / stores (reads W*H, writes W*H per frame).
 #include "ov2_common.cuh"
 
 namespace {
@@ -31,23 +31,45 @@ __device__ __forceinline__ int refl(int i, int n) {
     return i;
 }
 
+// Tile histogram -> clipped, redistributed -> LUT.  One CTA per (tile, frame).  Interior tiles whose rows are 4-byte
+// addressable are read as 32-bit words (4 pixels per load); tiles that reach into the reflected extension, or unaligned
+// images, take the byte path.  Per-warp sub-histograms (8 x 256 counters) keep the shared-memory atomics of different
+// warps on different banks / addresses; they are summed when the clip is applied.
 __global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
+    __shared__ int whist[8][256];
     __shared__ int hist[256];
     __shared__ int s_excess;
     const int tile = blockIdx.x, fr = blockIdx.y;
     const int tyi = tile / A.tx, txi = tile - tyi * A.tx;
     const uint8_t* src = A.src + A.sfstride * fr;
-    hist[threadIdx.x] = 0;
+    const int warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < 8 * 256; k += 256) (&whist[0][0])[k] = 0;
     if (threadIdx.x == 0) s_excess = 0;
     __syncthreads();
     const int x0 = txi * A.tw, y0 = tyi * A.th, area = A.tw * A.th;
-    for (int i = threadIdx.x; i < area; i += 256) {
-        int yy = i / A.tw, xx = i - yy * A.tw;
-        int x = refl(x0 + xx, A.w), y = refl(y0 + yy, A.h);
-        atomicAdd(&hist[__ldg(src + (size_t)y * A.spitch + x)], 1);
+    const bool words = x0 + A.tw <= A.w && y0 + A.th <= A.h && (A.tw & 3) == 0 && (x0 & 3) == 0 && (A.spitch & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(src)) & 3) == 0;
+    if (words) {
+        const int wpr = A.tw >> 2, nw = wpr * A.th;
+        for (int i = threadIdx.x; i < nw; i += 256) {
+            const int yy = i / wpr, xw = i - yy * wpr;
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(y0 + yy) * A.spitch + x0) + xw);
+            atomicAdd(&whist[warp][v & 255u], 1);
+            atomicAdd(&whist[warp][(v >> 8) & 255u], 1);
+            atomicAdd(&whist[warp][(v >> 16) & 255u], 1);
+            atomicAdd(&whist[warp][v >> 24], 1);
+        }
+    } else {
+        for (int i = threadIdx.x; i < area; i += 256) {
+            int yy = i / A.tw, xx = i - yy * A.tw;
+            int x = refl(x0 + xx, A.w), y = refl(y0 + yy, A.h);
+            atomicAdd(&whist[warp][__ldg(src + (size_t)y * A.spitch + x)], 1);
+        }
     }
     __syncthreads();
-    int v = hist[threadIdx.x];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += whist[k][threadIdx.x];
     if (v > A.clip) { atomicAdd(&s_excess, v - A.clip); v = A.clip; }
     __syncthreads();
     const int clipped = s_excess;
@@ -80,37 +102,66 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
     A.lut[(((size_t)fr * A.ty + tyi) * A.tx + txi) * 256 + threadIdx.x] = (uint8_t)q;
 }
 
+// Interpolation pass.  All rows between two tile-centre lines use the same two LUT rows (ty1, ty2): one CTA takes such a
+// band of one frame, stages those two LUT rows (2 x tiles_x x 256 bytes) in shared memory with coalesced loads, then
+// streams the band: 4 pixels per thread and step (one 32-bit load, one 32-bit store), the four LUT gathers per pixel hit
+// shared memory instead of L1/L2.  Reads W*H, writes W*H per frame.
+constexpr int APPLY_MAX_TX = 64;
 __global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
-    const int fr = blockIdx.z;
-    const int y = blockIdx.y;
-    const int xq = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (xq >= A.w) return;
-    const uint8_t* srow = A.src + A.sfstride * fr + (size_t)y * A.spitch;
-    uint8_t* drow = A.dst + A.dfstride * fr + (size_t)y * A.dpitch;
+    extern __shared__ uint8_t s_lut[];                       // [2][tx][256]
+    const int fr = blockIdx.y, band = blockIdx.x;            // band b: rows whose floor(y / th - 0.5) == b - 1
     const uint8_t* lut = A.lut + (size_t)fr * A.ty * A.tx * 256;
-    const float tyf = (float)y * A.inv_th - 0.5f;
-    int ty1 = __float2int_rd(tyf);
-    const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
-    int ty2 = ty1 + 1;
-    ty1 = max(ty1, 0);
-    ty2 = min(ty2, A.ty - 1);
-    const uint8_t* l1 = lut + (size_t)ty1 * A.tx * 256;
-    const uint8_t* l2 = lut + (size_t)ty2 * A.tx * 256;
+    // rows of this band: ty1 = b - 1 (clamped), ty2 = b (clamped)
+    int ylo = 0, yhi = A.h;
+    {
+        // tyf = y * inv_th - 0.5 in float, floor -> band index - 1; find the row range by scanning the candidates around
+        // the analytic boundary (th / 2 + (b - 1) * th) so the float rounding of the kernel's own expression decides
+        const int c0 = (band - 1) * A.th + A.th / 2;
+        ylo = max(0, c0 - 2); yhi = min(A.h, c0 + A.th + 2);
+    }
+    const int t1 = max(band - 1, 0), t2 = min(band, A.ty - 1);
+    const int lut_row = A.tx * 256;
+    for (int i = threadIdx.x * 16; i < lut_row; i += 256 * 16) {
+        *reinterpret_cast<uint4*>(s_lut + i) = __ldg(reinterpret_cast<const uint4*>(lut + (size_t)t1 * lut_row + i));
+        *reinterpret_cast<uint4*>(s_lut + lut_row + i) = __ldg(reinterpret_cast<const uint4*>(lut + (size_t)t2 * lut_row + i));
+    }
+    __syncthreads();
+    const uint8_t* l1 = s_lut;
+    const uint8_t* l2 = s_lut + lut_row;
+    const bool words = ((A.spitch | A.dpitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.src + A.sfstride * fr) | reinterpret_cast<uintptr_t>(A.dst + A.dfstride * fr)) & 3) == 0;
+    const int wq = (A.w + 3) >> 2;
+    for (int y = ylo; y < yhi; ++y) {
+        const float tyf = (float)y * A.inv_th - 0.5f;
+        const int ty1 = __float2int_rd(tyf);
+        if (ty1 != band - 1) continue;                       // row belongs to a neighbouring band
+        const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+        const uint8_t* srow = A.src + A.sfstride * fr + (size_t)y * A.spitch;
+        uint8_t* drow = A.dst + A.dfstride * fr + (size_t)y * A.dpitch;
+        for (int xw = threadIdx.x; xw < wq; xw += 256) {
+            const int xq = xw * 4;
+            uint32_t in;
+            if (words && xq + 4 <= A.w) in = __ldg(reinterpret_cast<const uint32_t*>(srow + xq));
+            else { in = 0; for (int k = 0; k < 4 && xq + k < A.w; ++k) in |= (uint32_t)srow[xq + k] << (8 * k); }
+            uint32_t out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = xq + k;
-        if (x >= A.w) break;
-        const float txf = (float)x * A.inv_tw - 0.5f;
-        int tx1 = __float2int_rd(txf);
-        const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
-        int tx2 = tx1 + 1;
-        tx1 = max(tx1, 0);
-        tx2 = min(tx2, A.tx - 1);
-        const int v = srow[x];
-        const float r = ((float)l1[tx1 * 256 + v] * xa1 + (float)l1[tx2 * 256 + v] * xa) * ya1 +
-                        ((float)l2[tx1 * 256 + v] * xa1 + (float)l2[tx2 * 256 + v] * xa) * ya;
-        int q = __float2int_rn(r);
-        drow[x] = (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+            for (int k = 0; k < 4; ++k) {
+                const int x = xq + k;
+                const float txf = (float)x * A.inv_tw - 0.5f;
+                int tx1 = __float2int_rd(txf);
+                const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+                int tx2 = tx1 + 1;
+                tx1 = max(tx1, 0);
+                tx2 = min(tx2, A.tx - 1);
+                const int v = (in >> (8 * k)) & 255;
+                const float r = ((float)l1[tx1 * 256 + v] * xa1 + (float)l1[tx2 * 256 + v] * xa) * ya1 +
+                                ((float)l2[tx1 * 256 + v] * xa1 + (float)l2[tx2 * 256 + v] * xa) * ya;
+                int q = __float2int_rn(r);
+                q = q < 0 ? 0 : (q > 255 ? 255 : q);
+                out |= (uint32_t)q << (8 * k);
+            }
+            if (words && xq + 4 <= A.w) *reinterpret_cast<uint32_t*>(drow + xq) = out;
+            else for (int k = 0; k < 4 && xq + k < A.w; ++k) drow[xq + k] = (uint8_t)(out >> (8 * k));
+        }
     }
 }
 
@@ -147,8 +198,13 @@ static ov2_status clahe_device(ov2_ctx* ctx, const uint8_t* src, int spitch, lon
     if ((st = ov2_scratch(ctx, (size_t)count * tiles_x * tiles_y * 256, &o)) != OV2_OK) return st;
     A.lut = (uint8_t*)o;
     OV2_LAUNCH(ctx, "clahe_lut_kernel", clahe_lut_kernel<<<dim3(tiles_x * tiles_y, count), 256, 0, ctx->stream>>>(A));
-    OV2_LAUNCH(ctx, "clahe_apply_kernel",
-               clahe_apply_kernel<<<dim3(div_up(width, 1024), height, count), 256, 0, ctx->stream>>>(A));
+    if (tiles_x > APPLY_MAX_TX) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_clahe: more than 64 tile columns");
+    {
+        const size_t smem = (size_t)2 * tiles_x * 256;
+        if (smem > 48 * 1024) OV2_CUDA(ctx, cudaFuncSetAttribute(clahe_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // bands 0 .. tiles_y: rows above the first / below the last tile-centre line clamp to one LUT row
+        OV2_LAUNCH(ctx, "clahe_apply_kernel", clahe_apply_kernel<<<dim3(tiles_y + 1, count), 256, smem, ctx->stream>>>(A));
+    }
     return OV2_OK;
 }
 

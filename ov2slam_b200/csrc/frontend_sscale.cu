@@ -31,6 +31,7 @@ struct RespArgs {
     const uint8_t* img; int w, h, pitch; long long fstride;
     int first, cs, nwc, nhc;
     float* resp;            // [count][ncells][cs*cs]
+    float2* cellmax;        // [count][ncells]: (first maximum of the cell's response, its row-major index as int bits)
 };
 
 __global__ void __launch_bounds__(256) ss_response_kernel(RespArgs A) {
@@ -56,8 +57,32 @@ __global__ void __launch_bounds__(256) ss_response_kernel(RespArgs A) {
     __syncthreads();
     sscale::phase_cov(threadIdx.x, blockDim.x, bl, cxx, cxy, cyy, cs);
     __syncthreads();
-    sscale::phase_response(threadIdx.x, blockDim.x, cxx, cxy, cyy,
-                           A.resp + ((size_t)fr * (A.nwc * A.nhc) + cell) * (size_t)(cs * cs), cs);
+    float* out = A.resp + ((size_t)fr * (A.nwc * A.nhc) + cell) * (size_t)(cs * cs);
+    sscale::phase_response(threadIdx.x, blockDim.x, cxx, cxy, cyy, out, cs);
+    // first maximum (row-major) of the unmasked response: lets the sweep skip its first arg-max scan whenever that pixel
+    // is not masked (the usual case)
+    __syncthreads();
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) {
+        const float v = out[i];                                   // written by this CTA just above
+        if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+            if (s_v[k] > bv || (s_v[k] == bv && s_i[k] < bi)) { bv = s_v[k]; bi = s_i[k]; }
+        A.cellmax[(size_t)fr * (A.nwc * A.nhc) + cell] = make_float2(bv, __int_as_float(bi));
+    }
 }
 
 struct SweepArgs {
@@ -67,6 +92,7 @@ struct SweepArgs {
     const int32_t* kp_off;           // [count+1] or NULL
     const float2* kps;
     const float* resp;               // [count][ncells][cs*cs]
+    const float2* cellmax;           // [count][ncells] first maximum per cell (value, index bits)
     double* quality;                 // in/out per frame
     int2* out_int;                   // [count][max_per_frame]
     int32_t* out_n;                  // [count]
@@ -183,9 +209,19 @@ __global__ void __launch_bounds__(SWEEP_MAX_WARPS * 32, 1) ss_sweep_kernel(Sweep
                 __threadfence_block();
             }
             if (search) {
+                const float2 cm = A.cellmax[(size_t)fr * ncells + cell];
                 for (int round = 0; round < 2; ++round) {
                     float mx; int idx;
-                    if (in_regs) {
+                    bool have = false;
+                    if (round == 0 && cm.x > 0.0f) {
+                        // the cell's first maximum is the answer unless a disc already covers it (masked pixels count as 0 < cm.x)
+                        const int ci = __float_as_int(cm.y);
+                        const int qy = ci / cs, qx = ci - qy * cs;
+                        const int gx = x0 + qx, gy = y0 + qy;
+                        if (!((bm[(size_t)gy * wpr + (gx >> 5)] >> (gx & 31)) & 1u)) { mx = cm.x; idx = ci; have = true; }
+                    }
+                    if (have) {
+                    } else if (in_regs) {
                         float bv = -INFINITY;
                         int bi = 0x7fffffff;
                         int yy = lane / cs, xx = lane - yy * cs;
@@ -336,10 +372,12 @@ extern "C" ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, 
     const size_t cell_px = (size_t)cellsize * cellsize;
     if ((st = ov2_scratch(ctx, sizeof(float) * (size_t)count * ncells * cell_px, &o)) != OV2_OK) return st;
     float* d_resp = (float*)o;
+    if ((st = ov2_scratch(ctx, sizeof(float2) * (size_t)count * ncells, &o)) != OV2_OK) return st;
+    float2* d_cellmax = (float2*)o;
 
     RespArgs RA;
     RA.img = pyr->l0; RA.w = W; RA.h = H; RA.pitch = (int)pyr->l0_pitch; RA.fstride = (long long)pyr->l0_fstride;
-    RA.first = first; RA.cs = cellsize; RA.nwc = nwc; RA.nhc = nhc; RA.resp = d_resp;
+    RA.first = first; RA.cs = cellsize; RA.nwc = nwc; RA.nhc = nhc; RA.resp = d_resp; RA.cellmax = d_cellmax;
     {
         const size_t smem = sscale::smem_bytes(cellsize);
         if (smem > 48 * 1024)
@@ -350,7 +388,7 @@ extern "C" ov2_status ov2_detect_single_scale(ov2_ctx* ctx, const ov2_pyr* pyr, 
     SA.w = W; SA.h = H; SA.cs = cellsize; SA.nwc = nwc; SA.nhc = nhc; SA.radius = cellsize / 4; SA.max_per_frame = max_per_frame;
     circle_halfwidths(SA.radius, SA.hw);
     SA.roi_x = roi[0]; SA.roi_y = roi[1]; SA.roi_w = roi[2]; SA.roi_h = roi[3];
-    SA.kp_off = d_off; SA.kps = d_kps; SA.resp = d_resp; SA.quality = d_q; SA.out_int = d_int; SA.out_n = d_cnt;
+    SA.kp_off = d_off; SA.kps = d_kps; SA.resp = d_resp; SA.cellmax = d_cellmax; SA.quality = d_q; SA.out_int = d_int; SA.out_n = d_cnt;
     {
         const size_t wpr = (size_t)(W + 31) / 32;
         size_t smem = (((size_t)H * wpr + 1) & ~(size_t)1) * 4 + (size_t)ncells * sizeof(int2) * 2 + (size_t)nhc * sizeof(int) +

@@ -243,3 +243,13 @@ def test_localba_bal_structure_fixture(ctx):
     assert np.abs(gpu["pose"] - ref["pose"]).max() <= 1e-6
     assert np.abs(gpu["lm_invdepth"] - ref["lm_invdepth"]).max() <= 1e-6
     assert (flags != r["flags"]).sum() <= 3
+
+
+@pytest.mark.parametrize("env", [{"OV2_BA_SCHUR_SMEM": "1"}, {"OV2_BA_NCOPY": "4"}, {"OV2_BA_COOP": "1"}])
+def test_localba_optional_kernel_modes(ctx, monkeypatch, env):
+    """The opt-in variants of the persistent kernel stay correct: shared-memory Schur accumulation under a CTA lock, privatised
+    accumulation copies + fold phase, cooperative launch."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _check(ctx, synth.make_ba_problem(3, 10, 2000, 8000))
+    _check(ctx, synth.make_ba_problem(42, 10, 1000, 4000, stereo=True))
