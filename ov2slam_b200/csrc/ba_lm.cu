@@ -283,12 +283,14 @@ constexpr int SCH = 8;   // observations staged per chunk (C3: 4 per landmark, C
 
 // CTA-local lock for the shared-memory accumulation mode: lane 0 spins on a shared-memory CAS, the warp follows.
 __device__ __forceinline__ void warp_lock(int* lock, int lane) {
+    if (!lock) return;                       // per-warp private block: nothing to serialise
     if (lane == 0)
         while (atomicCAS(lock, 0, 1) != 0) __nanosleep(20);
     __syncwarp();
     __threadfence_block();
 }
 __device__ __forceinline__ void warp_unlock(int* lock, int lane) {
+    if (!lock) return;
     __threadfence_block();
     __syncwarp();
     if (lane == 0) atomicExch(lock, 0);
@@ -420,17 +422,25 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
         if (e1 < 36 && e1a <= e1b) ACC(cS + (size_t)(6 * sa + e1a) * n + 6 * sa + e1b, aFF1);
         if (lane < 6) { ACC(cG + 6 * sa + lane, aG); ACC(cCn + 6 * sa + lane, aCn); }
     }
-    // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i -= EtF_i ge / ete
-    const int npair = m * m;
-    for (int e = lane; e < npair * 36; e += 32) {
-        const int pr = e / 36, q = e - 36 * pr;
-        const int i = pr / m, j = pr - m * i;
-        const int si = s_eslot[i], sj = s_eslot[j];
-        if (si > sj || (si == sj && i > j)) continue;   // upper block triangle; (i,i) once
-        const int a = q / 6, b = q - 6 * a;
-        if (si == sj && a > b) continue;
-        const double v = s_etf[6 * i + a] * s_etf[6 * j + b] * inv_ete;   // slots are unique in the list
-        ACC(cS + (size_t)(6 * si + a) * n + 6 * sj + b, -v);
+    // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i -= EtF_i ge / ete.  Pair-major: every unordered
+    // pair of touching keyframes once, oriented by slot (the upper block), the 36 entries of a block on lanes 0..31 + a
+    // second pass of 4 lanes - no per-entry divisions, no skipped iterations.
+    {
+        const int a0 = lane / 6, b0 = lane - 6 * a0;            // entry of pass 1
+        const int a1 = 5, b1 = 2 + lane;                        // entries 32..35 of pass 2 (lanes 0..3)
+        for (int i = 0; i < m; ++i) {
+            const int si = s_eslot[i];
+            for (int j = i; j < m; ++j) {
+                const int sj = s_eslot[j];
+                const bool swap = si > sj;                      // block (lo, hi) with lo <= hi; entry (a, b) = etf_lo[a] etf_hi[b]
+                const double* el = s_etf + 6 * (swap ? j : i);
+                const double* eh = s_etf + 6 * (swap ? i : j);
+                const int lo = swap ? sj : si, hi = swap ? si : sj;
+                double* blkp = cS + (size_t)(6 * lo) * n + 6 * hi;
+                if (i != j || a0 <= b0) ACC(blkp + (size_t)a0 * n + b0, -(el[a0] * eh[b0] * inv_ete));
+                if (lane < 4 && (i != j || a1 <= b1)) ACC(blkp + (size_t)a1 * n + b1, -(el[a1] * eh[b1] * inv_ete));
+            }
+        }
     }
     for (int e = lane; e < m * 6; e += 32) {
         const int i = e / 6, a = e - 6 * i;
@@ -455,9 +465,12 @@ __device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fai
     for (int j = 0; j < n; ++j) {
         const double p = sA[j * PIT + j];
         if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) *s_fail = 1; break; }   // uniform: every thread reads the same pivot
-        double ip = (double)__frcp_rn((float)p);
-        ip = ip * (2.0 - p * ip);
-        ip = ip * (2.0 - p * ip);
+        // 1 / p sits on the critical path of every pivot (B200: ~50 cycles per DEPENDENT fp64 operation - the 48-pivot loop
+        // is latency bound on this chain): MUFU double-precision seed (2^-23) + two Newton steps, no float round trip
+        double ip;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip) : "d"(p));
+        ip = fma(ip, fma(-p, ip, 1.0), ip);
+        ip = fma(ip, fma(-p, ip, 1.0), ip);
         const double* rowj = sA + j * PIT;
         const int c0 = j + 1 + sub;
         const int nq = (n - j + 3 - sub) >> 2;              // columns c = c0 + 4 q <= n
@@ -928,7 +941,25 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 bar.sync();
                 TR(1);
                 // ---- B: Schur elimination into this CTA's accumulation copy (global, RED) or shared-memory block (lock)
-                if (P.schur_smem) {
+                if (P.schur_smem == 2) {
+                    // per-WARP private copies of [rhs | F'r | column norms | S] in shared memory: plain read-modify-writes, no
+                    // lock, no RED; the CTA sums its copies and sends the non-zeros to the global block once per phase
+                    const int live_s = 3 * n + n * n;
+                    double* mine = s_work + P.smem_sacc_off + (size_t)warp * live_s;
+                    for (int e = lane; e < live_s; e += 32) mine[e] = 0.0;
+                    __syncwarp();
+                    double gmax_lm = 0.0;
+                    for (int l = gwarp; l < P.npts; l += gwarps) schur_landmark<true>(P, s_slot, s_etf, s_eslot, sJ, smeta, l, lane, radius, first_iter, mine, n, gmax_lm, nullptr);
+                    if (lane == 0 && gmax_lm > 0.0) atomic_max_pos(scal + SC_GMAX_LM, gmax_lm);
+                    __syncthreads();
+                    const double* all = s_work + P.smem_sacc_off;
+                    for (int e = tid; e < live_s; e += THREADS) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int w_ = 0; w_ < WARPS; ++w_) v += all[(size_t)w_ * live_s + e];
+                        if (v != 0.0) atomicAdd(P.acc + e, v);
+                    }
+                } else if (P.schur_smem) {
                     double* sS = s_work + P.smem_sacc_off;
                     const int live_s = 3 * n + n * n;
                     for (int e = tid; e < live_s; e += THREADS) sS[e] = 0.0;
@@ -1290,10 +1321,15 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     //  Schur phase; the lock serialises the eight warps of a CTA for the whole commit.  Kept because it is tested and
     //  documents the negative result.)
     const char* ssm = getenv("OV2_BA_SCHUR_SMEM");
-    if (H.n_max > 0 && s + schur + H.blk * sizeof(double) <= 100 * 1024 && ssm && atoi(ssm) != 0) {
+    if (H.n_max > 0 && s + schur + H.blk * sizeof(double) <= 100 * 1024 && ssm && atoi(ssm) == 1) {
         H.schur_smem = 1;
         H.ncopy = 1;
         schur += H.blk * sizeof(double);
+    } else if (H.n_max > 0 && s + schur + (size_t)WARPS * H.blk * sizeof(double) <= 190 * 1024 && !(ssm && atoi(ssm) == 0)) {
+        // mode 2 (default when it fits: reduced systems up to n = 54): one private block per warp, one CTA per SM
+        H.schur_smem = 2;
+        H.ncopy = 1;
+        schur += (size_t)WARPS * H.blk * sizeof(double);
     }
     H.smem_bytes = s + (schur > solve ? schur : solve) + 16;
     (void)world;
@@ -1397,7 +1433,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         if ((st = plan_window(ctx, &hp[k], world, st_off, in_off, work_off, plans[k], 8)) != OV2_OK) return st;
         if (plans[k].smem_bytes > smem_max) smem_max = plans[k].smem_bytes;
         const int wk = (pb.nobs + THREADS - 1) / THREADS;
-        const int wl = (pb.npts + 4 * WARPS - 1) / (4 * WARPS);          // ~4 landmarks per warp and phase
+        const int wl = (pb.npts + WARPS - 1) / WARPS;                  // a landmark per warp and phase (single window: every SM helps)
         const int w = wk > wl ? wk : wl;
         if (w > gmax_work) gmax_work = w;
     }
