@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
 // streams the band: 4 pixels per thread and step (one 32-bit load, one 32-bit store), the four LUT gathers per pixel hit
 // shared memory instead of L1/L2.  Reads W*H, writes W*H per frame.
 constexpr int APPLY_MAX_TX = 64;
-__global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
+__global__ void __launch_bounds__(512) clahe_apply_kernel(ClaheArgs A) {
     extern __shared__ uint8_t s_lut[];                       // [2][tx][256]
     const int fr = blockIdx.y, band = blockIdx.x;            // band b: rows whose floor(y / th - 0.5) == b - 1
     const uint8_t* lut = A.lut + (size_t)fr * A.ty * A.tx * 256;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
     }
     const int t1 = max(band - 1, 0), t2 = min(band, A.ty - 1);
     const int lut_row = A.tx * 256;
-    for (int i = threadIdx.x * 16; i < lut_row; i += 256 * 16) {
+    for (int i = threadIdx.x * 16; i < lut_row; i += blockDim.x * 16) {
         *reinterpret_cast<uint4*>(s_lut + i) = __ldg(reinterpret_cast<const uint4*>(lut + (size_t)t1 * lut_row + i));
         *reinterpret_cast<uint4*>(s_lut + lut_row + i) = __ldg(reinterpret_cast<const uint4*>(lut + (size_t)t2 * lut_row + i));
     }
@@ -130,36 +130,47 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(ClaheArgs A) {
     const uint8_t* l2 = s_lut + lut_row;
     const bool words = ((A.spitch | A.dpitch) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.src + A.sfstride * fr) | reinterpret_cast<uintptr_t>(A.dst + A.dfstride * fr)) & 3) == 0;
     const int wq = (A.w + 3) >> 2;
-    for (int y = ylo; y < yhi; ++y) {
-        const float tyf = (float)y * A.inv_th - 0.5f;
-        const int ty1 = __float2int_rd(tyf);
-        if (ty1 != band - 1) continue;                       // row belongs to a neighbouring band
-        const float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
-        const uint8_t* srow = A.src + A.sfstride * fr + (size_t)y * A.spitch;
-        uint8_t* drow = A.dst + A.dfstride * fr + (size_t)y * A.dpitch;
-        for (int xw = threadIdx.x; xw < wq; xw += 256) {
-            const int xq = xw * 4;
+    // first / last row of the band by the kernel's own float expression (candidates around the analytic boundary)
+    int ya_ = yhi, yb_ = ylo;
+    for (int y = ylo; y < yhi; ++y)
+        if (__float2int_rd((float)y * A.inv_th - 0.5f) == band - 1) { ya_ = min(ya_, y); yb_ = max(yb_, y + 1); }
+    // column-stationary: a thread keeps the horizontal interpolation data of its 4 pixels (two LUT column offsets and the
+    // two weights each - they depend on x only) in registers and walks down the rows of the band
+    for (int xw = threadIdx.x; xw < wq; xw += blockDim.x) {
+        const int xq = xw * 4;
+        int o1[4], o2[4];
+        float wa[4], wb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float txf = (float)(xq + k) * A.inv_tw - 0.5f;
+            int tx1 = __float2int_rd(txf);
+            wa[k] = txf - (float)tx1;
+            wb[k] = 1.0f - wa[k];
+            int tx2 = tx1 + 1;
+            tx1 = max(tx1, 0);
+            tx2 = min(tx2, A.tx - 1);
+            o1[k] = tx1 * 256; o2[k] = tx2 * 256;
+        }
+        const bool full = words && xq + 4 <= A.w;
+        for (int y = ya_; y < yb_; ++y) {
+            const float tyf = (float)y * A.inv_th - 0.5f;
+            const float ya = tyf - (float)(band - 1), ya1 = 1.0f - ya;
+            const uint8_t* srow = A.src + A.sfstride * fr + (size_t)y * A.spitch;
+            uint8_t* drow = A.dst + A.dfstride * fr + (size_t)y * A.dpitch;
             uint32_t in;
-            if (words && xq + 4 <= A.w) in = __ldg(reinterpret_cast<const uint32_t*>(srow + xq));
+            if (full) in = __ldg(reinterpret_cast<const uint32_t*>(srow + xq));
             else { in = 0; for (int k = 0; k < 4 && xq + k < A.w; ++k) in |= (uint32_t)srow[xq + k] << (8 * k); }
             uint32_t out = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int x = xq + k;
-                const float txf = (float)x * A.inv_tw - 0.5f;
-                int tx1 = __float2int_rd(txf);
-                const float xa = txf - (float)tx1, xa1 = 1.0f - xa;
-                int tx2 = tx1 + 1;
-                tx1 = max(tx1, 0);
-                tx2 = min(tx2, A.tx - 1);
                 const int v = (in >> (8 * k)) & 255;
-                const float r = ((float)l1[tx1 * 256 + v] * xa1 + (float)l1[tx2 * 256 + v] * xa) * ya1 +
-                                ((float)l2[tx1 * 256 + v] * xa1 + (float)l2[tx2 * 256 + v] * xa) * ya;
+                const float r = ((float)l1[o1[k] + v] * wb[k] + (float)l1[o2[k] + v] * wa[k]) * ya1 +
+                                ((float)l2[o1[k] + v] * wb[k] + (float)l2[o2[k] + v] * wa[k]) * ya;
                 int q = __float2int_rn(r);
                 q = q < 0 ? 0 : (q > 255 ? 255 : q);
                 out |= (uint32_t)q << (8 * k);
             }
-            if (words && xq + 4 <= A.w) *reinterpret_cast<uint32_t*>(drow + xq) = out;
+            if (full) *reinterpret_cast<uint32_t*>(drow + xq) = out;
             else for (int k = 0; k < 4 && xq + k < A.w; ++k) drow[xq + k] = (uint8_t)(out >> (8 * k));
         }
     }
@@ -203,7 +214,9 @@ static ov2_status clahe_device(ov2_ctx* ctx, const uint8_t* src, int spitch, lon
         const size_t smem = (size_t)2 * tiles_x * 256;
         if (smem > 48 * 1024) OV2_CUDA(ctx, cudaFuncSetAttribute(clahe_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // bands 0 .. tiles_y: rows above the first / below the last tile-centre line clamp to one LUT row
-        OV2_LAUNCH(ctx, "clahe_apply_kernel", clahe_apply_kernel<<<dim3(tiles_y + 1, count), 256, smem, ctx->stream>>>(A));
+        int nthr = ((((width + 3) >> 2) + 31) / 32) * 32;                  // one thread per 4-pixel column of the image
+        if (nthr > 512) nthr = 512;
+        OV2_LAUNCH(ctx, "clahe_apply_kernel", clahe_apply_kernel<<<dim3(tiles_y + 1, count), nthr, smem, ctx->stream>>>(A));
     }
     return OV2_OK;
 }
