@@ -310,10 +310,12 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
     double cnl = 0.0, ge = 0.0;
     int nact = 0;
     for (int p = p0 + lane; p < p1; p += 32) {
-        if (!P.active[p]) continue;
-        const double a = P.Jl[2 * (size_t)p], b = P.Jl[2 * (size_t)p + 1];
-        cnl += a * a + b * b;
-        ge += a * P.Jr[2 * (size_t)p] + b * P.Jr[2 * (size_t)p + 1];
+        const uint8_t act = P.active[p];                                   // loads issued together, selected after
+        const double2 jl = *reinterpret_cast<const double2*>(P.Jl + 2 * (size_t)p);
+        const double2 jr = *reinterpret_cast<const double2*>(P.Jr + 2 * (size_t)p);
+        if (!act) continue;
+        cnl += jl.x * jl.x + jl.y * jl.y;
+        ge += jl.x * jr.x + jl.y * jr.y;
         nact++;
     }
     cnl = warp_sum(cnl);
@@ -345,7 +347,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
     }
     __syncwarp();
     // anchor accumulators: lane owns entries e = lane and lane + 32 of the 6x6 (a = e / 6, b = e % 6, a <= b kept)
-    double aFF0 = 0.0, aFF1 = 0.0, aG = 0.0, aCn = 0.0;
+    double aFF0 = 0.0, aFF1 = 0.0, aG = 0.0, aCn = 0.0, aE = 0.0;
     const int e0a = lane / 6, e0b = lane - 6 * e0a;
     const int e1 = lane + 32, e1a = e1 / 6, e1b = e1 - 6 * e1a;
     // The Jacobian rows of the landmark's observations are staged in this warp's shared-memory slice SCH at a time (coalesced
@@ -359,9 +361,9 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
         if (lane < 2 * cnt) { sJl[lane] = P.Jl[2 * (size_t)pb + lane]; sJr[lane] = P.Jr[2 * (size_t)pb + lane]; }
         if (lane < cnt) {
             const int p = pb + lane;
-            int mt = -3;                                         // inactive
-            if (P.active[p]) mt = (P.obs_type && P.obs_type[p] == 2) ? -2 : s_slot[P.obs_cam[p]];   // -2: e-block-only row (schur_eliminator_impl.h:196-217)
-            smeta[lane] = mt;
+            const uint8_t act = P.active[p], ty = P.obs_type ? P.obs_type[p] : 0;
+            const int cam = P.obs_cam[p];
+            smeta[lane] = !act ? -3 : (ty == 2 ? -2 : s_slot[cam]);   // -3: inactive, -2: e-block-only row (schur_eliminator_impl.h:196-217)
         }
         __syncwarp();
         if (SM) warp_lock(lock, lane);
@@ -378,14 +380,10 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             if (lane < 6) {
                 aG += Ja[lane] * r0 + Ja[6 + lane] * r1;
                 aCn += Ja[lane] * Ja[lane] + Ja[6 + lane] * Ja[6 + lane];
-                s_etf[lane] += jl0 * Ja[lane] + jl1 * Ja[6 + lane];
+                aE += jl0 * Ja[lane] + jl1 * Ja[6 + lane];
             }
         }
         if (so >= 0) {
-            for (int e = lane; e < 36; e += 32) {
-                const int a = e / 6, b = e - 6 * a;
-                if (a <= b) ACC(cS + (size_t)(6 * so + a) * n + 6 * so + b, Jo[a] * Jo[b] + Jo[6 + a] * Jo[6 + b]);
-            }
             // E'F row of this keyframe: a stereo keyframe contributes two residual blocks (left and right camera) to the
             // same pose block, so look the slot up before appending a new entry
             int idx = -1;
@@ -395,20 +393,34 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
             const bool fresh = idx < 0;
             if (fresh) idx = m;
             if (lane < 6) {
-                ACC(cG + 6 * so + lane, Jo[lane] * r0 + Jo[6 + lane] * r1);
-                ACC(cCn + 6 * so + lane, Jo[lane] * Jo[lane] + Jo[6 + lane] * Jo[6 + lane]);
                 const double e = jl0 * Jo[lane] + jl1 * Jo[6 + lane];
                 s_etf[6 * idx + lane] = fresh ? e : s_etf[6 * idx + lane] + e;
             }
             if (lane == 0 && fresh) s_eslot[idx] = so;
-            if (sa >= 0) {
-                // cross block Ja' Jo into the upper block (min slot, max slot)
-                for (int e = lane; e < 36; e += 32) {
-                    const int a = e / 6, b = e - 6 * a;   // a: anchor column, b: observer column
-                    const double v = Ja[a] * Jo[b] + Ja[6 + a] * Jo[6 + b];
-                    if (sa < so) ACC(cS + (size_t)(6 * sa + a) * n + 6 * so + b, v);
-                    else ACC(cS + (size_t)(6 * so + b) * n + 6 * sa + a, v);
-                }
+            // The observation's six contributions per lane (observer diagonal block: 32 + 1 entries, F'r, column norms, cross
+            // block Ja' Jo: 32 + 4 entries) go to DISTINCT addresses: addresses and values first, then all the loads, then all
+            // the stores - the shared-memory mode pays one read-modify-write latency per observation instead of six.
+            const int l6 = lane < 6 ? lane : 0, l4 = lane & 3;
+            double* qp[6]; double qv[6]; bool qk[6];
+            qk[0] = e0a <= e0b; qp[0] = cS + (size_t)(6 * so + e0a) * n + 6 * so + e0b; qv[0] = Jo[e0a] * Jo[e0b] + Jo[6 + e0a] * Jo[6 + e0b];
+            qk[1] = lane == 3;  qp[1] = cS + (size_t)(6 * so + 5) * n + 6 * so + 5;     qv[1] = Jo[5] * Jo[5] + Jo[11] * Jo[11];
+            qk[2] = lane < 6;   qp[2] = cG + 6 * so + l6;                               qv[2] = Jo[l6] * r0 + Jo[6 + l6] * r1;
+            qk[3] = lane < 6;   qp[3] = cCn + 6 * so + l6;                              qv[3] = Jo[l6] * Jo[l6] + Jo[6 + l6] * Jo[6 + l6];
+            // cross block Ja' Jo into the upper block (min slot, max slot); a: anchor column, b: observer column
+            qk[4] = sa >= 0;             qv[4] = Ja[e0a] * Jo[e0b] + Ja[6 + e0a] * Jo[6 + e0b];
+            qk[5] = sa >= 0 && lane < 4; qv[5] = Ja[5] * Jo[2 + l4] + Ja[11] * Jo[8 + l4];
+            const int sa0 = sa >= 0 ? sa : 0;
+            if (sa0 < so) { qp[4] = cS + (size_t)(6 * sa0 + e0a) * n + 6 * so + e0b; qp[5] = cS + (size_t)(6 * sa0 + 5) * n + 6 * so + 2 + l4; }
+            else          { qp[4] = cS + (size_t)(6 * so + e0b) * n + 6 * sa0 + e0a; qp[5] = cS + (size_t)(6 * so + 2 + l4) * n + 6 * sa0 + 5; }
+            if (SM) {
+                double qo[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) qo[u] = qk[u] ? *qp[u] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u) if (qk[u]) *qp[u] = qo[u] + qv[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 6; ++u) if (qk[u]) atomicAdd(qp[u], qv[u]);
             }
             if (fresh) m++;
         }
@@ -422,23 +434,46 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
         if (e1 < 36 && e1a <= e1b) ACC(cS + (size_t)(6 * sa + e1a) * n + 6 * sa + e1b, aFF1);
         if (lane < 6) { ACC(cG + 6 * sa + lane, aG); ACC(cCn + 6 * sa + lane, aCn); }
     }
+    if (sa >= 0 && lane < 6) s_etf[lane] += aE;     // the anchor's E'F row was summed in registers
+    __syncwarp();
     // Schur complement: S[i,j] -= EtF_i' EtF_j / ete (upper blocks), rhs_i -= EtF_i ge / ete.  Pair-major: every unordered
     // pair of touching keyframes once, oriented by slot (the upper block), the 36 entries of a block on lanes 0..31 + a
     // second pass of 4 lanes - no per-entry divisions, no skipped iterations.
     {
         const int a0 = lane / 6, b0 = lane - 6 * a0;            // entry of pass 1
-        const int a1 = 5, b1 = 2 + lane;                        // entries 32..35 of pass 2 (lanes 0..3)
-        for (int i = 0; i < m; ++i) {
-            const int si = s_eslot[i];
-            for (int j = i; j < m; ++j) {
-                const int sj = s_eslot[j];
+        const int a1 = 5, b1 = 2 + (lane & 3);                  // entries 32..35 of pass 2 (lanes 0..3)
+        constexpr int U = 4;                                    // pairs per batch: 2 U independent read-modify-writes in flight
+        const int npair = m * (m + 1) / 2;
+        int i = 0, j = 0;
+        for (int t0 = 0; t0 < npair; t0 += U) {
+            double* q0[U]; double* q1[U]; double v0[U], v1[U]; bool k0[U], k1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool live = t0 + u < npair;
+                const int ii = live ? i : 0, jj = live ? j : 0;
+                const int si = s_eslot[ii], sj = s_eslot[jj];
                 const bool swap = si > sj;                      // block (lo, hi) with lo <= hi; entry (a, b) = etf_lo[a] etf_hi[b]
-                const double* el = s_etf + 6 * (swap ? j : i);
-                const double* eh = s_etf + 6 * (swap ? i : j);
+                const double* el = s_etf + 6 * (swap ? jj : ii);
+                const double* eh = s_etf + 6 * (swap ? ii : jj);
                 const int lo = swap ? sj : si, hi = swap ? si : sj;
                 double* blkp = cS + (size_t)(6 * lo) * n + 6 * hi;
-                if (i != j || a0 <= b0) ACC(blkp + (size_t)a0 * n + b0, -(el[a0] * eh[b0] * inv_ete));
-                if (lane < 4 && (i != j || a1 <= b1)) ACC(blkp + (size_t)a1 * n + b1, -(el[a1] * eh[b1] * inv_ete));
+                q0[u] = blkp + (size_t)a0 * n + b0;
+                q1[u] = blkp + (size_t)a1 * n + b1;
+                k0[u] = live && (ii != jj || a0 <= b0);
+                k1[u] = live && lane < 4 && (ii != jj || a1 <= b1);
+                v0[u] = -(el[a0] * eh[b0] * inv_ete);
+                v1[u] = -(el[a1] * eh[b1] * inv_ete);
+                if (live && ++j == m) { ++i; j = i; }
+            }
+            if (SM) {
+                double o0[U], o1[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { o0[u] = k0[u] ? *q0[u] : 0.0; o1[u] = k1[u] ? *q1[u] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { if (k0[u]) *q0[u] = o0[u] + v0[u]; if (k1[u]) *q1[u] = o1[u] + v1[u]; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) { if (k0[u]) atomicAdd(q0[u], v0[u]); if (k1[u]) atomicAdd(q1[u], v1[u]); }
             }
         }
     }
@@ -590,22 +625,28 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
             }
             __syncthreads();
             if (warp == 0) {
+                // One warp, lane = column, the column's 32 rows in REGISTERS (fully unrolled): per pivot the dependent
+                // chain is shuffle -> MUFU rsqrt seed + two Newton steps -> scale -> one shared-memory row broadcast ->
+                // 31 independent FMAs.  (The shared-memory read-modify-write form this replaces serialised ~16 row
+                // updates per pivot on the ~50-cycle fp64 latency: 1.5 k cycles per pivot, 25 us per block step.)
                 bool bad = false;
+                double a[CH_NB];
+#pragma unroll
+                for (int r = 0; r < CH_NB; ++r) a[r] = sU[r][lane];
+#pragma unroll
                 for (int j = 0; j < CH_NB; ++j) {
-                    const double d = sU[j][j];
+                    const double d = __shfl_sync(FULL, a[j], j);
                     bad = bad || !(d > 1e-30) || !(d < 1e30);
-                    double is = (double)rsqrtf((float)d);
-                    is = is * (1.5 - 0.5 * d * is * is);
-                    is = is * (1.5 - 0.5 * d * is * is);
-                    const double ujc = lane >= j ? sU[j][lane] * is : 0.0;
-                    __syncwarp();
-                    sU[j][lane] = ujc;
+                    double is;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(is) : "d"(d));
+                    is = fma(0.5 * is, fma(-d * is, is, 1.0), is);
+                    is = fma(0.5 * is, fma(-d * is, is, 1.0), is);
+                    const double ujc = lane >= j ? a[j] * is : 0.0;
+                    sU[j][lane] = ujc;                     // row j of U: final value, and the broadcast source below
                     if (lane == j) s_idiag[j] = is;
                     __syncwarp();
-#pragma unroll 4
-                    for (int r = j + 1; r < CH_NB; ++r)
-                        if (lane >= r) sU[r][lane] -= sU[j][r] * ujc;
-                    __syncwarp();
+#pragma unroll
+                    for (int r = j + 1; r < CH_NB; ++r) a[r] = fma(-sU[j][r], ujc, a[r]);   // entries below the diagonal (r > lane) are never read
                 }
                 if (bad && lane == 0) { s_bad = 1; scal[SC_CHOL_FAIL] = 1.0; }
             }

@@ -13,8 +13,26 @@ from oracle import image_ref as R
 
 pytestmark = pytest.mark.gpu
 
-SUBPIX_TOL = 1e-5   # px; observed on a B200 vs cv2 4.13: 6 135 points, 100 % bit-equal (scripts/parity_stats.py, profiles/r2_parity_stats.json)
-KLT_TOL = 1e-3      # px; see test_klt_parity
+# cornerSubPix, px.  vs cv2 4.13 on a B200: 6 135 points, 100 % bit-equal (scripts/parity_stats.py, profiles/r2_parity_stats.json);
+# the numpy restatement (boxes without cv2) orders two float sums differently: 2e-4.
+SUBPIX_TOL = 1e-5 if R.HAVE_CV2 else 2e-4
+# fb-KLT.  The bar is BIT-EXACT against oracle/image_ref.py::fb_klt_ref, which forms the window sums as exact integers
+# (as the kernel does).  cv2 accumulates the same sums in float SIMD lanes, in an order that depends on the build's vector
+# width: against cv2 4.13 32 589 tracks gave 0 status mismatches, 99.64 % bit-equal, max 5.6e-3 px (profiles/r2_parity_stats.json).
+KLT_CV2_TOL = 1e-2
+KLT_CV2_EQUAL_FRAC = 0.97
+
+
+def _klt_assert(out, st, prev, cur, kps, pri, win, lvl, min_frac=KLT_CV2_EQUAL_FRAC):
+    rp, rs = R.fb_klt_ref(prev, cur, kps, pri, win, lvl)
+    assert np.array_equal(st, rs), np.nonzero(st != rs)[0]
+    assert np.array_equal(out, rp), (np.abs(out - rp).max(), int((out != rp).any(axis=1).sum()))
+    if R.HAVE_CV2 and len(kps):
+        cp, cs = R.fb_klt_cv2(prev, cur, kps, pri, win, lvl)
+        assert np.array_equal(st, cs), np.nonzero(st != cs)[0]
+        d = np.abs(out - cp).max(axis=1)
+        assert d.max() <= KLT_CV2_TOL, (d.max(), int(np.argmax(d)))
+        assert (d == 0).mean() >= min_frac, (d == 0).mean()
 
 
 def _oracle_detect(im, cs, kps, th):
@@ -183,9 +201,8 @@ def _klt_inputs(seed, w, h, n_border=60):
 
 @pytest.mark.parametrize("nbpyrlvl", [0, 1, 3])
 def test_klt_parity(ctx, nbpyrlvl):
-    """fbKltTracking vs the oracle.  Tolerance: status flags identical and tracked positions within
-    1e-3 px, except keypoints the oracle itself marks borderline - none are expected: the integer
-    window sums make the arithmetic reproducible, so in practice positions are bit-equal."""
+    """fbKltTracking vs the oracle: status flags and tracked positions bit-equal to the exact-integer restatement; against
+    cv2 (when importable) statuses identical, positions within KLT_CV2_TOL and >= 97 % bit-equal (see the constants above)."""
     w, h = 640, 480
     prev, cur, flow, kps, is3d, pri = _klt_inputs(7, w, h)
     pp = api.Pyramid(ctx, 1, w, h, 3)
@@ -196,12 +213,7 @@ def test_klt_parity(ctx, nbpyrlvl):
     out = pri.copy()
     st = np.zeros(len(kps), np.uint8)
     ft.fb_klt_tracking(pp, cp, 9, nbpyrlvl, 30.0, 0.5, kps, out, st)
-    ref_fn = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
-    rp, rs = ref_fn(prev, cur, kps, pri, 9, nbpyrlvl)
-    assert np.array_equal(st, rs), np.nonzero(st != rs)[0]
-    d = np.abs(out - rp).max(axis=1)
-    assert d.max() <= KLT_TOL, (d.max(), np.argmax(d))
-    assert (d == 0).mean() > 0.98
+    _klt_assert(out, st, prev, cur, kps, pri, 9, nbpyrlvl)
     assert st.mean() > 0.5
     pp.close()
     cp.close()
@@ -226,15 +238,12 @@ def test_klt_mixed_levels_batched(ctx):
     out = pri.copy()
     st = np.zeros(len(kps), np.uint8)
     api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, lv, 30.0, 0.5, kps, out, st, frame_idx=fidx)
-    ref_fn = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
     o = 0
     for f, d in enumerate(data):
         n = len(d[3])
         for lvl in (1, 3):
             sel = np.nonzero(lv[o:o + n] == lvl)[0]
-            rp, rs = ref_fn(d[0], d[1], d[3][sel], d[5][sel], 9, lvl)
-            assert np.array_equal(st[o:o + n][sel], rs)
-            assert np.abs(out[o:o + n][sel] - rp).max() <= KLT_TOL
+            _klt_assert(out[o:o + n][sel], st[o:o + n][sel], d[0], d[1], d[3][sel], d[5][sel], 9, lvl, min_frac=0.9)
         o += n
     pp.close()
     cp.close()
@@ -281,7 +290,7 @@ def test_against_committed_goldens(ctx):
         st = np.zeros(len(out), np.uint8)
         api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, lvl, 30.0, 0.5, g["klt_kps"], out, st)
         assert np.array_equal(st, g[f"klt_{lvl}_status"]), lvl
-        assert np.abs(out - g[f"klt_{lvl}_tracked"]).max() <= KLT_TOL
+        assert np.abs(out - g[f"klt_{lvl}_tracked"]).max() <= KLT_CV2_TOL      # fixtures were generated with cv2 (scripts/make_golden.py)
     pp.close()
     cp.close()
 
@@ -432,8 +441,7 @@ def test_c4_resolution_1280x720_cell35(ctx):
     out = pri.copy()
     st = np.zeros(len(pts), np.uint8)
     api.FeatureTracker(ctx, 30, 0.01).fb_klt_tracking(pp, cp, 9, 3, 30.0, 0.5, pts, out, st)
-    rp, rs = (R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref)(eq_prev, eq_cur, pts, pri, 9, 3)
-    assert np.array_equal(st, rs) and np.abs(out - rp).max() <= KLT_TOL
+    _klt_assert(out, st, eq_prev, eq_cur, pts, pri, 9, 3)
     for p in (pp, cp, raw):
         p.close()
 
@@ -543,7 +551,6 @@ def test_c4_full_chain_stereo_1280x720(ctx):
     w, h, cs = L.C4_W, L.C4_H, L.C4_CELL
     prev, cur, right, kps, pri, lv, soff, slv = L.make_stereo_unit(4321)
     clahe = R.clahe_cv2 if R.HAVE_CV2 else R.clahe_ref
-    klt = R.fb_klt_cv2 if R.HAVE_CV2 else R.fb_klt_ref
     eq = {k: clahe(v) for k, v in (("prev", prev), ("cur", cur), ("right", right))}
     raw = {k: api.Pyramid(ctx, 1, w, h, 0) for k in eq}
     pyr = {k: api.Pyramid(ctx, 1, w, h, 3) for k in eq}
@@ -560,8 +567,7 @@ def test_c4_full_chain_stereo_1280x720(ctx):
     ft.fb_klt_tracking(pyr["prev"], pyr["cur"], 9, lv, 30.0, 0.5, kps, out, st)
     for lvl in (1, 3):
         idx = np.nonzero(lv == lvl)[0]
-        rp, rs = klt(eq["prev"], eq["cur"], kps[idx], pri[idx], 9, lvl)
-        assert np.array_equal(st[idx], rs) and np.abs(out[idx] - rp).max() <= KLT_TOL
+        _klt_assert(out[idx], st[idx], eq["prev"], eq["cur"], kps[idx], pri[idx], 9, lvl, min_frac=0.9)
     assert st.mean() > 0.7
     fe = api.FeatureExtractor(ctx, nmaxdist=cs, dmaxquality=L.C4_Q)
     ncell = L.C4_NCELL
@@ -592,13 +598,11 @@ def test_c4_full_chain_stereo_1280x720(ctx):
     inside = (out[:, 0] >= 0) & (out[:, 0] < w) & (out[:, 1] >= 0) & (out[:, 1] < h)
     for lvl in (1, 3):
         idx = np.nonzero((slv == lvl) & inside)[0]
-        rp, rs = klt(eq["cur"], eq["right"], out[idx], spri[idx], 9, lvl)
-        assert np.array_equal(sst[idx], rs) and np.abs(sout[idx] - rp).max() <= KLT_TOL
+        _klt_assert(sout[idx], sst[idx], eq["cur"], eq["right"], out[idx], spri[idx], 9, lvl, min_frac=0.9)
     nout = newp.copy()
     nst = np.full(ncell, 7, np.uint8)
     ft.fb_klt_tracking(pyr["cur"], pyr["right"], 9, 3, 30.0, 0.5, newp, nout, nst)
-    rp, rs = klt(eq["cur"], eq["right"], newp[:n], newp[:n].copy(), 9, 3)
-    assert np.array_equal(nst[:n], rs) and np.abs(nout[:n] - rp).max() <= KLT_TOL
+    _klt_assert(nout[:n], nst[:n], eq["cur"], eq["right"], newp[:n], newp[:n].copy(), 9, 3, min_frac=0.9)
     assert not nst[n:].any() and np.array_equal(nout[n:], newp[n:])      # empty slots: status 0, prior untouched
     assert sst.mean() > 0.5 and nst[:n].mean() > 0.5
     for p in list(raw.values()) + list(pyr.values()):
