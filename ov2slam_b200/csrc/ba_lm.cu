@@ -276,6 +276,14 @@ __device__ __forceinline__ double eval_block(const Prob& P, int i, int lm, const
 }
 
 // ------------------------------------------------------------------ Schur elimination (warp / landmark)
+
+// Fire-and-forget fp64 add into GLOBAL memory.  atomicAdd(double*) on a generic pointer compiles to a run-time address-space
+// test + ATOM.E.ADD.F64 (value returned) + a shared-memory CAS loop for the other branch; naming the state space gives one
+// RED.E.ADD.F64 and nothing else.
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
 // schur_eliminator_impl.h:179-308 for a scalar e-block: E'E, E'r, F'F, F'r, E'F per touching keyframe, then
 // S -= (E'F)' (E'E)^-1 (E'F), rhs -= (E'F)' (E'E)^-1 E'r.  The anchor keyframe's F'F / F'r / column norms are summed
 // over the landmark's observations in registers and leave the warp once.
@@ -304,7 +312,7 @@ __device__ __forceinline__ void warp_unlock(int* lock, int lane) {
 template <bool SM>
 __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restrict__ s_slot, double* s_etf, int* s_eslot, double* sJ, int* smeta,
                                                int l, int lane, double radius, int first_iter, double* acc, int n, double& gmax_lm, int* lock) {
-#define ACC(ptr, v) do { if (SM) *(ptr) += (v); else atomicAdd((ptr), (v)); } while (0)
+#define ACC(ptr, v) do { if (SM) *(ptr) += (v); else red_add_f64((ptr), (v)); } while (0)
     const int p0 = P.lm_ptr[l], p1 = P.lm_ptr[l + 1];
     double* const cRhs = acc; double* const cG = acc + n; double* const cCn = acc + 2 * n; double* const cS = acc + 3 * n;
     double cnl = 0.0, ge = 0.0;
@@ -420,7 +428,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
                 for (int u = 0; u < 6; ++u) if (qk[u]) *qp[u] = qo[u] + qv[u];
             } else {
 #pragma unroll
-                for (int u = 0; u < 6; ++u) if (qk[u]) atomicAdd(qp[u], qv[u]);
+                for (int u = 0; u < 6; ++u) if (qk[u]) red_add_f64(qp[u], qv[u]);
             }
             if (fresh) m++;
         }
@@ -473,7 +481,7 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
                 for (int u = 0; u < U; ++u) { if (k0[u]) *q0[u] = o0[u] + v0[u]; if (k1[u]) *q1[u] = o1[u] + v1[u]; }
             } else {
 #pragma unroll
-                for (int u = 0; u < U; ++u) { if (k0[u]) atomicAdd(q0[u], v0[u]); if (k1[u]) atomicAdd(q1[u], v1[u]); }
+                for (int u = 0; u < U; ++u) { if (k0[u]) red_add_f64(q0[u], v0[u]); if (k1[u]) red_add_f64(q1[u], v1[u]); }
             }
         }
     }
@@ -976,7 +984,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     if (tid == 0) {                               // one atomic per CTA: they all hit one address
                         double a = 0.0;
                         for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][0];
-                        if (a != 0.0) atomicAdd(scal + SC_COST, a);
+                        if (a != 0.0) red_add_f64(scal + SC_COST, a);
                     }
                 }
                 bar.sync();
@@ -998,7 +1006,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                         double v = 0.0;
 #pragma unroll
                         for (int w_ = 0; w_ < WARPS; ++w_) v += all[(size_t)w_ * live_s + e];
-                        if (v != 0.0) atomicAdd(P.acc + e, v);
+                        if (v != 0.0) red_add_f64(P.acc + e, v);
                     }
                 } else if (P.schur_smem) {
                     double* sS = s_work + P.smem_sacc_off;
@@ -1012,7 +1020,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     __syncthreads();
                     for (int e = tid; e < live_s; e += THREADS) {
                         const double v = sS[e];
-                        if (v != 0.0) atomicAdd(P.acc + e, v);
+                        if (v != 0.0) red_add_f64(P.acc + e, v);
                     }
                 } else {
                     double* acc = P.acc + (size_t)(bid % P.ncopy) * blk;
@@ -1120,7 +1128,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     if (tid < 4) {
                         double a = 0.0;
                         for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][tid];
-                        if (a != 0.0) atomicAdd(scal + SC_CAND_COST + tid, a);
+                        if (a != 0.0) red_add_f64(scal + SC_CAND_COST + tid, a);
                     }
                     // clear for the next iteration: accumulation copies and the other parity's scalars
                     for (size_t i = gtid; i < (size_t)P.ncopy * blk; i += gthreads) P.acc[i] = 0.0;
@@ -1196,7 +1204,7 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 if (tid < 3) {                                   // one atomic per CTA and counter
                     double a = 0.0;
                     for (int w_ = 0; w_ < WARPS; ++w_) a += s_red[w_][tid];
-                    if (a != 0.0) atomicAdd(cnt + tid, a);
+                    if (a != 0.0) red_add_f64(cnt + tid, a);
                 }
                 // the stop request lives in mapped HOST memory: ONE thread of the group reads it (every thread of every CTA
                 // polling it over PCIe cost 7 us per CTA of the group) and publishes it next to the counters

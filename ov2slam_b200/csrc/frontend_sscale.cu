@@ -43,33 +43,31 @@ __global__ void __launch_bounds__(256) ss_response_kernel(RespArgs A) {
     const int rw = cs + 2;
     uint8_t* raw = smem;                                          // (cs+2)^2: cell + 1-px halo from the PARENT image
     uint8_t* bl = raw + sscale::raw_bytes(cs);                    // cs^2 blurred
-    float* cxx = reinterpret_cast<float*>(bl + sscale::blur_bytes(cs));
-    float* cxy = cxx + cs * cs;
-    float* cyy = cxy + cs * cs;
+    double* cov = reinterpret_cast<double*>(bl + sscale::blur_bytes(cs));   // Sobel products [pixel][xx, xy, yy]
     const uint8_t* img = A.img + A.fstride * (A.first + fr);
-    for (int i = threadIdx.x; i < rw * rw; i += blockDim.x) {
-        const int yy = i / rw, xx = i - yy * rw;
-        const int gy = sscale::refl(y0 - 1 + yy, A.h), gx = sscale::refl(x0 - 1 + xx, A.w);
-        raw[i] = __ldg(img + (size_t)gy * A.pitch + gx);
+    {   // staging: a warp per tile row, a lane per column - the reflected column is formed once per lane, the row once per warp
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+        for (int xx = lane; xx < rw; xx += 32) {
+            const int gx = sscale::refl(x0 - 1 + xx, A.w);
+            for (int yy = warp; yy < rw; yy += nwarp) {
+                const int gy = sscale::refl(y0 - 1 + yy, A.h);
+                raw[yy * rw + xx] = __ldg(img + (size_t)gy * A.pitch + gx);
+            }
+        }
     }
     __syncthreads();
     sscale::phase_blur(threadIdx.x, blockDim.x, raw, bl, cs);
     __syncthreads();
-    sscale::phase_cov(threadIdx.x, blockDim.x, bl, cxx, cxy, cyy, cs);
+    sscale::phase_cov(threadIdx.x, blockDim.x, bl, cov, cs);
     __syncthreads();
     float* out = A.resp + ((size_t)fr * (A.nwc * A.nhc) + cell) * (size_t)(cs * cs);
-    sscale::phase_response(threadIdx.x, blockDim.x, cxx, cxy, cyy, out, cs);
-    // first maximum (row-major) of the unmasked response: lets the sweep skip its first arg-max scan whenever that pixel
-    // is not masked (the usual case)
-    __syncthreads();
-    __shared__ float s_v[8];
-    __shared__ int s_i[8];
+    // first maximum (row-major) of the unmasked response, tracked while the responses are written: lets the sweep skip its
+    // first arg-max scan whenever that pixel is not masked (the usual case)
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < cs * cs; i += blockDim.x) {
-        const float v = out[i];                                   // written by this CTA just above
-        if (v > bv) { bv = v; bi = i; }
-    }
+    sscale::phase_response(threadIdx.x, blockDim.x, cov, out, cs, bv, bi);
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(FULL, bv, o);

@@ -173,18 +173,20 @@ def test_single_scale_cell_math_matches_oracle(tmp_path):
     src.write_text(r'''
 #include "%s/ov2slam_b200/csrc/sscale_math.cuh"
 #include <vector>
-extern "C" void cell_response(const unsigned char* raw, int cs, float* out) {
+extern "C" void cell_response(const unsigned char* raw, int cs, float* out, int* best) {
     std::vector<unsigned char> bl(cs * cs);
-    std::vector<float> cxx(cs * cs), cxy(cs * cs), cyy(cs * cs);
+    std::vector<double> cov(3 * cs * cs);
     const int nt = 256;
     for (int t = 0; t < nt; ++t) sscale::phase_blur(t, nt, raw, bl.data(), cs);
-    for (int t = 0; t < nt; ++t) sscale::phase_cov(t, nt, bl.data(), cxx.data(), cxy.data(), cyy.data(), cs);
-    for (int t = 0; t < nt; ++t) sscale::phase_response(t, nt, cxx.data(), cxy.data(), cyy.data(), out, cs);
+    for (int t = 0; t < nt; ++t) sscale::phase_cov(t, nt, bl.data(), cov.data(), cs);
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int t = 0; t < nt; ++t) sscale::phase_response(t, nt, cov.data(), out, cs, bv, bi);
+    *best = bi;
 }''' % ROOT)
     so = tmp_path / "libs.so"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(so), str(src)])
     lib = ctypes.CDLL(str(so))
-    lib.cell_response.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.cell_response.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     rng = np.random.default_rng(21)
     for it in range(60):
         cs = int(rng.choice([50, 35, 16, 20, 33, 64, 8]))
@@ -192,9 +194,11 @@ extern "C" void cell_response(const unsigned char* raw, int cs, float* out) {
         if it % 2:
             raw = np.clip(raw.astype(np.int32) // 8 + 100, 0, 255).astype(np.uint8)    # low contrast: many exact ties / zeros
         out = np.empty((cs, cs), np.float32)
-        lib.cell_response(raw.ctypes.data, cs, out.ctypes.data)
+        best = np.zeros(1, np.int32)
+        lib.cell_response(raw.ctypes.data, cs, out.ctypes.data, best.ctypes.data)
         ref = R.min_eigen_ref(R.blur3_cell_ref(raw, 1, 1, cs))
         assert np.array_equal(out.view(np.int32), ref.view(np.int32)), (it, cs, int((out != ref).sum()))
+        assert int(best[0]) == int(np.argmax(ref))          # first maximum in row-major order (np.argmax returns the first)
 
 
 def test_pnp_solver_code_matches_oracle(tmp_path):
