@@ -46,45 +46,54 @@ SS_HD size_t smem_bytes(int cs) { return raw_bytes(cs) + blur_bytes(cs) + 3 * si
 // index division (the first version spent 440 thread-instructions per pixel, mostly integer address arithmetic).
 constexpr int SEG = 5;    // 35 x 7 = 245 items for the 256 threads of a 35-px cell
 
+#if defined(__CUDA_ARCH__)
+#define SS_UNROLL _Pragma("unroll")
+#else
+#define SS_UNROLL
+#endif
+
 // phase 1: raw = (cs+2)^2 tile (cell + 1-px halo from the parent image) -> bl = blurred cell.
 // S / 16 rounded half-to-even in the first 16*floor(cs/16) columns, half-up in the tail.
+// The row loops of all phases run a FIXED SEG iterations (stores predicated on yy < cs): fully unrolled, the sliding
+// window is register renaming and the row pointers are increments.
 SS_HD void phase_blur(int tid, int nt, const uint8_t* raw, uint8_t* bl, int cs) {
     const int rw = cs + 2, nvec16 = (cs >> 4) << 4;
     const int nseg = (cs + SEG - 1) / SEG;
     for (int item = tid; item < cs * nseg; item += nt) {
         const int seg = item / cs, xx = item - seg * cs;
         const int y0 = seg * SEG;
-        int y1 = y0 + SEG;
-        if (y1 > cs) y1 = cs;
         const uint8_t* p = raw + y0 * rw + xx;                   // raw row y0 = the row above output row y0
+        uint8_t* o = bl + y0 * cs + xx;
         int h0 = (int)p[0] + 2 * (int)p[1] + (int)p[2];
-        p += rw;
-        int h1 = (int)p[0] + 2 * (int)p[1] + (int)p[2];
+        int h1 = (int)p[rw] + 2 * (int)p[rw + 1] + (int)p[rw + 2];
         const bool even = xx < nvec16;
-        for (int yy = y0; yy < y1; ++yy) {
-            p += rw;
-            const int h2 = (int)p[0] + 2 * (int)p[1] + (int)p[2];
-            const int S = h0 + 2 * h1 + h2;
-            int v;
-            if (even) {
-                v = S >> 4;
-                const int rem = S & 15;
-                if (rem > 8 || (rem == 8 && (v & 1))) v++;
-            } else {
-                v = (S + 8) >> 4;
+        SS_UNROLL
+        for (int k = 0; k < SEG; ++k) {
+            if (y0 + k < cs) {
+                const uint8_t* q = p + (k + 2) * rw;
+                const int h2 = (int)q[0] + 2 * (int)q[1] + (int)q[2];
+                const int S = h0 + 2 * h1 + h2;
+                int v;
+                if (even) {
+                    v = S >> 4;
+                    const int rem = S & 15;
+                    if (rem > 8 || (rem == 8 && (v & 1))) v++;
+                } else {
+                    v = (S + 8) >> 4;
+                }
+                o[k * cs] = (uint8_t)v;
+                h0 = h1; h1 = h2;
             }
-            bl[yy * cs + xx] = (uint8_t)v;
-            h0 = h1; h1 = h2;
         }
     }
 }
 
 // Sobel row quantities of blurred row `row` at column x (xm / xp = reflected neighbours): d = right - left (exact), q = the
 // [k1 k2 k1] row filter - vector form (FMAs) in the first 32*floor(cs/32) columns, scalar form in the tail.
-SS_HD void cov_row(const uint8_t* row, int xm, int xx, int xp, bool vec, float& d, float& q) {
+SS_HD void cov_row(const uint8_t* row, int om, int op, bool vec, float& d, float& q) {
     const float k1 = 1.0f / 3060.0f, k2 = 2.0f / 3060.0f;       // float32(s), float32(2 s) (= 2 k1 exactly)
-    const int a = row[xm], c = row[xp];
-    const float A = (float)a, B = (float)row[xx], C = (float)c;
+    const int a = row[om], c = row[op];
+    const float A = (float)a, B = (float)row[0], C = (float)c;
     d = (float)(c - a);
     q = vec ? SS_FMA(k1, C, SS_FMA(k2, B, SS_MUL(k1, A))) : SS_ADD(SS_ADD(SS_MUL(k1, A), SS_MUL(k2, B)), SS_MUL(k1, C));
 }
@@ -98,25 +107,34 @@ SS_HD void phase_cov(int tid, int nt, const uint8_t* bl, double* cov, int cs) {
     for (int item = tid; item < cs * nseg; item += nt) {
         const int seg = item / cs, xx = item - seg * cs;
         const int y0 = seg * SEG;
-        int y1 = y0 + SEG;
-        if (y1 > cs) y1 = cs;
-        const int xm = refl(xx - 1, cs), xp = refl(xx + 1, cs);
+        const int om = refl(xx - 1, cs) - xx, op = refl(xx + 1, cs) - xx;
         const bool vec = xx < nvec32;
+        const uint8_t* r0 = bl + y0 * cs + xx;                   // current row, at column xx
         float dm, qm, d0, q0, dp, qp;
-        cov_row(bl + refl(y0 - 1, cs) * cs, xm, xx, xp, vec, dm, qm);
-        cov_row(bl + y0 * cs, xm, xx, xp, vec, d0, q0);
-        for (int yy = y0; yy < y1; ++yy) {
-            cov_row(bl + refl(yy + 1, cs) * cs, xm, xx, xp, vec, dp, qp);
-            // Dx: row [-1 0 1] (exact), column [k1 k2 k1] evaluated as fma(top + bottom, k1, mid * k2); Dy: column [-1 0 1]
-            const float dx = SS_FMA(SS_ADD(dm, dp), k1, SS_MUL(d0, k2));
-            const float dy = SS_SUB(qp, qm);
-            double* o = cov + 3 * (size_t)(yy * cs + xx);
-            o[0] = (double)SS_MUL(dx, dx);
-            o[1] = (double)SS_MUL(dx, dy);
-            o[2] = (double)SS_MUL(dy, dy);
-            dm = d0; qm = q0; d0 = dp; q0 = qp;
+        cov_row(y0 == 0 ? r0 + cs : r0 - cs, om, op, vec, dm, qm);     // REFLECT_101 inside the cell: row -1 = row 1
+        cov_row(r0, om, op, vec, d0, q0);
+        double* o = cov + 3 * (size_t)(y0 * cs + xx);
+        SS_UNROLL
+        for (int k = 0; k < SEG; ++k) {
+            if (y0 + k < cs) {
+                const uint8_t* rc = r0 + k * cs;
+                cov_row(y0 + k + 1 < cs ? rc + cs : rc - cs, om, op, vec, dp, qp);     // row cs = row cs - 2
+                // Dx: row [-1 0 1] (exact), column [k1 k2 k1] evaluated as fma(top + bottom, k1, mid * k2); Dy: column [-1 0 1]
+                const float dx = SS_FMA(SS_ADD(dm, dp), k1, SS_MUL(d0, k2));
+                const float dy = SS_SUB(qp, qm);
+                o[3 * k * cs + 0] = (double)SS_MUL(dx, dx);
+                o[3 * k * cs + 1] = (double)SS_MUL(dx, dy);
+                o[3 * k * cs + 2] = (double)SS_MUL(dy, dy);
+                dm = d0; qm = q0; d0 = dp; q0 = qp;
+            }
         }
     }
+}
+
+SS_HD void box_row(const double* r, int om, int op, double* a) {
+    a[0] = r[om] + r[0] + r[op];
+    a[1] = r[om + 1] + r[1] + r[op + 1];
+    a[2] = r[om + 2] + r[2] + r[op + 2];
 }
 
 // phase 3: 3x3 sums (exact in double whatever the order: nine float32 products spanning < 2^46; one rounding) and the
@@ -127,39 +145,30 @@ SS_HD void phase_response(int tid, int nt, const double* cov, float* out, int cs
     for (int item = tid; item < cs * nseg; item += nt) {
         const int seg = item / cs, xx = item - seg * cs;
         const int y0 = seg * SEG;
-        int y1 = y0 + SEG;
-        if (y1 > cs) y1 = cs;
         const int om = 3 * (refl(xx - 1, cs) - xx), op = 3 * (refl(xx + 1, cs) - xx);   // neighbour offsets (doubles)
+        const int rs = 3 * cs;                                                           // row stride (doubles)
+        const double* r0 = cov + 3 * (size_t)(y0 * cs + xx);
         double a0[3], a1[3], a2[3];                       // horizontal sums of rows y-1, y, y+1 for the three planes
-        {
-            const double* ra = cov + 3 * (size_t)(refl(y0 - 1, cs) * cs + xx);
-            const double* rb = cov + 3 * (size_t)(y0 * cs + xx);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int k = 0; k < 3; ++k) {
-                a0[k] = ra[om + k] + ra[k] + ra[op + k];
-                a1[k] = rb[om + k] + rb[k] + rb[op + k];
+        box_row(y0 == 0 ? r0 + rs : r0 - rs, om, op, a0);
+        box_row(r0, om, op, a1);
+        SS_UNROLL
+        for (int k = 0; k < SEG; ++k) {
+            if (y0 + k < cs) {
+                const double* rc = r0 + k * rs;
+                box_row(y0 + k + 1 < cs ? rc + rs : rc - rs, om, op, a2);
+                const double sxx = a0[0] + a1[0] + a2[0], sxy = a0[1] + a1[1] + a2[1], syy = a0[2] + a1[2] + a2[2];
+                const float fa = SS_MUL(SS_D2F(sxx), 0.5f);
+                const float fb = SS_D2F(sxy);
+                const float fc = SS_MUL(SS_D2F(syy), 0.5f);
+                const float t = SS_SUB(fa, fc);
+                const float q = SS_ADD(SS_MUL(t, t), SS_MUL(fb, fb));
+                const float v = SS_SUB(SS_ADD(fa, fc), SS_SQRT(q));
+                const int i = (y0 + k) * cs + xx;
+                out[i] = v;
+                if (v > best_v || (v == best_v && i < best_i)) { best_v = v; best_i = i; }
+                a0[0] = a1[0]; a0[1] = a1[1]; a0[2] = a1[2];
+                a1[0] = a2[0]; a1[1] = a2[1]; a1[2] = a2[2];
             }
-        }
-        for (int yy = y0; yy < y1; ++yy) {
-            const double* rc = cov + 3 * (size_t)(refl(yy + 1, cs) * cs + xx);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int k = 0; k < 3; ++k) a2[k] = rc[om + k] + rc[k] + rc[op + k];
-            const double sxx = a0[0] + a1[0] + a2[0], sxy = a0[1] + a1[1] + a2[1], syy = a0[2] + a1[2] + a2[2];
-            const float fa = SS_MUL(SS_D2F(sxx), 0.5f);
-            const float fb = SS_D2F(sxy);
-            const float fc = SS_MUL(SS_D2F(syy), 0.5f);
-            const float t = SS_SUB(fa, fc);
-            const float q = SS_ADD(SS_MUL(t, t), SS_MUL(fb, fb));
-            const float v = SS_SUB(SS_ADD(fa, fc), SS_SQRT(q));
-            const int i = yy * cs + xx;
-            out[i] = v;
-            if (v > best_v || (v == best_v && i < best_i)) { best_v = v; best_i = i; }
-            a0[0] = a1[0]; a0[1] = a1[1]; a0[2] = a1[2];
-            a1[0] = a2[0]; a1[1] = a2[1]; a1[2] = a2[2];
         }
     }
 }
