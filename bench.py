@@ -618,7 +618,7 @@ def gpu_arm(args):
             legs["c4"] = {"error": (str(e) + " | " + traceback.format_exc().splitlines()[-2])[:400]}
     if not args.no_c5:
         try:
-            legs["c5"] = L.c5_leg(torch, api, dist, ctx, rank, world, args, _peaks())
+            legs["c5"] = L.c5_leg(torch, api, dist, ctx, rank, world, args, _peaks(), _ncu_traffic)
         except Exception as e:
             import traceback
             legs["c5"] = {"error": (str(e) + " | " + traceback.format_exc().splitlines()[-2])[:400]}

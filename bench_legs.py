@@ -419,7 +419,7 @@ def ba_bytes_per_iteration(nobs: int, npts: int) -> float:
     return 67.0 * nobs + 64.0 * npts
 
 
-def c5_leg(torch, api, dist, ctx, rank, world, args, peaks):
+def c5_leg(torch, api, dist, ctx, rank, world, args, peaks, ncu_traffic=None):
     """1 GPU: ov2_localba_solve on the C5 window (host buffers in/out).  N GPUs: landmarks (with their observations)
     split N ways, reduced camera system summed over NVLink every LM iteration (ov2_localba_solve_sharded)."""
     from ov2slam_b200 import synth
@@ -470,7 +470,8 @@ def c5_leg(torch, api, dist, ctx, rank, world, args, peaks):
     peak, peak_src = peaks
     bytes_per_solve = its * ba_bytes_per_iteration(nobs, npts)
     out["roofline"] = {"bound": "hbm", "kernel": "localBA solve (all kernels of one two-stage solve)", "achieved": bytes_per_solve / dt / 1e9,
-                       "peak": peak * world, "unit": "GB/s", "frac": bytes_per_solve / dt / 1e9 / (peak * world), "traffic": None,
+                       "peak": peak * world, "unit": "GB/s", "frac": bytes_per_solve / dt / 1e9 / (peak * world),
+                       "traffic": ncu_traffic("c5:ba_lm_kernel") if (ncu_traffic and world == 1 and not args.c5_small) else None,
                        "peak_source": peak_src, "algorithmic_bytes_per_solve": bytes_per_solve,
                        "note": "67 N_obs + 64 N_pts bytes per LM iteration (SURVEY 8d) x iterations run; includes the H2D of the window "
                                "and the D2H of the states (host buffers in/out)"}

@@ -505,29 +505,16 @@ template <int QMAX>
 __device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fail) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int sub = tid & 3, r0 = tid >> 2, rows_per_pass = nt >> 2;
-    // Look-ahead: the NEXT pivot A[j+1][j+1] - (A[j+1][j] / p) A[j][j+1] and its reciprocal are formed by every thread at the
-    // start of step j, from three entries step j does not write (row j, column j, and the diagonal entry itself, which the
-    // bulk update skips and thread 0 stores one step later), so the dependent chain pivot -> reciprocal -> next pivot
-    // (~370 cycles of fp64 latency) overlaps the bulk update and the barrier instead of preceding them.
-    double p = sA[0], ip = 0.0;
-    if (p > 0.0 && isfinite(p)) {
+    for (int j = 0; j < n; ++j) {
+        const double p = sA[j * PIT + j];
+        if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) *s_fail = 1; break; }   // uniform: every thread reads the same pivot
+        // 1 / p sits on the critical path of every pivot (B200: ~50 cycles per DEPENDENT fp64 operation - the 48-pivot loop
+        // is latency bound on this chain): MUFU double-precision seed (2^-23) + two Newton steps, no float round trip
+        double ip;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip) : "d"(p));
         ip = fma(ip, fma(-p, ip, 1.0), ip);
         ip = fma(ip, fma(-p, ip, 1.0), ip);
-    }
-    for (int j = 0; j < n; ++j) {
-        if (!(p > 0.0) || !isfinite(p)) { if (tid == 0) *s_fail = 1; break; }   // uniform: every thread holds the same pivot
         const double* rowj = sA + j * PIT;
-        double p_next = 1.0, ip_next = 1.0;
-        if (j + 1 < n) {
-            const double f1 = sA[(j + 1) * PIT + j] * ip;
-            p_next = fma(-f1, rowj[j + 1], sA[(j + 1) * PIT + j + 1]);
-            // 1 / p: MUFU double-precision seed (2^-23) + two Newton steps, no float round trip
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip_next) : "d"(p_next));
-            ip_next = fma(ip_next, fma(-p_next, ip_next, 1.0), ip_next);
-            ip_next = fma(ip_next, fma(-p_next, ip_next, 1.0), ip_next);
-        }
-        if (tid == 0 && j > 0) sA[j * PIT + j] = p;          // the diagonal entry the previous step's bulk update skipped
         const int c0 = j + 1 + sub;
         const int nq = (n - j + 3 - sub) >> 2;              // columns c = c0 + 4 q <= n
         double pj[QMAX];
@@ -537,18 +524,16 @@ __device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fai
             if (r == j) continue;
             double* rowr = sA + r * PIT;
             const double f = rowr[j] * ip;
-            const bool next_diag = sub == 0 && r == j + 1;  // entry (j+1, j+1): carried in registers (p_next)
             double a[QMAX];
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) a[q] = q < nq ? rowr[c0 + 4 * q] : 0.0;
 #pragma unroll
-            for (int q = 0; q < QMAX; ++q) a[q] = fma(-f, pj[q], a[q]);
+            for (int q = 0; q < QMAX; ++q) a[q] -= f * pj[q];
 #pragma unroll
             for (int q = 0; q < QMAX; ++q)
-                if (q < nq && !(q == 0 && next_diag)) rowr[c0 + 4 * q] = a[q];
+                if (q < nq) rowr[c0 + 4 * q] = a[q];
         }
         __syncthreads();
-        p = p_next; ip = ip_next;
     }
 }
 
@@ -665,13 +650,14 @@ __device__ void reduced_solve_blocked_group(const Prob& P, double* T, int n, dou
                     is = fma(0.5 * is, fma(-d * is, is, 1.0), is);
                     is = fma(0.5 * is, fma(-d * is, is, 1.0), is);
                     const double ujc = lane >= j ? a[j] * is : 0.0;
-                    sU[j][lane] = ujc;                     // row j of U: final value (read by the panel solve after the block barrier)
+                    sU[j][lane] = ujc;                     // row j of U: final value, and the broadcast source below
                     if (lane == j) s_idiag[j] = is;
-                    // U[j][r] reaches the other lanes by shuffle, not through shared memory: no warp barrier inside the
-                    // 32-pivot chain, so the compiler interleaves this bulk update with the next pivot's rsqrt chain
-                    // (row j+1 first: it feeds the next pivot)
+                    __syncwarp();
+                    // (measured alternatives, both slower: broadcasting U[j][r] by shuffle - no warp barrier in the chain, but
+                    // 62 SHFL per pivot: +40 %; for the Gauss-Jordan above, forming the next pivot's reciprocal one step ahead,
+                    // redundantly in every thread or in a dedicated warp: +10 % - the pivot chain is not what bounds a step)
 #pragma unroll
-                    for (int r = j + 1; r < CH_NB; ++r) a[r] = fma(-__shfl_sync(FULL, ujc, r), ujc, a[r]);   // entries below the diagonal (r > lane) are never read
+                    for (int r = j + 1; r < CH_NB; ++r) a[r] = fma(-sU[j][r], ujc, a[r]);   // entries below the diagonal (r > lane) are never read
                 }
                 if (bad && lane == 0) { s_bad = 1; scal[SC_CHOL_FAIL] = 1.0; }
             }

@@ -9,7 +9,7 @@
 //   * per tile 256-bin histogram, clip = max(int(clip * area / 256), 1), excess redistributed
 //     (uniform batch + one each to bins 0, step, 2 step, ...), LUT = rint(cumsum * (255 / area))
 //   * per pixel float32 bilinear blend of the four neighbouring tile LUTs, rint.
-// clahe_lut_kernel: one CTA per (tile, frame), per-warp shared-memory histograms from 32-bit loads.
+// clahe_lut_kernel: one warp per (tile, frame), one shared-memory histogram per warp from 32-bit loads.
 // clahe_apply_kernel: one CTA per (band of rows between two tile-centre lines, frame), its two LUT rows staged in
 // shared memory, streaming pass with 32-bit loads / stores (reads W*H, writes W*H per frame).
 #include "ov2_common.cuh"
@@ -31,75 +31,107 @@ __device__ __forceinline__ int refl(int i, int n) {
     return i;
 }
 
-// Tile histogram -> clipped, redistributed -> LUT.  One CTA per (tile, frame).  Interior tiles whose rows are 4-byte
-// addressable are read as 32-bit words (4 pixels per load); tiles that reach into the reflected extension, or unaligned
-// images, take the byte path.  Per-warp sub-histograms (8 x 256 counters) keep the shared-memory atomics of different
-// warps on different banks / addresses; they are summed when the clip is applied.
-__global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
-    __shared__ int whist[8][256];
-    __shared__ int hist[256];
-    __shared__ int s_excess;
-    const int tile = blockIdx.x, fr = blockIdx.y;
+// Tile histogram -> clipped, redistributed -> LUT.  One WARP per (tile, frame), eight tiles per CTA, no block barrier:
+// with 52 x 52-pixel tiles (1280 x 720, 25 x 14 tiles) a CTA per tile spent more instructions zeroing, merging and
+// scanning eight sub-histograms (and waiting at five barriers) than counting.  A warp keeps ONE 256-bin histogram in shared
+// memory, counts 4 pixels per 32-bit load (interior tiles whose rows are 4-byte addressable; tiles that reach into the
+// reflected extension, or unaligned images, take the byte path), then every lane owns 8 consecutive bins for the clip,
+// the redistribution (uniform batch + one each to bins 0, step, 2 step, ...) and the prefix sum (8 local + one warp scan).
+constexpr int LUT_WARPS = 8;
+__global__ void __launch_bounds__(LUT_WARPS * 32) clahe_lut_kernel(ClaheArgs A) {
+    __shared__ __align__(16) int whist[LUT_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * LUT_WARPS + warp, fr = blockIdx.y;
+    if (tile >= A.tx * A.ty) return;
     const int tyi = tile / A.tx, txi = tile - tyi * A.tx;
     const uint8_t* src = A.src + A.sfstride * fr;
-    const int warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < 8 * 256; k += 256) (&whist[0][0])[k] = 0;
-    if (threadIdx.x == 0) s_excess = 0;
-    __syncthreads();
-    const int x0 = txi * A.tw, y0 = tyi * A.th, area = A.tw * A.th;
+    int* hist = whist[warp];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hist[lane + 32 * k] = 0;
+    __syncwarp();
+    const int x0 = txi * A.tw, y0 = tyi * A.th;
     const bool words = x0 + A.tw <= A.w && y0 + A.th <= A.h && (A.tw & 3) == 0 && (x0 & 3) == 0 && (A.spitch & 3) == 0 &&
                        ((reinterpret_cast<uintptr_t>(src)) & 3) == 0;
     if (words) {
         const int wpr = A.tw >> 2, nw = wpr * A.th;
-        for (int i = threadIdx.x; i < nw; i += 256) {
-            const int yy = i / wpr, xw = i - yy * wpr;
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(y0 + yy) * A.spitch + x0) + xw);
-            atomicAdd(&whist[warp][v & 255u], 1);
-            atomicAdd(&whist[warp][(v >> 8) & 255u], 1);
-            atomicAdd(&whist[warp][(v >> 16) & 255u], 1);
-            atomicAdd(&whist[warp][v >> 24], 1);
+        const int dy = 32 / wpr, dx = 32 - dy * wpr;
+        int yy = lane / wpr, xw = lane - yy * wpr;
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(src + (size_t)y0 * A.spitch + x0);
+        const int wpitch = A.spitch >> 2;
+        for (int i = lane; i < nw; i += 128) {               // four loads in flight per lane
+            uint32_t v[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ok[u] = i + 32 * u < nw;
+                v[u] = ok[u] ? __ldg(base + (size_t)yy * wpitch + xw) : 0u;
+                xw += dx; yy += dy;
+                if (xw >= wpr) { xw -= wpr; yy++; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) {
+                    atomicAdd(&hist[v[u] & 255u], 1);
+                    atomicAdd(&hist[(v[u] >> 8) & 255u], 1);
+                    atomicAdd(&hist[(v[u] >> 16) & 255u], 1);
+                    atomicAdd(&hist[v[u] >> 24], 1);
+                }
         }
     } else {
-        for (int i = threadIdx.x; i < area; i += 256) {
-            int yy = i / A.tw, xx = i - yy * A.tw;
-            int x = refl(x0 + xx, A.w), y = refl(y0 + yy, A.h);
-            atomicAdd(&whist[warp][__ldg(src + (size_t)y * A.spitch + x)], 1);
+        const int area = A.tw * A.th;
+        const int dy = 32 / A.tw, dx = 32 - dy * A.tw;
+        int yy = lane / A.tw, xx = lane - yy * A.tw;
+        for (int i = lane; i < area; i += 32) {
+            const int x = refl(x0 + xx, A.w), y = refl(y0 + yy, A.h);
+            atomicAdd(&hist[__ldg(src + (size_t)y * A.spitch + x)], 1);
+            xx += dx; yy += dy;
+            if (xx >= A.tw) { xx -= A.tw; yy++; }
         }
     }
-    __syncthreads();
-    int v = 0;
+    __syncwarp();
+    // lane owns bins 8 lane .. 8 lane + 7
+    int v[8];
+    {
+        const int4 a = *reinterpret_cast<const int4*>(hist + 8 * lane), b = *reinterpret_cast<const int4*>(hist + 8 * lane + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    int excess = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v += whist[k][threadIdx.x];
-    if (v > A.clip) { atomicAdd(&s_excess, v - A.clip); v = A.clip; }
-    __syncthreads();
-    const int clipped = s_excess;
-    const int batch = clipped / 256;
-    int residual = clipped - batch * 256;
-    v += batch;
+    for (int k = 0; k < 8; ++k)
+        if (v[k] > A.clip) { excess += v[k] - A.clip; v[k] = A.clip; }
+    const int clipped = __reduce_add_sync(0xffffffffu, excess);
+    const int batch = clipped >> 8;
+    const int residual = clipped - (batch << 8);
     if (residual != 0) {
         const int step = max(256 / residual, 1);
-        // bins 0, step, 2*step, ... (the first `residual` of them, while index < 256)
-        if (threadIdx.x % step == 0 && threadIdx.x / step < residual) v++;
-    }
-    hist[threadIdx.x] = v;
-    __syncthreads();
-    // inclusive prefix sum (256 entries) by warp 0: 8 values per lane + warp scan
-    __shared__ int cum[256];
-    if (threadIdx.x < 32) {
-        int loc[8], s = 0;
-        for (int k = 0; k < 8; ++k) { s += hist[threadIdx.x * 8 + k]; loc[k] = s; }
-        int incl = s;
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)threadIdx.x >= o) incl += t;
+        const unsigned inv = (65536u + (unsigned)step - 1u) / (unsigned)step;    // floor(b / step) = (b inv) >> 16 for b < 256, step <= 256
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned b = 8u * lane + k, q = (b * inv) >> 16;
+            // bins 0, step, 2*step, ... (the first `residual` of them, while index < 256)
+            if (b - q * step == 0u && (int)q < residual) v[k]++;
         }
-        const int base = incl - s;
-        for (int k = 0; k < 8; ++k) cum[threadIdx.x * 8 + k] = base + loc[k];
     }
-    __syncthreads();
-    int q = __float2int_rn((float)cum[threadIdx.x] * A.lut_scale);
-    q = q < 0 ? 0 : (q > 255 ? 255 : q);
-    A.lut[(((size_t)fr * A.ty + tyi) * A.tx + txi) * 256 + threadIdx.x] = (uint8_t)q;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] += batch; sum += v[k]; v[k] = sum; }      // local inclusive prefix
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int basec = incl - sum;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int q = __float2int_rn((float)(basec + v[k]) * A.lut_scale);
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        if (k < 4) lo |= (uint32_t)q << (8 * k);
+        else hi |= (uint32_t)q << (8 * (k - 4));
+    }
+    uint8_t* out = A.lut + (((size_t)fr * A.ty + tyi) * A.tx + txi) * 256 + 8 * lane;
+    *reinterpret_cast<uint2*>(out) = make_uint2(lo, hi);
 }
 
 // Interpolation pass.  All rows between two tile-centre lines use the same two LUT rows (ty1, ty2): one CTA takes such a
@@ -208,7 +240,7 @@ static ov2_status clahe_device(ov2_ctx* ctx, const uint8_t* src, int spitch, lon
     ov2_status st;
     if ((st = ov2_scratch(ctx, (size_t)count * tiles_x * tiles_y * 256, &o)) != OV2_OK) return st;
     A.lut = (uint8_t*)o;
-    OV2_LAUNCH(ctx, "clahe_lut_kernel", clahe_lut_kernel<<<dim3(tiles_x * tiles_y, count), 256, 0, ctx->stream>>>(A));
+    OV2_LAUNCH(ctx, "clahe_lut_kernel", clahe_lut_kernel<<<dim3((tiles_x * tiles_y + LUT_WARPS - 1) / LUT_WARPS, count), LUT_WARPS * 32, 0, ctx->stream>>>(A));
     if (tiles_x > APPLY_MAX_TX) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_clahe: more than 64 tile columns");
     {
         const size_t smem = (size_t)2 * tiles_x * 256;
