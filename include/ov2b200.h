@@ -204,6 +204,17 @@ OV2_API ov2_status ov2_pnp_solve(ov2_ctx* ctx, int nprob, const int32_t* offsets
 OV2_API ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, const int32_t* frame_idx, int first_frame, int per_frame,
                         const float* pts, uint8_t* desc32_out, uint8_t* valid_out);
 
+/* Descriptor selection for ov2_describe on this context (the reference selects it at compile time,
+ * /root/reference/CMakeLists.txt:12,35-39 and src/feature_extractor.cpp:69-70,242-246):
+ *   OV2_DESC_ORB_FALLBACK (default, pairs = NULL): the non-contrib branch described above.
+ *   OV2_DESC_BRIEF32: cv::xfeatures2d::BriefDescriptorExtractor::create() (32 bytes, no orientation):
+ *     256 tests SMOOTHED(y0, x0) < SMOOTHED(y1, x1) of 9 x 9 box sums around (int)(pt + 0.5), first test of a
+ *     byte in bit 7, border 28 px.  `pairs` = int8[256][4] = (y0, x0, y1, x1) in the order of opencv_contrib's
+ *     modules/xfeatures2d/src/generated_32.i (that table is not redistributed here; |offset| <= 24 is checked). */
+#define OV2_DESC_ORB_FALLBACK 0
+#define OV2_DESC_BRIEF32 1
+OV2_API ov2_status ov2_describe_config(ov2_ctx* ctx, int mode, const int8_t* pairs);
+
 /* ------------------------------------------------------------------ composite: one front-end step
  * P(prev), P(cur), K, F+S on cur (no existing keypoints), B(tracked), B(new) for `count` frame pairs in
  * ONE call (batch mode inside): what VisualFrontEnd::trackMono + MapManager::extractKeypoints do per

@@ -476,6 +476,52 @@ def describe_ref(im: np.ndarray, pts: np.ndarray):
     return desc, valid
 
 
+def brief32_ref(im: np.ndarray, pts: np.ndarray, pairs: np.ndarray):
+    """FeatureExtractor::describeBRIEF, DEFAULT (contrib) branch: cv::xfeatures2d::BriefDescriptorExtractor::create()
+    (feature_extractor.cpp:242-243; 32 bytes, use_orientation = false) as opencv_contrib's
+    modules/xfeatures2d/src/brief.cpp computes it:
+      KeyPointsFilter::runByImageBorder(kps, size, PATCH_SIZE/2 + KERNEL_SIZE/2 = 24 + 4)   (rounded point),
+      integral(gray, sum, CV_32S),
+      smoothedSum(pt, y, x) = box sum of the 9 x 9 pixels centred on ((int)(pt.y + 0.5) + y, (int)(pt.x + 0.5) + x),
+      desc[i] = sum_k (SMOOTHED(y0, x0) < SMOOTHED(y1, x1)) << (7 - k) over the 8 tests of byte i (generated_32.i).
+    `pairs` int8[256][4] = (y0, x0, y1, x1) in generated_32.i order.  opencv_contrib is not installed in this image:
+    this restatement is NOT pinned against cv2.xfeatures2d ("parity unpinned" for the BRIEF-32 mode); the ORB-fallback
+    mode above is pinned."""
+    pts = np.asarray(pts, np.float32).reshape(-1, 2)
+    pairs = np.asarray(pairs, np.int32).reshape(256, 4)
+    h, w = im.shape
+    n = len(pts)
+    desc = np.zeros((n, 32), np.uint8)
+    valid = np.zeros(n, np.uint8)
+    if n == 0:
+        return desc, valid
+    # one replicated column / row: at a .5 tie (int)(pt + 0.5) can exceed the rounded centre by one, so a box can reach
+    # one pixel past the image when W - 29 (H - 29) is even.  OpenCV reads the integral image out of its row there
+    # (meaningless values); the kernel and this restatement replicate the edge pixel instead.
+    imp = np.pad(im, ((0, 1), (0, 1)), mode="edge").astype(np.int64)
+    integ = np.zeros((h + 2, w + 2), np.int64)
+    integ[1:, 1:] = np.cumsum(np.cumsum(imp, axis=0), axis=1)
+    weights = (1 << (7 - np.arange(8))).astype(np.int32)
+    for i in range(n):
+        x, y = pts[i]
+        rx, ry = _cv_round(x), _cv_round(y)
+        if rx < 28 or ry < 28 or rx >= w - 28 or ry >= h - 28:
+            continue
+        cx, cy = int(float(x) + 0.5), int(float(y) + 0.5)
+
+        def smoothed(dy, dx):
+            yy = cy + dy
+            xx = cx + dx
+            return (integ[yy + 5, xx + 5] - integ[yy + 5, xx - 4] - integ[yy - 4, xx + 5] + integ[yy - 4, xx - 4])
+
+        a = smoothed(pairs[:, 0], pairs[:, 1])
+        b = smoothed(pairs[:, 2], pairs[:, 3])
+        bits = (a < b).astype(np.int32).reshape(32, 8)
+        desc[i] = (bits * weights[None, :]).sum(axis=1).astype(np.uint8)
+        valid[i] = 1
+    return desc, valid
+
+
 # ------------------------------------------------------------------ K: forward/backward LK
 def _lk_cv2(prev, cur, pts, init, maxlevel, win, maxit, eps):
     p0 = np.ascontiguousarray(pts, np.float32).reshape(-1, 1, 2)

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe", "ov2_preprocess",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_describe_config", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
     "ov2_ba_comm_create", "ov2_ba_comm_handle", "ov2_ba_comm_connect", "ov2_ba_comm_connect_local", "ov2_ba_comm_destroy", "ov2_localba_solve_p2p",
 ]
 
@@ -119,6 +119,7 @@ def load():
     lib.ov2_pnp_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, C.c_float, i32, i32, vp, vp, vp]
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    lib.ov2_describe_config.argtypes = [vp, i32, vp]
     lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
@@ -382,6 +383,14 @@ class FeatureExtractor:
                                                          cand.ctypes.data, cn.ctypes.data, 128, C.byref(cap)))
         flat = cand.reshape(-1)[:ncell * cap.value].reshape(ncell, cap.value)
         return [[(int(v & 255), int((v >> 8) & 255), float(v >> 16)) for v in flat[c, :cn[c]]] for c in range(ncell)]
+
+    DESC_ORB_FALLBACK, DESC_BRIEF32 = 0, 1
+
+    def describe_config(self, mode: int, pairs=None):
+        """ov2_describe_config: DESC_ORB_FALLBACK (reference built without opencv_contrib, the default here) or
+        DESC_BRIEF32 with the int8[256][4] = (y0, x0, y1, x1) test pairs of opencv_contrib's generated_32.i."""
+        keep = None if pairs is None else np.ascontiguousarray(pairs, np.int8).reshape(256, 4)
+        self.ctx.check(self.ctx.lib.ov2_describe_config(self.ctx.h, int(mode), None if keep is None else keep.ctypes.data))
 
     def describe_brief(self, pyr: Pyramid, pts, desc_out, valid_out, n=None, frame_idx=None, first_frame=0,
                        per_frame=None):

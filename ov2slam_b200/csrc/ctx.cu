@@ -44,6 +44,7 @@ extern "C" void ov2_destroy(ov2_ctx* ctx) {
     if (ctx->ba_hscal) cudaFreeHost(ctx->ba_hscal);
     if (ctx->ba_stop) cudaFreeHost(ctx->ba_stop);
     if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);   // pinned staging block of the BA path
+    if (ctx->desc_table) cudaFree(ctx->desc_table);
     if (ctx->pe0) { cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1); }
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);

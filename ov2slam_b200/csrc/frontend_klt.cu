@@ -15,6 +15,7 @@
 // Scharr derivatives are computed on the fly from a 12x12 8-bit neighbourhood (reflect-101 at
 // the image edge, constant 0 outside the image - exactly the planes buildOpticalFlowPyramid
 // would have materialised), so the tracker reads only the 8-bit pyramid.
+#include <climits>
 #include "ov2_common.cuh"
 #include "klt_setup.cuh"
 
@@ -34,6 +35,8 @@ struct KltArgs {
     uint8_t* status;
     int max_iter;
     float eps, ferr, fb_dist;
+    double eps2;           // epsilon^2 as OpenCV forms it (double)
+    float eps_lo, eps_hi;  // float brackets of eps2: outside them the float evaluation of |delta|^2 decides
     int* work_counter;   // persistent launch: warps pull keypoint indices from this counter (null: one warp per index)
 };
 
@@ -72,7 +75,7 @@ __device__ __forceinline__ long long warp_sum64(int s) {
 // Ipyr = template pyramid, Jpyr = search pyramid.  nxt: in = initial guess, out = result.
 template <int WIN>
 __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, float2 pt, float2& nxt, int maxlevel,
-                         int max_iter, double eps2, float& err_out, uint8_t* sP, int* sD, int lane) {
+                         int max_iter, double eps2, float eps_lo, float eps_hi, float& err_out, uint8_t* sP, int* sD, int lane) {
     constexpr int NPX = WIN * WIN;
     constexpr int PER_LANE = (NPX + 31) / 32;
     // window pixel owned by (lane, k).  WIN = 9: lane l < 27 owns the three horizontally adjacent pixels
@@ -125,6 +128,16 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         short Iv[PER_LANE], Ixv[PER_LANE], Iyv[PER_LANE];
         int sA11, sA12, sA22;
         kltsetup::template_rows(lane, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22);
+        // |b sums| <= max|J - I| * sum|Ix| with |J - I| <= 8160 (both are 8-bit intensities with 5 fractional bits): when
+        // 8160 * (sum|Ix| + sum|Iy|) < 2^31 the iterations' mismatch sums fit one exact 32-bit redux each (true for
+        // every window whose mean |gradient| is below ~3200 of the possible 8160, i.e. anything but a synthetic
+        // checkerboard; 8162 * 262000 < 2^31); otherwise the split 64-bit reduction is kept.  Same integers either way.
+        int sabs = 0;
+        if (PACK3) {
+#pragma unroll
+            for (int k = 0; k < PER_LANE; ++k) sabs += abs((int)Ixv[k]) + abs((int)Iyv[k]);
+        }
+        const bool b32 = PACK3 && __reduce_add_sync(FULL, sabs) < 262000;
         // |window sums| <= 81 * 4080^2 = 1.35e9 < 2^31 for the 9 x 9 window: one exact 32-bit redux each
         // (the b sums of the iterations can reach 2.7e9 and keep the split 64-bit reduction)
         float A11 = __int2float_rn(__reduce_add_sync(FULL, sA11)) * FLT_SCALE;
@@ -141,9 +154,14 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         nextPt.x -= half;
         nextPt.y -= half;
         float2 prevDelta = make_float2(0.f, 0.f);
+        // the lane's packed search taps are kept while the integer origin (jx, jy) of the window does not move
+        // (sub-pixel steps only change the bilinear weights)
+        int cjx = INT_MIN, cjy = INT_MIN;
+        unsigned top = 0, bot = 0;
         for (int j = 0; j < max_iter; ++j) {
             const int jx = __float2int_rd(nextPt.x), jy = __float2int_rd(nextPt.y);
-            if (jx < -WIN || jx >= lw || jy < -WIN || jy >= lh) {
+            const bool same = (jx == cjx) & (jy == cjy);
+            if (!same && (jx < -WIN || jx >= lw || jy < -WIN || jy >= lh)) {
                 if (level == 0) status = false;
                 break;
             }
@@ -154,21 +172,24 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
             iw10 = __float2int_rn((1.f - a) * b * 16384.f);
             iw11 = 16384 - iw00 - iw01 - iw10;
             int sb1 = 0, sb2 = 0;
-            if (PACK3 && packed_ok && jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
+            if (PACK3 && (same || (packed_ok && jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh))) {
                 // interior, word-aligned level (warp-uniform): the lane's 4 + 4 taps come from two aligned
                 // 32-bit words per row (funnel shift), the 14-bit bilinear weights are applied with
                 // dp2a (u16 x u8 pairs): 4 loads + 6 dp2a per lane instead of 12 byte loads + 12 IMADs.
                 // Same integers as the byte path (signed 16-bit weights x unsigned bytes, exact in int32).
                 if (lane < 27) {
-                    const uint8_t* q = Jimg + (size_t)(jy + lane_row) * Jpitch + (jx + lane_col);
-                    const uintptr_t qa = reinterpret_cast<uintptr_t>(q);
-                    const unsigned sh = (unsigned)(qa & 3) * 8u;
-                    const uint32_t* w = reinterpret_cast<const uint32_t*>(qa & ~(uintptr_t)3);
-                    const uint32_t* wb = reinterpret_cast<const uint32_t*>((qa & ~(uintptr_t)3) + Jpitch);
-                    const unsigned t0 = __ldg(w), b0 = __ldg(wb);
-                    unsigned t1 = 0, b1w = 0;
-                    if (sh) { t1 = __ldg(w + 1); b1w = __ldg(wb + 1); }
-                    const unsigned top = __funnelshift_r(t0, t1, sh), bot = __funnelshift_r(b0, b1w, sh);
+                    if (!same) {
+                        const uint8_t* q = Jimg + (size_t)(jy + lane_row) * Jpitch + (jx + lane_col);
+                        const uintptr_t qa = reinterpret_cast<uintptr_t>(q);
+                        const unsigned sh = (unsigned)(qa & 3) * 8u;
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(qa & ~(uintptr_t)3);
+                        const uint32_t* wb = reinterpret_cast<const uint32_t*>((qa & ~(uintptr_t)3) + Jpitch);
+                        const unsigned t0 = __ldg(w), b0 = __ldg(wb);
+                        unsigned t1 = 0, b1w = 0;
+                        if (sh) { t1 = __ldg(w + 1); b1w = __ldg(wb + 1); }
+                        top = __funnelshift_r(t0, t1, sh);
+                        bot = __funnelshift_r(b0, b1w, sh);
+                    }
                     const unsigned W01 = ((unsigned)iw00 & 0xFFFFu) | ((unsigned)iw01 << 16);
                     const unsigned W23 = ((unsigned)iw10 & 0xFFFFu) | ((unsigned)iw11 << 16);
                     const int j0 = dp2a_lo_su(W01, top, dp2a_lo_su(W23, bot, 256)) >> 9;
@@ -178,6 +199,8 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
                     sb1 = d0 * (int)Ixv[0] + d1 * (int)Ixv[1] + d2 * (int)Ixv[2];
                     sb2 = d0 * (int)Iyv[0] + d1 * (int)Iyv[1] + d2 * (int)Iyv[2];
                 }
+                cjx = jx;
+                cjy = jy;
             } else if (jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh) {
                 // interior (warp-uniform): every lane gathers its own 4 taps straight from L1/L2
                 const uint8_t* src = Jimg + (size_t)jy * Jpitch + jx;
@@ -215,14 +238,30 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
                     }
                 }
             }
-            float b1 = __ll2float_rn(warp_sum64(sb1)) * FLT_SCALE;
-            float b2 = __ll2float_rn(warp_sum64(sb2)) * FLT_SCALE;
+            float b1, b2;
+            if (b32) {
+                b1 = __int2float_rn(__reduce_add_sync(FULL, sb1)) * FLT_SCALE;
+                b2 = __int2float_rn(__reduce_add_sync(FULL, sb2)) * FLT_SCALE;
+            } else {
+                b1 = __ll2float_rn(warp_sum64(sb1)) * FLT_SCALE;
+                b2 = __ll2float_rn(warp_sum64(sb2)) * FLT_SCALE;
+            }
             float2 delta = make_float2((A12 * b2 - A22 * b1) * D, (A12 * b1 - A11 * b2) * D);
             nextPt.x += delta.x;
             nextPt.y += delta.y;
             nxt = make_float2(nextPt.x + half, nextPt.y + half);
-            if ((double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= eps2) break;
-            if (j > 0 && (double)fabsf(delta.x + prevDelta.x) < 0.01 && (double)fabsf(delta.y + prevDelta.y) < 0.01) {
+            // delta.ddot(delta) <= epsilon^2 is a double comparison in OpenCV; a float evaluation (relative error
+            // < 2e-7) decides it except within 1e-6 of the threshold, where the double expression is evaluated
+            {
+                const float q = delta.x * delta.x + delta.y * delta.y;
+                bool conv;
+                if (q < eps_lo) conv = true;
+                else if (q > eps_hi) conv = false;
+                else conv = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= eps2;
+                if (conv) break;
+            }
+            // (double)|f| < 0.01  <=>  |f| <= 0.01f: 0.01f = 0.00999999977... is the largest float below 0.01
+            if (j > 0 && fabsf(delta.x + prevDelta.x) <= 0.01f && fabsf(delta.y + prevDelta.y) <= 0.01f) {
                 nxt.x -= delta.x * 0.5f;
                 nxt.y -= delta.y * 0.5f;
                 break;
@@ -256,12 +295,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt
     if (maxlevel < 0) maxlevel = 0;
     const float2 kp = A.kps[i];
     float2 fwd = A.priors[i];
-    const double eps2 = (double)A.eps * (double)A.eps;
     float err = 0.f;
     // x < 0 marks an empty slot of a fixed-stride batch (the detectors pad their output with (-1, -1),
     // ov2_describe uses the same rule): status 0, prior untouched, no work
     bool ok = kp.x >= 0.f &&
-              lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, eps2, err, sPall[warp], sDall[warp], lane);
+              lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err, sPall[warp], sDall[warp], lane);
     // feature_tracker.cpp:79-101
     if (ok && err > A.ferr) ok = false;
     if (ok) {
@@ -272,7 +310,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt
         // backward: template from the current image at the forward result, search the previous image
         float2 back = kp;
         float err2 = 0.f;
-        bool ok2 = lk_track<WIN>(A.cur, A.prev, frame, fwd, back, 0, A.max_iter, eps2, err2, sPall[warp], sDall[warp], lane);
+        bool ok2 = lk_track<WIN>(A.cur, A.prev, frame, fwd, back, 0, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err2, sPall[warp], sDall[warp], lane);
         if (!ok2) ok = false;
         else {
             float dx = kp.x - back.x, dy = kp.y - back.y;
@@ -337,6 +375,9 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
     A.lvl_all = nbpyrlvl_all;
     A.max_iter = prm->max_iter;
     A.eps = prm->eps;
+    A.eps2 = (double)prm->eps * (double)prm->eps;
+    A.eps_lo = (float)(A.eps2 * (1.0 - 1e-6));
+    A.eps_hi = (float)(A.eps2 * (1.0 + 1e-6));
     A.ferr = prm->ferr;
     A.fb_dist = prm->fb_dist;
     const void* d = nullptr;

@@ -38,6 +38,8 @@ struct ov2_ctx {
     cudaEvent_t upload_ev = nullptr; // "images of this step are on the device" (ov2_frontend_step's upload token)
     // persistent small device blocks (tables)
     void* ba_ws = nullptr; size_t ba_ws_cap = 0;
+    int desc_mode = 0;            // OV2_DESC_* (ov2_describe_config)
+    int8_t* desc_table = nullptr; // device copy of the BRIEF-32 test pairs [256][4]
     double* ba_hscal = nullptr;   // pinned: per-iteration scalar readbacks of the LM controller (legacy path)
     int* ba_stop = nullptr;       // mapped pinned int: stop request polled by the persistent solve kernel
     // optional per-kernel CUDA-event timing (ov2_profile_enable): serialises launches

@@ -1,7 +1,7 @@
 // FeatureExtractor on the GPU: host shim over the C ABI (include/ov2b200.h).
 // Behaviour mirrored: /root/reference/src/feature_extractor.cpp:443-570 (detectGridFAST incl.
 // cornerSubPix and the nfast_th_ adaptation), :288-440 (detectSingleScale incl. the dmaxquality_
-// adaptation), :224-285 (describeBRIEF, non-contrib branch), :575-584
+// adaptation), :224-285 (describeBRIEF; non-contrib ORB branch by default, BRIEF-32 with -DOPENCV_CONTRIB), :575-584
 // (setMask).  The front-end thread is the only caller (under map_mutex_, visual_front_end.cpp:42),
 // so one lazily created context per process is enough.  No OpenCV on the hot path, no CPU fallback.
 #include "feature_extractor.hpp"
@@ -14,6 +14,12 @@
 
 #include "../../include/ov2b200.h"
 #include "pyr_cache.hpp"
+// The reference chooses its descriptor at compile time (CMakeLists.txt:12,35-39; feature_extractor.cpp:69-70,242-246).
+// A build with -DOPENCV_CONTRIB gets BRIEF-32: the kernel is table-driven and the 256 test pairs come from
+// opencv_contrib's generated_32.i through scripts/brief_table_from_contrib.py (writes include/ov2_brief32_pattern.h).
+#ifdef OPENCV_CONTRIB
+#include "../../include/ov2_brief32_pattern.h"
+#endif
 
 namespace {
 struct State {
@@ -22,6 +28,7 @@ struct State {
     // the tracking image and the raw image of a keyframe (map_manager.cpp:286-341: detect on `im`, describe on `imraw`,
     // twice): each is uploaded once, whatever the number of calls (pyr_cache.hpp)
     ov2shim::PyrCache<3> cache;
+    bool desc_configured = false;           // BRIEF-32 table loaded (contrib builds)
     std::mutex mu;
 };
 State& st() { static State s; return s; }
@@ -36,6 +43,15 @@ bool load_image(State& s, const cv::Mat& im) {
             return false;
         }
     }
+#ifdef OPENCV_CONTRIB
+    if (!s.desc_configured) {
+        if (ov2_describe_config(s.ctx, OV2_DESC_BRIEF32, &OV2_BRIEF32_PATTERN[0][0]) != OV2_OK) {
+            fprintf(stderr, "[ov2b200] FeatureExtractor: %s\n", ov2_last_error(s.ctx));
+            return false;
+        }
+        s.desc_configured = true;
+    }
+#endif
     s.pyr = s.cache.get(s.ctx, im, 0);
     if (!s.pyr) {
         fprintf(stderr, "[ov2b200] FeatureExtractor: %s\n", ov2_last_error(s.ctx));

@@ -183,6 +183,65 @@ def test_describe_bit_exact(ctx, w, h):
     pyr.close()
 
 
+@pytest.mark.parametrize("w,h", [(640, 480), (641, 481), (333, 245)])
+def test_describe_brief32_mode_bit_exact(ctx, w, h):
+    """The reference's default (contrib) descriptor, cv::xfeatures2d::BriefDescriptorExtractor (feature_extractor.cpp:242-243):
+    the kernel is table-driven (ov2_describe_config).  opencv_contrib's generated_32.i is not in this image, so the parity
+    here is kernel == oracle/image_ref.py::brief32_ref for randomly drawn tables (Gaussian, as BRIEF draws them) and for a
+    table of extreme offsets; switching back restores the ORB-fallback bits."""
+    from test_oracle_image import _random_brief_pairs
+    nfr = 2
+    imgs = np.stack([synth.make_frame(70 + i, w, h) for i in range(nfr)])
+    imgs[1] = np.random.default_rng(6).integers(0, 256, (h, w)).astype(np.uint8)
+    pyr = api.Pyramid(ctx, nfr, w, h, 0)
+    pyr.build(imgs)
+    fe = api.FeatureExtractor(ctx)
+    rng = np.random.default_rng(2)
+    n_per = 300
+    pts = (rng.random((nfr, n_per, 2)) * [w, h]).astype(np.float32)
+    pts[:, :40] = np.rint(pts[:, :40])
+    pts[:, 40:80] = np.floor(pts[:, 40:80]) + 0.5
+    pts[:, 80:100, 0] = rng.uniform(26.5, 29.5, (nfr, 20))
+    pts[:, 100:120, 0] = rng.uniform(w - 29.5, w - 26.5, (nfr, 20))
+    pts[:, 120:140, 1] = rng.uniform(26.5, 29.5, (nfr, 20))
+    pts[:, 140:160, 1] = rng.uniform(h - 29.5, h - 26.5, (nfr, 20))
+    pts[:, 160:170, 0] = w - 28.5                          # .5 ties at the last valid column / row
+    pts[:, 170:180, 1] = h - 28.5
+    pts[:, 180] = [-1, -1]
+    ext = np.zeros((256, 4), np.int8)
+    ext[:, 0] = np.tile([-24, 24, 0, -24], 64)
+    ext[:, 1] = np.tile([-24, 24, 24, 0], 64)
+    ext[:, 2] = np.tile([24, -24, -24, 24], 64)
+    ext[:, 3] = np.tile([24, -24, 0, 1], 64)
+    desc = np.empty((nfr, n_per, 32), np.uint8)
+    valid = np.empty((nfr, n_per), np.uint8)
+    try:
+        for pairs in (_random_brief_pairs(0), _random_brief_pairs(7), ext):
+            fe.describe_config(fe.DESC_BRIEF32, pairs)
+            fe.describe_brief(pyr, pts.reshape(-1, 2), desc.reshape(-1, 32), valid.reshape(-1), per_frame=n_per)
+            for f in range(nfr):
+                q = pts[f].copy()
+                q[180] = [0, 0]
+                rd, rv = R.brief32_ref(imgs[f], q, pairs)
+                assert np.array_equal(valid[f], rv), f
+                assert np.array_equal(desc[f], rd), (f, int(np.unpackbits(desc[f] ^ rd).sum()))
+            assert valid.sum() > 0.5 * valid.size
+        with pytest.raises(Exception):
+            fe.describe_config(fe.DESC_BRIEF32, None)          # no built-in table: loud, not silent
+        bad = _random_brief_pairs(0).copy()
+        bad[3, 2] = 25
+        with pytest.raises(Exception):
+            fe.describe_config(fe.DESC_BRIEF32, bad)
+    finally:
+        fe.describe_config(fe.DESC_ORB_FALLBACK)
+    fe.describe_brief(pyr, pts.reshape(-1, 2), desc.reshape(-1, 32), valid.reshape(-1), per_frame=n_per)
+    q = pts[0].copy()
+    q[180] = [0, 0]
+    rd, rv = (R.describe_cv2 if R.HAVE_CV2 else R.describe_ref)(imgs[0], q)
+    assert np.array_equal(valid[0], rv) and np.array_equal(desc[0], rd)
+    pyr.close()
+
+
 def _klt_inputs(seed, w, h, n_border=60):
     prev, cur, flow = synth.make_pair(seed, w, h)
     ipts, _, _ = R.detect_grid_fast_nosubpix(prev, 16, np.zeros((0, 2)), 10, use_cv2=False)

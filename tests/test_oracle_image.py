@@ -269,3 +269,38 @@ def test_golden_single_scale(cs, tag):
     assert np.array_equal(ip, g[f"ss_{cs}_{tag}_int"])
     assert qn == float(g[f"ss_{cs}_{tag}_q"][1])
     assert np.abs(sp - g[f"ss_{cs}_{tag}_subpix"]).max() <= 2e-4
+
+
+def _random_brief_pairs(seed=0):
+    """A stand-in for opencv_contrib's generated_32.i (not redistributable / not in this image): 256 test pairs drawn the
+    way BRIEF draws them (isotropic Gaussian, sigma = PATCH_SIZE / 5, clipped to the 48 x 48 patch)."""
+    rng = np.random.default_rng(seed)
+    return np.clip(np.rint(rng.normal(0, 48 / 5.0, (256, 4))), -24, 24).astype(np.int8)
+
+
+def test_brief32_restatement_matches_direct_box_sums():
+    """brief32_ref (integral image, as brief.cpp does it) against the definition evaluated directly: 9 x 9 box sums
+    around (int)(pt + 0.5), first test of a byte in bit 7, 28-pixel border on the rounded point."""
+    rng = np.random.default_rng(5)
+    im = rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    pairs = _random_brief_pairs(1)
+    pts = np.concatenate([rng.uniform(20, 140, (40, 2)), [[27.4, 60.0], [27.5, 60.0], [28.5, 60.2], [131.49, 91.5], [131.5, 91.49], [60.5, 28.5]]]).astype(np.float32)
+    pts[:, 1] = np.clip(pts[:, 1], 0, 119)
+    desc, valid = R.brief32_ref(im, pts, pairs)
+    imp = np.pad(im, ((0, 1), (0, 1)), mode="edge").astype(np.int64)
+    for i, (x, y) in enumerate(pts):
+        rx, ry = R._cv_round(x), R._cv_round(y)
+        ok = 28 <= rx < 160 - 28 and 28 <= ry < 120 - 28
+        assert valid[i] == int(ok)
+        if not ok:
+            assert not desc[i].any()
+            continue
+        cx, cy = int(float(x) + 0.5), int(float(y) + 0.5)
+        box = lambda dy, dx: int(imp[cy + dy - 4:cy + dy + 5, cx + dx - 4:cx + dx + 5].sum())
+        for byte in range(32):
+            v = 0
+            for k in range(8):
+                y0, x0, y1, x1 = (int(t) for t in pairs[byte * 8 + k])
+                v |= int(box(y0, x0) < box(y1, x1)) << (7 - k)
+            assert desc[i, byte] == v
+    assert valid.sum() > 20
