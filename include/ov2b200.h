@@ -215,6 +215,20 @@ OV2_API ov2_status ov2_describe(ov2_ctx* ctx, const ov2_pyr* pyr, int n, const i
 #define OV2_DESC_BRIEF32 1
 OV2_API ov2_status ov2_describe_config(ov2_ctx* ctx, int mode, const int8_t* pairs);
 
+/* ------------------------------------------------------------------ 8f-3: stereo prior by a row search
+ * Replaces the per-keypoint loop over FeatureTracker::getLineMinSAD(iml, imr, pt, nwinsize, xprior, l1err, bgoleft)
+ * (/root/reference/src/feature_tracker.cpp:138-204) that MapManager::stereoMatching runs for every 2-D keypoint of a
+ * keyframe on the coarsest pyramid level when `bdo_stereo_rect` is set (/root/reference/src/map_manager.cpp:417-431):
+ * for each point (coordinates of pyramid level `level`) the column of the right image, scanned in unit steps from the
+ * point's own column (downwards when goleft), whose nwinsize x nwinsize window has the smallest mean absolute
+ * difference to the sub-pixel patch of the left image.  xprior_out = that column (float, same fractional part as the
+ * input) or -1 when the window shrinks to nothing at the border / no candidate is below 255; l1err_out = the minimum
+ * (255 when xprior is -1; the reference leaves it unset there).  nwinsize must be odd (OV2_ERR_INVALID otherwise, the
+ * reference prints a message and returns) and <= 15.  Frame addressing as ov2_fb_klt. */
+OV2_API ov2_status ov2_line_min_sad(ov2_ctx* ctx, const ov2_pyr* left, const ov2_pyr* right, int level, int n,
+                            const int32_t* frame_idx, int first_frame, int per_frame, const float* pts, int nwinsize,
+                            int goleft, float* xprior_out, float* l1err_out);
+
 /* ------------------------------------------------------------------ composite: one front-end step
  * P(prev), P(cur), K, F+S on cur (no existing keypoints), B(tracked), B(new) for `count` frame pairs in
  * ONE call (batch mode inside): what VisualFrontEnd::trackMono + MapManager::extractKeypoints do per

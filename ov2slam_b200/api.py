@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe", "ov2_preprocess",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_describe_config", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_describe_config", "ov2_line_min_sad", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
     "ov2_ba_comm_create", "ov2_ba_comm_handle", "ov2_ba_comm_connect", "ov2_ba_comm_connect_local", "ov2_ba_comm_destroy", "ov2_localba_solve_p2p",
 ]
 
@@ -120,6 +120,7 @@ def load():
     lib.ov2_debug_fast_cells.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, C.POINTER(i32)]
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.ov2_describe_config.argtypes = [vp, i32, vp]
+    lib.ov2_line_min_sad.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp]
     lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
@@ -313,6 +314,18 @@ class FeatureTracker:
         self.ctx.check(self.ctx.lib.ov2_fb_klt(self.ctx.h, prev.h_, cur.h_, C.byref(prm), n, _ptr(frame_idx),
                                                int(first_frame), int(per_frame or 0), lv_ptr, lv_all,
                                                _ptr(kps), _ptr(priors_inout), _ptr(status_out)))
+
+    def line_min_sad(self, left: Pyramid, right: Pyramid, level: int, pts, nwinsize, goleft, xprior_out, l1err_out,
+                     n=None, frame_idx=None, first_frame=0, per_frame=None):
+        """getLineMinSAD (feature_tracker.cpp:138-204) for a batch of points of pyramid level `level` (the stereo prior
+        MapManager::stereoMatching computes per keypoint, map_manager.cpp:417-431): xprior_out / l1err_out (n,) float32."""
+        if n is None:
+            n = int(pts.shape[0])
+        if frame_idx is None and per_frame is None:
+            per_frame = max(n, 1)
+        self.ctx.check(self.ctx.lib.ov2_line_min_sad(self.ctx.h, left.h_, right.h_, int(level), n, _ptr(frame_idx), int(first_frame),
+                                                     int(per_frame or 0), _ptr(pts), int(nwinsize), 1 if goleft else 0,
+                                                     _ptr(xprior_out), _ptr(l1err_out)))
 
 
 class FeatureExtractor:

@@ -28,6 +28,7 @@ SOURCES = {
     "frontend_desc.cu": ["-fmad=false"],
     "frontend_clahe.cu": ["-fmad=false"],
     "frontend_sscale.cu": ["-fmad=false"],
+    "frontend_sad.cu": ["-fmad=false"],
     "frontend_step.cu": [],
     "ba_solver.cu": [],
     "ba_lm.cu": [],

@@ -34,6 +34,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <thread>
 
 namespace balm {
 
@@ -494,6 +496,245 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
 #undef ACC
 }
 
+// ------------------------------------------------------------------ Schur elimination, "owner" mode (reduced systems up to n = 96)
+// The RED path above sends ~900 fp64 reductions per landmark to the global block and a B200 SM retires one fp64 RED lane
+// every ~2.4-3.6 cycles: a batched C3 solve spent 6.7 of its 11.9 ms there (OV2_BA_TRACE, round 2).  This mode forms the
+// same sums where nothing has to be shared:
+//   B1  camera part F'F, F'r, column norms: the observations are pre-sorted by (anchor keyframe, observing keyframe)
+//       (host: pack_window), so a chunk of <= PCH observations touches ONE 12 x 12 Gram block [Ja | Jo]'[Ja | Jo]; a warp
+//       owns a chunk, its lanes own the 78 + 12 entries (upper triangle + gradient), the chunk's Jacobian rows pass through the
+//       warp's staging slice of shared memory, and the chunk's totals leave as <= 102 REDs (was ~89 per observation).
+//   B2  landmark part: SG lanes per landmark form ete / g_e and the landmark's E'F row as a DENSE n-vector in a shared-memory
+//       tile (one row per landmark, 32 / SG rows per warp); then S -= sum_rows w y y', rhs -= sum_rows w g_e y with every
+//       thread owning 3 x 3 register tiles of the upper triangle over ALL rounds (no atomics at all), flushed once per phase.
+constexpr int PCH = 32;           // observations per pair chunk
+
+template <int SG>
+__device__ __forceinline__ void owner_fill_row(const Prob& P, const int* __restrict__ s_slot, int l, int sl, bool in, double radius, int first_iter,
+                                               double* row, double& w_out, double& ge_out, double& gmax_lm) {
+    const int p0 = in ? P.lm_ptr[l] : 0, p1 = in ? P.lm_ptr[l + 1] : 0;
+    const int sa = in ? s_slot[P.lm_anchor_cam[l]] : -1;
+    double cnl = 0.0, ge = 0.0, aE[6] = {0, 0, 0, 0, 0, 0};
+    int nact = 0;
+    for (int p = p0 + sl; p < p1; p += SG) {
+        const uint8_t act = P.active[p];
+        const double2 jl = *reinterpret_cast<const double2*>(P.Jl + 2 * (size_t)p);
+        const double2 jr = *reinterpret_cast<const double2*>(P.Jr + 2 * (size_t)p);
+        if (!act) continue;
+        cnl += jl.x * jl.x + jl.y * jl.y;
+        ge += jl.x * jr.x + jl.y * jr.y;
+        nact++;
+        if (P.obs_type && P.obs_type[p] == 2) continue;          // e-block-only row (schur_eliminator_impl.h:196-217)
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        if (sa >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) aE[k] += jl.x * Ja[k] + jl.y * Ja[6 + k];
+        }
+        const int so = s_slot[P.obs_cam[p]];
+        if (so >= 0) {
+            const double* Jo = P.Jo + 12 * (size_t)p;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(row + 6 * so + k, jl.x * Jo[k] + jl.y * Jo[6 + k]);   // a stereo keyframe observes twice
+        }
+    }
+#pragma unroll
+    for (int o = SG / 2; o > 0; o >>= 1) {
+        cnl += __shfl_xor_sync(FULL, cnl, o);
+        ge += __shfl_xor_sync(FULL, ge, o);
+        nact += __shfl_xor_sync(FULL, nact, o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) aE[k] += __shfl_xor_sync(FULL, aE[k], o);
+    }
+    w_out = 0.0;
+    ge_out = 0.0;
+    if (!in) return;
+    if (nact == 0) {   // unused parameter block: dropped from the program (program.cc:305-387)
+        if (sl == 0) { P.ete[l] = 0.0; P.ge[l] = 0.0; }
+        return;
+    }
+    double sc = P.sc_lm[l];
+    if (first_iter) {
+        sc = 1.0 / (1.0 + sqrt(cnl));
+        if (sl == 0) P.sc_lm[l] = sc;
+    }
+    const double diag = fmin(fmax(cnl * sc * sc, 1e-6), 1e32);
+    const double ete = cnl + diag / (radius * sc * sc);
+    if (sl == 0) {
+        P.ete[l] = ete;
+        P.ge[l] = ge;
+        if (sa >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(row + 6 * sa + k, aE[k]);
+        }
+    }
+    gmax_lm = fmax(gmax_lm, fabs(ge));
+    w_out = 1.0 / ete;
+    ge_out = ge;
+}
+
+template <int NT, int SG>
+__device__ __noinline__ void schur_owner_phase(const Prob& P, const int* __restrict__ s_slot, double* s_tile, int n, double radius, int first_iter,
+                                               int bid, int G, double* scal) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarps = G * WARPS, gwarp = bid * WARPS + warp;
+    double* const cRhs = P.acc; double* const cG = P.acc + n; double* const cCn = P.acc + 2 * n; double* const cS = P.acc + 3 * n;
+    // ---------------- B1: camera part, one pair chunk per warp
+    const bool tracing = P.trace != nullptr && bid == 0 && tid == 0;
+    const unsigned long long t_b1 = tracing ? global_ns() : 0;
+    {
+        double* st = s_tile + (size_t)warp * (PCH * 26);
+        int ia0[3], ja0[3], ja1[3], ei[3], ej[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = lane + 32 * k;
+            ei[k] = -1; ej[k] = -1; ia0[k] = 0; ja0[k] = 0; ja1[k] = 0;
+            if (e < 78) {
+                int i = 0, rem = e;
+                while (rem >= 12 - i) { rem -= 12 - i; ++i; }
+                const int j = i + rem;
+                ei[k] = i; ej[k] = j;
+                ia0[k] = i < 6 ? i : i + 6;
+                ja0[k] = j < 6 ? j : j + 6;
+                ja1[k] = ja0[k] + 6;
+            } else if (e < 90) {
+                const int i = e - 78;
+                ei[k] = i; ej[k] = 12;                              // gradient entry: [Ja | Jo]' r
+                ia0[k] = i < 6 ? i : i + 6;
+                ja0[k] = 24; ja1[k] = 25;
+            }
+        }
+        for (int c = gwarp; c < P.npchunk; c += gwarps) {
+            const int2 ch = P.pair_chunk[c];
+            const int cnt = ch.y - ch.x;                             // <= PCH = 32: lane q looks after observation q
+            int pq = 0, onq = 0;
+            if (lane < cnt) {
+                pq = P.pair_perm[ch.x + lane];
+                onq = (P.active[pq] && !(P.obs_type && P.obs_type[pq] == 2)) ? 1 : 0;
+            }
+            const int pf = __shfl_sync(FULL, pq, 0);
+            const int sa = s_slot[P.lm_anchor_cam[P.obs_lm[pf]]], so = s_slot[P.obs_cam[pf]];
+            if (sa < 0 && so < 0) continue;                         // both keyframes constant / unused (warp-uniform)
+            // the whole chunk's rows [Ja | Jo | r] go to this warp's staging slice with every load in flight at once (staging
+            // four observations at a time left the phase waiting on one L2 round trip per stage: 4.1 ms of a batched C3 solve)
+            __syncwarp();
+            for (int e0 = 0; e0 < cnt * 26; e0 += 32) {             // uniform trip count: the shuffles need every lane
+                const int e = e0 + lane;
+                const bool ok = e < cnt * 26;
+                const int q = ok ? e / 26 : 0, k = e - 26 * q;
+                const int p = __shfl_sync(FULL, pq, q);
+                const int on = __shfl_sync(FULL, onq, q);
+                if (ok) {
+                    const double v = k < 12 ? P.Ja[12 * (size_t)p + k] : (k < 24 ? P.Jo[12 * (size_t)p + (k - 12)] : P.Jr[2 * (size_t)p + (k - 24)]);
+                    st[e] = on ? v : 0.0;
+                }
+            }
+            __syncwarp();
+            double a[3] = {0.0, 0.0, 0.0};
+            for (int q = 0; q < cnt; ++q) {
+                const double* v = st + 26 * q;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a[k] += v[ia0[k]] * v[ja0[k]] + v[ia0[k] + 6] * v[ja1[k]];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = ei[k], j = ej[k];
+                double v = a[k];
+                if (i < 0 || v == 0.0) continue;
+                if (j == 12) {                                      // F'r
+                    if (i < 6) { if (sa >= 0) red_add_f64(cG + 6 * sa + i, v); }
+                    else if (so >= 0) red_add_f64(cG + 6 * so + (i - 6), v);
+                } else if (j < 6) {                                 // anchor diagonal block (i <= j < 6)
+                    if (sa >= 0) {
+                        red_add_f64(cS + (size_t)(6 * sa + i) * n + 6 * sa + j, v);
+                        if (i == j) red_add_f64(cCn + 6 * sa + i, v);
+                    }
+                } else if (i >= 6) {                                // observer diagonal block
+                    if (so >= 0) {
+                        red_add_f64(cS + (size_t)(6 * so + (i - 6)) * n + 6 * so + (j - 6), v);
+                        if (i == j) red_add_f64(cCn + 6 * so + (i - 6), v);
+                    }
+                } else if (sa >= 0 && so >= 0) {                    // cross block Ja' Jo into the upper block (min slot, max slot)
+                    const int ca = i, cb = j - 6;
+                    if (sa < so) red_add_f64(cS + (size_t)(6 * sa + ca) * n + 6 * so + cb, v);
+                    else if (sa > so) red_add_f64(cS + (size_t)(6 * so + cb) * n + 6 * sa + ca, v);
+                    else {                                          // same pose block twice: Ja'Jo + Jo'Ja lands in its diagonal block
+                        if (ca == cb) { v *= 2.0; red_add_f64(cCn + 6 * sa + ca, v); }
+                        const int lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
+                        red_add_f64(cS + (size_t)(6 * sa + lo) * n + 6 * sa + hi, v);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tracing) P.trace[15] += global_ns() - t_b1;                 // trace slot 15 = B1 share of B:schur in this mode
+    // ---------------- B2: landmark part
+    constexpr int R = WARPS * (32 / SG);                            // tile rows (landmarks per round and CTA)
+    const int TP = n + 2;
+    double* tw = s_tile + (size_t)R * TP;
+    double* tg = tw + R;
+    const int nt3 = n / 3, ntile = nt3 * (nt3 + 1) / 2;
+    int ti[NT], tj[NT];
+    double acc[NT][9];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        const int t = tid + THREADS * k;
+        ti[k] = -1; tj[k] = 0;
+        if (t < ntile) {
+            int i = 0, rem = t;
+            while (rem >= nt3 - i) { rem -= nt3 - i; ++i; }
+            ti[k] = i; tj[k] = i + rem;
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) acc[k][e] = 0.0;
+    }
+    double racc = 0.0, gmax_lm = 0.0;
+    const int sub = lane / SG, sl = lane - sub * SG;
+    const int myrow = warp * (32 / SG) + sub;
+    for (int l0 = bid * R; l0 < P.npts; l0 += G * R) {
+        for (int e = tid; e < R * TP + 2 * R; e += THREADS) s_tile[e] = 0.0;
+        __syncthreads();
+        {
+            const int l = l0 + myrow;
+            double w, g;
+            owner_fill_row<SG>(P, s_slot, l, sl, l < P.npts, radius, first_iter, s_tile + (size_t)myrow * TP, w, g, gmax_lm);
+            if (sl == 0) { tw[myrow] = w; tg[myrow] = g; }
+        }
+        __syncthreads();
+        const int rows = min(R, P.npts - l0);
+        for (int r = 0; r < rows; ++r) {
+            const double w = tw[r];
+            if (w == 0.0) continue;                                  // landmark dropped from the program (uniform)
+            const double* y = s_tile + (size_t)r * TP;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                if (ti[k] < 0) continue;
+                const double yi0 = y[3 * ti[k]] * w, yi1 = y[3 * ti[k] + 1] * w, yi2 = y[3 * ti[k] + 2] * w;
+                const double yj0 = y[3 * tj[k]], yj1 = y[3 * tj[k] + 1], yj2 = y[3 * tj[k] + 2];
+                acc[k][0] -= yi0 * yj0; acc[k][1] -= yi0 * yj1; acc[k][2] -= yi0 * yj2;
+                acc[k][3] -= yi1 * yj0; acc[k][4] -= yi1 * yj1; acc[k][5] -= yi1 * yj2;
+                acc[k][6] -= yi2 * yj0; acc[k][7] -= yi2 * yj1; acc[k][8] -= yi2 * yj2;
+            }
+            if (tid < n) racc -= y[tid] * (w * tg[r]);
+        }
+        __syncthreads();
+    }
+    // flush: every upper-triangle entry of this CTA's partial system has exactly one owner
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        if (ti[k] < 0) continue;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+            const int r = 3 * ti[k] + e / 3, c = 3 * tj[k] + e % 3;
+            const double v = acc[k][e];
+            if (r <= c && v != 0.0) red_add_f64(cS + (size_t)r * n + c, v);
+        }
+    }
+    if (tid < n && racc != 0.0) red_add_f64(cRhs + tid, racc);
+    gmax_lm = warp_max(gmax_lm);
+    if (lane == 0 && gmax_lm > 0.0) atomic_max_pos(scal + SC_GMAX_LM, gmax_lm);
+}
+
 // ------------------------------------------------------------------ reduced camera system, n <= 96: CTA-wide Gauss-Jordan in shared memory
 // Augmented system [S + D | b] in shared memory (row pitch n + 2); pivot step j updates every row r != j for the columns
 // c > j: A[r][c] -= (A[r][j] / A[j][j]) A[j][c].  Row j and column j are not written in step j, so ONE block barrier per
@@ -830,6 +1071,65 @@ __device__ __forceinline__ void backsub_landmark(const Prob& P, const int* __res
     cost_out += cost;
 }
 
+// Sub-group variant: SG lanes per landmark, 32 / SG landmarks per warp in flight.  A landmark has ~4 (C3) to ~8 (C5)
+// observations, so one warp per landmark leaves most lanes idle and - worse - strings the landmarks' dependent load chains
+// (CSR pointers -> Jacobian rows -> reduction -> second pass) one after the other: measured 3.9 ms of a 11.9 ms batched C3
+// solve.  Same arithmetic per observation; the per-landmark sums are formed inside the sub-group.
+template <int SG>
+__device__ __forceinline__ void backsub_landmarks_sg(const Prob& P, const int* __restrict__ s_slot, const double* __restrict__ s_cam,
+                                                     int l0, int lane, const double* __restrict__ invd, double* __restrict__ cand_invd,
+                                                     int use_huber, double& mcc_out, double& st2_out, double& cx2_out, double& cost_out) {
+    const int sub = lane / SG, sl = lane - sub * SG;
+    const int l = l0 + sub;
+    const bool in = l < P.npts;
+    const double ete = in ? P.ete[l] : 0.0;
+    const bool live = in && ete != 0.0;     // ete == 0: landmark not in the program, candidate stays equal
+    const int p0 = live ? P.lm_ptr[l] : 0, p1 = live ? P.lm_ptr[l + 1] : 0;
+    const int sa = live ? s_slot[P.lm_anchor_cam[l]] : -1;
+    double za[6] = {0, 0, 0, 0, 0, 0};
+    if (sa >= 0)
+        for (int k = 0; k < 6; ++k) za[k] = P.z[6 * sa + k];
+    double acc = 0.0;
+    for (int p = p0 + sl; p < p1; p += SG) {
+        if (!P.active[p]) continue;
+        const int so = (P.obs_type && P.obs_type[p] == 2) ? -1 : s_slot[P.obs_cam[p]];
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        const double* Jo = P.Jo + 12 * (size_t)p;
+        double f0 = 0.0, f1 = 0.0;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 += Ja[k] * za[k]; f1 += Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = P.z[6 * so + k]; f0 += Jo[k] * zk; f1 += Jo[6 + k] * zk; }
+        acc += P.Jl[2 * (size_t)p] * f0 + P.Jl[2 * (size_t)p + 1] * f1;
+    }
+#pragma unroll
+    for (int o = SG / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    const double y = live ? (P.ge[l] - acc) / ete : 0.0;
+    const double dl = -y;
+    const double cl = live ? invd[l] + dl : 0.0;
+    double mcc = 0.0, cost = 0.0;
+    for (int p = p0 + sl; p < p1; p += SG) {
+        if (!P.active[p]) continue;
+        const int so = (P.obs_type && P.obs_type[p] == 2) ? -1 : s_slot[P.obs_cam[p]];
+        const double* Ja = P.Ja + 12 * (size_t)p;
+        const double* Jo = P.Jo + 12 * (size_t)p;
+        double f0 = P.Jl[2 * (size_t)p] * dl, f1 = P.Jl[2 * (size_t)p + 1] * dl;
+        if (sa >= 0)
+            for (int k = 0; k < 6; ++k) { f0 -= Ja[k] * za[k]; f1 -= Ja[6 + k] * za[k]; }
+        if (so >= 0)
+            for (int k = 0; k < 6; ++k) { const double zk = P.z[6 * so + k]; f0 -= Jo[k] * zk; f1 -= Jo[6 + k] * zk; }
+        mcc -= f0 * (P.Jr[2 * (size_t)p] + 0.5 * f0) + f1 * (P.Jr[2 * (size_t)p + 1] + 0.5 * f1);
+        cost += eval_block<false>(P, p, l, s_cam, cl, use_huber);
+    }
+    if (live && sl == 0) {
+        cand_invd[l] = cl;
+        st2_out += dl * dl;
+        cx2_out += cl * cl;
+    }
+    mcc_out += mcc;
+    cost_out += cost;
+}
+
 // ------------------------------------------------------------------ multi-GPU exchange (peer memory over NVLink)
 // Every rank exports one buffer (see ba_lm.cuh); xsync() is a barrier between the ranks' kernels: CTA 0 / thread 0
 // writes its epoch into slot `rank` of every peer's flag array (release, system scope) and waits until every peer
@@ -993,7 +1293,18 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 bar.sync();
                 TR(1);
                 // ---- B: Schur elimination into this CTA's accumulation copy (global, RED) or shared-memory block (lock)
-                if (P.schur_smem == 2) {
+                if (P.schur_smem == 3) {
+                    // owner mode (n <= 96): pair-sorted Gram blocks + dense landmark rows, no per-observation reductions
+                    if (n <= 66) {
+                        if (P.sg == 4) schur_owner_phase<1, 4>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                        else if (P.sg == 8) schur_owner_phase<1, 8>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                        else schur_owner_phase<1, 32>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                    } else {
+                        if (P.sg == 4) schur_owner_phase<3, 4>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                        else if (P.sg == 8) schur_owner_phase<3, 8>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                        else schur_owner_phase<3, 32>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
+                    }
+                } else if (P.schur_smem == 2) {
                     // per-WARP private copies of [rhs | F'r | column norms | S] in shared memory: plain read-modify-writes, no
                     // lock, no RED; the CTA sums its copies and sends the non-zeros to the global block once per phase
                     const int live_s = 3 * n + n * n;
@@ -1121,8 +1432,16 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                     }
                     __syncthreads();
                     double mcc = 0.0, cost = 0.0, lst2 = 0.0, lcx2 = 0.0;
-                    for (int l = gwarp; l < P.npts; l += gwarps)
-                        backsub_landmark(P, s_slot, s_cam, l, lane, x_invd, c_invd, use_huber, mcc, lst2, lcx2, cost);
+                    if (P.sg == 4) {
+                        for (int l0 = gwarp * 8; l0 < P.npts; l0 += gwarps * 8)
+                            backsub_landmarks_sg<4>(P, s_slot, s_cam, l0, lane, x_invd, c_invd, use_huber, mcc, lst2, lcx2, cost);
+                    } else if (P.sg == 8) {
+                        for (int l0 = gwarp * 4; l0 < P.npts; l0 += gwarps * 4)
+                            backsub_landmarks_sg<8>(P, s_slot, s_cam, l0, lane, x_invd, c_invd, use_huber, mcc, lst2, lcx2, cost);
+                    } else {
+                        for (int l = gwarp; l < P.npts; l += gwarps)
+                            backsub_landmark(P, s_slot, s_cam, l, lane, x_invd, c_invd, use_huber, mcc, lst2, lcx2, cost);
+                    }
                     // the keyframe part of the norms counts once per window (rank 0, CTA 0)
                     if (bid == 0 && X.rank == 0) { lst2 += st2; lcx2 += cx2; }
                     mcc = warp_sum(mcc); cost = warp_sum(cost); lst2 = warp_sum(lst2); lcx2 = warp_sum(lcx2);
@@ -1281,9 +1600,11 @@ namespace {
 
 struct HostPlan {
     size_t off_prob, off_pose, off_invd, off_apx, off_opx, off_lac, off_oc, off_ol, off_lp, off_pc, off_ty, in_bytes;   // uploaded block
+    size_t off_pp, off_pch; int pch_cap, sg;   // owner mode: pair-sorted permutation, chunk table (capacity), lanes per landmark
     // device-only work areas (offsets into the work block)
     size_t w_pose1, w_invd1, w_active, w_flags, w_camused, w_camslot, w_Jr, w_Ja, w_Jo, w_Jl, w_chi2, w_dpos, w_sclm, w_ete, w_ge,
            w_acc, w_total, w_scal, w_z, w_panel, w_sccam, w_counts, w_bar, w_result, w_trace, work_bytes, zero_off, zero_bytes;
+    size_t out_result, out_flags, act_rel;   // offsets inside the batch's output region / 'active' region (set up by balm_solve)
     int ncv_max, n_max, ncopy, solve_blocked, schur_smem;
     size_t blk, smem_work_off, smem_bytes, smem_sacc_off;
 };
@@ -1299,7 +1620,7 @@ size_t take(size_t& off, size_t bytes, size_t align = 256) {
 
 // Plans one window: offsets of its inputs inside the upload block and of its work areas inside the work block.
 static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world, size_t& st_off, size_t& in_off, size_t& work_off,
-                              HostPlan& H, int ncopy_cap, bool single_window) {
+                              size_t& zero_off, size_t& out_off, size_t& act_off, HostPlan& H, int ncopy_cap, bool single_window) {
     const int ncam = pb->ncam, npts = pb->npts, nobs = pb->nobs;
     int ncv = 0;
     for (int c = 0; c < ncam; ++c) ncv += pb->pose_const[c] ? 0 : 1;
@@ -1327,21 +1648,32 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     H.off_lp = take(in_off, sizeof(int32_t) * (size_t)(npts + 1));
     H.off_pc = take(in_off, (size_t)ncam);
     H.off_ty = take(in_off, pb->obs_type ? (size_t)(nobs > 0 ? nobs : 1) : 0);
+    {
+        // owner-mode Schur (n <= 96): observations sorted by (anchor keyframe, observing keyframe) + chunk table
+        const size_t ngmax = (size_t)ncam * ncam < (size_t)(nobs > 0 ? nobs : 1) ? (size_t)ncam * ncam : (size_t)(nobs > 0 ? nobs : 1);
+        H.pch_cap = (int)((size_t)(nobs > 0 ? nobs : 1) / PCH + ngmax + 1);
+        H.off_pp = take(in_off, sizeof(int32_t) * (size_t)(nobs > 0 ? nobs : 1));
+        H.off_pch = take(in_off, sizeof(int2) * (size_t)H.pch_cap);
+        const double avg = npts > 0 ? (double)nobs / (double)npts : 0.0;
+        H.sg = avg <= 5.0 ? 4 : (avg <= 12.0 ? 8 : 32);
+        if (getenv("OV2_BA_SG")) { const int e = atoi(getenv("OV2_BA_SG")); if (e == 4 || e == 8 || e == 32) H.sg = e; }
+    }
     const size_t no = nobs > 0 ? nobs : 1, np = npts > 0 ? npts : 1;
-    // zero-initialised part first (one memset): flags, cam_used, counts, barrier, result
-    H.zero_off = take(work_off, 0);
-    H.w_flags = take(work_off, no);
-    H.w_camused = take(work_off, 2 * (size_t)ncam);
-    H.w_counts = take(work_off, sizeof(double) * 8);
-    H.w_bar = take(work_off, sizeof(unsigned) * 4);
-    H.w_result = take(work_off, sizeof(Result));
-    H.w_trace = take(work_off, sizeof(unsigned long long) * 16);
-    H.w_sclm = take(work_off, sizeof(double) * np);
-    H.w_sccam = take(work_off, sizeof(double) * MAX_N);
-    H.zero_bytes = work_off - H.zero_off;
+    // results (Result record + outlier flags) of all windows sit together in the output region, the 'active' bytes of all
+    // windows in another: one memset each and ONE D2H for a whole batch (w_flags / w_result / w_active are made absolute
+    // offsets by balm_solve once every window is planned)
+    H.out_result = take(out_off, sizeof(Result), 64);
+    H.out_flags = take(out_off, no, 64);
+    H.act_rel = take(act_off, no, 64);
+    // zero-initialised small arrays of all windows: a region of their own (relative offsets until balm_solve places it)
+    H.w_camused = take(zero_off, 2 * (size_t)ncam);
+    H.w_counts = take(zero_off, sizeof(double) * 8);
+    H.w_bar = take(zero_off, sizeof(unsigned) * 4);
+    H.w_trace = take(zero_off, sizeof(unsigned long long) * 16);
+    H.w_sclm = take(zero_off, sizeof(double) * np);
+    H.w_sccam = take(zero_off, sizeof(double) * MAX_N);
     H.w_pose1 = take(work_off, sizeof(double) * 7 * ncam);
     H.w_invd1 = take(work_off, sizeof(double) * np);
-    H.w_active = take(work_off, no);
     H.w_camslot = take(work_off, sizeof(int32_t) * ncam);
     H.w_Jr = take(work_off, sizeof(double) * 2 * no);
     H.w_Ja = take(work_off, sizeof(double) * 12 * no);
@@ -1385,6 +1717,18 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
         H.schur_smem = 2;
         H.ncopy = 1;
         schur += (size_t)WARPS * H.blk * sizeof(double);
+    }
+    // mode 3 (default up to n = 96, single windows and batches): owner mode, see schur_owner_phase
+    // Single windows spread over many CTAs stay on mode 2 when it fits (measured C3: 119 us vs 236 us per solve in the
+    // Schur phase at 148 CTAs - there the phase is latency, not RED bound); batches (1-2 CTAs per window) take mode 3.
+    if (H.n_max > 0 && H.n_max <= 96 && ((ssm && atoi(ssm) == 3) || (!ssm && !(single_window && H.schur_smem == 2)))) {
+        const size_t R = (size_t)WARPS * (32 / H.sg);
+        size_t tile = (R * (size_t)(H.n_max + 2) + 2 * R) * sizeof(double);
+        const size_t stage = (size_t)WARPS * PCH * 26 * sizeof(double);
+        if (tile < stage) tile = stage;
+        H.schur_smem = 3;
+        H.ncopy = 1;
+        schur = (tile + 15) & ~(size_t)15;
     }
     H.smem_bytes = s + (schur > solve ? schur : solve) + 16;
     (void)world;
@@ -1437,7 +1781,9 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.counts = (double*)(dwork + H.w_counts); P.bar = (unsigned*)(dwork + H.w_bar); P.result = (Result*)(dwork + H.w_result);
     P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
+    P.sg = H.sg;   // lanes per landmark in the per-landmark phases
     P.schur_smem = H.schur_smem; P.smem_sacc_off = (int)H.smem_sacc_off;
+    P.pair_perm = (const int32_t*)(din + H.off_pp); P.pair_chunk = (const int2*)(din + H.off_pch); P.npchunk = 0;
     P.smem_work_off = (int)H.smem_work_off;
 }
 
@@ -1458,7 +1804,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     std::vector<HostPlan> plans(nprob);
     std::vector<ov2_ba_problem> hp(nprob);           // host-resident views of every window (device inputs are copied down)
     std::vector<std::vector<char>> hold;              // storage for inputs that came as device pointers
-    size_t st_off = 0, in_off = 0, work_off = 0;
+    size_t st_off = 0, in_off = 0, work_off = 0, zero_off = 0, out_off = 0, act_off = 0;
     size_t smem_max = 0;
     int gmax_work = 1;
     for (int k = 0; k < nprob; ++k) {
@@ -1485,7 +1831,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         hp[k].Kr = (const double*)pull(pb.Kr, 32);
         hp[k].Trl = (const double*)pull(pb.Trl, 56);
         if (pb.obs_type && (!pb.Kr || !pb.Trl)) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_type given without Kr / Trl");
-        if ((st = plan_window(ctx, &hp[k], world, st_off, in_off, work_off, plans[k], 8, nprob == 1)) != OV2_OK) return st;
+        if ((st = plan_window(ctx, &hp[k], world, st_off, in_off, work_off, zero_off, out_off, act_off, plans[k], 8, nprob == 1)) != OV2_OK) return st;
         if (plans[k].smem_bytes > smem_max) smem_max = plans[k].smem_bytes;
         const int wk = (pb.nobs + THREADS - 1) / THREADS;
         const int wl = (pb.npts + WARPS - 1) / WARPS;                  // a landmark per warp and phase (single window: every SM helps)
@@ -1497,22 +1843,38 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     const size_t st_bytes = (st_off + 255) & ~(size_t)255;
     for (int k = 0; k < nprob; ++k) {
         HostPlan& H = plans[k];
-        for (size_t* f : {&H.off_prob, &H.off_apx, &H.off_opx, &H.off_lac, &H.off_oc, &H.off_ol, &H.off_lp, &H.off_pc, &H.off_ty}) *f += st_bytes;
+        for (size_t* f : {&H.off_prob, &H.off_apx, &H.off_opx, &H.off_lac, &H.off_oc, &H.off_ol, &H.off_lp, &H.off_pc, &H.off_ty, &H.off_pp, &H.off_pch}) *f += st_bytes;
     }
     const size_t in_bytes = st_bytes + ((in_off + 255) & ~(size_t)255);
-    if (ctx->ba_ws_cap < in_bytes) {
+    // work block layout: [per-window work areas | zero region | output region (Result + flags) | 'active' region]
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t zbase = al(work_off), zbytes = al(zero_off);
+    const size_t obase = zbase + zbytes, obytes = al(out_off);
+    const size_t abase = obase + obytes, abytes = al(act_off);
+    for (int k = 0; k < nprob; ++k) {
+        HostPlan& H = plans[k];
+        for (size_t* f : {&H.w_camused, &H.w_counts, &H.w_bar, &H.w_trace, &H.w_sclm, &H.w_sccam}) *f += zbase;
+        H.w_result = obase + H.out_result;
+        H.w_flags = obase + H.out_flags;
+        H.w_active = abase + H.act_rel;
+    }
+    const size_t host_need = in_bytes + obytes;      // pinned: [packed inputs / returned states | returned output region]
+    if (ctx->ba_ws_cap < host_need) {
         if (ctx->ba_ws) cudaFreeHost(ctx->ba_ws);
         ctx->ba_ws = nullptr; ctx->ba_ws_cap = 0;
-        OV2_CUDA(ctx, cudaHostAlloc(&ctx->ba_ws, in_bytes * 2, cudaHostAllocDefault));
-        ctx->ba_ws_cap = in_bytes * 2;
+        OV2_CUDA(ctx, cudaHostAlloc(&ctx->ba_ws, host_need * 2, cudaHostAllocDefault));
+        ctx->ba_ws_cap = host_need * 2;
     }
     char* hpk = (char*)ctx->ba_ws;
+    char* hout = hpk + in_bytes;
     void* o = nullptr;
     if ((st = ov2_scratch(ctx, in_bytes, &o)) != OV2_OK) return st;
     char* din = (char*)o;
-    if ((st = ov2_scratch(ctx, work_off + 256, &o)) != OV2_OK) return st;
+    if ((st = ov2_scratch(ctx, abase + abytes + 256, &o)) != OV2_OK) return st;
     char* dwork = (char*)o;
-    for (int k = 0; k < nprob; ++k) {
+    // one window's share of the packing: validation, CSR by landmark, copies into the pinned block, the Prob record.
+    // Windows write disjoint parts of the block, so a batch is packed by a few host threads.  Returns an error text.
+    auto pack_window = [&](int k) -> const char* {
         const ov2_ba_problem& pb = hp[k];
         const HostPlan& H = plans[k];
         const int ncam = pb.ncam, npts = pb.npts, nobs = pb.nobs;
@@ -1521,17 +1883,16 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         memset(lp, 0, sizeof(int32_t) * (size_t)(npts + 1));
         for (int i = 0; i < nobs; ++i) {
             const int l = pb.obs_lm[i];
-            if (l < 0 || l >= npts || (i > 0 && l < pb.obs_lm[i - 1]))
-                return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_lm must be sorted ascending and in range");
+            if (l < 0 || l >= npts || (i > 0 && l < pb.obs_lm[i - 1])) return "ov2_localba_solve: obs_lm must be sorted ascending and in range";
             lp[l + 1]++;
         }
         for (int l = 0; l < npts; ++l) lp[l + 1] += lp[l];
         for (int i = 0; i < nobs; ++i)
-            if (pb.obs_cam[i] < 0 || pb.obs_cam[i] >= ncam) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_cam out of range");
+            if (pb.obs_cam[i] < 0 || pb.obs_cam[i] >= ncam) return "ov2_localba_solve: obs_cam out of range";
         for (int l = 0; l < npts; ++l)
-            if (pb.lm_anchor_cam[l] < 0 || pb.lm_anchor_cam[l] >= ncam) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: lm_anchor_cam out of range");
-        if ((st = host_copy(ctx, hpk + H.off_pose, pbs[k].pose, sizeof(double) * 7 * ncam)) != OV2_OK) return st;
-        if ((st = host_copy(ctx, hpk + H.off_invd, pbs[k].lm_invdepth, sizeof(double) * (size_t)npts)) != OV2_OK) return st;
+            if (pb.lm_anchor_cam[l] < 0 || pb.lm_anchor_cam[l] >= ncam) return "ov2_localba_solve: lm_anchor_cam out of range";
+        if (host_copy(ctx, hpk + H.off_pose, pbs[k].pose, sizeof(double) * 7 * ncam) != OV2_OK) return "ov2_localba_solve: copying the poses failed";
+        if (host_copy(ctx, hpk + H.off_invd, pbs[k].lm_invdepth, sizeof(double) * (size_t)npts) != OV2_OK) return "ov2_localba_solve: copying the inverse depths failed";
         memcpy(hpk + H.off_apx, pb.lm_anchor_px, sizeof(double) * 2 * (size_t)npts);
         memcpy(hpk + H.off_opx, pb.obs_px, sizeof(double) * 2 * (size_t)nobs);
         memcpy(hpk + H.off_lac, pb.lm_anchor_cam, sizeof(int32_t) * (size_t)npts);
@@ -1541,7 +1902,49 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         if (pb.obs_type) memcpy(hpk + H.off_ty, pb.obs_type, (size_t)nobs);
         Prob P;
         fill_prob(&pb, opts, H, din, dwork, P, pb.K, pb.Kr, pb.Trl, stop_flag_dev);
+        if (H.schur_smem == 3) {
+            // stable counting sort of the observations by (anchor keyframe, observing keyframe), cut into chunks of <= PCH
+            int32_t* perm = (int32_t*)(hpk + H.off_pp);
+            int2* chunks = (int2*)(hpk + H.off_pch);
+            std::vector<int32_t> head((size_t)ncam * ncam + 1, 0);
+            for (int i = 0; i < nobs; ++i) head[(size_t)pb.lm_anchor_cam[pb.obs_lm[i]] * ncam + pb.obs_cam[i] + 1]++;
+            for (size_t g = 0; g < (size_t)ncam * ncam; ++g) head[g + 1] += head[g];
+            {
+                std::vector<int32_t> cur(head.begin(), head.end() - 1);
+                for (int i = 0; i < nobs; ++i) perm[cur[(size_t)pb.lm_anchor_cam[pb.obs_lm[i]] * ncam + pb.obs_cam[i]]++] = i;
+            }
+            int nch = 0;
+            for (size_t g = 0; g < (size_t)ncam * ncam; ++g)
+                for (int b = head[g]; b < head[g + 1]; b += PCH) {
+                    if (nch >= H.pch_cap) return "ov2_localba_solve: pair chunk table overflow";
+                    chunks[nch++] = make_int2(b, b + PCH < head[g + 1] ? b + PCH : head[g + 1]);
+                }
+            P.npchunk = nch;
+        }
         memcpy(hpk + H.off_prob, &P, sizeof(P));
+        return nullptr;
+    };
+    {
+        int nthr = nprob >= 8 ? 8 : 1;
+        const unsigned hc = std::thread::hardware_concurrency();
+        if (hc > 0 && (unsigned)nthr > hc) nthr = (int)hc;
+        if (getenv("OV2_BA_PACK_THREADS")) { const int e = atoi(getenv("OV2_BA_PACK_THREADS")); if (e >= 1 && e <= 64) nthr = e; }
+        std::atomic<int> next(0);
+        std::atomic<const char*> perr(nullptr);
+        auto worker = [&]() {
+            for (int k = next.fetch_add(1); k < nprob; k = next.fetch_add(1)) {
+                const char* e = pack_window(k);
+                if (e) { perr.store(e); return; }
+            }
+        };
+        if (nthr <= 1) worker();
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthr; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto& t : pool) t.join();
+        }
+        if (perr.load()) return ov2_fail(ctx, OV2_ERR_INVALID, perr.load());
     }
     // the Prob records must be contiguous for the kernel: they are the first thing of each window's block, so gather them
     std::vector<Prob> parr(nprob);
@@ -1552,11 +1955,8 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     OV2_CUDA(ctx, cudaMemcpyAsync(din, hpk, in_bytes, cudaMemcpyHostToDevice, s));
     if (nprob == 1) dprobs = (Prob*)(din + plans[0].off_prob);
     else OV2_CUDA(ctx, cudaMemcpyAsync(dprobs, parr.data(), sizeof(Prob) * (size_t)nprob, cudaMemcpyHostToDevice, s));   // parr outlives the sync below
-    for (int k = 0; k < nprob; ++k) {
-        const HostPlan& H = plans[k];
-        OV2_CUDA(ctx, cudaMemsetAsync(dwork + H.zero_off, 0, H.zero_bytes, s));
-        OV2_CUDA(ctx, cudaMemsetAsync(dwork + H.w_active, 1, (size_t)(pbs[k].nobs > 0 ? pbs[k].nobs : 1), s));
-    }
+    OV2_CUDA(ctx, cudaMemsetAsync(dwork + zbase, 0, zbytes + obytes, s));   // zero region + output region of every window
+    OV2_CUDA(ctx, cudaMemsetAsync(dwork + abase, 1, abytes, s));            // every observation starts active
     // ---- launch geometry: G CTAs per window, all groups co-resident (cooperative launch)
     {
         // raised only when a window needs more than any before (a function-attribute change while another stream runs the
@@ -1607,25 +2007,25 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     if (ctx->profiling) ov2_prof_end(ctx, "ba_lm_kernel");
     // ---- results: [pose | invd] live in the input block (buffer 0), flags + result record in the work block
     OV2_CUDA(ctx, cudaMemcpyAsync(hpk, din, st_bytes, cudaMemcpyDeviceToHost, s));   // poses and inverse depths of every window: one copy
+    OV2_CUDA(ctx, cudaMemcpyAsync(hout, dwork + obase, obytes, cudaMemcpyDeviceToHost, s));   // Result records + outlier flags: one copy
     std::vector<Result> hres(nprob);
-    std::vector<std::vector<uint8_t>> hflags(nprob);
+    std::vector<char> flags_to_host(nprob, 0);
     for (int k = 0; k < nprob; ++k) {
-        OV2_CUDA(ctx, cudaMemcpyAsync(&hres[k], dwork + plans[k].w_result, sizeof(Result), cudaMemcpyDeviceToHost, s));
         if (outlier_outs && outlier_outs[k] && pbs[k].nobs > 0) {
             if (ov2_is_device_ptr(outlier_outs[k])) {
                 OV2_CUDA(ctx, cudaMemcpyAsync(outlier_outs[k], dwork + plans[k].w_flags, (size_t)pbs[k].nobs, cudaMemcpyDeviceToDevice, s));
             } else {
-                hflags[k].resize(pbs[k].nobs);
-                OV2_CUDA(ctx, cudaMemcpyAsync(hflags[k].data(), dwork + plans[k].w_flags, (size_t)pbs[k].nobs, cudaMemcpyDeviceToHost, s));
+                flags_to_host[k] = 1;
             }
         }
     }
     OV2_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int k = 0; k < nprob; ++k) memcpy(&hres[k], hout + plans[k].out_result, sizeof(Result));
     if (getenv("OV2_BA_TRACE")) {
         unsigned long long tr[16];
         cudaMemcpy(tr, dwork + plans[0].w_trace, sizeof(tr), cudaMemcpyDeviceToHost);
         static const char* names[16] = {"setup0", "A:eval", "B:schur", "B2:fold", "C:solve", "C:wait", "D:backsub", "E:ctl", "scan", "wb", "setup1", "bar0",
-                                        "chol:P1", "chol:bar", "chol:P2", "chol:back"};
+                                        "chol:P1", "chol:bar", "chol:P2", "chol:back|ownerB1"};
         fprintf(stderr, "[ba trace] G=%d grid=%d smem=%zu ncopy=%d smemS=%d |", G, grid, smem_max, plans[0].ncopy, plans[0].schur_smem);
         for (int k = 0; k < 16; ++k) fprintf(stderr, " %s %.1fus", names[k], tr[k] / 1e3);
         fprintf(stderr, "\n");
@@ -1640,7 +2040,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
             if (ov2_is_device_ptr(pbs[k].lm_invdepth)) cudaMemcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib, cudaMemcpyHostToDevice);
             else memcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib);
         }
-        if (!hflags[k].empty()) memcpy(outlier_outs[k], hflags[k].data(), hflags[k].size());
+        if (flags_to_host[k]) memcpy(outlier_outs[k], hout + plans[k].out_flags, (size_t)pbs[k].nobs);
         ov2_ba_result& r = results[k];
         memset(&r, 0, sizeof(r));
         r.iters_robust = hres[k].iters_robust; r.iters_refine = hres[k].iters_refine;

@@ -47,6 +47,10 @@ struct Prob {
     Result* result;
     unsigned long long* trace;         // optional [16] per-phase nanoseconds (OV2_BA_TRACE=1), NULL otherwise
     int ncv_max, ncopy, solve_blocked, smem_work_off, schur_smem, smem_sacc_off;
+    int sg;                            // lanes per landmark in the per-landmark phases (4, 8 or 32)
+    const int32_t* pair_perm;          // [nobs] observation indices sorted by (anchor keyframe, observing keyframe)   (owner mode)
+    const int2* pair_chunk;            // [npchunk] (begin, end) into pair_perm, <= PCH observations of ONE pair each
+    int npchunk;
     size_t blk;
 };
 

@@ -123,11 +123,16 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
         const bool tmpl_aligned = ((reinterpret_cast<uintptr_t>(Iimg) | (uintptr_t)Ipitch) & 3) == 0;
         const int off = kltsetup::stage_patch(lane, Iimg, Ipitch, lw, lh, ix, iy, tmpl_aligned, sP);
         __syncwarp();
-        kltsetup::scharr_rows(lane, sP, off, ix, iy, lw, lh, sD);
-        __syncwarp();
         short Iv[PER_LANE], Ixv[PER_LANE], Iyv[PER_LANE];
         int sA11, sA12, sA22;
-        kltsetup::template_rows(lane, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22);
+        if (tmpl_aligned && kltsetup::patch_interior(ix, iy, lw, lh)) {
+            // interior (warp-uniform): interpolate first, differentiate after - same integers, one pass, no derivative patch
+            kltsetup::template_direct(lane, sP, off, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22);
+        } else {
+            kltsetup::scharr_rows(lane, sP, off, ix, iy, lw, lh, sD);
+            __syncwarp();
+            kltsetup::template_rows(lane, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22);
+        }
         // |b sums| <= max|J - I| * sum|Ix| with |J - I| <= 8160 (both are 8-bit intensities with 5 fractional bits): when
         // 8160 * (sum|Ix| + sum|Iy|) < 2^31 the iterations' mismatch sums fit one exact 32-bit redux each (true for
         // every window whose mean |gradient| is below ~3200 of the possible 8160, i.e. anything but a synthetic

@@ -137,4 +137,86 @@ KLT_HD void template_rows(int lane, const uint8_t* sP, int off, const int* sD, i
     }
 }
 
+// dp2a: signed 16-bit halves of a times UNSIGNED bytes of b (lo: bytes 0, 1; hi: bytes 2, 3), plus c
+KLT_HD int dp2a_lo_su16(unsigned a, unsigned b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return c + (int)(short)(a & 0xFFFFu) * (int)(b & 255u) + (int)(short)(a >> 16) * (int)((b >> 8) & 255u);
+#endif
+}
+KLT_HD int dp2a_hi_su16(unsigned a, unsigned b, int c) {
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return c + (int)(short)(a & 0xFFFFu) * (int)((b >> 16) & 255u) + (int)(short)(a >> 16) * (int)(b >> 24);
+#endif
+}
+KLT_HD unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {   // bytes of hi:lo shifted right by sh bits (sh = 0, 8, 16, 24)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+// Phases 2 + 3 in one for the INTERIOR case (patch_interior(): every Scharr tap is a real pixel, no reflected border and
+// no zero plane).  The bilinear interpolation and the Scharr filter are both exact integer linear maps, so they commute:
+//   bilinear(Scharr(P))  ==  Scharr(W),   W[r][c] = P[r][c] iw00 + P[r][c+1] iw01 + P[r+1][c] iw10 + P[r+1][c+1] iw11
+// with W <= 255 * 16385 (22 bits) and the Scharr sums of W below 2^27: same integers as template_rows() produces from the
+// int16 derivative planes, then the same roundings (I: (W + 2^8) >> 9, Ix / Iy: (. + 2^13) >> 14).  A lane forms the 3 x 5 W
+// values around its three pixels straight from the staged bytes with dp2a; nothing is written to sD and no second
+// __syncwarp is needed.  Lane l < 27 owns window pixels (l / 3, 3 (l % 3) ..+2) as in template_rows().
+KLT_HD void template_direct(int lane, const uint8_t* sP, int off, int iw00, int iw01, int iw10, int iw11,
+                            short* Iv, short* Ixv, short* Iyv, int& sA11, int& sA12, int& sA22) {
+    sA11 = 0; sA12 = 0; sA22 = 0;
+    Iv[0] = Iv[1] = Iv[2] = 0; Ixv[0] = Ixv[1] = Ixv[2] = 0; Iyv[0] = Iyv[1] = Iyv[2] = 0;
+    if (lane >= 27) return;
+    const int y = lane / 3, x0 = 3 * (lane - 3 * y);
+    const unsigned W01 = ((unsigned)iw00 & 0xFFFFu) | ((unsigned)iw01 << 16);
+    const unsigned W23 = ((unsigned)iw10 & 0xFFFFu) | ((unsigned)iw11 << 16);
+    // neighbourhood rows y .. y+3, bytes bo .. bo+5 of each 16-byte row (bo = off + x0 <= 9)
+    const int bo = off + x0, wi = bo >> 2;
+    const unsigned sh = (unsigned)(bo & 3) * 8u;
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(sP + (y + r) * SP_PITCH);
+        const unsigned w0 = rw[wi], w1 = rw[wi + 1], w2 = wi < 2 ? rw[wi + 2] : 0u;
+        lo[r] = funnel_r(w0, w1, sh);      // bytes bo .. bo+3
+        hi[r] = funnel_r(w1, w2, sh);      // bytes bo+4 .. bo+7 (only bo+4, bo+5 are used)
+    }
+    int W[3][5];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const unsigned t = lo[r], b = lo[r + 1];
+        const unsigned t3 = funnel_r(lo[r], hi[r], 24u), b3 = funnel_r(lo[r + 1], hi[r + 1], 24u);
+        W[r][0] = dp2a_lo_su16(W01, t, dp2a_lo_su16(W23, b, 0));
+        W[r][1] = dp2a_lo_su16(W01, t >> 8, dp2a_lo_su16(W23, b >> 8, 0));
+        W[r][2] = dp2a_hi_su16(W01, t, dp2a_hi_su16(W23, b, 0));
+        W[r][3] = dp2a_lo_su16(W01, t3, dp2a_lo_su16(W23, b3, 0));
+        W[r][4] = dp2a_lo_su16(W01, hi[r], dp2a_lo_su16(W23, hi[r + 1], 0));
+    }
+    int vs[5], vd[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        vs[c] = (W[0][c] + W[2][c]) * 3 + W[1][c] * 10;
+        vd[c] = W[2][c] - W[0][c];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ival = (W[1][k + 1] + (1 << 8)) >> 9;
+        const int ixval = (vs[k + 2] - vs[k] + (1 << 13)) >> 14;
+        const int iyval = ((vd[k] + vd[k + 2]) * 3 + vd[k + 1] * 10 + (1 << 13)) >> 14;
+        Iv[k] = (short)ival; Ixv[k] = (short)ixval; Iyv[k] = (short)iyval;
+        sA11 += ixval * ixval;
+        sA12 += ixval * iyval;
+        sA22 += iyval * iyval;
+    }
+}
+
 }  // namespace kltsetup

@@ -13,8 +13,9 @@ from ov2slam_b200 import api, synth  # noqa: E402
 ctx = api.Context(0)
 clone = lambda d: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in d.items()}
 base = [synth.make_ba_problem(100 + i, 10, 2000, 8000) for i in range(8)]
-for K in (64, 128, 148, 296, 592):
-    for ctas in (None, "1", "2", "4"):
+KS = [int(a) for a in sys.argv[1:]] or [64, 128, 148, 296, 592]
+for K in KS:
+    for ctas in ((None,) if len(sys.argv) > 1 else (None, "1", "2", "4")):
         if ctas is None:
             os.environ.pop("OV2_BA_CTAS", None)
         else:

@@ -13,10 +13,10 @@ opt = api.Optimizer(ctx)
 clone = lambda d: {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in d.items()}
 c3 = synth.make_ba_problem(3, 10, 2000, 8000)
 c5 = synth.make_ba_problem(5, 50, 20000, 150000)
-for smem in ("2", "0"):
+for smem in ("3", "2", "0"):
     os.environ["OV2_BA_SCHUR_SMEM"] = smem
-    for name, pb, gs in (("C3", c3, ("64", "148", "296")), ("C5", c5, ("296",))):
-        if name == "C5" and smem == "0":
+    for name, pb, gs in (("C3", c3, ("16", "32", "64", "148")), ("C5", c5, ("296",))):
+        if name == "C5" and smem != "2":
             continue
         for g in gs:
             os.environ["OV2_BA_CTAS"] = g

@@ -666,3 +666,39 @@ def test_c4_full_chain_stereo_1280x720(ctx):
     assert sst.mean() > 0.5 and nst[:n].mean() > 0.5
     for p in list(raw.values()) + list(pyr.values()):
         p.close()
+
+
+@pytest.mark.parametrize("w,h,level", [(640, 480, 3), (1280, 720, 3), (333, 245, 1)])
+def test_line_min_sad_batch_bit_exact(ctx, w, h, level):
+    """8f-3: the batched stereo prior (ov2_line_min_sad) against the restatement of FeatureTracker::getLineMinSAD
+    (feature_tracker.cpp:138-204) on the same pyramid level: identical columns and errors, both scan directions, sub-pixel
+    points, the border window shrink, window sizes 7 (the reference's) / 5 / 9, empty slots."""
+    left = synth.make_frame(91, w, h, nrect=80)
+    right = np.ascontiguousarray(np.roll(left, -9, axis=1))
+    right[:, -9:] = np.random.default_rng(1).integers(0, 256, (h, 9)).astype(np.uint8)
+    pl = api.Pyramid(ctx, 1, w, h, 3)
+    pr = api.Pyramid(ctx, 1, w, h, 3)
+    pl.build(left[None])
+    pr.build(right[None])
+    L, Rr = pl.download(0, level), pr.download(0, level)
+    lh, lw = L.shape
+    rng = np.random.default_rng(4)
+    n = 120
+    pts = (rng.random((n, 2)) * [lw - 1, lh - 1]).astype(np.float32)
+    pts[:10] = np.rint(pts[:10])
+    pts[10:16] = [[2.3, lh / 2], [lw - 2.2, lh / 3], [lw / 2 + 0.5, 1.4], [lw / 2 + 0.5, lh - 1.6], [0.4, 0.3], [lw - 1.0, lh - 1.0]]
+    pts[16] = [-1, -1]
+    ft = api.FeatureTracker(ctx)
+    for ws, gl in ((7, True), (7, False), (5, True), (9, False)):
+        xp = np.full(n, 7.0, np.float32)
+        er = np.full(n, 7.0, np.float32)
+        ft.line_min_sad(pl, pr, level, pts, ws, gl, xp, er)
+        for i in range(n):
+            rx, re = R.line_min_sad_ref(L, Rr, pts[i], ws, gl)
+            assert np.float32(xp[i]) == np.float32(rx), (ws, gl, i, pts[i], xp[i], rx)
+            assert np.float32(er[i]) == np.float32(255.0 if re is None else re), (ws, gl, i, er[i], re)
+        assert (xp >= 0).sum() > 0.8 * n
+    with pytest.raises(Exception):
+        ft.line_min_sad(pl, pr, level, pts, 8, True, xp, er)      # even window: the reference refuses too
+    pl.close()
+    pr.close()

@@ -153,6 +153,19 @@ int main() {
       }
     }
     if (A11 != g11 || A12 != g12 || A22 != g22) bad++;
+    // interior fast path: template_direct (interpolate first, differentiate after) must give the same integers
+    if (aligned && patch_interior(ix, iy, lw, lh)) {
+      long d11 = 0, d12 = 0, d22 = 0;
+      for (int l = 0; l < 32; ++l) {
+        short Iv[3], Ix[3], Iy[3], Jv[3], Jx[3], Jy[3]; int s11, s12, s22, t11, t12, t22;
+        template_rows(l, sP, off, sD, iw00, iw01, iw10, iw11, Iv, Ix, Iy, s11, s12, s22);
+        template_direct(l, sP, off, iw00, iw01, iw10, iw11, Jv, Jx, Jy, t11, t12, t22);
+        for (int k = 0; k < 3; ++k) if (Iv[k] != Jv[k] || Ix[k] != Jx[k] || Iy[k] != Jy[k]) bad++;
+        if (s11 != t11 || s12 != t12 || s22 != t22) bad++;
+        d11 += t11; d12 += t12; d22 += t22;
+      }
+      if (A11 != d11 || A12 != d12 || A22 != d22) bad++;
+    }
   }
   printf("%%ld bad, %%ld interior, %%ld border\n", bad, n_int, n_brd);
   return (bad || n_int < 1000 || n_brd < 1000) ? 1 : 0;

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from ov2slam_b200 import api, build, synth
+from oracle import image_ref as R_img
 
 
 def test_host_shims_compile_and_link():
@@ -45,55 +46,8 @@ def test_host_shims_match_python_binding(ctx, tmp_path):
     assert got["ngood"] == int(st.sum())
 
 
-def _rect_subpix_template(src, ws, cx, cy):
-    """cv::getRectSubPix 8u->8u as OpenCV's own template computes it (imgproc/samplers.cpp: 16-bit fixed-point bilinear
-    weights, (sum + 2^15) >> 16, replicated border) - float32 arithmetic mirrored step by step."""
-    f = np.float32
-    cx = f(cx) - f((ws - 1) * 0.5)
-    cy = f(cy) - f((ws - 1) * 0.5)
-    ipx, ipy = int(np.floor(cx)), int(np.floor(cy))
-    a, b = f(cx - f(ipx)), f(cy - f(ipy))
-    one = f(1.0)
-    rnd = lambda v: int(np.rint(f(v)))
-    a11, a12 = rnd((one - a) * (one - b) * f(65536)), rnd(a * (one - b) * f(65536))
-    a21, a22 = rnd((one - a) * b * f(65536)), rnd(a * b * f(65536))
-    h, w = src.shape
-    ys = np.clip(np.arange(ipy, ipy + ws + 1), 0, h - 1)
-    xs = np.clip(np.arange(ipx, ipx + ws + 1), 0, w - 1)
-    p = src[np.ix_(ys, xs)].astype(np.int64)
-    v = p[:-1, :-1] * a11 + p[:-1, 1:] * a12 + p[1:, :-1] * a21 + p[1:, 1:] * a22
-    return ((v + (1 << 15)) >> 16).astype(np.uint8)
-
-
-def _line_min_sad_ref(iml, imr, pt, nwinsize, goleft, subpix):
-    """FeatureTracker::getLineMinSAD (/root/reference/src/feature_tracker.cpp:138-204) restated; `subpix` = the
-    getRectSubPix to use (the OpenCV template above, or cv2's)."""
-    f = np.float32
-    if nwinsize % 2 == 0:
-        return -1.0, None
-    x, y = f(pt[0]), f(pt[1])
-    hw = nwinsize // 2
-    rows, cols = imr.shape
-    if x - hw < 0:
-        hw = int(f(hw) + (x - f(hw)))
-    if x + hw >= cols:
-        hw = int(f(hw) + (x + f(hw) - f(cols) - f(1)))
-    if y - hw < 0:
-        hw = int(f(hw) + (y - f(hw)))
-    if y + hw >= rows:
-        hw = int(f(hw) + (y + f(hw) - f(rows) - f(1)))
-    if hw <= 0:
-        return -1.0, None
-    ws = 2 * hw + 1
-    patch = subpix(iml, ws, x, y).astype(np.int64)
-    minsad, xprior = f(255.0), f(-1.0)
-    c = x
-    while (c >= hw) if goleft else (c < cols - hw):
-        e = f(f(np.abs(patch - subpix(imr, ws, c, y).astype(np.int64)).sum()) / f(ws * ws))
-        if e < minsad:
-            minsad, xprior = e, c
-        c = f(c - f(1)) if goleft else f(c + f(1))
-    return float(xprior), float(minsad)
+_rect_subpix_template = R_img.get_rect_subpix_u8_ref
+_line_min_sad_ref = R_img.line_min_sad_ref
 
 
 def test_get_line_min_sad_matches_the_reference_function():
