@@ -293,7 +293,9 @@ typedef struct {
 /* outlier_out (optional): [nobs] bytes, bit0 = flagged after solve #1, bit1 = after solve #2.
  * The whole two-stage solve (both Ceres solves, every LM iteration, both outlier scans) is ONE kernel launch with the
  * trust-region controller on the device (csrc/ba_lm.cu); OV2_BA_LEGACY=1 selects the round-1 path (one launch per phase,
- * controller on the host) as a cross-check.  At most 64 optimised and 256 total keyframes per window. */
+ * controller on the host) as a cross-check.  At most 64 optimised and 256 total keyframes per window.
+ * Residency of a window's arrays is decided on `pose`: host poses = every array of the window (and outlier_out) is host
+ * memory, the reference's flow; device poses = each array is inspected and may be either. */
 OV2_API ov2_status ov2_localba_solve(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
                              ov2_ba_result* res, uint8_t* outlier_out);
 

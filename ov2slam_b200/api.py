@@ -492,14 +492,32 @@ class Optimizer:
         return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags
 
 
+_BA_KEYS = ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px")
+_BA_RES_DTYPE = np.dtype([("iters_robust", np.int32), ("iters_refine", np.int32), ("initial_cost", np.float64), ("final_cost", np.float64),
+                          ("n_outliers_first", np.int32), ("n_outliers_second", np.int32), ("termination", np.int32), ("_pad", np.int32)])
+assert _BA_RES_DTYPE.itemsize == C.sizeof(BaResult)
+
+
+def _c_array(a):
+    """a itself when it already is a C-contiguous ndarray (the usual case: no copy, no new object), a contiguous copy otherwise."""
+    return a if isinstance(a, np.ndarray) and a.flags.c_contiguous else np.ascontiguousarray(a)
+
+
+def _addr(a: np.ndarray) -> int:
+    """Address of a contiguous ndarray's first byte (3x cheaper than a.ctypes.data; read-only or empty arrays take that route)."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):
+        return a.ctypes.data
+
+
 def _ba_problem_struct(pb: dict, keep: dict) -> BaProblem:
-    for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px"):
-        keep[k] = np.ascontiguousarray(pb[k])
+    for k in _BA_KEYS:
+        keep[k] = _c_array(pb[k])
     assert keep["pose"].dtype == np.float64 and keep["obs_px"].dtype == np.float64 and keep["lm_invdepth"].dtype == np.float64
     assert keep["obs_cam"].dtype == np.int32 and keep["obs_lm"].dtype == np.int32 and keep["pose_const"].dtype == np.uint8
     return BaProblem(len(keep["pose"]), len(keep["lm_invdepth"]), len(keep["obs_cam"]),
-                     *[keep[k].ctypes.data for k in ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
-                                                     "obs_cam", "obs_lm", "obs_px")], *_stereo_ptrs(pb, keep))
+                     *[_addr(keep[k]) for k in _BA_KEYS], *_stereo_ptrs(pb, keep))
 
 
 def local_ba_batch(ctx: Context, pbs: list, **opts):
@@ -512,14 +530,22 @@ def local_ba_batch(ctx: Context, pbs: list, **opts):
     keeps = [dict() for _ in pbs]
     arr = (BaProblem * n)(*[_ba_problem_struct(pb, kp) for pb, kp in zip(pbs, keeps)])
     res = (BaResult * n)()
-    flags = [np.zeros(max(len(kp["obs_cam"]), 1), np.uint8) for kp in keeps]
-    fl = (C.c_void_p * n)(*[f.ctypes.data for f in flags])
+    nobs = [len(kp["obs_cam"]) for kp in keeps]
+    offs = np.concatenate([[0], np.cumsum([max(v, 1) for v in nobs])]).astype(np.int64)
+    allflags = np.zeros(int(offs[-1]), np.uint8)                      # one buffer, one slice per window
+    base = _addr(allflags)
+    fl = (C.c_void_p * n)(*[base + int(v) for v in offs[:-1]])
     ctx.check(ctx.lib.ov2_localba_solve_batch(ctx.h, n, arr, C.byref(bo), res, fl))
     for pb, kp in zip(pbs, keeps):
-        pb["pose"][...] = kp["pose"]
-        pb["lm_invdepth"][...] = kp["lm_invdepth"]
-    return ([{f: getattr(r, f) for f, _ in BaResult._fields_} for r in res],
-            [f[:len(kp["obs_cam"])] for f, kp in zip(flags, keeps)])
+        if kp["pose"] is not pb["pose"]:
+            pb["pose"][...] = kp["pose"]
+        if kp["lm_invdepth"] is not pb["lm_invdepth"]:
+            pb["lm_invdepth"][...] = kp["lm_invdepth"]
+    rec = np.frombuffer(res, dtype=_BA_RES_DTYPE, count=n)
+    names = [f for f, _ in BaResult._fields_]
+    cols = [rec[f].tolist() for f in names]
+    return ([dict(zip(names, row)) for row in zip(*cols)],
+            [allflags[int(offs[i]):int(offs[i]) + nobs[i]] for i in range(n)])
 
 
 def request_stop_local_ba(ctx: Context, stop: bool = True):

@@ -505,9 +505,20 @@ __device__ __forceinline__ void schur_landmark(const Prob& P, const int* __restr
 //       owns a chunk, its lanes own the 78 + 12 entries (upper triangle + gradient), the chunk's Jacobian rows pass through the
 //       warp's staging slice of shared memory, and the chunk's totals leave as <= 102 REDs (was ~89 per observation).
 //   B2  landmark part: SG lanes per landmark form ete / g_e and the landmark's E'F row as a DENSE n-vector in a shared-memory
-//       tile (one row per landmark, 32 / SG rows per warp); then S -= sum_rows w y y', rhs -= sum_rows w g_e y with every
-//       thread owning 3 x 3 register tiles of the upper triangle over ALL rounds (no atomics at all), flushed once per phase.
+//       tile (one row per landmark, 32 / SG rows per warp); then S -= sum_rows w y y', rhs -= sum_rows w g_e y on the FP64
+//       tensor cores, every warp owning 8 x 8 tiles of the upper triangle over ALL rounds (no atomics at all), flushed once.
 constexpr int PCH = 32;           // observations per pair chunk
+
+// FP64 tensor-core tile product (DMMA): D(8x8) = A(8x4) B(4x8) + C.  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
+// lane = 4 g + t; A: (row g, col t); B: (row t, col g); C/D: (row g, cols 2t, 2t+1).
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// pitch (doubles) of the owner-mode landmark tile: >= n rounded up to 8, congruent 4 mod 16
+__host__ __device__ __forceinline__ int owner_tile_pitch(int n) {
+    const int n8 = (n + 7) & ~7;
+    return n8 + ((4 - n8) % 16 + 16) % 16;
+}
 
 template <int SG>
 __device__ __forceinline__ void owner_fill_row(const Prob& P, const int* __restrict__ s_slot, int l, int sl, bool in, double radius, int first_iter,
@@ -617,15 +628,26 @@ __device__ __noinline__ void schur_owner_phase(const Prob& P, const int* __restr
             // the whole chunk's rows [Ja | Jo | r] go to this warp's staging slice with every load in flight at once (staging
             // four observations at a time left the phase waiting on one L2 round trip per stage: 4.1 ms of a batched C3 solve)
             __syncwarp();
-            for (int e0 = 0; e0 < cnt * 26; e0 += 32) {             // uniform trip count: the shuffles need every lane
-                const int e = e0 + lane;
-                const bool ok = e < cnt * 26;
-                const int q = ok ? e / 26 : 0, k = e - 26 * q;
-                const int p = __shfl_sync(FULL, pq, q);
-                const int on = __shfl_sync(FULL, onq, q);
-                if (ok) {
-                    const double v = k < 12 ? P.Ja[12 * (size_t)p + k] : (k < 24 ? P.Jo[12 * (size_t)p + (k - 12)] : P.Jr[2 * (size_t)p + (k - 24)]);
-                    st[e] = on ? v : 0.0;
+            // (two unrolled halves of 13 loads per lane: every load of a half is issued before the first store needs its value -
+            //  a rolled load -> store loop waited one L2 round trip per element, 14.6 us per chunk)
+            const int tot = cnt * 26;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double vals[13];
+#pragma unroll
+                for (int j = 0; j < 13; ++j) {
+                    const int e = (half * 13 + j) * 32 + lane;
+                    const bool ok = e < tot;
+                    const int q = ok ? e / 26 : 0, k = e - 26 * q;
+                    const int p = __shfl_sync(FULL, pq, q);
+                    const int on = __shfl_sync(FULL, onq, q);
+                    const double* src = k < 12 ? P.Ja + 12 * (size_t)p + k : (k < 24 ? P.Jo + 12 * (size_t)p + (k - 12) : P.Jr + 2 * (size_t)p + (k - 24));
+                    vals[j] = (ok && on) ? *src : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 13; ++j) {
+                    const int e = (half * 13 + j) * 32 + lane;
+                    if (e < tot) st[e] = vals[j];
                 }
             }
             __syncwarp();
@@ -669,28 +691,31 @@ __device__ __noinline__ void schur_owner_phase(const Prob& P, const int* __restr
     __syncthreads();
     if (tracing) P.trace[15] += global_ns() - t_b1;                 // trace slot 15 = B1 share of B:schur in this mode
     // ---------------- B2: landmark part
+    // S -= sum_rows w y y' is the one contraction of this phase: FP64 tensor cores (DMMA m8n8k4), a warp owns up to NT 8 x 8
+    // tiles of the upper triangle and keeps their accumulators in registers over ALL rounds; per 4-row step and tile two
+    // shared-memory loads (tile pitch = 4 mod 16 doubles: conflict-free half-warps) and one DMMA.
     constexpr int R = WARPS * (32 / SG);                            // tile rows (landmarks per round and CTA)
-    const int TP = n + 2;
+    const int TP = owner_tile_pitch(n);
     double* tw = s_tile + (size_t)R * TP;
     double* tg = tw + R;
-    const int nt3 = n / 3, ntile = nt3 * (nt3 + 1) / 2;
-    int ti[NT], tj[NT];
-    double acc[NT][9];
+    const int nb8 = (n + 7) >> 3, ntile = nb8 * (nb8 + 1) / 2;
+    int bi[NT], bj[NT];
+    double acc[NT][2];
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
-        const int t = tid + THREADS * k;
-        ti[k] = -1; tj[k] = 0;
+        const int t = warp + WARPS * k;
+        bi[k] = -1; bj[k] = 0;
         if (t < ntile) {
             int i = 0, rem = t;
-            while (rem >= nt3 - i) { rem -= nt3 - i; ++i; }
-            ti[k] = i; tj[k] = i + rem;
+            while (rem >= nb8 - i) { rem -= nb8 - i; ++i; }
+            bi[k] = i; bj[k] = i + rem;
         }
-#pragma unroll
-        for (int e = 0; e < 9; ++e) acc[k][e] = 0.0;
+        acc[k][0] = 0.0; acc[k][1] = 0.0;
     }
     double racc = 0.0, gmax_lm = 0.0;
     const int sub = lane / SG, sl = lane - sub * SG;
     const int myrow = warp * (32 / SG) + sub;
+    const int fg = lane >> 2, ft = lane & 3;                        // DMMA fragment coordinates
     for (int l0 = bid * R; l0 < P.npts; l0 += G * R) {
         for (int e = tid; e < R * TP + 2 * R; e += THREADS) s_tile[e] = 0.0;
         __syncthreads();
@@ -702,32 +727,31 @@ __device__ __noinline__ void schur_owner_phase(const Prob& P, const int* __restr
         }
         __syncthreads();
         const int rows = min(R, P.npts - l0);
-        for (int r = 0; r < rows; ++r) {
-            const double w = tw[r];
-            if (w == 0.0) continue;                                  // landmark dropped from the program (uniform)
-            const double* y = s_tile + (size_t)r * TP;
+        for (int k0 = 0; k0 < rows; k0 += 4) {                      // rows beyond `rows` are zero rows with w = 0
+            const double* yk = s_tile + (size_t)(k0 + ft) * TP;
+            const double wv = tw[k0 + ft];
 #pragma unroll
             for (int k = 0; k < NT; ++k) {
-                if (ti[k] < 0) continue;
-                const double yi0 = y[3 * ti[k]] * w, yi1 = y[3 * ti[k] + 1] * w, yi2 = y[3 * ti[k] + 2] * w;
-                const double yj0 = y[3 * tj[k]], yj1 = y[3 * tj[k] + 1], yj2 = y[3 * tj[k] + 2];
-                acc[k][0] -= yi0 * yj0; acc[k][1] -= yi0 * yj1; acc[k][2] -= yi0 * yj2;
-                acc[k][3] -= yi1 * yj0; acc[k][4] -= yi1 * yj1; acc[k][5] -= yi1 * yj2;
-                acc[k][6] -= yi2 * yj0; acc[k][7] -= yi2 * yj1; acc[k][8] -= yi2 * yj2;
+                if (bi[k] < 0) continue;                            // warp-uniform
+                dmma_884(acc[k][0], acc[k][1], yk[8 * bi[k] + fg] * wv, yk[8 * bj[k] + fg]);
             }
-            if (tid < n) racc -= y[tid] * (w * tg[r]);
+        }
+        if (tid < n) {
+            double ra = 0.0;
+            for (int r = 0; r < rows; ++r) ra += s_tile[(size_t)r * TP + tid] * (tw[r] * tg[r]);
+            racc -= ra;
         }
         __syncthreads();
     }
     // flush: every upper-triangle entry of this CTA's partial system has exactly one owner
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
-        if (ti[k] < 0) continue;
+        if (bi[k] < 0) continue;
 #pragma unroll
-        for (int e = 0; e < 9; ++e) {
-            const int r = 3 * ti[k] + e / 3, c = 3 * tj[k] + e % 3;
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * bi[k] + fg, c = 8 * bj[k] + 2 * ft + e;
             const double v = acc[k][e];
-            if (r <= c && v != 0.0) red_add_f64(cS + (size_t)r * n + c, v);
+            if (r <= c && c < n && v != 0.0) red_add_f64(cS + (size_t)r * n + c, -v);
         }
     }
     if (tid < n && racc != 0.0) red_add_f64(cRhs + tid, racc);
@@ -820,11 +844,6 @@ __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radi
 }
 
 // ------------------------------------------------------------------ reduced camera system, n > 96: blocked Cholesky (one CTA)
-// FP64 tensor-core tile product (DMMA): D(8x8) = A(8x4) B(4x8) + C.  Fragment layout (PTX ISA, mma.m8n8k4 .f64):
-// lane = 4 g + t; A: (row g, col t); B: (row t, col g); C/D: (row g, cols 2t, 2t+1).
-__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // ------------------------------------------------------------------ reduced camera system, n > 96: blocked Cholesky across the group
 // Same factorisation as reduced_solve_blocked, but only the sequential part of a block step stays on CTA 0 (diagonal
@@ -1295,15 +1314,13 @@ __global__ void __launch_bounds__(THREADS, 2) ba_lm_kernel(const Prob* __restric
                 // ---- B: Schur elimination into this CTA's accumulation copy (global, RED) or shared-memory block (lock)
                 if (P.schur_smem == 3) {
                     // owner mode (n <= 96): pair-sorted Gram blocks + dense landmark rows, no per-observation reductions
-                    if (n <= 66) {
-                        if (P.sg == 4) schur_owner_phase<1, 4>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                        else if (P.sg == 8) schur_owner_phase<1, 8>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                        else schur_owner_phase<1, 32>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                    } else {
-                        if (P.sg == 4) schur_owner_phase<3, 4>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                        else if (P.sg == 8) schur_owner_phase<3, 8>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                        else schur_owner_phase<3, 32>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal);
-                    }
+#define OV2_OWNER(NT_) do { if (P.sg == 4) schur_owner_phase<NT_, 4>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal); \
+                            else if (P.sg == 8) schur_owner_phase<NT_, 8>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal); \
+                            else schur_owner_phase<NT_, 32>(P, s_slot, s_work, n, radius, first_iter, bid, G, scal); } while (0)
+                    if (n <= 48) OV2_OWNER(3);            // 21 upper 8 x 8 tiles over 8 warps
+                    else if (n <= 72) OV2_OWNER(6);       // 45
+                    else OV2_OWNER(10);                   // 78 (n = 96)
+#undef OV2_OWNER
                 } else if (P.schur_smem == 2) {
                     // per-WARP private copies of [rhs | F'r | column norms | S] in shared memory: plain read-modify-writes, no
                     // lock, no RED; the CTA sums its copies and sends the non-zeros to the global block once per phase
@@ -1723,7 +1740,7 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
     // Schur phase at 148 CTAs - there the phase is latency, not RED bound); batches (1-2 CTAs per window) take mode 3.
     if (H.n_max > 0 && H.n_max <= 96 && ((ssm && atoi(ssm) == 3) || (!ssm && !(single_window && H.schur_smem == 2)))) {
         const size_t R = (size_t)WARPS * (32 / H.sg);
-        size_t tile = (R * (size_t)(H.n_max + 2) + 2 * R) * sizeof(double);
+        size_t tile = (R * (size_t)owner_tile_pitch(H.n_max) + 2 * R) * sizeof(double);
         const size_t stage = (size_t)WARPS * PCH * 26 * sizeof(double);
         if (tile < stage) tile = stage;
         H.schur_smem = 3;
@@ -1787,9 +1804,9 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.smem_work_off = (int)H.smem_work_off;
 }
 
-static ov2_status host_copy(ov2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+static ov2_status host_copy(ov2_ctx* ctx, void* dst, const void* src, size_t bytes, bool maybe_device = true) {
     if (bytes == 0) return OV2_OK;
-    if (ov2_is_device_ptr(src)) OV2_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    if (maybe_device && ov2_is_device_ptr(src)) OV2_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     else memcpy(dst, src, bytes);
     return OV2_OK;
 }
@@ -1804,6 +1821,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     std::vector<HostPlan> plans(nprob);
     std::vector<ov2_ba_problem> hp(nprob);           // host-resident views of every window (device inputs are copied down)
     std::vector<std::vector<char>> hold;              // storage for inputs that came as device pointers
+    std::vector<char> win_on_device(nprob, 0);
     size_t st_off = 0, in_off = 0, work_off = 0, zero_off = 0, out_off = 0, act_off = 0;
     size_t smem_max = 0;
     int gmax_work = 1;
@@ -1814,8 +1832,13 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         hp[k] = pb;
         // the flattened window is host data in the reference's flow (optimizer.cpp:43-430); device-resident inputs are
         // accepted and staged through the host once (the solve itself never leaves the device)
+        // cudaPointerGetAttributes costs ~1.5 us on a plain host pointer: 15 queries per window were 6 ms of a 296-window batch.
+        // One query per window: a window whose `pose` array is host memory is taken to be host memory throughout (the
+        // reference's flow, optimizer.cpp:43-430); only windows whose poses live on the device are inspected array by array.
+        const bool win_dev = ov2_is_device_ptr(pb.pose);
+        win_on_device[k] = win_dev ? 1 : 0;
         auto pull = [&](const void* p, size_t bytes) -> const void* {
-            if (!p || bytes == 0 || !ov2_is_device_ptr(p)) return p;
+            if (!p || bytes == 0 || !win_dev || !ov2_is_device_ptr(p)) return p;
             hold.emplace_back(bytes);
             cudaMemcpy(hold.back().data(), p, bytes, cudaMemcpyDeviceToHost);
             return hold.back().data();
@@ -1891,8 +1914,8 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
             if (pb.obs_cam[i] < 0 || pb.obs_cam[i] >= ncam) return "ov2_localba_solve: obs_cam out of range";
         for (int l = 0; l < npts; ++l)
             if (pb.lm_anchor_cam[l] < 0 || pb.lm_anchor_cam[l] >= ncam) return "ov2_localba_solve: lm_anchor_cam out of range";
-        if (host_copy(ctx, hpk + H.off_pose, pbs[k].pose, sizeof(double) * 7 * ncam) != OV2_OK) return "ov2_localba_solve: copying the poses failed";
-        if (host_copy(ctx, hpk + H.off_invd, pbs[k].lm_invdepth, sizeof(double) * (size_t)npts) != OV2_OK) return "ov2_localba_solve: copying the inverse depths failed";
+        if (host_copy(ctx, hpk + H.off_pose, pbs[k].pose, sizeof(double) * 7 * ncam, win_on_device[k] != 0) != OV2_OK) return "ov2_localba_solve: copying the poses failed";
+        if (host_copy(ctx, hpk + H.off_invd, pbs[k].lm_invdepth, sizeof(double) * (size_t)npts, win_on_device[k] != 0) != OV2_OK) return "ov2_localba_solve: copying the inverse depths failed";
         memcpy(hpk + H.off_apx, pb.lm_anchor_px, sizeof(double) * 2 * (size_t)npts);
         memcpy(hpk + H.off_opx, pb.obs_px, sizeof(double) * 2 * (size_t)nobs);
         memcpy(hpk + H.off_lac, pb.lm_anchor_cam, sizeof(int32_t) * (size_t)npts);
@@ -2012,7 +2035,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     std::vector<char> flags_to_host(nprob, 0);
     for (int k = 0; k < nprob; ++k) {
         if (outlier_outs && outlier_outs[k] && pbs[k].nobs > 0) {
-            if (ov2_is_device_ptr(outlier_outs[k])) {
+            if (win_on_device[k] && ov2_is_device_ptr(outlier_outs[k])) {
                 OV2_CUDA(ctx, cudaMemcpyAsync(outlier_outs[k], dwork + plans[k].w_flags, (size_t)pbs[k].nobs, cudaMemcpyDeviceToDevice, s));
             } else {
                 flags_to_host[k] = 1;
@@ -2034,10 +2057,10 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     for (int k = 0; k < nprob; ++k) {
         const HostPlan& H = plans[k];
         const size_t pb_bytes = sizeof(double) * 7 * pbs[k].ncam, ib = sizeof(double) * (size_t)pbs[k].npts;
-        if (ov2_is_device_ptr(pbs[k].pose)) cudaMemcpy(pbs[k].pose, hpk + H.off_pose, pb_bytes, cudaMemcpyHostToDevice);
+        if (win_on_device[k]) cudaMemcpy(pbs[k].pose, hpk + H.off_pose, pb_bytes, cudaMemcpyHostToDevice);
         else memcpy(pbs[k].pose, hpk + H.off_pose, pb_bytes);
         if (ib) {
-            if (ov2_is_device_ptr(pbs[k].lm_invdepth)) cudaMemcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib, cudaMemcpyHostToDevice);
+            if (win_on_device[k] && ov2_is_device_ptr(pbs[k].lm_invdepth)) cudaMemcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib, cudaMemcpyHostToDevice);
             else memcpy(pbs[k].lm_invdepth, hpk + H.off_invd, ib);
         }
         if (flags_to_host[k]) memcpy(outlier_outs[k], hout + plans[k].out_flags, (size_t)pbs[k].nobs);
