@@ -111,8 +111,8 @@ def build_optimizer_shim(verbose: bool = False) -> Path:
         obj = LIB / "obj" / (name + ".o")
         src = host / name
         if _newer(src, obj) or any(d.is_file() and _newer(d, obj) for d in deps):
-            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", str(host / "standin" / "ref"), "-I", str(host / "standin"),
-                   "-c", str(src), "-o", str(obj)]
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-DOV2_EXTERNAL_LOOSE_FULL_BA", "-I", str(host / "standin" / "ref"),
+                   "-I", str(host / "standin"), "-c", str(src), "-o", str(obj)]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)

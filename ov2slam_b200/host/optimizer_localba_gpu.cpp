@@ -21,7 +21,9 @@
 #include <atomic>
 #include <chrono>
 #include <iostream>
+#include <algorithm>
 #include <map>
+#include <set>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -69,6 +71,86 @@ struct Window {
     }
 };
 
+
+// Landmarks of the window: the first valid observer (ascending keyframe id) anchors the inverse depth, every further observer
+// contributes one residual block (two for a stereo keypoint); observers outside the window join it as constant keyframes.
+// The same loop body in localBA (optimizer.cpp:191-392), looseBA (:1023-1226) and fullBA (:1794-1990).
+void flatten_landmarks(MapManager& map, Window& win, const std::vector<int>& lm_order, const int newest, const bool stereo) {
+    MapManager* pmap_ = &map;
+    for (int lmid : lm_order) {
+        auto lm = pmap_->getMapPoint(lmid);
+        if (!lm || lm->isBad()) continue;
+        int anchor_cam = -1;
+        const int l = (int)win.lmids.size();
+        for (int kfid : lm->getKfObsSet()) {
+            if (kfid > newest) continue;
+            auto cit = win.cam_of_kf.find(kfid);
+            std::shared_ptr<Frame> kf = cit != win.cam_of_kf.end() ? win.kfs[cit->second] : pmap_->getKeyframe(kfid);
+            if (!kf) { pmap_->removeMapPointObs(kfid, lmid); continue; }
+            const int cam = win.add_camera(kfid, kf, /*constant=*/cit == win.cam_of_kf.end());
+            const auto kp = kf->getKeypointById(lmid);
+            if (kp.lmid_ != lmid) { pmap_->removeMapPointObs(lmid, kfid); continue; }
+            // kp.scale_ is 0 for every keypoint the reference's front-end creates (map_manager.cpp adds
+            // keypoints without a scale), so the residuals' information matrix 2^-scale * I is the identity
+            if (anchor_cam < 0) {
+                anchor_cam = cam;
+                win.lmids.push_back(lmid);
+                win.lms.push_back(lm);
+                win.lm_anchor_cam.push_back(cam);
+                win.lm_anchor_px.push_back(kp.unpx_.x);
+                win.lm_anchor_px.push_back(kp.unpx_.y);
+                win.lm_invdepth.push_back(1.0 / (kf->getTcw() * lm->getPoint()).z());
+                // the anchor's own right-camera observation constrains the inverse depth alone (optimizer.cpp:268-284)
+                if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 2);
+                continue;
+            }
+            win.add_obs(cam, l, kp.unpx_.x, kp.unpx_.y, 0);            // appended landmark by landmark: already sorted
+            if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 1);   // (optimizer.cpp:295-324)
+        }
+    }
+}
+
+// Gauge (at least two constant keyframes in mono, one in stereo: optimizer.cpp:65-69, 396-407 / :1228-1239 / :1992-2003; the
+// reference walks an unordered_map there, ascending keyframe id is used here) and the solver's capacity (64 optimised
+// keyframes: beyond that the OLDEST optimised keyframes are held constant, said once on stderr).
+void fix_gauge_and_capacity(Window& win, const bool stereo, const char* who) {
+    size_t nconst = 0;
+    for (uint8_t c : win.pose_const) nconst += c;
+    const size_t nmincst = stereo ? 1 : 2;
+    std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
+    for (auto it = by_id.begin(); nconst < nmincst && it != by_id.end(); ++it)
+        if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
+    size_t nvar = win.pose_const.size() - nconst;
+    if (nvar > 64) {
+        static bool told = false;
+        if (!told) { std::cerr << "[ov2b200] " << who << ": " << nvar << " optimised keyframes, the oldest " << nvar - 64 << " are held constant\n"; told = true; }
+        for (auto it = by_id.begin(); nvar > 64 && it != by_id.end(); ++it)
+            if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nvar--; }
+    }
+}
+
+// ov2_ba_problem view of a window (K / Kr / Trl storage supplied by the caller).
+void make_problem(const Window& win, Window& wmut, const Frame& ref, const bool stereo, double K[4], double Kr[4], double Trl[7], ov2_ba_problem& pb) {
+    auto cal = ref.pcalib_leftcam_;
+    K[0] = cal->fx_; K[1] = cal->fy_; K[2] = cal->cx_; K[3] = cal->cy_;
+    pb.ncam = (int)win.kfids.size(); pb.npts = (int)win.lmids.size(); pb.nobs = (int)win.obs_cam.size();
+    pb.K = K; pb.pose = wmut.pose.data(); pb.pose_const = win.pose_const.data();
+    pb.lm_anchor_cam = win.lm_anchor_cam.data(); pb.lm_anchor_px = win.lm_anchor_px.data();
+    pb.lm_invdepth = wmut.lm_invdepth.data();
+    pb.obs_cam = win.obs_cam.data(); pb.obs_lm = win.obs_lm.data(); pb.obs_px = win.obs_px.data();
+    pb.obs_type = nullptr; pb.Kr = nullptr; pb.Trl = nullptr;
+    if (stereo) {
+        auto calr = ref.pcalib_rightcam_;
+        Kr[0] = calr->fx_; Kr[1] = calr->fy_; Kr[2] = calr->cx_; Kr[3] = calr->cy_;
+        const Sophus::SE3d T = calr->getExtrinsic().inverse();          // Trl (optimizer.cpp:112-114)
+        const Eigen::Quaterniond q = T.unit_quaternion();
+        const Eigen::Vector3d t = T.translation();
+        const double e[7] = {t.x(), t.y(), t.z(), q.x(), q.y(), q.z(), q.w()};
+        for (int i = 0; i < 7; ++i) Trl[i] = e[i];
+        pb.obs_type = win.obs_type.data(); pb.Kr = Kr; pb.Trl = Trl;
+    }
+}
+
 }  // namespace
 
 void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
@@ -106,87 +188,16 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
                 if (lm_seen.emplace(kp.lmid_, 1).second) lm_order.push_back(kp.lmid_);
     }
 
-    // ---- 2. landmarks: first valid observer (ascending kf id) anchors the inverse depth, every
-    //         further observer contributes one residual block (optimizer.cpp:191-392)
-    std::vector<std::pair<int, int>> bad_obs;     // (kfid, lmid) to drop from the map afterwards
-    for (int lmid : lm_order) {
-        auto lm = pmap_->getMapPoint(lmid);
-        if (!lm || lm->isBad()) continue;
-        int anchor_cam = -1;
-        const int l = (int)win.lmids.size();
-        for (int kfid : lm->getKfObsSet()) {
-            if (kfid > newest) continue;
-            auto cit = win.cam_of_kf.find(kfid);
-            std::shared_ptr<Frame> kf = cit != win.cam_of_kf.end() ? win.kfs[cit->second] : pmap_->getKeyframe(kfid);
-            if (!kf) { pmap_->removeMapPointObs(kfid, lmid); continue; }
-            const int cam = win.add_camera(kfid, kf, /*constant=*/cit == win.cam_of_kf.end());
-            const auto kp = kf->getKeypointById(lmid);
-            if (kp.lmid_ != lmid) { pmap_->removeMapPointObs(lmid, kfid); continue; }
-            // kp.scale_ is 0 for every keypoint the reference's front-end creates (map_manager.cpp adds
-            // keypoints without a scale), so the residuals' information matrix 2^-scale * I is the identity
-            if (anchor_cam < 0) {
-                anchor_cam = cam;
-                win.lmids.push_back(lmid);
-                win.lms.push_back(lm);
-                win.lm_anchor_cam.push_back(cam);
-                win.lm_anchor_px.push_back(kp.unpx_.x);
-                win.lm_anchor_px.push_back(kp.unpx_.y);
-                win.lm_invdepth.push_back(1.0 / (kf->getTcw() * lm->getPoint()).z());
-                // the anchor's own right-camera observation constrains the inverse depth alone (optimizer.cpp:268-284)
-                if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 2);
-                continue;
-            }
-            win.add_obs(cam, l, kp.unpx_.x, kp.unpx_.y, 0);            // appended landmark by landmark: already sorted
-            if (stereo && kp.is_stereo_) win.add_obs(cam, l, kp.runpx_.x, kp.runpx_.y, 1);   // (optimizer.cpp:295-324)
-        }
-    }
-    // ---- 3. gauge: at least two constant keyframes in mono, one in stereo (optimizer.cpp:65-69, 396-407).
-    //         The reference walks its unordered_map of local keyframes (unspecified order); ascending
-    //         keyframe id is used here.
-    size_t nconst = 0;
-    for (uint8_t c : win.pose_const) nconst += c;
-    {
-        const size_t nmincst = stereo ? 1 : 2;
-        std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
-        for (auto it = by_id.begin(); nconst < nmincst && it != by_id.end(); ++it)
-            if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
-    }
+    // ---- 2. landmarks (optimizer.cpp:191-392)
+    flatten_landmarks(*pmap_, win, lm_order, newest, stereo);
+    // ---- 3. gauge + solver capacity
+    fix_gauge_and_capacity(win, stereo, "localBA");
     if (win.obs_cam.empty()) return;
-    // ov2_localba_solve optimises at most 64 keyframes per window (MAX_VAR_CAMS): beyond that the OLDEST optimised
-    // keyframes are held constant (the reference has no such limit; windows that large do not occur with the shipped
-    // nmin_covscore / covisibility settings - said once on stderr if it ever happens)
-    {
-        size_t nvar = win.pose_const.size() - nconst;
-        if (nvar > 64) {
-            static bool told = false;
-            if (!told) { std::cerr << "[ov2b200] localBA: " << nvar << " optimised keyframes, the oldest " << nvar - 64 << " are held constant\n"; told = true; }
-            std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
-            for (auto it = by_id.begin(); nvar > 64 && it != by_id.end(); ++it)
-                if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nvar--; }
-        }
-    }
 
     // ---- 4. solve on the GPU (replaces ceres::Solve x2 + the two outlier scans)
-    auto cal = newframe.pcalib_leftcam_;
-    const double K[4] = {cal->fx_, cal->fy_, cal->cx_, cal->cy_};
+    double K[4], Kr[4] = {0, 0, 0, 0}, Trl[7] = {0, 0, 0, 0, 0, 0, 1};
     ov2_ba_problem pb;
-    pb.ncam = (int)win.kfids.size(); pb.npts = (int)win.lmids.size(); pb.nobs = (int)win.obs_cam.size();
-    pb.K = K; pb.pose = win.pose.data(); pb.pose_const = win.pose_const.data();
-    pb.lm_anchor_cam = win.lm_anchor_cam.data(); pb.lm_anchor_px = win.lm_anchor_px.data();
-    pb.lm_invdepth = win.lm_invdepth.data();
-    pb.obs_cam = win.obs_cam.data(); pb.obs_lm = win.obs_lm.data(); pb.obs_px = win.obs_px.data();
-    double Kr[4] = {0, 0, 0, 0}, Trl[7] = {0, 0, 0, 0, 0, 0, 1};
-    pb.obs_type = nullptr; pb.Kr = nullptr; pb.Trl = nullptr;
-    if (stereo) {
-        auto calr = newframe.pcalib_rightcam_;
-        Kr[0] = calr->fx_; Kr[1] = calr->fy_; Kr[2] = calr->cx_; Kr[3] = calr->cy_;
-        const Sophus::SE3d T = calr->getExtrinsic().inverse();          // Trl (optimizer.cpp:112-114)
-        const Eigen::Quaterniond q = T.unit_quaternion();
-        const Eigen::Vector3d t = T.translation();
-        const double e[7] = {t.x(), t.y(), t.z(), q.x(), q.y(), q.z(), q.w()};
-        for (int i = 0; i < 7; ++i) Trl[i] = e[i];
-        pb.obs_type = win.obs_type.data(); pb.Kr = Kr; pb.Trl = Trl;
-    }
+    make_problem(win, win, newframe, stereo, K, Kr, Trl, pb);
     ov2_ba_opts op;
     op.max_iters_robust = 5; op.max_iters_refine = 10;                // optimizer.cpp:462, :610
     op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-3;
@@ -263,4 +274,205 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     }
     bstop_localba_ = false;                                            // optimizer.cpp:896: a stop request is consumed by the BA it interrupted
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8f-4: Optimizer::looseBA (/root/reference/src/optimizer.cpp:900-1671) and Optimizer::fullBA (:1674-2331) - the same
+// residual blocks and the same Ceres configuration as localBA over bigger windows (a loop's keyframes / the whole map),
+// so the flattening above and the same solve kernel serve them.  What differs is the window rule, the iteration budget
+// and the write-back, restated below.  Compile these two with -DOV2_EXTERNAL_LOOSE_FULL_BA on the reference side (an
+// #ifndef around the two bodies, like localBA's); without the define the reference keeps its Ceres versions.
+namespace {
+
+// keyframes [first, last]: the first `nmincst` that exist are constant, the others are optimised and bring their 3-D
+// keypoints' map points in (ascending map-point id: the reference collects them in a std::set)
+void window_of_range(MapManager& map, Window& win, const int first, const int last, const bool stereo, std::vector<int>& lm_order) {
+    const size_t nmincst = stereo ? 1 : 2;
+    size_t ncst = 0;
+    std::set<int> lmids;
+    for (int kfid = first; kfid <= last; ++kfid) {
+        auto kf = map.getKeyframe(kfid);
+        if (!kf) continue;
+        const bool constant = ncst < nmincst;
+        if (constant) ncst++;
+        win.add_camera(kfid, kf, constant);
+        if (!constant)
+            for (const auto& kp : kf->getKeypoints3d()) lmids.insert(kp.lmid_);
+    }
+    lm_order.assign(lmids.begin(), lmids.end());
+}
+
+// world point of landmark l from its anchor keyframe's CURRENT pose in the map (optimizer.cpp:1497-1511, :2262-2275)
+bool world_point(const Window& win, size_t l, Eigen::Vector3d& out) {
+    const double invd = win.lm_invdepth[l];
+    if (1.0 / invd <= 0.0) return false;
+    auto ait = win.cam_of_kf.find(win.lms[l]->kfid_);
+    if (ait == win.cam_of_kf.end()) return false;
+    auto kfa = win.kfs[ait->second];
+    const auto kp = kfa->getKeypointById(win.lmids[l]);
+    out = kfa->getTwc() * ((1.0 / invd) * kfa->pcalib_leftcam_->iK_ * Eigen::Vector3d(kp.unpx_.x, kp.unpx_.y, 1.0));
+    return true;
+}
+
+void cull_bad(MapManager& map, const std::set<int>& bad, const int newest_kfid) {
+    for (int lmid : bad) {
+        auto lm = map.getMapPoint(lmid);
+        if (!lm) continue;
+        if (lm->isBad()) { map.removeMapPoint(lmid); continue; }
+        if (lm->getKfObsSet().size() < 3 && lm->kfid_ < newest_kfid - 3 && !lm->isobs_) map.removeMapPoint(lmid);
+    }
+}
+
+}  // namespace
+
+#ifdef OV2_EXTERNAL_LOOSE_FULL_BA
+void Optimizer::looseBA(const int inikfid, const int nkfid, const bool buse_robust_cost)
+{
+    auto pnew = pmap_->getKeyframe(nkfid);
+    if (!pnew) return;
+    Frame& newframe = *pnew;
+    ov2_ctx* ctx = ba_context();
+    if (!ctx) { std::cerr << "[ov2b200] looseBA: no CUDA device (no CPU fallback)\n"; return; }
+    if (!pslamstate_->buse_inv_depth_) { std::cerr << "[ov2b200] looseBA: only the anchored inverse-depth parametrisation is built\n"; return; }
+    const bool stereo = pslamstate_->stereo_;
+    Window win;
+    std::vector<int> lm_order;
+    window_of_range(*pmap_, win, inikfid, nkfid, stereo, lm_order);          // optimizer.cpp:989-1020
+    flatten_landmarks(*pmap_, win, lm_order, newframe.kfid_, stereo);        // :1023-1226
+    fix_gauge_and_capacity(win, stereo, "looseBA");                          // :1228-1239
+    if (win.obs_cam.empty()) return;
+    double K[4], Kr[4] = {0, 0, 0, 0}, Trl[7] = {0, 0, 0, 0, 0, 0, 1};
+    ov2_ba_problem pb;
+    make_problem(win, win, newframe, stereo, K, Kr, Trl, pb);
+    ov2_ba_opts op;
+    op.max_iters_robust = 5; op.max_iters_refine = 0;                         // one solve: :1297-1310
+    op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-4;
+    op.use_robust = buse_robust_cost ? 1 : 0;
+    op.apply_l2_after_robust = 0;                                             // no refinement solve in looseBA
+    op.refine_loss = -1;
+    ov2_ba_result res;
+    std::vector<uint8_t> flags(win.obs_cam.size(), 0);
+    const Sophus::SE3d iniTnewkfw = newframe.getTcw();                        // :1452
+    if (ov2_localba_solve(ctx, &pb, &op, &res, flags.data()) != OV2_OK) {
+        std::cerr << "[ov2b200] looseBA: " << ov2_last_error(ctx) << "\n";
+        return;
+    }
+    // ---- write-back (:1322-1671)
+    std::set<int> bad;
+    for (size_t i = 0; i < flags.size(); ++i)
+        if (flags[i] & 1) bad.insert(win.lmids[win.obs_lm[i]]);
+    std::lock_guard<std::mutex> lock2(pmap_->optim_mutex_);
+    std::lock_guard<std::mutex> lock(pmap_->map_mutex_);
+    // the reference computes the landmarks' world points from the anchors' poses BEFORE the keyframes move (:1476-1521)
+    std::vector<std::pair<int, Eigen::Vector3d>> wpts;
+    for (size_t l = 0; l < win.lmids.size(); ++l) {
+        if (win.lms[l]->isBad()) { bad.insert(win.lmids[l]); continue; }
+        Eigen::Vector3d w;
+        if (world_point(win, l, w)) wpts.emplace_back(win.lmids[l], w);
+        else bad.insert(win.lmids[l]);
+    }
+    for (const auto& lw : wpts) pmap_->updateMapPoint(lw.first, lw.second);
+    const auto cnew = win.cam_of_kf.find(newframe.kfid_);
+    const double* pn = &win.pose[7 * cnew->second];
+    const Sophus::SE3d optTwnewkf(Eigen::Quaterniond(pn[6], pn[3], pn[4], pn[5]), Eigen::Vector3d(pn[0], pn[1], pn[2]));
+    for (size_t c = 0; c < win.kfids.size(); ++c) {
+        if (win.pose_const[c]) continue;
+        const double* p = &win.pose[7 * c];
+        win.kfs[c]->setTwc(Sophus::SE3d(Eigen::Quaterniond(p[6], p[3], p[4], p[5]), Eigen::Vector3d(p[0], p[1], p[2])));
+    }
+    // keyframes created after the loop keyframe follow it rigidly, with the map points they anchor (:1541-1587)
+    std::set<int> moved;
+    const std::set<int> in_window(win.lmids.begin(), win.lmids.end());
+    for (int kfid = newframe.kfid_ + 1; kfid <= pmap_->nkfid_; ++kfid) {
+        if (win.cam_of_kf.count(kfid)) continue;
+        auto kf = pmap_->getKeyframe(kfid);
+        if (!kf) continue;
+        const Sophus::SE3d updTwkf = optTwnewkf * (iniTnewkfw * kf->getTwc());
+        for (const auto& kp : kf->getKeypoints3d()) {
+            if (moved.count(kp.lmid_) || in_window.count(kp.lmid_)) continue;
+            auto lm = pmap_->getMapPoint(kp.lmid_);
+            if (!lm) { pmap_->removeMapPointObs(kp.lmid_, kfid); continue; }
+            if (lm->kfid_ == kfid) {
+                pmap_->updateMapPoint(kp.lmid_, updTwkf * kf->projWorldToCam(lm->getPoint()));
+                moved.insert(lm->lmid_);
+            }
+        }
+        kf->setTwc(updTwkf);
+    }
+    for (size_t i = 0; i < flags.size(); ++i) {                              // rejected right-camera observations (:1589-1600)
+        if (!(flags[i] & 1) || win.obs_type[i] == 0) continue;
+        win.kfs[win.obs_cam[i]]->removeStereoKeypointById(win.lmids[win.obs_lm[i]]);
+    }
+    for (size_t i = 0; i < flags.size(); ++i) {                              // rejected left-camera observations (:1602-1617)
+        if (!(flags[i] & 1) || win.obs_type[i] != 0) continue;
+        const int kfid = win.kfids[win.obs_cam[i]], lmid = win.lmids[win.obs_lm[i]];
+        pmap_->removeMapPointObs(lmid, kfid);
+        if (kfid == pmap_->pcurframe_->kfid_) pmap_->removeObsFromCurFrameById(lmid);
+    }
+    cull_bad(*pmap_, bad, newframe.kfid_);                                    // :1619-1647
+    pmap_->pcurframe_->setTwc(optTwnewkf * (iniTnewkfw * pmap_->pcurframe_->getTwc()));   // :1649-1653
+}
+
+void Optimizer::fullBA(const bool buse_robust_cost)
+{
+    auto pfirst = pmap_->getKeyframe(0);
+    if (!pfirst) return;
+    Frame& newframe = *pfirst;                                                // calibration holder (:1676)
+    ov2_ctx* ctx = ba_context();
+    if (!ctx) { std::cerr << "[ov2b200] fullBA: no CUDA device (no CPU fallback)\n"; return; }
+    if (!pslamstate_->buse_inv_depth_) { std::cerr << "[ov2b200] fullBA: only the anchored inverse-depth parametrisation is built\n"; return; }
+    const bool stereo = pslamstate_->stereo_;
+    Window win;
+    std::vector<int> lm_order;
+    window_of_range(*pmap_, win, 0, pmap_->nkfid_, stereo, lm_order);        // :1752-1790
+    // fullBA has no `kfid > newframe.kfid_` filter worth the name: every keyframe of the map is in the window
+    flatten_landmarks(*pmap_, win, lm_order, pmap_->nkfid_, stereo);         // :1794-1990
+    fix_gauge_and_capacity(win, stereo, "fullBA");                           // :1992-2003
+    if (win.obs_cam.empty()) return;
+    double K[4], Kr[4] = {0, 0, 0, 0}, Trl[7] = {0, 0, 0, 0, 0, 0, 1};
+    ov2_ba_problem pb;
+    make_problem(win, win, newframe, stereo, K, Kr, Trl, pb);
+    ov2_ba_opts op;
+    op.max_iters_robust = 100; op.max_iters_refine = 100;                     // :2055-2061, :2149 (same options object)
+    op.huber_th = pslamstate_->robust_mono_th_; op.function_tolerance = 1.e-6;   // Ceres' default: fullBA does not set it
+    op.use_robust = buse_robust_cost ? 1 : 0;
+    // the reference refines only when the first scan rejected something (:2140); the solve kernel refines whenever asked
+    // to, which is the same thing unless nothing was rejected - and then the refinement starts at a converged point with
+    // the same residual set and returns at its first iteration
+    op.apply_l2_after_robust = pslamstate_->apply_l2_after_robust_ ? 1 : 0;
+    op.refine_loss = -1;
+    ov2_ba_result res;
+    std::vector<uint8_t> flags(win.obs_cam.size(), 0);
+    if (ov2_localba_solve(ctx, &pb, &op, &res, flags.data()) != OV2_OK) {
+        std::cerr << "[ov2b200] fullBA: " << ov2_last_error(ctx) << "\n";
+        return;
+    }
+    // ---- write-back (:2180-2331)
+    std::set<int> bad;
+    std::lock_guard<std::mutex> lock(pmap_->map_mutex_);
+    for (size_t i = 0; i < flags.size(); ++i) {
+        if (!flags[i]) continue;
+        const int kfid = win.kfids[win.obs_cam[i]], lmid = win.lmids[win.obs_lm[i]];
+        if (win.obs_type[i] == 0) {
+            pmap_->removeMapPointObs(lmid, kfid);
+            if (kfid == pmap_->pcurframe_->kfid_) pmap_->removeObsFromCurFrameById(lmid);
+        } else {
+            win.kfs[win.obs_cam[i]]->removeStereoKeypointById(lmid);
+        }
+        bad.insert(lmid);
+    }
+    for (size_t c = 0; c < win.kfids.size(); ++c) {
+        if (win.pose_const[c]) continue;
+        const double* p = &win.pose[7 * c];
+        win.kfs[c]->setTwc(Sophus::SE3d(Eigen::Quaterniond(p[6], p[3], p[4], p[5]), Eigen::Vector3d(p[0], p[1], p[2])));
+    }
+    for (size_t l = 0; l < win.lmids.size(); ++l) {
+        const int lmid = win.lmids[l];
+        if (win.lms[l]->isBad()) { pmap_->removeMapPoint(lmid); bad.erase(lmid); continue; }
+        Eigen::Vector3d w;
+        if (!world_point(win, l, w)) { pmap_->removeMapPoint(lmid); bad.erase(lmid); continue; }
+        pmap_->updateMapPoint(lmid, w, win.lm_invdepth[l]);
+    }
+    cull_bad(*pmap_, bad, pmap_->nkfid_);
+}
+#endif  // OV2_EXTERNAL_LOOSE_FULL_BA
 

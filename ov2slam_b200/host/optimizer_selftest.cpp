@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "optimizer.hpp"
@@ -81,13 +82,30 @@ int main(int argc, char** argv) {
     }
     // the newest keyframe is the one localBA is called for; constant keyframes get a covisibility score below
     // nmin_covscore so that the window walk freezes them (optimizer.cpp:150-188)
+    std::vector<Sophus::SE3d> anchors_before;
+    for (int c = 0; c < ncam; ++c) anchors_before.push_back(map->map_pkfs_[c]->getTwc());
     auto newkf = map->map_pkfs_[ncam - 1];
     for (int c = 0; c < ncam - 1; ++c) newkf->covkfs_[c] = pc[c] ? 0 : 1000;
     map->pcurframe_ = newkf;
+    map->nkfid_ = ncam - 1;
     Optimizer opt(params, map);
-    if (argc > 3) opt.signalStopLocalBA();
-    opt.localBA(*newkf, true);
-    if (opt.stopLocalBA()) { fprintf(stderr, "bstop_localba_ not cleared\n"); return 4; }
+    const std::string mode = argc > 3 ? argv[3] : "";
+    Sophus::SE3d cur_before, new_before;
+    if (mode == "loose" || mode == "full") {
+        // the current frame is its own object in the reference (the map stores keyframe COPIES): looseBA moves it rigidly
+        // with the loop keyframe (optimizer.cpp:1649-1653)
+        auto cur = std::make_shared<Frame>(*newkf);
+        cur->setTwc(newkf->getTwc() * Sophus::SE3d(Eigen::Quaterniond(1, 0, 0, 0), Eigen::Vector3d(0.1, -0.05, 0.2)));
+        map->pcurframe_ = cur;
+        cur_before = cur->getTwc();
+        new_before = newkf->getTwc();
+        if (mode == "loose") opt.looseBA(0, ncam - 1, true);
+        else opt.fullBA(true);
+    } else {
+        if (mode == "stop") opt.signalStopLocalBA();
+        opt.localBA(*newkf, true);
+        if (opt.stopLocalBA()) { fprintf(stderr, "bstop_localba_ not cleared\n"); return 4; }
+    }
     f = fopen(argv[2], "wb");
     if (!f) return 3;
     for (int c = 0; c < ncam; ++c) {
@@ -98,12 +116,23 @@ int main(int argc, char** argv) {
     }
     for (int l = 0; l < npts; ++l) {
         auto lm = map->getMapPoint(l);
-        const double v = lm ? lm->invdepth_ : -1.0;
+        double v = lm ? lm->invdepth_ : -1.0;
+        // looseBA updates the world point only (updateMapPoint(lmid, wpt), optimizer.cpp:1531-1535): report the inverse depth the
+        // point has in its anchor keyframe AS THE SOLVE LEFT IT - looseBA forms the point with the anchor's pose before the
+        // keyframes move, so the pre-solve pose is the one to look through (saved in anchors_before)
+        if (lm && mode == "loose") v = 1.0 / (anchors_before[lac[l]].inverse() * lm->getPoint()).z();
         fwrite(&v, sizeof(double), 1, f);
+    }
+    if (mode == "loose") {
+        // rigid follow-up of the current frame: Twcur' = Twnew_opt * (Tnew_w_ini * Twcur)
+        const Sophus::SE3d expect = newkf->getTwc() * (new_before.inverse() * cur_before);
+        const Sophus::SE3d got = map->pcurframe_->getTwc();
+        const Eigen::Vector3d d = got.translation() - expect.translation();
+        if (d.x() * d.x() + d.y() * d.y() + d.z() * d.z() > 1e-18) { fprintf(stderr, "current frame not moved with the loop keyframe\n"); return 5; }
     }
     const int32_t nrem = (int32_t)map->removed_obs_.size();
     fwrite(&nrem, 4, 1, f);
     fclose(f);
-    printf("localBA done: %d keyframes, %d map points, %d observations removed, %zu points removed\n", ncam, npts, nrem, map->removed_points_.size());
+    printf("BA shim done: %d keyframes, %d map points, %d observations removed, %zu points removed\n", ncam, npts, nrem, map->removed_points_.size());
     return 0;
 }

@@ -58,6 +58,7 @@ public:
     Keypoint getKeypointById(const int lmid) const { auto it = mapkps_.find(lmid); return it == mapkps_.end() ? Keypoint() : it->second; }
     void removeStereoKeypointById(const int lmid) { auto it = mapkps_.find(lmid); if (it != mapkps_.end()) it->second.is_stereo_ = false; }
     Sophus::SE3d getTcw() const { return Twc_.inverse(); }
+    Eigen::Vector3d projWorldToCam(const Eigen::Vector3d& wpt) const { return Twc_.inverse() * wpt; }
     Sophus::SE3d getTwc() const { return Twc_; }
     void setTwc(const Sophus::SE3d& Twc) { Twc_ = Twc; }
     std::map<int, int> getCovisibleKfMap() const { return covkfs_; }
@@ -81,6 +82,7 @@ public:
     std::unordered_map<int, std::shared_ptr<Frame>> map_pkfs_;
     std::unordered_map<int, std::shared_ptr<MapPoint>> map_plms_;
     std::shared_ptr<Frame> pcurframe_;
+    int nkfid_ = 0;                                     // id of the newest keyframe
     std::mutex map_mutex_, optim_mutex_;
     std::vector<std::pair<int, int>> removed_obs_;      // (lmid, kfid) - for the self-test's report
     std::vector<int> removed_points_;

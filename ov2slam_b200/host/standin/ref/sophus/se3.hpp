@@ -12,6 +12,7 @@ public:
     const Eigen::Vector3d& translation() const { return t_; }
     Eigen::Matrix3d rotationMatrix() const { return q_.toRotationMatrix(); }
     Eigen::Vector3d operator*(const Eigen::Vector3d& p) const { return rotationMatrix() * p + t_; }
+    SE3d operator*(const SE3d& o) const { return SE3d(q_ * o.q_, rotationMatrix() * o.t_ + t_); }
     SE3d inverse() const {
         const Eigen::Quaterniond qi = q_.conjugate();
         const Eigen::Vector3d ti = qi.toRotationMatrix() * t_;

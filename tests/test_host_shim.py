@@ -161,3 +161,39 @@ def test_optimizer_localba_shim_updates_the_map_like_the_flat_solve(ctx, tmp_pat
     alive = invd >= 0
     assert alive.mean() > 0.9
     assert np.abs(invd[alive] - ref["lm_invdepth"][alive]).max() <= 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,stereo", [("loose", False), ("loose", True), ("full", False), ("full", True)])
+def test_optimizer_loose_and_full_ba_shims(ctx, tmp_path, mode, stereo):
+    """8f-4: the drop-in Optimizer::looseBA / fullBA (optimizer.cpp:900-1671 / 1674-2331; same residual blocks as localBA over a
+    keyframe RANGE: the first two (mono) / one (stereo) keyframes constant, all others optimised, one 5-iteration solve with
+    function_tolerance 1e-4 for looseBA, up to 100 + 100 iterations at Ceres' default 1e-6 for fullBA) on a synthetic map:
+    the map they leave behind equals ov2_localba_solve on the flat window with those options; looseBA also moves the current
+    frame rigidly with the loop keyframe (checked inside the self-test)."""
+    exe = build.build_optimizer_shim()
+    pb = synth.make_ba_problem(71 + stereo, 9, 600, 2400, stereo=stereo)
+    pb["pose_const"] = np.zeros_like(pb["pose_const"])
+    pb["pose_const"][:1 if stereo else 2] = 1
+    pb = _drop_landmarks_seen_only_by_constant_keyframes(pb)
+    _write_window(tmp_path / "w.bin", pb)
+    out = subprocess.run([str(exe), str(tmp_path / "w.bin"), str(tmp_path / "r.bin"), mode], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ncam, npts = len(pb["pose"]), len(pb["lm_invdepth"])
+    raw = np.fromfile(tmp_path / "r.bin", np.uint8)
+    pose = raw[:ncam * 56].view(np.float64).reshape(ncam, 7)
+    invd = raw[ncam * 56:ncam * 56 + npts * 8].view(np.float64)
+    ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    if mode == "loose":
+        res, flags = api.Optimizer(ctx).local_ba(ref, max_iters_robust=5, max_iters_refine=0, function_tolerance=1e-4, apply_l2_after_robust=0)
+        assert res["iters_refine"] == 0
+    else:
+        res, flags = api.Optimizer(ctx).local_ba(ref, max_iters_robust=100, max_iters_refine=100, function_tolerance=1e-6)
+    assert res["final_cost"] < res["initial_cost"]
+    for c in range(ncam):
+        assert np.abs(pose[c, :3] - ref["pose"][c, :3]).max() <= 1e-7
+        q, r = pose[c, 3:], ref["pose"][c, 3:] / np.linalg.norm(ref["pose"][c, 3:])
+        assert min(np.abs(q - r).max(), np.abs(q + r).max()) <= 1e-7
+    alive = invd >= 0
+    assert alive.mean() > 0.9
+    assert np.abs(invd[alive] - ref["lm_invdepth"][alive]).max() <= 1e-6 * np.abs(ref["lm_invdepth"][alive]).max() + 1e-7
