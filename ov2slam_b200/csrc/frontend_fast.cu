@@ -424,6 +424,168 @@ __global__ void __launch_bounds__(32) fast_sweep_kernel(SweepArgs A) {
     }
 }
 
+// Wavefront variant: the sequential cell order is the semantics, but a cell only reads mask bits of its own area, and a disc
+// (radius cs / 4) reaches no further than the neighbouring cells - so cell (r, c) needs (r, c-1), (r-1, c-1), (r-1, c) and
+// (r-1, c+1) finished, nothing else.  One warp per cell row, row r trailing row r-1 by two cells (as ss_sweep_kernel does):
+// exactly the sequential result in nwc + 2 nhc cell times instead of nwc * nhc (one warp per frame was 10 % of the C2 step,
+// pure latency).  Detections are kept per cell and put in cell order at the end.
+constexpr int FSWEEP_MAX_WARPS = 16;
+
+__global__ void __launch_bounds__(FSWEEP_MAX_WARPS * 32, 1) fast_sweep_wave_kernel(SweepArgs A) {
+    extern __shared__ uint32_t sm[];
+    __shared__ int s_cnt[2];
+    const int tid = threadIdx.x, fr = blockIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int wpr = (A.w + 31) >> 5, ncells = A.nwc * A.nhc;
+    uint32_t* bm = sm;                                                        // h * wpr words, bit = 1: mask is 0.0f there
+    int2* det = reinterpret_cast<int2*>(sm + (((size_t)A.h * wpr + 1) & ~(size_t)1));   // per cell, x < 0: none
+    int* skey_all = reinterpret_cast<int*>(det + ncells);                    // [nwarps][cap] sort keys
+    volatile int* progress = reinterpret_cast<volatile int*>(skey_all + (size_t)nwarps * A.cap);   // [nhc]
+    uint8_t* occ = reinterpret_cast<uint8_t*>(const_cast<int*>(progress) + A.nhc);       // (nhc+1)*(nwc+1)
+    int* skey = skey_all + (size_t)warp * A.cap;
+    for (int i = tid; i < A.h * wpr; i += nthreads) bm[i] = 0;
+    for (int i = tid; i < ncells; i += nthreads) det[i] = make_int2(-1, -1);
+    for (int i = tid; i < A.nhc; i += nthreads) progress[i] = 0;
+    const int nocc = (A.nhc + 1) * (A.nwc + 1);
+    for (int i = tid; i < nocc; i += nthreads) occ[i] = 0;
+    __syncthreads();
+    const int nrows = 2 * A.radius + 1;
+    // existing keypoints: occupancy + discs (feature_extractor.cpp:471-474); painting commutes (atomicOr)
+    if (A.kp_off) {
+        const int k0 = A.kp_off[fr], k1 = A.kp_off[fr + 1];
+        for (int k = k0 + tid; k < k1; k += nthreads) {
+            const float2 px = A.kps[k];
+            const int rr = (int)(px.y / (float)A.cs), cc = (int)(px.x / (float)A.cs);
+            if (rr >= 0 && rr <= A.nhc && cc >= 0 && cc <= A.nwc) occ[rr * (A.nwc + 1) + cc] = 1;
+            const int cx = __float2int_rn(px.x), cy = __float2int_rn(px.y);
+            for (int rI = 0; rI < nrows; ++rI) {
+                const int dy = rI - A.radius;
+                const int hwv = A.hw[dy < 0 ? -dy : dy];
+                paint_row(bm, wpr, A.w, A.h, cy + dy, cx - hwv, cx + hwv);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t* cand = A.cand + (size_t)fr * ncells * A.cap;
+    const int32_t* cand_n = A.cand_n + (size_t)fr * ncells;
+    for (int r = warp; r < A.nhc; r += nwarps) {
+        for (int c = 0; c < A.nwc; ++c) {
+            const int cell = r * A.nwc + c;
+            const int x0 = c * A.cs, y0 = r * A.cs;
+            const bool search = !occ[r * (A.nwc + 1) + c] && (x0 + A.cs < A.w - 1 && y0 + A.cs < A.h - 1);
+            // the cell's candidates do not depend on any other cell: fetch them before waiting for the neighbours
+            const int n = search ? cand_n[cell] : 0;
+            uint32_t cdv[4] = {0u, 0u, 0u, 0u};                                // cap <= 128: four candidates per lane
+            if (n > 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = 32 * q + lane;
+                    if (j < n) cdv[q] = __ldg(cand + (size_t)cell * A.cap + j);
+                }
+            }
+            if (r > 0) {
+                const int need = min(c + 2, A.nwc);                            // row r-1 has finished cell c+1 (or its last cell)
+                while (progress[r - 1] < need) __nanosleep(40);
+                __threadfence_block();
+            }
+            if (n > 0) {
+                // mask filter + ordered compaction of survivors into skey
+                int ns = 0, vmax = -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = 32 * q + lane;
+                    if (32 * q >= n) break;                                    // uniform
+                    bool ok = false;
+                    const uint32_t cd = cdv[q];
+                    if (j < n) {
+                        const int kx = cd & 255, ky = (cd >> 8) & 255;
+                        const int mx = x0 + (kx >> 2), my = y0 + ky;
+                        ok = ((bm[(size_t)my * wpr + (mx >> 5)] >> (mx & 31)) & 1u) == 0;
+                    }
+                    const unsigned m = __ballot_sync(FULL, ok);
+                    if (ok) {
+                        const int pos = ns + __popc(m & ((1u << lane) - 1));
+                        skey[pos] = (int)((cd >> 16) << 8) | j;                // (response << 8) | candidate index
+                        vmax = max(vmax, (int)(cd >> 16));
+                    }
+                    ns += __popc(m);
+                }
+                if (ns > 0) {
+                    vmax = __reduce_max_sync(FULL, vmax);
+                    __syncwarp();
+                    int nmax = 0, firstmax = 0x7fffffff;
+                    for (int base = 0; base < ns; base += 32) {
+                        const int j = base + lane;
+                        const bool is = j < ns && (skey[j] >> 8) == vmax;
+                        const unsigned m = __ballot_sync(FULL, is);
+                        if (m && firstmax == 0x7fffffff) firstmax = base + __ffs(m) - 1;
+                        nmax += __popc(m);
+                    }
+                    int win_j;
+                    if (nmax == 1 || ns <= 16) {
+                        win_j = skey[firstmax] & 255;                          // unique maximum / libstdc++'s insertion-sort range
+                    } else {
+                        if (lane == 0) ov2sort::sort_desc(skey, ns);
+                        __syncwarp();
+                        win_j = skey[0] & 255;
+                    }
+                    __syncwarp();
+                    if (vmax >= 20) {                                          // vkps.at(0).response >= 20
+                        const int wq = win_j >> 5;                              // uniform
+                        const uint32_t mine = wq == 0 ? cdv[0] : (wq == 1 ? cdv[1] : (wq == 2 ? cdv[2] : cdv[3]));
+                        const uint32_t cd = __shfl_sync(FULL, mine, win_j & 31);
+                        const int px = x0 + (int)(cd & 255), py = y0 + (int)((cd >> 8) & 255);
+                        if (lane == 0) det[cell] = make_int2(px, py);
+                        for (int rI = lane; rI < nrows; rI += 32) {
+                            const int dy = rI - A.radius;
+                            const int hwv = A.hw[dy < 0 ? -dy : dy];
+                            paint_row(bm, wpr, A.w, A.h, py + dy, px - hwv, px + hwv);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __threadfence_block();                                            // discs before the counter
+            __syncwarp();
+            if (lane == 0) progress[r] = c + 1;
+        }
+    }
+    __syncthreads();
+    // assembly in cell order + the adaptive threshold (feature_extractor.cpp:546-552)
+    int2* out = A.out_int + (size_t)fr * A.max_per_frame;
+    if (warp == 0) {
+        int nbkps = 0, nbempty = 0;
+        for (int base = 0; base < ncells; base += 32) {
+            const int cell = base + lane;
+            bool empty = false, has = false;
+            int2 d = make_int2(-1, -1);
+            if (cell < ncells) {
+                const int r = cell / A.nwc, c = cell - r * A.nwc;
+                empty = !occ[r * (A.nwc + 1) + c];
+                d = det[cell];
+                has = d.x >= 0;
+            }
+            const unsigned mh = __ballot_sync(FULL, has);
+            if (has) {
+                const int pos = nbkps + __popc(mh & ((1u << lane) - 1));
+                if (pos < A.max_per_frame) out[pos] = d;
+            }
+            nbkps += __popc(mh);
+            nbempty += __popc(__ballot_sync(FULL, empty));
+        }
+        if (lane == 0) {
+            A.out_n[fr] = nbkps;
+            int th = A.th[fr];
+            if ((double)nbkps < 0.5 * (double)nbempty && nbempty > 10) th = (int)((double)th * 0.66);
+            else if (nbkps == nbempty) th = (int)((double)th * 1.5);
+            A.th[fr] = th;
+            s_cnt[0] = nbkps;
+        }
+    }
+    __syncthreads();
+    for (int i = s_cnt[0] + tid; i < A.max_per_frame; i += nthreads) out[i] = make_int2(-1, -1);
+}
+
 // ---------------------------------------------------------------------------------- S
 struct SubpixArgs {
     const uint8_t* img; int w, h, pitch; long long fstride;
@@ -675,12 +837,27 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     SA.out_int = d_int; SA.out_n = d_cnt;
     {
         size_t wpr = (size_t)(W + 31) / 32;
+        // wavefront sweep (one warp per cell row) unless the bitmap + per-warp sort keys do not fit, cap > 128 or OV2_FAST_SWEEP=seq
+        const int nw = nhc < FSWEEP_MAX_WARPS ? nhc : FSWEEP_MAX_WARPS;
+        size_t wsmem = ((((size_t)H * wpr + 1) & ~(size_t)1)) * 4 + (size_t)nwc * nhc * 8 + (size_t)nw * cap * 4 + (size_t)nhc * 4 +
+                       (size_t)(nhc + 1) * (nwc + 1);
+        wsmem = (wsmem + 15) & ~(size_t)15;
+        const char* fs = getenv("OV2_FAST_SWEEP");
+        if (cap <= 128 && wsmem <= 200 * 1024 && !(fs && fs[0] == 's')) {
+            static size_t wave_attr[16] = {0};
+            if (wsmem > 48 * 1024 && wsmem > wave_attr[ctx->device & 15]) {
+                OV2_CUDA(ctx, cudaFuncSetAttribute(fast_sweep_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                wave_attr[ctx->device & 15] = wsmem;
+            }
+            OV2_LAUNCH(ctx, "fast_sweep_kernel", fast_sweep_wave_kernel<<<count, nw * 32, wsmem, ctx->stream>>>(SA));
+        } else {
         size_t smem = (size_t)H * wpr * 4 + (size_t)cap * 4 + (size_t)(nhc + 1) * (nwc + 1);
         smem = (smem + 15) & ~(size_t)15;
         if (smem > 227 * 1024) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_grid_fast: image too large for the shared-memory mask bitmap");
         if (smem > 48 * 1024)
             OV2_CUDA(ctx, cudaFuncSetAttribute(fast_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OV2_LAUNCH(ctx, "fast_sweep_kernel", fast_sweep_kernel<<<count, 32, smem, ctx->stream>>>(SA));
+        }
     }
     SubpixArgs PA;
     PA.img = pyr->l0; PA.w = W; PA.h = H; PA.pitch = (int)pyr->l0_pitch; PA.fstride = (long long)pyr->l0_fstride;

@@ -444,3 +444,22 @@ int main(int argc, char** argv) {
     assert out.returncode == 0, out.stdout
     worst, iters = out.stdout.split()
     assert float(worst) < 1e-3 and int(iters) <= 50
+
+
+def test_brief_table_extractor_parses_generated_32_format():
+    """scripts/brief_table_from_contrib.py (the one step a contrib build needs for BRIEF-32): a file in generated_32.i's format
+    comes back as the int8[256][4] table in test order, and a file whose shifts break the bit-order assumption is refused."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("brief_tab", str(ROOT / "scripts" / "brief_table_from_contrib.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(0)
+    t = rng.integers(-24, 25, (256, 4))
+    lines = []
+    for i in range(32):
+        terms = " + ".join("((SMOOTHED(%d, %d) < SMOOTHED(%d, %d)) << %d)" % (*t[i * 8 + k], 7 - k) for k in range(8))
+        lines.append("    desc[%d] = (uchar)(%s);" % (i, terms))
+    txt = "\n".join(lines)
+    assert np.array_equal(mod.parse(txt), t.astype(np.int8))
+    with pytest.raises(SystemExit):
+        mod.parse(txt.replace("<< 7)", "<< 6)", 1))
