@@ -233,7 +233,10 @@ OV2_API ov2_status ov2_line_min_sad(ov2_ctx* ctx, const ov2_pyr* left, const ov2
  * P(prev), P(cur), K, F+S on cur (no existing keypoints), B(tracked), B(new) for `count` frame pairs in
  * ONE call (batch mode inside): what VisualFrontEnd::trackMono + MapManager::extractKeypoints do per
  * frame (/root/reference/src/visual_front_end.cpp:65-128, src/map_manager.cpp:286-341).  Pointers
- * host or device as everywhere; n_kps = count * kps_per_frame; cellsize <= 0 skips F/B(new). */
+ * host or device as everywhere; n_kps = count * kps_per_frame; cellsize <= 0 skips F/B(new).
+ * The step is captured into a CUDA graph per distinct argument block (at most 16 are kept per context): zero the struct
+ * before filling it (its padding bytes are part of the cache key), and reuse argument blocks - a block that changes every
+ * call runs eagerly.  A detector cell that exceeds its candidate capacity makes the call return OV2_ERR_CAPACITY. */
 typedef struct {
     const uint8_t* prev_images; const uint8_t* cur_images; size_t row_stride, frame_stride; int count;
     ov2_klt_params klt; int n_kps, kps_per_frame; const uint8_t* nbpyrlvl; int nbpyrlvl_all;

@@ -30,6 +30,10 @@
 
 namespace {
 
+// launch grids of per-observation / per-landmark kernels: an empty shard still launches one (idle) block - a zero-block
+// grid is cudaErrorInvalidConfiguration
+static inline int grid1(int n, int per_block) { const int g = (n + per_block - 1) / per_block; return g < 1 ? 1 : g; }
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAX_VAR_CAMS = 64;
 constexpr int MAX_N = 6 * MAX_VAR_CAMS;
@@ -862,7 +866,7 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
     const int nobs = D.nobs;
     // Program::RemoveFixedBlocks: cameras that are constant or touch no active residual drop out
     OV2_CUDA(ctx, cudaMemsetAsync(D.cam_used, 0, D.ncam, st));
-    OV2_LAUNCH(ctx, "ba_cam_used_kernel", ba_cam_used_kernel<<<div_up(nobs, 256), 256, 0, st>>>(D));
+    OV2_LAUNCH(ctx, "ba_cam_used_kernel", ba_cam_used_kernel<<<grid1(nobs, 256), 256, 0, st>>>(D));
     std::vector<uint8_t> used(D.ncam), cst(D.ncam);
     if (sh && sh->fn) {
         // a camera is in the program if ANY rank has an active residual touching it
@@ -956,8 +960,8 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
         // ---- ComputeTrustRegionStep
         OV2_CUDA(ctx, cudaMemsetAsync(D.scal, 0, accum_bytes, st));
         if (x_is_new)
-            OV2_LAUNCH(ctx, "ba_eval_kernel<jac>", ba_eval_kernel<true><<<div_up(nobs, 128), 128, 0, st>>>(D, pose, invd));
-        OV2_LAUNCH(ctx, "ba_schur_kernel", ba_schur_kernel<<<div_up(D.npts, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(D, radius, first_iter));
+            OV2_LAUNCH(ctx, "ba_eval_kernel<jac>", ba_eval_kernel<true><<<grid1(nobs, 128), 128, 0, st>>>(D, pose, invd));
+        OV2_LAUNCH(ctx, "ba_schur_kernel", ba_schur_kernel<<<grid1(D.npts, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(D, radius, first_iter));
         if (sh && sh->fn) {
             // the ONE bulk collective per LM iteration: [cost, gmax, rhs, F'r, column norms, S] summed over
             // ranks (NVLink / NVSwitch via NCCL in the caller); every rank then solves the same system
@@ -984,7 +988,7 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
                        ba_backsub_kernel<<<nlm_blocks + 2, 128, 0, st>>>(D, pose, cand_pose, invd, cand_invd, nlm_blocks,
                                                                          (!sh || sh->rank == 0) ? 1 : 0, x_is_new ? 1 : 0));
         }
-        OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<div_up(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
+        OV2_LAUNCH(ctx, "ba_eval_kernel<cost>", ba_eval_kernel<false><<<grid1(nobs, 128), 128, 0, st>>>(D, cand_pose, cand_invd));
         first_iter = 0;
         if (sh && sh->fn) {
             // tiny second collective: candidate cost, model cost change, landmark step / candidate norms
@@ -1054,7 +1058,8 @@ static ov2_status ba_ceres_solve(ov2_ctx* ctx, BaDev& D, double*& pose, double*&
 
 static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2_ba_opts* opts,
                                ov2_ba_result* res, uint8_t* outlier_out, const Shard* sh) {
-    if (!ctx || !pb || !opts || !res || pb->ncam <= 0 || pb->npts <= 0 || pb->nobs < 0)
+    // a shard of a sharded solve may be empty (no landmarks / no observations): it still takes part in every collective
+    if (!ctx || !pb || !opts || !res || pb->ncam <= 0 || pb->npts < 0 || (pb->npts == 0 && !sh) || pb->nobs < 0)
         return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: bad arguments");
     memset(res, 0, sizeof(*res));
     if (pb->nobs == 0 && !sh) return OV2_OK;
@@ -1200,7 +1205,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
     double* h = ctx->ba_hscal + SC_COUNT;   // second half: the LM controller uses the first
     OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, 3 * sizeof(double), s));
     const int deact = opts->apply_l2_after_robust ? 1 : 0;
-    OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 1, deact));
+    OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<grid1(nobs, 256), 256, 0, s>>>(D, (double)th_f, 1, deact));
     OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
     OV2_CUDA(ctx, cudaStreamSynchronize(s));
     res->iters_robust = s1.iterations;
@@ -1225,7 +1230,7 @@ static ov2_status localba_impl(ov2_ctx* ctx, const ov2_ba_problem* pb, const ov2
         if ((st = ba_ceres_solve(ctx, D, pose, cand_pose, invd, cand_invd, opts->max_iters_refine, opts->function_tolerance, &s2, sh)) != OV2_OK)
             return st;
         OV2_CUDA(ctx, cudaMemsetAsync(D.scal + SC_NBAD, 0, 3 * sizeof(double), s));
-        OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<div_up(nobs, 256), 256, 0, s>>>(D, (double)th_f, 2, 0));
+        OV2_LAUNCH(ctx, "ba_flag_kernel", ba_flag_kernel<<<grid1(nobs, 256), 256, 0, s>>>(D, (double)th_f, 2, 0));
         OV2_CUDA(ctx, cudaMemcpyAsync(h, D.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s));
         OV2_CUDA(ctx, cudaStreamSynchronize(s));
         res->iters_refine = s2.iterations;

@@ -819,9 +819,11 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
     d_cand = (uint32_t*)o;
     if ((st = ov2_scratch(ctx, sizeof(int32_t) * (size_t)count * ncells, &o)) != OV2_OK) return st;
     d_candn = (int32_t*)o;
-    if ((st = ov2_scratch(ctx, sizeof(int32_t), &o)) != OV2_OK) return st;
-    d_ovf = (int32_t*)o;
-    OV2_CUDA(ctx, cudaMemsetAsync(d_ovf, 0, sizeof(int32_t), ctx->stream));
+    {   // sticky, context-owned flag (reported by this call when it synchronises, else by ov2_batch_end / ov2_frontend_step)
+        int* f = nullptr;
+        if ((st = ov2_cap_flag_get(ctx, &f)) != OV2_OK) return st;
+        d_ovf = (int32_t*)f;
+    }
 
     FastArgs FA;
     FA.img = pyr->l0; FA.w = W; FA.h = H; FA.pitch = (int)pyr->l0_pitch; FA.fstride = (long long)pyr->l0_fstride;
@@ -872,16 +874,14 @@ extern "C" ov2_status ov2_grid_fast(ov2_ctx* ctx, const ov2_pyr* pyr, int first,
         }
     }
     OV2_LAUNCH(ctx, "subpix_kernel", subpix_kernel<<<div_up(PA.n, 4), 128, 0, ctx->stream>>>(PA));
-    // capacity overflow is an error, never a silent truncation
-    int ovf = 0;
-    bool host_out = !ctx->pending.empty() && !ctx->batch;   // batch mode: nothing has been synchronised yet
+    // capacity overflow is an error, never a silent truncation: the flag's D2H mirror is enqueued behind the kernels (it is
+    // captured into the composite step's CUDA graph too); a call that synchronises reports it here, a call that only
+    // enqueues (batch mode, device outputs) leaves it to the next synchronising call of this context
+    const bool host_out = !ctx->pending.empty() && !ctx->batch;
+    if ((st = ov2_cap_flag_mirror(ctx)) != OV2_OK) return st;
     st = ov2_end(ctx);
     if (st != OV2_OK) return st;
-    if (host_out) {
-        OV2_CUDA(ctx, cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ovf) return ov2_fail(ctx, OV2_ERR_CAPACITY, "ov2_grid_fast: per-cell candidate capacity exceeded");
-    }
+    if (host_out) return ov2_cap_flag_check(ctx, "ov2_grid_fast: per-cell candidate capacity exceeded");
     return OV2_OK;
 }
 

@@ -129,7 +129,15 @@ extern "C" ov2_status ov2_frontend_step(ov2_ctx* ctx, ov2_pyr* prev, ov2_pyr* cu
         }
     }
     if (!done) {
-        if (!g) ctx->step_graphs.push_back({key, nullptr, 0, 0});
+        if (!g) {
+            // bounded cache: argument blocks that change every call (per-frame buffers) must not grow it without limit
+            if (ctx->step_graphs.size() >= 16) {
+                auto& old = ctx->step_graphs.front();
+                if (old.state == 1 && old.exec) cudaGraphExecDestroy(old.exec);
+                ctx->step_graphs.erase(ctx->step_graphs.begin());
+            }
+            ctx->step_graphs.push_back({key, nullptr, 0, 0});
+        }
         st = enqueue_step(ctx, prev, cur, a);
         if (st != OV2_OK) return abort_batch(st);
         ctx->batch = false;
@@ -140,5 +148,6 @@ extern "C" ov2_status ov2_frontend_step(ov2_ctx* ctx, ov2_pyr* prev, ov2_pyr* cu
         token.drop();
         if (ce != cudaSuccess) return ov2_fail(ctx, OV2_ERR_CUDA, "cudaEventSynchronize(upload)", ce);
     }
-    return ov2_wait_stream(ctx);
+    if ((st = ov2_wait_stream(ctx)) != OV2_OK) return st;
+    return ov2_cap_flag_check(ctx, "ov2_frontend_step: a detector cell exceeded its candidate capacity");
 }

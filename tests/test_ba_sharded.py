@@ -62,14 +62,21 @@ def test_allreduce_callback_sums_over_gloo_group():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_solve_matches_unsharded(ctx, world):
+@pytest.mark.parametrize("world,empty", [(2, False), (3, False), (3, True)])
+def test_sharded_solve_matches_unsharded(ctx, world, empty):
+    """The round-1 callback path (ov2_localba_solve_sharded).  With `empty` the last rank owns no landmark and no observation:
+    it must still take part in every all-reduce (zero-block launches made it return early and hang the others)."""
     import ctypes as C
     import torch
     pb = synth.make_ba_problem(31, 12, 1500, 9000)
     ref = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
     rres, rflags = api.Optimizer(ctx).local_ba(ref)
-    shards = api.partition_ba_problem(pb, world)
+    shards = api.partition_ba_problem(pb, world - 1 if empty else world)
+    if empty:
+        e = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in shards[0][0].items()}
+        for k in ("lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px"):
+            e[k] = e[k][:0].copy()
+        shards.append((e, np.zeros(0, np.int64), np.zeros(0, np.int64)))
     ctxs = [api.Context(0) for _ in range(world)]
     barrier = threading.Barrier(world)
     slots = [None] * world
