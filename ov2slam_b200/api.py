@@ -476,19 +476,16 @@ class Optimizer:
         o = dict(DEFAULT_BA_OPTS)
         o.update(opts)
         bo = BaOpts(**o)
-        ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
-        keep = {k: np.ascontiguousarray(pb[k]) for k in
-                ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth", "obs_cam", "obs_lm", "obs_px")}
-        assert keep["pose"].dtype == np.float64 and keep["obs_px"].dtype == np.float64
-        assert keep["obs_cam"].dtype == np.int32 and keep["pose_const"].dtype == np.uint8
-        p = BaProblem(ncam, npts, nobs, *[keep[k].ctypes.data for k in
-                                          ("K", "pose", "pose_const", "lm_anchor_cam", "lm_anchor_px", "lm_invdepth",
-                                           "obs_cam", "obs_lm", "obs_px")], *_stereo_ptrs(pb, keep))
+        keep = {}
+        p = _ba_problem_struct(pb, keep)
+        nobs = len(keep["obs_cam"])
         res = BaResult()
         flags = np.zeros(nobs, np.uint8)
         self.ctx.check(self.ctx.lib.ov2_localba_solve(self.ctx.h, C.byref(p), C.byref(bo), C.byref(res), flags.ctypes.data))
-        pb["pose"][...] = keep["pose"]
-        pb["lm_invdepth"][...] = keep["lm_invdepth"]
+        if keep["pose"] is not pb["pose"]:
+            pb["pose"][...] = keep["pose"]
+        if keep["lm_invdepth"] is not pb["lm_invdepth"]:
+            pb["lm_invdepth"][...] = keep["lm_invdepth"]
         return {f: getattr(res, f) for f, _ in BaResult._fields_}, flags
 
 
