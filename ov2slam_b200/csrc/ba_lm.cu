@@ -802,6 +802,78 @@ __device__ __forceinline__ void gj_pivots(double* sA, int n, int PIT, int* s_fai
     }
 }
 
+// Two pivots per barrier (n <= 48).  The 48-pivot loop above is a latency chain: barrier -> pivot read -> reciprocal ->
+// row factor -> update -> store, ~0.5 us per pivot, 24 us of a 75 us LM iteration of a single C3 window.  Eliminating
+// columns j and j+1 in one step halves the barriers and overlaps the second reciprocal with the first update's loads:
+//   a = A[j][j], b = A[j][j+1], c = A[j+1][j], d = A[j+1][j+1];   m = c / a;   d' = d - m b   (the SAME second pivot the
+//   scalar loop meets);   row j+1 := row j+1 - m row j;   row j := row j - (b / d') row j+1;   every other row r:
+//   f0 = A[r][j] / a,  f1 = (A[r][j+1] - f0 b) / d',  row r -= f0 row j(old) + f1 row j+1(new).
+// Rows j and j+1 are rewritten in their own step, so the step's readers take them from a double-buffered copy (pbuf) that
+// the rows' owners filled at the end of the previous step.
+template <int QMAX>
+__device__ __forceinline__ void gj_pivots2(double* sA, int n, int PIT, double* pbuf, int* s_fail) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int sub = tid & 3, r0 = tid >> 2, rows_per_pass = nt >> 2;
+    for (int e = tid; e < 2 * PIT; e += nt) pbuf[e] = sA[e];        // rows 0 and 1 -> parity 0
+    __syncthreads();
+    for (int j = 0; j < n; j += 2) {
+        const int par = (j >> 1) & 1;
+        const double* P0 = pbuf + (size_t)(2 * par) * PIT;
+        const double* P1 = P0 + PIT;
+        double* N0 = pbuf + (size_t)(2 * (par ^ 1)) * PIT;
+        double* N1 = N0 + PIT;
+        const double a = P0[j], b = P0[j + 1], c = P1[j], d = P1[j + 1];
+        if (!(a > 0.0) || !isfinite(a)) { if (tid == 0) *s_fail = 1; break; }   // uniform: every thread reads the same pivots
+        double ip0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip0) : "d"(a));
+        ip0 = fma(ip0, fma(-a, ip0, 1.0), ip0);
+        ip0 = fma(ip0, fma(-a, ip0, 1.0), ip0);
+        const double m = c * ip0;
+        const double d2 = d - m * b;
+        if (!(d2 > 0.0) || !isfinite(d2)) { if (tid == 0) *s_fail = 1; break; }
+        double ip1;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ip1) : "d"(d2));
+        ip1 = fma(ip1, fma(-d2, ip1, 1.0), ip1);
+        ip1 = fma(ip1, fma(-d2, ip1, 1.0), ip1);
+        const double g = b * ip1;
+        const int c0 = j + 2 + sub;
+        const int nq = (n - j + 2 - sub) >> 2;              // columns c = c0 + 4 q <= n
+        double p0[QMAX], p1[QMAX];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            p0[q] = q < nq ? P0[c0 + 4 * q] : 0.0;
+            p1[q] = q < nq ? P1[c0 + 4 * q] - m * p0[q] : 0.0;
+        }
+        for (int r = r0; r < n; r += rows_per_pass) {
+            double* rowr = sA + r * PIT;
+            double v[QMAX];
+            if (r == j) {
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) v[q] = p0[q] - g * p1[q];
+            } else if (r == j + 1) {
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) v[q] = p1[q];
+                if (sub == 0) rowr[j + 1] = d2;              // the diagonal holds the second pivot (z = A[i][n] / A[i][i])
+            } else {
+                const double f0 = rowr[j] * ip0;
+                const double f1 = (rowr[j + 1] - f0 * b) * ip1;
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) v[q] = q < nq ? rowr[c0 + 4 * q] : 0.0;
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) v[q] -= f0 * p0[q] + f1 * p1[q];
+            }
+            double* nxt = r == j + 2 ? N0 : (r == j + 3 ? N1 : nullptr);
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q)
+                if (q < nq) {
+                    rowr[c0 + 4 * q] = v[q];
+                    if (nxt) nxt[c0 + 4 * q] = v[q];
+                }
+        }
+        __syncthreads();
+    }
+}
+
 __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radius, int first_iter, double* sA, double* scal) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int PIT = n + 2;
@@ -829,7 +901,8 @@ __device__ void reduced_solve_small(const Prob& P, double* T, int n, double radi
     }
     __syncthreads();
     TRS(12);
-    if (n <= 48) gj_pivots<13>(sA, n, PIT, &s_fail);         // (n + 1 + 3) / 4 columns per thread
+    if (n <= 48 && P.gj2) gj_pivots2<13>(sA, n, PIT, sA + (size_t)n * PIT, &s_fail);   // two pivots per barrier
+    else if (n <= 48) gj_pivots<13>(sA, n, PIT, &s_fail);    // (n + 1 + 3) / 4 columns per thread
     else if (n <= 64) gj_pivots<17>(sA, n, PIT, &s_fail);
     else gj_pivots<25>(sA, n, PIT, &s_fail);
     __syncthreads();
@@ -1713,7 +1786,7 @@ static ov2_status plan_window(ov2_ctx* ctx, const ov2_ba_problem* pb, int world,
                    (size_t)WARPS * 28 * SCH * sizeof(double) + (size_t)WARPS * SCH * sizeof(int) + 16;
     schur = (schur + 15) & ~(size_t)15;
     const size_t solve = H.solve_blocked ? (size_t)CH_NB * (size_t)((((size_t)H.n_max + 15) & ~(size_t)15) + 8) * sizeof(double)
-                                         : (size_t)H.n_max * (size_t)(H.n_max + 2) * sizeof(double);
+                                         : (size_t)(H.n_max + 4) * (size_t)(H.n_max + 2) * sizeof(double);   // + 4 rows: pivot-row double buffer of gj_pivots2
     // shared-memory accumulation of the reduced system (behind the Schur scratch) when the whole block fits next to it
     // with two CTAs per SM still possible
     H.smem_sacc_off = schur / sizeof(double);
@@ -1799,6 +1872,7 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
     P.sg = H.sg;   // lanes per landmark in the per-landmark phases
+    P.gj2 = getenv("OV2_BA_GJ2") ? atoi(getenv("OV2_BA_GJ2")) : 1;   // two-pivot Gauss-Jordan steps for n <= 48 (0: one pivot per barrier)
     P.schur_smem = H.schur_smem; P.smem_sacc_off = (int)H.smem_sacc_off;
     P.pair_perm = (const int32_t*)(din + H.off_pp); P.pair_chunk = (const int2*)(din + H.off_pch); P.npchunk = 0;
     P.smem_work_off = (int)H.smem_work_off;

@@ -51,6 +51,7 @@ struct Prob {
     const int32_t* pair_perm;          // [nobs] observation indices sorted by (anchor keyframe, observing keyframe)   (owner mode)
     const int2* pair_chunk;            // [npchunk] (begin, end) into pair_perm, <= PCH observations of ONE pair each
     int npchunk;
+    int gj2;                           // reduced solve n <= 48: two pivots per barrier
     size_t blk;
 };
 
