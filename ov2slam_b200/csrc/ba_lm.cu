@@ -1872,7 +1872,10 @@ static void fill_prob(const ov2_ba_problem* pb, const ov2_ba_opts* opts, const H
     P.trace = getenv("OV2_BA_TRACE") ? (unsigned long long*)(dwork + H.w_trace) : nullptr;
     P.ncv_max = H.ncv_max; P.ncopy = H.ncopy; P.blk = H.blk; P.solve_blocked = H.solve_blocked;
     P.sg = H.sg;   // lanes per landmark in the per-landmark phases
-    P.gj2 = getenv("OV2_BA_GJ2") ? atoi(getenv("OV2_BA_GJ2")) : 1;   // two-pivot Gauss-Jordan steps for n <= 48 (0: one pivot per barrier)
+    // two-pivot Gauss-Jordan steps for n <= 48: opt-in (OV2_BA_GJ2=1).  Measured on a B200 (C3, 148 CTAs): pivot loop 172 us vs
+    // 152 us per solve with one pivot per barrier - the longer dependent chain of a step (two reciprocals + the second
+    // pivot's elimination) and 26 more live registers cost more than the 24 saved barriers.  Kept: tested, documents the result.
+    P.gj2 = getenv("OV2_BA_GJ2") ? atoi(getenv("OV2_BA_GJ2")) : 0;
     P.schur_smem = H.schur_smem; P.smem_sacc_off = (int)H.smem_sacc_off;
     P.pair_perm = (const int32_t*)(din + H.off_pp); P.pair_chunk = (const int2*)(din + H.off_pch); P.npchunk = 0;
     P.smem_work_off = (int)H.smem_work_off;

@@ -245,10 +245,14 @@ def test_localba_bal_structure_fixture(ctx):
     assert (flags != r["flags"]).sum() <= 3
 
 
-@pytest.mark.parametrize("env", [{"OV2_BA_SCHUR_SMEM": "1"}, {"OV2_BA_NCOPY": "4"}, {"OV2_BA_COOP": "1"}])
+@pytest.mark.parametrize("env", [{"OV2_BA_SCHUR_SMEM": "1"}, {"OV2_BA_NCOPY": "4"}, {"OV2_BA_COOP": "1"}, {"OV2_BA_GJ2": "1"},
+                                 {"OV2_BA_SCHUR_SMEM": "3"}, {"OV2_BA_SCHUR_SMEM": "0"}, {"OV2_BA_SCHUR_SMEM": "3", "OV2_BA_SG": "8"},
+                                 {"OV2_BA_SG": "32"}])
 def test_localba_optional_kernel_modes(ctx, monkeypatch, env):
     """The opt-in variants of the persistent kernel stay correct: shared-memory Schur accumulation under a CTA lock, privatised
-    accumulation copies + fold phase, cooperative launch."""
+    accumulation copies + fold phase, cooperative launch, two-pivot Gauss-Jordan steps, and - forced on a SINGLE window - the
+    owner-mode Schur phase that batches use by default (pair-sorted Gram blocks + DMMA landmark rows), the plain RED path, and
+    the other sub-group widths of the per-landmark phases."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _check(ctx, synth.make_ba_problem(3, 10, 2000, 8000))
