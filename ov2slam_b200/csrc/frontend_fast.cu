@@ -59,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "{\n"
         ".reg .pred P1;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"   /* suspend-time hint: sleep, do not spin (the spin was 7.6 % of the kernel's instructions) */
         "@P1 bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
@@ -156,18 +156,23 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
         }
     }
     __syncthreads();
+    // ring offsets for this pitch, once per thread (they were 16 IMADs per tested pixel)
+    int roff[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) roff[k] = c_ring_dy[k] * rp + c_ring_dx[k];
     // pass 1b (dense over the survivors): the 16-pixel ring test
     const int nq = s_nq;
     for (int q = threadIdx.x; q < nq; q += blockDim.x) {
         const int yx = qlist[q];
         const uint8_t* p = roi + (yx >> 8) * rp + (yx & 255);
         const int v = *p;
+        const int vlo = v - th, vhi = v + th;              // bright: ring < v - th, dark: ring > v + th
         unsigned bright = 0, dark = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            int dk_ = v - (int)p[c_ring_dy[k] * rp + c_ring_dx[k]];
-            bright |= (unsigned)(dk_ > th) << k;
-            dark |= (unsigned)(dk_ < -th) << k;
+            const int rk = (int)p[roff[k]];
+            bright |= (unsigned)(rk < vlo) << k;
+            dark |= (unsigned)(rk > vhi) << k;
         }
         unsigned b = bright | (bright << 16), dk = dark | (dark << 16);
         b &= b >> 1; b &= b >> 2; b &= b >> 4; b &= b >> 1;
@@ -188,7 +193,7 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
         const int v = *p;
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)p[c_ring_dy[k] * rp + c_ring_dx[k]];
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)p[roff[k]];
         int lo;
         if (A.score_mode == 1) {
             // s = max_k min(d[k..k+8]) (bright) / max_k min(-d[k..k+8]) (dark) with a sparse table:
@@ -259,6 +264,7 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
         uint32_t* out = A.cand + ((size_t)fr * (A.nwc * A.nhc) + cell) * A.cap;
         const uint32_t* kw = reinterpret_cast<const uint32_t*>(keep);
         const int nw = cs2p >> 2, lane = threadIdx.x;
+        const unsigned rcs = 0xFFFFFFFFu / (unsigned)cs + 1u;          // ceil(2^32 / cs): floor(pi * rcs / 2^32) == pi / cs for pi < 2^16
         int n = 0;
         for (int base = 0; base < nw; base += 32) {
             const int wi = base + lane;
@@ -273,7 +279,7 @@ __global__ void fast_cells_kernel(FastArgs A, const __grid_constant__ CUtensorMa
                     if ((ww >> (8 * b)) & 0xFFu) {
                         if (lane == 0 && n < A.cap) {
                             const int pi = (base + L) * 4 + b;
-                            const int yy = pi / cs, xx = pi - yy * cs;
+                            const int yy = (int)__umulhi((unsigned)pi, rcs), xx = pi - yy * cs;   // pi / cs, exact for pi < 2^16
                             out[n] = ((uint32_t)(sc[pi] - 1) << 16) | ((uint32_t)yy << 8) | (uint32_t)xx;
                         }
                         n++;
