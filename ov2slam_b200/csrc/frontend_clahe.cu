@@ -196,9 +196,16 @@ __global__ void __launch_bounds__(512) clahe_apply_kernel(ClaheArgs A) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int v = (in >> (8 * k)) & 255;
-                const float r = ((float)l1[o1[k] + v] * wb[k] + (float)l1[o2[k] + v] * wa[k]) * ya1 +
-                                ((float)l2[o1[k] + v] * wb[k] + (float)l2[o2[k] + v] * wa[k]) * ya;
-                int q = __float2int_rn(r);
+                // byte -> float and float -> nearest int WITHOUT the conversion unit (I2F / F2I issue at a quarter of the
+                // FP32 rate; five of them per pixel): 2^23 + b is exactly the float with mantissa b, and r + 1.5 * 2^23
+                // rounds r to nearest-even into the mantissa - the same values as (float)b and rint(r).  0.68 -> 0.65 ms per
+                // C4 step; staging the LUT rows as floats instead (4x the shared memory) measured slower, 0.71 ms.
+                const float a11 = __uint_as_float(0x4B000000u | l1[o1[k] + v]) - 8388608.0f;
+                const float a12 = __uint_as_float(0x4B000000u | l1[o2[k] + v]) - 8388608.0f;
+                const float a21 = __uint_as_float(0x4B000000u | l2[o1[k] + v]) - 8388608.0f;
+                const float a22 = __uint_as_float(0x4B000000u | l2[o2[k] + v]) - 8388608.0f;
+                const float r = (a11 * wb[k] + a12 * wa[k]) * ya1 + (a21 * wb[k] + a22 * wa[k]) * ya;
+                int q = __float_as_int(r + 12582912.0f) - 0x4B400000;
                 q = q < 0 ? 0 : (q > 255 ? 255 : q);
                 out |= (uint32_t)q << (8 * k);
             }
