@@ -16,6 +16,7 @@
 // the image edge, constant 0 outside the image - exactly the planes buildOpticalFlowPyramid
 // would have materialised), so the tracker reads only the 8-bit pyramid.
 #include <climits>
+#include <cstdio>
 #include "ov2_common.cuh"
 #include "klt_setup.cuh"
 
@@ -38,6 +39,11 @@ struct KltArgs {
     double eps2;           // epsilon^2 as OpenCV forms it (double)
     float eps_lo, eps_hi;  // float brackets of eps2: outside them the float evaluation of |delta|^2 decides
     int* work_counter;   // persistent launch: warps pull keypoint indices from this counter (null: one warp per index)
+    // three-keypoints-per-warp kernel: keypoints it cannot take (border windows, unaligned levels, huge gradients) are
+    // appended here and tracked by the one-warp-per-keypoint kernel in a second launch
+    int* defer_list;
+    int* defer_count;
+    int from_list;       // 1: fb_klt_kernel takes its keypoint indices from defer_list[0 .. *defer_count)
 };
 
 __device__ __forceinline__ int reflect101_safe(int i, int n) {
@@ -279,6 +285,44 @@ __device__ bool lk_track(const PyrView& Ipyr, const PyrView& Jpyr, int frame, fl
 #undef PIX
 }
 
+// One keypoint, whole warp: forward track, checks, backward track, forward-backward test (feature_tracker.cpp:35-137).
+template <int WIN>
+__device__ __forceinline__ void klt_one(const KltArgs& A, int i, uint8_t* sPw, int* sDw, int lane) {
+    const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
+    int maxlevel = A.lvls ? (int)A.lvls[i] : A.lvl_all;
+    if (maxlevel > A.prev.nlev - 1) maxlevel = A.prev.nlev - 1;  // feature_tracker.cpp:50-52
+    if (maxlevel < 0) maxlevel = 0;
+    const float2 kp = A.kps[i];
+    float2 fwd = A.priors[i];
+    float err = 0.f;
+    // x < 0 marks an empty slot of a fixed-stride batch (the detectors pad their output with (-1, -1),
+    // ov2_describe uses the same rule): status 0, prior untouched, no work
+    bool ok = kp.x >= 0.f &&
+              lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err, sPw, sDw, lane);
+    // feature_tracker.cpp:79-101
+    if (ok && err > A.ferr) ok = false;
+    if (ok) {
+        const float w0 = (float)A.cur.w[0], h0 = (float)A.cur.h[0];
+        if (!(1.f <= fwd.x && fwd.x < w0 - 1.f && 1.f <= fwd.y && fwd.y < h0 - 1.f)) ok = false;
+    }
+    if (ok) {
+        // backward: template from the current image at the forward result, search the previous image
+        float2 back = kp;
+        float err2 = 0.f;
+        bool ok2 = lk_track<WIN>(A.cur, A.prev, frame, fwd, back, 0, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err2, sPw, sDw, lane);
+        if (!ok2) ok = false;
+        else {
+            float dx = kp.x - back.x, dy = kp.y - back.y;
+            double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+            if (nrm > (double)A.fb_dist) ok = false;
+        }
+    }
+    if (lane == 0) {
+        A.priors[i] = fwd;
+        A.status[i] = ok ? 1 : 0;
+    }
+}
+
 // Keypoints need very different iteration counts (1 .. 30 per level), so a static warp <-> keypoint
 // assignment leaves SM slots idle while the slowest warp of a CTA finishes.  The persistent variant
 // fills the GPU once (resident CTAs only) and every warp pulls the next keypoint from a global counter.
@@ -293,44 +337,217 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA) fb_klt
         if (lane == 0) nxt_i = atomicAdd(A.work_counter, 1);
         i = __shfl_sync(FULL, nxt_i, 0);
     }
+    if (A.from_list) {
+        if (i >= *A.defer_count) return;
+        i = A.defer_list[i];
+    }
     if (i >= A.n) return;
-    const int frame = A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame;
-    int maxlevel = A.lvls ? (int)A.lvls[i] : A.lvl_all;
-    if (maxlevel > A.prev.nlev - 1) maxlevel = A.prev.nlev - 1;  // feature_tracker.cpp:50-52
-    if (maxlevel < 0) maxlevel = 0;
-    const float2 kp = A.kps[i];
-    float2 fwd = A.priors[i];
-    float err = 0.f;
-    // x < 0 marks an empty slot of a fixed-stride batch (the detectors pad their output with (-1, -1),
-    // ov2_describe uses the same rule): status 0, prior untouched, no work
-    bool ok = kp.x >= 0.f &&
-              lk_track<WIN>(A.prev, A.cur, frame, kp, fwd, maxlevel, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err, sPall[warp], sDall[warp], lane);
-    // feature_tracker.cpp:79-101
-    if (ok && err > A.ferr) ok = false;
-    if (ok) {
-        const float w0 = (float)A.cur.w[0], h0 = (float)A.cur.h[0];
-        if (!(1.f <= fwd.x && fwd.x < w0 - 1.f && 1.f <= fwd.y && fwd.y < h0 - 1.f)) ok = false;
-    }
-    if (ok) {
-        // backward: template from the current image at the forward result, search the previous image
-        float2 back = kp;
-        float err2 = 0.f;
-        bool ok2 = lk_track<WIN>(A.cur, A.prev, frame, fwd, back, 0, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err2, sPall[warp], sDall[warp], lane);
-        if (!ok2) ok = false;
-        else {
-            float dx = kp.x - back.x, dy = kp.y - back.y;
-            double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
-            if (nrm > (double)A.fb_dist) ok = false;
-        }
-    }
-    if (lane == 0) {
-        A.priors[i] = fwd;
-        A.status[i] = ok ? 1 : 0;
-    }
+    klt_one<WIN>(A, i, sPall[warp], sDall[warp], lane);
     if (!A.work_counter) return;
     __syncwarp();
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Three keypoints per warp.  In fb_klt_kernel every lane of the warp replays the per-keypoint scalar part of an LK
+// iteration (floor, bilinear weights, the two reductions, the 2 x 2 solve, the convergence tests: ~100 of the ~110
+// instructions of an iteration) and of a level set-up for ONE keypoint.  Here a warp carries three keypoints: lanes
+// 10 g .. 10 g + 9 belong to keypoint g, lane r < 9 of a group owns window ROW r (nine pixels, klt_setup.cuh::template_row9 /
+// mismatch_row9: the same integers), lane 9 fetches the tenth search row; the scalar part is computed once per lane for the
+// lane's own keypoint, so one pass of it serves three keypoints.  The three keypoints walk the pyramid levels and the
+// iterations in lock step (a group that has converged idles until the others have).  Only interior, word-aligned windows
+// are handled; a keypoint that meets anything else (border window at any level or iteration, unaligned aliased level 0,
+// gradients too large for the 32-bit reduction) is appended to defer_list and tracked from scratch by fb_klt_kernel
+// afterwards - results are those of fb_klt_kernel by construction.
+__device__ __forceinline__ int group_sum9(int v, int r, int leader) {
+    int t;
+    t = __shfl_down_sync(FULL, v, 8); if (r <= 1) v += t;
+    t = __shfl_down_sync(FULL, v, 4); if (r < 4) v += t;
+    t = __shfl_down_sync(FULL, v, 2); if (r < 2) v += t;
+    t = __shfl_down_sync(FULL, v, 1); if (r < 1) v += t;
+    return __shfl_sync(FULL, v, leader);
+}
+
+// state: 0 = lost (status false), 1 = tracked, 2 = deferred.  `run`: the group holds a keypoint to track in this call.
+__device__ int lk_track3(const PyrView& Ipyr, const PyrView& Jpyr, int frame, bool run, float2 pt, float2& nxt, int maxlevel, int max_iter,
+                         double eps2, float eps_lo, float eps_hi, float& err_out, int lane, int r, int leader) {
+    constexpr int WIN = 9;
+    const float half = (WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    bool status = true, defer = false;
+    float err = 0.f;
+    const int lmax = __reduce_max_sync(FULL, run ? maxlevel : -1);
+    for (int level = lmax; level >= 0; --level) {
+        bool act = run && !defer && level <= maxlevel;
+        const int lw = Ipyr.w[level], lh = Ipyr.h[level];
+        const uint8_t* Iimg = Ipyr.lvl[level] + Ipyr.fstride[level] * frame;
+        const uint8_t* Jimg = Jpyr.lvl[level] + Jpyr.fstride[level] * frame;
+        const int Ipitch = Ipyr.pitch[level], Jpitch = Jpyr.pitch[level];
+        const bool aligned = ((reinterpret_cast<uintptr_t>(Iimg) | (uintptr_t)Ipitch | reinterpret_cast<uintptr_t>(Jimg) | (uintptr_t)Jpitch) & 3) == 0;
+        const float sc = 1.f / (float)(1 << level);
+        float2 prevPt = make_float2(pt.x * sc, pt.y * sc);
+        float2 nextPt;
+        if (level == maxlevel) nextPt = make_float2(nxt.x * sc, nxt.y * sc);
+        else nextPt = make_float2(nxt.x * 2.f, nxt.y * 2.f);
+        if (act) nxt = nextPt;
+        prevPt.x -= half;
+        prevPt.y -= half;
+        const int ix = __float2int_rd(prevPt.x), iy = __float2int_rd(prevPt.y);
+        if (act && (ix < -WIN || ix >= lw || iy < -WIN || iy >= lh)) {
+            if (level == 0) { status = false; err = 0.f; }
+            act = false;
+        }
+        if (act && !(aligned && kltsetup::patch_interior(ix, iy, lw, lh))) { defer = true; act = false; }
+        float a = prevPt.x - (float)ix, b = prevPt.y - (float)iy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+        int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+        int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+        // ---- level set-up: window row r of the group's keypoint
+        short Iv[9], Ixv[9], Iyv[9];
+        int sA11 = 0, sA12 = 0, sA22 = 0, sabs = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { Iv[k] = 0; Ixv[k] = 0; Iyv[k] = 0; }
+        if (act && r < 9) {
+            unsigned nb[4][3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kltsetup::load_row12(Iimg + (size_t)(iy - 1 + r + k) * Ipitch, ix - 1, lw, nb[k]);
+            kltsetup::template_row9(nb, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sA11, sA12, sA22, sabs);
+        }
+        sA11 = group_sum9(sA11, r, leader);
+        sA12 = group_sum9(sA12, r, leader);
+        sA22 = group_sum9(sA22, r, leader);
+        sabs = group_sum9(sabs, r, leader);
+        const float A11 = __int2float_rn(sA11) * FLT_SCALE, A12 = __int2float_rn(sA12) * FLT_SCALE, A22 = __int2float_rn(sA22) * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - __fsqrt_rn((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+        if (act) {
+            err = minEig;
+            if ((double)minEig < 1e-4 || D < 1.1920928955078125e-07f) {
+                if (level == 0) status = false;
+                act = false;
+            }
+        }
+        if (act && sabs >= 262000) { defer = true; act = false; }   // the mismatch sums might not fit 32 bits: leave it to fb_klt_kernel
+        D = 1.f / D;
+        nextPt.x -= half;
+        nextPt.y -= half;
+        float2 prevDelta = make_float2(0.f, 0.f);
+        bool it_on = act;
+        int cjx = INT_MIN, cjy = INT_MIN;
+        unsigned tw[3] = {0u, 0u, 0u}, bw[3] = {0u, 0u, 0u};
+        for (int j = 0; j < max_iter; ++j) {
+            if (!__any_sync(FULL, it_on)) break;
+            const int jx = __float2int_rd(nextPt.x), jy = __float2int_rd(nextPt.y);
+            if (it_on && (jx < -WIN || jx >= lw || jy < -WIN || jy >= lh)) {
+                if (level == 0) status = false;
+                it_on = false;
+            }
+            if (it_on && !(jx >= 0 && jy >= 0 && jx + WIN < lw && jy + WIN < lh)) { defer = true; it_on = false; }
+            a = nextPt.x - (float)jx;
+            b = nextPt.y - (float)jy;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+            iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+            iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            // search rows: lane r (0..9) holds row jy + r; the row below comes from the next lane.  Reloaded only when the
+            // window's integer origin moved.
+            const bool reload = it_on && (jx != cjx || jy != cjy);
+            if (reload) {
+                kltsetup::load_row12(Jimg + (size_t)(jy + r) * Jpitch, jx, lw, tw);
+                cjx = jx; cjy = jy;
+            }
+            if (__any_sync(FULL, reload)) {
+                const unsigned n0 = __shfl_down_sync(FULL, tw[0], 1), n1 = __shfl_down_sync(FULL, tw[1], 1), n2 = __shfl_down_sync(FULL, tw[2], 1);
+                if (reload) { bw[0] = n0; bw[1] = n1; bw[2] = n2; }
+            }
+            int sb1 = 0, sb2 = 0;
+            if (it_on && r < 9) kltsetup::mismatch_row9(tw, bw, iw00, iw01, iw10, iw11, Iv, Ixv, Iyv, sb1, sb2);
+            sb1 = group_sum9(sb1, r, leader);
+            sb2 = group_sum9(sb2, r, leader);
+            if (it_on) {
+                const float b1 = __int2float_rn(sb1) * FLT_SCALE, b2 = __int2float_rn(sb2) * FLT_SCALE;
+                const float2 delta = make_float2((A12 * b2 - A22 * b1) * D, (A12 * b1 - A11 * b2) * D);
+                nextPt.x += delta.x;
+                nextPt.y += delta.y;
+                nxt = make_float2(nextPt.x + half, nextPt.y + half);
+                const float q = delta.x * delta.x + delta.y * delta.y;
+                bool conv;
+                if (q < eps_lo) conv = true;
+                else if (q > eps_hi) conv = false;
+                else conv = (double)delta.x * (double)delta.x + (double)delta.y * (double)delta.y <= eps2;
+                if (conv) it_on = false;
+                else if (j > 0 && fabsf(delta.x + prevDelta.x) <= 0.01f && fabsf(delta.y + prevDelta.y) <= 0.01f) {
+                    nxt.x -= delta.x * 0.5f;
+                    nxt.y -= delta.y * 0.5f;
+                    it_on = false;
+                }
+                prevDelta = delta;
+            }
+        }
+    }
+    err_out = err;
+    return defer ? 2 : (status ? 1 : 0);
+}
+
+template <int WARPS_PER_CTA>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) fb_klt3_kernel(KltArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane / 10, r = lane - 10 * g;
+    const bool member = g < 3;
+    const int leader = 10 * g;                     // lanes 30, 31: leader 30 (a group without a keypoint)
+    const int ntrip = (A.n + 2) / 3;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(A.work_counter, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= ntrip) return;
+        const int i = 3 * t + (member ? g : 0);
+        const bool have = member && i < A.n;
+        const int frame = have ? (A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame) : 0;
+        int maxlevel = have ? (A.lvls ? (int)A.lvls[i] : A.lvl_all) : 0;
+        if (maxlevel > A.prev.nlev - 1) maxlevel = A.prev.nlev - 1;  // feature_tracker.cpp:50-52
+        if (maxlevel < 0) maxlevel = 0;
+        const float2 kp = have ? A.kps[i] : make_float2(-1.f, -1.f);
+        float2 fwd = have ? A.priors[i] : make_float2(0.f, 0.f);
+        const bool run = have && kp.x >= 0.f;     // x < 0: empty slot - status 0, prior untouched
+        float err = 0.f;
+        int st = lk_track3(A.prev, A.cur, frame, run, kp, fwd, maxlevel, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err, lane, r, leader);
+        bool ok = run && st == 1;
+        bool defer = run && st == 2;
+        // feature_tracker.cpp:79-101
+        if (ok && err > A.ferr) ok = false;
+        if (ok) {
+            const float w0 = (float)A.cur.w[0], h0 = (float)A.cur.h[0];
+            if (!(1.f <= fwd.x && fwd.x < w0 - 1.f && 1.f <= fwd.y && fwd.y < h0 - 1.f)) ok = false;
+        }
+        // backward: template from the current image at the forward result, search the previous image (all groups in lock step)
+        float2 back = kp;
+        float err2 = 0.f;
+        st = lk_track3(A.cur, A.prev, frame, ok, fwd, back, 0, A.max_iter, A.eps2, A.eps_lo, A.eps_hi, err2, lane, r, leader);
+        if (ok) {
+            if (st == 2) { defer = true; ok = false; }
+            else if (st == 0) ok = false;
+            else {
+                const float dx = kp.x - back.x, dy = kp.y - back.y;
+                const double nrm = sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+                if (nrm > (double)A.fb_dist) ok = false;
+            }
+        }
+        if (have && r == 0) {
+            if (defer) {
+                A.defer_list[atomicAdd(A.defer_count, 1)] = i;       // prior untouched: klt_one starts from the same guess
+            } else {
+                if (run) A.priors[i] = fwd;
+                A.status[i] = ok ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+// (Draining the deferred list inside the same launch was tried twice - warps leaving when the list is momentarily empty:
+//  the last few warps inherit the whole tail, 33 ms; warps polling a completion counter: thousands of pollers on the cache
+//  line that also holds the work-queue counters, 83 ms.  The second launch below costs one launch gap.)
 
 template <int WPC>
 ov2_status launch_klt(ov2_ctx* ctx, KltArgs& A, bool persistent) {
@@ -397,6 +614,37 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
     A.priors = (float2*)o;
     if ((st = ov2_stage_out(ctx, status_out, (size_t)n, &o)) != OV2_OK) return st;
     A.status = (uint8_t*)o;
+    A.defer_list = nullptr; A.defer_count = nullptr; A.from_list = 0;
+    {
+        // three keypoints per warp (OV2_KLT_MODE=3) + the one-warp-per-keypoint kernel for what it defers
+        const char* m = getenv("OV2_KLT_MODE");
+        if (m && atoi(m) == 3 && n >= 96) {
+            void* o2 = nullptr;
+            if ((st = ov2_scratch(ctx, sizeof(int) * ((size_t)n + 4), &o2)) != OV2_OK) return st;
+            int* blk = (int*)o2;                               // [0] triple counter, [1] deferred count, [2] list counter, [4..] list
+            OV2_CUDA(ctx, cudaMemsetAsync(blk, 0, sizeof(int) * 4, ctx->stream));
+            A.work_counter = blk;
+            A.defer_count = blk + 1;
+            A.defer_list = blk + 4;
+            int per_sm = 0;
+            OV2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fb_klt3_kernel<8>, 256, 0));
+            const int ntrip = (n + 2) / 3;
+            int grid = per_sm * ctx->sm_count;
+            if (grid > div_up(ntrip, 8)) grid = div_up(ntrip, 8);
+            OV2_LAUNCH(ctx, "fb_klt_kernel", (fb_klt3_kernel<8><<<grid, 256, 0, ctx->stream>>>(A)));
+            KltArgs B = A;
+            B.work_counter = blk + 2;
+            B.from_list = 1;
+            OV2_LAUNCH(ctx, "fb_klt_deferred", (fb_klt_kernel<9, 8><<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(B)));
+            if (getenv("OV2_KLT_DEBUG")) {
+                int nd = 0;
+                cudaMemcpyAsync(&nd, blk + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+                fprintf(stderr, "[klt3] %d keypoints, %d deferred (%.1f %%)\n", n, nd, 100.0 * nd / (n > 0 ? n : 1));
+            }
+            return ov2_end(ctx);
+        }
+    }
     {
         const char* e = getenv("OV2_KLT_WPC");
         const int wpc = e ? atoi(e) : 8;
