@@ -44,6 +44,10 @@ struct KltArgs {
     int* defer_list;
     int* defer_count;
     int from_list;       // 1: fb_klt_kernel takes its keypoint indices from defer_list[0 .. *defer_count)
+    // keypoints bucketed by pyramid depth (klt_bucket_kernel) so that the three keypoints of a warp walk the same number of
+    // levels: bucket[0 .. n) = depth <= 1, bucket[n .. 2n) = deeper; bucket_count[0], [1] = their sizes.  NULL: consecutive indices
+    const int* bucket;
+    const int* bucket_count;
 };
 
 __device__ __forceinline__ int reflect101_safe(int i, int n) {
@@ -490,20 +494,48 @@ __device__ int lk_track3(const PyrView& Ipyr, const PyrView& Jpyr, int frame, bo
     return defer ? 2 : (status ? 1 : 0);
 }
 
+// Pre-pass of the three-keypoints-per-warp kernel: split the keypoint indices by pyramid depth (warp-aggregated appends; the
+// order inside a bucket is irrelevant - a keypoint's result does not depend on which keypoints share its warp).
+__global__ void __launch_bounds__(256) klt_bucket_kernel(KltArgs A, int* bucket, int* bucket_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = i < A.n;
+    int lvl = valid ? (int)A.lvls[i] : 0;
+    if (lvl > A.prev.nlev - 1) lvl = A.prev.nlev - 1;
+    const bool deep = valid && lvl > 1, shallow = valid && !deep;
+    const unsigned md = __ballot_sync(FULL, deep), ms = __ballot_sync(FULL, shallow);
+    int bd = 0, bs = 0;
+    if (lane == 0) {
+        if (md) bd = atomicAdd(bucket_count + 1, __popc(md));
+        if (ms) bs = atomicAdd(bucket_count, __popc(ms));
+    }
+    bd = __shfl_sync(FULL, bd, 0);
+    bs = __shfl_sync(FULL, bs, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (deep) bucket[A.n + bd + __popc(md & lt)] = i;
+    if (shallow) bucket[bs + __popc(ms & lt)] = i;
+}
+
 template <int WARPS_PER_CTA>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) fb_klt3_kernel(KltArgs A) {
     const int lane = threadIdx.x & 31;
     const int g = lane / 10, r = lane - 10 * g;
     const bool member = g < 3;
     const int leader = 10 * g;                     // lanes 30, 31: leader 30 (a group without a keypoint)
-    const int ntrip = (A.n + 2) / 3;
+    int n0 = A.n, n1 = 0;                          // bucket sizes (no buckets: everything in "bucket 0", identity order)
+    if (A.bucket) { n0 = A.bucket_count[0]; n1 = A.bucket_count[1]; }
+    const int ntrip0 = (n0 + 2) / 3, ntrip = ntrip0 + (n1 + 2) / 3;
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(A.work_counter, 1);
         t = __shfl_sync(FULL, t, 0);
         if (t >= ntrip) return;
-        const int i = 3 * t + (member ? g : 0);
-        const bool have = member && i < A.n;
+        int i = 0;
+        bool have = false;
+        if (member) {
+            const int e = t < ntrip0 ? 3 * t + g : 3 * (t - ntrip0) + g;      // entry inside the triple's bucket
+            have = e < (t < ntrip0 ? n0 : n1);
+            if (have) i = A.bucket ? A.bucket[(t < ntrip0 ? 0 : A.n) + e] : e;
+        }
         const int frame = have ? (A.frame_idx ? A.frame_idx[i] : A.first_frame + i / A.per_frame) : 0;
         int maxlevel = have ? (A.lvls ? (int)A.lvls[i] : A.lvl_all) : 0;
         if (maxlevel > A.prev.nlev - 1) maxlevel = A.prev.nlev - 1;  // feature_tracker.cpp:50-52
@@ -614,7 +646,7 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
     A.priors = (float2*)o;
     if ((st = ov2_stage_out(ctx, status_out, (size_t)n, &o)) != OV2_OK) return st;
     A.status = (uint8_t*)o;
-    A.defer_list = nullptr; A.defer_count = nullptr; A.from_list = 0;
+    A.defer_list = nullptr; A.defer_count = nullptr; A.from_list = 0; A.bucket = nullptr; A.bucket_count = nullptr;
     {
         // three keypoints per warp (OV2_KLT_MODE=3) + the one-warp-per-keypoint kernel for what it defers
         const char* m = getenv("OV2_KLT_MODE");
@@ -626,6 +658,16 @@ extern "C" ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_py
             A.work_counter = blk;
             A.defer_count = blk + 1;
             A.defer_list = blk + 4;
+            A.bucket = nullptr; A.bucket_count = nullptr;
+            if (A.lvls && !(getenv("OV2_KLT_BUCKET") && atoi(getenv("OV2_KLT_BUCKET")) == 0)) {
+                void* o3 = nullptr;
+                if ((st = ov2_scratch(ctx, sizeof(int) * (2 * (size_t)n + 2), &o3)) != OV2_OK) return st;
+                int* bk = (int*)o3;                            // [0], [1] bucket sizes, [2 ..] the two buckets
+                OV2_CUDA(ctx, cudaMemsetAsync(bk, 0, sizeof(int) * 2, ctx->stream));
+                OV2_LAUNCH(ctx, "klt_bucket_kernel", (klt_bucket_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(A, bk + 2, bk)));
+                A.bucket = bk + 2;
+                A.bucket_count = bk;
+            }
             int per_sm = 0;
             OV2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fb_klt3_kernel<8>, 256, 0));
             const int ntrip = (n + 2) / 3;
