@@ -229,6 +229,37 @@ OV2_API ov2_status ov2_line_min_sad(ov2_ctx* ctx, const ov2_pyr* left, const ov2
                             const int32_t* frame_idx, int first_frame, int per_frame, const float* pts, int nwinsize,
                             int goleft, float* xprior_out, float* l1err_out);
 
+/* ------------------------------------------------------------------ 8f-4: local-map matching
+ * The data-parallel core of Mapper::matchToMap(frame, fmaxprojerr, fdistratio, set_local_lmids)
+ * (/root/reference/src/mapper.cpp:576-774): for every candidate map point of the local map (cand_mp, in the caller's
+ * iteration order) projection into the frame, culling, the keypoints of the four surrounding grid cells
+ * (Frame::getSurroundingKeypoints, src/frame.cpp:624-650), pixel distance, "never observed together", mean co-projection
+ * error, minimal descriptor distance (MapPoint::computeMinDescDist, src/map_point.cpp:236-252), best / second with the
+ * 0.9 ratio test -> best_kp_out[ncand] (keypoint index or -1), best_dist_out[ncand]; then per keypoint the candidate with
+ * the smallest distance (later candidates win ties) -> kp_match_out[nkps] (index INTO cand_mp or -1), kp_dist_out[nkps]
+ * (1024 when unmatched).  The caller (the Mapper shim) flattens the map and applies the merges (mapper.cpp:559-570).
+ * Map-point table = the candidates AND the map points of the frame's keypoints.  Rotations are 3x3 matrices (row major)
+ * followed by the translation: Tcw[12], kf_Tcw[nkfs][12].  dist = (k1, k2, p1, p2, k3) of the pinhole model or NULL
+ * (fisheye calibrations are not built: keep the reference's matchToMap for them).  dmaxpxdist = fmaxprojerr, doubled by
+ * the caller when the frame has fewer than 30 3-D keypoints (:597-600); view_th = cos(max half field of view) (:586-596). */
+typedef struct {
+    double Tcw[12]; double K[4]; const double* dist;
+    int img_w, img_h, ncellsize, nbwcells, ncells;
+    const int32_t* cell_ptr;      /* [ncells + 1] keypoints per grid cell (Frame::vgridkps_), CSR */
+    const int32_t* cell_kp;       /* [nkps] keypoint indices, cell by cell, in the cell lists' order */
+    int nkps; const float* kp_px; /* [nkps][2] kp.px_ */
+    const int32_t* kp_lm;         /* [nkps] map-point table index of the keypoint's map point, -1: none */
+    int nmps; const double* mp_xyz;                                   /* [nmps][3] */
+    const int32_t* mp_desc_ptr; int ndesc; const uint8_t* desc;       /* [nmps + 1], [ndesc][32] */
+    const uint64_t* mp_kfmask;    /* [nmps][4] bit k: observed by local keyframe k (k < 256) */
+    const int32_t* mp_obs_ptr; int nobs; const int32_t* obs_kf; const float* obs_px;   /* [nmps + 1], [nobs], [nobs][2] */
+    int nkfs; const double* kf_Tcw;                                   /* [nkfs][12] */
+    int ncand; const int32_t* cand_mp;
+    float dmaxpxdist, fdistratio, view_th;
+} ov2_match_problem;
+OV2_API ov2_status ov2_match_to_map(ov2_ctx* ctx, const ov2_match_problem* p, int32_t* best_kp_out, float* best_dist_out,
+                            int32_t* kp_match_out, float* kp_dist_out);
+
 /* ------------------------------------------------------------------ composite: one front-end step
  * P(prev), P(cur), K, F+S on cur (no existing keypoints), B(tracked), B(new) for `count` frame pairs in
  * ONE call (batch mode inside): what VisualFrontEnd::trackMono + MapManager::extractKeypoints do per

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "ov2_batch_begin", "ov2_batch_end",
     "ov2_host_alloc", "ov2_host_free", "ov2_launch_count", "ov2_profile_enable", "ov2_profile_query",
     "ov2_pyr_create", "ov2_pyr_destroy", "ov2_pyr_build", "ov2_pyr_download", "ov2_clahe", "ov2_preprocess",
-    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_describe_config", "ov2_line_min_sad", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
+    "ov2_fb_klt", "ov2_grid_fast", "ov2_detect_single_scale", "ov2_pnp_solve", "ov2_debug_fast_cells", "ov2_describe", "ov2_describe_config", "ov2_line_min_sad", "ov2_match_to_map", "ov2_frontend_step", "ov2_localba_solve", "ov2_localba_solve_sharded", "ov2_localba_solve_batch", "ov2_localba_request_stop",
     "ov2_ba_comm_create", "ov2_ba_comm_handle", "ov2_ba_comm_connect", "ov2_ba_comm_connect_local", "ov2_ba_comm_destroy", "ov2_localba_solve_p2p",
 ]
 
@@ -59,6 +59,17 @@ class BaProblem(C.Structure):
                 ("lm_anchor_cam", C.c_void_p), ("lm_anchor_px", C.c_void_p), ("lm_invdepth", C.c_void_p),
                 ("obs_cam", C.c_void_p), ("obs_lm", C.c_void_p), ("obs_px", C.c_void_p),
                 ("obs_type", C.c_void_p), ("Kr", C.c_void_p), ("Trl", C.c_void_p)]
+
+
+class MatchProblem(C.Structure):
+    """ov2_match_problem (include/ov2b200.h), field for field."""
+    _fields_ = [("Tcw", C.c_double * 12), ("K", C.c_double * 4), ("dist", C.c_void_p),
+                ("img_w", C.c_int), ("img_h", C.c_int), ("ncellsize", C.c_int), ("nbwcells", C.c_int), ("ncells", C.c_int),
+                ("cell_ptr", C.c_void_p), ("cell_kp", C.c_void_p), ("nkps", C.c_int), ("kp_px", C.c_void_p), ("kp_lm", C.c_void_p),
+                ("nmps", C.c_int), ("mp_xyz", C.c_void_p), ("mp_desc_ptr", C.c_void_p), ("ndesc", C.c_int), ("desc", C.c_void_p),
+                ("mp_kfmask", C.c_void_p), ("mp_obs_ptr", C.c_void_p), ("nobs", C.c_int), ("obs_kf", C.c_void_p), ("obs_px", C.c_void_p),
+                ("nkfs", C.c_int), ("kf_Tcw", C.c_void_p), ("ncand", C.c_int), ("cand_mp", C.c_void_p),
+                ("dmaxpxdist", C.c_float), ("fdistratio", C.c_float), ("view_th", C.c_float)]
 
 
 class BaOpts(C.Structure):
@@ -121,6 +132,7 @@ def load():
     lib.ov2_describe.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     lib.ov2_describe_config.argtypes = [vp, i32, vp]
     lib.ov2_line_min_sad.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp]
+    lib.ov2_match_to_map.argtypes = [vp, C.POINTER(MatchProblem), vp, vp, vp, vp]
     lib.ov2_frontend_step.argtypes = [vp, vp, vp, C.POINTER(FrontendStepArgs)]
     lib.ov2_localba_solve.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp]
     lib.ov2_localba_solve_sharded.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOpts), C.POINTER(BaResult), vp,
@@ -543,6 +555,44 @@ def local_ba_batch(ctx: Context, pbs: list, **opts):
     cols = [rec[f].tolist() for f in names]
     return ([dict(zip(names, row)) for row in zip(*cols)],
             [allflags[int(offs[i]):int(offs[i]) + nobs[i]] for i in range(n)])
+
+
+def match_to_map(ctx: Context, sc: dict):
+    """Mapper::matchToMap (mapper.cpp:576-774) on a flattened scene (dict as ov2slam_b200.synth.make_match_scene builds it):
+    returns (best_kp int32[ncand], best_dist float32[ncand], kp_match int32[nkps], kp_dist float32[nkps])."""
+    keep = {}
+
+    def arr(k, dt):
+        keep[k] = np.ascontiguousarray(sc[k], dt)
+        return keep[k].ctypes.data if keep[k].size else None
+
+    p = MatchProblem()
+    p.Tcw[:] = [float(v) for v in np.asarray(sc["Tcw"], np.float64).reshape(-1)]
+    p.K[:] = [float(v) for v in sc["K"]]
+    p.dist = arr("dist", np.float64) if sc.get("dist") is not None else None
+    p.img_w, p.img_h, p.ncellsize, p.nbwcells = int(sc["img_w"]), int(sc["img_h"]), int(sc["ncellsize"]), int(sc["nbwcells"])
+    p.ncells = len(sc["cell_ptr"]) - 1
+    p.cell_ptr, p.cell_kp = arr("cell_ptr", np.int32), arr("cell_kp", np.int32)
+    p.nkps = len(sc["kp_px"])
+    p.kp_px, p.kp_lm = arr("kp_px", np.float32), arr("kp_lm", np.int32)
+    p.nmps = len(sc["mp_xyz"])
+    p.mp_xyz, p.mp_desc_ptr = arr("mp_xyz", np.float64), arr("mp_desc_ptr", np.int32)
+    p.ndesc = len(sc["desc"])
+    p.desc, p.mp_kfmask = arr("desc", np.uint8), arr("mp_kfmask", np.uint64)
+    p.mp_obs_ptr = arr("mp_obs_ptr", np.int32)
+    p.nobs = len(sc["obs_kf"])
+    p.obs_kf, p.obs_px = arr("obs_kf", np.int32), arr("obs_px", np.float32)
+    p.nkfs = len(np.asarray(sc["kf_Tcw"]).reshape(-1, 12))
+    p.kf_Tcw = arr("kf_Tcw", np.float64)
+    p.ncand = len(sc["cand_mp"])
+    p.cand_mp = arr("cand_mp", np.int32)
+    p.dmaxpxdist, p.fdistratio, p.view_th = float(sc["dmaxpxdist"]), float(sc["fdistratio"]), float(sc["view_th"])
+    best_kp = np.full(max(p.ncand, 1), -1, np.int32)
+    best_dist = np.zeros(max(p.ncand, 1), np.float32)
+    kp_match = np.full(max(p.nkps, 1), -1, np.int32)
+    kp_dist = np.zeros(max(p.nkps, 1), np.float32)
+    ctx.check(ctx.lib.ov2_match_to_map(ctx.h, C.byref(p), best_kp.ctypes.data, best_dist.ctypes.data, kp_match.ctypes.data, kp_dist.ctypes.data))
+    return best_kp[:p.ncand], best_dist[:p.ncand], kp_match[:p.nkps], kp_dist[:p.nkps]
 
 
 def request_stop_local_ba(ctx: Context, stop: bool = True):

@@ -34,6 +34,7 @@ SOURCES = {
     "ba_lm.cu": [],
     "ba_comm.cu": [],
     "pnp_solver.cu": [],
+    "match_map.cu": ["-fmad=false"],
 }
 
 

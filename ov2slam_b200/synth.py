@@ -290,3 +290,108 @@ def make_ba_problem(seed: int, ncam: int = 10, npts: int = 2000, nobs: int = 800
         obs_px=np.array(obs_px, np.float64).reshape(-1, 2),
         truth_pose=truth_pose, truth_invdepth=lm_invdepth_true,
     )
+
+
+# ----------------------------------------------------------------------------- local-map matching scene (Mapper::matchToMap)
+def _proj_radtan(P, K, dist):
+    x, y = P[:, 0] / P[:, 2], P[:, 1] / P[:, 2]
+    if dist is not None:
+        k1, k2, p1, p2, k3 = dist
+        r2 = x * x + y * y
+        cd = 1 + k1 * r2 + k2 * r2 * r2 + k3 * r2 ** 3
+        x, y = x * cd + 2 * p1 * x * y + p2 * (r2 + 2 * x * x), y * cd + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return np.stack([K[0] * x + K[2], K[1] * y + K[3]], 1)
+
+
+def make_match_scene(seed: int, nkps: int = 800, ncand: int = 400, nkfs: int = 12, distorted: bool = True,
+                     w: int = 752, h: int = 480, ncellsize: int = 35) -> dict:
+    """A flattened Mapper::matchToMap problem (the arrays ov2_match_to_map takes): a frame with `nkps` keypoints in its grid
+    (85 % of them attached to a map point), `nkfs` keyframes around it, and `ncand` local map points the frame does not
+    observe - half of them near-duplicates of observed map points (close in space, descriptors a few bits apart, mostly seen
+    from other keyframes), the rest unrelated.  Map points carry 1-4 descriptors and 1-5 keyframe observations."""
+    rng = np.random.default_rng(seed)
+    K = np.array([458.654, 457.296, 367.215, 248.375])
+    dist = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]) if distorted else None
+
+    def pose(scale):
+        R = _so3_exp(rng.normal(0, 0.05 * scale, 3))
+        t = rng.normal(0, 0.3 * scale, 3)
+        return np.concatenate([R.reshape(-1), t])       # Tcw: camera <- world
+
+    Tcw = pose(0.2)
+    kf_T = np.stack([pose(1.0) for _ in range(nkfs)])
+    R, t = Tcw[:9].reshape(3, 3), Tcw[9:]
+    # observed map points: sample pixels, back-project at random depths into the world
+    nobs_mp = int(0.85 * nkps)
+    pix = np.stack([rng.uniform(5, w - 5, nkps), rng.uniform(5, h - 5, nkps)], 1)
+    z = rng.uniform(2.0, 10.0, nkps)
+    cam = np.stack([(pix[:, 0] - K[2]) / K[0] * z, (pix[:, 1] - K[3]) / K[1] * z, z], 1)
+    world = (cam - t) @ R                                  # R^T (cam - t)
+    kp_px = _proj_radtan(world @ R.T + t, K, dist).astype(np.float32)
+    inimg = (kp_px[:, 0] >= 0) & (kp_px[:, 1] >= 0) & (kp_px[:, 0] < w) & (kp_px[:, 1] < h)
+    kp_px[~inimg] = [w / 2, h / 2]
+    kp_lm = np.where(np.arange(nkps) < nobs_mp, np.arange(nkps), -1).astype(np.int32)
+    order = rng.permutation(nkps)
+    kp_px, kp_lm_src = kp_px[order], kp_lm[order]
+    # map point table: [observed map points | candidates]
+    nm = nobs_mp + ncand
+    xyz = np.zeros((nm, 3))
+    xyz[:nobs_mp] = world[:nobs_mp]
+    base_desc = rng.integers(0, 256, (nm, 32), dtype=np.uint8)
+    dup = rng.random(ncand) < 0.5
+    src = rng.integers(0, nobs_mp, ncand)
+    for c in range(ncand):
+        m = nobs_mp + c
+        if dup[c]:
+            xyz[m] = xyz[src[c]] + rng.normal(0, 0.01, 3)
+            d = base_desc[src[c]].copy()
+            for b in rng.integers(0, 256, rng.integers(0, 30)):
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            base_desc[m] = d
+        else:
+            zz = rng.uniform(1.0, 12.0)
+            p = np.array([(rng.uniform(-60, w + 60) - K[2]) / K[0] * zz, (rng.uniform(-60, h + 60) - K[3]) / K[1] * zz, zz])
+            if rng.random() < 0.05:
+                p[2] = -p[2]
+            xyz[m] = (p - t) @ R
+    desc_ptr, descs = [0], []
+    for m in range(nm):
+        nd = int(rng.integers(1, 5)) if rng.random() > 0.03 else 0     # a few map points without descriptor
+        for _ in range(nd):
+            d = base_desc[m].copy()
+            for b in rng.integers(0, 256, rng.integers(0, 6)):
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            descs.append(d)
+        desc_ptr.append(len(descs))
+    kfmask = np.zeros((nm, 4), np.uint64)
+    obs_ptr, obs_kf, obs_px = [0], [], []
+    for m in range(nm):
+        if m >= nobs_mp and dup[m - nobs_mp] and rng.random() < 0.8:
+            free = [k for k in range(nkfs) if not (int(kfmask[src[m - nobs_mp], k >> 6]) >> (k & 63)) & 1]
+            kfs = rng.choice(free, min(len(free), int(rng.integers(1, 4))), replace=False) if free else []
+        else:
+            kfs = rng.choice(nkfs, int(rng.integers(1, 6)), replace=False)
+        for k in sorted(int(v) for v in kfs):
+            kfmask[m, k >> 6] |= np.uint64(1) << np.uint64(k & 63)
+            T = kf_T[k]
+            cp = T[:9].reshape(3, 3) @ xyz[m] + T[9:]
+            if cp[2] < 0.2:
+                cp[2] = 0.2
+            q = _proj_radtan(cp[None], K, dist)[0] + rng.normal(0, 0.7, 2)
+            obs_kf.append(k)
+            obs_px.append(q)
+        obs_ptr.append(len(obs_kf))
+    nbw, nbh = int(np.ceil(np.float32(w) / ncellsize)), int(np.ceil(np.float32(h) / ncellsize))
+    cell = (np.floor(kp_px[:, 1] / np.float32(ncellsize)).astype(int) * nbw + np.floor(kp_px[:, 0] / np.float32(ncellsize)).astype(int))
+    cell_kp = np.argsort(cell, kind="stable").astype(np.int32)
+    cell_ptr = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=nbw * nbh))]).astype(np.int32)
+    vfov, hfov = 0.5 * h / K[1], 0.5 * w / K[0]
+    view_th = np.float32(np.cos(np.float32(np.arctan(np.float32(max(vfov, hfov))))))
+    return dict(K=K, dist=dist, img_w=w, img_h=h, ncellsize=ncellsize, nbwcells=nbw, Tcw=Tcw, cell_ptr=cell_ptr, cell_kp=cell_kp,
+                kp_px=np.ascontiguousarray(kp_px, np.float32), kp_lm=np.ascontiguousarray(kp_lm_src, np.int32),
+                mp_xyz=xyz, mp_desc_ptr=np.asarray(desc_ptr, np.int32),
+                desc=np.asarray(descs, np.uint8).reshape(-1, 32), mp_kfmask=kfmask,
+                mp_obs_ptr=np.asarray(obs_ptr, np.int32), obs_kf=np.asarray(obs_kf, np.int32),
+                obs_px=np.asarray(obs_px, np.float32).reshape(-1, 2), kf_Tcw=kf_T,
+                cand_mp=(nobs_mp + rng.permutation(ncand)).astype(np.int32),
+                dmaxpxdist=np.float32(2.0 * 2), fdistratio=np.float32(0.2), view_th=view_th)
