@@ -120,6 +120,29 @@ def build_optimizer_shim(verbose: bool = False) -> Path:
         objs.append(str(obj))
     exe = LIB / "optimizer_selftest"
     subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    build_mapper_shim(verbose)
+    return exe
+
+
+def build_mapper_shim(verbose: bool = False) -> Path:
+    """Compile the drop-in Mapper::matchToMap (host/mapper_match_gpu.cpp) against the stand-in map headers and link its
+    self-test driver."""
+    host = ROOT / "host"
+    build()
+    objs = []
+    deps = list(host.glob("*.hpp")) + list((host / "standin").rglob("*"))
+    for name in ("mapper_match_gpu.cpp", "mapper_selftest.cpp"):
+        obj = LIB / "obj" / (name + ".o")
+        src = host / name
+        if _newer(src, obj) or any(d.is_file() and _newer(d, obj) for d in deps):
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", str(host / "standin" / "ref"), "-I", str(host / "standin"),
+                   "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        objs.append(str(obj))
+    exe = LIB / "mapper_selftest"
+    subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return exe
 
 

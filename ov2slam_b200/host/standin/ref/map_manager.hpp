@@ -23,7 +23,12 @@ struct SlamParams {
 
 class CameraCalibration {
 public:
+    enum Model { Pinhole, Fisheye };
+    Model model_ = Pinhole;
     double fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0;
+    double k1_ = 0, k2_ = 0, p1_ = 0, p2_ = 0;
+    double img_w_ = 0, img_h_ = 0;
+    cv::Mat Dcv_;                                       // empty: no distortion (camera_calibration.cpp:262)
     Eigen::Matrix3d iK_;
     Sophus::SE3d Tc0ci_;
     void setK(double fx, double fy, double cx, double cy) {
@@ -36,6 +41,7 @@ public:
 
 struct Keypoint {
     int lmid_ = -1;
+    cv::Point2f px_;
     cv::Point2f unpx_, runpx_;
     int scale_ = 0;
     bool is3d_ = false, is_stereo_ = false;
@@ -47,9 +53,17 @@ public:
     size_t nbkps_ = 0, nb2dkps_ = 0, nb3dkps_ = 0, nb_stereo_kps_ = 0;
     std::shared_ptr<CameraCalibration> pcalib_leftcam_, pcalib_rightcam_;
     std::unordered_map<int, Keypoint> mapkps_;
+    std::vector<std::vector<int>> vgridkps_;            // keypoint (= map point) ids per grid cell, insertion order
+    size_t ncellsize_ = 35, nbwcells_ = 0, nbhcells_ = 0;
     std::map<int, int> covkfs_;
     Sophus::SE3d Twc_;
 
+    std::vector<Keypoint> getKeypoints() const {
+        std::vector<Keypoint> v;
+        for (const auto& kv : mapkps_) v.push_back(kv.second);
+        return v;
+    }
+    bool isObservingKp(const int lmid) const { return mapkps_.count(lmid) != 0; }
     std::vector<Keypoint> getKeypoints3d() const {
         std::vector<Keypoint> v;
         for (const auto& kv : mapkps_) if (kv.second.is3d_) v.push_back(kv.second);
@@ -68,8 +82,10 @@ public:
 class MapPoint {
 public:
     int lmid_ = -1, kfid_ = -1;
-    bool isobs_ = true, bad_ = false;
+    bool isobs_ = true, bad_ = false, is3d_ = true;
     double invdepth_ = -1;
+    cv::Mat desc_;                                      // the map point's representative descriptor (1 x 32, 8-bit)
+    std::unordered_map<int, cv::Mat> map_kf_desc_;      // one descriptor per observing keyframe
     Eigen::Vector3d ptxyz_;
     std::set<int> set_kfids_;
     bool isBad() const { return bad_; }

@@ -1,12 +1,16 @@
 """The drop-in C++ classes (ov2slam_b200/host/) behave like the Python binding of the same C ABI:
 CPU part = they compile and link; GPU part = same keypoints / descriptors / tracks."""
+import os
 import subprocess
+from pathlib import Path
 
 import numpy as np
 import pytest
 
 from ov2slam_b200 import api, build, synth
 from oracle import image_ref as R_img
+
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_host_shims_compile_and_link():
@@ -197,3 +201,118 @@ def test_optimizer_loose_and_full_ba_shims(ctx, tmp_path, mode, stereo):
     alive = invd >= 0
     assert alive.mean() > 0.9
     assert np.abs(invd[alive] - ref["lm_invdepth"][alive]).max() <= 1e-6 * np.abs(ref["lm_invdepth"][alive]).max() + 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- Mapper::matchToMap drop-in
+def _write_match_scene(path, sc):
+    hd = np.array([len(sc["kp_px"]), len(sc["mp_xyz"]), len(sc["desc"]), len(sc["obs_kf"]), len(sc["kf_Tcw"]), len(sc["cand_mp"]),
+                   len(sc["cell_ptr"]) - 1, sc["nbwcells"], sc["ncellsize"], sc["img_w"], sc["img_h"], sc["dist"] is not None], np.int32)
+    dist = np.zeros(5) if sc["dist"] is None else np.asarray(sc["dist"], np.float64)
+    with open(path, "wb") as f:
+        f.write(hd.tobytes())
+        for a, t in ((sc["K"], np.float64), (dist, np.float64), (sc["Tcw"], np.float64), (sc["kf_Tcw"], np.float64), (sc["mp_xyz"], np.float64),
+                     (sc["kp_px"], np.float32), (sc["obs_px"], np.float32), (sc["cell_ptr"], np.int32), (sc["cell_kp"], np.int32),
+                     (sc["kp_lm"], np.int32), (sc["mp_desc_ptr"], np.int32), (sc["mp_obs_ptr"], np.int32), (sc["obs_kf"], np.int32),
+                     (sc["cand_mp"], np.int32), (sc["desc"], np.uint8)):
+            f.write(np.ascontiguousarray(a, t).tobytes())
+
+
+def _read_match_result(path):
+    raw = np.fromfile(path, np.int32)
+    n = int(raw[0])
+    order = raw[1:1 + n]
+    m = int(raw[1 + n])
+    pairs = raw[2 + n:2 + n + 2 * m].reshape(m, 2)
+    return order, {(int(a), int(b)) for a, b in pairs}, int(raw[2 + n + 2 * m])
+
+
+def _read_match_dump(path):
+    raw = np.fromfile(path, np.uint8)
+    hd = raw[:48].view(np.int32)
+    nkps, nmps, ndesc, nobs, nkfs, ncand, ncells, nbw, cs, w, h, has_dist = (int(v) for v in hd)
+    fl = raw[48:60].view(np.float32)
+    off = [60]
+
+    def take(n, t):
+        b = n * np.dtype(t).itemsize
+        a = raw[off[0]:off[0] + b].view(t).copy()
+        off[0] += b
+        return a
+    sc = dict(img_w=w, img_h=h, ncellsize=cs, nbwcells=nbw, dmaxpxdist=fl[0], fdistratio=fl[1], view_th=fl[2])
+    sc["K"] = take(4, np.float64)
+    d = take(5, np.float64)
+    sc["dist"] = d if has_dist else None
+    sc["Tcw"] = take(12, np.float64)
+    sc["kf_Tcw"] = take(12 * nkfs, np.float64).reshape(nkfs, 12)
+    sc["mp_xyz"] = take(3 * nmps, np.float64).reshape(nmps, 3)
+    sc["kp_px"] = take(2 * nkps, np.float32).reshape(nkps, 2)
+    sc["obs_px"] = take(2 * nobs, np.float32).reshape(nobs, 2)
+    sc["cell_ptr"] = take(ncells + 1, np.int32)
+    sc["cell_kp"] = take(int(sc["cell_ptr"][-1]), np.int32)
+    sc["kp_lm"] = take(nkps, np.int32)
+    sc["mp_desc_ptr"] = take(nmps + 1, np.int32)
+    sc["mp_obs_ptr"] = take(nmps + 1, np.int32)
+    sc["obs_kf"] = take(nobs, np.int32)
+    sc["cand_mp"] = take(ncand, np.int32)
+    sc["mp_kfmask"] = take(4 * nmps, np.uint64).reshape(nmps, 4)
+    sc["desc"] = take(32 * ndesc, np.uint8).reshape(ndesc, 32)
+    assert off[0] == len(raw)
+    return sc
+
+
+def _match_pairs_by_identity(sc, kp_match):
+    """(keypoint, map point) pairs named by what they ARE (pixel + own map point's position; candidate's position), so that two
+    flattenings of the same map with different index orders can be compared."""
+    out = set()
+    for j, c in enumerate(kp_match):
+        if c >= 0:
+            out.add((tuple(sc["kp_px"][j]), tuple(sc["mp_xyz"][sc["kp_lm"][j]]), tuple(sc["mp_xyz"][sc["cand_mp"][c]])))
+    return out
+
+
+@pytest.mark.parametrize("distorted", [True, False])
+def test_mapper_match_shim_flattens_the_map_like_the_scene(tmp_path, distorted):
+    """The drop-in Mapper::matchToMap (host/mapper_match_gpu.cpp, against the stand-in map classes) on a synthetic map, with the
+    GPU call replaced by a recorder (tests/helpers/match_dump.c, LD_PRELOAD): the flat problem it builds from the frame grid, the
+    keyframes and the map points gives, through the oracle, the matches of the scene the map was built from (candidates in the
+    order the shim walked the id set); map points without descriptor are filtered, keypoints whose map point is gone are dropped
+    from the map (mapper.cpp:667-672), the search radius doubles for a frame with fewer than 30 3-D keypoints."""
+    from oracle import match_ref as M
+    exe = build.build_mapper_shim()
+    rec = tmp_path / "librec.so"
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-o", str(rec), str(ROOT / "tests" / "helpers" / "match_dump.c")])
+    sc = synth.make_match_scene(5 + distorted, nkps=500, ncand=260, nkfs=9, distorted=distorted)
+    _write_match_scene(tmp_path / "s.bin", sc)
+    env = dict(os.environ, LD_PRELOAD=str(rec), OV2_MATCH_DUMP=str(tmp_path / "d.bin"))
+    out = subprocess.run([str(exe), str(tmp_path / "s.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    order, pairs, ndropped = _read_match_result(tmp_path / "r.bin")
+    assert not pairs and ndropped == int((sc["kp_lm"] < 0).sum())
+    dump = _read_match_dump(tmp_path / "d.bin")
+    assert dump["dmaxpxdist"] == sc["dmaxpxdist"] and dump["fdistratio"] == sc["fdistratio"]
+    assert abs(float(dump["view_th"]) - float(sc["view_th"])) <= 1e-6
+    ndesc_of = np.diff(sc["mp_desc_ptr"])
+    assert len(dump["cand_mp"]) == int((ndesc_of[sc["cand_mp"]] > 0).sum())
+    ref = dict(sc, cand_mp=np.asarray(order, np.int32))
+    want = _match_pairs_by_identity(ref, M.match_to_map(ref)[2])
+    got = _match_pairs_by_identity(dump, M.match_to_map(dump)[2])
+    assert len(want) > 40
+    # poses travel through unit quaternions (as in the reference's map): last-bit differences in the projections
+    assert len(want ^ got) <= max(1, len(want) // 100)
+
+
+@pytest.mark.gpu
+def test_mapper_match_shim_matches_python_binding(ctx, tmp_path):
+    """The same drop-in end to end on the GPU: the (keypoint id -> map-point id) map it returns equals ov2_match_to_map on the scene
+    the map was built from, candidates in the order the shim walked the id set."""
+    exe = build.build_mapper_shim()
+    sc = synth.make_match_scene(9, nkps=1200, ncand=700, nkfs=12, distorted=True)
+    _write_match_scene(tmp_path / "s.bin", sc)
+    out = subprocess.run([str(exe), str(tmp_path / "s.bin"), str(tmp_path / "r.bin")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    order, pairs, _ = _read_match_result(tmp_path / "r.bin")
+    ref = dict(sc, cand_mp=np.asarray(order, np.int32))
+    _, _, kp_match, _ = api.match_to_map(ctx, ref)
+    want = {(int(sc["kp_lm"][j]), int(order[c])) for j, c in enumerate(kp_match) if c >= 0}
+    assert len(want) > 100
+    assert len(want ^ pairs) <= max(1, len(want) // 100)
