@@ -121,6 +121,7 @@ def build_optimizer_shim(verbose: bool = False) -> Path:
     exe = LIB / "optimizer_selftest"
     subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     build_mapper_shim(verbose)
+    build_stereo_shim(verbose)
     return exe
 
 
@@ -142,6 +143,28 @@ def build_mapper_shim(verbose: bool = False) -> Path:
             subprocess.check_call(cmd)
         objs.append(str(obj))
     exe = LIB / "mapper_selftest"
+    subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    return exe
+
+
+def build_stereo_shim(verbose: bool = False) -> Path:
+    """Compile the drop-in MapManager::stereoMatching (host/map_manager_stereo_gpu.cpp) with the drop-in FeatureTracker against the
+    stand-in map / OpenCV headers and link its self-test driver."""
+    host = ROOT / "host"
+    build()
+    objs = []
+    deps = list(host.glob("*.hpp")) + list((host / "standin").rglob("*"))
+    for name in ("feature_tracker.cpp", "map_manager_stereo_gpu.cpp", "stereo_selftest.cpp"):
+        obj = LIB / "obj" / (name + ".stereo.o")
+        src = host / name
+        if _newer(src, obj) or any(d.is_file() and _newer(d, obj) for d in deps):
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", str(host / "standin" / "ref"), "-I", str(host / "standin"), "-I", str(host),
+                   "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        objs.append(str(obj))
+    exe = LIB / "stereo_selftest"
     subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return exe
 

@@ -106,6 +106,13 @@ std::map<int,int> Mapper::matchToMap(const Frame &frame, const float fmaxprojerr
         }
         cell_ptr[c + 1] = (int32_t)cell_kp.size();
     }
+    // the ABI stages nkps grid entries: a grid that lists fewer keypoints than the frame holds is padded (the padding is never
+    // reached through cell_ptr); one that lists more (an id in two cells) is not something the reference's Frame produces
+    if (cell_kp.size() > vkps.size()) {
+        std::cerr << "[ov2b200] matchToMap: the frame's grid lists more keypoints than the frame holds\n";
+        return map_previd_newid;
+    }
+    cell_kp.resize(vkps.size(), 0);
     // ---- per map point: world point, descriptors, keyframe set (as raw as getKfObsSet() returns it), valid observations
     std::unordered_map<int, int> kf_index;
     std::vector<std::shared_ptr<Frame>> kfs;

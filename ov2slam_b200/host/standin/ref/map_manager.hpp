@@ -4,6 +4,7 @@
 // ov2slam_b200/host/optimizer_localba_gpu.cpp in a container without the reference's dependencies (ROS, PCL, OpenCV,
 // Eigen, Sophus); on a box that builds the reference, its own headers are used instead.
 #pragma once
+#include <cmath>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -15,8 +16,13 @@
 #include <opencv2/core.hpp>
 #include <sophus/se3.hpp>
 
+class FeatureTracker;   // the drop-in class of host/feature_tracker.hpp (the reference's include/feature_tracker.hpp)
+
 struct SlamParams {
     int nmin_covscore_ = 25;
+    int nklt_pyr_lvl_ = 3, nklt_win_size_ = 9;
+    float nklt_err_ = 30.f, fmax_fbklt_dist_ = 0.5f;
+    bool bdo_stereo_rect_ = false, debug_ = false, log_timings_ = false;
     bool stereo_ = false, buse_inv_depth_ = true, apply_l2_after_robust_ = true;
     float robust_mono_th_ = 5.9915f;
 };
@@ -37,12 +43,18 @@ public:
         iK_.m[0] = 1.0 / fx; iK_.m[2] = -cx / fx; iK_.m[4] = 1.0 / fy; iK_.m[5] = -cy / fy;
     }
     Sophus::SE3d getExtrinsic() const { return Tc0ci_; }
+    // stand-in calibrations carry no distortion model on this path (rectified / undistorted images)
+    cv::Point2f undistortImagePoint(const cv::Point2f& pt) const { return pt; }
+    cv::Point2f projectCamToImageDist(const Eigen::Vector3d& pt) const {
+        return cv::Point2f((float)(fx_ * pt.x() / pt.z() + cx_), (float)(fy_ * pt.y() / pt.z() + cy_));
+    }
 };
 
 struct Keypoint {
     int lmid_ = -1;
     cv::Point2f px_;
-    cv::Point2f unpx_, runpx_;
+    cv::Point2f unpx_, runpx_, rpx_;
+    Eigen::Vector3d bv_;
     int scale_ = 0;
     bool is3d_ = false, is_stereo_ = false;
 };
@@ -73,6 +85,34 @@ public:
     void removeStereoKeypointById(const int lmid) { auto it = mapkps_.find(lmid); if (it != mapkps_.end()) it->second.is_stereo_ = false; }
     Sophus::SE3d getTcw() const { return Twc_.inverse(); }
     Eigen::Vector3d projWorldToCam(const Eigen::Vector3d& wpt) const { return Twc_.inverse() * wpt; }
+    // ---- what MapManager::stereoMatching reads and writes (frame.cpp:423-433, 594-622, 830-870)
+    Eigen::Matrix3d Frl_;
+    cv::Point2f projCamToRightImageDist(const Eigen::Vector3d& pt) const {
+        return pcalib_rightcam_->projectCamToImageDist(pcalib_rightcam_->Tc0ci_.inverse() * pt);
+    }
+    cv::Point2f projWorldToRightImageDist(const Eigen::Vector3d& wpt) const { return projCamToRightImageDist(projWorldToCam(wpt)); }
+    bool isInRightImage(const cv::Point2f& pt) const {
+        return pt.x >= 0 && pt.y >= 0 && pt.x < pcalib_rightcam_->img_w_ && pt.y < pcalib_rightcam_->img_h_;
+    }
+    std::vector<Keypoint> getSurroundingKeypoints(const Keypoint& kp) const {
+        std::vector<Keypoint> vkps;
+        const int rkp = (int)std::floor(kp.px_.y / ncellsize_), ckp = (int)std::floor(kp.px_.x / ncellsize_);
+        for (int r = rkp - 1; r < rkp + 1; r++)
+            for (int c = ckp - 1; c < ckp + 1; c++) {
+                const int idx = r * (int)nbwcells_ + c;
+                if (r < 0 || c < 0 || idx >= (int)vgridkps_.size()) continue;
+                for (const int id : vgridkps_[idx])
+                    if (id != kp.lmid_) { auto it = mapkps_.find(id); if (it != mapkps_.end()) vkps.push_back(it->second); }
+            }
+        return vkps;
+    }
+    void updateKeypointStereo(const int lmid, const cv::Point2f& pt) {
+        auto it = mapkps_.find(lmid);
+        if (it == mapkps_.end()) return;
+        it->second.rpx_ = pt;
+        it->second.runpx_ = pcalib_rightcam_->undistortImagePoint(pt);
+        if (!it->second.is_stereo_) { it->second.is_stereo_ = true; nb_stereo_kps_++; }
+    }
     Sophus::SE3d getTwc() const { return Twc_; }
     void setTwc(const Sophus::SE3d& Twc) { Twc_ = Twc; }
     std::map<int, int> getCovisibleKfMap() const { return covkfs_; }
@@ -98,6 +138,9 @@ public:
     std::unordered_map<int, std::shared_ptr<Frame>> map_pkfs_;
     std::unordered_map<int, std::shared_ptr<MapPoint>> map_plms_;
     std::shared_ptr<Frame> pcurframe_;
+    std::shared_ptr<SlamParams> pslamstate_;
+    std::shared_ptr<FeatureTracker> ptracker_;
+    void stereoMatching(Frame &frame, const std::vector<cv::Mat> &vleftpyr, const std::vector<cv::Mat> &vrightpyr);   // map_manager.hpp:83
     int nkfid_ = 0;                                     // id of the newest keyframe
     std::mutex map_mutex_, optim_mutex_;
     std::vector<std::pair<int, int>> removed_obs_;      // (lmid, kfid) - for the self-test's report

@@ -2,7 +2,10 @@
 // that class the per-frame pose refinement links against (src/visual_front_end.cpp:791-801).  Stand-in copy for the
 // container's compile check; a real build includes the reference's own header (Eigen::Vector2d comes from Eigen there).
 #pragma once
+#include <cmath>
 #include <vector>
+
+#include <opencv2/core.hpp>
 
 #include <Eigen/Dense>
 #include <sophus/se3.hpp>
@@ -19,6 +22,17 @@ struct Vector2d {
 
 class MultiViewGeometry {
 public:
+    // multi_view_geometry.cpp:798-821 (float intermediates as there)
+    static float computeSampsonDistance(const Eigen::Matrix3d &Frl, const cv::Point2f &leftpt, const cv::Point2f &rightpt) {
+        const Eigen::Vector3d l(leftpt.x, leftpt.y, 1.), r(rightpt.x, rightpt.y, 1.);
+        const Eigen::Vector3d Fl = Frl * l, Ftr = Frl.transpose() * r;
+        float num = (float)(r.x() * Fl.x() + r.y() * Fl.y() + r.z() * Fl.z());
+        num *= num;
+        const float x1 = (float)Ftr.x(), x2 = (float)Fl.x(), y1 = (float)Ftr.y(), y2 = (float)Fl.y();
+        const float den = x1 * x1 + y1 * y1 + x2 * x2 + y2 * y2;
+        return std::sqrt(num / den);
+    }
+
     static bool ceresPnP(const std::vector<Eigen::Vector2d, Eigen::aligned_allocator<Eigen::Vector2d> > &vunkps,
                         const std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d> > &vwpts,
                         Sophus::SE3d &Twc,
