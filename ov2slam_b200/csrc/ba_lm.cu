@@ -35,6 +35,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include <thread>
 
 namespace balm {
@@ -1914,10 +1915,12 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         // reference's flow, optimizer.cpp:43-430); only windows whose poses live on the device are inspected array by array.
         const bool win_dev = ov2_is_device_ptr(pb.pose);
         win_on_device[k] = win_dev ? 1 : 0;
+        cudaError_t pull_err = cudaSuccess;
         auto pull = [&](const void* p, size_t bytes) -> const void* {
             if (!p || bytes == 0 || !win_dev || !ov2_is_device_ptr(p)) return p;
             hold.emplace_back(bytes);
-            cudaMemcpy(hold.back().data(), p, bytes, cudaMemcpyDeviceToHost);
+            const cudaError_t ce = cudaMemcpy(hold.back().data(), p, bytes, cudaMemcpyDeviceToHost);
+            if (ce != cudaSuccess) pull_err = ce;
             return hold.back().data();
         };
         hp[k].K = (const double*)pull(pb.K, 32);
@@ -1930,6 +1933,7 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
         hp[k].obs_type = (const uint8_t*)pull(pb.obs_type, (size_t)pb.nobs);
         hp[k].Kr = (const double*)pull(pb.Kr, 32);
         hp[k].Trl = (const double*)pull(pb.Trl, 56);
+        if (pull_err != cudaSuccess) return ov2_fail(ctx, OV2_ERR_CUDA, "ov2_localba_solve: staging a device-resident window", pull_err);
         if (pb.obs_type && (!pb.Kr || !pb.Trl)) return ov2_fail(ctx, OV2_ERR_INVALID, "ov2_localba_solve: obs_type given without Kr / Trl");
         if ((st = plan_window(ctx, &hp[k], world, st_off, in_off, work_off, zero_off, out_off, act_off, plans[k], 8, nprob == 1)) != OV2_OK) return st;
         if (plans[k].smem_bytes > smem_max) smem_max = plans[k].smem_bytes;
@@ -2061,7 +2065,10 @@ ov2_status balm_solve(ov2_ctx* ctx, int nprob, const ov2_ba_problem* pbs, const 
     {
         // raised only when a window needs more than any before (a function-attribute change while another stream runs the
         // kernel may serialise with it)
+        // (check + set + record under one lock: two host threads with their own contexts may make their first solves concurrently)
         static size_t attr_smem[16] = {0};
+        static std::mutex attr_mu;
+        std::lock_guard<std::mutex> attr_lock(attr_mu);
         const int dv = ctx->device & 15;
         if (smem_max > attr_smem[dv]) {
             OV2_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
