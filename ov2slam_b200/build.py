@@ -85,7 +85,7 @@ def build_host_shims(verbose: bool = False) -> Path:
     host = ROOT / "host"
     build()
     objs = []
-    for name in ("feature_extractor.cpp", "feature_tracker.cpp", "shim_selftest.cpp"):
+    for name in ("feature_extractor.cpp", "feature_tracker.cpp", "shim_selftest.cpp", "clahe_gpu.cpp", "clahe_selftest.cpp"):
         obj = LIB / "obj" / (name + ".o")
         src = host / name
         if _newer(src, obj) or any(_newer(h, obj) for h in host.glob("*.hpp")):
@@ -95,7 +95,9 @@ def build_host_shims(verbose: bool = False) -> Path:
             subprocess.check_call(cmd)
         objs.append(str(obj))
     exe = LIB / "shim_selftest"
-    subprocess.check_call(["g++", "-o", str(exe), *objs, "-L", str(LIB), "-lov2b200", "-lpthread",
+    subprocess.check_call(["g++", "-o", str(exe), *objs[:3], "-L", str(LIB), "-lov2b200", "-lpthread",
+                           "-Wl,-rpath,$ORIGIN"])
+    subprocess.check_call(["g++", "-o", str(LIB / "clahe_selftest"), *objs[3:], "-L", str(LIB), "-lov2b200", "-lpthread",
                            "-Wl,-rpath,$ORIGIN"])
     build_optimizer_shim(verbose)
     return exe

@@ -9,6 +9,7 @@
 #include <memory>
 #include <vector>
 
+#define OV2_STANDIN_OPENCV 1
 #define CV_8U 0
 #define CV_8UC1 0
 

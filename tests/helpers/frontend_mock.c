@@ -3,6 +3,7 @@
  * MapManager::stereoMatching drop-in (ov2slam_b200/host/map_manager_stereo_gpu.cpp: which keypoints go to which tracker call with
  * which prior, what happens to the answers) can be checked on a box without a GPU.  Every tracker / row-search call is appended to
  * $OV2_MOCK_LOG; tests/test_host_shim.py replays the same rules in Python.
+ *   CLAHE        dst = 255 - src (row strides honoured), arguments logged
  *   row search   xprior = floor(x) - 2 when floor(x) >= 3 and floor(y) % 4 != 0, else -1
  *   tracker      prior += (-0.5, dy), dy = 4 when floor(pt.x) % 7 == 0 else 0.25;
  *                status = floor(3 pt.x + pt.y) % 4 != 0 on a 2-level call (nbpyrlvl 1), floor(pt.x + 2 pt.y) % 6 != 0 otherwise */
@@ -72,5 +73,22 @@ ov2_status ov2_fb_klt(ov2_ctx* ctx, const ov2_pyr* prev, const ov2_pyr* cur, con
         priors_inout[2 * i + 1] += ((int)floorf(x) % 7 == 0) ? 4.f : 0.25f;
         status_out[i] = nbpyrlvl_all == 1 ? ((int)floorf(3.f * x + y) % 4 != 0) : ((int)floorf(x + 2.f * y) % 6 != 0);
     }
+    return OV2_OK;
+}
+
+ov2_status ov2_clahe(ov2_ctx* ctx, const uint8_t* src, uint8_t* dst, int width, int height, size_t row_stride, size_t frame_stride, int count,
+                     double clip_limit, int tiles_x, int tiles_y) {
+    (void)ctx; (void)frame_stride;
+    FILE* f = log_file();
+    if (f) {
+        int32_t hd[8] = {4, width, height, (int32_t)row_stride, count, (int32_t)(clip_limit * 1000), tiles_x, tiles_y};
+        hd[0] = 4;
+        fwrite(hd, 4, 8, f);
+        int32_t inplace = src == dst;
+        fwrite(&inplace, 4, 1, f);
+        fclose(f);
+    }
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) dst[(size_t)y * row_stride + x] = (uint8_t)(255 - src[(size_t)y * row_stride + x]);
     return OV2_OK;
 }

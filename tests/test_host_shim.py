@@ -562,3 +562,27 @@ def test_stereo_matching_shim_on_the_device(tmp_path):
     err = np.abs(rpx[inner & is_stereo] - (px[inner & is_stereo] - np.array([disp, 0.0], np.float32)))
     assert np.median(err[:, 0]) < 0.05 and (err[:, 0] < 0.5).mean() > 0.97 and err[:, 1].max() == 0.0
     assert not is_stereo[~alive].any()
+
+
+def test_clahe_adapter_routes_cv_clahe_calls_to_the_device_call(tmp_path):
+    """The cv::CLAHE adapter (host/clahe_gpu.cpp; replaces the reference's one cv::createCLAHE call, ov2slam.cpp:87) with the device
+    call mocked (dst = 255 - src): a ROI source (row step > width) into a fresh destination and an in-place call both reach
+    ov2_clahe with the image size, ONE row stride valid for both buffers, clip limit 3 and the W/50 x H/50 tile grid; an empty
+    image gives an empty result."""
+    build.build_host_shims()
+    exe = build.LIB / "clahe_selftest"
+    mock = tmp_path / "libmock.so"
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-o", str(mock), str(ROOT / "tests" / "helpers" / "frontend_mock.c"), "-lm"])
+    w, h = 173, 121
+    env = dict(os.environ, LD_PRELOAD=str(mock), OV2_MOCK_LOG=str(tmp_path / "log.bin"))
+    out = subprocess.run([str(exe), str(w), str(h), str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=60, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    yy, xx = np.mgrid[0:h, 0:w]
+    src = ((xx * 7 + yy * 13 + (xx * yy) % 5) & 255).astype(np.uint8)
+    got = np.fromfile(tmp_path / "o.bin", np.uint8).reshape(2, h, w)
+    assert np.array_equal(got[0], 255 - src) and np.array_equal(got[1], 255 - src)
+    log = np.fromfile(tmp_path / "log.bin", np.int32).reshape(-1, 9)
+    assert len(log) == 2 and (log[:, 0] == 4).all()
+    for rec in log:
+        assert tuple(rec[1:3]) == (w, h) and rec[3] == w and rec[4] == 1 and rec[5] == 3000 and tuple(rec[6:8]) == (w // 50, h // 50)
+        assert rec[8] == 1          # both calls equalise in place in the destination's layout (the source was copied there first / is it)
