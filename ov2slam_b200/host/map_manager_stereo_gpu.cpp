@@ -19,168 +19,125 @@
 #include "multi_view_geometry.hpp"
 #include "feature_tracker.hpp"         // the drop-in class (host/feature_tracker.hpp)
 
+namespace {
+
+// keypoints queued for one tracker call: id, left pixel, starting point in the right image
+struct TrackQueue {
+    std::vector<int> ids;
+    std::vector<cv::Point2f> left, right;
+    void push(int id, const cv::Point2f& l, const cv::Point2f& r) { ids.push_back(id); left.push_back(l); right.push_back(r); }
+    bool empty() const { return ids.empty(); }
+    size_t size() const { return ids.size(); }
+};
+
+// the inverse-distance-weighted depth of the 3-D keypoints around `kp` (the four grid cells Frame::getSurroundingKeypoints visits);
+// false when there is none (map_manager.cpp:437-463)
+bool neighbour_depth(const MapManager& map, const Frame& frame, const Keypoint& kp, double& depth) {
+    double zsum = 0., wsum = 0.;
+    size_t used = 0;
+    for (const auto& other : frame.getSurroundingKeypoints(kp)) {
+        if (!other.is3d_) continue;
+        const auto plm = map.getMapPoint(other.lmid_);
+        if (plm == nullptr) continue;
+        const float dx = other.unpx_.x - kp.unpx_.x, dy = other.unpx_.y - kp.unpx_.y;      // cv::norm(Point2f): float difference,
+        const double wgt = 1. / std::sqrt((double)dx * dx + (double)dy * dy);               // double sum of squares
+        wsum += wgt;
+        zsum += wgt * frame.projWorldToCam(plm->getPoint()).z();
+        used++;
+    }
+    if (used == 0) return false;
+    depth = zsum / wsum;
+    return true;
+}
+
+}  // namespace
+
 void MapManager::stereoMatching(Frame &frame, const std::vector<cv::Mat> &vleftpyr, const std::vector<cv::Mat> &vrightpyr)
 {
-    // Find stereo correspondances with left kps
-    auto vleftkps = frame.getKeypoints();
-    size_t nbkps = vleftkps.size();
-
-    const size_t nmaxpyrlvl = pslamstate_->nklt_pyr_lvl_ * 2;          // index of the coarsest image in the pyramid vectors
-    const int winsize = 7;
-    const float uppyrcoef = std::pow(2, pslamstate_->nklt_pyr_lvl_);
-    const float downpyrcoef = 1. / uppyrcoef;
-
-    std::vector<int> v3dkpids, vkpids;
-    std::vector<cv::Point2f> v3dkps, v3dpriors, vkps, vpriors;
-    v3dkpids.reserve(frame.nb3dkps_); v3dkps.reserve(frame.nb3dkps_); v3dpriors.reserve(frame.nb3dkps_);
-    vkpids.reserve(nbkps); vkps.reserve(nbkps); vpriors.reserve(nbkps);
-
-    // rectified rigs: the keypoints whose prior comes from the row search, and where their prior sits in vpriors
-    std::vector<cv::Point2f> vsadpts;
-    std::vector<size_t> vsadslot;
-    const bool bsad = pslamstate_->bdo_stereo_rect_;
-    if (bsad && (vleftpyr.size() <= nmaxpyrlvl || vrightpyr.size() <= nmaxpyrlvl)) {
-        std::cerr << "[ov2b200] stereoMatching: the pyramids have no level " << pslamstate_->nklt_pyr_lvl_ << " for the row search\n";
+    const SlamParams& cfg = *pslamstate_;
+    const bool rectified = cfg.bdo_stereo_rect_;
+    const int coarsest = cfg.nklt_pyr_lvl_;                      // pyramid level of the row search (entry 2 * level of the vectors)
+    const float up = std::pow(2, coarsest), down = 1. / up;
+    if (rectified && (vleftpyr.size() <= (size_t)(2 * coarsest) || vrightpyr.size() <= (size_t)(2 * coarsest))) {
+        std::cerr << "[ov2b200] stereoMatching: the pyramids have no level " << coarsest << " for the row search\n";
         return;
     }
 
-    for (size_t i = 0; i < nbkps; i++) {
-        auto &kp = vleftkps.at(i);
-        cv::Point2f priorpt = kp.px_;
-
-        // If 3D, check if we can find a prior in right image (:405-420)
+    // ---- 1. every keypoint of the frame goes to one of two queues: `guided` (a prior from geometry exists: tracked on 2 levels
+    //         first) or `blind` (full pyramid).  Keypoint order is kept inside each queue.                       (:395-493)
+    TrackQueue guided, blind;
+    std::vector<cv::Point2f> rowsearch_pts;                       // rectified rigs: coarsest-level pixels awaiting the row search
+    std::vector<size_t> rowsearch_slot;                           // ... and the entry of `blind` each one belongs to
+    for (const Keypoint& kp : frame.getKeypoints()) {
         if (kp.is3d_) {
-            auto plm = getMapPoint(kp.lmid_);
-            if (plm != nullptr) {
-                cv::Point2f projpt = frame.projWorldToRightImageDist(plm->getPoint());
-                if (frame.isInRightImage(projpt)) {
-                    v3dkps.push_back(kp.px_);
-                    v3dpriors.push_back(projpt);
-                    v3dkpids.push_back(kp.lmid_);
-                    continue;
-                }
-            } else {
+            const auto plm = getMapPoint(kp.lmid_);
+            if (plm == nullptr) {                                 // dangling observation: drop it, no stereo for it (:411-414)
                 removeMapPointObs(kp.lmid_, frame.kfid_);
                 continue;
             }
+            const cv::Point2f proj = frame.projWorldToRightImageDist(plm->getPoint());
+            if (frame.isInRightImage(proj)) { guided.push(kp.lmid_, kp.px_, proj); continue; }
         }
-
-        if (bsad) {
-            // prior from the row search on the coarsest level: queued, resolved by one device call below (:422-435)
-            vsadpts.push_back(cv::Point2f(kp.px_.x * downpyrcoef, kp.px_.y * downpyrcoef));
-            vsadslot.push_back(vkps.size());
+        if (rectified) {
+            rowsearch_pts.push_back(cv::Point2f(kp.px_.x * down, kp.px_.y * down));
+            rowsearch_slot.push_back(blind.size());
         } else {
-            // prior from the depth of the 3-D neighbours (:437-480)
-            const size_t nbmin3dcokps = 1;
-            auto vnearkps = frame.getSurroundingKeypoints(kp);
-            size_t nb3dkp = 0;
-            double mean_z = 0., weights = 0.;
-            for (const auto &cokp : vnearkps) {
-                if (!cokp.is3d_) continue;
-                auto plm = getMapPoint(cokp.lmid_);
-                if (plm == nullptr) continue;
-                nb3dkp++;
-                const float dx = cokp.unpx_.x - kp.unpx_.x, dy = cokp.unpx_.y - kp.unpx_.y;       // cv::norm(Point2f): float difference,
-                const double coef = 1. / std::sqrt((double)dx * dx + (double)dy * dy);             // double sum of squares
-                weights += coef;
-                mean_z += coef * frame.projWorldToCam(plm->getPoint()).z();
-            }
-            if (nb3dkp >= nbmin3dcokps) {
-                mean_z /= weights;
-                const Eigen::Vector3d predcampt = mean_z * (kp.bv_ / kp.bv_.z());
-                cv::Point2f projpt = frame.projCamToRightImageDist(predcampt);
-                if (frame.isInRightImage(projpt)) {
-                    v3dkps.push_back(kp.px_);
-                    v3dpriors.push_back(projpt);
-                    v3dkpids.push_back(kp.lmid_);
-                    continue;
-                }
+            double depth;
+            if (neighbour_depth(*this, frame, kp, depth)) {
+                const Eigen::Vector3d campt = depth * (kp.bv_ / kp.bv_.z());
+                const cv::Point2f proj = frame.projCamToRightImageDist(campt);
+                if (frame.isInRightImage(proj)) { guided.push(kp.lmid_, kp.px_, proj); continue; }
             }
         }
-        vkpids.push_back(kp.lmid_);
-        vkps.push_back(kp.px_);
-        vpriors.push_back(priorpt);
+        blind.push(kp.lmid_, kp.px_, kp.px_);
     }
 
-    if (!vsadpts.empty()) {
-        std::vector<float> vxprior, vl1err;
-        ptracker_->getLineMinSADBatch(vleftpyr, vrightpyr, pslamstate_->nklt_pyr_lvl_, vsadpts, winsize, true, vxprior, vl1err);
-        for (size_t k = 0; k < vsadpts.size(); k++) {
-            float xprior = vxprior[k];
-            xprior *= uppyrcoef;
-            const size_t slot = vsadslot[k];
-            if (xprior >= 0 && xprior <= vkps[slot].x) vpriors[slot].x = xprior;       // :431-433
+    // ---- 2. rectified rigs: ONE device call finds the best column on the coarsest level for all queued keypoints; a hit to the
+    //         left of the keypoint becomes the x of its starting point                                            (:417-435)
+    if (!rowsearch_pts.empty()) {
+        std::vector<float> col, err;
+        ptracker_->getLineMinSADBatch(vleftpyr, vrightpyr, coarsest, rowsearch_pts, 7, true, col, err);
+        for (size_t k = 0; k < col.size(); ++k) {
+            const float x = col[k] * up;
+            const size_t slot = rowsearch_slot[k];
+            if (x >= 0 && x <= blind.left[slot].x) blind.right[slot].x = x;
         }
     }
 
-    // Storing good tracks
-    std::vector<cv::Point2f> vgoodrkps;
-    std::vector<int> vgoodids;
-    vgoodrkps.reserve(nbkps);
-    vgoodids.reserve(nbkps);
-
-    // 1st track 3d kps if using prior (:497-541)
-    if (!v3dpriors.empty()) {
-        size_t nbpyrlvl = 1;
-        int nwinsize = pslamstate_->nklt_win_size_;
-        if (vleftpyr.size() < 2 * (nbpyrlvl + 1)) nbpyrlvl = vleftpyr.size() / 2 - 1;
-        std::vector<bool> vkpstatus;
-        ptracker_->fbKltTracking(vleftpyr, vrightpyr, nwinsize, nbpyrlvl, pslamstate_->nklt_err_, pslamstate_->fmax_fbklt_dist_,
-                                 v3dkps, v3dpriors, vkpstatus);
-        size_t nbgood = 0;
-        const size_t nb3dkps = v3dkps.size();
-        for (size_t i = 0; i < nb3dkps; i++) {
-            if (vkpstatus.at(i)) {
-                vgoodrkps.push_back(v3dpriors.at(i));
-                vgoodids.push_back(v3dkpids.at(i));
-                nbgood++;
-            } else {
-                // tracking failed: retry on the full pyramid with the 2-D keypoints
-                vkpids.push_back(v3dkpids.at(i));
-                vkps.push_back(v3dkps.at(i));
-                vpriors.push_back(v3dpriors.at(i));
-            }
+    // ---- 3. the two forward-backward KLT passes; a guided track that fails is retried blind from where the tracker left it
+    TrackQueue matched;                                            // id, (unused), right pixel
+    auto track = [&](TrackQueue& q, int nlevels, TrackQueue* retry, const char* what) {
+        if (q.empty()) return;
+        std::vector<bool> ok;
+        ptracker_->fbKltTracking(vleftpyr, vrightpyr, cfg.nklt_win_size_, nlevels, cfg.nklt_err_, cfg.fmax_fbklt_dist_, q.left, q.right, ok);
+        size_t kept = 0;
+        for (size_t i = 0; i < q.size(); ++i) {
+            if (ok.at(i)) { matched.push(q.ids[i], q.left[i], q.right[i]); kept++; }
+            else if (retry) retry->push(q.ids[i], q.left[i], q.right[i]);
         }
-        if (pslamstate_->debug_)
-            std::cout << "\n >>> Stereo KLT Tracking on priors : " << nbgood << " out of " << nb3dkps << " kps tracked!\n";
-    }
+        if (cfg.debug_) std::cout << "\n >>> Stereo KLT Tracking " << what << " : " << kept << " out of " << q.size() << " kps tracked!\n";
+    };
+    int guided_levels = 1;                                         // 2 levels (:499-504)
+    if (vleftpyr.size() < 2 * (size_t)(guided_levels + 1)) guided_levels = (int)(vleftpyr.size() / 2) - 1;
+    track(guided, guided_levels, &blind, "on priors");
+    track(blind, cfg.nklt_pyr_lvl_, nullptr, "w. no priors");
 
-    // 2nd track other kps if any (:544-572)
-    if (!vkps.empty()) {
-        std::vector<bool> vkpstatus;
-        ptracker_->fbKltTracking(vleftpyr, vrightpyr, pslamstate_->nklt_win_size_, pslamstate_->nklt_pyr_lvl_, pslamstate_->nklt_err_,
-                                 pslamstate_->fmax_fbklt_dist_, vkps, vpriors, vkpstatus);
-        size_t nbgood = 0;
-        const size_t nb2dkps = vkps.size();
-        for (size_t i = 0; i < nb2dkps; i++) {
-            if (vkpstatus.at(i)) {
-                vgoodrkps.push_back(vpriors.at(i));
-                vgoodids.push_back(vkpids.at(i));
-                nbgood++;
-            }
-        }
-        if (pslamstate_->debug_)
-            std::cout << "\n >>> Stereo KLT Tracking w. no priors : " << nbgood << " out of " << nb2dkps << " kps tracked!\n";
-    }
-
-    nbkps = vgoodids.size();
-    size_t nbgood = 0;
-    float epi_err = 0.;
-    for (size_t i = 0; i < nbkps; i++) {
-        cv::Point2f lunpx = frame.getKeypointById(vgoodids.at(i)).unpx_;
-        cv::Point2f runpx = frame.pcalib_rightcam_->undistortImagePoint(vgoodrkps.at(i));
-        // Check epipolar consistency (same row for rectified images)
-        if (pslamstate_->bdo_stereo_rect_) {
-            epi_err = fabs(lunpx.y - runpx.y);
-            vgoodrkps.at(i).y = lunpx.y;               // correct the right keypoint onto the same row
+    // ---- 4. epipolar gate and map update (:575-604)
+    size_t nstereo = 0;
+    for (size_t i = 0; i < matched.size(); ++i) {
+        const cv::Point2f lun = frame.getKeypointById(matched.ids[i]).unpx_;
+        const cv::Point2f run = frame.pcalib_rightcam_->undistortImagePoint(matched.right[i]);
+        float epi;
+        if (rectified) {
+            epi = fabs(lun.y - run.y);
+            matched.right[i].y = lun.y;                            // same row by construction of the rig
         } else {
-            epi_err = MultiViewGeometry::computeSampsonDistance(frame.Frl_, lunpx, runpx);
+            epi = MultiViewGeometry::computeSampsonDistance(frame.Frl_, lun, run);
         }
-        if (epi_err <= 2.) {
-            frame.updateKeypointStereo(vgoodids.at(i), vgoodrkps.at(i));
-            nbgood++;
+        if (epi <= 2.) {
+            frame.updateKeypointStereo(matched.ids[i], matched.right[i]);
+            nstereo++;
         }
     }
-    if (pslamstate_->debug_)
-        std::cout << "\n \t>>> Nb of stereo tracks: " << nbgood << " out of " << nbkps << "\n";
+    if (cfg.debug_) std::cout << "\n \t>>> Nb of stereo tracks: " << nstereo << " out of " << matched.size() << "\n";
 }
