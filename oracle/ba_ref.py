@@ -19,7 +19,9 @@ numpy float64 restatement of what the reference executes between problem setup a
   unused / constant blocks        program.cc:305-387 (RemoveFixedBlocks)
   two-stage solve + outlier scan  /root/reference/src/optimizer.cpp:436-479, :492-594, :603-627, :637-735
 
-PINNING STATUS.  Ceres / Eigen / Sophus cannot be built in this container (no Eigen, glog), and
+PINNING STATUS.  The residuals, Jacobians and the pose update ARE pinned against the reference's own source (compiled in place against
+stand-in linear-algebra headers: oracle/ref_build, tests/test_oracle_vs_reference_source.py).  Ceres / Eigen / Sophus proper cannot be
+built in this container (no Eigen, glog), and
 the reference has no fixture for localBA, so the END-TO-END solve is **parity unpinned** against
 the real Ceres.  What is pinned (tests/test_oracle_ba.py):
   * HuberLoss and the Corrector against Ceres' own known answers (loss_function_test.cc:92-103,
