@@ -23,9 +23,10 @@ numpy float64 restatement of /root/reference/src/multi_view_geometry.cpp:492-588
 Deliberately not modelled: options.max_solver_time_in_seconds = 0.005 (:538), a wall-clock cap that
 makes the reference itself non-deterministic (Ceres checks it between iterations).
 
-PINNING STATUS: parity unpinned against the real Ceres (it cannot be built here); the Jacobian is
-pinned by central differences, the loop shares its LM / Huber / corrector pieces with ba_ref.py (pinned
-against Ceres' own known-answer tests), and the whole solve against ground truth and against
+PINNING STATUS: pinned against the real Ceres 2.0 of the reference tree running the reference's own cost function with the calls
+ceresPnP makes (DENSE_QR, Huber wrapper, outlier scan, L2 refinement): same outliers, verdict and pose to 1e-9
+(tests/test_oracle_vs_reference_ceres.py::test_ceres_pnp_equals_real_ceres; that build uses a stand-in linear-algebra header instead
+of Eigen, see oracle/ba_ref.py).  Also: the Jacobian against central differences, the whole solve against ground truth and against
 scipy.optimize.least_squares on the same cost (tests/test_oracle_pnp.py).
 """
 from __future__ import annotations

@@ -162,3 +162,63 @@ extern "C" int ov2ref_local_ba(int ncam, int npts, int nobs, const double* K, co
     for (int l = 0; l < npts; ++l) lm_invdepth[l] = invd[l][0];
     return solves;
 }
+
+// MultiViewGeometry::ceresPnP (/root/reference/src/multi_view_geometry.cpp:492-588) with the same Ceres calls: one pose block with
+// SE3LeftParameterization, ReprojectionErrorSE3 blocks (sigma = 2^scale) behind LossFunctionWrapper(HuberLoss(sqrt(chi2th))), DENSE_QR,
+// Levenberg-Marquardt, nmaxiter iterations, function_tolerance 1e-3; outlier scan on the last Evaluate; all outliers -> false without
+// touching Twc; optional second solve with the trivial loss on the inliers.  The 5 ms wall-clock cap is lifted.
+// Returns -1 when every block is an outlier, else summary.IsSolutionUsable().
+extern "C" int ov2ref_ceres_pnp(int n, const double* unpx, const double* wpts, const int32_t* scales, double* Twc, int nmaxiter, double chi2th_in,
+                                int use_robust, int apply_l2_after_robust, const double* Kin, uint8_t* outlier, double* summaries /* [2][8] */) {
+    const float chi2th = (float)chi2th_in;
+    const float fx = (float)Kin[0], fy = (float)Kin[1], cx = (float)Kin[2], cy = (float)Kin[3];      // float arguments (:497)
+    ceres::Problem problem;
+    const double chi2thrtsq = std::sqrt(chi2th);
+    auto* loss_function = new ceres::LossFunctionWrapper(new ceres::HuberLoss(chi2thrtsq), ceres::TAKE_OWNERSHIP);
+    if (!use_robust) loss_function->Reset(NULL, ceres::TAKE_OWNERSHIP);
+    std::array<double, 7> posepar;
+    for (int i = 0; i < 7; ++i) posepar[i] = Twc[i];
+    {   // PoseParametersBlock(0, Twc) stores Sophus' unit quaternion
+        const double q = std::sqrt(posepar[3] * posepar[3] + posepar[4] * posepar[4] + posepar[5] * posepar[5] + posepar[6] * posepar[6]);
+        for (int i = 3; i < 7; ++i) posepar[i] /= q;
+    }
+    problem.AddParameterBlock(posepar.data(), 7, new SE3LeftParameterization());
+    std::vector<DirectLeftSE3::ReprojectionErrorSE3*> verrors;
+    std::vector<ceres::ResidualBlockId> vrids;
+    for (int i = 0; i < n; ++i) {
+        auto* f = new DirectLeftSE3::ReprojectionErrorSE3(unpx[2 * i], unpx[2 * i + 1], fx, fy, cx, cy,
+                                                          Eigen::Vector3d(wpts[3 * i], wpts[3 * i + 1], wpts[3 * i + 2]), std::pow(2., scales ? scales[i] : 0));
+        vrids.push_back(problem.AddResidualBlock(f, loss_function, posepar.data()));
+        verrors.push_back(f);
+    }
+    ceres::Solver::Options options;
+    options.linear_solver_type = ceres::DENSE_QR;
+    options.trust_region_strategy_type = ceres::LEVENBERG_MARQUARDT;
+    options.num_threads = 1;
+    options.max_num_iterations = nmaxiter;
+    options.max_solver_time_in_seconds = 1e9;
+    options.function_tolerance = 1.e-3;
+    options.minimizer_progress_to_stdout = false;
+    options.logging_type = ceres::SILENT;
+    memset(summaries, 0, sizeof(double) * 16);
+    ceres::Solver::Summary summary;
+    ceres::Solve(options, &problem, &summary);
+    dump_summary(summary, summaries);
+    int nbbad = 0;
+    for (int i = 0; i < n; ++i) {
+        outlier[i] = 0;
+        if (verrors[i]->chi2err_ > chi2th || !verrors[i]->isdepthpositive_) {
+            if (apply_l2_after_robust) problem.RemoveResidualBlock(vrids[i]);
+            outlier[i] = 1;
+            nbbad++;
+        }
+    }
+    if (nbbad == n) return -1;
+    if (apply_l2_after_robust && nbbad > 0) {
+        loss_function->Reset(NULL, ceres::TAKE_OWNERSHIP);
+        ceres::Solve(options, &problem, &summary);
+        dump_summary(summary, summaries + 8);
+    }
+    for (int i = 0; i < 7; ++i) Twc[i] = posepar[i];
+    return summary.IsSolutionUsable() ? 1 : 0;
+}

@@ -150,3 +150,34 @@ def test_bal_structure_window_equals_real_ceres(lib):
     pb = {k: v for k, v in pb.items() if k != "truth_pose"}
     res, _ = check(lib, pb)
     assert res["n_outliers_first"] > 0
+
+
+@pytest.mark.parametrize("seed,npts,noise,nout", [(1, 300, 0.5, 30), (2, 120, 1.0, 0), (3, 700, 0.3, 100), (4, 40, 0.5, 8)])
+def test_ceres_pnp_equals_real_ceres(lib, seed, npts, noise, nout):
+    """oracle/pnp_ref.py::ceres_pnp against MultiViewGeometry::ceresPnP's Ceres calls (multi_view_geometry.cpp:492-588: one pose block,
+    ReprojectionErrorSE3 with sigma = 2^octave behind a Huber wrapper, DENSE_QR, 5 iterations, outlier scan, L2 refinement on the inliers)
+    run by the real Ceres on the reference's cost function: same outliers, same verdict, same pose."""
+    from oracle import pnp_ref as P
+    rng = np.random.default_rng(seed)
+    K = np.array([458.654, 457.296, 367.215, 248.375], np.float32).astype(np.float64)      # the reference passes floats
+    q = B.quat_normalize(np.array([0.05, -0.02, 0.03, 1.0]) + rng.normal(0, 0.1, 4))
+    Ttrue = np.concatenate([rng.normal(0, 0.5, 3), q])
+    R, t = B.quat_to_rot(q), Ttrue[:3]
+    pc = np.stack([rng.uniform(-2, 2, npts), rng.uniform(-1.5, 1.5, npts), rng.uniform(2, 9, npts)], 1)
+    w = pc @ R.T + t
+    px = np.stack([K[0] * pc[:, 0] / pc[:, 2] + K[2], K[1] * pc[:, 1] / pc[:, 2] + K[3]], 1) + rng.normal(0, noise, (npts, 2))
+    px[:nout] += rng.uniform(8, 40, (nout, 2)) * rng.choice([-1, 1], (nout, 2))
+    scales = rng.integers(0, 3, npts).astype(np.int32)
+    T0 = Ttrue.copy()
+    T0[:3] += rng.normal(0, 0.05, 3)
+    T0[3:] = B.quat_normalize(T0[3:] + rng.normal(0, 0.01, 4))
+    for robust, l2 in ((1, 1), (1, 0), (0, 0)):
+        T = T0.copy()
+        out, summ = np.zeros(npts, np.uint8), np.zeros((2, 8))
+        lib.ov2ref_ceres_pnp.restype = C.c_int
+        rc = lib.ov2ref_ceres_pnp(npts, np.ascontiguousarray(px).ctypes.data_as(D), np.ascontiguousarray(w).ctypes.data_as(D), scales.ctypes.data_as(I),
+                                  T.ctypes.data_as(D), 5, C.c_double(5.9915), robust, l2, K.ctypes.data_as(D), out.ctypes.data_as(U), summ.ctypes.data_as(D))
+        ok, pose, outliers = P.ceres_pnp(px, w, T0.copy(), K, nmaxiter=5, chi2th=5.9915, use_robust=bool(robust), apply_l2_after_robust=bool(l2), scales=scales)
+        assert rc in (0, 1) and bool(rc) == ok
+        assert np.array_equal(np.nonzero(out)[0], outliers) and (nout == 0 or len(outliers) >= nout // 2)
+        assert np.abs(T - pose).max() <= 1e-9
