@@ -123,6 +123,10 @@ def test_options_trivial_loss_and_single_stage(lib):
     check(lib, pb, l2=0)
     check(lib, pb, max_iters_robust=2, max_iters_refine=3)                # NO_CONVERGENCE at the iteration cap
     check(lib, pb, ftol=1e-9, max_iters_robust=30, max_iters_refine=30)
+    # the budgets of Optimizer::looseBA (optimizer.cpp:1298-1299: one 5-iteration solve at 1e-4) and fullBA (:2056: 100 iterations at Ceres'
+    # default 1e-6), which the drop-ins pass to the same solve
+    check(lib, pb, ftol=1e-4, max_iters_robust=5, l2=0)
+    check(lib, pb, ftol=1e-6, max_iters_robust=100, max_iters_refine=100)
 
 
 def test_rejected_steps_follow_real_ceres(lib):
