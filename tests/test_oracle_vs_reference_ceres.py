@@ -201,3 +201,55 @@ def test_c_restatement_used_as_cpu_baseline_equals_real_ceres(lib):
         last = ref["summ"][ref["solves"] - 1]
         assert abs(last[1] - rc["final_cost"]) <= 1e-9 * rc["final_cost"]
         assert np.abs(ref["pose"] - o["pose"]).max() <= 1e-9 and np.abs(ref["invd"] - o["lm_invdepth"]).max() <= 1e-9
+
+
+def test_product_pnp_solver_code_equals_real_ceres(lib, tmp_path):
+    """The PRODUCT's ceresPnP solve (ov2slam_b200/csrc/pnp_math.cuh - the code the CUDA kernel instantiates - compiled for the host with
+    its single-lane context) directly against the real Ceres running the reference's cost function: same verdict, same rejected blocks,
+    pose to 1e-9 (normal equations in the kernel code, DENSE_QR in Ceres)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "p.cpp"
+    src.write_text(r"""
+#include "%s/ov2slam_b200/csrc/pnp_math.cuh"
+#include <vector>
+extern "C" int pnp_host(int n, const double* unpx, const double* wpts, const int* scales, const double* K, double* pose, int nmaxiter, float chi2th,
+                        int use_robust, int apply_l2, unsigned char* flags) {
+    pnp::Problem P; P.n = n; P.unpx = unpx; P.wpts = wpts; P.scales = scales;
+    for (int i = 0; i < 4; ++i) P.K[i] = K[i];
+    std::vector<double> chi2(n); std::vector<unsigned char> dep(n), work(n);
+    pnp::SerialPar par; pnp::Summary S;
+    return pnp::ceres_pnp(par, P, pose, nmaxiter, chi2th, use_robust != 0, apply_l2 != 0, chi2.data(), dep.data(), flags, work.data(), S) ? 1 : 0;
+}""" % root)
+    so = tmp_path / "libp.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(so), str(src)])
+    host = C.CDLL(str(so))
+    lib.ov2ref_ceres_pnp.restype = C.c_int
+    K = np.array([458.654, 457.296, 367.215, 248.375], np.float32).astype(np.float64)
+    rng = np.random.default_rng(8)
+    nbad_total = 0
+    for case in range(10):
+        n = int(rng.integers(40, 500))
+        q = B.quat_normalize(np.array([0.0, 0.0, 0.0, 1.0]) + rng.normal(0, 0.15, 4))
+        Ttrue = np.concatenate([rng.normal(0, 0.5, 3), q])
+        pc = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2, 10, n)], 1)
+        w = np.ascontiguousarray(pc @ B.quat_to_rot(q).T + Ttrue[:3])
+        px = np.stack([K[0] * pc[:, 0] / pc[:, 2] + K[2], K[1] * pc[:, 1] / pc[:, 2] + K[3]], 1) + rng.normal(0, 0.6, (n, 2))
+        nbad = n // 8 if case % 2 else 0
+        px[:nbad] += rng.uniform(15, 60, (nbad, 2))
+        px = np.ascontiguousarray(px)
+        scales = rng.integers(0, 3, n).astype(np.int32)
+        T0 = B.pose_plus(Ttrue, np.concatenate([rng.normal(0, 0.05, 3), rng.normal(0, 0.02, 3)]))
+        for l2 in (1, 0):
+            Tc, Th = T0.copy(), T0.copy()
+            oc, oh, summ = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros((2, 8))
+            rc = lib.ov2ref_ceres_pnp(n, px.ctypes.data_as(D), w.ctypes.data_as(D), scales.ctypes.data_as(I), Tc.ctypes.data_as(D), 5, C.c_double(5.9915),
+                                      1, l2, K.ctypes.data_as(D), oc.ctypes.data_as(U), summ.ctypes.data_as(D))
+            rh = host.pnp_host(n, px.ctypes.data_as(D), w.ctypes.data_as(D), scales.ctypes.data_as(I), K.ctypes.data_as(D), Th.ctypes.data_as(D), 5,
+                               C.c_float(5.9915), 1, l2, oh.ctypes.data_as(U))
+            assert rc in (0, 1) and rc == rh
+            assert np.array_equal(oc, oh)
+            assert np.abs(Tc - Th).max() <= 1e-9
+            nbad_total += int(oc.sum())
+    assert nbad_total > 100
