@@ -21,7 +21,7 @@ numpy float64 restatement of what the reference executes between problem setup a
 
 PINNING STATUS.  Pinned against the reference's own code (tests/test_oracle_vs_reference_source.py, test_oracle_vs_reference_ceres.py):
   * residuals, Jacobians, chi2 / depth flags and the pose update against /root/reference/src/ceres_parametrization.cpp compiled in
-    place (oracle/ref_build/build_ref.py), 1.3e-13 relative;
+    place with the reference tree's own Sophus headers (oracle/ref_build/build_ref.py), 1.3e-13 relative;
   * the WHOLE two-stage solve - every iteration's cost, cost change, step norm, relative decrease, radius, gradient max-norm and
     accept / reject decision, termination, both outlier scans, final state - against the Ceres 2.0 vendored in the reference tree,
     compiled in place and driven with the Ceres calls Optimizer::localBA makes (oracle/ref_build/build_ceres_ref.py, ceres_ba_ref.cpp):

@@ -1,7 +1,8 @@
 """Recipe for oracle/_ref/libov2ref_ceres.so: the Ceres 2.0 sources vendored in the reference tree
 (/root/reference/Thirdparty/ceres-solver/internal/ceres/*.cc, compiled where they lie, nothing copied), the reference's residual
 source (src/ceres_parametrization.cpp) and oracle/ref_build/ceres_ba_ref.cpp (a driver that sets a window up and solves it the way
-Optimizer::localBA does), against the stand-in linear-algebra headers of oracle/ref_build/mini (this container has no Eigen), Ceres'
+Optimizer::localBA does), with the reference tree's own Sophus 1.1 headers, against the stand-in Eigen header of oracle/ref_build/mini
+(this container has no Eigen), Ceres'
 own miniglog, and a hand-written config.h for a dependency-free build (oracle/ref_build/ceres_cfg).
 
 Not compiled: tests / benchmarks, covariance*, and three files off the DENSE_SCHUR + Levenberg-Marquardt path that need
@@ -27,7 +28,7 @@ CERES = REF / "Thirdparty" / "ceres-solver"
 SKIP = ("_test", "test_util", "gmock", "benchmark", "evaluator_test_utils", "generate_", "dogleg_strategy", "polynomial",
         "line_search_direction", "covariance")
 INC = ["-I", str(HERE / "ceres_api"), "-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"), "-I", str(CERES / "internal"),
-       "-I", str(CERES / "internal" / "ceres" / "miniglog"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization")]
+       "-I", str(CERES / "internal" / "ceres" / "miniglog"), "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization")]
 FLAGS = ["-std=c++17", "-O2", "-fPIC", "-w", "-DNDEBUG", "-DMAX_LOG_LEVEL=-1"]     # miniglog: warnings and errors only
 
 

@@ -1,0 +1,3 @@
+// part of Core in this stand-in (oracle test infrastructure)
+#pragma once
+#include "../../Core"
