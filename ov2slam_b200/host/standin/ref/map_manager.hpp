@@ -20,8 +20,8 @@ class FeatureTracker;   // the drop-in class of host/feature_tracker.hpp (the re
 
 struct SlamParams {
     int nmin_covscore_ = 25;
-    int nklt_pyr_lvl_ = 3, nklt_win_size_ = 9;
-    float nklt_err_ = 30.f, fmax_fbklt_dist_ = 0.5f;
+    int nklt_pyr_lvl_ = 3, nklt_win_size_ = 9, nklt_err_ = 30;
+    float fmax_fbklt_dist_ = 0.5f;
     bool bdo_stereo_rect_ = false, debug_ = false, log_timings_ = false;
     bool stereo_ = false, buse_inv_depth_ = true, apply_l2_after_robust_ = true;
     float robust_mono_th_ = 5.9915f;
