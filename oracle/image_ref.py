@@ -19,7 +19,11 @@ cv2.setNumThreads(1), in two layers:
 
 The reference has no tests or golden vectors of its own for this path, so
 "pinned" here means pinned to the third-party library the reference calls, not to a fixture
-of the reference.
+of the reference.  The ORCHESTRATION around those calls (grid walk, masks, sort order, threshold /
+quality adaptation, descriptor re-alignment, the forward-backward tracking flow, the row search) is
+in addition checked against the reference's own src/feature_extractor.cpp and src/feature_tracker.cpp,
+compiled where they lie on stand-in OpenCV containers whose arithmetic calls are answered by cv2
+(oracle/ref_build/mini_cv, cv_callbacks.py; tests/test_oracle_vs_reference_frontend.py).
 """
 from __future__ import annotations
 
