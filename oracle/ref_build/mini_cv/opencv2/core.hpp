@@ -10,10 +10,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <iomanip>
+#include <iostream>
 #include <memory>
 #include <string>
 #include <vector>
 
+#define OV2_STANDIN_OPENCV 1      // the drop-in classes take their stand-in branch on these containers
 #define CV_8U 0
 #define CV_8UC1 0
 #define CV_32F 5
@@ -70,6 +73,7 @@ struct TermCriteria {
     double epsilon;
     TermCriteria(int t = 0, int c = 0, double e = 0) : type(t), maxCount(c), epsilon(e) {}
 };
+class FileStorage;      // named by the reference's SlamParams constructor (YAML loading: not compiled here)
 template <typename T> using Ptr = std::shared_ptr<T>;
 template <typename T, typename... A> Ptr<T> makePtr(A&&... a) { return std::make_shared<T>(std::forward<A>(a)...); }
 
@@ -98,7 +102,20 @@ public:
     int type() const { return flags; }
     size_t elemSize() const { return esz(flags); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    Size size() const { return Size(cols, rows); }
+    // OpenCV's Mat::size is a member OBJECT that is callable and streamable
+    struct MatSize {
+        const Mat* m;
+        Size operator()() const { return Size(m->cols, m->rows); }
+        friend std::ostream& operator<<(std::ostream& os, const MatSize& s) { return os << s.m->cols << " x " << s.m->rows; }
+    };
+    MatSize size{this};
+    Mat(const Mat& o) : rows(o.rows), cols(o.cols), flags(o.flags), step(o.step), data(o.data), parent_data(o.parent_data), parent_rows(o.parent_rows),
+                        parent_cols(o.parent_cols), buf_(o.buf_) {}
+    Mat& operator=(const Mat& o) {
+        rows = o.rows; cols = o.cols; flags = o.flags; step = o.step; data = o.data; parent_data = o.parent_data; parent_rows = o.parent_rows;
+        parent_cols = o.parent_cols; buf_ = o.buf_;
+        return *this;
+    }
     void release() { *this = Mat(); }
     Mat clone() const {
         Mat m;
