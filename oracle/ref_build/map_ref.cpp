@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE (oracle/): the REFERENCE'S OWN Optimizer::localBA (/root/reference/src/optimizer.cpp, compiled where it lies with
+// frame.cpp, map_point.cpp, map_manager.cpp, camera_calibration.cpp, multi_view_geometry.cpp and the Ceres 2.0 of the reference tree)
+// run end to end on a map that this driver builds through the reference's own map API from a flat window: keyframes are created in
+// index order (Frame::addKeypoint, MapManager::addMapPoint for landmarks first seen there, prepareFrame, addKeyframe), landmarks get
+// their 3-D position from the anchor keyframe (MapManager::updateMapPoint), covisibility comes from MapManager::updateFrameCovisibility,
+// then localBA(newest keyframe, robust) selects its window, sets the Ceres problem up, solves, culls and writes back - all reference code.
+// tests/test_oracle_vs_reference_map.py compares the map it leaves behind with the flat solve (oracle/ba_ref.py::local_ba, which
+// equals the GPU solve and what the drop-in Optimizer::localBA feeds it).
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "optimizer.hpp"
+
+extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K, int width, int height, const double* pose /* [ncam][7] Twc */,
+                                   const int32_t* lm_anchor_cam, const double* lm_anchor_px, const double* lm_invdepth, const int32_t* obs_cam,
+                                   const int32_t* obs_lm, const double* obs_px, int nmin_covscore, double* pose_out, double* xyz_out /* [npts][3] world */,
+                                   uint8_t* lm_alive /* [npts] */, int32_t* nobs_left /* [npts] keyframes still observing */) {
+    auto params = std::make_shared<SlamParams>();
+    SlamParams& S = *params;
+    S.debug_ = false; S.log_timings_ = false;
+    S.stereo_ = false; S.mono_ = true; S.bdo_stereo_rect_ = false;
+    S.buse_inv_depth_ = true; S.apply_l2_after_robust_ = true; S.robust_mono_th_ = 5.9915f;
+    S.use_sparse_schur_ = false;                      // DENSE_SCHUR (no sparse library in this build; optimizer.cpp:439-443)
+    S.use_dogleg_ = false; S.use_subspace_dogleg_ = false; S.use_nonmonotic_step_ = false;
+    S.bforce_realtime_ = false;
+    S.nmin_covscore_ = nmin_covscore;
+    S.nbmaxkps_ = 100000;
+    S.blocalba_is_on_ = false;
+    auto calib = std::make_shared<CameraCalibration>("pinhole", K[0], K[1], K[2], K[3], 0., 0., 0., 0., (double)width, (double)height);
+    calib->Dcv_.release();                            // undistorted images: undistortImagePoint returns the pixel itself (camera_calibration.cpp:262)
+    auto cur = std::make_shared<Frame>(calib, 35);
+    auto fe = std::make_shared<FeatureExtractor>(1000, 35, 0.001, 10);
+    auto ft = std::make_shared<FeatureTracker>(30, 0.01f, nullptr);
+    auto map = std::make_shared<MapManager>(params, cur, fe, ft);
+    Optimizer opt(params, map);
+
+    // observations per keyframe, in window order
+    std::vector<std::vector<std::pair<int, const double*>>> per_kf(ncam);
+    for (int l = 0; l < npts; ++l) per_kf[lm_anchor_cam[l]].push_back({l, lm_anchor_px + 2 * l});
+    for (int i = 0; i < nobs; ++i) per_kf[obs_cam[i]].push_back({obs_lm[i], obs_px + 2 * i});
+    std::vector<int> lmid_of(npts, -1);
+    for (int c = 0; c < ncam; ++c) {
+        cur->reset();
+        cur->updateFrame(c, 0.05 * c);
+        const double* p = pose + 7 * c;
+        cur->setTwc(Sophus::SE3d(Eigen::Quaterniond(p[6], p[3], p[4], p[5]), Eigen::Vector3d(p[0], p[1], p[2])));
+        for (const auto& ob : per_kf[c]) {
+            const int l = ob.first;
+            const cv::Point2f px((float)ob.second[0], (float)ob.second[1]);
+            if (lmid_of[l] < 0) {
+                if (lm_anchor_cam[l] != c) return -2;            // the anchor must be the first keyframe that sees a landmark
+                lmid_of[l] = map->nlmid_;
+                cur->addKeypoint(px, map->nlmid_);
+                map->addMapPoint();
+            } else {
+                cur->addKeypoint(px, lmid_of[l]);
+            }
+        }
+        map->prepareFrame();
+        map->addKeyframe();
+    }
+    for (int l = 0; l < npts; ++l) {
+        auto kf = map->getKeyframe(lm_anchor_cam[l]);
+        const Keypoint kp = kf->getKeypointById(lmid_of[l]);
+        const double z = 1. / lm_invdepth[l];
+        const Eigen::Vector3d campt = z * (kp.bv_ / kp.bv_.z());
+        map->updateMapPoint(lmid_of[l], kf->projCamToWorld(campt), lm_invdepth[l]);
+    }
+    for (int c = 0; c < ncam; ++c) map->updateFrameCovisibility(*map->getKeyframe(c));
+
+    opt.localBA(*map->getKeyframe(ncam - 1), true);
+
+    for (int c = 0; c < ncam; ++c) {
+        const Sophus::SE3d T = map->getKeyframe(c)->getTwc();
+        const Eigen::Vector3d t = T.translation();
+        const Eigen::Quaterniond q = T.unit_quaternion();
+        double* o = pose_out + 7 * c;
+        o[0] = t.x(); o[1] = t.y(); o[2] = t.z(); o[3] = q.x(); o[4] = q.y(); o[5] = q.z(); o[6] = q.w();
+    }
+    for (int l = 0; l < npts; ++l) {
+        auto plm = map->getMapPoint(lmid_of[l]);
+        lm_alive[l] = plm != nullptr;
+        nobs_left[l] = plm ? (int)plm->getKfObsSet().size() : 0;
+        const Eigen::Vector3d w = plm ? plm->getPoint() : Eigen::Vector3d(0, 0, 0);
+        xyz_out[3 * l] = w.x(); xyz_out[3 * l + 1] = w.y(); xyz_out[3 * l + 2] = w.z();
+    }
+    return 0;
+}

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
 #include <iomanip>
 #include <iostream>
@@ -62,11 +63,23 @@ template <typename T> struct Rect_ {
     T x, y, width, height;
     Rect_() : x(0), y(0), width(0), height(0) {}
     Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
+    Rect_(const Point_<T>& a, const Point_<T>& b) : x(std::min(a.x, b.x)), y(std::min(a.y, b.y)), width(std::max(a.x, b.x) - std::min(a.x, b.x)), height(std::max(a.y, b.y) - std::min(a.y, b.y)) {}
+    friend std::ostream& operator<<(std::ostream& os, const Rect_& r) { return os << "[" << r.width << " x " << r.height << " from (" << r.x << ", " << r.y << ")]"; }
     bool empty() const { return width <= 0 || height <= 0; }
 };
 typedef Rect_<int> Rect;
-struct Scalar { double val[4]; Scalar(double v0 = 0, double v1 = 0, double v2 = 0, double v3 = 0) : val{v0, v1, v2, v3} {} };
-struct Range { int start, end; Range() : start(0), end(0) {} Range(int s, int e) : start(s), end(e) {} };
+struct Scalar {
+    double val[4];
+    Scalar(double v0 = 0, double v1 = 0, double v2 = 0, double v3 = 0) : val{v0, v1, v2, v3} {}
+    double operator[](int i) const { return val[i]; }
+    double& operator[](int i) { return val[i]; }
+};
+struct Range {
+    int start, end;
+    Range() : start(0), end(0) {}
+    Range(int s, int e) : start(s), end(e) {}
+    static Range all() { return Range(-2147483647 - 1, 2147483647); }
+};
 struct TermCriteria {
     enum { COUNT = 1, MAX_ITER = 1, EPS = 2 };
     int type, maxCount;
@@ -127,6 +140,14 @@ public:
     void copyTo(Mat& o) const { o = clone(); }
     unsigned char* ptr(int r = 0) { return data + (size_t)r * step; }
     const unsigned char* ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <class T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (size_t)i * step); }
+    template <class T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (size_t)i * step); }
+    Mat col(int c) const { return (*this)(Rect(c, 0, 1, rows)); }
+    Mat& operator/=(double d) {
+        for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) { if (flags == CV_32F) at<float>(i, j) = (float)(at<float>(i, j) / d); else if (flags == CV_64F) at<double>(i, j) /= d; }
+        return *this;
+    }
+    static Mat eye(int r, int c, int type) { Mat m(r, c, type); for (int i = 0; i < r && i < c; ++i) { if (type == CV_32F) m.at<float>(i, i) = 1.f; else if (type == CV_64F) m.at<double>(i, i) = 1.0; else m.at<unsigned char>(i, i) = 1; } return m; }
     template <class T> T& at(int y, int x) { return ((T*)(data + (size_t)y * step))[x]; }
     template <class T> const T& at(int y, int x) const { return ((const T*)(data + (size_t)y * step))[x]; }
     Mat operator()(const Rect& r) const {
@@ -139,7 +160,18 @@ public:
         m.parent_cols = parent_data ? parent_cols : cols;
         return m;
     }
+    Mat operator()(const Range& rr, const Range& cr) const {
+        const int r0 = rr.start < 0 ? 0 : rr.start, r1 = rr.end > rows ? rows : rr.end, c0 = cr.start < 0 ? 0 : cr.start, c1 = cr.end > cols ? cols : cr.end;
+        return (*this)(Rect(c0, r0, c1 - c0, r1 - r0));
+    }
     Mat row(int r) const { return (*this)(Rect(0, r, cols, 1)); }
+    Mat& operator=(const Scalar& s) { return setTo(s); }            // fills (a ROI of) the matrix
+    friend std::ostream& operator<<(std::ostream& os, const Mat& m) {
+        for (int r = 0; r < m.rows; ++r) {
+            for (int c = 0; c < m.cols; ++c) os << (c ? ", " : (r ? "\n " : "[")) << (m.flags == CV_8U ? (double)m.at<unsigned char>(r, c) : (m.flags == CV_32F ? (double)m.at<float>(r, c) : m.at<double>(r, c)));
+        }
+        return os << "]";
+    }
     Mat& setTo(const Scalar& s) {
         for (int r = 0; r < rows; ++r)
             for (int c = 0; c < cols; ++c) {
@@ -164,7 +196,22 @@ public:
 private:
     std::shared_ptr<unsigned char> buf_;
 };
-enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4, NORM_HAMMING = 6 };
+inline Mat operator*(double s, const Mat& m) {
+    Mat r = m.clone();
+    for (int i = 0; i < r.rows; ++i)
+        for (int j = 0; j < r.cols; ++j) {
+            if (r.type() == CV_64F) r.at<double>(i, j) *= s;
+            else if (r.type() == CV_32F) r.at<float>(i, j) = (float)(r.at<float>(i, j) * s);
+            else r.at<unsigned char>(i, j) = (unsigned char)(r.at<unsigned char>(i, j) * s);
+        }
+    return r;
+}
+struct Matx34f {
+    float val[12];
+    Matx34f() : val{} {}
+    Matx34f(float a, float b, float c, float d, float e, float f, float g, float h, float i, float j, float k, float l) : val{a, b, c, d, e, f, g, h, i, j, k, l} {}
+};
 typedef const Mat& InputArray;
 typedef Mat& OutputArray;
 
@@ -205,8 +252,12 @@ struct MiniCvCallbacks {
 };
 MiniCvCallbacks& mini_cv_callbacks();
 inline double norm(const Mat& a, const Mat& b, int type) {                    // 8-bit matrices, L1: an exact integer sum
-    if (type != NORM_L1 || a.type() != CV_8U) { fprintf(stderr, "oracle mini OpenCV: only the 8-bit L1 norm is provided\n"); abort(); }
+    if ((type != NORM_L1 && type != NORM_HAMMING) || a.type() != CV_8U) { fprintf(stderr, "oracle mini OpenCV: only the 8-bit L1 / Hamming norms are provided\n"); abort(); }
     long s = 0;
+    if (type == NORM_HAMMING) {
+        for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) s += __builtin_popcount((unsigned)(a.at<unsigned char>(r, c) ^ b.at<unsigned char>(r, c)));
+        return (double)s;
+    }
     for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) s += std::abs((int)a.at<unsigned char>(r, c) - (int)b.at<unsigned char>(r, c));
     return (double)s;
 }

@@ -6,7 +6,12 @@
 
 namespace pcl {
 struct PointXYZ { float x = 0, y = 0, z = 0; };
-struct PointXYZRGB { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; };
+struct PointXYZRGB {
+    float x = 0, y = 0, z = 0;
+    unsigned char r = 0, g = 0, b = 0;
+    PointXYZRGB() {}
+    PointXYZRGB(unsigned char r_, unsigned char g_, unsigned char b_) : r(r_), g(g_), b(b_) {}
+};
 template <class P> struct PointCloud {
     typedef std::shared_ptr<PointCloud> Ptr;
     std::vector<P> points;

@@ -28,6 +28,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <unordered_set>
+
 #include "optimizer.hpp"          // the reference's, unchanged
 #include "../../include/ov2b200.h"
 
@@ -110,16 +112,26 @@ void flatten_landmarks(MapManager& map, Window& win, const std::vector<int>& lm_
     }
 }
 
-// Gauge (at least two constant keyframes in mono, one in stereo: optimizer.cpp:65-69, 396-407 / :1228-1239 / :1992-2003; the
-// reference walks an unordered_map there, ascending keyframe id is used here) and the solver's capacity (64 optimised
-// keyframes: beyond that the OLDEST optimised keyframes are held constant, said once on stderr).
-void fix_gauge_and_capacity(Window& win, const bool stereo, const char* who) {
+// Gauge (at least two constant keyframes in mono, one in stereo: optimizer.cpp:65-69, 396-407 / :1228-1239 / :1992-2003) and the solver's
+// capacity (64 optimised keyframes: beyond that the OLDEST optimised keyframes are held constant, said once on stderr).
+// `reference_walk` (localBA): the reference walks its keyframe hash map from begin() and counts every keyframe it visits, constant
+// already or not (`nbcstkfs++`, :400-406) - with libstdc++ the walk starts at the LAST keyframe inserted, which is keyframe 0 of a
+// fully covisible window: it is "fixed" a second time, the count reaches two and only ONE keyframe is constant.  The drop-in does the
+// same walk over a hash map filled in the same order (Window::cam_of_kf), so that it fixes what the reference fixes
+// (tests/test_oracle_vs_reference_map.py runs the reference's own localBA next to it).  looseBA / fullBA keep ascending keyframe ids.
+void fix_gauge_and_capacity(Window& win, const bool stereo, const char* who, const bool reference_walk = false) {
     size_t nconst = 0;
     for (uint8_t c : win.pose_const) nconst += c;
     const size_t nmincst = stereo ? 1 : 2;
     std::map<int, int> by_id(win.cam_of_kf.begin(), win.cam_of_kf.end());
-    for (auto it = by_id.begin(); nconst < nmincst && it != by_id.end(); ++it)
-        if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
+    if (reference_walk) {
+        for (auto it = win.cam_of_kf.begin(); nconst < nmincst && it != win.cam_of_kf.end(); ++it) { win.pose_const[it->second] = 1; nconst++; }
+        nconst = 0;
+        for (uint8_t c : win.pose_const) nconst += c;
+    } else {
+        for (auto it = by_id.begin(); nconst < nmincst && it != by_id.end(); ++it)
+            if (!win.pose_const[it->second]) { win.pose_const[it->second] = 1; nconst++; }
+    }
     size_t nvar = win.pose_const.size() - nconst;
     if (nvar > 64) {
         static bool told = false;
@@ -171,9 +183,8 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
     Window win;
     std::map<int, int> cov = newframe.getCovisibleKfMap();
     cov.emplace(newframe.kfid_, newframe.nb3dkps_);
-    std::vector<int> lm_order;            // landmark ids seen from optimised keyframes, de-duplicated
-    std::unordered_map<int, int> lm_seen;
-    bool freeze = false;
+    std::unordered_set<int> set_lmids2opt;   // landmark ids seen from optimised keyframes; walked in the hash set's order, as the reference
+    bool freeze = false;                     // does (:135, :191): it decides in which order keyframes outside the window join it
     const int newest = cov.rbegin()->first;
     for (auto it = cov.rbegin(); it != cov.rend(); ++it) {
         const int kfid = it->first;
@@ -184,14 +195,14 @@ void Optimizer::localBA(Frame &newframe, const bool buse_robust_cost)
         if (!optimise) freeze = true;
         win.add_camera(kfid, kf, !optimise);
         if (optimise)
-            for (const auto& kp : kf->getKeypoints3d())
-                if (lm_seen.emplace(kp.lmid_, 1).second) lm_order.push_back(kp.lmid_);
+            for (const auto& kp : kf->getKeypoints3d()) set_lmids2opt.insert(kp.lmid_);
     }
 
     // ---- 2. landmarks (optimizer.cpp:191-392)
+    const std::vector<int> lm_order(set_lmids2opt.begin(), set_lmids2opt.end());
     flatten_landmarks(*pmap_, win, lm_order, newest, stereo);
     // ---- 3. gauge + solver capacity
-    fix_gauge_and_capacity(win, stereo, "localBA");
+    fix_gauge_and_capacity(win, stereo, "localBA", /*reference_walk=*/true);
     if (win.obs_cam.empty()) return;
 
     // ---- 4. solve on the GPU (replaces ceres::Solve x2 + the two outlier scans)

@@ -85,7 +85,9 @@ int main(int argc, char** argv) {
     std::vector<Sophus::SE3d> anchors_before;
     for (int c = 0; c < ncam; ++c) anchors_before.push_back(map->map_pkfs_[c]->getTwc());
     auto newkf = map->map_pkfs_[ncam - 1];
-    for (int c = 0; c < ncam - 1; ++c) newkf->covkfs_[c] = pc[c] ? 0 : 1000;
+    const std::string mode0 = argc > 3 ? argv[3] : "";
+    // "gauge": every keyframe strongly covisible, none pre-marked constant - the gauge rule alone decides what is fixed
+    for (int c = 0; c < ncam - 1; ++c) newkf->covkfs_[c] = (pc[c] && mode0 != "gauge") ? 0 : 1000;
     map->pcurframe_ = newkf;
     map->nkfid_ = ncam - 1;
     Optimizer opt(params, map);

@@ -1,0 +1,110 @@
+"""The REFERENCE'S OWN Optimizer::localBA run end to end (oracle/_ref/libov2ref_map.so: src/optimizer.cpp, frame.cpp, map_point.cpp,
+map_manager.cpp, camera_calibration.cpp, multi_view_geometry.cpp compiled where they lie, with the Ceres 2.0 and Sophus of the reference
+tree; stand-ins only for Eigen, the OpenCV containers and PCL) on maps built through the reference's own map API:
+  * what it leaves in the map equals the flat solve (oracle/ba_ref.py::local_ba, == the GPU solve) of the same window, with the
+    keyframes the reference itself chose to hold constant;
+  * the drop-in Optimizer::localBA (ov2slam_b200/host/optimizer_localba_gpu.cpp), with its device call recorded instead of executed,
+    hands the GPU the same window: the same constant keyframes (the reference's gauge walk over its keyframe hash map fixes ONE
+    keyframe where the comment promises two), the same landmarks and observations."""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ba_ref as B
+from ov2slam_b200 import build, synth
+
+pytest.importorskip("cv2")
+ROOT = Path(__file__).resolve().parents[1]
+D, I, U = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from oracle.ref_build import build_map_ref, cv_callbacks as CB
+    so = build_map_ref.build()
+    if so is None:
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref is present")
+    lib = C.CDLL(str(so))
+    cb = CB._Callbacks(*[C.cast(f, C.c_void_p) for f in CB._KEEP])
+    lib.ov2ref_cv_set_callbacks(C.byref(cb))
+    lib.ov2ref_run_local_ba.restype = C.c_int
+    return lib
+
+
+def reference_local_ba(lib, pb, nmin_covscore=25):
+    ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
+    a = {k: np.ascontiguousarray(pb[k], t) for k, t in (("K", np.float64), ("pose", np.float64), ("lm_anchor_cam", np.int32), ("lm_anchor_px", np.float64),
+                                                        ("lm_invdepth", np.float64), ("obs_cam", np.int32), ("obs_lm", np.int32), ("obs_px", np.float64))}
+    pose, xyz, alive, left = np.zeros((ncam, 7)), np.zeros((npts, 3)), np.zeros(npts, np.uint8), np.zeros(npts, np.int32)
+    rc = lib.ov2ref_run_local_ba(ncam, npts, nobs, a["K"].ctypes.data_as(D), 752, 480, a["pose"].ctypes.data_as(D), a["lm_anchor_cam"].ctypes.data_as(I),
+                                 a["lm_anchor_px"].ctypes.data_as(D), a["lm_invdepth"].ctypes.data_as(D), a["obs_cam"].ctypes.data_as(I),
+                                 a["obs_lm"].ctypes.data_as(I), a["obs_px"].ctypes.data_as(D), nmin_covscore, pose.ctypes.data_as(D), xyz.ctypes.data_as(D),
+                                 alive.ctypes.data_as(U), left.ctypes.data_as(I))
+    assert rc == 0
+    return pose, xyz, alive.astype(bool), left
+
+
+def world_points(pb, pose, invd):
+    fx, fy, cx, cy = pb["K"]
+    ua, ca = pb["lm_anchor_px"], pb["lm_anchor_cam"]
+    bear = np.stack([(ua[:, 0] - cx) / fx, (ua[:, 1] - cy) / fy, np.ones(len(ua))], 1) / invd[:, None]
+    R = B.quat_to_rot(B.quat_normalize(pose[ca, 3:]))
+    return (R @ bear[..., None])[..., 0] + pose[ca, :3]
+
+
+@pytest.mark.parametrize("seed,ncam,npts,nobs", [(3, 6, 200, 800), (12, 8, 300, 1300), (17, 5, 150, 520)])
+def test_reference_local_ba_leaves_the_map_of_the_flat_solve(lib, seed, ncam, npts, nobs, capfd):
+    pb = synth.make_ba_problem(seed, ncam, npts, nobs)
+    pose, xyz, alive, left = reference_local_ba(lib, pb)
+    const = np.abs(pose - pb["pose"]).max(1) <= 1e-14          # (a constant keyframe comes back re-normalised: equal to rounding)
+    assert const[0] and const.sum() == 1                       # every keyframe covisible: only keyframe 0 ends up constant (see the module docstring)
+    o = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    o["pose_const"] = const.astype(np.uint8)
+    res = B.local_ba(o)
+    assert res["n_outliers_first"] > 0 and res["iters_refine"] > 0
+    assert np.abs(pose - o["pose"]).max() <= 1e-9
+    w = world_points(pb, o["pose"], o["lm_invdepth"])
+    assert alive.mean() > 0.95 and np.abs(w[alive] - xyz[alive]).max() <= 1e-8
+    # observations the two scans flagged are removed from the map (optimizer.cpp:741-897): per landmark, observers left = observers - flagged
+    nobs_of = 1 + np.bincount(pb["obs_lm"], minlength=npts)
+    bad_of = np.bincount(pb["obs_lm"], weights=(res["flags"] != 0).astype(float), minlength=npts).astype(int)
+    assert np.array_equal(left[alive], (nobs_of - bad_of)[alive])
+
+
+def _write_window(path, pb):
+    ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
+    with open(path, "wb") as f:
+        f.write(np.array([ncam, npts, nobs, 0], np.int32).tobytes())
+        f.write(np.asarray(pb["K"], np.float64).tobytes() + np.zeros(4).tobytes() + np.array([0, 0, 0, 0, 0, 0, 1.0]).tobytes())
+        for k, t in (("pose", np.float64), ("pose_const", np.uint8), ("lm_anchor_cam", np.int32), ("lm_anchor_px", np.float64), ("lm_invdepth", np.float64),
+                     ("obs_cam", np.int32), ("obs_lm", np.int32), ("obs_px", np.float64)):
+            f.write(np.ascontiguousarray(pb[k], t).tobytes())
+        f.write(np.zeros(nobs, np.uint8).tobytes())
+
+
+@pytest.mark.parametrize("seed,ncam,npts,nobs", [(3, 6, 200, 800), (12, 8, 300, 1300)])
+def test_drop_in_local_ba_hands_over_the_window_the_reference_solves(lib, tmp_path, seed, ncam, npts, nobs):
+    pb = synth.make_ba_problem(seed, ncam, npts, nobs)
+    pose, _, _, _ = reference_local_ba(lib, pb)
+    ref_const = np.abs(pose - pb["pose"]).max(1) <= 1e-14
+    exe = build.build_optimizer_shim()
+    rec = tmp_path / "librec.so"
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-o", str(rec), str(ROOT / "tests" / "helpers" / "ba_dump.c")])
+    _write_window(tmp_path / "w.bin", pb)
+    env = dict(os.environ, LD_PRELOAD=str(rec), OV2_BA_DUMP=str(tmp_path / "d.bin"))
+    out = subprocess.run([str(exe), str(tmp_path / "w.bin"), str(tmp_path / "r.bin"), "gauge"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = np.fromfile(tmp_path / "d.bin", np.uint8)
+    n = raw[:12].view(np.int32)
+    dcam, dpts, dobs = int(n[0]), int(n[1]), int(n[2])
+    dpose = raw[12:12 + 56 * dcam].view(np.float64).reshape(dcam, 7)
+    dconst = raw[12 + 56 * dcam:12 + 57 * dcam].astype(bool)
+    assert (dcam, dpts, dobs) == (ncam, npts, nobs)
+    # keyframes by identity (their pose): the drop-in's constant set is the reference's
+    for c in range(dcam):
+        k = int(np.argmin(np.abs(pb["pose"] - dpose[c]).sum(1)))
+        assert np.abs(pb["pose"][k] - dpose[c]).max() <= 1e-12 and dconst[c] == ref_const[k]
