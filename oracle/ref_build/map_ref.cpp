@@ -15,7 +15,7 @@
 
 extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K, int width, int height, const double* pose /* [ncam][7] Twc */,
                                    const int32_t* lm_anchor_cam, const double* lm_anchor_px, const double* lm_invdepth, const int32_t* obs_cam,
-                                   const int32_t* obs_lm, const double* obs_px, int nmin_covscore, double* pose_out, double* xyz_out /* [npts][3] world */,
+                                   const int32_t* obs_lm, const double* obs_px, int nmin_covscore, int mode /* 0 localBA, 1 looseBA, 2 fullBA */, double* pose_out, double* xyz_out /* [npts][3] world */,
                                    uint8_t* lm_alive /* [npts] */, int32_t* nobs_left /* [npts] keyframes still observing */) {
     auto params = std::make_shared<SlamParams>();
     SlamParams& S = *params;
@@ -70,7 +70,9 @@ extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K
     }
     for (int c = 0; c < ncam; ++c) map->updateFrameCovisibility(*map->getKeyframe(c));
 
-    opt.localBA(*map->getKeyframe(ncam - 1), true);
+    if (mode == 1) opt.looseBA(0, ncam - 1, true);              // optimizer.cpp:900-1671
+    else if (mode == 2) opt.fullBA(true);                        // :1674-2331
+    else opt.localBA(*map->getKeyframe(ncam - 1), true);
 
     for (int c = 0; c < ncam; ++c) {
         const Sophus::SE3d T = map->getKeyframe(c)->getTwc();

@@ -35,17 +35,36 @@ def lib():
     return lib
 
 
-def reference_local_ba(lib, pb, nmin_covscore=25):
+def reference_local_ba(lib, pb, nmin_covscore=25, mode=0):
     ncam, npts, nobs = len(pb["pose"]), len(pb["lm_invdepth"]), len(pb["obs_cam"])
     a = {k: np.ascontiguousarray(pb[k], t) for k, t in (("K", np.float64), ("pose", np.float64), ("lm_anchor_cam", np.int32), ("lm_anchor_px", np.float64),
                                                         ("lm_invdepth", np.float64), ("obs_cam", np.int32), ("obs_lm", np.int32), ("obs_px", np.float64))}
     pose, xyz, alive, left = np.zeros((ncam, 7)), np.zeros((npts, 3)), np.zeros(npts, np.uint8), np.zeros(npts, np.int32)
     rc = lib.ov2ref_run_local_ba(ncam, npts, nobs, a["K"].ctypes.data_as(D), 752, 480, a["pose"].ctypes.data_as(D), a["lm_anchor_cam"].ctypes.data_as(I),
                                  a["lm_anchor_px"].ctypes.data_as(D), a["lm_invdepth"].ctypes.data_as(D), a["obs_cam"].ctypes.data_as(I),
-                                 a["obs_lm"].ctypes.data_as(I), a["obs_px"].ctypes.data_as(D), nmin_covscore, pose.ctypes.data_as(D), xyz.ctypes.data_as(D),
+                                 a["obs_lm"].ctypes.data_as(I), a["obs_px"].ctypes.data_as(D), nmin_covscore, mode, pose.ctypes.data_as(D), xyz.ctypes.data_as(D),
                                  alive.ctypes.data_as(U), left.ctypes.data_as(I))
     assert rc == 0
     return pose, xyz, alive.astype(bool), left
+
+
+def inside_image(pb, w=752, h=480, margin=2.0):
+    """The window without the observations (and landmarks) whose pixels fall outside the image: the reference's Frame keeps its keypoints
+    in a grid over the image and indexes it unchecked."""
+    ok_l = (pb["lm_anchor_px"][:, 0] >= margin) & (pb["lm_anchor_px"][:, 0] < w - margin) & (pb["lm_anchor_px"][:, 1] >= margin) & (pb["lm_anchor_px"][:, 1] < h - margin)
+    ok_o = (pb["obs_px"][:, 0] >= margin) & (pb["obs_px"][:, 0] < w - margin) & (pb["obs_px"][:, 1] >= margin) & (pb["obs_px"][:, 1] < h - margin)
+    ok_o &= ok_l[pb["obs_lm"]]
+    ok_l &= np.bincount(pb["obs_lm"][ok_o], minlength=len(ok_l)) > 0
+    ok_o &= ok_l[pb["obs_lm"]]
+    new_id = np.cumsum(ok_l) - 1
+    out = dict(pb)
+    for k in ("lm_anchor_cam", "lm_anchor_px", "lm_invdepth"):
+        out[k] = pb[k][ok_l].copy()
+    for k in ("obs_cam", "obs_px"):
+        out[k] = pb[k][ok_o].copy()
+    out["obs_lm"] = new_id[pb["obs_lm"][ok_o]].astype(np.int32)
+    out["pose"] = pb["pose"].copy()
+    return out
 
 
 def world_points(pb, pose, invd):
@@ -108,3 +127,24 @@ def test_drop_in_local_ba_hands_over_the_window_the_reference_solves(lib, tmp_pa
     for c in range(dcam):
         k = int(np.argmin(np.abs(pb["pose"] - dpose[c]).sum(1)))
         assert np.abs(pb["pose"][k] - dpose[c]).max() <= 1e-12 and dconst[c] == ref_const[k]
+
+
+@pytest.mark.parametrize("mode,seed", [(1, 4), (2, 4), (1, 9), (2, 9)])
+def test_reference_loose_and_full_ba_leave_the_map_of_the_flat_solve(lib, mode, seed):
+    """Optimizer::looseBA (keyframe range, one 5-iteration solve at 1e-4, optimizer.cpp:900-1671) and fullBA (all keyframes, 100 + 100
+    iterations at Ceres' default tolerance, :1674-2331), the reference's own code end to end: the first two keyframes of the range are held
+    constant (mono) and the map they leave equals the flat solve with those budgets - what the drop-ins pass to the GPU solve
+    (tests/test_host_shim.py::test_optimizer_loose_and_full_ba_shims)."""
+    pb = inside_image(synth.make_ba_problem(seed, 6, 200, 800))
+    pose, xyz, alive, _ = reference_local_ba(lib, pb, mode=mode)
+    const = np.abs(pose - pb["pose"]).max(1) <= 1e-14
+    assert list(np.nonzero(const)[0]) == [0, 1]
+    o = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    o["pose_const"] = const.astype(np.uint8)
+    if mode == 1:
+        B.local_ba(o, max_iters_robust=5, max_iters_refine=0, function_tolerance=1e-4, apply_l2_after_robust=False)
+    else:
+        B.local_ba(o, max_iters_robust=100, max_iters_refine=100, function_tolerance=1e-6)
+    assert np.abs(pose - o["pose"]).max() <= 1e-8
+    w = world_points(pb, o["pose"], o["lm_invdepth"])
+    assert alive.mean() > 0.9 and np.abs(w[alive] - xyz[alive]).max() <= 1e-7
