@@ -21,8 +21,10 @@ The reference iterates an unordered_set of map-point ids; the order of `cand_mp`
 Rotations are applied as 3 x 3 matrices (the reference goes through Sophus' quaternion product: last-bit differences in
 the camera-frame point).
 
-PINNING STATUS: the distortion model is pinned against cv2; the flow itself is a restatement checked by hand-built cases
-(tests/test_oracle_match.py) - there is no way to run the reference's Mapper here.
+PINNING STATUS: the distortion model is pinned against cv2; the flow against the reference's own Mapper::matchToMap (src/mapper.cpp
+compiled in place with the reference's Frame / MapManager / MapPoint, oracle/ref_build/build_map_ref.py) on maps built from flattened
+scenes with an undistorted calibration: the same pairs for the same candidate order (tests/test_oracle_vs_reference_map.py); hand-built
+cases in tests/test_oracle_match.py.
 """
 from __future__ import annotations
 

@@ -1,5 +1,5 @@
 """Recipe for oracle/_ref/libov2ref_map.so: the reference's OWN map and optimizer code - src/optimizer.cpp, frame.cpp, map_point.cpp,
-map_manager.cpp, camera_calibration.cpp, multi_view_geometry.cpp, feature_extractor.cpp, feature_tracker.cpp (compiled where they lie,
+map_manager.cpp, camera_calibration.cpp, multi_view_geometry.cpp, feature_extractor.cpp, feature_tracker.cpp, mapper.cpp, estimator.cpp (compiled where they lie,
 nothing copied) - with the Ceres 2.0 objects of build_ceres_ref.py, the reference tree's Sophus, and this directory's stand-ins for what
 the container lacks (Eigen: mini/, OpenCV containers: mini_cv/ with arithmetic through cv2 callbacks, PCL: mini_pcl/), plus the drivers
 map_ref.cpp / fe_ref.cpp.  TEST INFRASTRUCTURE: only tests/ use what this builds."""
@@ -18,7 +18,8 @@ OUTDIR = HERE.parent / "_ref"
 OUT = OUTDIR / "libov2ref_map.so"
 REF = Path("/root/reference")
 CERES = REF / "Thirdparty" / "ceres-solver"
-REF_SOURCES = ["optimizer", "frame", "map_point", "map_manager", "camera_calibration", "multi_view_geometry", "feature_extractor", "feature_tracker"]
+REF_SOURCES = ["optimizer", "frame", "map_point", "map_manager", "camera_calibration", "multi_view_geometry", "feature_extractor", "feature_tracker", "mapper",
+               "estimator"]
 INC = ["-I", str(HERE / "mini_pcl"), "-I", str(HERE / "ceres_api"), "-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"),
        "-I", str(CERES / "internal" / "ceres" / "miniglog"), "-I", str(HERE / "mini_cv"), "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"),
        "-I", str(REF / "include"), "-I", str(REF / "include" / "ceres_parametrization")]

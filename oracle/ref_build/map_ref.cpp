@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "optimizer.hpp"
+#include "mapper.hpp"
+#include "loop_closer.hpp"
 
 extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K, int width, int height, const double* pose /* [ncam][7] Twc */,
                                    const int32_t* lm_anchor_cam, const double* lm_anchor_px, const double* lm_invdepth, const int32_t* obs_cam,
@@ -89,4 +91,75 @@ extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K
         xyz_out[3 * l] = w.x(); xyz_out[3 * l + 1] = w.y(); xyz_out[3 * l + 2] = w.z();
     }
     return 0;
+}
+
+
+// ---- loop closing is outside the scope: mapper.cpp refers to three LoopCloser entry points (src/loop_closer.cpp needs cv::BFMatcher & co)
+LoopCloser::LoopCloser(std::shared_ptr<SlamParams>, std::shared_ptr<MapManager>) { fprintf(stderr, "oracle/_ref: LoopCloser is not part of this build\n"); abort(); }
+void LoopCloser::run() { abort(); }
+void LoopCloser::addNewKf(const std::shared_ptr<Frame>&, const cv::Mat&) { abort(); }
+
+// The REFERENCE'S OWN Mapper::matchToMap (/root/reference/src/mapper.cpp:576-774) on a map built from a flattened matching scene
+// (ov2slam_b200.synth.make_match_scene, undistorted): keyframes with their poses and the keypoints that observe the map points, map
+// points with position / descriptors / keyframe sets, the frame with its keypoints added in index order (so its grid cells list them
+// in that order).  A default-constructed Mapper is used (its other constructor starts the mapper, estimator and loop-closer threads).
+// ids: map point m <-> lmid m; a keypoint without map point gets lmid 1000000 + its index; keyframe k <-> kfid 10 + k; the frame is 5000.
+// Returns the number of pairs; order_out = the order in which the candidate id set was walked.
+extern "C" int ov2ref_match_to_map(int nkps, int nmps, int nkfs, int ncand, const double* K, int width, int height, int ncellsize, const double* Tcw,
+                                   const double* kf_Tcw, const double* mp_xyz, const float* kp_px, const int32_t* kp_lm, const int32_t* desc_ptr,
+                                   const uint8_t* desc, const int32_t* obs_ptr, const int32_t* obs_kf, const float* obs_px, const int32_t* cand_mp,
+                                   float fmaxprojerr, float fdistratio, int32_t* order_out, int32_t* pairs_out) {
+    auto params = std::make_shared<SlamParams>();
+    params->debug_ = false; params->log_timings_ = false;
+    auto calib = std::make_shared<CameraCalibration>("pinhole", K[0], K[1], K[2], K[3], 0., 0., 0., 0., (double)width, (double)height);
+    calib->Dcv_.release();
+    auto cur = std::make_shared<Frame>(calib, (size_t)ncellsize);
+    auto map = std::make_shared<MapManager>(params, cur, nullptr, nullptr);
+    auto pose_of = [](const double* T) {               // camera <- world (row-major R, t)  ->  Twc
+        Eigen::Matrix3d R;
+        R << T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8];
+        return Sophus::SE3d(Eigen::Quaterniond(R), Eigen::Vector3d(T[9], T[10], T[11])).inverse();
+    };
+    std::vector<std::shared_ptr<Frame>> kfs(nkfs);
+    for (int k = 0; k < nkfs; ++k) {
+        kfs[k] = std::make_shared<Frame>(calib, (size_t)ncellsize);
+        kfs[k]->id_ = kfs[k]->kfid_ = 10 + k;
+        kfs[k]->setTwc(pose_of(kf_Tcw + 12 * k));
+        map->map_pkfs_.emplace(10 + k, kfs[k]);
+    }
+    for (int m = 0; m < nmps; ++m) {
+        auto lm = std::make_shared<MapPoint>(m, 0, true);
+        lm->set_kfids_.clear();
+        lm->setPoint(Eigen::Vector3d(mp_xyz[3 * m], mp_xyz[3 * m + 1], mp_xyz[3 * m + 2]));
+        lm->is3d_ = true;
+        for (int d = desc_ptr[m]; d < desc_ptr[m + 1]; ++d) {
+            cv::Mat row(1, 32, CV_8U);
+            memcpy(row.data, desc + 32 * (size_t)d, 32);
+            if (d == desc_ptr[m]) lm->desc_ = row;
+            lm->map_kf_desc_.emplace(1000 + d - desc_ptr[m], row);
+        }
+        for (int o = obs_ptr[m]; o < obs_ptr[m + 1]; ++o) {
+            lm->addKfObs(10 + obs_kf[o]);
+            Keypoint kp;                                      // straight into the hash map: an observation may lie outside the image, the grid is not read
+            kp.lmid_ = m;
+            kp.px_ = cv::Point2f(obs_px[2 * o], obs_px[2 * o + 1]);
+            kp.unpx_ = kp.px_;
+            kfs[obs_kf[o]]->mapkps_[m] = kp;
+        }
+        map->map_plms_.emplace(m, lm);
+    }
+    Frame frame(calib, (size_t)ncellsize);
+    frame.id_ = frame.kfid_ = 5000;
+    frame.setTwc(pose_of(Tcw));
+    for (int j = 0; j < nkps; ++j) frame.addKeypoint(cv::Point2f(kp_px[2 * j], kp_px[2 * j + 1]), kp_lm[j] >= 0 ? kp_lm[j] : 1000000 + j);
+    std::unordered_set<int> local(cand_mp, cand_mp + ncand);
+    int n = 0;
+    for (const int id : local) order_out[n++] = id;
+    Mapper mapper;
+    mapper.pslamstate_ = params;
+    mapper.pmap_ = map;
+    const std::map<int, int> res = mapper.matchToMap(frame, fmaxprojerr, fdistratio, local);
+    n = 0;
+    for (const auto& kv : res) { pairs_out[2 * n] = kv.first; pairs_out[2 * n + 1] = kv.second; ++n; }
+    return n;
 }

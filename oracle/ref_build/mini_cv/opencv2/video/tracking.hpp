@@ -24,4 +24,12 @@ inline void calcOpticalFlowPyrLK(const std::vector<Mat>& prev, const std::vector
                            crit.maxCount, crit.epsilon, flags, minEigThreshold);
 }
 
+// the pyramid vector as the reference keeps it: 2 * (maxLevel + 1) entries (image, derivative, ...); only entry 0 carries pixels here,
+// the tracker callback re-derives the levels from it
+inline int buildOpticalFlowPyramid(const Mat& img, std::vector<Mat>& pyr, Size, int maxLevel, bool = true, int = 4, int = 0, bool = true) {
+    pyr.assign(2 * (size_t)(maxLevel + 1), Mat());
+    pyr[0] = img;
+    return maxLevel;
+}
+
 }  // namespace cv

@@ -148,3 +148,31 @@ def test_reference_loose_and_full_ba_leave_the_map_of_the_flat_solve(lib, mode, 
     assert np.abs(pose - o["pose"]).max() <= 1e-8
     w = world_points(pb, o["pose"], o["lm_invdepth"])
     assert alive.mean() > 0.9 and np.abs(w[alive] - xyz[alive]).max() <= 1e-7
+
+
+@pytest.mark.parametrize("seed,nkps,ncand", [(5, 500, 260), (6, 1200, 700), (7, 300, 400)])
+def test_match_to_map_equals_the_reference_source(lib, seed, nkps, ncand):
+    """The REFERENCE'S OWN Mapper::matchToMap (src/mapper.cpp:576-774, with Frame / MapManager / MapPoint of the reference) on a map built
+    from a flattened matching scene (undistorted calibration): the pairs it returns are those of oracle/match_ref.py::match_to_map (which
+    the GPU operator is compared with) for the same candidate order.  Poses pass through unit quaternions on the reference's side, so a
+    projection may differ in the last bit: at most 1 % of the pairs may differ."""
+    from oracle import match_ref as M
+    sc = synth.make_match_scene(seed, nkps=nkps, ncand=ncand, nkfs=9, distorted=False)
+    nmps, nkfs = len(sc["mp_xyz"]), len(sc["kf_Tcw"])
+    a = {k: np.ascontiguousarray(sc[k], t) for k, t in (("K", np.float64), ("Tcw", np.float64), ("kf_Tcw", np.float64), ("mp_xyz", np.float64), ("kp_px", np.float32),
+                                                        ("kp_lm", np.int32), ("mp_desc_ptr", np.int32), ("desc", np.uint8), ("mp_obs_ptr", np.int32),
+                                                        ("obs_kf", np.int32), ("obs_px", np.float32), ("cand_mp", np.int32))}
+    order, pairs = np.zeros(ncand, np.int32), np.zeros((nkps, 2), np.int32)
+    F32 = C.POINTER(C.c_float)
+    lib.ov2ref_match_to_map.restype = C.c_int
+    n = lib.ov2ref_match_to_map(nkps, nmps, nkfs, ncand, a["K"].ctypes.data_as(D), sc["img_w"], sc["img_h"], sc["ncellsize"], a["Tcw"].ctypes.data_as(D),
+                                a["kf_Tcw"].ctypes.data_as(D), a["mp_xyz"].ctypes.data_as(D), a["kp_px"].ctypes.data_as(F32), a["kp_lm"].ctypes.data_as(I),
+                                a["mp_desc_ptr"].ctypes.data_as(I), a["desc"].ctypes.data_as(U), a["mp_obs_ptr"].ctypes.data_as(I), a["obs_kf"].ctypes.data_as(I),
+                                a["obs_px"].ctypes.data_as(F32), a["cand_mp"].ctypes.data_as(I), C.c_float(2.0), C.c_float(0.2), order.ctypes.data_as(I),
+                                pairs.ctypes.data_as(I))
+    got = {(int(p[0]), int(p[1])) for p in pairs[:n]}
+    ref = dict(sc, cand_mp=order)
+    kp_match = M.match_to_map(ref)[2]
+    want = {(int(sc["kp_lm"][j]), int(order[c])) for j, c in enumerate(kp_match) if c >= 0}
+    assert len(want) > 40
+    assert len(want ^ got) <= max(1, len(want) // 100)
