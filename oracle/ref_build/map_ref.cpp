@@ -163,3 +163,54 @@ extern "C" int ov2ref_match_to_map(int nkps, int nmps, int nkfs, int ncand, cons
     for (const auto& kv : res) { pairs_out[2 * n] = kv.first; pairs_out[2 * n + 1] = kv.second; ++n; }
     return n;
 }
+
+
+// The REFERENCE'S OWN MapManager::stereoMatching (/root/reference/src/map_manager.cpp:367-611, with its FeatureTracker: fbKltTracking and
+// getLineMinSAD of src/feature_tracker.cpp) on a synthetic stereo keyframe: keypoints (pixel, 3-D flag, map point or none), a rig, and
+// the two image pyramids (levels 0-3, built by the caller with the real library; entry 2 * level of the reference's pyramid vectors).
+// out: per keypoint, in Frame::getKeypoints() order: lmid, is_stereo, right pixel.
+extern "C" int ov2ref_stereo_matching(int nkps, int rect, const double* K, const double* Kr, const double* Tc0c1, const double* Twc, int width, int height,
+                                      int ncellsize, const int32_t* lmid, const int32_t* is3d, const int32_t* has_mp, const float* px, const double* wpt,
+                                      const uint8_t* const* left_levels, const uint8_t* const* right_levels, const int32_t* level_rows, const int32_t* level_cols,
+                                      int32_t* order_out, int32_t* is_stereo_out, float* rpx_out) {
+    auto params = std::make_shared<SlamParams>();
+    SlamParams& S = *params;
+    S.debug_ = false; S.log_timings_ = false; S.stereo_ = true; S.mono_ = false;
+    S.bdo_stereo_rect_ = rect != 0;
+    S.nklt_pyr_lvl_ = 3; S.nklt_win_size_ = 9; S.nklt_err_ = 30; S.fmax_fbklt_dist_ = 0.5f;
+    auto lcal = std::make_shared<CameraCalibration>("pinhole", K[0], K[1], K[2], K[3], 0., 0., 0., 0., (double)width, (double)height);
+    auto rcal = std::make_shared<CameraCalibration>("pinhole", Kr[0], Kr[1], Kr[2], Kr[3], 0., 0., 0., 0., (double)width, (double)height);
+    lcal->Dcv_.release();
+    rcal->Dcv_.release();
+    rcal->setupExtrinsic(Sophus::SE3d(Eigen::Quaterniond(Tc0c1[6], Tc0c1[3], Tc0c1[4], Tc0c1[5]), Eigen::Vector3d(Tc0c1[0], Tc0c1[1], Tc0c1[2])));
+    auto cur = std::make_shared<Frame>(lcal, rcal, (size_t)ncellsize);
+    auto ft = std::make_shared<FeatureTracker>(30, 0.01f, nullptr);
+    auto map = std::make_shared<MapManager>(params, cur, nullptr, ft);
+    Frame frame(lcal, rcal, (size_t)ncellsize);
+    frame.id_ = frame.kfid_ = 7;
+    frame.setTwc(Sophus::SE3d(Eigen::Quaterniond(Twc[6], Twc[3], Twc[4], Twc[5]), Eigen::Vector3d(Twc[0], Twc[1], Twc[2])));
+    for (int j = 0; j < nkps; ++j) {
+        frame.addKeypoint(cv::Point2f(px[2 * j], px[2 * j + 1]), lmid[j]);
+        if (has_mp[j]) {
+            auto lm = std::make_shared<MapPoint>(lmid[j], 7, true);
+            lm->setPoint(Eigen::Vector3d(wpt[3 * j], wpt[3 * j + 1], wpt[3 * j + 2]));
+            lm->is3d_ = true;
+            map->map_plms_.emplace(lmid[j], lm);
+        }
+        if (is3d[j]) frame.turnKeypoint3d(lmid[j]);
+    }
+    std::vector<cv::Mat> lpyr(8), rpyr(8);
+    for (int lv = 0; lv < 4; ++lv) {
+        lpyr[2 * lv] = cv::Mat(level_rows[lv], level_cols[lv], CV_8UC1, (void*)left_levels[lv]);
+        rpyr[2 * lv] = cv::Mat(level_rows[lv], level_cols[lv], CV_8UC1, (void*)right_levels[lv]);
+    }
+    int n = 0;
+    for (const auto& kp : frame.getKeypoints()) order_out[n++] = kp.lmid_;
+    map->stereoMatching(frame, lpyr, rpyr);
+    for (int i = 0; i < n; ++i) {
+        const Keypoint kp = frame.getKeypointById(order_out[i]);
+        is_stereo_out[i] = kp.lmid_ == order_out[i] && kp.is_stereo_ ? 1 : 0;
+        rpx_out[2 * i] = kp.rpx_.x; rpx_out[2 * i + 1] = kp.rpx_.y;
+    }
+    return n;
+}

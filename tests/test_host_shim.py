@@ -398,9 +398,18 @@ def _mock_klt(pts, pri, nlv):
     return out, st
 
 
-def _stereo_flow(sc, order):
-    """MapManager::stereoMatching (map_manager.cpp:367-611) restated over the scene, with the mock's tracker / row-search rules:
-    the expected device calls and the expected stereo keypoints."""
+def _mock_sad(sp):
+    """The canned row search of tests/helpers/frontend_mock.c (coarsest-level pixels in, best column out)."""
+    fx, fy = np.floor(sp[:, 0]).astype(int), np.floor(sp[:, 1]).astype(int)
+    return np.where((fx >= 3) & (fy % 4 != 0), (fx - 2).astype(np.float32), np.float32(-1))
+
+
+def _stereo_flow(sc, order, klt=None, sad=None):
+    """MapManager::stereoMatching (map_manager.cpp:367-611) restated over the scene: the expected tracker / row-search calls and the
+    expected stereo keypoints.  klt(pts, priors, nlevels) -> (moved priors, status) and sad(coarsest-level pts) -> columns default to the
+    mock's rules; tests/test_oracle_vs_reference_map.py passes the real library's functions to compare with the reference's own code."""
+    klt = klt or _mock_klt
+    sad = sad or _mock_sad
     f32 = np.float32
     K, idx = sc["K"], {int(l): i for i, l in enumerate(sc["lmid"])}
     Rcw, Rrl = sc["Rwc"].T, sc["Rrig"].T
@@ -457,8 +466,7 @@ def _stereo_flow(sc, order):
     if sad_pts:
         sp = np.asarray(sad_pts, np.float32)
         calls.append(("sad", 3, 7, 1, sp))
-        fx, fy = np.floor(sp[:, 0]).astype(int), np.floor(sp[:, 1]).astype(int)
-        xpr = np.where((fx >= 3) & (fy % 4 != 0), (fx - 2).astype(np.float32), f32(-1)) * f32(8.0)
+        xpr = np.asarray(sad(sp), np.float32) * f32(8.0)
         for k, slot in enumerate(sad_slot):
             if xpr[k] >= 0 and xpr[k] <= v2["pts"][slot][0]:
                 v2["pri"][slot][0] = xpr[k]
@@ -466,7 +474,7 @@ def _stereo_flow(sc, order):
     if v3["ids"]:
         pts, pri = np.asarray(v3["pts"], np.float32), np.asarray(v3["pri"], np.float32)
         calls.append(("klt", 1, 9, pts, pri))
-        out, st = _mock_klt(pts, pri, 1)
+        out, st = klt(pts, pri, 1)
         for k, lm in enumerate(v3["ids"]):
             if st[k]:
                 good.append((lm, out[k]))
@@ -475,7 +483,7 @@ def _stereo_flow(sc, order):
     if v2["ids"]:
         pts, pri = np.asarray(v2["pts"], np.float32), np.asarray(v2["pri"], np.float32)
         calls.append(("klt", 3, 9, pts, pri))
-        out, st = _mock_klt(pts, pri, 3)
+        out, st = klt(pts, pri, 3)
         good += [(lm, out[k]) for k, lm in enumerate(v2["ids"]) if st[k]]
     stereo = {}
     for lm, rp in good:
