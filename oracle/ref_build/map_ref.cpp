@@ -15,6 +15,11 @@
 #include "mapper.hpp"
 #include "loop_closer.hpp"
 
+#include <algorithm>
+
+extern "C" void* ov2ref_fe_create(int, int, double, int);
+extern "C" void ov2ref_fe_destroy(void*);
+
 extern "C" int ov2ref_run_local_ba(int ncam, int npts, int nobs, const double* K, int width, int height, const double* pose /* [ncam][7] Twc */,
                                    const int32_t* lm_anchor_cam, const double* lm_anchor_px, const double* lm_invdepth, const int32_t* obs_cam,
                                    const int32_t* obs_lm, const double* obs_px, int nmin_covscore, int mode /* 0 localBA, 1 looseBA, 2 fullBA */, double* pose_out, double* xyz_out /* [npts][3] world */,
@@ -213,4 +218,46 @@ extern "C" int ov2ref_stereo_matching(int nkps, int rect, const double* K, const
         rpx_out[2 * i] = kp.rpx_.x; rpx_out[2 * i + 1] = kp.rpx_.y;
     }
     return n;
+}
+
+
+// The REFERENCE'S OWN MapManager::extractKeypoints (/root/reference/src/map_manager.cpp:286-341: describe the tracked keypoints on the raw
+// image, detect new ones where the tracks left cells empty, describe those, add them to the frame and the map) - the caller of the
+// detector and the descriptor that one front-end step mirrors.  in: tracked keypoints (each gets a map point); detector: 0 FAST grid,
+// 1 single scale.  out: every keypoint of the frame afterwards: lmid, pixel, 32-byte descriptor (zero when none), has_desc.
+extern "C" int ov2ref_extract_keypoints(const uint8_t* im, const uint8_t* imraw, int rows, int cols, const double* K, int nmaxdist, int detector, int nfast_th,
+                                        double dmaxquality, const float* tracked, int ntracked, int cap, int32_t* lmid_out, float* px_out, uint8_t* desc_out,
+                                        uint8_t* has_desc_out, int* fast_th_out, double* quality_out) {
+    auto params = std::make_shared<SlamParams>();
+    SlamParams& S = *params;
+    S.debug_ = false; S.log_timings_ = false;
+    S.use_brief_ = true; S.use_shi_tomasi_ = false; S.use_fast_ = detector == 0; S.use_singlescale_detector_ = detector == 1;
+    S.nmaxdist_ = nmaxdist; S.nbmaxkps_ = 100000;
+    auto calib = std::make_shared<CameraCalibration>("pinhole", K[0], K[1], K[2], K[3], 0., 0., 0., 0., (double)cols, (double)rows);
+    calib->Dcv_.release();
+    auto cur = std::make_shared<Frame>(calib, (size_t)nmaxdist);
+    ov2ref_fe_destroy(ov2ref_fe_create(1000, nmaxdist, dmaxquality, nfast_th));       // resets the file-scope detector objects
+    auto fe = std::make_shared<FeatureExtractor>(1000, nmaxdist, dmaxquality, nfast_th);
+    auto map = std::make_shared<MapManager>(params, cur, fe, nullptr);
+    cur->updateFrame(1, 0.05);
+    for (int i = 0; i < ntracked; ++i) {
+        cur->addKeypoint(cv::Point2f(tracked[2 * i], tracked[2 * i + 1]), map->nlmid_);
+        map->addMapPoint();
+    }
+    cv::Mat mim(rows, cols, CV_8UC1, (void*)im), mraw(rows, cols, CV_8UC1, (void*)imraw);
+    map->extractKeypoints(mim, mraw);
+    *fast_th_out = fe->nfast_th_;
+    *quality_out = fe->dmaxquality_;
+    std::vector<Keypoint> kps = cur->getKeypoints();
+    std::sort(kps.begin(), kps.end(), [](const Keypoint& a, const Keypoint& b) { return a.lmid_ < b.lmid_; });
+    int n = 0;
+    for (const auto& kp : kps) {
+        if (n >= cap) break;
+        lmid_out[n] = kp.lmid_;
+        px_out[2 * n] = kp.px_.x; px_out[2 * n + 1] = kp.px_.y;
+        has_desc_out[n] = kp.desc_.empty() ? 0 : 1;
+        if (has_desc_out[n]) memcpy(desc_out + 32 * (size_t)n, kp.desc_.ptr(0), 32); else memset(desc_out + 32 * (size_t)n, 0, 32);
+        ++n;
+    }
+    return (int)kps.size();
 }

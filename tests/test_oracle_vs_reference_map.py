@@ -228,3 +228,38 @@ def test_stereo_matching_equals_the_reference_source(lib, rect):
     for l, p in zip(order, rpx):
         if int(l) in want:
             assert np.abs(p - want[int(l)]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("detector,w,h,cs", [(0, 640, 480, 50), (1, 752, 480, 35)])
+def test_extract_keypoints_equals_the_reference_source(lib, detector, w, h, cs):
+    """The REFERENCE'S OWN MapManager::extractKeypoints (src/map_manager.cpp:286-341) - the caller of the detector and the descriptor that
+    one front-end step mirrors (ov2_frontend_step / oracle frontend composite): tracked keypoints are described on the raw image, new ones
+    are detected in the cells the tracks left empty (roi = the calibration's 5 px border), described and added with new map-point ids.
+    Keypoints, ids, descriptors and the adapted detector state equal the oracle's composition of its numpy restatements."""
+    from oracle import image_ref as R
+    im = synth.make_pair(100 + detector, w, h)[0]
+    rng = np.random.default_rng(4)
+    first = R.detect_grid_fast_nosubpix(im, cs, np.zeros((0, 2)), 10, use_cv2=False)[0].astype(np.float32)
+    tracked = np.ascontiguousarray(first[::4] + rng.uniform(-0.4, 0.4, first[::4].shape).astype(np.float32))
+    cap = 4096
+    lmid, px, desc, has = np.zeros(cap, np.int32), np.zeros((cap, 2), np.float32), np.zeros((cap, 32), np.uint8), np.zeros(cap, np.uint8)
+    th, q = C.c_int(), C.c_double()
+    K = np.array([458.654, 457.296, 367.215, 248.375])
+    lib.ov2ref_extract_keypoints.restype = C.c_int
+    n = lib.ov2ref_extract_keypoints(im.ctypes.data_as(U), im.ctypes.data_as(U), h, w, K.ctypes.data_as(D), cs, detector, 10, C.c_double(0.001),
+                                     tracked.ctypes.data_as(C.POINTER(C.c_float)), len(tracked), cap, lmid.ctypes.data_as(I), px.ctypes.data_as(C.POINTER(C.c_float)),
+                                     desc.ctypes.data_as(U), has.ctypes.data_as(U), C.byref(th), C.byref(q))
+    assert len(tracked) < n <= cap
+    roi = (5, 5, w - 10, h - 10)                                  # CameraCalibration's roi_rect_ (camera_calibration.cpp:72-73)
+    if detector == 0:
+        ipts, want_th, _ = R.detect_grid_fast_nosubpix(im, cs, tracked, 10, use_cv2=False)
+        assert th.value == want_th
+    else:
+        ipts, want_q, _ = R.detect_single_scale_nosubpix(im, cs, tracked, roi, 0.001, use_cv2=False)
+        assert q.value == want_q
+    new = R.corner_subpix_cv2(im, ipts.astype(np.float32)) if len(ipts) else np.zeros((0, 2), np.float32)
+    want_px = np.concatenate([tracked, new])
+    assert n == len(want_px) and np.array_equal(lmid[:n], np.arange(n))        # tracked keep ids 0 .., new keypoints get the next ids in order
+    assert np.array_equal(px[:n], want_px)
+    wd, wv = R.describe_ref(im, want_px)
+    assert np.array_equal(has[:n], wv) and np.array_equal(desc[:n][wv > 0], wd[wv > 0])
