@@ -27,7 +27,7 @@ REF = Path("/root/reference")
 CERES = REF / "Thirdparty" / "ceres-solver"
 SKIP = ("_test", "test_util", "gmock", "benchmark", "evaluator_test_utils", "generate_", "dogleg_strategy", "polynomial",
         "line_search_direction", "covariance")
-INC = ["-I", str(HERE / "ceres_api"), "-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"), "-I", str(CERES / "internal"),
+INC = ["-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"), "-I", str(CERES / "internal"),
        "-I", str(CERES / "internal" / "ceres" / "miniglog"), "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization")]
 FLAGS = ["-std=c++17", "-O2", "-fPIC", "-w", "-DNDEBUG", "-DMAX_LOG_LEVEL=-1"]     # miniglog: warnings and errors only
 
@@ -49,8 +49,7 @@ def build(force: bool = False, verbose: bool = False):
     if not CERES.exists():
         return OUT if OUT.exists() else None
     src = sources()
-    deps = src + [p for p in (HERE / "mini").rglob("*") if p.is_file()] + [p for p in (HERE / "ceres_cfg").rglob("*") if p.is_file()] + \
-        [HERE / "ceres_api" / "ceres" / "ceres.h"]
+    deps = src + [p for p in (HERE / "mini").rglob("*") if p.is_file()] + [p for p in (HERE / "ceres_cfg").rglob("*") if p.is_file()]
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return OUT
     objdir = OUTDIR / "ceres_obj"

@@ -20,7 +20,7 @@ REF = Path("/root/reference")
 CERES = REF / "Thirdparty" / "ceres-solver"
 REF_SOURCES = ["optimizer", "frame", "map_point", "map_manager", "camera_calibration", "multi_view_geometry", "feature_extractor", "feature_tracker", "mapper",
                "estimator"]
-INC = ["-I", str(HERE / "mini_pcl"), "-I", str(HERE / "ceres_api"), "-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"),
+INC = ["-I", str(HERE / "mini_pcl"), "-I", str(HERE / "ceres_cfg"), "-I", str(CERES / "include"),
        "-I", str(CERES / "internal" / "ceres" / "miniglog"), "-I", str(HERE / "mini_cv"), "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"),
        "-I", str(REF / "include"), "-I", str(REF / "include" / "ceres_parametrization")]
 
@@ -35,7 +35,7 @@ def build(force: bool = False):
     if build_ceres_ref.build() is None:
         return None
     src = [REF / "src" / (n + ".cpp") for n in REF_SOURCES] + [HERE / "map_ref.cpp", HERE / "fe_ref.cpp"]
-    hdrs = [p for d in ("mini", "mini_cv", "mini_pcl", "ceres_cfg", "ceres_api") for p in (HERE / d).rglob("*") if p.is_file()]
+    hdrs = [p for d in ("mini", "mini_cv", "mini_pcl", "ceres_cfg") for p in (HERE / d).rglob("*") if p.is_file()]
     ceres_objs = [o for o in sorted((OUTDIR / "ceres_obj").glob("*.o")) if "ceres_ba_ref" not in o.name]
     deps = src + hdrs + ceres_objs
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):

@@ -1,7 +1,7 @@
 """Recipe for oracle/_ref/libov2ref_residuals.so: the reference's OWN residual source (src/ceres_parametrization.cpp with its
 headers, compiled where it lies under /root/reference - nothing is copied) + oracle/ref_build/residual_ref.cpp (C entry points),
-with the real Sophus 1.1 headers of the reference tree (Thirdparty/Sophus), against the stand-in Eigen header and the declarations-only
-Ceres interface of oracle/ref_build/mini (this container has no Eigen).
+with the real Sophus 1.1 and Ceres 2.0 public headers of the reference tree (Thirdparty/Sophus, Thirdparty/ceres-solver/include), against the
+stand-in Eigen header of oracle/ref_build/mini (this container has no Eigen).
 
 TEST INFRASTRUCTURE: only tests/, __graft_entry__ (build + smoke) and bench.py's CPU legs may use what this builds.
 /root/reference does not exist on the GPU box: the library is built here and travels with the snapshot (oracle/_ref/ is
@@ -30,6 +30,8 @@ def build(force: bool = False) -> Path | None:
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable",
+                           "-I", str(HERE / "ceres_cfg"), "-I", str(REF / "Thirdparty" / "ceres-solver" / "include"),
+                           "-I", str(REF / "Thirdparty" / "ceres-solver" / "internal" / "ceres" / "miniglog"),
                            "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization"),
                            str(SRC), str(HERE / "residual_ref.cpp"), "-o", str(OUT)])
     return OUT

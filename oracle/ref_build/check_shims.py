@@ -50,7 +50,7 @@ def make_overlay() -> Path:
 
 def include_flags() -> list[str]:
     ceres = REF / "Thirdparty" / "ceres-solver"
-    dirs = [make_overlay(), HERE / "mini_pcl", HERE / "ceres_api", HERE / "ceres_cfg", ceres / "include", ceres / "internal" / "ceres" / "miniglog",
+    dirs = [make_overlay(), HERE / "mini_pcl", HERE / "ceres_cfg", ceres / "include", ceres / "internal" / "ceres" / "miniglog",
             HERE / "mini_cv", REF / "Thirdparty" / "Sophus", HERE / "mini", REF / "include" / "ceres_parametrization"]
     out = []
     for d in dirs:

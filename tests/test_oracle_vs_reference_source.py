@@ -1,6 +1,6 @@
 """The restatements (oracle/ba_ref.py, oracle/pnp_ref.py) against the REFERENCE'S OWN residual source: oracle/_ref/libov2ref_residuals.so
 is /root/reference/src/ceres_parametrization.cpp compiled where it lies (recipe oracle/ref_build/build_ref.py) with the reference tree's own
-Sophus 1.1 headers, against a stand-in Eigen header and a declarations-only Ceres interface (oracle/ref_build/mini: this container has no Eigen).  Pins rows R and Q of the scope table
+Sophus 1.1 and Ceres 2.0 public headers, against a stand-in Eigen header (oracle/ref_build/mini: this container has no Eigen).  Pins rows R and Q of the scope table
 (residuals, chi2 / depth flags, every Jacobian block, SE3LeftParameterization::Plus) and the ceresPnP residual to what the
 reference's code computes."""
 import ctypes as C
