@@ -15,6 +15,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 OUT = HERE.parent / "_ref" / "libov2ref_residuals.so"
 REF = Path("/root/reference")
+CERES = REF / "Thirdparty" / "ceres-solver"
 SRC = REF / "src" / "ceres_parametrization.cpp"
 
 
@@ -33,7 +34,11 @@ def build(force: bool = False) -> Path | None:
                            "-I", str(HERE / "ceres_cfg"), "-I", str(REF / "Thirdparty" / "ceres-solver" / "include"),
                            "-I", str(REF / "Thirdparty" / "ceres-solver" / "internal" / "ceres" / "miniglog"),
                            "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization"),
-                           str(SRC), str(HERE / "residual_ref.cpp"), "-o", str(OUT)])
+                           str(SRC), str(HERE / "residual_ref.cpp"),
+                           # the two Ceres base classes the cost functions derive from have out-of-line members
+                           str(CERES / "internal" / "ceres" / "local_parameterization.cc"),
+                           str(CERES / "internal" / "ceres" / "miniglog" / "glog" / "logging.cc"), "-I", str(CERES / "internal"),
+                           "-Wl,--no-undefined", "-o", str(OUT)])
     return OUT
 
 
