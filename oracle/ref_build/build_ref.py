@@ -30,7 +30,7 @@ def build(force: bool = False) -> Path | None:
     if not force and OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable",
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w",
                            "-I", str(HERE / "ceres_cfg"), "-I", str(REF / "Thirdparty" / "ceres-solver" / "include"),
                            "-I", str(REF / "Thirdparty" / "ceres-solver" / "internal" / "ceres" / "miniglog"),
                            "-I", str(REF / "Thirdparty" / "Sophus"), "-I", str(HERE / "mini"), "-I", str(REF / "include" / "ceres_parametrization"),
