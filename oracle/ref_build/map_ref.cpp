@@ -261,3 +261,27 @@ extern "C" int ov2ref_extract_keypoints(const uint8_t* im, const uint8_t* imraw,
     }
     return (int)kps.size();
 }
+
+
+// The REFERENCE'S OWN MultiViewGeometry::ceresPnP (/root/reference/src/multi_view_geometry.cpp:492-588), called as
+// VisualFrontEnd::computePose does (src/visual_front_end.cpp:791-801).  It caps the solve at 5 ms of wall clock: callers keep the
+// problem small enough for that not to bind on this build.  Returns its verdict; outliers_out gets the rejected indices.
+extern "C" int ov2ref_real_ceres_pnp(int n, const double* unpx, const double* wpts, const int32_t* scales, double* Twc, int nmaxiter, float chi2th, int use_robust,
+                                     int apply_l2, const float* K, int32_t* outliers_out, int* noutliers) {
+    std::vector<Eigen::Vector2d, Eigen::aligned_allocator<Eigen::Vector2d>> vunkps;
+    std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d>> vwpts;
+    std::vector<int> vscales, vout;
+    for (int i = 0; i < n; ++i) {
+        vunkps.push_back(Eigen::Vector2d(unpx[2 * i], unpx[2 * i + 1]));
+        vwpts.push_back(Eigen::Vector3d(wpts[3 * i], wpts[3 * i + 1], wpts[3 * i + 2]));
+        vscales.push_back(scales ? scales[i] : 0);
+    }
+    Sophus::SE3d T(Eigen::Quaterniond(Twc[6], Twc[3], Twc[4], Twc[5]), Eigen::Vector3d(Twc[0], Twc[1], Twc[2]));
+    const bool ok = MultiViewGeometry::ceresPnP(vunkps, vwpts, vscales, T, nmaxiter, chi2th, use_robust != 0, apply_l2 != 0, K[0], K[1], K[2], K[3], vout);
+    const Eigen::Vector3d t = T.translation();
+    const Eigen::Quaterniond q = T.unit_quaternion();
+    Twc[0] = t.x(); Twc[1] = t.y(); Twc[2] = t.z(); Twc[3] = q.x(); Twc[4] = q.y(); Twc[5] = q.z(); Twc[6] = q.w();
+    *noutliers = (int)vout.size();
+    for (size_t i = 0; i < vout.size(); ++i) outliers_out[i] = vout[i];
+    return ok ? 1 : 0;
+}

@@ -263,3 +263,33 @@ def test_extract_keypoints_equals_the_reference_source(lib, detector, w, h, cs):
     assert np.array_equal(px[:n], want_px)
     wd, wv = R.describe_ref(im, want_px)
     assert np.array_equal(has[:n], wv) and np.array_equal(desc[:n][wv > 0], wd[wv > 0])
+
+
+def test_ceres_pnp_equals_the_reference_function(lib):
+    """The REFERENCE'S OWN MultiViewGeometry::ceresPnP (src/multi_view_geometry.cpp:492-588) - the function the drop-in
+    host/multi_view_geometry_pnp_gpu.cpp replaces - on small problems (its 5 ms wall-clock cap must not bind on this build): verdict,
+    rejected blocks and pose of oracle/pnp_ref.py::ceres_pnp."""
+    from oracle import pnp_ref as P
+    K32 = np.array([458.654, 457.296, 367.215, 248.375], np.float32)
+    K = K32.astype(np.float64)
+    rng = np.random.default_rng(12)
+    lib.ov2ref_real_ceres_pnp.restype = C.c_int
+    for case in range(6):
+        n = 40 + 10 * case
+        q = B.quat_normalize(np.array([0.0, 0.0, 0.0, 1.0]) + rng.normal(0, 0.1, 4))
+        Ttrue = np.concatenate([rng.normal(0, 0.5, 3), q])
+        pc = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2, 10, n)], 1)
+        w = np.ascontiguousarray(pc @ B.quat_to_rot(q).T + Ttrue[:3])
+        px = np.stack([K[0] * pc[:, 0] / pc[:, 2] + K[2], K[1] * pc[:, 1] / pc[:, 2] + K[3]], 1) + rng.normal(0, 0.5, (n, 2))
+        nbad = n // 8 if case % 2 else 0
+        px[:nbad] += rng.uniform(15, 50, (nbad, 2))
+        px = np.ascontiguousarray(px)
+        scales = rng.integers(0, 3, n).astype(np.int32)
+        T0 = B.pose_plus(Ttrue, np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.015, 3)]))
+        T = T0.copy()
+        out, nout = np.zeros(n, np.int32), C.c_int()
+        rc = lib.ov2ref_real_ceres_pnp(n, px.ctypes.data_as(D), w.ctypes.data_as(D), scales.ctypes.data_as(I), T.ctypes.data_as(D), 5, C.c_float(5.9915), 1, 1,
+                                       K32.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(I), C.byref(nout))
+        ok, pose, outliers = P.ceres_pnp(px, w, T0.copy(), K, nmaxiter=5, chi2th=5.9915, use_robust=True, apply_l2_after_robust=True, scales=scales)
+        assert bool(rc) == ok and np.array_equal(out[:nout.value], outliers)
+        assert np.abs(T - pose).max() <= 1e-9
