@@ -286,10 +286,13 @@ def test_ceres_pnp_equals_the_reference_function(lib):
         px = np.ascontiguousarray(px)
         scales = rng.integers(0, 3, n).astype(np.int32)
         T0 = B.pose_plus(Ttrue, np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.015, 3)]))
-        T = T0.copy()
-        out, nout = np.zeros(n, np.int32), C.c_int()
-        rc = lib.ov2ref_real_ceres_pnp(n, px.ctypes.data_as(D), w.ctypes.data_as(D), scales.ctypes.data_as(I), T.ctypes.data_as(D), 5, C.c_float(5.9915), 1, 1,
-                                       K32.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(I), C.byref(nout))
         ok, pose, outliers = P.ceres_pnp(px, w, T0.copy(), K, nmaxiter=5, chi2th=5.9915, use_robust=True, apply_l2_after_robust=True, scales=scales)
-        assert bool(rc) == ok and np.array_equal(out[:nout.value], outliers)
-        assert np.abs(T - pose).max() <= 1e-9
+        for attempt in range(4):            # the reference's cap is on wall-clock time: a solve cut short on a busy machine is retried
+            T = T0.copy()
+            out, nout = np.zeros(n, np.int32), C.c_int()
+            rc = lib.ov2ref_real_ceres_pnp(n, px.ctypes.data_as(D), w.ctypes.data_as(D), scales.ctypes.data_as(I), T.ctypes.data_as(D), 5, C.c_float(5.9915), 1, 1,
+                                           K32.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(I), C.byref(nout))
+            if bool(rc) == ok and np.array_equal(out[:nout.value], outliers) and np.abs(T - pose).max() <= 1e-9:
+                break
+        else:
+            raise AssertionError((case, rc, ok, np.abs(T - pose).max()))
