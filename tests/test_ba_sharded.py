@@ -47,6 +47,8 @@ def _gloo_worker(rank, world, port, q):
 
 def test_allreduce_callback_sums_over_gloo_group():
     import multiprocessing as mp
+    from ov2slam_b200 import build
+    build.build()                                           # before the workers start: on a fresh checkout both would compile it at once
     ctxmp = mp.get_context("spawn")
     q = ctxmp.Queue()
     port = 29500 + os.getpid() % 2000
