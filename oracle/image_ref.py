@@ -60,7 +60,10 @@ def build_helpers(force: bool = False) -> Path:
     so = _BUILD / "libov2oracle_sort.so"
     src = _HERE / "stdsort_helper.cpp"
     if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), str(src)])
+        # compiled under a private name and renamed: several processes may get here at once on a fresh checkout (the CPU arm's workers)
+        tmp = so.with_name(f"{so.name}.{os.getpid()}.tmp")
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(tmp), str(src)])
+        os.replace(tmp, so)
     return so
 
 
